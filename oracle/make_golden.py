@@ -1,0 +1,185 @@
+"""
+TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference/gru4rec.py, evaluation.py, gpu_ops.py, datatools.py) on top of oracle/theano_shim.
+
+Run here (the GPU box has no /root/reference):   python oracle/make_golden.py
+Each fixture holds, for one small configuration: the synthetic data, the reference's initial and final
+weights, every train_function call (X, Y, M, R, cost), the sample store contents, dropout masks, the
+epoch losses the reference printed, and evaluate_gpu's Recall/MRR.  tests/test_oracle_golden.py
+replays them through oracle/gru4rec_oracle.py; tests/test_gpu_golden.py through the CUDA path.
+"""
+import io
+import os
+import sys
+import re
+import contextlib
+import numpy as np
+import pandas as pd
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+REF = '/root/reference'
+
+import theano_shim
+theano_shim.install()
+sys.path.insert(0, REF)
+cwd = os.getcwd()
+import gru4rec as ref_gru4rec          # the reference module (it chdir()s during import and back)
+import evaluation as ref_evaluation
+os.chdir(cwd)
+from gru4rec_b200.synth import make_sessions, train_test_split
+
+CONFIGS = {
+    # name: (data kwargs, model kwargs, fit kwargs)
+    'bprmax_none': (dict(n_items=60, n_events=700, seed=1),
+                    dict(loss='bpr-max', final_act='elu-0.5', hidden_act='tanh', layers=[12], batch_size=6, n_epochs=2,
+                         learning_rate=0.2, momentum=0.3, n_sample=16, sample_alpha=0.0, bpreg=1.0),
+                    dict(sample_store=16 * 40)),
+    'xe_shared_logq': (dict(n_items=80, n_events=800, seed=2),
+                       dict(loss='cross-entropy', final_act='softmax', layers=[12], batch_size=5, n_epochs=2,
+                            constrained_embedding=True, learning_rate=0.2, momentum=0.2, n_sample=24, sample_alpha=0.5,
+                            bpreg=0.0, logq=1.0, dropout_p_hidden=0.4),
+                       dict(sample_store=24 * 50)),
+    'xe_embed_2layer': (dict(n_items=70, n_events=700, seed=3),
+                        dict(loss='cross-entropy', final_act='softmax', layers=[8, 12], batch_size=4, n_epochs=2,
+                             embedding=8, learning_rate=0.1, momentum=0.0, n_sample=12, sample_alpha=0.75,
+                             dropout_p_embed=0.3, dropout_p_hidden=0.2, lmbd=0.001),
+                        dict(sample_store=12 * 30)),
+    'top1max_none_2layer': (dict(n_items=50, n_events=600, seed=4),
+                            dict(loss='top1-max', final_act='tanh', hidden_act='tanh', layers=[8, 8], batch_size=5, n_epochs=1,
+                                 learning_rate=0.1, momentum=0.1, n_sample=10, sample_alpha=1.0),
+                            dict(sample_store=10 * 25)),
+    'bprmax_shared_nosample': (dict(n_items=40, n_events=500, seed=5),
+                               dict(loss='bpr-max', final_act='elu-1', layers=[10], batch_size=6, n_epochs=1,
+                                    constrained_embedding=True, learning_rate=0.05, momentum=0.4, n_sample=0, bpreg=1.95),
+                               dict(sample_store=0)),
+    'xe_none_default': (dict(n_items=100, n_events=900, seed=6),        # BASELINE configs[0] shape, shrunk
+                        dict(loss='cross-entropy', final_act='softmax', layers=[16], batch_size=8, n_epochs=1, n_sample=32),
+                        dict(sample_store=32 * 20)),
+}
+
+
+def weights_of(gru):
+    w = {}
+    for i in range(len(gru.layers)):
+        w['Wx%d' % i] = gru.Wx[i].get_value()
+        w['Wh%d' % i] = gru.Wh[i].get_value()
+        w['Wrz%d' % i] = gru.Wrz[i].get_value()
+        w['Bh%d' % i] = gru.Bh[i].get_value()
+    w['Wy'] = gru.Wy.get_value()
+    w['By'] = gru.By.get_value()
+    if getattr(gru, 'embedding', 0) and not gru.constrained_embedding:
+        w['E'] = gru.E.get_value()
+    return w
+
+
+def run_one(name, dkw, mkw, fkw):
+    df = make_sessions(**dkw)
+    train, test = train_test_split(df, 0.25)
+    train_in = train.copy()
+    gru = ref_gru4rec.GRU4Rec(**mkw)
+    theano_shim.LOG_CALLS = True
+    del theano_shim.FUNCTION_LOG[:]
+    del theano_shim.RANDOM_LOG[:]
+    theano_shim.RandomStreams._rid = 0
+    ref_gru4rec.mrng = theano_shim.RandomStreams(12345)
+    # capture initial weights: init() is called inside fit(); wrap it
+    orig_init = gru.init
+    init_w = {}
+
+    def init_and_capture(data):
+        r = orig_init(data)
+        init_w.update(weights_of(gru))
+        return r
+    gru.init = init_and_capture
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        gru.fit(train, **fkw)
+    log = buf.getvalue()
+    assert not gru.error_during_train, log
+    epoch_loss = [float(x) for x in re.findall(r'loss: ([0-9.]+)', log)]
+    calls = list(theano_shim.FUNCTION_LOG)
+    rnd = list(theano_shim.RANDOM_LOG)
+    theano_shim.LOG_CALLS = False
+    out = dict(config_name=name)
+    out['train_SessionId'] = train_in['SessionId'].values
+    out['train_ItemId'] = train_in['ItemId'].values
+    out['train_Time'] = train_in['Time'].values
+    out['test_SessionId'] = test['SessionId'].values
+    out['test_ItemId'] = test['ItemId'].values
+    out['test_Time'] = test['Time'].values
+    out['itemidmap_index'] = gru.itemidmap.index.values
+    out['n_items'] = gru.n_items
+    for k, v in init_w.items():
+        out['init_' + k] = v
+    for k, v in weights_of(gru).items():
+        out['final_' + k] = v
+    for i in range(len(gru.layers)):
+        out['final_H%d' % i] = gru.H[i].get_value()
+    # train calls: 4 inputs.  generate_samples calls: 0 inputs (ST, STI in `upd`)
+    B = mkw['batch_size']
+    tr = [c for c in calls if len(c[1]) == 4]
+    gen = [(pos, c) for pos, c in enumerate(calls) if len(c[1]) == 0]
+    n = len(tr)
+    X = np.full((n, B), -1, dtype=np.int64); Y = np.full((n, B), -1, dtype=np.int64)
+    R = np.zeros((n, B), dtype=np.int8); M = np.zeros(n, dtype=np.int64); cost = np.zeros(n, dtype=np.float32)
+    for s, c in enumerate(tr):
+        m = int(c[1][2])
+        M[s] = m
+        X[s, :m] = c[1][0]; Y[s, :m] = c[1][1][:m]; R[s, :m] = np.asarray(c[1][3]).reshape(-1)
+        cost[s] = c[2][0]
+    out.update(step_X=X, step_Y=Y, step_R=R, step_M=M, step_cost=cost)
+    # sample stores, and the index of the first train step served by each store
+    stores = []
+    first_step = []
+    for pos, c in gen:
+        st = [u for u in c[3] if u.ndim == 2][0]
+        stores.append(st)
+        first_step.append(sum(1 for cc in calls[:pos] if len(cc[1]) == 4))
+    if stores:
+        out['sample_stores'] = np.stack(stores)
+        out['store_first_step'] = np.array(first_step, dtype=np.int64)
+        out['sample_uniforms'] = np.stack([r[2] for r in rnd if r[1] == 'uniform'])
+    out['sampling_P_float32'] = np.zeros(0, dtype=np.float32)
+    # dropout masks in call order (rid identifies which dropout site: creation order embed -> hidden layers)
+    bins = [r for r in rnd if r[1] == 'binomial']
+    rids = sorted(set(r[0] for r in bins))
+    for j, rid in enumerate(rids):
+        ms = [r[2] for r in bins if r[0] == rid]
+        assert len(ms) == n, (len(ms), n)
+        width = ms[0].shape[1]
+        arr = np.zeros((n, B, width), dtype=np.float32)
+        for s, mk in enumerate(ms):
+            arr[s, :mk.shape[0]] = mk
+        out['dropmask_site%d' % j] = arr
+    out['epoch_loss'] = np.array(epoch_loss, dtype=np.float64)
+    # evaluation through the reference's evaluate_gpu (batch_size chosen small to exercise lane replacement)
+    for mode in ('standard', 'conservative'):
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            rec, mrr = ref_evaluation.evaluate_gpu(gru, test.copy(), cut_off=[1, 5, 20], batch_size=7, mode=mode)
+        out['eval_%s_recall' % mode] = np.array([float(r) for r in rec])
+        out['eval_%s_mrr' % mode] = np.array([float(r) for r in mrr])
+    # predict_next_batch on a fixed probe (reference serving path, gru4rec.py:665-728)
+    probe_items = gru.itemidmap.index.values[:5]
+    sess = np.arange(5)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        p1 = gru.predict_next_batch(sess, probe_items, None, batch=5)
+        p2 = gru.predict_next_batch(sess, probe_items[::-1].copy(), None, batch=5)
+    out['predict_probe_items'] = probe_items
+    out['predict_out1'] = p1.values
+    out['predict_out2'] = p2.values
+    out['model_kwargs'] = np.array(repr(mkw))
+    out['fit_kwargs'] = np.array(repr(fkw))
+    path = os.path.join(ROOT, 'tests', 'golden', name + '.npz')
+    np.savez_compressed(path, **out)
+    print('%-28s steps=%d epoch_loss=%s R@20=%.4f -> %s (%d KB)' % (name, n, epoch_loss, out['eval_standard_recall'][2], path, os.path.getsize(path) // 1024))
+
+
+if __name__ == '__main__':
+    sel = sys.argv[1:] or list(CONFIGS)
+    for name in sel:
+        run_one(name, *CONFIGS[name])

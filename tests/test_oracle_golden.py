@@ -1,0 +1,120 @@
+"""The NumPy oracle replayed against fixtures produced by the reference's own code (oracle/make_golden.py)."""
+import numpy as np
+import pytest
+import gru4rec_oracle as orc
+from golden_utils import golden_names, load_golden, frames, init_weights, step_masks, step_samples
+
+NAMES = golden_names()
+
+
+def _model(g):
+    return orc.OracleGRU4Rec(**g['model_kwargs'])
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_init_matches_reference(name):
+    g = load_golden(name)
+    m = _model(g)
+    m.init(int(g['n_items']))
+    w = init_weights(g)
+    for i in range(len(m.layers)):
+        np.testing.assert_array_equal(m.Wx[i], w['Wx'][i])
+        np.testing.assert_array_equal(m.Wh[i], w['Wh'][i])
+        np.testing.assert_array_equal(m.Wrz[i], w['Wrz'][i])
+    np.testing.assert_array_equal(m.Wy, w['Wy'])
+    if 'E' in w:
+        np.testing.assert_array_equal(m.E, w['E'])
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_schedule_matches_reference(name):
+    g = load_golden(name)
+    tr, _ = frames(g)
+    mk = g['model_kwargs']
+    d = orc.prepare_fit_data(tr)
+    assert list(d['itemids']) == list(g['itemidmap_index'])
+    n_sample = mk['n_sample'] if g['fit_kwargs'].get('sample_store', 1) else mk['n_sample']
+    steps = orc.build_train_schedule(d['data_items'], d['offset_sessions'], d['base_order'], mk['batch_size'], mk['n_sample'])
+    n_ep = mk['n_epochs']
+    assert len(steps) * n_ep == len(g['step_M'])
+    for e in range(n_ep):
+        for s, st in enumerate(steps):
+            k = e * len(steps) + s
+            M = st['M']
+            assert M == g['step_M'][k]
+            np.testing.assert_array_equal(st['X'], g['step_X'][k, :M])
+            np.testing.assert_array_equal(st['Y'], g['step_Y'][k, :M])
+            np.testing.assert_array_equal(st['R'].astype(np.int8), g['step_R'][k, :M])
+
+
+@pytest.mark.parametrize('name', [n for n in NAMES if 'nosample' not in n])
+def test_sample_store_matches_reference(name):
+    """sampling CDF (gru4rec.py:543-545,556) + K2 (custom_theano_ops.py:318-349) on the recorded uniforms."""
+    g = load_golden(name)
+    tr, _ = frames(g)
+    mk = g['model_kwargs']
+    d = orc.prepare_fit_data(tr)
+    P = orc.sampling_cdf(d['supports'], mk.get('sample_alpha', 0.75)).astype(np.float32)
+    for k in range(len(g['sample_stores'])):
+        st = orc.searchsorted_k2(P, g['sample_uniforms'][k]).reshape(g['sample_stores'][k].shape)
+        np.testing.assert_array_equal(st, g['sample_stores'][k])
+        st2 = orc.searchsorted_k2_loop(P, g['sample_uniforms'][k][:500])
+        np.testing.assert_array_equal(st2, g['sample_stores'][k].reshape(-1)[:500])
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_training_trajectory_matches_reference(name):
+    g = load_golden(name)
+    tr, _ = frames(g)
+    mk = g['model_kwargs']
+    d = orc.prepare_fit_data(tr)
+    m = _model(g)
+    m.init(int(g['n_items']))
+    if mk.get('logq', 0):
+        m.P0 = d['supports'].astype(np.float32)
+    steps = orc.build_train_schedule(d['data_items'], d['offset_sessions'], d['base_order'], mk['batch_size'], mk['n_sample'])
+    costs = []
+    k = 0
+    for e in range(mk['n_epochs']):
+        for h in m.H:
+            h[:] = 0
+        for st in steps:
+            c = m.train_step(st['X'], st['Y'], st['R'], samples=step_samples(g, k), masks=step_masks(g, k, st['M']), slots=st['slots'])
+            costs.append(c)
+            k += 1
+    costs = np.array(costs)
+    np.testing.assert_allclose(costs, g['step_cost'], rtol=2e-4, atol=1e-6)
+    fw = init_weights(g, 'final_')
+    for i in range(len(m.layers)):
+        np.testing.assert_allclose(m.Wx[i], fw['Wx'][i], rtol=5e-3, atol=1e-4)
+        np.testing.assert_allclose(m.Wh[i], fw['Wh'][i], rtol=5e-3, atol=1e-4)
+        np.testing.assert_allclose(m.Wrz[i], fw['Wrz'][i], rtol=5e-3, atol=1e-4)
+        np.testing.assert_allclose(m.Bh[i], fw['Bh'][i], rtol=5e-3, atol=1e-4)
+    np.testing.assert_allclose(m.Wy, fw['Wy'], rtol=5e-3, atol=1e-4)
+    np.testing.assert_allclose(m.By, fw['By'], rtol=5e-3, atol=1e-4)
+    if 'E' in fw:
+        np.testing.assert_allclose(m.E, fw['E'], rtol=5e-3, atol=1e-4)
+    # epoch loss as printed by the reference (gru4rec.py:654,661)
+    cc = g['step_M'].astype(np.float64)
+    n_ep = mk['n_epochs']
+    per = len(steps)
+    for e in range(n_ep):
+        sl = slice(e * per, (e + 1) * per)
+        avgc = np.sum(costs[sl] * cc[sl]) / np.sum(cc[sl])
+        assert abs(avgc - g['epoch_loss'][e]) < 2e-4 * max(1, abs(avgc))
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_evaluation_matches_reference(name):
+    g = load_golden(name)
+    tr, te = frames(g)
+    mk = g['model_kwargs']
+    d = orc.prepare_fit_data(tr)
+    m = _model(g)
+    m.set_weights(**init_weights(g, 'final_'))
+    m.batch_size = mk['batch_size']
+    items, off = orc.prepare_eval_data(te, d['itemidmap'])
+    for mode in ('standard', 'conservative'):
+        rec, mrr = m.evaluate(items, off, batch_size=7, cut_off=(1, 5, 20), mode=mode)
+        np.testing.assert_allclose(rec, g['eval_%s_recall' % mode], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(mrr, g['eval_%s_mrr' % mode], rtol=1e-6, atol=1e-9)

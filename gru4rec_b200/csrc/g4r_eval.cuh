@@ -1,0 +1,311 @@
+// g4r_eval.cuh -- scoring path: evaluate_gpu's compiled function (evaluation.py:57-76) and predict
+// (gru4rec.py:699-710).  Full-catalogue scores are never materialised for evaluation: each CTA scores a tile of
+// consecutive items against all lanes and counts how many beat / tie the lane's target score.
+// Included at the end of g4r_lib.cu (uses its handle type and helper macros).
+#pragma once
+
+constexpr int EV_IT = 64;     // items per CTA tile
+constexpr int EV_TB = 32;     // lanes per row tile
+constexpr int EV_KT = 128;    // feature slab
+constexpr int EV_LDS = EV_KT + 4;
+constexpr int EV_THREADS = 256;
+
+// target score of every lane, computed with the same sequential k order as the tile kernel (bitwise equal)
+__global__ void __launch_bounds__(128) k_eval_tgt(ModelDev md, int s, float* tgt, int* cnt) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int M = md.wM[s];
+  if (b >= M) return;
+  const int item = md.wY[(size_t)s * md.B + b];
+  const float* yr = md.layer[md.n_layers - 1].y + (size_t)b * md.ldL;
+  const float* wr = md.Wy + (size_t)item * md.ldL;
+  float a = 0.f;
+  for (int c4 = 0; c4 < md.ldL / 4; c4++) {
+    const float4 y = ld4(yr + c4 * 4), w = ld4(wr + c4 * 4);
+    a = fmaf(y.x, w.x, a); a = fmaf(y.y, w.y, a); a = fmaf(y.z, w.z, a); a = fmaf(y.w, w.w, a);
+  }
+  float sc = a + md.By[item];
+  if (md.fact.kind <= G4R_ACT_SELU) sc = act_fwd(md.fact, sc);
+  tgt[b] = sc;
+  cnt[b * 2 + 0] = 0; cnt[b * 2 + 1] = 0;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(EV_THREADS) k_eval_score(ModelDev md, int s, const float* __restrict__ tgt, int* cnt, float* out) {
+  extern __shared__ __align__(16) float smem[];
+  float* sY = smem;                        // [EV_TB][EV_LDS]
+  float* sW = sY + EV_TB * EV_LDS;         // [EV_IT][EV_LDS]
+  int* sCnt = reinterpret_cast<int*>(sW + EV_IT * EV_LDS);   // [EV_TB][2]
+  const int M = md.wM[s];
+  const int I = md.n_items, ldL = md.ldL;
+  const int i0 = blockIdx.x * EV_IT;
+  const int ni = min(EV_IT, I - i0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* Y = md.layer[md.n_layers - 1].y;
+  const bool hoist = ldL <= EV_KT;
+  if (hoist) {
+    const int kw = ldL / 4;
+    for (int i = tid; i < EV_IT * kw; i += EV_THREADS) {
+      const int rr = i / kw, c4 = i % kw;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rr < ni) v = ld4(md.Wy + (size_t)(i0 + rr) * ldL + c4 * 4);
+      st4(sW + rr * EV_LDS + c4 * 4, v);
+    }
+  }
+  for (int b0 = 0; b0 < M; b0 += EV_TB) {
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) acc[q] = 0.f;
+    if (tid < EV_TB * 2) sCnt[tid] = 0;
+    for (int k0 = 0; k0 < ldL; k0 += EV_KT) {
+      const int kw = min(EV_KT, ldL - k0) / 4;
+      __syncthreads();
+      for (int i = tid; i < EV_TB * kw; i += EV_THREADS) {
+        const int rr = i / kw, c4 = i % kw;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b0 + rr < M) v = ld4(Y + (size_t)(b0 + rr) * ldL + k0 + c4 * 4);
+        st4(sY + rr * EV_LDS + c4 * 4, v);
+      }
+      if (!hoist) {
+        for (int i = tid; i < EV_IT * kw; i += EV_THREADS) {
+          const int rr = i / kw, c4 = i % kw;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rr < ni) v = ld4(md.Wy + (size_t)(i0 + rr) * ldL + k0 + c4 * 4);
+          st4(sW + rr * EV_LDS + c4 * 4, v);
+        }
+      }
+      __syncthreads();
+      const float* yr = sY + lane * EV_LDS;
+      for (int c4 = 0; c4 < kw; c4++) {
+        const float4 y = ld4(yr + c4 * 4);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const float4 w = ld4(sW + (warp + 8 * q) * EV_LDS + c4 * 4);
+          acc[q] = fmaf(y.x, w.x, acc[q]); acc[q] = fmaf(y.y, w.y, acc[q]); acc[q] = fmaf(y.z, w.z, acc[q]); acc[q] = fmaf(y.w, w.w, acc[q]);
+        }
+      }
+    }
+    const int b = b0 + lane;
+    if (b < M) {
+      int gt = 0, eq = 0;
+      const float t = WRITE ? 0.f : tgt[b];
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const int it = i0 + warp + 8 * q;
+        if (warp + 8 * q < ni) {
+          float sc = acc[q] + md.By[it];
+          if (WRITE) out[(size_t)b * I + it] = sc;
+          else {
+            if (md.fact.kind <= G4R_ACT_SELU) sc = act_fwd(md.fact, sc);
+            gt += sc > t; eq += sc == t;
+          }
+        }
+      }
+      if (!WRITE) { if (gt) atomicAdd(&sCnt[lane * 2], gt); if (eq) atomicAdd(&sCnt[lane * 2 + 1], eq); }
+    }
+    __syncthreads();
+    if (!WRITE && tid < EV_TB * 2) {
+      const int bb = b0 + tid / 2;
+      if (bb < M && sCnt[tid]) atomicAdd(&cnt[bb * 2 + (tid & 1)], sCnt[tid]);
+    }
+  }
+}
+static size_t eval_smem_bytes() { return (size_t)(EV_TB * EV_LDS + EV_IT * EV_LDS) * sizeof(float) + EV_TB * 2 * sizeof(int) + 64; }
+
+// ranks + per-cutoff sums (evaluation.py:60-75), accumulated in double on the device
+__global__ void k_eval_rank(ModelDev md, int s, const int* cnt, const int* cut, int n_cut, int mode, double* sums) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int M = md.wM[s];
+  for (int b = 0; b < M; b++) {
+    const int gt = cnt[b * 2], eq = cnt[b * 2 + 1];
+    double rank;
+    if (mode == 1) rank = (double)(gt + eq);
+    else if (mode == 2) rank = (double)gt + 0.5 * (double)(eq - 1) + 1.0;
+    else rank = (double)(gt + 1);
+    for (int j = 0; j < n_cut; j++) {
+      if (rank <= (double)cut[j]) { sums[j] += 1.0; sums[n_cut + j] += 1.0 / rank; }
+    }
+  }
+}
+
+// final activation of the predict path (gru4rec.py:499-505): elementwise, softmax, or softmax for softmax_logit
+__global__ void __launch_bounds__(256) k_predict_act(ModelDev md, float* out, int batch) {
+  const int b = blockIdx.x;
+  if (b >= batch) return;
+  float* row = out + (size_t)b * md.n_items;
+  const int I = md.n_items;
+  __shared__ float red[32];
+  if (md.fact.kind <= G4R_ACT_SELU) {
+    for (int i = threadIdx.x; i < I; i += blockDim.x) row[i] = act_fwd(md.fact, row[i]);
+    return;
+  }
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < I; i += blockDim.x) m = fmaxf(m, row[i]);
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); w++) m = fmaxf(m, red[w]);
+  __syncthreads();
+  float z = 0.f;
+  for (int i = threadIdx.x; i < I; i += blockDim.x) z += expf(row[i] - m);
+  z = warp_sum(z);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = z;
+  __syncthreads();
+  z = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); w++) z += red[w];
+  for (int i = threadIdx.x; i < I; i += blockDim.x) row[i] = __fdiv_rn(expf(row[i] - m), z);
+}
+
+struct EvalCtx {
+  ModelDev mde;
+  int Be = 0;
+  int *hX = nullptr, *hY = nullptr, *hSlot = nullptr, *hM = nullptr, *hSti = nullptr; uint8_t* hF = nullptr; uint32_t* hG = nullptr;
+  int *dX = nullptr, *dY = nullptr, *dSlot = nullptr, *dM = nullptr, *dSti = nullptr; uint8_t* dF = nullptr; uint32_t* dG = nullptr;
+  int* dCut = nullptr; double* dSums = nullptr; float* dOut = nullptr; size_t out_cap = 0;
+  int cap = 0;
+};
+static std::map<g4r_handle*, EvalCtx> g_eval;
+
+static void eval_release(g4r_handle* h) {
+  auto it = g_eval.find(h);
+  if (it == g_eval.end()) return;
+  EvalCtx& e = it->second;
+  cudaFreeHost(e.hX); cudaFreeHost(e.hY); cudaFreeHost(e.hSlot); cudaFreeHost(e.hF); cudaFreeHost(e.hM); cudaFreeHost(e.hSti); cudaFreeHost(e.hG);
+  cudaFree(e.dX); cudaFree(e.dY); cudaFree(e.dSlot); cudaFree(e.dF); cudaFree(e.dM); cudaFree(e.dSti); cudaFree(e.dG);
+  cudaFree(e.dCut); cudaFree(e.dSums); if (e.dOut) cudaFree(e.dOut);
+  g_eval.erase(it);
+}
+
+static int eval_ctx(g4r_handle* h, EvalCtx** out) {
+  auto it = g_eval.find(h);
+  if (it != g_eval.end()) { *out = &it->second; return G4R_OK; }
+  EvalCtx e;
+  e.Be = h->cfg.eval_batch_size > 0 ? h->cfg.eval_batch_size : h->cfg.batch_size;
+  e.cap = 512;
+  const size_t nb = (size_t)e.cap * e.Be;
+  CK(cudaMallocHost(&e.hX, nb * sizeof(int))); CK(cudaMallocHost(&e.hY, nb * sizeof(int))); CK(cudaMallocHost(&e.hSlot, nb * sizeof(int)));
+  CK(cudaMallocHost(&e.hF, nb)); CK(cudaMallocHost(&e.hM, e.cap * sizeof(int))); CK(cudaMallocHost(&e.hSti, e.cap * sizeof(int))); CK(cudaMallocHost(&e.hG, e.cap * sizeof(uint32_t)));
+  CK(cudaMalloc(&e.dX, nb * sizeof(int))); CK(cudaMalloc(&e.dY, nb * sizeof(int))); CK(cudaMalloc(&e.dSlot, nb * sizeof(int)));
+  CK(cudaMalloc(&e.dF, nb)); CK(cudaMalloc(&e.dM, e.cap * sizeof(int))); CK(cudaMalloc(&e.dSti, e.cap * sizeof(int))); CK(cudaMalloc(&e.dG, e.cap * sizeof(uint32_t)));
+  CK(cudaMalloc(&e.dCut, 64 * sizeof(int))); CK(cudaMalloc(&e.dSums, 128 * sizeof(double)));
+  e.mde = h->md;
+  e.mde.B = e.Be;
+  e.mde.wX = e.dX; e.mde.wY = e.dY; e.mde.wSlot = e.dSlot; e.mde.wM = e.dM; e.mde.wSti = e.dSti; e.mde.wF = e.dF; e.mde.wG = e.dG;
+  cudaFuncSetAttribute(k_eval_score<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eval_smem_bytes());
+  cudaFuncSetAttribute(k_eval_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eval_smem_bytes());
+  g_eval[h] = e;
+  *out = &g_eval[h];
+  return G4R_OK;
+}
+
+static int eval_forward(g4r_handle* h, EvalCtx* e, int s) {
+  const ModelDev& md = e->mde;
+  cudaStream_t st = h->stream;
+  if (md.mode != 0) { k_gather_in<<<std::max(1, (e->Be + 7) / 8), 256, 0, st>>>(md, nullptr, s, 0); h->launches++; }
+  for (int li = 0; li < md.n_layers; li++) {
+    const LayerDev& ly = md.layer[li];
+    k_f1<<<tiles2(2 * ly.L, e->Be), GEMM_THREADS, 0, st>>>(md, nullptr, s, li, h->He[li]);
+    k_f2<<<tiles2(ly.L, e->Be), GEMM_THREADS, 0, st>>>(md, nullptr, s, li, h->He[li], 0);
+    h->launches += 2;
+  }
+  return G4R_OK;
+}
+
+extern "C" int g4r_eval_schedule(g4r_handle* h, const g4r_schedule* s, const int32_t* cut_off, int32_t n_cut, int32_t mode,
+                                 double* recall_sum, double* mrr_sum, int64_t* n_events) {
+  if (!h || !s || !cut_off || n_cut <= 0 || n_cut > 64 || !recall_sum || !mrr_sum) return G4R_ERR_INVALID;
+  if (mode < 0 || mode > 2) FAIL(G4R_ERR_INVALID, "eval mode must be 0 (standard), 1 (conservative) or 2 (median)");
+  cudaSetDevice(h->cfg.device);
+  EvalCtx* e = nullptr;
+  int rc = eval_ctx(h, &e);
+  if (rc) return rc;
+  if (s->B != e->Be) FAIL(G4R_ERR_INVALID, "schedule batch size != eval_batch_size");
+  const int Be = e->Be, I = h->md.n_items;
+  cudaStream_t st = h->stream;
+  for (int i = 0; i < h->md.n_layers; i++) CK(cudaMemsetAsync(h->He[i], 0, (size_t)Be * h->md.layer[i].ldL * sizeof(float), st));   // gru4rec.py:731-733
+  CK(cudaMemcpyAsync(e->dCut, cut_off, n_cut * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(e->dSums, 0, 128 * sizeof(double), st));
+  int64_t done = 0;
+  while (done < s->n_steps) {
+    const int64_t w = std::min<int64_t>(e->cap, s->n_steps - done);
+    CK(cudaStreamSynchronize(st));   // staging buffers are reused
+    memcpy(e->hX, s->X.data() + done * Be, (size_t)w * Be * sizeof(int));
+    memcpy(e->hY, s->Y.data() + done * Be, (size_t)w * Be * sizeof(int));
+    memcpy(e->hSlot, s->slots.data() + done * Be, (size_t)w * Be * sizeof(int));
+    memcpy(e->hF, s->F.data() + done * Be, (size_t)w * Be);
+    memcpy(e->hM, s->M.data() + done, (size_t)w * sizeof(int));
+    for (int64_t i = 0; i < w; i++) {
+      e->hSti[i] = -1; e->hG[i] = 0;
+      const int M = e->hM[i];
+      for (int b = 0; b < M; b++) {
+        const int x = e->hX[i * Be + b], y = e->hY[i * Be + b];
+        if (x < 0 || x >= I || y < 0 || y >= I) FAIL(G4R_ERR_INDEX, "Index out of bounds");
+      }
+    }
+    CK(cudaMemcpyAsync(e->dX, e->hX, (size_t)w * Be * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->dY, e->hY, (size_t)w * Be * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->dSlot, e->hSlot, (size_t)w * Be * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->dF, e->hF, (size_t)w * Be, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->dM, e->hM, (size_t)w * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->dSti, e->hSti, (size_t)w * sizeof(int), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->dG, e->hG, (size_t)w * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    for (int64_t i = 0; i < w; i++) {
+      eval_forward(h, e, (int)i);
+      k_eval_tgt<<<(Be + 127) / 128, 128, 0, st>>>(e->mde, (int)i, h->dTgt, h->dRankCnt);
+      k_eval_score<false><<<(I + EV_IT - 1) / EV_IT, EV_THREADS, eval_smem_bytes(), st>>>(e->mde, (int)i, h->dTgt, h->dRankCnt, nullptr);
+      k_eval_rank<<<1, 32, 0, st>>>(e->mde, (int)i, h->dRankCnt, e->dCut, n_cut, mode, e->dSums);
+      h->launches += 3;
+    }
+    CK(cudaGetLastError());
+    done += w;
+  }
+  std::vector<double> sums(128);
+  CK(cudaMemcpyAsync(sums.data(), e->dSums, 128 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int j = 0; j < n_cut; j++) { recall_sum[j] = sums[j]; mrr_sum[j] = sums[n_cut + j]; }
+  if (n_events) *n_events = s->n_events;
+  return G4R_OK;
+}
+
+extern "C" int g4r_predict(g4r_handle* h, const int32_t* X, int32_t batch, const uint8_t* reset_mask, float* out) {
+  if (!h || !X || !out) return G4R_ERR_INVALID;
+  cudaSetDevice(h->cfg.device);
+  EvalCtx* e = nullptr;
+  int rc = eval_ctx(h, &e);
+  if (rc) return rc;
+  const int Be = e->Be, I = h->md.n_items;
+  if (batch <= 0 || batch > Be) FAIL(G4R_ERR_INVALID, "predict batch exceeds eval_batch_size");
+  cudaStream_t st = h->stream;
+  for (int b = 0; b < Be; b++) {
+    e->hX[b] = b < batch ? X[b] : -1; e->hY[b] = 0; e->hSlot[b] = b;
+    e->hF[b] = (b < batch && reset_mask && reset_mask[b]) ? 2 : 0;
+    if (b < batch && (X[b] < 0 || X[b] >= I)) FAIL(G4R_ERR_INDEX, "Index out of bounds");
+  }
+  e->hM[0] = batch; e->hSti[0] = -1; e->hG[0] = 0;
+  CK(cudaMemcpyAsync(e->dX, e->hX, (size_t)Be * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(e->dY, e->hY, (size_t)Be * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(e->dSlot, e->hSlot, (size_t)Be * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(e->dF, e->hF, (size_t)Be, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(e->dM, e->hM, sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(e->dSti, e->hSti, sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(e->dG, e->hG, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  const size_t need = (size_t)batch * I;
+  if (e->out_cap < need) { if (e->dOut) cudaFree(e->dOut); CK(cudaMalloc(&e->dOut, need * sizeof(float))); e->out_cap = need; }
+  eval_forward(h, e, 0);
+  k_eval_score<true><<<(I + EV_IT - 1) / EV_IT, EV_THREADS, eval_smem_bytes(), st>>>(e->mde, 0, nullptr, nullptr, e->dOut);
+  k_predict_act<<<batch, 256, 0, st>>>(e->mde, e->dOut, batch);
+  h->launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, e->dOut, need * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return G4R_OK;
+}
+
+// hidden state of the scoring path (predict_next_batch zeroes it when the batch size changes, gru4rec.py:696-697)
+extern "C" int g4r_reset_eval_hidden(g4r_handle* h) {
+  if (!h) return G4R_ERR_INVALID;
+  cudaSetDevice(h->cfg.device);
+  const int Be = h->cfg.eval_batch_size > 0 ? h->cfg.eval_batch_size : h->cfg.batch_size;
+  for (int i = 0; i < h->md.n_layers; i++) CK(cudaMemsetAsync(h->He[i], 0, (size_t)Be * h->md.layer[i].ldL * sizeof(float), h->stream));
+  return G4R_OK;
+}

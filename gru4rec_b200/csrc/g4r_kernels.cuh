@@ -1,0 +1,987 @@
+// g4r_kernels.cuh -- device code of the GRU4Rec session-parallel training step for sm_100a.
+//
+// One mini-batch (reference: one call of the compiled Theano `train_function`, gru4rec.py:584,623) is a
+// fixed sequence of phases.  Each phase is a __device__ function parameterised on (cta, n_cta) so the same
+// code runs either as one kernel per phase (CUDA-graph replay; easy to profile with ncu) or inside the
+// persistent cooperative kernel (g4r_persistent.cuh) with grid barriers between phases.
+//
+// Data layout (all fp32, row-major, leading dimension padded to a multiple of 4 floats so every row is
+// a whole number of 16-byte vectors; padding columns are zero and stay zero):
+//   item tables   Wy [I x ldL], By [I], E [I x ldE], Wx0 [I x ld3] (no-embedding mode) + acc/vel twins
+//   dense         Wx[l] [in x ld3], Wh[l] [L x ldL], Wrz[l] [L x ld2], Bh[l] [ld3] + acc/vel twins
+//   hidden state  H[l] [B x ldL] in PHYSICAL lanes; a step addresses lane b through slot[b]
+//   score columns are processed in (item, position)-sorted order so that all duplicates of an item are
+//   adjacent and owned by one CTA (deterministic sparse Adagrad without atomics); the plan kernel builds
+//   that order for a whole window of steps off the critical path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/g4r.h"
+
+#define G4R_EPS_ADA 1e-6f
+#define G4R_EPS_LOG 1e-24f
+#define G4R_NSTAT 8
+
+struct ActSpec { int kind; float p1, p2; };
+
+struct LayerDev {
+  int L, ldL, ld2, ld3;
+  int in_dim, ld_in;       // in_dim==0: layer 0 of no-embedding mode (input rows gathered from Wx0, no matmul)
+  float *Wx, *Wx_acc, *Wx_vel;
+  float *Wh, *Wh_acc, *Wh_vel;
+  float *Wrz, *Wrz_acc, *Wrz_vel;
+  float *Bh, *Bh_acc, *Bh_vel;
+  float *H;                // training hidden state, physical lanes [B x ldL]
+  float *Hold, *r, *z, *ah, *ht, *y;   // forward saves, compact lanes [Bmax x ldL]
+  float *dvec;             // [Bmax x ld3]  (da_h | da_r | da_z)
+  float *dy;               // [Bmax x ldL]  upstream gradient wrt this layer's (dropped) output
+  const float* in;         // [Bmax x ld_in] input activations (layer>0: y of the layer below; layer 0: in0)
+};
+
+struct ModelDev {
+  int n_items, n_layers, B, Bld, S, mode;   // mode: 0 none, 1 embed, 2 shared
+  int L, ldL;                               // last layer
+  int in0_dim, ld_in0;                      // width of gathered input rows for embed/shared
+  int NP;                                   // capacity of score columns per step (B + S rounded up to 4)
+  int NCH;                                  // number of column chunks (CTAs of the score phases)
+  int loss; ActSpec fact, hact;
+  float p_drop_h, p_drop_e, lr, mom, lmbd, bpreg, logq, alpha;
+  int adapt; int nn_top1;                   // nn_top1 = M + n_sample term handled at run time (uses S_cfg)
+  int S_cfg;
+  uint32_t drop_seed;
+  LayerDev layer[G4R_MAX_LAYERS];
+  float *Wy, *Wy_acc, *Wy_vel; float *By, *By_acc, *By_vel;
+  float *E, *E_acc, *E_vel;                 // embed mode table (none mode: layer[0].Wx is the table)
+  float *Sx, *in0, *dSx;                    // [Bmax x ld_in0] gathered rows, dropped input, grad wrt gathered rows
+  float *snapAcc, *snapVel;                 // shared mode: acc/vel rows of X taken before the Wy update
+  const float *logP0t, *logP0s;             // logq * log(P0) for targets, logq * log(P0**alpha) for samples
+  // step scratch
+  float *O;                                 // [NP x Bld] pre-activation scores, column-major (col*Bld + b)
+  float *DSY; float *DBY;                   // [NP x ldL], [NP]
+  float *part;                              // [NCH x Bmax x ldL] partial dL/dh per chunk
+  float *stat;                              // [NCH x Bmax x NSTAT]
+  float *RS;                                // [Bmax x NSTAT] final row statistics
+  float *cost;                              // [CAP]
+  int   *nanflag;
+  // device-resident window of the schedule + plans
+  int CAP;
+  const int *wX, *wY, *wSlot, *wM, *wSti, *wXnext; const uint8_t *wF, *wXflag; const uint32_t* wG;
+  int *pItem, *pPos, *pTcol, *pCbeg;
+  const int* ST;                            // sample store [rows x S] int32
+};
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float act_fwd(const ActSpec a, float x) {
+  switch (a.kind) {
+    case G4R_ACT_LINEAR: return x;
+    case G4R_ACT_RELU: return fmaxf(x, 0.f);
+    case G4R_ACT_TANH: return tanhf(x);
+    case G4R_ACT_LEAKY: return x >= 0.f ? x : a.p1 * x;
+    case G4R_ACT_ELU: return x >= 0.f ? x : a.p1 * (expf(x) - 1.0f);
+    case G4R_ACT_SELU: return a.p1 * (x >= 0.f ? x : a.p2 * (expf(x) - 1.0f));
+    default: return x;
+  }
+}
+// derivative given pre-activation x and output y
+__device__ __forceinline__ float act_der(const ActSpec a, float x, float y) {
+  switch (a.kind) {
+    case G4R_ACT_LINEAR: return 1.f;
+    case G4R_ACT_RELU: return x > 0.f ? 1.f : 0.f;
+    case G4R_ACT_TANH: return 1.f - y * y;
+    case G4R_ACT_LEAKY: return x >= 0.f ? 1.f : a.p1;
+    case G4R_ACT_ELU: return x >= 0.f ? 1.f : a.p1 * expf(x);
+    case G4R_ACT_SELU: return a.p1 * (x >= 0.f ? 1.f : a.p2 * expf(x));
+    default: return 1.f;
+  }
+}
+
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16; return x;
+}
+// dropout mask/retain for element idx of stream `stream` at global step `gstep` (definition shared with the oracle)
+__device__ __forceinline__ float drop_scale(uint32_t seed, uint32_t gstep, uint32_t stream, uint32_t idx, float retain) {
+  uint32_t k = mix32(seed ^ (0x9E3779B9U * (stream + 1U)));
+  k = mix32(k + gstep);
+  uint32_t r = mix32(k + idx);
+  float u = (float)(r >> 8) * (1.0f / 16777216.0f);
+  return u < retain ? __fdiv_rn(1.0f, retain) : 0.f;
+}
+#define G4R_STREAM_EMBED 100u
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// ------------------------------------------------------------------------------------------------
+// generic CTA-tile GEMM accumulate: acc[TM][TN] += sum_k A(m,k) * B(k,n) for the thread's micro tile of a
+// BM x BN CTA tile.  A(m,k), B(k,n) are fetched through functors (bounds handled by the functor).
+// ------------------------------------------------------------------------------------------------
+template <int BM, int BN, int BK, int TM, int TN, bool A_KFAST, bool B_NFAST, class FA, class FB>
+__device__ __forceinline__ void gemm_tile_acc(float (&acc)[TM][TN], int K, FA fa, FB fb, float* sA, float* sB) {
+  constexpr int NT = (BM / TM) * (BN / TN);
+  const int tid = threadIdx.x;
+  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    for (int i = tid; i < BM * BK; i += NT) {
+      int m, k;
+      if (A_KFAST) { k = i % BK; m = i / BK; } else { m = i % BM; k = i / BM; }
+      sA[k * (BM + 1) + m] = (k0 + k < K) ? fa(m, k0 + k) : 0.f;
+    }
+    for (int i = tid; i < BK * BN; i += NT) {
+      int n, k;
+      if (B_NFAST) { n = i % BN; k = i / BN; } else { k = i % BK; n = i / BK; }
+      sB[k * (BN + 1) + n] = (k0 + k < K) ? fb(k0 + k, n) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < BK; k++) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; i++) a[i] = sA[k * (BM + 1) + ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; j++) b[j] = sB[k * (BN + 1) + tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; i++)
+#pragma unroll
+        for (int j = 0; j < TN; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+}
+constexpr int GB = 32;   // CTA tile edge of the small-GEMM phases
+constexpr int GK = 32;
+constexpr int GT = 2;    // micro tile
+constexpr int GEMM_THREADS = (GB / GT) * (GB / GT);   // 256
+
+// dense Adagrad(+momentum) on one element (gru4rec.py:330-340,390-406)
+__device__ __forceinline__ void dense_update(const ModelDev& md, float* p, float* acc, float* vel, float g) {
+  float gs = g;
+  if (md.adapt == G4R_ADAPT_ADAGRAD) {
+    float a = *acc + g * g;
+    *acc = a;
+    gs = __fdiv_rn(g, sqrtf(a + G4R_EPS_ADA));
+  }
+  float pv = *p;
+  if (md.mom > 0.f) {
+    float v2 = md.mom * (*vel) - md.lr * (gs + md.lmbd * pv);
+    *vel = v2;
+    *p = pv + v2;
+  } else {
+    *p = pv * (1.0f - md.lr * md.lmbd) - md.lr * gs;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// phase G0: gather input rows for embedding modes (gru4rec.py:440-443 / 450-451), one warp per lane
+// ------------------------------------------------------------------------------------------------
+__device__ void phase_gather_in(const ModelDev& md, int s, bool train, int cta, int ncta) {
+  const int M = md.wM[s];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const float* tab = (md.mode == 2) ? md.Wy : md.E;
+  const int ld = md.ld_in0, W = md.in0_dim;
+  const uint32_t gstep = md.wG[s];
+  const float retain = 1.0f - md.p_drop_e;
+  for (int b = cta * nwarp + warp; b < M; b += ncta * nwarp) {
+    const int item = md.wX[(size_t)s * md.B + b];
+    const float* row = tab + (size_t)item * ld;
+    for (int c4 = lane; c4 < ld / 4; c4 += 32) {
+      float4 v = ld4(row + c4 * 4);
+      st4(md.Sx + (size_t)b * ld + c4 * 4, v);
+      if (train && md.p_drop_e > 0.f) {
+        const uint32_t base = (uint32_t)(b * W + c4 * 4);
+        v.x *= (c4 * 4 + 0 < W) ? drop_scale(md.drop_seed, gstep, G4R_STREAM_EMBED, base + 0, retain) : 0.f;
+        v.y *= (c4 * 4 + 1 < W) ? drop_scale(md.drop_seed, gstep, G4R_STREAM_EMBED, base + 1, retain) : 0.f;
+        v.z *= (c4 * 4 + 2 < W) ? drop_scale(md.drop_seed, gstep, G4R_STREAM_EMBED, base + 2, retain) : 0.f;
+        v.w *= (c4 * 4 + 3 < W) ? drop_scale(md.drop_seed, gstep, G4R_STREAM_EMBED, base + 3, retain) : 0.f;
+      }
+      st4(md.in0 + (size_t)b * ld + c4 * 4, v);
+      if (train && md.mode == 2) {
+        if (md.Wy_acc) st4(md.snapAcc + (size_t)b * ld + c4 * 4, ld4(md.Wy_acc + (size_t)item * ld + c4 * 4));
+        if (md.Wy_vel) st4(md.snapVel + (size_t)b * ld + c4 * 4, ld4(md.Wy_vel + (size_t)item * ld + c4 * 4));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// phase F1: rz = sigmoid(vec[:, L:] + H @ Wrz)  (gru4rec.py:460 / 473).  Tile = 32 lanes x 32 gate columns.
+// Hsrc: hidden-state array this pass reads/writes (training H or evaluation H), physical lanes.
+// flags bit1: zero the lane's state before the step (evaluation.py:136-139).
+// ------------------------------------------------------------------------------------------------
+__device__ void phase_f1(const ModelDev& md, int li, int s, float* Hsrc, int tile, float* sA, float* sB) {
+  const LayerDev& ly = md.layer[li];
+  const int M = md.wM[s];
+  const int L = ly.L;
+  const int ntn = (2 * L + GB - 1) / GB;
+  const int tn = tile % ntn, tm = tile / ntn;
+  const int m0 = tm * GB, n0 = tn * GB;
+  if (m0 >= M) return;
+  const int* slot = md.wSlot + (size_t)s * md.B;
+  const uint8_t* fl = md.wF + (size_t)s * md.B;
+  float acc[GT][GT] = {};
+  auto fa_h = [&](int m, int k) -> float {
+    int b = m0 + m;
+    if (b >= M) return 0.f;
+    if (fl[b] & 2) return 0.f;
+    return Hsrc[(size_t)slot[b] * ly.ldL + k];
+  };
+  auto fb_rz = [&](int k, int n) -> float { int c = n0 + n; return c < 2 * L ? ly.Wrz[(size_t)k * ly.ld2 + c] : 0.f; };
+  gemm_tile_acc<GB, GB, GK, GT, GT, true, true>(acc, L, fa_h, fb_rz, sA, sB);
+  if (ly.in_dim > 0) {
+    auto fa_in = [&](int m, int k) -> float { int b = m0 + m; return b < M ? ly.in[(size_t)b * ly.ld_in + k] : 0.f; };
+    auto fb_wx = [&](int k, int n) -> float { int c = n0 + n; return c < 2 * L ? ly.Wx[(size_t)k * ly.ld3 + L + c] : 0.f; };
+    gemm_tile_acc<GB, GB, GK, GT, GT, true, true>(acc, ly.in_dim, fa_in, fb_wx, sA, sB);
+  }
+  const int tx = threadIdx.x % (GB / GT), ty = threadIdx.x / (GB / GT);
+#pragma unroll
+  for (int i = 0; i < GT; i++) {
+    const int b = m0 + ty * GT + i;
+    if (b >= M) continue;
+#pragma unroll
+    for (int j = 0; j < GT; j++) {
+      const int c = n0 + tx * GT + j;
+      if (c >= 2 * L) continue;
+      float v = acc[i][j] + ly.Bh[L + c];
+      if (ly.in_dim == 0) v += ly.Wx[(size_t)md.wX[(size_t)s * md.B + b] * ly.ld3 + L + c];
+      const float g = sigmoidf_(v);
+      if (c < L) ly.r[(size_t)b * ly.ldL + c] = g; else ly.z[(size_t)b * ly.ldL + (c - L)] = g;
+    }
+  }
+  // the tiles of column block 0 also materialise the compact copy of the old hidden state
+  if (tn == 0) {
+    for (int i = threadIdx.x; i < GB * ly.ldL; i += blockDim.x) {
+      const int b = m0 + i / ly.ldL, k = i % ly.ldL;
+      if (b < M) ly.Hold[(size_t)b * ly.ldL + k] = (fl[b] & 2) ? 0.f : Hsrc[(size_t)slot[b] * ly.ldL + k];
+    }
+  }
+}
+__device__ __forceinline__ int f1_tiles(const ModelDev& md, int li, int Bmax) {
+  return ((2 * md.layer[li].L + GB - 1) / GB) * ((Bmax + GB - 1) / GB);
+}
+
+// ------------------------------------------------------------------------------------------------
+// phase F2: h~ = act((H*r) @ Wh + vec[:, :L]); h = (1-z) H + z h~; dropout; H_new (gru4rec.py:461-466)
+// ------------------------------------------------------------------------------------------------
+__device__ void phase_f2(const ModelDev& md, int li, int s, float* Hsrc, bool train, int tile, float* sA, float* sB) {
+  const LayerDev& ly = md.layer[li];
+  const int M = md.wM[s];
+  const int L = ly.L;
+  const int ntn = (L + GB - 1) / GB;
+  const int tn = tile % ntn, tm = tile / ntn;
+  const int m0 = tm * GB, n0 = tn * GB;
+  if (m0 >= M) return;
+  const int* slot = md.wSlot + (size_t)s * md.B;
+  const uint8_t* fl = md.wF + (size_t)s * md.B;
+  float acc[GT][GT] = {};
+  auto fa_hr = [&](int m, int k) -> float {
+    int b = m0 + m;
+    return b < M ? ly.Hold[(size_t)b * ly.ldL + k] * ly.r[(size_t)b * ly.ldL + k] : 0.f;
+  };
+  auto fb_wh = [&](int k, int n) -> float { int c = n0 + n; return c < L ? ly.Wh[(size_t)k * ly.ldL + c] : 0.f; };
+  gemm_tile_acc<GB, GB, GK, GT, GT, true, true>(acc, L, fa_hr, fb_wh, sA, sB);
+  if (ly.in_dim > 0) {
+    auto fa_in = [&](int m, int k) -> float { int b = m0 + m; return b < M ? ly.in[(size_t)b * ly.ld_in + k] : 0.f; };
+    auto fb_wx = [&](int k, int n) -> float { int c = n0 + n; return c < L ? ly.Wx[(size_t)k * ly.ld3 + c] : 0.f; };
+    gemm_tile_acc<GB, GB, GK, GT, GT, true, true>(acc, ly.in_dim, fa_in, fb_wx, sA, sB);
+  }
+  const int tx = threadIdx.x % (GB / GT), ty = threadIdx.x / (GB / GT);
+  const uint32_t gstep = md.wG[s];
+  const float retain = 1.0f - md.p_drop_h;
+#pragma unroll
+  for (int i = 0; i < GT; i++) {
+    const int b = m0 + ty * GT + i;
+    if (b >= M) continue;
+#pragma unroll
+    for (int j = 0; j < GT; j++) {
+      const int c = n0 + tx * GT + j;
+      if (c >= L) continue;
+      float v = acc[i][j] + ly.Bh[c];
+      if (ly.in_dim == 0) v += ly.Wx[(size_t)md.wX[(size_t)s * md.B + b] * ly.ld3 + c];
+      const float ht = act_fwd(md.hact, v);
+      const float z = ly.z[(size_t)b * ly.ldL + c];
+      const float ho = ly.Hold[(size_t)b * ly.ldL + c];
+      float h = (1.0f - z) * ho + z * ht;
+      if (train && md.p_drop_h > 0.f) h *= drop_scale(md.drop_seed, gstep, (uint32_t)li, (uint32_t)(b * L + c), retain);
+      ly.ah[(size_t)b * ly.ldL + c] = v;
+      ly.ht[(size_t)b * ly.ldL + c] = ht;
+      ly.y[(size_t)b * ly.ldL + c] = h;
+      Hsrc[(size_t)slot[b] * ly.ldL + c] = (train && (fl[b] & 1)) ? 0.f : h;
+    }
+  }
+}
+__device__ __forceinline__ int f2_tiles(const ModelDev& md, int li, int Bmax) {
+  return ((md.layer[li].L + GB - 1) / GB) * ((Bmax + GB - 1) / GB);
+}
+
+// ------------------------------------------------------------------------------------------------
+// phase S1: sampled scores o = h @ Sy^T + by (- logq correction) for this CTA's column chunk, plus the
+// chunk's partial row statistics of the loss.  (gru4rec.py:482-496, 225-248)
+// ------------------------------------------------------------------------------------------------
+constexpr int SC_CT = 16;    // columns per sub tile
+constexpr int SC_TB = 32;    // lanes per row tile
+constexpr int SC_KT = 128;   // feature slab
+constexpr int SC_LDS = SC_KT + 4;
+constexpr int SC_THREADS = 256;
+
+struct RowStat { float m, Z, A, Q, D, T, aux; };
+
+__device__ __forceinline__ bool loss_pairwise(int loss) { return loss == G4R_LOSS_BPR_MAX || loss == G4R_LOSS_TOP1_MAX || loss == G4R_LOSS_BPR || loss == G4R_LOSS_TOP1; }
+__device__ __forceinline__ bool loss_softmaxneg(int loss) { return loss == G4R_LOSS_BPR_MAX || loss == G4R_LOSS_TOP1_MAX; }
+
+// merge (m,Z,A,Q,D) of two partial softmax-weighted sums
+__device__ __forceinline__ void stat_merge(float& m, float& Z, float& A, float& Q, float& D, float m2, float Z2, float A2, float Q2, float D2) {
+  const float mn = fmaxf(m, m2);
+  const float e1 = (m == -INFINITY) ? 0.f : expf(m - mn), e2 = (m2 == -INFINITY) ? 0.f : expf(m2 - mn);
+  Z = Z * e1 + Z2 * e2; A = A * e1 + A2 * e2; Q = Q * e1 + Q2 * e2; D = D * e1 + D2 * e2; m = mn;
+}
+
+__device__ void phase_score(const ModelDev& md, int s, int chunk, float* smem) {
+  const int M = md.wM[s];
+  const int sti = md.wSti[s];
+  const int N = M + (sti >= 0 ? md.S : 0);
+  const int* cbeg = md.pCbeg + (size_t)s * (md.NCH + 1);
+  const int cb = cbeg[chunk], ce = cbeg[chunk + 1];
+  if (cb >= ce) return;
+  const int L = md.L, ldL = md.ldL;
+  const float* Y = md.layer[md.n_layers - 1].y;
+  const int* pItem = md.pItem + (size_t)s * md.NP;
+  const int* pPos = md.pPos + (size_t)s * md.NP;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* sY = smem;                              // [SC_TB][SC_LDS]
+  float* sS = sY + SC_TB * SC_LDS;               // [SC_CT][SC_LDS]
+  float* sT = sS + SC_CT * SC_LDS;               // [Bmax] target activations (pairwise losses)
+  // --- target activations for pairwise losses: every chunk needs t_b = f(o_b,target) of every lane
+  const bool pw = loss_pairwise(md.loss);
+  if (pw) {
+    for (int b = warp; b < M; b += SC_THREADS / 32) {
+      const int item = md.wY[(size_t)s * md.B + b];
+      const float* wr = md.Wy + (size_t)item * ldL;
+      const float* yr = Y + (size_t)b * ldL;
+      float a = 0.f;
+      for (int c4 = lane; c4 < ldL / 4; c4 += 32) {
+        const float4 w = ld4(wr + c4 * 4), y = ld4(yr + c4 * 4);
+        a = fmaf(w.x, y.x, a); a = fmaf(w.y, y.y, a); a = fmaf(w.z, y.z, a); a = fmaf(w.w, y.w, a);
+      }
+      a = warp_sum(a);
+      if (lane == 0) {
+        float o = a + md.By[item];
+        if (md.logq > 0.f) o -= md.logP0t[item];
+        sT[b] = act_fwd(md.fact, o);
+      }
+    }
+  }
+  __syncthreads();
+  // --- scores
+  for (int j0 = cb; j0 < ce; j0 += SC_CT) {
+    const int nj = min(SC_CT, ce - j0);
+    for (int b0 = 0; b0 < M; b0 += SC_TB) {
+      float acc0 = 0.f, acc1 = 0.f;
+      for (int k0 = 0; k0 < ldL; k0 += SC_KT) {
+        const int kw = min(SC_KT, ldL - k0) / 4;       // float4 per row in this slab
+        for (int i = tid; i < SC_TB * kw; i += SC_THREADS) {
+          const int rr = i / kw, c4 = i % kw;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (b0 + rr < M) v = ld4(Y + (size_t)(b0 + rr) * ldL + k0 + c4 * 4);
+          st4(sY + rr * SC_LDS + c4 * 4, v);
+        }
+        for (int i = tid; i < nj * kw; i += SC_THREADS) {
+          const int rr = i / kw, c4 = i % kw;
+          st4(sS + rr * SC_LDS + c4 * 4, ld4(md.Wy + (size_t)pItem[j0 + rr] * ldL + k0 + c4 * 4));
+        }
+        __syncthreads();
+        const float* yr = sY + lane * SC_LDS;
+        const float* s0 = sS + warp * SC_LDS;
+        const float* s1 = sS + (warp + 8) * SC_LDS;
+        const bool h0 = warp < nj, h1 = warp + 8 < nj;
+        for (int c4 = 0; c4 < kw; c4++) {
+          const float4 y = ld4(yr + c4 * 4);
+          if (h0) { const float4 w = ld4(s0 + c4 * 4); acc0 = fmaf(y.x, w.x, acc0); acc0 = fmaf(y.y, w.y, acc0); acc0 = fmaf(y.z, w.z, acc0); acc0 = fmaf(y.w, w.w, acc0); }
+          if (h1) { const float4 w = ld4(s1 + c4 * 4); acc1 = fmaf(y.x, w.x, acc1); acc1 = fmaf(y.y, w.y, acc1); acc1 = fmaf(y.z, w.z, acc1); acc1 = fmaf(y.w, w.w, acc1); }
+        }
+        __syncthreads();
+      }
+      const int b = b0 + lane;
+      if (b < M) {
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          const int jj = warp + q * 8;
+          if (jj < nj) {
+            const int j = j0 + jj, item = pItem[j];
+            float o = (q ? acc1 : acc0) + md.By[item];
+            if (md.logq > 0.f) o -= (pPos[j] < M) ? md.logP0t[item] : md.logP0s[item];
+            md.O[(size_t)j * md.Bld + b] = o;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();   // O of this chunk written by this CTA is visible to it
+  // --- partial row statistics over this chunk's columns: warp per lane b, lanes over columns
+  const int* tcol = md.pTcol + (size_t)s * md.B;
+  for (int b = warp; b < M; b += SC_THREADS / 32) {
+    float m = -INFINITY, Z = 0.f, A = 0.f, Q = 0.f, D = 0.f, T = 0.f;
+    const int tc = tcol[b];
+    const float t = pw ? sT[b] : 0.f;
+    // pass 1: max
+    if (md.loss == G4R_LOSS_XE || md.loss == G4R_LOSS_XE_LOGIT || loss_softmaxneg(md.loss)) {
+      for (int j = cb + lane; j < ce; j += 32) {
+        const float o = md.O[(size_t)j * md.Bld + b];
+        if (loss_softmaxneg(md.loss)) { if (j != tc) m = fmaxf(m, act_fwd(md.fact, o)); }
+        else m = fmaxf(m, o);
+      }
+      m = warp_max(m);
+      if (loss_softmaxneg(md.loss)) m = fmaxf(m, 0.f);   // the zeroed diagonal takes part in the max (gru4rec.py:200-202)
+    }
+    for (int j = cb + lane; j < ce; j += 32) {
+      const float o = md.O[(size_t)j * md.Bld + b];
+      if (md.loss == G4R_LOSS_XE || md.loss == G4R_LOSS_XE_LOGIT) {
+        Z += expf(o - m);
+        if (j == tc) T = o;
+      } else {
+        const float y = act_fwd(md.fact, o);
+        if (md.loss == G4R_LOSS_BPR_MAX) {
+          if (j != tc) { const float e = expf(y - m), sg = sigmoidf_(t - y); Z += e; A += sg * e; Q += y * y * e; D += sg * (1.f - sg) * e; }
+        } else if (md.loss == G4R_LOSS_TOP1_MAX) {
+          if (j != tc) { const float e = expf(y - m), a1 = sigmoidf_(y - t), b1 = sigmoidf_(y * y); Z += e; A += (a1 + b1) * e; D += a1 * (1.f - a1) * e; }
+        } else if (md.loss == G4R_LOSS_BPR) {
+          const float sg = sigmoidf_(t - y);
+          A += -logf(sg);
+          if (j != tc) D += 1.f - sg;
+        } else {  // TOP1
+          const float a1 = sigmoidf_(y - t), b1 = sigmoidf_(y * y);
+          A += a1 + b1;
+          if (j != tc) D += a1 * (1.f - a1);
+        }
+      }
+    }
+    Z = warp_sum(Z); A = warp_sum(A); Q = warp_sum(Q); D = warp_sum(D); T = warp_sum(T);
+    if (lane == 0) {
+      float* st = md.stat + ((size_t)chunk * md.B + b) * G4R_NSTAT;
+      st[0] = m; st[1] = Z; st[2] = A; st[3] = Q; st[4] = D; st[5] = T;
+      st[6] = (tc >= cb && tc < ce) ? 1.f : 0.f;
+      if (pw) st[7] = t;
+    }
+  }
+}
+__host__ __device__ inline size_t score_smem_bytes(int Bmax) { return (size_t)(SC_TB * SC_LDS + SC_CT * SC_LDS + Bmax + 32) * sizeof(float); }
+
+// ------------------------------------------------------------------------------------------------
+// phase S2: combine chunk statistics -> final row statistics, per-row loss, cost (single CTA, deterministic)
+// RS[b] = {m, Z, A', Q', D', t_or_targetO, loss_b}
+// ------------------------------------------------------------------------------------------------
+__device__ void phase_stats(const ModelDev& md, int s, float* smem) {
+  const int M = md.wM[s];
+  const int sti = md.wSti[s];
+  const int N = M + (sti >= 0 ? md.S : 0);
+  const int* cbeg = md.pCbeg + (size_t)s * (md.NCH + 1);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  float* sLoss = smem;   // [Bmax]
+  for (int b = warp; b < M; b += nwarp) {
+    float m = -INFINITY, Z = 0.f, A = 0.f, Q = 0.f, D = 0.f, T = 0.f, tt = 0.f;
+    for (int c = lane; c < md.NCH; c += 32) {
+      if (cbeg[c] >= cbeg[c + 1]) continue;
+      const float* st = md.stat + ((size_t)c * md.B + b) * G4R_NSTAT;
+      if (md.loss == G4R_LOSS_BPR || md.loss == G4R_LOSS_TOP1) { A += st[2]; D += st[4]; }
+      else stat_merge(m, Z, A, Q, D, st[0], st[1], st[2], st[3], st[4]);
+      if (st[6] > 0.f) T = st[5];
+      tt = st[7];
+    }
+    // butterfly merge across lanes
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, m, o), Z2 = __shfl_xor_sync(0xffffffffu, Z, o), A2 = __shfl_xor_sync(0xffffffffu, A, o),
+                  Q2 = __shfl_xor_sync(0xffffffffu, Q, o), D2 = __shfl_xor_sync(0xffffffffu, D, o), T2 = __shfl_xor_sync(0xffffffffu, T, o);
+      if (md.loss == G4R_LOSS_BPR || md.loss == G4R_LOSS_TOP1) { A += A2; D += D2; }
+      else stat_merge(m, Z, A, Q, D, m2, Z2, A2, Q2, D2);
+      T += T2;     // exactly one chunk owns the target column
+    }
+    if (lane == 0) {
+      float* rs = md.RS + (size_t)b * G4R_NSTAT;
+      float loss = 0.f;
+      if (md.loss == G4R_LOSS_XE) {
+        const float pt = __fdiv_rn(expf(T - m), Z);
+        loss = -logf(pt + G4R_EPS_LOG);
+        rs[0] = m; rs[1] = Z; rs[5] = T; rs[2] = pt;
+      } else if (md.loss == G4R_LOSS_XE_LOGIT) {
+        loss = logf(Z) - (T - m);
+        rs[0] = m; rs[1] = Z; rs[5] = T;
+      } else if (md.loss == G4R_LOSS_BPR_MAX) {
+        const float Ap = __fdiv_rn(A, Z), Qp = __fdiv_rn(Q, Z), Dp = __fdiv_rn(D, Z);
+        loss = -logf(Ap + G4R_EPS_LOG) + md.bpreg * Qp;
+        rs[0] = m; rs[1] = Z; rs[2] = Ap; rs[3] = Qp; rs[4] = Dp; rs[5] = tt;
+      } else if (md.loss == G4R_LOSS_TOP1_MAX) {
+        const float Ap = __fdiv_rn(A, Z), Dp = __fdiv_rn(D, Z);
+        loss = Ap;
+        rs[0] = m; rs[1] = Z; rs[2] = Ap; rs[4] = Dp; rs[5] = tt;
+      } else if (md.loss == G4R_LOSS_BPR) {
+        loss = A;
+        rs[4] = D; rs[5] = tt;
+      } else {  // TOP1 (gru4rec.py:242-244): mean over the N columns, last term over M + n_sample
+        const float c = sigmoidf_(tt * tt);
+        loss = __fdiv_rn(A, (float)N) - __fdiv_rn(c, (float)(M + md.S_cfg));
+        rs[4] = D; rs[5] = tt;
+      }
+      rs[6] = loss;
+      sLoss[b] = loss;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float c = 0.f;
+    for (int b = 0; b < M; b++) c += sLoss[b];
+    c = __fdiv_rn(c, (float)md.B);            // cost = loss / batch_size (gru4rec.py:577)
+    md.cost[s] = c;
+    if (c != c) atomicExch(md.nanflag, 1);
+  }
+}
+
+// dL/do for element (b, column j) given final row statistics (already divided by batch_size)
+__device__ __forceinline__ float loss_grad_elem(const ModelDev& md, const float* rs, float o, bool is_t, int M, int N) {
+  const float invB = __fdiv_rn(1.0f, (float)md.B);
+  if (md.loss == G4R_LOSS_XE) {
+    const float p = __fdiv_rn(expf(o - rs[0]), rs[1]);
+    const float fac = __fdiv_rn(rs[2], rs[2] + G4R_EPS_LOG);
+    return fac * (p - (is_t ? 1.f : 0.f)) * invB;
+  }
+  if (md.loss == G4R_LOSS_XE_LOGIT) {
+    const float p = __fdiv_rn(expf(o - rs[0]), rs[1]);
+    return (p - (is_t ? 1.f : 0.f)) * invB;
+  }
+  const float y = act_fwd(md.fact, o);
+  const float fd = act_der(md.fact, o, y);
+  const float t = rs[5];
+  float dy;
+  if (md.loss == G4R_LOSS_BPR_MAX) {
+    const float Ap = rs[2], Qp = rs[3], Dp = rs[4];
+    const float invA = __fdiv_rn(1.0f, Ap + G4R_EPS_LOG);
+    if (is_t) dy = -invA * Dp;
+    else {
+      const float sj = __fdiv_rn(expf(y - rs[0]), rs[1]);
+      const float sg = sigmoidf_(t - y);
+      const float dLds = -invA * sg + md.bpreg * y * y;
+      const float mean = -invA * Ap + md.bpreg * Qp;
+      dy = sj * (dLds - mean) + invA * sj * sg * (1.f - sg) + 2.f * md.bpreg * y * sj;
+    }
+  } else if (md.loss == G4R_LOSS_TOP1_MAX) {
+    const float Ap = rs[2], Dp = rs[4];
+    if (is_t) dy = -Dp;
+    else {
+      const float sj = __fdiv_rn(expf(y - rs[0]), rs[1]);
+      const float a1 = sigmoidf_(y - t), b1 = sigmoidf_(y * y);
+      dy = sj * ((a1 + b1) - Ap) + sj * a1 * (1.f - a1) + sj * b1 * (1.f - b1) * 2.f * y;
+    }
+  } else if (md.loss == G4R_LOSS_BPR) {
+    if (is_t) dy = -rs[4];
+    else dy = 1.f - sigmoidf_(t - y);
+  } else {  // TOP1
+    const float invN = __fdiv_rn(1.0f, (float)N);
+    if (is_t) {
+      const float c = sigmoidf_(t * t);
+      dy = -rs[4] * invN + c * (1.f - c) * 2.f * t * invN - __fdiv_rn(c * (1.f - c) * 2.f * t, (float)(M + md.S_cfg));
+    } else {
+      const float a1 = sigmoidf_(y - t), b1 = sigmoidf_(y * y);
+      dy = (a1 * (1.f - a1) + b1 * (1.f - b1) * 2.f * y) * invN;
+    }
+  }
+  return dy * fd * invB;
+}
+
+// ------------------------------------------------------------------------------------------------
+// phase S3: loss gradient for this chunk's columns, dSy / dby rows, partial dL/dh, then the sparse
+// Adagrad(+momentum) update of the chunk's Wy / By rows (gru4rec.py:383-384 grads, 407-431 updates).
+// Duplicates of an item are adjacent (sorted plan) and handled sequentially in position order:
+// acc / velocity keep the LAST occurrence (set_subtensor), the parameter accumulates all (inc_subtensor).
+// ------------------------------------------------------------------------------------------------
+__device__ void phase_lossgrad(const ModelDev& md, int s, int chunk, float* smem) {
+  const int M = md.wM[s];
+  const int sti = md.wSti[s];
+  const int N = M + (sti >= 0 ? md.S : 0);
+  const int* cbeg = md.pCbeg + (size_t)s * (md.NCH + 1);
+  const int cb = cbeg[chunk], ce = cbeg[chunk + 1];
+  if (cb >= ce) return;
+  const int L = md.L, ldL = md.ldL;
+  (void)L;
+  const float* Y = md.layer[md.n_layers - 1].y;
+  const int* pItem = md.pItem + (size_t)s * md.NP;
+  const int* pPos = md.pPos + (size_t)s * md.NP;
+  const int* tcol = md.pTcol + (size_t)s * md.B;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Bp = md.Bld;
+  float* sY = smem;                              // [SC_TB][SC_LDS]
+  float* sS = sY + SC_TB * SC_LDS;               // [SC_CT][SC_LDS]
+  float* sG = sS + SC_CT * SC_LDS;               // [SC_CT][Bp]
+  float* part = md.part + (size_t)chunk * md.B * ldL;
+  for (int j0 = cb; j0 < ce; j0 += SC_CT) {
+    const int nj = min(SC_CT, ce - j0);
+    // gradients of the sub tile
+    for (int i = tid; i < SC_CT * Bp; i += SC_THREADS) {
+      const int jj = i / Bp, b = i % Bp;
+      float g = 0.f;
+      if (jj < nj && b < M) g = loss_grad_elem(md, md.RS + (size_t)b * G4R_NSTAT, md.O[(size_t)(j0 + jj) * Bp + b], tcol[b] == j0 + jj, M, N);
+      sG[i] = g;
+    }
+    __syncthreads();
+    // dby
+    for (int jj = warp; jj < nj; jj += SC_THREADS / 32) {
+      float a = 0.f;
+      for (int b = lane; b < M; b += 32) a += sG[jj * Bp + b];
+      a = warp_sum(a);
+      if (lane == 0) md.DBY[j0 + jj] = a;
+    }
+    for (int k0 = 0; k0 < ldL; k0 += SC_KT) {
+      const int kw = min(SC_KT, ldL - k0) / 4;
+      // stage Sy slab
+      for (int i = tid; i < nj * kw; i += SC_THREADS) {
+        const int rr = i / kw, c4 = i % kw;
+        st4(sS + rr * SC_LDS + c4 * 4, ld4(md.Wy + (size_t)pItem[j0 + rr] * ldL + k0 + c4 * 4));
+      }
+      float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0;     // dSy for columns warp, warp+8 at feature quad `lane`
+      for (int b0 = 0; b0 < M; b0 += SC_TB) {
+        __syncthreads();
+        for (int i = tid; i < SC_TB * kw; i += SC_THREADS) {
+          const int rr = i / kw, c4 = i % kw;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (b0 + rr < M) v = ld4(Y + (size_t)(b0 + rr) * ldL + k0 + c4 * 4);
+          st4(sY + rr * SC_LDS + c4 * 4, v);
+        }
+        __syncthreads();
+        // dSy_j[k] += sum_b g[b][j] * y[b][k]
+        if (lane < kw) {
+          const int nb = min(SC_TB, M - b0);
+          for (int bb = 0; bb < nb; bb++) {
+            const float4 y = ld4(sY + bb * SC_LDS + lane * 4);
+            const float g0 = sG[warp * Bp + b0 + bb], g1 = sG[(warp + 8) * Bp + b0 + bb];
+            d0.x = fmaf(g0, y.x, d0.x); d0.y = fmaf(g0, y.y, d0.y); d0.z = fmaf(g0, y.z, d0.z); d0.w = fmaf(g0, y.w, d0.w);
+            d1.x = fmaf(g1, y.x, d1.x); d1.y = fmaf(g1, y.y, d1.y); d1.z = fmaf(g1, y.z, d1.z); d1.w = fmaf(g1, y.w, d1.w);
+          }
+        }
+        // partial dL/dh[b][k] (+)= sum_j g[b][j] * Sy_j[k] : warp handles lanes b = b0 + warp + 8*q
+        if (lane < kw) {
+          for (int bb = warp; bb < SC_TB && b0 + bb < M; bb += SC_THREADS / 32) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int jj = 0; jj < nj; jj++) {
+              const float g = sG[jj * Bp + b0 + bb];
+              const float4 w = ld4(sS + jj * SC_LDS + lane * 4);
+              a.x = fmaf(g, w.x, a.x); a.y = fmaf(g, w.y, a.y); a.z = fmaf(g, w.z, a.z); a.w = fmaf(g, w.w, a.w);
+            }
+            float* dst = part + (size_t)(b0 + bb) * ldL + k0 + lane * 4;
+            if (j0 > cb) { const float4 o = ld4(dst); a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; }
+            st4(dst, a);
+          }
+        }
+      }
+      if (lane < kw) {
+        if (warp < nj) st4(md.DSY + (size_t)(j0 + warp) * ldL + k0 + lane * 4, d0);
+        if (warp + 8 < nj) st4(md.DSY + (size_t)(j0 + warp + 8) * ldL + k0 + lane * 4, d1);
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  // ---- sparse update of this chunk's item groups; one warp per group
+  const bool ada = md.adapt == G4R_ADAPT_ADAGRAD;
+  const bool mom = md.mom > 0.f;
+  for (int j = cb + warp; j < ce; j += SC_THREADS / 32) {
+    const int item = pItem[j];
+    if (j > cb && pItem[j - 1] == item) continue;          // not a group start
+    int je = j + 1;
+    while (je < ce && pItem[je] == item) je++;
+    {
+      float* prow = md.Wy + (size_t)item * ldL;
+      float* arow = md.Wy_acc ? md.Wy_acc + (size_t)item * ldL : nullptr;
+      float* vrow = md.Wy_vel ? md.Wy_vel + (size_t)item * ldL : nullptr;
+      for (int c4 = lane; c4 < ldL / 4; c4 += 32) {
+        const float4 p0 = ld4(prow + c4 * 4);
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), v0 = a0, al = a0, vl = a0;
+        if (ada) a0 = ld4(arow + c4 * 4);
+        if (mom) v0 = ld4(vrow + c4 * 4);
+        float4 ps = p0;
+        for (int jj = j; jj < je; jj++) {
+          const float4 g = ld4(md.DSY + (size_t)jj * ldL + c4 * 4);
+          float4 gs = g;
+          if (ada) {
+            al.x = a0.x + g.x * g.x; al.y = a0.y + g.y * g.y; al.z = a0.z + g.z * g.z; al.w = a0.w + g.w * g.w;
+            gs.x = __fdiv_rn(g.x, sqrtf(al.x + G4R_EPS_ADA)); gs.y = __fdiv_rn(g.y, sqrtf(al.y + G4R_EPS_ADA));
+            gs.z = __fdiv_rn(g.z, sqrtf(al.z + G4R_EPS_ADA)); gs.w = __fdiv_rn(g.w, sqrtf(al.w + G4R_EPS_ADA));
+          }
+          float4 d;
+          if (md.lmbd > 0.f) { d.x = md.lr * (gs.x + md.lmbd * p0.x); d.y = md.lr * (gs.y + md.lmbd * p0.y); d.z = md.lr * (gs.z + md.lmbd * p0.z); d.w = md.lr * (gs.w + md.lmbd * p0.w); }
+          else { d.x = md.lr * gs.x; d.y = md.lr * gs.y; d.z = md.lr * gs.z; d.w = md.lr * gs.w; }
+          if (mom) {
+            vl.x = md.mom * v0.x - d.x; vl.y = md.mom * v0.y - d.y; vl.z = md.mom * v0.z - d.z; vl.w = md.mom * v0.w - d.w;
+            ps.x += vl.x; ps.y += vl.y; ps.z += vl.z; ps.w += vl.w;
+          } else { ps.x -= d.x; ps.y -= d.y; ps.z -= d.z; ps.w -= d.w; }
+        }
+        st4(prow + c4 * 4, ps);
+        if (ada) st4(arow + c4 * 4, al);
+        if (mom) st4(vrow + c4 * 4, vl);
+      }
+    }
+    if (lane == 0) {   // By (gru4rec.py:486-489)
+      const float p0 = md.By[item];
+      float a0 = ada ? md.By_acc[item] : 0.f, v0 = mom ? md.By_vel[item] : 0.f, al = 0.f, vl = 0.f, ps = p0;
+      for (int jj = j; jj < je; jj++) {
+        const float g = md.DBY[jj];
+        float gs = g;
+        if (ada) { al = a0 + g * g; gs = __fdiv_rn(g, sqrtf(al + G4R_EPS_ADA)); }
+        const float d = md.lmbd > 0.f ? md.lr * (gs + md.lmbd * p0) : md.lr * gs;
+        if (mom) { vl = md.mom * v0 - d; ps += vl; } else ps -= d;
+      }
+      md.By[item] = ps;
+      if (ada) md.By_acc[item] = al;
+      if (mom) md.By_vel[item] = vl;
+    }
+  }
+}
+__host__ __device__ inline size_t lossgrad_smem_bytes(int Bld) { return (size_t)(SC_TB * SC_LDS + SC_CT * SC_LDS + SC_CT * Bld + 32) * sizeof(float); }
+
+// ------------------------------------------------------------------------------------------------
+// phase B1: elementwise part of the GRU backward: dh, dz, dh~, da_h, da_z
+// ------------------------------------------------------------------------------------------------
+__device__ void phase_b1(const ModelDev& md, int li, int s, int cta, int ncta) {
+  const LayerDev& ly = md.layer[li];
+  const int M = md.wM[s];
+  const int L = ly.L, ldL = ly.ldL;
+  const bool last = (li == md.n_layers - 1);
+  const int* cbeg = md.pCbeg + (size_t)s * (md.NCH + 1);
+  const uint32_t gstep = md.wG[s];
+  const float retain = 1.0f - md.p_drop_h;
+  for (int i = cta * blockDim.x + threadIdx.x; i < M * L; i += ncta * blockDim.x) {
+    const int b = i / L, c = i % L;
+    float dy;
+    if (last) {
+      dy = 0.f;
+      for (int ch = 0; ch < md.NCH; ch++)
+        if (cbeg[ch] < cbeg[ch + 1]) dy += md.part[((size_t)ch * md.B + b) * ldL + c];
+    } else dy = ly.dy[(size_t)b * ldL + c];
+    float dh = dy;
+    if (md.p_drop_h > 0.f) dh *= drop_scale(md.drop_seed, gstep, (uint32_t)li, (uint32_t)(b * L + c), retain);
+    const size_t o = (size_t)b * ldL + c;
+    const float ht = ly.ht[o], ho = ly.Hold[o], z = ly.z[o];
+    const float dz = dh * (ht - ho);
+    const float dht = dh * z;
+    const float dah = dht * act_der(md.hact, ly.ah[o], ht);
+    ly.dvec[(size_t)b * ly.ld3 + c] = dah;
+    ly.dvec[(size_t)b * ly.ld3 + 2 * L + c] = dz * z * (1.f - z);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// phase B2: d(H*r) = da_h @ Wh^T ; dr = d(H*r) * H ; da_r = dr r (1-r)
+// ------------------------------------------------------------------------------------------------
+__device__ void phase_b2(const ModelDev& md, int li, int s, int tile, float* sA, float* sB) {
+  const LayerDev& ly = md.layer[li];
+  const int M = md.wM[s];
+  const int L = ly.L;
+  const int ntn = (L + GB - 1) / GB;
+  const int tn = tile % ntn, tm = tile / ntn;
+  const int m0 = tm * GB, n0 = tn * GB;
+  if (m0 >= M) return;
+  float acc[GT][GT] = {};
+  auto fa = [&](int m, int k) -> float { int b = m0 + m; return b < M ? ly.dvec[(size_t)b * ly.ld3 + k] : 0.f; };
+  auto fb = [&](int k, int n) -> float { int c = n0 + n; return c < L ? ly.Wh[(size_t)c * ly.ldL + k] : 0.f; };   // Wh^T
+  gemm_tile_acc<GB, GB, GK, GT, GT, true, false>(acc, L, fa, fb, sA, sB);
+  const int tx = threadIdx.x % (GB / GT), ty = threadIdx.x / (GB / GT);
+#pragma unroll
+  for (int i = 0; i < GT; i++) {
+    const int b = m0 + ty * GT + i;
+    if (b >= M) continue;
+#pragma unroll
+    for (int j = 0; j < GT; j++) {
+      const int c = n0 + tx * GT + j;
+      if (c >= L) continue;
+      const size_t o = (size_t)b * ly.ldL + c;
+      const float r = ly.r[o];
+      ly.dvec[(size_t)b * ly.ld3 + L + c] = acc[i][j] * ly.Hold[o] * r * (1.f - r);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// phase B3: gradient wrt the layer input: din = dvec @ Wx^T (only layers with an input matmul).
+// layer > 0: becomes dy of the layer below.  layer 0 (embed/shared): dSx = din * embed-dropout mask.
+// ------------------------------------------------------------------------------------------------
+__device__ void phase_b3(const ModelDev& md, int li, int s, int tile, float* sA, float* sB) {
+  const LayerDev& ly = md.layer[li];
+  const int M = md.wM[s];
+  const int L = ly.L, K = 3 * L, IN = ly.in_dim;
+  const int ntn = (IN + GB - 1) / GB;
+  const int tn = tile % ntn, tm = tile / ntn;
+  const int m0 = tm * GB, n0 = tn * GB;
+  if (m0 >= M) return;
+  float acc[GT][GT] = {};
+  auto fa = [&](int m, int k) -> float { int b = m0 + m; return b < M ? ly.dvec[(size_t)b * ly.ld3 + k] : 0.f; };
+  auto fb = [&](int k, int n) -> float { int c = n0 + n; return c < IN ? ly.Wx[(size_t)c * ly.ld3 + k] : 0.f; };   // Wx^T
+  gemm_tile_acc<GB, GB, GK, GT, GT, true, false>(acc, K, fa, fb, sA, sB);
+  const int tx = threadIdx.x % (GB / GT), ty = threadIdx.x / (GB / GT);
+  const uint32_t gstep = md.wG[s];
+  const float retain = 1.0f - md.p_drop_e;
+#pragma unroll
+  for (int i = 0; i < GT; i++) {
+    const int b = m0 + ty * GT + i;
+    if (b >= M) continue;
+#pragma unroll
+    for (int j = 0; j < GT; j++) {
+      const int c = n0 + tx * GT + j;
+      if (c >= IN) continue;
+      float v = acc[i][j];
+      if (li > 0) md.layer[li - 1].dy[(size_t)b * md.layer[li - 1].ldL + c] = v;
+      else {
+        if (md.p_drop_e > 0.f) v *= drop_scale(md.drop_seed, gstep, G4R_STREAM_EMBED, (uint32_t)(b * IN + c), retain);
+        md.dSx[(size_t)b * md.ld_in0 + c] = v;
+      }
+    }
+  }
+}
+__device__ __forceinline__ int b3_tiles(const ModelDev& md, int li, int Bmax) {
+  return ((md.layer[li].in_dim + GB - 1) / GB) * ((Bmax + GB - 1) / GB);
+}
+
+// ------------------------------------------------------------------------------------------------
+// phase D: dense weight gradients fused with their Adagrad(+momentum) update (gru4rec.py:390-406)
+//   dWh = (H*r)^T da_h ; dWrz = H^T da_rz ; dWx = in^T dvec ; dBh = sum_b dvec
+// job space: [Wh tiles | Wrz tiles | Wx tiles | Bh blocks]
+// ------------------------------------------------------------------------------------------------
+struct DenseJobs { int nWh, nWrz, nWx, nBh; };
+__host__ __device__ inline DenseJobs dense_jobs(int L, int in_dim) {
+  DenseJobs j;
+  const int tl = (L + GB - 1) / GB;
+  j.nWh = tl * tl;
+  j.nWrz = tl * ((2 * L + GB - 1) / GB);
+  j.nWx = in_dim > 0 ? ((in_dim + GB - 1) / GB) * ((3 * L + GB - 1) / GB) : 0;
+  j.nBh = (3 * L + GEMM_THREADS - 1) / GEMM_THREADS;
+  return j;
+}
+__device__ void phase_dense(const ModelDev& md, int li, int s, int job, float* sA, float* sB) {
+  const LayerDev& ly = md.layer[li];
+  const int M = md.wM[s];
+  const int L = ly.L;
+  const DenseJobs dj = dense_jobs(L, ly.in_dim);
+  const int tx = threadIdx.x % (GB / GT), ty = threadIdx.x / (GB / GT);
+  float acc[GT][GT] = {};
+  if (job < dj.nWh) {
+    const int ntn = (L + GB - 1) / GB;
+    const int m0 = (job / ntn) * GB, n0 = (job % ntn) * GB;
+    auto fa = [&](int m, int k) -> float { int kk = m0 + m; return kk < L ? ly.Hold[(size_t)k * ly.ldL + kk] * ly.r[(size_t)k * ly.ldL + kk] : 0.f; };
+    auto fb = [&](int k, int n) -> float { int c = n0 + n; return c < L ? ly.dvec[(size_t)k * ly.ld3 + c] : 0.f; };
+    gemm_tile_acc<GB, GB, GK, GT, GT, false, true>(acc, M, fa, fb, sA, sB);
+#pragma unroll
+    for (int i = 0; i < GT; i++)
+#pragma unroll
+      for (int j = 0; j < GT; j++) {
+        const int rr = m0 + ty * GT + i, c = n0 + tx * GT + j;
+        if (rr < L && c < L) { const size_t o = (size_t)rr * ly.ldL + c; dense_update(md, ly.Wh + o, ly.Wh_acc ? ly.Wh_acc + o : nullptr, ly.Wh_vel ? ly.Wh_vel + o : nullptr, acc[i][j]); }
+      }
+    return;
+  }
+  job -= dj.nWh;
+  if (job < dj.nWrz) {
+    const int ntn = (2 * L + GB - 1) / GB;
+    const int m0 = (job / ntn) * GB, n0 = (job % ntn) * GB;
+    auto fa = [&](int m, int k) -> float { int kk = m0 + m; return kk < L ? ly.Hold[(size_t)k * ly.ldL + kk] : 0.f; };
+    auto fb = [&](int k, int n) -> float { int c = n0 + n; return c < 2 * L ? ly.dvec[(size_t)k * ly.ld3 + L + c] : 0.f; };
+    gemm_tile_acc<GB, GB, GK, GT, GT, false, true>(acc, M, fa, fb, sA, sB);
+#pragma unroll
+    for (int i = 0; i < GT; i++)
+#pragma unroll
+      for (int j = 0; j < GT; j++) {
+        const int rr = m0 + ty * GT + i, c = n0 + tx * GT + j;
+        if (rr < L && c < 2 * L) { const size_t o = (size_t)rr * ly.ld2 + c; dense_update(md, ly.Wrz + o, ly.Wrz_acc ? ly.Wrz_acc + o : nullptr, ly.Wrz_vel ? ly.Wrz_vel + o : nullptr, acc[i][j]); }
+      }
+    return;
+  }
+  job -= dj.nWrz;
+  if (job < dj.nWx) {
+    const int IN = ly.in_dim;
+    const int ntn = (3 * L + GB - 1) / GB;
+    const int m0 = (job / ntn) * GB, n0 = (job % ntn) * GB;
+    auto fa = [&](int m, int k) -> float { int kk = m0 + m; return kk < IN ? ly.in[(size_t)k * ly.ld_in + kk] : 0.f; };
+    auto fb = [&](int k, int n) -> float { int c = n0 + n; return c < 3 * L ? ly.dvec[(size_t)k * ly.ld3 + c] : 0.f; };
+    gemm_tile_acc<GB, GB, GK, GT, GT, false, true>(acc, M, fa, fb, sA, sB);
+#pragma unroll
+    for (int i = 0; i < GT; i++)
+#pragma unroll
+      for (int j = 0; j < GT; j++) {
+        const int rr = m0 + ty * GT + i, c = n0 + tx * GT + j;
+        if (rr < IN && c < 3 * L) { const size_t o = (size_t)rr * ly.ld3 + c; dense_update(md, ly.Wx + o, ly.Wx_acc ? ly.Wx_acc + o : nullptr, ly.Wx_vel ? ly.Wx_vel + o : nullptr, acc[i][j]); }
+      }
+    return;
+  }
+  job -= dj.nWx;
+  {
+    const int c = job * GEMM_THREADS + threadIdx.x;
+    if (c < 3 * L) {
+      float g = 0.f;
+      for (int b = 0; b < M; b++) g += ly.dvec[(size_t)b * ly.ld3 + c];
+      dense_update(md, ly.Bh + c, ly.Bh_acc ? ly.Bh_acc + c : nullptr, ly.Bh_vel ? ly.Bh_vel + c : nullptr, g);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// phase X: sparse update of the gathered INPUT rows (gru4rec.py:407-431 applied to Wx0[X] / E[X] / Wy[X]).
+// One CTA per duplicate group of X (chain through wXnext); members processed in position order.
+// ------------------------------------------------------------------------------------------------
+__device__ void phase_sparse_in(const ModelDev& md, int s, int b) {
+  const int M = md.wM[s];
+  if (b >= M) return;
+  const uint8_t xf = md.wXflag[(size_t)s * md.B + b];
+  if (!(xf & 1)) return;                      // not the first position of its group
+  const int item = md.wX[(size_t)s * md.B + b];
+  const int* xnext = md.wXnext + (size_t)s * md.B;
+  float *tab, *tacc, *tvel; const float* G; int ld, ldg;
+  if (md.mode == 0) { const LayerDev& l0 = md.layer[0]; tab = l0.Wx; tacc = l0.Wx_acc; tvel = l0.Wx_vel; G = l0.dvec; ld = l0.ld3; ldg = l0.ld3; }
+  else if (md.mode == 1) { tab = md.E; tacc = md.E_acc; tvel = md.E_vel; G = md.dSx; ld = md.ld_in0; ldg = md.ld_in0; }
+  else { tab = md.Wy; tacc = md.Wy_acc; tvel = md.Wy_vel; G = md.dSx; ld = md.ldL; ldg = md.ld_in0; }
+  const bool ada = md.adapt == G4R_ADAPT_ADAGRAD, mom = md.mom > 0.f;
+  const bool shared = md.mode == 2;
+  const bool write_state = !(shared && (xf & 2));     // shared: a later (Y / sample) occurrence owns acc / velocity
+  float* prow = tab + (size_t)item * ld;
+  for (int c4 = threadIdx.x; c4 < ld / 4; c4 += blockDim.x) {
+    const float4 pcur = ld4(prow + c4 * 4);
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), v0 = a0, al = a0, vl = a0, p0 = pcur;
+    if (shared) {
+      p0 = ld4(md.Sx + (size_t)b * ldg + c4 * 4);         // row value before the Wy update (sparam)
+      if (ada) a0 = ld4(md.snapAcc + (size_t)b * ldg + c4 * 4);
+      if (mom) v0 = ld4(md.snapVel + (size_t)b * ldg + c4 * 4);
+    } else {
+      if (ada) a0 = ld4(tacc + (size_t)item * ld + c4 * 4);
+      if (mom) v0 = ld4(tvel + (size_t)item * ld + c4 * 4);
+    }
+    float4 ps = pcur;
+    for (int bb = b; bb >= 0; bb = xnext[bb]) {
+      const float4 g = ld4(G + (size_t)bb * ldg + c4 * 4);
+      float4 gs = g;
+      if (ada) {
+        al.x = a0.x + g.x * g.x; al.y = a0.y + g.y * g.y; al.z = a0.z + g.z * g.z; al.w = a0.w + g.w * g.w;
+        gs.x = __fdiv_rn(g.x, sqrtf(al.x + G4R_EPS_ADA)); gs.y = __fdiv_rn(g.y, sqrtf(al.y + G4R_EPS_ADA));
+        gs.z = __fdiv_rn(g.z, sqrtf(al.z + G4R_EPS_ADA)); gs.w = __fdiv_rn(g.w, sqrtf(al.w + G4R_EPS_ADA));
+      }
+      float4 d;
+      if (md.lmbd > 0.f) { d.x = md.lr * (gs.x + md.lmbd * p0.x); d.y = md.lr * (gs.y + md.lmbd * p0.y); d.z = md.lr * (gs.z + md.lmbd * p0.z); d.w = md.lr * (gs.w + md.lmbd * p0.w); }
+      else { d.x = md.lr * gs.x; d.y = md.lr * gs.y; d.z = md.lr * gs.z; d.w = md.lr * gs.w; }
+      if (mom) {
+        vl.x = md.mom * v0.x - d.x; vl.y = md.mom * v0.y - d.y; vl.z = md.mom * v0.z - d.z; vl.w = md.mom * v0.w - d.w;
+        ps.x += vl.x; ps.y += vl.y; ps.z += vl.z; ps.w += vl.w;
+      } else { ps.x -= d.x; ps.y -= d.y; ps.z -= d.z; ps.w -= d.w; }
+    }
+    st4(prow + c4 * 4, ps);
+    if (write_state) {
+      if (ada) st4(tacc + (size_t)item * ld + c4 * 4, al);
+      if (mom) st4(tvel + (size_t)item * ld + c4 * 4, vl);
+    }
+  }
+}

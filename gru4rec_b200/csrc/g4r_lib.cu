@@ -1,0 +1,812 @@
+// g4r_lib.cu -- host side of libg4r.so: handle, workspace carving, the session-parallel schedule builder,
+// the per-step launch sequence, negative sampling, and the C ABI declared in include/g4r.h.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+#include "g4r_kernels.cuh"
+#include "g4r_misc.cuh"
+
+#define G4R_VERSION 100
+
+static thread_local std::string g_create_error;
+struct g4r_handle;
+static void eval_release(g4r_handle* h);
+
+struct TensorInfo { float* ptr; int64_t rows, cols, ld; };
+
+struct g4r_schedule {
+  int B = 0, mode = 0;
+  int64_t n_steps = 0, n_events = 0;
+  std::vector<int32_t> X, Y, slots, M;
+  std::vector<uint8_t> F;
+};
+
+struct g4r_handle {
+  g4r_config cfg;
+  ModelDev md;
+  std::string err;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  char* ws = nullptr; size_t ws_bytes = 0; bool own_ws = false;
+  size_t ws_off = 0;
+  std::map<std::string, TensorInfo> tensors;
+  int Bmax = 0, n_sm = 148;
+  int CAP = 0;
+  // window staging (pinned host) and device arrays (non-const views of md.w*)
+  int *hX = nullptr, *hY = nullptr, *hSlot = nullptr, *hM = nullptr, *hSti = nullptr; uint8_t* hF = nullptr; uint32_t* hG = nullptr;
+  float* hCost = nullptr;
+  int *dX = nullptr, *dY = nullptr, *dSlot = nullptr, *dM = nullptr, *dSti = nullptr, *dXnext = nullptr; uint8_t *dF = nullptr, *dXflag = nullptr; uint32_t* dG = nullptr;
+  int* dStepBase = nullptr;
+  // sampling
+  float *dP = nullptr, *dLogP0t = nullptr, *dLogP0s = nullptr, *dU = nullptr;
+  int* dST = nullptr; int gen_len = 0; int64_t sample_ptr = 0; bool have_store = false; bool have_cdf = false;
+  int32_t* dMrgState = nullptr; int n_streams = 0; bool mrg_init = false; int64_t mrg_rstate[6];
+  // evaluation hidden state
+  float* He[G4R_MAX_LAYERS] = {};
+  int* dRankCnt = nullptr; float* dTgt = nullptr;
+  // bookkeeping
+  uint32_t global_step = 0;
+  int win_steps = 0;
+  int64_t launches = 0;
+  int npow2 = 0;
+};
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return G4R_ERR_CUDA; } } while (0)
+#define FAIL(code, msg) do { h->err = (msg); return (code); } while (0)
+
+static inline int round4(int x) { return (x + 3) & ~3; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------
+// workspace layout: computed identically in a dry run (bytes) and for real (carving)
+// ------------------------------------------------------------------------------------------------
+struct Carver {
+  char* base; size_t off; bool dry;
+  template <class T> T* take(size_t n) {
+    off = align_up(off, 256);
+    T* p = dry ? nullptr : reinterpret_cast<T*>(base + off);
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+static int validate_config(const g4r_config& c, std::string& err) {
+  if (c.n_items <= 0 || c.n_layers <= 0 || c.n_layers > G4R_MAX_LAYERS || c.batch_size <= 0) { err = "invalid sizes"; return G4R_ERR_INVALID; }
+  for (int i = 0; i < c.n_layers; i++) if (c.layers[i] <= 0) { err = "invalid layer width"; return G4R_ERR_INVALID; }
+  if (c.adapt != G4R_ADAPT_ADAGRAD && c.adapt != G4R_ADAPT_NONE) { err = "adapt: only adagrad / None run on the device path"; return G4R_ERR_INVALID; }
+  if (c.hidden_act < G4R_ACT_LINEAR || c.hidden_act > G4R_ACT_SELU) { err = "hidden_act unsupported"; return G4R_ERR_INVALID; }
+  const bool elem = c.final_act >= G4R_ACT_LINEAR && c.final_act <= G4R_ACT_SELU;
+  bool ok = false;
+  if (c.loss == G4R_LOSS_XE && c.final_act == G4R_ACT_SOFTMAX) ok = true;
+  if (c.loss == G4R_LOSS_XE_LOGIT && c.final_act == G4R_ACT_SOFTMAX_LOGIT) ok = true;
+  if ((c.loss == G4R_LOSS_BPR_MAX || c.loss == G4R_LOSS_TOP1_MAX || c.loss == G4R_LOSS_BPR || c.loss == G4R_LOSS_TOP1) && elem) ok = true;
+  if (!ok) { err = "loss / final_act combination not implemented on the device path"; return G4R_ERR_INVALID; }
+  if (c.smoothing != 0.f) { err = "smoothing not implemented on the device path"; return G4R_ERR_INVALID; }
+  if (c.constrained_embedding && c.embedding) { /* reference: constrained wins (gru4rec.py:272) */ }
+  if (c.n_sample < 0) { err = "n_sample < 0"; return G4R_ERR_INVALID; }
+  return G4R_OK;
+}
+
+static int model_mode(const g4r_config& c) { return c.constrained_embedding ? 2 : (c.embedding > 0 ? 1 : 0); }
+
+static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
+  const int mode = model_mode(c);
+  const int nl = c.n_layers;
+  const int B = c.batch_size;
+  const int Be = c.eval_batch_size > 0 ? c.eval_batch_size : B;
+  const int Bmax = std::max(B, Be);
+  const int Llast = c.layers[nl - 1], ldL = round4(Llast);
+  const bool mom = c.momentum > 0.f;
+  const bool ada = c.adapt == G4R_ADAPT_ADAGRAD;
+  const int gen_len = (c.n_sample > 0 && c.sample_store > 0) ? c.sample_store / c.n_sample : 0;
+  const bool store = gen_len > 1;
+  const int S = store ? c.n_sample : 0;
+  const int NP = round4(B + S);
+  const int NCH = std::max(1, std::min(n_sm, (NP + 3) / 4));
+  const int CAP = c.max_resident_steps > 0 ? c.max_resident_steps : 2048;
+  ModelDev md; memset(&md, 0, sizeof(md));
+  md.n_items = c.n_items; md.n_layers = nl; md.B = B; md.Bld = round4(Bmax); md.S = S; md.mode = mode; md.L = Llast; md.ldL = ldL;
+  md.NP = NP; md.NCH = NCH; md.CAP = CAP; md.S_cfg = c.n_sample;
+  md.loss = c.loss; md.fact = {c.final_act, c.final_act_p1, c.final_act_p2}; md.hact = {c.hidden_act, c.hidden_act_p1, c.hidden_act_p2};
+  md.p_drop_h = c.dropout_p_hidden; md.p_drop_e = c.dropout_p_embed; md.lr = c.learning_rate; md.mom = c.momentum; md.lmbd = c.lmbd;
+  md.bpreg = c.bpreg; md.logq = c.logq; md.alpha = c.sample_alpha; md.adapt = c.adapt; md.drop_seed = c.dropout_seed;
+  md.in0_dim = mode == 2 ? Llast : (mode == 1 ? c.embedding : 0);
+  md.ld_in0 = round4(md.in0_dim);
+  auto reg = [&](const std::string& name, float* p, int64_t rows, int64_t cols, int64_t ld) { if (!cv.dry) h->tensors[name] = TensorInfo{p, rows, cols, ld}; };
+  auto table3 = [&](const std::string& name, int64_t rows, int64_t cols, float** p, float** a, float** v, int64_t ld_override = 0) {
+    const int64_t ld = ld_override > 0 ? ld_override : round4((int)cols);
+    *p = cv.take<float>((size_t)rows * ld); reg(name, *p, rows, cols, ld);
+    *a = ada ? cv.take<float>((size_t)rows * ld) : nullptr; if (ada) reg(name + ".acc", *a, rows, cols, ld);
+    *v = mom ? cv.take<float>((size_t)rows * ld) : nullptr; if (mom) reg(name + ".vel", *v, rows, cols, ld);
+  };
+  // item tables
+  table3("Wy", c.n_items, Llast, &md.Wy, &md.Wy_acc, &md.Wy_vel);
+  table3("By", c.n_items, 1, &md.By, &md.By_acc, &md.By_vel, 1);   // dense [I] vector
+  if (mode == 1) table3("E", c.n_items, c.embedding, &md.E, &md.E_acc, &md.E_vel);
+  for (int i = 0; i < nl; i++) {
+    LayerDev& ly = md.layer[i];
+    const int L = c.layers[i];
+    ly.L = L; ly.ldL = round4(L); ly.ld2 = round4(2 * L); ly.ld3 = round4(3 * L);
+    int in_rows;
+    if (i == 0) { in_rows = mode == 0 ? c.n_items : md.in0_dim; ly.in_dim = mode == 0 ? 0 : md.in0_dim; ly.ld_in = md.ld_in0; }
+    else { in_rows = c.layers[i - 1]; ly.in_dim = c.layers[i - 1]; ly.ld_in = round4(c.layers[i - 1]); }
+    const std::string si = std::to_string(i);
+    table3("Wx" + si, in_rows, 3 * L, &ly.Wx, &ly.Wx_acc, &ly.Wx_vel);
+    table3("Wh" + si, L, L, &ly.Wh, &ly.Wh_acc, &ly.Wh_vel);
+    table3("Wrz" + si, L, 2 * L, &ly.Wrz, &ly.Wrz_acc, &ly.Wrz_vel);
+    table3("Bh" + si, 1, 3 * L, &ly.Bh, &ly.Bh_acc, &ly.Bh_vel);
+    ly.H = cv.take<float>((size_t)B * ly.ldL); reg("H" + si, ly.H, B, L, ly.ldL);
+    float* he = cv.take<float>((size_t)Be * ly.ldL); if (!cv.dry) h->He[i] = he;
+    reg("He" + si, he, Be, L, ly.ldL);
+    ly.Hold = cv.take<float>((size_t)Bmax * ly.ldL); ly.r = cv.take<float>((size_t)Bmax * ly.ldL); ly.z = cv.take<float>((size_t)Bmax * ly.ldL);
+    ly.ah = cv.take<float>((size_t)Bmax * ly.ldL); ly.ht = cv.take<float>((size_t)Bmax * ly.ldL); ly.y = cv.take<float>((size_t)Bmax * ly.ldL);
+    ly.dvec = cv.take<float>((size_t)Bmax * ly.ld3); ly.dy = cv.take<float>((size_t)Bmax * ly.ldL);
+    reg("y" + si, ly.y, Bmax, L, ly.ldL); reg("dvec" + si, ly.dvec, Bmax, 3 * L, ly.ld3);
+  }
+  if (mode != 0) {
+    md.Sx = cv.take<float>((size_t)Bmax * md.ld_in0); md.in0 = cv.take<float>((size_t)Bmax * md.ld_in0); md.dSx = cv.take<float>((size_t)Bmax * md.ld_in0);
+    if (mode == 2) { md.snapAcc = cv.take<float>((size_t)Bmax * md.ld_in0); md.snapVel = cv.take<float>((size_t)Bmax * md.ld_in0); }
+    reg("dSx", md.dSx, Bmax, md.in0_dim, md.ld_in0);
+  }
+  for (int i = 0; i < nl; i++) md.layer[i].in = (i == 0) ? md.in0 : md.layer[i - 1].y;
+  // step scratch
+  md.O = cv.take<float>((size_t)NP * md.Bld);
+  md.DSY = cv.take<float>((size_t)NP * ldL); md.DBY = cv.take<float>((size_t)NP);
+  md.part = cv.take<float>((size_t)NCH * B * ldL);
+  md.stat = cv.take<float>((size_t)NCH * B * G4R_NSTAT);
+  md.RS = cv.take<float>((size_t)Bmax * G4R_NSTAT);
+  md.cost = cv.take<float>((size_t)CAP);
+  md.nanflag = cv.take<int>(4);
+  reg("O", md.O, NP, Bmax, md.Bld); reg("DSY", md.DSY, NP, Llast, ldL);
+  // schedule window + plans
+  int* dX = cv.take<int>((size_t)CAP * B); int* dY = cv.take<int>((size_t)CAP * B); int* dSlot = cv.take<int>((size_t)CAP * B);
+  int* dXnext = cv.take<int>((size_t)CAP * B);
+  uint8_t* dF = cv.take<uint8_t>((size_t)CAP * B); uint8_t* dXflag = cv.take<uint8_t>((size_t)CAP * B);
+  int* dM = cv.take<int>(CAP); int* dSti = cv.take<int>(CAP); uint32_t* dG = cv.take<uint32_t>(CAP);
+  md.pItem = cv.take<int>((size_t)CAP * NP); md.pPos = cv.take<int>((size_t)CAP * NP);
+  md.pTcol = cv.take<int>((size_t)CAP * B); md.pCbeg = cv.take<int>((size_t)CAP * (NCH + 1));
+  int* dStepBase = cv.take<int>(4);
+  // sampling
+  float* dP = cv.take<float>(c.n_items); float* dL0t = cv.take<float>(c.n_items); float* dL0s = cv.take<float>(c.n_items);
+  int* dST = store ? cv.take<int>((size_t)gen_len * c.n_sample) : nullptr;
+  float* dU = store ? cv.take<float>((size_t)gen_len * c.n_sample) : nullptr;
+  int32_t* dMrg = cv.take<int32_t>((size_t)15360 * 6);
+  // evaluation
+  int* dRank = cv.take<int>((size_t)Be * 4); float* dTgt = cv.take<float>(Be);
+  if (!cv.dry) {
+    md.wX = dX; md.wY = dY; md.wSlot = dSlot; md.wM = dM; md.wSti = dSti; md.wXnext = dXnext; md.wF = dF; md.wXflag = dXflag; md.wG = dG;
+    md.ST = dST; md.logP0t = dL0t; md.logP0s = dL0s;
+    h->md = md; h->Bmax = Bmax; h->CAP = CAP; h->gen_len = store ? gen_len : 0;
+    h->dX = dX; h->dY = dY; h->dSlot = dSlot; h->dM = dM; h->dSti = dSti; h->dXnext = dXnext; h->dF = dF; h->dXflag = dXflag; h->dG = dG;
+    h->dStepBase = dStepBase; h->dP = dP; h->dLogP0t = dL0t; h->dLogP0s = dL0s; h->dST = dST; h->dU = dU; h->dMrgState = dMrg;
+    h->dRankCnt = dRank; h->dTgt = dTgt;
+    h->npow2 = next_pow2(B + S);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels: one per phase (thin wrappers around the phase functions)
+// ------------------------------------------------------------------------------------------------
+#define STEP_IDX (base ? (*base + off) : off)
+__global__ void __launch_bounds__(256) k_gather_in(ModelDev md, const int* base, int off, int train) { phase_gather_in(md, STEP_IDX, train != 0, blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(GEMM_THREADS) k_f1(ModelDev md, const int* base, int off, int li, float* Hsrc) {
+  __shared__ float sA[GK * (GB + 1)], sB[GK * (GB + 1)];
+  phase_f1(md, li, STEP_IDX, Hsrc, blockIdx.x, sA, sB);
+}
+__global__ void __launch_bounds__(GEMM_THREADS) k_f2(ModelDev md, const int* base, int off, int li, float* Hsrc, int train) {
+  __shared__ float sA[GK * (GB + 1)], sB[GK * (GB + 1)];
+  phase_f2(md, li, STEP_IDX, Hsrc, train != 0, blockIdx.x, sA, sB);
+}
+__global__ void __launch_bounds__(SC_THREADS) k_score(ModelDev md, const int* base, int off) {
+  extern __shared__ __align__(16) float smem[];
+  phase_score(md, STEP_IDX, blockIdx.x, smem);
+}
+__global__ void __launch_bounds__(256) k_stats(ModelDev md, const int* base, int off) {
+  extern __shared__ __align__(16) float smem[];
+  phase_stats(md, STEP_IDX, smem);
+}
+__global__ void __launch_bounds__(SC_THREADS) k_lossgrad(ModelDev md, const int* base, int off) {
+  extern __shared__ __align__(16) float smem[];
+  phase_lossgrad(md, STEP_IDX, blockIdx.x, smem);
+}
+__global__ void __launch_bounds__(256) k_b1(ModelDev md, const int* base, int off, int li) { phase_b1(md, li, STEP_IDX, blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(GEMM_THREADS) k_b2(ModelDev md, const int* base, int off, int li) {
+  __shared__ float sA[GK * (GB + 1)], sB[GK * (GB + 1)];
+  phase_b2(md, li, STEP_IDX, blockIdx.x, sA, sB);
+}
+__global__ void __launch_bounds__(GEMM_THREADS) k_b3(ModelDev md, const int* base, int off, int li) {
+  __shared__ float sA[GK * (GB + 1)], sB[GK * (GB + 1)];
+  phase_b3(md, li, STEP_IDX, blockIdx.x, sA, sB);
+}
+__global__ void __launch_bounds__(GEMM_THREADS) k_dense(ModelDev md, const int* base, int off, int li) {
+  __shared__ float sA[GK * (GB + 1)], sB[GK * (GB + 1)];
+  phase_dense(md, li, STEP_IDX, blockIdx.x, sA, sB);
+}
+__global__ void __launch_bounds__(128) k_sparse_in(ModelDev md, const int* base, int off) { phase_sparse_in(md, STEP_IDX, blockIdx.x); }
+__global__ void k_advance(int* base, int n) { if (threadIdx.x == 0 && blockIdx.x == 0) *base += n; }
+
+static int tiles2(int cols, int rows) { return ((cols + GB - 1) / GB) * ((rows + GB - 1) / GB); }
+
+// enqueue the kernels of one training step (window-relative index = *base + off when base != nullptr)
+static int enqueue_train_step(g4r_handle* h, const int* base, int off) {
+  const ModelDev& md = h->md;
+  cudaStream_t st = h->stream;
+  const int B = md.B;
+  if (md.mode != 0) { k_gather_in<<<std::max(1, (B + 7) / 8), 256, 0, st>>>(md, base, off, 1); h->launches++; }
+  for (int li = 0; li < md.n_layers; li++) {
+    const LayerDev& ly = md.layer[li];
+    k_f1<<<tiles2(2 * ly.L, B), GEMM_THREADS, 0, st>>>(md, base, off, li, ly.H);
+    k_f2<<<tiles2(ly.L, B), GEMM_THREADS, 0, st>>>(md, base, off, li, ly.H, 1);
+    h->launches += 2;
+  }
+  k_score<<<md.NCH, SC_THREADS, score_smem_bytes(h->Bmax), st>>>(md, base, off);
+  k_stats<<<1, 256, (size_t)(h->Bmax + 32) * sizeof(float), st>>>(md, base, off);
+  k_lossgrad<<<md.NCH, SC_THREADS, lossgrad_smem_bytes(md.Bld), st>>>(md, base, off);
+  h->launches += 3;
+  for (int li = md.n_layers - 1; li >= 0; li--) {
+    const LayerDev& ly = md.layer[li];
+    k_b1<<<std::max(1, std::min(h->n_sm, (B * ly.L + 255) / 256)), 256, 0, st>>>(md, base, off, li);
+    k_b2<<<tiles2(ly.L, B), GEMM_THREADS, 0, st>>>(md, base, off, li);
+    h->launches += 2;
+    if (ly.in_dim > 0) { k_b3<<<tiles2(ly.in_dim, B), GEMM_THREADS, 0, st>>>(md, base, off, li); h->launches++; }
+    const DenseJobs dj = dense_jobs(ly.L, ly.in_dim);
+    k_dense<<<dj.nWh + dj.nWrz + dj.nWx + dj.nBh, GEMM_THREADS, 0, st>>>(md, base, off, li);
+    h->launches++;
+  }
+  k_sparse_in<<<B, 128, 0, st>>>(md, base, off);
+  h->launches++;
+  return G4R_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: lifecycle
+// ------------------------------------------------------------------------------------------------
+extern "C" int g4r_version(void) { return G4R_VERSION; }
+
+extern "C" const char* g4r_last_error(const g4r_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int g4r_workspace_bytes(const g4r_config* cfg, size_t* bytes) {
+  if (!cfg || !bytes) return G4R_ERR_INVALID;
+  std::string err;
+  int rc = validate_config(*cfg, err);
+  if (rc) { g_create_error = err; return rc; }
+  int n_sm = 148;
+  int dev_count = 0;
+  if (cudaGetDeviceCount(&dev_count) == cudaSuccess && dev_count > cfg->device) {
+    cudaDeviceProp p; if (cudaGetDeviceProperties(&p, cfg->device) == cudaSuccess) n_sm = p.multiProcessorCount;
+  }
+  Carver cv{nullptr, 0, true};
+  layout(*cfg, cv, nullptr, n_sm);
+  *bytes = align_up(cv.off, 256) + 256;
+  return G4R_OK;
+}
+
+extern "C" int g4r_destroy(g4r_handle* h) {
+  if (!h) return G4R_OK;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  eval_release(h);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->hX) cudaFreeHost(h->hX);
+  if (h->hY) cudaFreeHost(h->hY);
+  if (h->hSlot) cudaFreeHost(h->hSlot);
+  if (h->hM) cudaFreeHost(h->hM);
+  if (h->hSti) cudaFreeHost(h->hSti);
+  if (h->hF) cudaFreeHost(h->hF);
+  if (h->hG) cudaFreeHost(h->hG);
+  if (h->hCost) cudaFreeHost(h->hCost);
+  if (h->own_ws && h->ws) cudaFree(h->ws);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return G4R_OK;
+}
+
+extern "C" int g4r_create(const g4r_config* cfg, void* device_workspace, size_t workspace_bytes, g4r_handle** out) {
+  if (!cfg || !out) { g_create_error = "null argument"; return G4R_ERR_INVALID; }
+  std::string err;
+  int rc = validate_config(*cfg, err);
+  if (rc) { g_create_error = err; return rc; }
+  int dev_count = 0;
+  cudaError_t ce = cudaGetDeviceCount(&dev_count);
+  if (ce != cudaSuccess || dev_count <= cfg->device) {
+    g_create_error = "no CUDA device available: libg4r has no CPU path";
+    return G4R_ERR_CUDA;
+  }
+  g4r_handle* h = new g4r_handle();
+  h->cfg = *cfg;
+  auto bail = [&](int code, const std::string& m) { g_create_error = m; g4r_destroy(h); return code; };
+  if (cudaSetDevice(cfg->device) != cudaSuccess) return bail(G4R_ERR_CUDA, "cudaSetDevice failed");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return bail(G4R_ERR_CUDA, "cudaGetDeviceProperties failed");
+  h->n_sm = prop.multiProcessorCount;
+  size_t need = 0;
+  { Carver cv{nullptr, 0, true}; layout(*cfg, cv, nullptr, h->n_sm); need = align_up(cv.off, 256) + 256; }
+  if (device_workspace) {
+    if (workspace_bytes < need) return bail(G4R_ERR_INVALID, "workspace too small");
+    h->ws = (char*)device_workspace; h->own_ws = false;
+  } else {
+    if (cudaMalloc(&h->ws, need) != cudaSuccess) return bail(G4R_ERR_CUDA, "cudaMalloc of workspace failed");
+    h->own_ws = true;
+  }
+  h->ws_bytes = need;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(G4R_ERR_CUDA, "stream create failed");
+  cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
+  if (cudaMemsetAsync(h->ws, 0, need, h->stream) != cudaSuccess) return bail(G4R_ERR_CUDA, "memset failed");
+  // 256-byte align the carve base
+  char* base = (char*)align_up((size_t)h->ws, 256);
+  Carver cv{base, 0, false};
+  layout(*cfg, cv, h, h->n_sm);
+  const int B = cfg->batch_size, CAP = h->CAP;
+  bool ok = true;
+  ok &= cudaMallocHost(&h->hX, (size_t)CAP * B * sizeof(int)) == cudaSuccess;
+  ok &= cudaMallocHost(&h->hY, (size_t)CAP * B * sizeof(int)) == cudaSuccess;
+  ok &= cudaMallocHost(&h->hSlot, (size_t)CAP * B * sizeof(int)) == cudaSuccess;
+  ok &= cudaMallocHost(&h->hF, (size_t)CAP * B) == cudaSuccess;
+  ok &= cudaMallocHost(&h->hM, (size_t)CAP * sizeof(int)) == cudaSuccess;
+  ok &= cudaMallocHost(&h->hSti, (size_t)CAP * sizeof(int)) == cudaSuccess;
+  ok &= cudaMallocHost(&h->hG, (size_t)CAP * sizeof(uint32_t)) == cudaSuccess;
+  ok &= cudaMallocHost(&h->hCost, (size_t)CAP * sizeof(float)) == cudaSuccess;
+  if (!ok) return bail(G4R_ERR_CUDA, "pinned host allocation failed");
+  // opt in to large dynamic shared memory where needed
+  cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)score_smem_bytes(h->Bmax));
+  cudaFuncSetAttribute(k_lossgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lossgrad_smem_bytes(h->md.Bld));
+  cudaFuncSetAttribute(k_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)h->npow2 * 8 + 1024));
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess) return bail(G4R_ERR_CUDA, "init sync failed");
+  *out = h;
+  return G4R_OK;
+}
+
+extern "C" void* g4r_stream(g4r_handle* h) { return h ? (void*)h->stream : nullptr; }
+extern "C" int64_t g4r_kernel_launches(const g4r_handle* h) { return h ? h->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// tensors
+// ------------------------------------------------------------------------------------------------
+static TensorInfo* find_tensor(g4r_handle* h, const char* name) {
+  auto it = h->tensors.find(name ? name : "");
+  return it == h->tensors.end() ? nullptr : &it->second;
+}
+extern "C" int g4r_tensor_shape(g4r_handle* h, const char* name, int64_t* rows, int64_t* cols) {
+  if (!h) return G4R_ERR_INVALID;
+  TensorInfo* t = find_tensor(h, name);
+  if (!t) FAIL(G4R_ERR_INVALID, std::string("unknown tensor ") + (name ? name : "(null)"));
+  if (rows) *rows = t->rows;
+  if (cols) *cols = t->cols;
+  return G4R_OK;
+}
+extern "C" int g4r_set_tensor(g4r_handle* h, const char* name, const float* host, int64_t rows, int64_t cols) {
+  if (!h || !host) return G4R_ERR_INVALID;
+  TensorInfo* t = find_tensor(h, name);
+  if (!t) FAIL(G4R_ERR_INVALID, std::string("unknown tensor ") + (name ? name : "(null)"));
+  if (rows != t->rows || cols != t->cols) FAIL(G4R_ERR_INVALID, std::string("shape mismatch for ") + name);
+  cudaSetDevice(h->cfg.device);
+  CK(cudaMemcpy2DAsync(t->ptr, t->ld * sizeof(float), host, cols * sizeof(float), cols * sizeof(float), rows, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return G4R_OK;
+}
+extern "C" int g4r_get_tensor(g4r_handle* h, const char* name, float* host, int64_t rows, int64_t cols) {
+  if (!h || !host) return G4R_ERR_INVALID;
+  TensorInfo* t = find_tensor(h, name);
+  if (!t) FAIL(G4R_ERR_INVALID, std::string("unknown tensor ") + (name ? name : "(null)"));
+  if (rows != t->rows || cols != t->cols) FAIL(G4R_ERR_INVALID, std::string("shape mismatch for ") + name);
+  cudaSetDevice(h->cfg.device);
+  CK(cudaMemcpy2DAsync(host, cols * sizeof(float), t->ptr, t->ld * sizeof(float), cols * sizeof(float), rows, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return G4R_OK;
+}
+extern "C" int g4r_reset_hidden(g4r_handle* h) {
+  if (!h) return G4R_ERR_INVALID;
+  cudaSetDevice(h->cfg.device);
+  for (int i = 0; i < h->md.n_layers; i++) CK(cudaMemsetAsync(h->md.layer[i].H, 0, (size_t)h->md.B * h->md.layer[i].ldL * sizeof(float), h->stream));
+  return G4R_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// negative sampling
+// ------------------------------------------------------------------------------------------------
+extern "C" int g4r_set_sampling_cdf(g4r_handle* h, const float* P, int64_t n) {
+  if (!h || !P) return G4R_ERR_INVALID;
+  if (n != h->cfg.n_items) FAIL(G4R_ERR_INVALID, "cdf length != n_items");
+  cudaSetDevice(h->cfg.device);
+  CK(cudaMemcpyAsync(h->dP, P, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->have_cdf = true;
+  return G4R_OK;
+}
+extern "C" int g4r_set_logq_support(g4r_handle* h, const float* P0, int64_t n) {
+  if (!h || !P0) return G4R_ERR_INVALID;
+  if (n != h->cfg.n_items) FAIL(G4R_ERR_INVALID, "support length != n_items");
+  // gru4rec.py:495: logq * log(concat(P0[targets], P0[samples] ** sample_alpha)), float32 arithmetic
+  std::vector<float> lt(n), ls(n);
+  for (int64_t i = 0; i < n; i++) {
+    lt[i] = h->cfg.logq * logf(P0[i]);
+    ls[i] = h->cfg.logq * logf(powf(P0[i], h->cfg.sample_alpha));
+  }
+  cudaSetDevice(h->cfg.device);
+  CK(cudaMemcpyAsync(h->dLogP0t, lt.data(), n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->dLogP0s, ls.data(), n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return G4R_OK;
+}
+extern "C" int g4r_sample_store_rows(g4r_handle* h) { return h ? h->gen_len : 0; }
+extern "C" int g4r_set_sample_pointer(g4r_handle* h, int64_t p) { if (!h) return G4R_ERR_INVALID; h->sample_ptr = p; return G4R_OK; }
+extern "C" int64_t g4r_get_sample_pointer(g4r_handle* h) { return h ? h->sample_ptr : -1; }
+
+static void mrg_host_init(g4r_handle* h);
+
+static int launch_search_store(g4r_handle* h) {
+  const int64_t n = (int64_t)h->gen_len * h->cfg.n_sample;
+  k_searchsorted<int><<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->dP, h->cfg.n_items, h->dU, n, h->dST);
+  h->launches++;
+  CK(cudaGetLastError());
+  h->sample_ptr = 0; h->have_store = true;
+  return G4R_OK;
+}
+
+extern "C" int g4r_generate_samples(g4r_handle* h) {
+  if (!h) return G4R_ERR_INVALID;
+  if (h->gen_len <= 0) FAIL(G4R_ERR_STATE, "no sample store configured");
+  if (!h->have_cdf) FAIL(G4R_ERR_STATE, "sampling cdf not set");
+  cudaSetDevice(h->cfg.device);
+  const int64_t n = (int64_t)h->gen_len * h->cfg.n_sample;
+  if (!h->mrg_init) { mrg_host_init(h); }
+  // Each uniform() call takes a block of substreams once (graph construction); the compiled function then keeps
+  // advancing the same streams (rstate is a shared-variable update) -- SURVEY Appendix B.
+  k_mrg_uniform<<<(h->n_streams + 127) / 128, 128, 0, h->stream>>>(h->dMrgState, h->n_streams, h->dU, n);
+  h->launches++;
+  CK(cudaGetLastError());
+  return launch_search_store(h);
+}
+extern "C" int g4r_mrg_uniform(g4r_handle* h, float* out, int64_t n) {
+  if (!h || !out) return G4R_ERR_INVALID;
+  if (h->gen_len <= 0 || n > (int64_t)h->gen_len * h->cfg.n_sample) FAIL(G4R_ERR_INVALID, "n exceeds uniform scratch");
+  cudaSetDevice(h->cfg.device);
+  if (!h->mrg_init) mrg_host_init(h);
+  k_mrg_uniform<<<(h->n_streams + 127) / 128, 128, 0, h->stream>>>(h->dMrgState, h->n_streams, h->dU, n);
+  h->launches++;
+  CK(cudaMemcpyAsync(out, h->dU, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return G4R_OK;
+}
+extern "C" int g4r_generate_samples_from_uniform(g4r_handle* h, const float* u, int64_t n) {
+  if (!h || !u) return G4R_ERR_INVALID;
+  if (h->gen_len <= 0) FAIL(G4R_ERR_STATE, "no sample store configured");
+  if (!h->have_cdf) FAIL(G4R_ERR_STATE, "sampling cdf not set");
+  if (n != (int64_t)h->gen_len * h->cfg.n_sample) FAIL(G4R_ERR_INVALID, "uniform count != generate_length * n_sample");
+  cudaSetDevice(h->cfg.device);
+  CK(cudaMemcpyAsync(h->dU, u, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  return launch_search_store(h);
+}
+extern "C" int g4r_set_sample_store(g4r_handle* h, const int64_t* st, int64_t rows) {
+  if (!h || !st) return G4R_ERR_INVALID;
+  if (h->gen_len <= 0 || rows != h->gen_len) FAIL(G4R_ERR_INVALID, "rows != generate_length");
+  const int64_t n = rows * h->cfg.n_sample;
+  std::vector<int> tmp(n);
+  for (int64_t i = 0; i < n; i++) {
+    if (st[i] < 0 || st[i] >= h->cfg.n_items) FAIL(G4R_ERR_INDEX, "Index out of bounds");
+    tmp[i] = (int)st[i];
+  }
+  cudaSetDevice(h->cfg.device);
+  CK(cudaMemcpyAsync(h->dST, tmp.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->sample_ptr = 0; h->have_store = true;
+  return G4R_OK;
+}
+extern "C" int g4r_get_sample_store(g4r_handle* h, int64_t* st, int64_t rows) {
+  if (!h || !st) return G4R_ERR_INVALID;
+  if (h->gen_len <= 0 || rows != h->gen_len) FAIL(G4R_ERR_INVALID, "rows != generate_length");
+  const int64_t n = rows * h->cfg.n_sample;
+  std::vector<int> tmp(n);
+  cudaSetDevice(h->cfg.device);
+  CK(cudaMemcpyAsync(tmp.data(), h->dST, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int64_t i = 0; i < n; i++) st[i] = tmp[i];
+  return G4R_OK;
+}
+
+// ---- MRG31k3p substream set-up on the host (theano.sandbox.rng_mrg restatement) ----
+static const int64_t MRG_M1 = 2147483647LL, MRG_M2 = 2147462579LL;
+static const int64_t A1p72[3][3] = {{1516919229, 758510237, 499121365}, {1884998244, 1516919229, 335398200}, {601897748, 1884998244, 358115744}};
+static const int64_t A2p72[3][3] = {{1228857673, 1496414766, 954677935}, {1133297478, 1407477216, 1496414766}, {2002613992, 1639496704, 1407477216}};
+static const int64_t A1p134[3][3] = {{1702500920, 1849582496, 1656874625}, {828554832, 1702500920, 1512419905}, {1143731069, 828554832, 102237247}};
+static const int64_t A2p134[3][3] = {{796789021, 1464208080, 607337906}, {1241679051, 1431130166, 1464208080}, {1401213391, 1178684362, 1431130166}};
+static void matvec_mod(const int64_t A[3][3], const int64_t* v, int64_t m, int64_t* o) {
+  for (int i = 0; i < 3; i++) {
+    unsigned __int128 s = 0;
+    for (int j = 0; j < 3; j++) s += (unsigned __int128)A[i][j] * (unsigned __int128)v[j];
+    o[i] = (int64_t)(s % (unsigned __int128)m);
+  }
+}
+static void mrg_ff(const int64_t* s, const int64_t A1[3][3], const int64_t A2[3][3], int64_t* o) {
+  matvec_mod(A1, s, MRG_M1, o); matvec_mod(A2, s + 3, MRG_M2, o + 3);
+}
+static void mrg_host_init(g4r_handle* h) {
+  const int64_t n = (int64_t)h->gen_len * h->cfg.n_sample;
+  int64_t r = n; if (r > 6) r = r / 6;
+  h->n_streams = (int)std::min<int64_t>(r, 15360);
+  for (int i = 0; i < 6; i++) h->mrg_rstate[i] = h->cfg.mrg_seed ? h->cfg.mrg_seed : 12345;
+  std::vector<int32_t> st((size_t)h->n_streams * 6);
+  int64_t cur[6]; memcpy(cur, h->mrg_rstate, sizeof(cur));
+  for (int i = 0; i < h->n_streams; i++) {
+    for (int k = 0; k < 6; k++) st[(size_t)i * 6 + k] = (int32_t)cur[k];
+    int64_t nx[6]; mrg_ff(cur, A1p72, A2p72, nx); memcpy(cur, nx, sizeof(cur));
+  }
+  int64_t nb[6]; mrg_ff(h->mrg_rstate, A1p134, A2p134, nb); memcpy(h->mrg_rstate, nb, sizeof(nb));
+  cudaMemcpyAsync(h->dMrgState, st.data(), st.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream);
+  cudaStreamSynchronize(h->stream);
+  h->mrg_init = true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone custom ops
+// ------------------------------------------------------------------------------------------------
+extern "C" int g4r_searchsorted(g4r_handle* h, const float* d, int64_t n_d, const float* x, int64_t n_x, int64_t* y) {
+  if (!h || !d || !x || !y || n_d <= 0 || n_x < 0) return G4R_ERR_INVALID;
+  if (n_x == 0) return G4R_OK;
+  cudaSetDevice(h->cfg.device);
+  float *dd = nullptr, *dx = nullptr; long long* dy = nullptr;
+  CK(cudaMalloc(&dd, n_d * sizeof(float))); CK(cudaMalloc(&dx, n_x * sizeof(float))); CK(cudaMalloc(&dy, n_x * sizeof(long long)));
+  CK(cudaMemcpyAsync(dd, d, n_d * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(dx, x, n_x * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  k_searchsorted<long long><<<(unsigned)((n_x + 255) / 256), 256, 0, h->stream>>>(dd, (int)n_d, dx, n_x, dy);
+  h->launches++;
+  CK(cudaMemcpyAsync(y, dy, n_x * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(dd); cudaFree(dx); cudaFree(dy);
+  return G4R_OK;
+}
+extern "C" int g4r_gather_rows(g4r_handle* h, const float* table, int64_t rows, int64_t cols, const int64_t* idx, int64_t n_idx, float* out) {
+  if (!h || !table || !idx || !out || rows <= 0 || cols <= 0 || n_idx < 0) return G4R_ERR_INVALID;
+  if (n_idx == 0) return G4R_OK;
+  cudaSetDevice(h->cfg.device);
+  float *dt = nullptr, *dout = nullptr; long long* di = nullptr; int* derr = nullptr;
+  CK(cudaMalloc(&dt, rows * cols * sizeof(float))); CK(cudaMalloc(&dout, n_idx * cols * sizeof(float)));
+  CK(cudaMalloc(&di, n_idx * sizeof(long long))); CK(cudaMalloc(&derr, sizeof(int)));
+  CK(cudaMemcpyAsync(dt, table, rows * cols * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(di, idx, n_idx * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(derr, 0, sizeof(int), h->stream));
+  k_gather_rows<<<(unsigned)std::min<int64_t>(n_idx, 148 * 8), 128, 0, h->stream>>>(dt, rows, cols, di, n_idx, dout, derr);
+  h->launches++;
+  int herr = 0;
+  CK(cudaMemcpyAsync(out, dout, n_idx * cols * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(&herr, derr, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(dt); cudaFree(dout); cudaFree(di); cudaFree(derr);
+  if (herr) FAIL(G4R_ERR_INDEX, "Index out of bounds");
+  return G4R_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// schedule builder (gru4rec.py:594-651; evaluation.py:90-139), host C++
+// ------------------------------------------------------------------------------------------------
+extern "C" int g4r_schedule_build(const int64_t* data_items, int64_t n_events, const int32_t* offs, int64_t n_sessions,
+                                  const int64_t* order, int32_t B, int32_t n_sample, int32_t mode, g4r_schedule** out) {
+  if (!data_items || !offs || !out || B <= 0 || n_sessions < 0) return G4R_ERR_INVALID;
+  if (n_sessions < B) { g_create_error = "index out of bounds: fewer sessions than batch_size (reference: IndexError at gru4rec.py:596)"; return G4R_ERR_INDEX; }
+  g4r_schedule* s = new g4r_schedule();
+  s->B = B; s->mode = mode;
+  auto sess_of = [&](int64_t it) -> int64_t { return order ? order[it] : it; };
+  std::vector<int64_t> iters(B), start(B), end(B);
+  std::vector<int32_t> slots(B);
+  std::vector<uint8_t> zero_next(B, 0);
+  for (int b = 0; b < B; b++) { iters[b] = b; start[b] = offs[sess_of(b)]; end[b] = offs[sess_of(b) + 1]; slots[b] = b; }
+  int64_t maxiter = B - 1;
+  int M = B;
+  while (true) {
+    int64_t minlen = end[0] - start[0];
+    for (int b = 1; b < M; b++) minlen = std::min(minlen, end[b] - start[b]);
+    for (int64_t i = 0; i + 1 < minlen; i++) {
+      const size_t base = s->X.size();
+      s->X.resize(base + B, -1); s->Y.resize(base + B, -1); s->slots.resize(base + B, 0); s->F.resize(base + B, 0);
+      for (int b = 0; b < M; b++) {
+        const int64_t p = start[b] + i;
+        if (p + 1 >= n_events) { delete s; g_create_error = "schedule: event index out of range"; return G4R_ERR_INDEX; }
+        s->X[base + b] = (int32_t)data_items[p];
+        s->Y[base + b] = (int32_t)data_items[p + 1];
+        s->slots[base + b] = slots[b];
+        uint8_t f = 0;
+        if (mode == 0) { if (p + 1 == end[b] - 1) f |= 1; }
+        else if (zero_next[b]) { f |= 2; }
+        s->F[base + b] = f;
+      }
+      if (mode == 1) std::fill(zero_next.begin(), zero_next.begin() + M, 0);
+      s->M.push_back(M);
+      s->n_events += M;
+    }
+    std::vector<uint8_t> fin(M), valid(M);
+    int n_finished = 0;
+    for (int b = 0; b < M; b++) { start[b] += minlen - 1; fin[b] = (end[b] - start[b] <= 1); }
+    for (int b = 0; b < M; b++) if (fin[b]) { n_finished++; iters[b] = maxiter + n_finished; }
+    maxiter += n_finished;
+    int n_valid = 0;
+    for (int b = 0; b < M; b++) { valid[b] = iters[b] < n_sessions; n_valid += valid[b]; }
+    if (n_valid == 0 || (mode == 0 && n_valid < 2 && n_sample == 0)) break;
+    for (int b = 0; b < M; b++) if (fin[b] && valid[b]) {
+      const int64_t ss = sess_of(iters[b]);
+      start[b] = offs[ss]; end[b] = offs[ss + 1];
+      if (mode == 1) zero_next[b] = 1;
+    }
+    int w = 0;
+    for (int b = 0; b < M; b++) if (valid[b]) {
+      iters[w] = iters[b]; start[w] = start[b]; end[w] = end[b]; slots[w] = slots[b]; zero_next[w] = zero_next[b]; w++;
+    }
+    M = w;
+  }
+  s->n_steps = (int64_t)s->M.size();
+  *out = s;
+  return G4R_OK;
+}
+extern "C" int g4r_schedule_free(g4r_schedule* s) { delete s; return G4R_OK; }
+extern "C" int64_t g4r_schedule_steps(const g4r_schedule* s) { return s ? s->n_steps : 0; }
+extern "C" int64_t g4r_schedule_events(const g4r_schedule* s) { return s ? s->n_events : 0; }
+extern "C" int g4r_schedule_export(const g4r_schedule* s, int32_t* X, int32_t* Y, uint8_t* flags, int32_t* M, int32_t* slots) {
+  if (!s) return G4R_ERR_INVALID;
+  const size_t n = s->X.size();
+  if (X) memcpy(X, s->X.data(), n * sizeof(int32_t));
+  if (Y) memcpy(Y, s->Y.data(), n * sizeof(int32_t));
+  if (flags) memcpy(flags, s->F.data(), n);
+  if (slots) memcpy(slots, s->slots.data(), n * sizeof(int32_t));
+  if (M) memcpy(M, s->M.data(), s->M.size() * sizeof(int32_t));
+  return G4R_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// window upload + plan
+// ------------------------------------------------------------------------------------------------
+// copies steps [first, first+n) of the schedule into the pinned staging buffers; assigns sample-store rows
+// and global step counters; stops early at a sample-store wrap.  Returns the number of steps staged.
+static int64_t stage_window(g4r_handle* h, const g4r_schedule* s, int64_t first, int64_t n) {
+  const int B = h->md.B;
+  n = std::min<int64_t>(n, h->CAP);
+  const bool store = h->gen_len > 0;
+  if (store && h->sample_ptr >= h->gen_len) return 0;   // caller must regenerate first
+  if (store) n = std::min<int64_t>(n, h->gen_len - h->sample_ptr);
+  memcpy(h->hX, s->X.data() + first * B, (size_t)n * B * sizeof(int));
+  memcpy(h->hY, s->Y.data() + first * B, (size_t)n * B * sizeof(int));
+  memcpy(h->hSlot, s->slots.data() + first * B, (size_t)n * B * sizeof(int));
+  memcpy(h->hF, s->F.data() + first * B, (size_t)n * B);
+  memcpy(h->hM, s->M.data() + first, (size_t)n * sizeof(int));
+  for (int64_t i = 0; i < n; i++) {
+    h->hSti[i] = store ? (int)(h->sample_ptr + i) : -1;
+    h->hG[i] = h->global_step + (uint32_t)i;
+  }
+  return n;
+}
+
+static int validate_window(g4r_handle* h, int64_t n) {
+  const int B = h->md.B, I = h->md.n_items;
+  for (int64_t i = 0; i < n; i++) {
+    const int M = h->hM[i];
+    if (M <= 0 || M > B) FAIL(G4R_ERR_INVALID, "batch size out of range");
+    for (int b = 0; b < M; b++) {
+      const int x = h->hX[i * B + b], y = h->hY[i * B + b], sl = h->hSlot[i * B + b];
+      if (x < 0 || x >= I || y < 0 || y >= I) FAIL(G4R_ERR_INDEX, "Index out of bounds");
+      if (sl < 0 || sl >= B) FAIL(G4R_ERR_INDEX, "lane slot out of bounds");
+    }
+  }
+  return G4R_OK;
+}
+
+static int upload_window(g4r_handle* h, int64_t n) {
+  const int B = h->md.B;
+  int rc = validate_window(h, n);
+  if (rc) return rc;
+  if (h->gen_len > 0 && !h->have_store) FAIL(G4R_ERR_STATE, "sample store not generated");
+  cudaStream_t st = h->stream;
+  CK(cudaMemcpyAsync(h->dX, h->hX, (size_t)n * B * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->dY, h->hY, (size_t)n * B * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->dSlot, h->hSlot, (size_t)n * B * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->dF, h->hF, (size_t)n * B, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->dM, h->hM, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->dSti, h->hSti, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(h->dG, h->hG, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  k_plan<<<(unsigned)n, 256, (size_t)h->npow2 * 8 + 1024, st>>>(h->md, h->dXnext, h->dXflag, h->npow2);
+  h->launches++;
+  CK(cudaGetLastError());
+  h->win_steps = (int)n;
+  return G4R_OK;
+}
+
+static int run_window(g4r_handle* h, int64_t n) {
+  for (int64_t i = 0; i < n; i++) enqueue_train_step(h, nullptr, (int)i);
+  CK(cudaGetLastError());
+  if (h->gen_len > 0) h->sample_ptr += n;
+  h->global_step += (uint32_t)n;
+  return G4R_OK;
+}
+
+extern "C" int g4r_upload_steps(g4r_handle* h, const g4r_schedule* s, int64_t first, int64_t n) {
+  if (!h || !s) return G4R_ERR_INVALID;
+  if (s->B != h->md.B) FAIL(G4R_ERR_INVALID, "schedule batch size != model batch size");
+  if (first < 0 || n <= 0 || first + n > s->n_steps) FAIL(G4R_ERR_INVALID, "step range out of schedule");
+  if (n > h->CAP) FAIL(G4R_ERR_INVALID, "n exceeds the resident window capacity");
+  cudaSetDevice(h->cfg.device);
+  if (h->gen_len > 0 && h->sample_ptr + n > h->gen_len) FAIL(G4R_ERR_STATE, "window would wrap the sample store; regenerate or shorten");
+  const int64_t got = stage_window(h, s, first, n);
+  if (got != n) FAIL(G4R_ERR_STATE, "could not stage the window");
+  return upload_window(h, n);
+}
+
+extern "C" int g4r_run_uploaded(g4r_handle* h, float* cost_out, float* device_ms) {
+  if (!h) return G4R_ERR_INVALID;
+  if (h->win_steps <= 0) FAIL(G4R_ERR_STATE, "no uploaded window");
+  cudaSetDevice(h->cfg.device);
+  const int n = h->win_steps;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  int rc = run_window(h, n);
+  if (rc) return rc;
+  CK(cudaEventRecord(h->ev1, h->stream));
+  if (cost_out) CK(cudaMemcpyAsync(h->hCost, h->md.cost, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (cost_out) memcpy(cost_out, h->hCost, (size_t)n * sizeof(float));
+  if (device_ms) CK(cudaEventElapsedTime(device_ms, h->ev0, h->ev1));
+  // re-running the same window is allowed for benchmarking: undo the pointer advance only on request (not here)
+  return G4R_OK;
+}
+
+extern "C" int g4r_train_steps(g4r_handle* h, const g4r_schedule* s, int64_t first, int64_t n, float* cost_out, int64_t* nan_step) {
+  if (!h || !s) return G4R_ERR_INVALID;
+  if (s->B != h->md.B) FAIL(G4R_ERR_INVALID, "schedule batch size != model batch size");
+  if (first < 0 || n < 0 || first + n > s->n_steps) FAIL(G4R_ERR_INVALID, "step range out of schedule");
+  cudaSetDevice(h->cfg.device);
+  if (nan_step) *nan_step = -1;
+  int64_t done = 0;
+  while (done < n) {
+    if (h->gen_len > 0 && (!h->have_store || h->sample_ptr >= h->gen_len)) {   // gru4rec.py:618-621
+      int rc = g4r_generate_samples(h);
+      if (rc) return rc;
+    }
+    const int64_t w = stage_window(h, s, first + done, n - done);
+    if (w <= 0) FAIL(G4R_ERR_STATE, "empty window");
+    int rc = upload_window(h, w);
+    if (rc) return rc;
+    rc = run_window(h, w);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->hCost, h->md.cost, (size_t)w * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int64_t i = 0; i < w; i++) {
+      if (cost_out) cost_out[done + i] = h->hCost[i];
+      if (h->hCost[i] != h->hCost[i]) {
+        if (nan_step) *nan_step = first + done + i;
+        FAIL(G4R_ERR_NAN, "NaN error!");
+      }
+    }
+    done += w;
+  }
+  return G4R_OK;
+}
+
+extern "C" int g4r_train_step(g4r_handle* h, const int32_t* X, const int32_t* Y, int32_t M, const int8_t* R, float* cost) {
+  if (!h || !X || !Y) return G4R_ERR_INVALID;
+  const int B = h->md.B;
+  if (M <= 0 || M > B) FAIL(G4R_ERR_INVALID, "M out of range");
+  cudaSetDevice(h->cfg.device);
+  if (h->gen_len > 0 && (!h->have_store || h->sample_ptr >= h->gen_len)) {
+    int rc = g4r_generate_samples(h);
+    if (rc) return rc;
+  }
+  for (int b = 0; b < B; b++) {
+    h->hX[b] = b < M ? X[b] : -1; h->hY[b] = b < M ? Y[b] : -1; h->hSlot[b] = b;
+    h->hF[b] = (b < M && R && R[b]) ? 1 : 0;
+  }
+  h->hM[0] = M; h->hSti[0] = h->gen_len > 0 ? (int)h->sample_ptr : -1; h->hG[0] = h->global_step;
+  int rc = upload_window(h, 1);
+  if (rc) return rc;
+  rc = run_window(h, 1);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->hCost, h->md.cost, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (cost) *cost = h->hCost[0];
+  if (h->hCost[0] != h->hCost[0]) FAIL(G4R_ERR_NAN, "NaN error!");
+  return G4R_OK;
+}
+
+#include "g4r_eval.cuh"

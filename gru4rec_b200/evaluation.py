@@ -1,0 +1,38 @@
+"""evaluate_gpu with the reference's signature and return value (hidasib/GRU4Rec evaluation.py:15-147)."""
+import numpy as np
+import pandas as pd
+
+from . import _lib
+
+_MODES = {'standard': 0, 'conservative': 1, 'median': 2, 'tiebreaking': 0}
+
+
+def evaluate_gpu(gru, test_data, items=None, session_key='SessionId', item_key='ItemId', time_key='Time', cut_off=[20], batch_size=100, mode='standard'):
+    '''
+    Recall@N and MRR@N of next-item prediction, session-parallel (evaluation.py:15-147).
+    Returns (recall_list, mrr_list), one entry per cut-off.  `mode` as in the reference; 'tiebreaking' adds
+    U(0,1)*1e-10 noise in the reference, which is below float32 resolution for scores > 1e-3 -- it is evaluated as
+    'standard' here.  `items` (ranking against a subset) is not implemented on the device path.
+    '''
+    if gru.error_during_train: raise Exception
+    if mode not in _MODES:
+        raise NotImplementedError
+    if items is not None:
+        raise NotImplementedError('evaluate_gpu(items=...) is not implemented on the device path')
+    multi_cut_off = (type(cut_off) == list) or (type(cut_off) == tuple)
+    cuts = list(cut_off) if multi_cut_off else [cut_off]
+    print('Measuring Recall@{} and MRR@{}'.format(','.join([str(c) for c in cuts]), ','.join([str(c) for c in cuts])))
+    test_data = pd.merge(test_data, pd.DataFrame({'ItemIdx': gru.itemidmap.values, item_key: gru.itemidmap.index}), on=item_key, how='inner')
+    test_data.sort_values([session_key, time_key, item_key], inplace=True)
+    test_data_items = test_data.ItemIdx.values
+    offset_sessions = np.zeros(test_data[session_key].nunique() + 1, dtype=np.int32)
+    offset_sessions[1:] = test_data.groupby(session_key).size().cumsum()
+    eng = gru._ensure_engine(batch_size)
+    if eng.cfg.eval_batch_size != batch_size:
+        # the scoring lanes are a property of the engine; rebuild with exactly this many
+        eng = gru._build_engine(sample_store=0, eval_lanes=batch_size)
+    sched = _lib.Schedule(test_data_items, offset_sessions, None, batch_size, 0, mode=1)
+    rec, mrr, n = eng.eval_schedule(sched, cuts, _MODES[mode])
+    recall = [float(r) / n for r in rec]
+    mrrs = [float(m) / n for m in mrr]
+    return recall, mrrs

@@ -1,0 +1,436 @@
+"""GRU4Rec with the reference's class surface (hidasib/GRU4Rec gru4rec.py:27-781) on the B200 engine.
+
+`run.py -g gru4rec_b200.gru4rec` (or the root-level shim module `gru4rec`) selects this class through the
+reference's own plugin seam (run.py:21,39).  Constructor arguments, set_params() coercions and prints,
+fit() / predict_next_batch() / savemodel() / loadmodel() signatures and printed lines follow the reference;
+the per-mini-batch work runs in libg4r.so (hand-written sm_100a CUDA) through ctypes.  PyTorch is used
+only to allocate the device workspace.  There is no CPU fallback.
+"""
+import pickle
+import time
+from collections import OrderedDict  # noqa: F401  (param files use it)
+
+import numpy as np
+import pandas as pd
+
+from . import datatools
+from . import _lib
+
+
+class _DeviceParam(object):
+    """Stand-in for a Theano shared variable: get_value()/set_value() round-trip through the engine."""
+
+    def __init__(self, owner, name):
+        self._owner = owner
+        self.name = name
+
+    def get_value(self, borrow=False):
+        return self._owner._get_param(self.name)
+
+    def set_value(self, value, borrow=False):
+        self._owner._set_param(self.name, value)
+
+
+class GRU4Rec:
+    '''
+    GRU4Rec(loss='bpr-max', final_act='elu-1', hidden_act='tanh', layers=[100],
+                 n_epochs=10, batch_size=32, dropout_p_hidden=0.0, dropout_p_embed=0.0, learning_rate=0.1, momentum=0.0, lmbd=0.0, embedding=0, n_sample=2048, sample_alpha=0.75, smoothing=0.0, constrained_embedding=False,
+                 adapt='adagrad', adapt_params=[], grad_cap=0.0, bpreg=1.0, logq=0.0,
+                 sigma=0.0, init_as_normal=False, train_random_order=False, time_sort=True,
+                 session_key='SessionId', item_key='ItemId', time_key='Time')
+    Same parameters as the reference class (gru4rec.py:28-96).  Options that only exist as Theano graph variants
+    and are unused by every shipped parameter file (adapt in {'rmsprop','adam','adadelta'}, grad_cap, smoothing,
+    loss/final_act pairs other than {cross-entropy+softmax, xe_logit+softmax_logit, pairwise losses + elementwise
+    activations}) raise NotImplementedError when fit() builds the engine.
+    '''
+
+    def __init__(self, loss='bpr-max', final_act='linear', hidden_act='tanh', layers=[100],
+                 n_epochs=10, batch_size=32, dropout_p_hidden=0.0, dropout_p_embed=0.0, learning_rate=0.1, momentum=0.0, lmbd=0.0, embedding=0, n_sample=2048, sample_alpha=0.75, smoothing=0.0, constrained_embedding=False,
+                 adapt='adagrad', adapt_params=[], grad_cap=0.0, bpreg=1.0, logq=0.0,
+                 sigma=0.0, init_as_normal=False, train_random_order=False, time_sort=True,
+                 session_key='SessionId', item_key='ItemId', time_key='Time'):
+        self.layers = layers
+        self.n_epochs = n_epochs
+        self.batch_size = batch_size
+        self.dropout_p_hidden = dropout_p_hidden
+        self.dropout_p_embed = dropout_p_embed
+        self.learning_rate = learning_rate
+        self.adapt_params = adapt_params
+        self.momentum = momentum
+        self.sigma = sigma
+        self.init_as_normal = init_as_normal
+        self.session_key = session_key
+        self.item_key = item_key
+        self.time_key = time_key
+        self.grad_cap = grad_cap
+        self.bpreg = bpreg
+        self.logq = logq
+        self.train_random_order = train_random_order
+        self.lmbd = lmbd
+        if embedding == 'layersize':
+            self.embedding = self.layers[0]
+        else:
+            self.embedding = embedding
+        self.constrained_embedding = constrained_embedding
+        self.time_sort = time_sort
+        self.adapt = adapt
+        self.loss = loss
+        self.set_loss_function(self.loss)
+        self.final_act = final_act
+        self.set_final_activation(self.final_act)
+        self.hidden_act = hidden_act
+        self.set_hidden_activation(self.hidden_act)
+        self.n_sample = n_sample
+        self.sample_alpha = sample_alpha
+        self.smoothing = smoothing
+        # engine-side options (not part of the reference surface)
+        self.device = 0
+        self.dropout_seed = 0
+        self.eval_lanes = 512            # run.py evaluates with batch_size=512 (run.py:127)
+        self.step_mode = 0
+        self._engine = None
+        self._host = None                # numpy copies of the parameters when no engine is alive
+
+    # ---- same validation behaviour as the reference setters (gru4rec.py:136-161) ----
+    def set_loss_function(self, loss):
+        if loss not in ('cross-entropy', 'bpr', 'bpr-max', 'top1', 'top1-max', 'xe_logit'):
+            raise NotImplementedError
+
+    def set_final_activation(self, final_act):
+        _lib.parse_act(final_act)
+
+    def set_hidden_activation(self, hidden_act):
+        if hidden_act in ('softmax', 'softmax_logit'):
+            raise NotImplementedError
+        _lib.parse_act(hidden_act)
+
+    def set_params(self, **kvargs):
+        """gru4rec.py:162-187, including the printed lines."""
+        maxk_len = np.max([len(str(x)) for x in kvargs.keys()])
+        maxv_len = np.max([len(str(x)) for x in kvargs.values()])
+        for k, v in kvargs.items():
+            if not hasattr(self, k):
+                print('Unkown attribute: {}'.format(k))
+                raise NotImplementedError
+            else:
+                if type(v) == str and k == 'adapt_params': v = [float(l) for l in v.split('/')]
+                elif type(v) == str and type(getattr(self, k)) == list: v = [int(l) for l in v.split('/')]
+                if type(v) == str and type(getattr(self, k)) == bool:
+                    if v == 'True' or v == '1': v = True
+                    elif v == 'False' or v == '0': v = False
+                    else:
+                        print('Invalid value for boolean parameter: {}'.format(v))
+                        raise NotImplementedError
+                if k == 'embedding' and v == 'layersize':
+                    self.embedding = 'layersize'
+                setattr(self, k, type(getattr(self, k))(v))
+                if k == 'loss': self.set_loss_function(self.loss)
+                if k == 'final_act': self.set_final_activation(self.final_act)
+                if k == 'hidden_act': self.set_hidden_activation(self.hidden_act)
+                print('SET   {}{}TO   {}{}(type: {})'.format(k, ' ' * (maxk_len - len(k) + 3), getattr(self, k), ' ' * (maxv_len - len(str(getattr(self, k))) + 3), type(getattr(self, k))))
+        if self.embedding == 'layersize':
+            self.embedding = self.layers[0]
+            print('SET   {}{}TO   {}{}(type: {})'.format('embedding', ' ' * (maxk_len - len('embedding') + 3), getattr(self, 'embedding'), ' ' * (maxv_len - len(str(getattr(self, 'embedding'))) + 3), type(getattr(self, 'embedding'))))
+
+    # ---- weight initialisation, draw order as in the reference (gru4rec.py:254-294) ----
+    def init_matrix(self, shape):
+        if self.sigma != 0: sigma = self.sigma
+        else: sigma = np.sqrt(6.0 / (shape[0] + shape[1]))
+        if self.init_as_normal:
+            return np.asarray(np.random.randn(*shape) * sigma, dtype=np.float32)
+        else:
+            return np.asarray(np.random.rand(*shape) * sigma * 2 - sigma, dtype=np.float32)
+
+    def _init_host_weights(self):
+        np.random.seed(42)
+        w = {}
+        if self.constrained_embedding:
+            n_features = self.layers[-1]
+        elif self.embedding:
+            w['E'] = self.init_matrix((self.n_items, self.embedding))
+            n_features = self.embedding
+        else:
+            n_features = self.n_items
+        for i in range(len(self.layers)):
+            nin = self.layers[i - 1] if i > 0 else n_features
+            m = [self.init_matrix((nin, self.layers[i])) for _ in range(3)]
+            w['Wx%d' % i] = np.hstack(m)
+            w['Wh%d' % i] = self.init_matrix((self.layers[i], self.layers[i]))
+            m2 = [self.init_matrix((self.layers[i], self.layers[i])) for _ in range(2)]
+            w['Wrz%d' % i] = np.hstack(m2)
+            w['Bh%d' % i] = np.zeros((self.layers[i] * 3,), dtype=np.float32)
+        w['Wy'] = self.init_matrix((self.n_items, self.layers[-1]))
+        w['By'] = np.zeros((self.n_items, 1), dtype=np.float32)
+        return w
+
+    def init(self, data):
+        datatools.sort_if_needed(data, [self.session_key, self.time_key])
+        offset_sessions = datatools.compute_offset(data, self.session_key)
+        self._host = self._init_host_weights()
+        return offset_sessions
+
+    # ---- engine management ----
+    def _param_names(self):
+        names = []
+        for i in range(len(self.layers)):
+            names += ['Wx%d' % i, 'Wh%d' % i, 'Wrz%d' % i, 'Bh%d' % i]
+        names += ['Wy', 'By']
+        if self.embedding and not self.constrained_embedding:
+            names.append('E')
+        return names
+
+    def _make_config(self, sample_store, eval_lanes):
+        cfg = _lib.G4RConfig()
+        if self.adapt not in _lib.ADAPT:
+            raise NotImplementedError('adapt=%r is not implemented on the device path' % (self.adapt,))
+        if self.grad_cap:
+            raise NotImplementedError('grad_cap is not implemented on the device path')
+        cfg.n_items = self.n_items
+        cfg.n_layers = len(self.layers)
+        for i, l in enumerate(self.layers):
+            cfg.layers[i] = l
+        cfg.batch_size = self.batch_size
+        cfg.constrained_embedding = 1 if self.constrained_embedding else 0
+        cfg.embedding = 0 if self.constrained_embedding else int(self.embedding or 0)
+        cfg.loss = _lib.LOSS[self.loss]
+        cfg.final_act, cfg.final_act_p1, cfg.final_act_p2 = _lib.parse_act(self.final_act)
+        cfg.hidden_act, cfg.hidden_act_p1, cfg.hidden_act_p2 = _lib.parse_act(self.hidden_act)
+        cfg.dropout_p_hidden = self.dropout_p_hidden
+        cfg.dropout_p_embed = self.dropout_p_embed
+        cfg.learning_rate = self.learning_rate
+        cfg.momentum = self.momentum
+        cfg.lmbd = self.lmbd
+        cfg.n_sample = self.n_sample
+        cfg.sample_alpha = self.sample_alpha
+        cfg.smoothing = self.smoothing
+        cfg.bpreg = self.bpreg
+        cfg.logq = self.logq
+        cfg.adapt = _lib.ADAPT[self.adapt]
+        cfg.sample_store = int(sample_store)
+        cfg.dropout_seed = self.dropout_seed
+        cfg.mrg_seed = 12345
+        cfg.max_resident_steps = 0
+        cfg.world_size, cfg.rank = 1, 0
+        cfg.eval_batch_size = eval_lanes
+        cfg.step_mode = self.step_mode
+        return cfg
+
+    def _build_engine(self, sample_store=0, eval_lanes=None):
+        eval_lanes = self.eval_lanes if eval_lanes is None else eval_lanes
+        host = self._host if self._host is not None else self._pull_host()
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+        eng = _lib.Engine(self._make_config(sample_store, eval_lanes), device=self.device)
+        for name in self._param_names():
+            eng.set(name, host[name])
+        self._engine = eng
+        self._engine_eval_lanes = eval_lanes
+        self._host = None
+        self._bind_params()
+        return eng
+
+    def _bind_params(self):
+        n = len(self.layers)
+        self.Wx = [_DeviceParam(self, 'Wx%d' % i) for i in range(n)]
+        self.Wh = [_DeviceParam(self, 'Wh%d' % i) for i in range(n)]
+        self.Wrz = [_DeviceParam(self, 'Wrz%d' % i) for i in range(n)]
+        self.Bh = [_DeviceParam(self, 'Bh%d' % i) for i in range(n)]
+        self.H = [_DeviceParam(self, 'H%d' % i) for i in range(n)]
+        self.Wy = _DeviceParam(self, 'Wy')
+        self.By = _DeviceParam(self, 'By')
+        if self.embedding and not self.constrained_embedding:
+            self.E = _DeviceParam(self, 'E')
+
+    def _get_param(self, name):
+        if self._engine is not None:
+            a = self._engine.get(name)
+            return a.reshape(-1) if name.startswith('Bh') else a
+        return self._host[name]
+
+    def _set_param(self, name, value):
+        if self._engine is not None:
+            self._engine.set(name, value)
+        else:
+            self._host[name] = np.asarray(value, dtype=np.float32)
+
+    def _pull_host(self):
+        return {name: self._get_param(name) for name in self._param_names()}
+
+    def _ensure_engine(self, eval_lanes):
+        if self._engine is None or self._engine_eval_lanes < eval_lanes:
+            self._build_engine(sample_store=0, eval_lanes=max(eval_lanes, self.eval_lanes))
+        return self._engine
+
+    def generate_neg_samples(self, pop, length):
+        """Legacy host-side sampler (store_type='cpu'; gru4rec.py:507-514)."""
+        if self.sample_alpha:
+            sample = np.searchsorted(pop, np.random.rand(self.n_sample * length))
+        else:
+            sample = np.random.choice(self.n_items, size=self.n_sample * length)
+        if length > 1:
+            sample = sample.reshape((length, self.n_sample))
+        return sample
+
+    # ---- training (gru4rec.py:515-664) ----
+    def fit(self, data, sample_store=10000000, store_type='gpu'):
+        '''
+        Trains the network.  Same arguments, data-frame side effects ('ItemIdx' column, in-place sort) and
+        printed lines as the reference (gru4rec.py:515-664).
+        '''
+        self.predict = None
+        self.error_during_train = False
+        itemids = data[self.item_key].unique()
+        self.n_items = len(itemids)
+        self.itemidmap = pd.Series(data=np.arange(self.n_items), index=itemids, name='ItemIdx')
+        data['ItemIdx'] = self.itemidmap[data[self.item_key].values].values
+        offset_sessions = self.init(data)
+        pop = data.groupby(self.item_key).size()
+        P0 = None
+        if self.logq:
+            P0 = pop[self.itemidmap.index.values].values.astype(np.float32)
+        generate_length = 0
+        use_store = False
+        if self.n_sample:
+            pop = pop[self.itemidmap.index.values].values ** self.sample_alpha
+            pop = pop.cumsum() / pop.sum()
+            pop[-1] = 1
+            if sample_store:
+                generate_length = sample_store // self.n_sample
+                if generate_length <= 1:
+                    sample_store = 0
+                    print('No example store was used')
+                elif store_type == 'cpu':
+                    use_store = True
+                    print('Created sample store with {} batches of samples (type=CPU)'.format(generate_length))
+                elif store_type == 'gpu':
+                    use_store = True
+                else:
+                    print('Invalid store type {}'.format(store_type))
+                    raise NotImplementedError
+            else:
+                print('No example store was used')
+        eng = self._build_engine(sample_store=(sample_store if use_store else 0))
+        if P0 is not None:
+            eng.set_logq_support(P0)
+        if use_store:
+            eng.set_sampling_cdf(pop.astype(np.float32))
+            if store_type == 'gpu':
+                eng.generate_samples()
+                print('Created sample store with {} batches of samples (type=GPU)'.format(generate_length))
+            else:
+                eng.set_sample_store(self.generate_neg_samples(pop, generate_length))
+        base_order = np.argsort(data.groupby(self.session_key)[self.time_key].min().values) if self.time_sort else np.arange(len(offset_sessions) - 1)
+        data_items = data.ItemIdx.values
+        sched = None
+        n_sample_eff = self.n_sample if use_store else (self.n_sample if store_type == 'cpu' else self.n_sample)
+        for epoch in range(self.n_epochs):
+            t0 = time.time()
+            eng.reset_hidden()
+            session_idx_arr = np.random.permutation(len(offset_sessions) - 1) if self.train_random_order else base_order
+            if sched is None or self.train_random_order:
+                sched = _lib.Schedule(data_items, offset_sessions, session_idx_arr, self.batch_size, n_sample_eff, mode=0)
+                cc = sched.export()['M'].astype(np.float64)
+            try:
+                if use_store and store_type == 'cpu':
+                    c = self._train_epoch_cpu_store(eng, sched, pop, generate_length)
+                else:
+                    c = eng.train_steps(sched, 0, sched.n_steps)
+            except _lib.NaNError:
+                print(str(epoch) + ': NaN error!')
+                self.error_during_train = True
+                return
+            avgc = np.sum(c * cc) / np.sum(cc)
+            if np.isnan(avgc):
+                print('Epoch {}: NaN error!'.format(str(epoch)))
+                self.error_during_train = True
+                return
+            t1 = time.time()
+            dt = t1 - t0
+            print('Epoch{} --> loss: {:.6f} \t({:.2f}s) \t[{:.2f} mb/s | {:.0f} e/s]'.format(epoch + 1, avgc, dt, len(c) / dt, np.sum(cc) / dt))
+
+    def _train_epoch_cpu_store(self, eng, sched, pop, generate_length):
+        """store_type='cpu' (legacy, gru4rec.py:605-614): samples are drawn by NumPy on the host, one store at a time."""
+        costs = []
+        done = 0
+        while done < sched.n_steps:
+            if eng.get_sample_pointer() >= generate_length:
+                eng.set_sample_store(self.generate_neg_samples(pop, generate_length))
+            n = min(sched.n_steps - done, generate_length - eng.get_sample_pointer())
+            costs.append(eng.train_steps(sched, done, n))
+            done += n
+        return np.concatenate(costs)
+
+    # ---- serving (gru4rec.py:665-728) ----
+    def predict_next_batch(self, session_ids, input_item_ids, predict_for_item_ids=None, batch=100):
+        '''
+        Gives prediction scores for a selected set of items; same contract as the reference
+        (gru4rec.py:665-728): hidden state kept per batch coordinate while the session id stays the same.
+        Returns a DataFrame, rows = items, columns = events of the batch.
+        '''
+        if self.error_during_train: raise Exception
+        eng = self._ensure_engine(batch)
+        if getattr(self, 'predict', None) is None or self.predict_batch != batch:
+            self.predict_batch = batch
+            eng.reset_eval_hidden()
+            self.current_session = np.ones(batch) * -1
+            self.predict = True
+        session_ids = np.asarray(session_ids)
+        reset = (session_ids != self.current_session)
+        if reset.any():
+            self.current_session = session_ids.copy()
+        in_idxs = self.itemidmap[input_item_ids].values
+        preds = eng.predict(in_idxs, reset.astype(np.uint8)).T          # items x batch
+        if predict_for_item_ids is not None:
+            iIdxs = self.itemidmap[predict_for_item_ids].values
+            preds = preds[iIdxs]
+            if self.final_act in ('softmax', 'softmax_logit'):
+                preds = preds / preds.sum(axis=0, keepdims=True)          # softmax over the requested subset
+            return pd.DataFrame(data=preds, index=predict_for_item_ids)
+        return pd.DataFrame(data=preds, index=self.itemidmap.index)
+
+    # ---- persistence (gru4rec.py:742-781): pickle of the object with NumPy parameters ----
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        host = self._host if self._engine is None else self._pull_host()
+        for k in ('_engine', 'Wx', 'Wh', 'Wrz', 'Bh', 'H', 'Wy', 'By', 'E', '_host'):
+            st.pop(k, None)
+        n = len(self.layers)
+        st['Wx'] = [host['Wx%d' % i] for i in range(n)]
+        st['Wh'] = [host['Wh%d' % i] for i in range(n)]
+        st['Wrz'] = [host['Wrz%d' % i] for i in range(n)]
+        st['Bh'] = [host['Bh%d' % i].reshape(-1) for i in range(n)]
+        st['H'] = [np.zeros((self.batch_size, self.layers[i]), dtype=np.float32) for i in range(n)]
+        st['Wy'] = host['Wy']
+        st['By'] = host['By']
+        if 'E' in host:
+            st['E'] = host['E']
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        n = len(self.layers)
+        host = {}
+        for i in range(n):
+            host['Wx%d' % i] = np.asarray(self.Wx[i], dtype=np.float32)
+            host['Wh%d' % i] = np.asarray(self.Wh[i], dtype=np.float32)
+            host['Wrz%d' % i] = np.asarray(self.Wrz[i], dtype=np.float32)
+            host['Bh%d' % i] = np.asarray(self.Bh[i], dtype=np.float32).reshape(-1)
+        host['Wy'] = np.asarray(self.Wy, dtype=np.float32)
+        host['By'] = np.asarray(self.By, dtype=np.float32).reshape(-1, 1)
+        if getattr(self, 'embedding', 0) and not getattr(self, 'constrained_embedding', False) and 'E' in st:
+            host['E'] = np.asarray(self.E, dtype=np.float32)
+        self._host = host
+        self._engine = None
+        self.predict = None
+        for k, v in (('device', 0), ('dropout_seed', 0), ('eval_lanes', 512), ('step_mode', 0)):
+            if not hasattr(self, k):
+                setattr(self, k, v)
+
+    def savemodel(self, fname):
+        with open(fname, 'wb') as f:
+            pickle.dump(self, f)
+
+    @classmethod
+    def loadmodel(cls, fname):
+        return pd.read_pickle(fname)

@@ -1,0 +1,154 @@
+/*
+ * g4r.h -- C ABI of libg4r.so: the B200 (sm_100a) GRU4Rec session-parallel training step.
+ *
+ * This is the drop-in boundary for the hot path of hidasib/GRU4Rec.  In the reference the boundary is
+ * the set of compiled Theano functions that gru4rec.py / evaluation.py call once per mini-batch; each
+ * entry point below names the reference interface (file:line under /root/reference) it replaces.
+ * Plain pointers and sizes only; no torch / Python types.  All functions return 0 on success or a
+ * negative g4r_status; g4r_last_error() gives the message.  A handle is not thread-safe; one handle per
+ * process per device (reference: single Python thread, single CUDA context, .theanorc_gru4rec:3).
+ *
+ * Unless a parameter is documented as a device pointer, buffers are HOST memory; the library does the
+ * host<->device copies on its own stream (these copies are what bench.py's "e2e" number includes).
+ */
+#ifndef G4R_H
+#define G4R_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G4R_MAX_LAYERS 8
+
+typedef enum {
+  G4R_OK = 0,
+  G4R_ERR_INVALID = -1,        /* bad argument / unsupported configuration (reference: NotImplementedError) */
+  G4R_ERR_INDEX = -2,          /* index out of bounds (reference: IndexError, custom_theano_ops.py:586-591) */
+  G4R_ERR_CUDA = -3,           /* CUDA runtime failure (reference: RuntimeError "gpuarray error") */
+  G4R_ERR_NAN = -4,            /* NaN cost detected (reference: gru4rec.py:626-629) */
+  G4R_ERR_STATE = -5
+} g4r_status;
+
+typedef enum { G4R_LOSS_XE = 0, G4R_LOSS_BPR_MAX = 1, G4R_LOSS_TOP1_MAX = 2, G4R_LOSS_BPR = 3, G4R_LOSS_TOP1 = 4,
+               G4R_LOSS_XE_LOGIT = 5 } g4r_loss;                       /* gru4rec.py:136-143 */
+typedef enum { G4R_ACT_LINEAR = 0, G4R_ACT_RELU = 1, G4R_ACT_TANH = 2, G4R_ACT_LEAKY = 3, G4R_ACT_ELU = 4,
+               G4R_ACT_SELU = 5, G4R_ACT_SOFTMAX = 6, G4R_ACT_SOFTMAX_LOGIT = 7 } g4r_act;   /* gru4rec.py:144-161 */
+typedef enum { G4R_ADAPT_NONE = 0, G4R_ADAPT_ADAGRAD = 1 } g4r_adapt;  /* gru4rec.py:392-399 (others: not on device) */
+
+/* Mirrors the GRU4Rec constructor arguments that shape the compiled step (gru4rec.py:97-135). */
+typedef struct g4r_config {
+  int32_t n_items;
+  int32_t n_layers;
+  int32_t layers[G4R_MAX_LAYERS];
+  int32_t batch_size;
+  int32_t embedding;              /* 0: none; >0: separate item embedding E of this width (gru4rec.py:449-456) */
+  int32_t constrained_embedding;  /* 1: Wy doubles as the input embedding (gru4rec.py:438-448) */
+  int32_t loss;                   /* g4r_loss */
+  int32_t final_act;              /* g4r_act */
+  float final_act_p1, final_act_p2;
+  int32_t hidden_act;             /* g4r_act (elementwise ones) */
+  float hidden_act_p1, hidden_act_p2;
+  float dropout_p_hidden, dropout_p_embed;
+  float learning_rate, momentum, lmbd;
+  int32_t n_sample;
+  float sample_alpha;
+  float smoothing, bpreg, logq;
+  int32_t adapt;                  /* g4r_adapt */
+  int32_t sample_store;           /* capacity of the negative-sample store in ids (gru4rec.py:515,547); 0 = none */
+  uint32_t dropout_seed;
+  uint32_t mrg_seed;              /* MRG_RandomStreams seed (Theano default 12345) */
+  int32_t max_resident_steps;     /* capacity (in mini-batches) of the device-resident schedule window; 0 = default */
+  int32_t device;                 /* CUDA device ordinal */
+  int32_t world_size, rank;       /* data-parallel geometry (1,0 for single GPU) */
+  int32_t eval_batch_size;        /* lanes reserved for the scoring path (evaluation.py batch_size); 0 = batch_size */
+  int32_t step_mode;              /* 0: one kernel per phase (CUDA-graph replay); 1: persistent cooperative kernel */
+  int32_t reserved[7];
+} g4r_config;
+
+typedef struct g4r_handle g4r_handle;
+typedef struct g4r_schedule g4r_schedule;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------ */
+int g4r_version(void);
+/* Bytes of device memory the handle needs; the caller may allocate them (e.g. a torch uint8 tensor used
+ * purely as an allocator) and pass the DEVICE pointer to g4r_create, or pass NULL to let the library
+ * cudaMalloc.  Replaces: theano.shared(...) allocations in GRU4Rec.init (gru4rec.py:267-294,331,401,425,556-558). */
+int g4r_workspace_bytes(const g4r_config* cfg, size_t* bytes);
+int g4r_create(const g4r_config* cfg, void* device_workspace, size_t workspace_bytes, g4r_handle** out);
+int g4r_destroy(g4r_handle* h);
+const char* g4r_last_error(const g4r_handle* h);   /* h may be NULL: last creation error */
+/* cudaStream_t the step kernels are launched on (for CUDA-event timing by the caller). */
+void* g4r_stream(g4r_handle* h);
+
+/* ---- parameters: shared-variable get_value/set_value (gru4rec.py:745-767, 590, 649-651) ----------- */
+/* names: "Wx0".."Wx7","Wh*","Wrz*","Bh*","H*","Wy","By","E", and optimizer state "<name>.acc", "<name>.vel". */
+int g4r_tensor_shape(g4r_handle* h, const char* name, int64_t* rows, int64_t* cols);
+int g4r_set_tensor(g4r_handle* h, const char* name, const float* host, int64_t rows, int64_t cols);
+int g4r_get_tensor(g4r_handle* h, const char* name, float* host, int64_t rows, int64_t cols);
+int g4r_reset_hidden(g4r_handle* h);               /* gru4rec.py:589-590 */
+
+/* ---- negative sampling (gru4rec.py:539-566) ------------------------------------------------------- */
+int g4r_set_sampling_cdf(g4r_handle* h, const float* P, int64_t n);     /* P (gru4rec.py:556) */
+int g4r_set_logq_support(g4r_handle* h, const float* P0, int64_t n);    /* P0 (gru4rec.py:541) */
+/* generate_samples(): MRG31k3p uniforms + binary search into P; resets the sample pointer (gru4rec.py:559-564). */
+int g4r_generate_samples(g4r_handle* h);
+/* Same search on caller-supplied uniforms (parity at the K2 boundary; custom_theano_ops.py:318-349). */
+int g4r_generate_samples_from_uniform(g4r_handle* h, const float* u, int64_t n);
+int g4r_set_sample_store(g4r_handle* h, const int64_t* st, int64_t rows);   /* rows x n_sample */
+int g4r_get_sample_store(g4r_handle* h, int64_t* st, int64_t rows);
+int g4r_sample_store_rows(g4r_handle* h);                                    /* generate_length (gru4rec.py:547) */
+int g4r_set_sample_pointer(g4r_handle* h, int64_t p);                        /* STI (gru4rec.py:558,583) */
+int64_t g4r_get_sample_pointer(g4r_handle* h);
+/* Raw MRG uniforms (theano.sandbox.rng_mrg restatement) for tests. */
+int g4r_mrg_uniform(g4r_handle* h, float* out, int64_t n);
+
+/* ---- stand-alone custom ops (custom_theano_ops.py) ------------------------------------------------ */
+/* GpuBinarySearchSorted (custom_theano_ops.py:275-407): y[i] = index of x[i] in sorted d. */
+int g4r_searchsorted(g4r_handle* h, const float* d, int64_t n_d, const float* x, int64_t n_x, int64_t* y);
+/* GpuAdvancedSubtensor1_fast (custom_theano_ops.py:409-595): out[i,:] = table[idx[i],:], negative wrap,
+ * out-of-range -> G4R_ERR_INDEX. */
+int g4r_gather_rows(g4r_handle* h, const float* table, int64_t rows, int64_t cols, const int64_t* idx, int64_t n_idx, float* out);
+
+/* ---- session-parallel schedule (gru4rec.py:585-651; evaluation.py:90-139) -------------------------- */
+/* Builds every mini-batch of one epoch on the host: X/Y item indices, reset flags, batch sizes, lane slots.
+ * mode 0 = training order semantics (reset-after flags), 1 = evaluation (zero-before flags).
+ * session_order: permutation of sessions (gru4rec.py:585/593) or NULL for identity. */
+int g4r_schedule_build(const int64_t* data_items, int64_t n_events, const int32_t* offset_sessions, int64_t n_sessions,
+                       const int64_t* session_order, int32_t batch_size, int32_t n_sample, int32_t mode, g4r_schedule** out);
+int g4r_schedule_free(g4r_schedule* s);
+int64_t g4r_schedule_steps(const g4r_schedule* s);
+int64_t g4r_schedule_events(const g4r_schedule* s);       /* sum of batch sizes */
+/* Copies out step arrays (each step padded to batch_size entries; unused lanes = -1 / 0). Any pointer may be NULL. */
+int g4r_schedule_export(const g4r_schedule* s, int32_t* X, int32_t* Y, uint8_t* flags, int32_t* M, int32_t* slots);
+
+/* ---- the compiled step: train_function(X, Y, M, R) -> cost (gru4rec.py:584,623) ------------------- */
+/* One mini-batch from host arrays; returns the cost (D2H) like the reference call. */
+int g4r_train_step(g4r_handle* h, const int32_t* X, const int32_t* Y, int32_t M, const int8_t* R, float* cost);
+/* Steps [first, first+n) of a schedule: uploads the window, runs every step on the device without host
+ * round trips, regenerates the sample store when the pointer wraps (gru4rec.py:618-621), copies the n
+ * costs back.  NaN cost -> G4R_ERR_NAN with *nan_step set (gru4rec.py:626-629). */
+int g4r_train_steps(g4r_handle* h, const g4r_schedule* s, int64_t first, int64_t n, float* cost_out, int64_t* nan_step);
+/* Two-phase variant used for device-resident timing: upload (H2D + per-step column plans) then run. */
+int g4r_upload_steps(g4r_handle* h, const g4r_schedule* s, int64_t first, int64_t n);
+int g4r_run_uploaded(g4r_handle* h, float* cost_out /* may be NULL */, float* device_ms /* may be NULL */);
+/* Counters for bench.py: kernels launched by this handle so far. */
+int64_t g4r_kernel_launches(const g4r_handle* h);
+
+/* ---- scoring path: evaluate(X, Y, M) (evaluation.py:76,108) and predict (gru4rec.py:706-710) ------- */
+/* Runs a whole evaluation schedule: full-catalogue scores, rank of the target, per-cutoff hit counts and
+ * reciprocal-rank sums.  mode: 0 standard, 1 conservative, 2 median (evaluation.py:60-64).
+ * recall_sum/mrr_sum: n_cut doubles each (sums, not yet divided by the number of events). */
+int g4r_eval_schedule(g4r_handle* h, const g4r_schedule* s, const int32_t* cut_off, int32_t n_cut, int32_t mode,
+                      double* recall_sum, double* mrr_sum, int64_t* n_events);
+/* predict_next_batch's device call: scores of all items for `batch` lanes; reset_mask zeroes lanes first
+ * (gru4rec.py:712-717).  out: [batch x n_items] row-major. */
+int g4r_predict(g4r_handle* h, const int32_t* X, int32_t batch, const uint8_t* reset_mask, float* out);
+/* Zero the scoring-path hidden state (gru4rec.py:696-697). */
+int g4r_reset_eval_hidden(g4r_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,109 @@
+"""CPU-side tests (-m "not gpu"): the C-ABI library loads and exports every symbol include/g4r.h declares,
+the C++ schedule builder equals the oracle's literal restatement, and the host class keeps the reference surface."""
+import os
+import re
+import numpy as np
+import pytest
+import gru4rec_oracle as orc
+from gru4rec_b200 import _lib
+from gru4rec_b200.synth import make_sessions
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, 'include', 'g4r.h')).read()
+    declared = set(re.findall(r'^(?:int|int64_t|void\*|const char\*)\s+(g4r_[a-z0-9_]+)\s*\(', hdr, flags=re.M))
+    assert declared, 'no declarations parsed'
+    for name in sorted(declared):
+        assert hasattr(lib, name), 'libg4r.so does not export %s' % name
+    assert set(_lib.EXPORTS) == declared
+    assert lib.g4r_version() >= 100
+
+
+@pytest.mark.parametrize('B,n_sample,seed', [(4, 8, 0), (8, 0, 1), (16, 4, 2), (3, 0, 3)])
+def test_train_schedule_equals_oracle(B, n_sample, seed):
+    df = make_sessions(n_items=50, n_events=600, seed=seed)
+    d = orc.prepare_fit_data(df)
+    steps = orc.build_train_schedule(d['data_items'], d['offset_sessions'], d['base_order'], B, n_sample)
+    s = _lib.Schedule(d['data_items'], d['offset_sessions'], d['base_order'], B, n_sample, mode=0)
+    e = s.export()
+    assert s.n_steps == len(steps)
+    assert s.n_events == sum(st['M'] for st in steps)
+    for k, st in enumerate(steps):
+        M = st['M']
+        assert e['M'][k] == M
+        np.testing.assert_array_equal(e['X'][k, :M], st['X'])
+        np.testing.assert_array_equal(e['Y'][k, :M], st['Y'])
+        np.testing.assert_array_equal(e['F'][k, :M] & 1, st['R'].astype(np.uint8))
+        np.testing.assert_array_equal(e['slots'][k, :M], st['slots'])
+
+
+@pytest.mark.parametrize('B,seed', [(5, 0), (11, 1), (32, 2)])
+def test_eval_schedule_equals_oracle(B, seed):
+    df = make_sessions(n_items=50, n_events=700, seed=seed)
+    d = orc.prepare_fit_data(df)
+    steps = orc.build_eval_schedule(d['data_items'], d['offset_sessions'], B)
+    s = _lib.Schedule(d['data_items'], d['offset_sessions'], None, B, 0, mode=1)
+    e = s.export()
+    assert s.n_steps == len(steps)
+    for k, st in enumerate(steps):
+        M = st['M']
+        assert e['M'][k] == M
+        np.testing.assert_array_equal(e['X'][k, :M], st['X'])
+        np.testing.assert_array_equal(e['Y'][k, :M], st['Y'])
+        np.testing.assert_array_equal((e['F'][k, :M] >> 1) & 1, st['Z'].astype(np.uint8))
+        np.testing.assert_array_equal(e['slots'][k, :M], st['slots'])
+
+
+def test_schedule_too_few_sessions_is_index_error():
+    df = make_sessions(n_items=20, n_events=30, seed=0)
+    d = orc.prepare_fit_data(df)
+    with pytest.raises(IndexError):
+        _lib.Schedule(d['data_items'], d['offset_sessions'], d['base_order'], 64, 8, mode=0)
+
+
+def test_engine_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    from gpu_utils import make_cfg
+    with pytest.raises(RuntimeError):
+        _lib.Engine(make_cfg(10, dict(layers=[4], batch_size=2, n_sample=0)))
+    with pytest.raises(RuntimeError):
+        _lib.Engine(make_cfg(10, dict(layers=[4], batch_size=2, n_sample=0)), use_torch_allocator=False)
+
+
+def test_set_params_surface(capsys):
+    import gru4rec
+    g = gru4rec.GRU4Rec()
+    g.set_params(layers='100/50', loss='cross-entropy', final_act='softmax', constrained_embedding='True', momentum='0.2', batch_size='64')
+    assert g.layers == [100, 50] and g.constrained_embedding is True and g.momentum == 0.2 and g.batch_size == 64
+    out = capsys.readouterr().out
+    assert 'SET   layers' in out and "(type: <class 'list'>)" in out
+    with pytest.raises(NotImplementedError):
+        g.set_params(no_such_param=1)
+    with pytest.raises(NotImplementedError):
+        g.set_params(constrained_embedding='maybe')
+    with pytest.raises(NotImplementedError):
+        gru4rec.GRU4Rec(loss='nope')
+
+
+def test_mrg_constants_self_consistency():
+    """A1p72 / A1p134 are powers of the one-step MRG31k3p transition matrices (checks the recalled constants)."""
+    A1 = np.array([[0, 4194304, 129], [1, 0, 0], [0, 1, 0]], dtype=object)
+    A2 = np.array([[32768, 0, 32769], [1, 0, 0], [0, 1, 0]], dtype=object)
+
+    def mpow(A, e, m):
+        R = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1]], dtype=object)
+        while e:
+            if e & 1:
+                R = R.dot(A) % m
+            A = A.dot(A) % m
+            e >>= 1
+        return R
+    assert (mpow(A1, 2 ** 72, orc.M1) == orc.A1p72.astype(object)).all()
+    assert (mpow(A2, 2 ** 72, orc.M2) == orc.A2p72.astype(object)).all()
+    assert (mpow(A1, 2 ** 134, orc.M1) == orc.A1p134.astype(object)).all()
+    assert (mpow(A2, 2 ** 134, orc.M2) == orc.A2p134.astype(object)).all()

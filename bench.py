@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""bench.py -- mini-batches/sec of the GRU4Rec session-parallel training step on synthetic RSC15-shaped sessions.
+
+Contract: python bench.py --gpus N --steps K --warmup W   (torchrun for N>1) prints ONE JSON line.
+  value   : whole-job mini-batches/s with the schedule window, sample store and parameters resident in HBM
+  e2e     : the same metric through the reference-facing call (host schedule arrays -> H2D -> steps -> D2H costs)
+  roofline: dominant kernel's algorithmic bytes / its CUDA-event duration vs the measured HBM peak
+  cpu_baseline: the NumPy oracle (port of the reference; Theano is not installable) on the host cores, bounded sample
+--impl reference : times that CPU port alone (rank 0 only), same metric / config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# workload = BASELINE.json configs[1]: RSC15 1-layer GRU(100) BPR-max n_sample=2048 batch=32 (param_samples/rsc15_bpr-max.py)
+WORKLOAD = dict(name='rsc15_bprmax_gru100_b32_ns2048', n_items=37483,
+                model=dict(layers=[100], loss='bpr-max', final_act='elu-0.5', hidden_act='tanh', batch_size=32, dropout_p_embed=0.0,
+                           dropout_p_hidden=0.0, learning_rate=0.2, momentum=0.3, sample_alpha=0.0, n_sample=2048, bpreg=1.0,
+                           constrained_embedding=False),
+                sample_store=10000000)
+ALGO_BYTES_PER_STEP = 6041792
+
+
+def algo_bytes_lossgrad(N, L, mom=True):
+    """sparse Adagrad(+momentum) of the N gathered Wy rows + By: (param, acc[, vel]) read + write."""
+    T = 6 if mom else 4
+    return T * 4 * (N * L + N)
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu_index=0):
+        threading.Thread.__init__(self, daemon=True)
+        self.rows = []
+        self.stop_flag = False
+        self.gpu_index = gpu_index
+
+    def run(self):
+        q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        try:
+            p = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=' + q, '--format=csv,noheader,nounits', '-lms', '100'],
+                                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            return
+        while not self.stop_flag:
+            line = p.stdout.readline()
+            if not line:
+                break
+            self.rows.append([x.strip() for x in line.split(',')])
+        p.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(np.max(mx)), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def build_workload(n_steps_needed, seed=0):
+    from gru4rec_b200.synth import make_session_arrays
+    B = WORKLOAD['model']['batch_size']
+    n_events = int((n_steps_needed + 64) * B * 1.6) + 20000
+    return make_session_arrays(WORKLOAD['n_items'], n_events, seed=seed)
+
+
+def oracle_steps_per_sec(items, offset, order, supports, n_warm, n_steps, budget_s):
+    """The NumPy restatement of the reference step (oracle/) on the host cores."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import gru4rec_oracle as orc
+    mk = dict(WORKLOAD['model'])
+    m = orc.OracleGRU4Rec(**mk)
+    m.init(WORKLOAD['n_items'])
+    P = orc.sampling_cdf(supports, mk['sample_alpha']).astype(np.float32)
+    rs = np.random.RandomState(1)
+    B = mk['batch_size']
+    # literal schedule restatement on a prefix of the data (the schedule itself is outside the timed step)
+    n_sess = int(np.searchsorted(offset, (n_warm + n_steps + 8) * B * 3))
+    n_sess = max(min(n_sess, len(offset) - 1), B + 1)
+    steps = orc.build_train_schedule(items, offset[:n_sess + 1], order[:n_sess], B, mk['n_sample'])
+    steps = steps[:n_warm + n_steps]
+    t_start = time.time()
+    done = 0
+    t0 = None
+    for k, st in enumerate(steps):
+        if k == n_warm:
+            t0 = time.time()
+        smp = orc.searchsorted_k2(P, rs.rand(mk['n_sample']).astype(np.float32))
+        m.train_step(st['X'], st['Y'], st['R'], samples=smp, slots=st['slots'])
+        if k >= n_warm:
+            done += 1
+            if time.time() - t_start > budget_s:
+                break
+    dt = time.time() - t0
+    try:
+        from threadpoolctl import threadpool_info
+        cores = max([p.get('num_threads', 1) for p in threadpool_info()] + [1])
+    except Exception:
+        cores = os.cpu_count()
+    return done / dt, done, cores
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    n = args.steps
+    items, offset, order, supports = build_workload(min(n, 4000) + args.warmup)
+    v, done, cores = oracle_steps_per_sec(items, offset, order, supports, args.warmup, n, budget_s=150.0)
+    out = {
+        'metric': 'mini-batches/sec', 'value': v, 'unit': 'mb/s', 'n_gpus': args.gpus, 'steps': done, 'warmup': args.warmup,
+        'ms_per_step': 1000.0 / v, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'impl': 'reference',
+        'config': {'workload': WORKLOAD['name'], 'n_items': WORKLOAD['n_items'], 'global_batch': WORKLOAD['model']['batch_size'],
+                   'note': 'reference CPU path = NumPy restatement of gru4rec.py (oracle/); Theano is not installable offline'},
+        'cpu_baseline': {'value': v, 'unit': 'mb/s', 'cores': cores, 'kind': 'port',
+                         'sample': '%d timed mini-batches of the same workload after %d warm-up (time-bounded)' % (done, args.warmup)},
+        'e2e': {'value': v, 'unit': 'mb/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=4000)
+    ap.add_argument('--warmup', type=int, default=200)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--step-mode', type=int, default=-1)
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+    import torch
+    from gru4rec_b200 import _lib
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (no CPU fallback)')
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    K, W = args.steps, max(args.warmup, 3)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from gpu_utils import make_cfg
+    mk = dict(WORKLOAD['model'])
+    cfg = make_cfg(WORKLOAD['n_items'], mk, sample_store=WORKLOAD['sample_store'], eval_lanes=0,
+                   max_resident_steps=max(K, W) + 8, step_mode=max(args.step_mode, 0))
+    eng = _lib.Engine(cfg, device=local_rank)
+    # parameters: the reference's initialisation (gru4rec.py:254-294); data: synthetic RSC15-shaped sessions, disjoint per rank
+    import gru4rec as g4
+    gru = g4.GRU4Rec(**mk)
+    gru.n_items = WORKLOAD['n_items']
+    host = gru._init_host_weights()
+    for name, w in host.items():
+        eng.set(name, w)
+    items, offset, order, supports = build_workload(2 * (K + W), seed=rank)
+    P = supports.astype(np.float64) ** mk['sample_alpha']
+    P = P.cumsum() / P.sum(); P[-1] = 1
+    eng.set_sampling_cdf(P.astype(np.float32))
+    eng.generate_samples()
+    sched = _lib.Schedule(items, offset, order, mk['batch_size'], mk['n_sample'], mode=0)
+    assert sched.n_steps >= 2 * (K + W), 'synthetic workload too small'
+    B = mk['batch_size']
+    N = B + mk['n_sample']
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm: warm-up window, then K timed steps from an uploaded window
+    eng.reset_hidden()
+    eng.upload_steps(sched, 0, W)
+    eng.run_uploaded(W, want_cost=False)
+    eng.upload_steps(sched, W, K)
+    launches0 = eng.kernel_launches()
+    clocks = ClockSampler(local_rank); clocks.start()
+    time.sleep(0.3)
+    barrier()
+    t0 = time.time()
+    costs, dev_ms = eng.run_uploaded(K, want_cost=True)
+    barrier()
+    wall = time.time() - t0
+    launches = eng.kernel_launches() - launches0
+    if dist is not None:
+        t = torch.tensor([dev_ms], device='cuda'); dist.all_reduce(t, op=dist.ReduceOp.MAX); dev_ms = float(t.item())
+    value = world * K / (dev_ms / 1000.0)
+    assert np.isfinite(costs).all(), 'non-finite cost in the timed region'
+    # ---- end-to-end arm: host schedule arrays in, costs out, every window (H2D + plan + steps + D2H inside the timing)
+    first = W + K
+    barrier()
+    t0 = time.time()
+    c2 = eng.train_steps(sched, first, K)
+    barrier()
+    e2e_s = time.time() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device='cuda'); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
+    clocks.stop_flag = True
+    e2e_value = world * K / e2e_s
+    h2d = B * (4 + 4 + 4 + 1) + 12
+    # ---- per-kernel roofline from CUDA events around every launch of one more pass over a short window
+    prof_n = min(K, 512)
+    eng.upload_steps(sched, first + K, prof_n)
+    prof = eng.profile_uploaded()
+    peak, peak_src = peak_hbm()
+    dom_name = max(prof, key=lambda k: prof[k][0])
+    lg_ms, lg_n = prof['lossgrad_update']
+    lg_bytes = algo_bytes_lossgrad(N, mk['layers'][-1], mk['momentum'] > 0)
+    achieved = lg_bytes / (lg_ms / lg_n * 1e-3) / 1e9
+    phase_us = {k: round(v[0] / v[1] * 1000.0, 3) for k, v in prof.items()}
+    out = {
+        'metric': 'mini-batches/sec', 'value': value, 'unit': 'mb/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+        'ms_per_step': dev_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD['name'], 'n_items': WORKLOAD['n_items'], 'global_batch': B * world, 'n_sample': mk['n_sample'],
+                   'layers': mk['layers'], 'params': 'param_samples/rsc15_bpr-max.py', 'parallelism': 'dp%d' % world,
+                   'l2': 'working set (item tables + Adagrad/momentum state = 180 MB) larger than L2; rows touched change every step',
+                   'step_mode': int(cfg.step_mode), 'events_per_sec': value * B},
+        'e2e': {'value': e2e_value, 'unit': 'mb/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4},
+        'gpu_launches': int(launches),
+        'clocks': clocks.summary(),
+        'roofline': {'bound': 'hbm', 'kernel': 'k_lossgrad (loss gradient + sparse Adagrad/momentum update of Wy/By rows)',
+                     'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                     'peak_source': peak_src, 'algorithmic_bytes_per_launch': lg_bytes, 'us_per_launch': lg_ms / lg_n * 1000.0,
+                     'dominant_phase_by_time': dom_name, 'phase_us': phase_us,
+                     'whole_step': {'algorithmic_bytes': ALGO_BYTES_PER_STEP, 'achieved': ALGO_BYTES_PER_STEP * (value / world) / 1e9,
+                                    'frac': ALGO_BYTES_PER_STEP * (value / world) / 1e9 / peak,
+                                    'note': 'latency-bound: dependent phases per mini-batch, working set near L2 size'}},
+        'wall_s_timed_region': wall,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, done, cores = oracle_steps_per_sec(items, offset, order, supports, 10, 2000, budget_s=20.0)
+        out['cpu_baseline'] = {'value': v, 'unit': 'mb/s', 'cores': cores, 'kind': 'port',
+                               'sample': '%d mini-batches of the same workload through the NumPy oracle (~20 s)' % done}
+    if rank == 0:
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

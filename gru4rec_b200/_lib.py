@@ -38,6 +38,7 @@ EXPORTS = [
     'g4r_mrg_uniform', 'g4r_searchsorted', 'g4r_gather_rows',
     'g4r_schedule_build', 'g4r_schedule_free', 'g4r_schedule_steps', 'g4r_schedule_events', 'g4r_schedule_export',
     'g4r_train_step', 'g4r_train_steps', 'g4r_upload_steps', 'g4r_run_uploaded', 'g4r_kernel_launches',
+    'g4r_profile_uploaded', 'g4r_phase_name', 'g4r_phase_count',
     'g4r_eval_schedule', 'g4r_predict', 'g4r_reset_eval_hidden',
 ]
 
@@ -86,6 +87,9 @@ def load():
     lib.g4r_upload_steps.argtypes = [vp, vp, i64, i64]
     lib.g4r_run_uploaded.argtypes = [vp, vp, C.POINTER(C.c_float)]
     lib.g4r_kernel_launches.argtypes = [vp]; lib.g4r_kernel_launches.restype = i64
+    lib.g4r_profile_uploaded.argtypes = [vp, vp, vp, i32]
+    lib.g4r_phase_name.argtypes = [i32]; lib.g4r_phase_name.restype = C.c_char_p
+    lib.g4r_phase_count.restype = C.c_int
     lib.g4r_eval_schedule.argtypes = [vp, vp, vp, i32, i32, vp, vp, C.POINTER(i64)]
     lib.g4r_predict.argtypes = [vp, vp, i32, vp, vp]
     lib.g4r_reset_eval_hidden.argtypes = [vp]
@@ -304,6 +308,13 @@ class Engine(object):
         ms = C.c_float()
         self._check(self.lib.g4r_run_uploaded(self.h, _ptr(costs), C.byref(ms)))
         return costs, ms.value
+
+    def profile_uploaded(self):
+        """{phase name: (total device ms, launches)} for one pass over the uploaded window."""
+        n = self.lib.g4r_phase_count()
+        ms = np.zeros(n, dtype=np.float32); cnt = np.zeros(n, dtype=np.int32)
+        self._check(self.lib.g4r_profile_uploaded(self.h, _ptr(ms), _ptr(cnt), n))
+        return {self.lib.g4r_phase_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i] > 0}
 
     def kernel_launches(self):
         return self.lib.g4r_kernel_launches(self.h)

@@ -54,7 +54,22 @@ struct g4r_handle {
   int win_steps = 0;
   int64_t launches = 0;
   int npow2 = 0;
+  // per-phase profiling (g4r_profile_uploaded)
+  bool prof = false;
+  std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_phase;
 };
+
+enum { PH_GATHER = 0, PH_F1, PH_F2, PH_SCORE, PH_STATS, PH_LOSSGRAD, PH_B1, PH_B2, PH_B3, PH_DENSE, PH_SPARSE_IN, PH_COUNT };
+static const char* kPhaseNames[PH_COUNT] = {"gather_in", "gru_rz", "gru_h", "score", "stats", "lossgrad_update", "gru_bwd_elem", "gru_bwd_dHr", "gru_bwd_din", "dense_update", "sparse_in_update"};
+
+// LAUNCH(phase, kernel<<<...>>>(...)): counts the launch and, when profiling, brackets it with CUDA events
+#define LAUNCH(ph, ...) do { \
+    cudaEvent_t e0_ = nullptr, e1_ = nullptr; \
+    if (h->prof) { cudaEventCreate(&e0_); cudaEventCreate(&e1_); cudaEventRecord(e0_, h->stream); } \
+    __VA_ARGS__; \
+    h->launches++; \
+    if (h->prof) { cudaEventRecord(e1_, h->stream); h->prof_ev.push_back(e0_); h->prof_ev.push_back(e1_); h->prof_phase.push_back(ph); } \
+  } while (0)
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return G4R_ERR_CUDA; } } while (0)
 #define FAIL(code, msg) do { h->err = (msg); return (code); } while (0)
@@ -239,29 +254,24 @@ static int enqueue_train_step(g4r_handle* h, const int* base, int off) {
   const ModelDev& md = h->md;
   cudaStream_t st = h->stream;
   const int B = md.B;
-  if (md.mode != 0) { k_gather_in<<<std::max(1, (B + 7) / 8), 256, 0, st>>>(md, base, off, 1); h->launches++; }
+  if (md.mode != 0) LAUNCH(PH_GATHER, k_gather_in<<<std::max(1, (B + 7) / 8), 256, 0, st>>>(md, base, off, 1));
   for (int li = 0; li < md.n_layers; li++) {
     const LayerDev& ly = md.layer[li];
-    k_f1<<<tiles2(2 * ly.L, B), GEMM_THREADS, 0, st>>>(md, base, off, li, ly.H);
-    k_f2<<<tiles2(ly.L, B), GEMM_THREADS, 0, st>>>(md, base, off, li, ly.H, 1);
-    h->launches += 2;
+    LAUNCH(PH_F1, k_f1<<<tiles2(2 * ly.L, B), GEMM_THREADS, 0, st>>>(md, base, off, li, ly.H));
+    LAUNCH(PH_F2, k_f2<<<tiles2(ly.L, B), GEMM_THREADS, 0, st>>>(md, base, off, li, ly.H, 1));
   }
-  k_score<<<md.NCH, SC_THREADS, score_smem_bytes(h->Bmax), st>>>(md, base, off);
-  k_stats<<<1, 256, (size_t)(h->Bmax + 32) * sizeof(float), st>>>(md, base, off);
-  k_lossgrad<<<md.NCH, SC_THREADS, lossgrad_smem_bytes(md.Bld), st>>>(md, base, off);
-  h->launches += 3;
+  LAUNCH(PH_SCORE, k_score<<<md.NCH, SC_THREADS, score_smem_bytes(h->Bmax), st>>>(md, base, off));
+  LAUNCH(PH_STATS, k_stats<<<1, 256, (size_t)(h->Bmax + 32) * sizeof(float), st>>>(md, base, off));
+  LAUNCH(PH_LOSSGRAD, k_lossgrad<<<md.NCH, SC_THREADS, lossgrad_smem_bytes(md.Bld), st>>>(md, base, off));
   for (int li = md.n_layers - 1; li >= 0; li--) {
     const LayerDev& ly = md.layer[li];
-    k_b1<<<std::max(1, std::min(h->n_sm, (B * ly.L + 255) / 256)), 256, 0, st>>>(md, base, off, li);
-    k_b2<<<tiles2(ly.L, B), GEMM_THREADS, 0, st>>>(md, base, off, li);
-    h->launches += 2;
-    if (ly.in_dim > 0) { k_b3<<<tiles2(ly.in_dim, B), GEMM_THREADS, 0, st>>>(md, base, off, li); h->launches++; }
+    LAUNCH(PH_B1, k_b1<<<std::max(1, std::min(h->n_sm, (B * ly.L + 255) / 256)), 256, 0, st>>>(md, base, off, li));
+    LAUNCH(PH_B2, k_b2<<<tiles2(ly.L, B), GEMM_THREADS, 0, st>>>(md, base, off, li));
+    if (ly.in_dim > 0) LAUNCH(PH_B3, k_b3<<<tiles2(ly.in_dim, B), GEMM_THREADS, 0, st>>>(md, base, off, li));
     const DenseJobs dj = dense_jobs(ly.L, ly.in_dim);
-    k_dense<<<dj.nWh + dj.nWrz + dj.nWx + dj.nBh, GEMM_THREADS, 0, st>>>(md, base, off, li);
-    h->launches++;
+    LAUNCH(PH_DENSE, k_dense<<<dj.nWh + dj.nWrz + dj.nWx + dj.nBh, GEMM_THREADS, 0, st>>>(md, base, off, li));
   }
-  k_sparse_in<<<B, 128, 0, st>>>(md, base, off);
-  h->launches++;
+  LAUNCH(PH_SPARSE_IN, k_sparse_in<<<B, 128, 0, st>>>(md, base, off));
   return G4R_OK;
 }
 
@@ -751,6 +761,28 @@ extern "C" int g4r_run_uploaded(g4r_handle* h, float* cost_out, float* device_ms
   // re-running the same window is allowed for benchmarking: undo the pointer advance only on request (not here)
   return G4R_OK;
 }
+
+extern "C" int g4r_profile_uploaded(g4r_handle* h, float* phase_ms, int32_t* phase_launches, int32_t n_phases) {
+  if (!h || !phase_ms || !phase_launches || n_phases < PH_COUNT) return G4R_ERR_INVALID;
+  if (h->win_steps <= 0) FAIL(G4R_ERR_STATE, "no uploaded window");
+  cudaSetDevice(h->cfg.device);
+  h->prof = true; h->prof_ev.clear(); h->prof_phase.clear();
+  int rc = run_window(h, h->win_steps);
+  h->prof = false;
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < n_phases; i++) { phase_ms[i] = 0.f; phase_launches[i] = 0; }
+  for (size_t k = 0; k < h->prof_phase.size(); k++) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->prof_ev[2 * k], h->prof_ev[2 * k + 1]);
+    phase_ms[h->prof_phase[k]] += ms; phase_launches[h->prof_phase[k]]++;
+    cudaEventDestroy(h->prof_ev[2 * k]); cudaEventDestroy(h->prof_ev[2 * k + 1]);
+  }
+  h->prof_ev.clear(); h->prof_phase.clear();
+  return G4R_OK;
+}
+extern "C" const char* g4r_phase_name(int32_t i) { return (i >= 0 && i < PH_COUNT) ? kPhaseNames[i] : ""; }
+extern "C" int g4r_phase_count(void) { return PH_COUNT; }
 
 extern "C" int g4r_train_steps(g4r_handle* h, const g4r_schedule* s, int64_t first, int64_t n, float* cost_out, int64_t* nan_step) {
   if (!h || !s) return G4R_ERR_INVALID;

@@ -133,6 +133,12 @@ int g4r_train_steps(g4r_handle* h, const g4r_schedule* s, int64_t first, int64_t
 /* Two-phase variant used for device-resident timing: upload (H2D + per-step column plans) then run. */
 int g4r_upload_steps(g4r_handle* h, const g4r_schedule* s, int64_t first, int64_t n);
 int g4r_run_uploaded(g4r_handle* h, float* cost_out /* may be NULL */, float* device_ms /* may be NULL */);
+/* Re-runs the uploaded window with CUDA events around every kernel launch; sums device time and launch counts
+ * per phase (index i is named by g4r_phase_name(i); n_phases must be >= g4r_phase_count()).  For bench.py's
+ * roofline: achieved bytes/s of the dominant kernel = its algorithmic bytes / its mean duration. */
+int g4r_profile_uploaded(g4r_handle* h, float* phase_ms, int32_t* phase_launches, int32_t n_phases);
+const char* g4r_phase_name(int32_t i);
+int g4r_phase_count(void);
 /* Counters for bench.py: kernels launched by this handle so far. */
 int64_t g4r_kernel_launches(const g4r_handle* h);
 

@@ -334,9 +334,8 @@ class MRGStreams:
         out = np.empty(n, dtype=np.float32)
         pos = 0
         while pos < n:
-            u = mrg_next(st)
             k = min(ns, n - pos)
-            out[pos:pos + k] = u[:k]
+            out[pos:pos + k] = mrg_next(st[:k])      # a stream only advances when it produces a sample
             pos += k
         return out
 

@@ -85,7 +85,7 @@ def peak_hbm():
 def build_workload(n_steps_needed, seed=0):
     from gru4rec_b200.synth import make_session_arrays
     B = WORKLOAD['model']['batch_size']
-    n_events = int((n_steps_needed + 64) * B * 1.6) + 20000
+    n_events = max(int((n_steps_needed + 64) * B * 1.6) + 20000, 4 * WORKLOAD["n_items"])
     return make_session_arrays(WORKLOAD['n_items'], n_events, seed=seed)
 
 
@@ -170,8 +170,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     K, W = args.steps, max(args.warmup, 3)
-    sys.path.insert(0, os.path.join(ROOT, 'tests'))
-    from gpu_utils import make_cfg
+    make_cfg = _lib.make_config
     mk = dict(WORKLOAD['model'])
     cfg = make_cfg(WORKLOAD['n_items'], mk, sample_store=WORKLOAD['sample_store'], eval_lanes=0,
                    max_resident_steps=max(K, W) + 8, step_mode=max(args.step_mode, 0))

@@ -38,7 +38,7 @@ EXPORTS = [
     'g4r_mrg_uniform', 'g4r_searchsorted', 'g4r_gather_rows',
     'g4r_schedule_build', 'g4r_schedule_free', 'g4r_schedule_steps', 'g4r_schedule_events', 'g4r_schedule_export',
     'g4r_train_step', 'g4r_train_steps', 'g4r_upload_steps', 'g4r_run_uploaded', 'g4r_kernel_launches',
-    'g4r_profile_uploaded', 'g4r_phase_name', 'g4r_phase_count',
+    'g4r_profile_uploaded', 'g4r_phase_name', 'g4r_phase_count', 'g4r_persistent_stamps',
     'g4r_eval_schedule', 'g4r_predict', 'g4r_reset_eval_hidden',
 ]
 
@@ -90,6 +90,7 @@ def load():
     lib.g4r_profile_uploaded.argtypes = [vp, vp, vp, i32]
     lib.g4r_phase_name.argtypes = [i32]; lib.g4r_phase_name.restype = C.c_char_p
     lib.g4r_phase_count.restype = C.c_int
+    lib.g4r_persistent_stamps.argtypes = [vp, i32, vp, i64]
     lib.g4r_eval_schedule.argtypes = [vp, vp, vp, i32, i32, vp, vp, C.POINTER(i64)]
     lib.g4r_predict.argtypes = [vp, vp, i32, vp, vp]
     lib.g4r_reset_eval_hidden.argtypes = [vp]
@@ -119,6 +120,41 @@ def parse_act(name):
         p = [float(x) for x in name.split('-')[1:]]
         return ACT['selu'], p[0], p[1]
     raise NotImplementedError
+
+
+def make_config(n_items, mk, sample_store=0, eval_lanes=0, max_resident_steps=0, step_mode=0):
+    cfg = G4RConfig()
+    layers = mk.get('layers', [100])
+    cfg.n_items = n_items
+    cfg.n_layers = len(layers)
+    for i, l in enumerate(layers):
+        cfg.layers[i] = l
+    cfg.batch_size = mk.get('batch_size', 32)
+    cfg.constrained_embedding = 1 if mk.get('constrained_embedding') else 0
+    cfg.embedding = 0 if mk.get('constrained_embedding') else int(mk.get('embedding', 0) or 0)
+    cfg.loss = LOSS[mk.get('loss', 'bpr-max')]
+    cfg.final_act, cfg.final_act_p1, cfg.final_act_p2 = parse_act(mk.get('final_act', 'linear'))
+    cfg.hidden_act, cfg.hidden_act_p1, cfg.hidden_act_p2 = parse_act(mk.get('hidden_act', 'tanh'))
+    cfg.dropout_p_hidden = mk.get('dropout_p_hidden', 0.0)
+    cfg.dropout_p_embed = mk.get('dropout_p_embed', 0.0)
+    cfg.learning_rate = mk.get('learning_rate', 0.1)
+    cfg.momentum = mk.get('momentum', 0.0)
+    cfg.lmbd = mk.get('lmbd', 0.0)
+    cfg.n_sample = mk.get('n_sample', 2048)
+    cfg.sample_alpha = mk.get('sample_alpha', 0.75)
+    cfg.smoothing = mk.get('smoothing', 0.0)
+    cfg.bpreg = mk.get('bpreg', 1.0)
+    cfg.logq = mk.get('logq', 0.0)
+    cfg.adapt = ADAPT[mk.get('adapt', 'adagrad')]
+    cfg.sample_store = sample_store
+    cfg.dropout_seed = mk.get('dropout_seed', 0)
+    cfg.mrg_seed = 12345
+    cfg.max_resident_steps = max_resident_steps
+    cfg.world_size, cfg.rank = 1, 0
+    cfg.eval_batch_size = eval_lanes
+    cfg.step_mode = step_mode
+    return cfg
+
 
 
 class Schedule(object):
@@ -315,6 +351,11 @@ class Engine(object):
         ms = np.zeros(n, dtype=np.float32); cnt = np.zeros(n, dtype=np.int32)
         self._check(self.lib.g4r_profile_uploaded(self.h, _ptr(ms), _ptr(cnt), n))
         return {self.lib.g4r_phase_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i] > 0}
+
+    def persistent_stamps(self, enable=True, n_steps=0):
+        out = np.zeros((n_steps, 16), dtype=np.uint64) if n_steps > 0 else None
+        self._check(self.lib.g4r_persistent_stamps(self.h, 1 if enable else 0, _ptr(out), n_steps))
+        return out
 
     def kernel_launches(self):
         return self.lib.g4r_kernel_launches(self.h)

@@ -11,7 +11,8 @@ constexpr int EV_LDS = EV_KT + 4;
 constexpr int EV_THREADS = 256;
 
 // target score of every lane, computed with the same sequential k order as the tile kernel (bitwise equal)
-__global__ void __launch_bounds__(128) k_eval_tgt(ModelDev md, int s, float* tgt, int* cnt) {
+__global__ void __launch_bounds__(128) k_eval_tgt(int slot, int s, float* tgt, int* cnt) {
+  const ModelDev& md = MD;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   const int M = md.wM[s];
   if (b >= M) return;
@@ -30,7 +31,8 @@ __global__ void __launch_bounds__(128) k_eval_tgt(ModelDev md, int s, float* tgt
 }
 
 template <bool WRITE>
-__global__ void __launch_bounds__(EV_THREADS) k_eval_score(ModelDev md, int s, const float* __restrict__ tgt, int* cnt, float* out) {
+__global__ void __launch_bounds__(EV_THREADS) k_eval_score(int slot, int s, const float* __restrict__ tgt, int* cnt, float* out) {
+  const ModelDev& md = MD;
   extern __shared__ __align__(16) float smem[];
   float* sY = smem;                        // [EV_TB][EV_LDS]
   float* sW = sY + EV_TB * EV_LDS;         // [EV_IT][EV_LDS]
@@ -112,7 +114,8 @@ __global__ void __launch_bounds__(EV_THREADS) k_eval_score(ModelDev md, int s, c
 static size_t eval_smem_bytes() { return (size_t)(EV_TB * EV_LDS + EV_IT * EV_LDS) * sizeof(float) + EV_TB * 2 * sizeof(int) + 64; }
 
 // ranks + per-cutoff sums (evaluation.py:60-75), accumulated in double on the device
-__global__ void k_eval_rank(ModelDev md, int s, const int* cnt, const int* cut, int n_cut, int mode, double* sums) {
+__global__ void k_eval_rank(int slot, int s, const int* cnt, const int* cut, int n_cut, int mode, double* sums) {
+  const ModelDev& md = MD;
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const int M = md.wM[s];
   for (int b = 0; b < M; b++) {
@@ -128,7 +131,8 @@ __global__ void k_eval_rank(ModelDev md, int s, const int* cnt, const int* cut, 
 }
 
 // final activation of the predict path (gru4rec.py:499-505): elementwise, softmax, or softmax for softmax_logit
-__global__ void __launch_bounds__(256) k_predict_act(ModelDev md, float* out, int batch) {
+__global__ void __launch_bounds__(256) k_predict_act(int slot, float* out, int batch) {
+  const ModelDev& md = MD;
   const int b = blockIdx.x;
   if (b >= batch) return;
   float* row = out + (size_t)b * md.n_items;
@@ -163,6 +167,7 @@ struct EvalCtx {
   int *dX = nullptr, *dY = nullptr, *dSlot = nullptr, *dM = nullptr, *dSti = nullptr; uint8_t* dF = nullptr; uint32_t* dG = nullptr;
   int* dCut = nullptr; double* dSums = nullptr; float* dOut = nullptr; size_t out_cap = 0;
   int cap = 0;
+  int slot = -1;
 };
 static std::map<g4r_handle*, EvalCtx> g_eval;
 
@@ -173,6 +178,7 @@ static void eval_release(g4r_handle* h) {
   cudaFreeHost(e.hX); cudaFreeHost(e.hY); cudaFreeHost(e.hSlot); cudaFreeHost(e.hF); cudaFreeHost(e.hM); cudaFreeHost(e.hSti); cudaFreeHost(e.hG);
   cudaFree(e.dX); cudaFree(e.dY); cudaFree(e.dSlot); cudaFree(e.dF); cudaFree(e.dM); cudaFree(e.dSti); cudaFree(e.dG);
   cudaFree(e.dCut); cudaFree(e.dSums); if (e.dOut) cudaFree(e.dOut);
+  slot_free(e.slot);
   g_eval.erase(it);
 }
 
@@ -191,6 +197,9 @@ static int eval_ctx(g4r_handle* h, EvalCtx** out) {
   e.mde = h->md;
   e.mde.B = e.Be;
   e.mde.wX = e.dX; e.mde.wY = e.dY; e.mde.wSlot = e.dSlot; e.mde.wM = e.dM; e.mde.wSti = e.dSti; e.mde.wF = e.dF; e.mde.wG = e.dG;
+  e.slot = slot_alloc();
+  if (e.slot < 0) FAIL(G4R_ERR_STATE, "too many live g4r handles in this process");
+  CK(slot_upload(e.slot, e.mde, h->stream));
   cudaFuncSetAttribute(k_eval_score<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eval_smem_bytes());
   cudaFuncSetAttribute(k_eval_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eval_smem_bytes());
   g_eval[h] = e;
@@ -201,11 +210,11 @@ static int eval_ctx(g4r_handle* h, EvalCtx** out) {
 static int eval_forward(g4r_handle* h, EvalCtx* e, int s) {
   const ModelDev& md = e->mde;
   cudaStream_t st = h->stream;
-  if (md.mode != 0) { k_gather_in<<<std::max(1, (e->Be + 7) / 8), 256, 0, st>>>(md, nullptr, s, 0); h->launches++; }
+  if (md.mode != 0) { k_gather_in<<<std::max(1, (e->Be + 7) / 8), 256, 0, st>>>(e->slot, nullptr, s, 0); h->launches++; }
   for (int li = 0; li < md.n_layers; li++) {
     const LayerDev& ly = md.layer[li];
-    k_f1<<<tiles2(2 * ly.L, e->Be), GEMM_THREADS, 0, st>>>(md, nullptr, s, li, h->He[li]);
-    k_f2<<<tiles2(ly.L, e->Be), GEMM_THREADS, 0, st>>>(md, nullptr, s, li, h->He[li], 0);
+    k_f1<<<tiles2(2 * ly.L, e->Be), GEMM_THREADS, 0, st>>>(e->slot, nullptr, s, li, h->He[li]);
+    k_f2<<<tiles2(ly.L, e->Be), GEMM_THREADS, 0, st>>>(e->slot, nullptr, s, li, h->He[li], 0);
     h->launches += 2;
   }
   return G4R_OK;
@@ -219,8 +228,8 @@ extern "C" int g4r_eval_schedule(g4r_handle* h, const g4r_schedule* s, const int
   EvalCtx* e = nullptr;
   int rc = eval_ctx(h, &e);
   if (rc) return rc;
-  if (s->B != e->Be) FAIL(G4R_ERR_INVALID, "schedule batch size != eval_batch_size");
-  const int Be = e->Be, I = h->md.n_items;
+  if (s->B > e->Be) FAIL(G4R_ERR_INVALID, "schedule batch size exceeds eval_batch_size");
+  const int Be = e->Be, Bs = s->B, I = h->md.n_items;
   cudaStream_t st = h->stream;
   for (int i = 0; i < h->md.n_layers; i++) CK(cudaMemsetAsync(h->He[i], 0, (size_t)Be * h->md.layer[i].ldL * sizeof(float), st));   // gru4rec.py:731-733
   CK(cudaMemcpyAsync(e->dCut, cut_off, n_cut * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -229,10 +238,12 @@ extern "C" int g4r_eval_schedule(g4r_handle* h, const g4r_schedule* s, const int
   while (done < s->n_steps) {
     const int64_t w = std::min<int64_t>(e->cap, s->n_steps - done);
     CK(cudaStreamSynchronize(st));   // staging buffers are reused
-    memcpy(e->hX, s->X.data() + done * Be, (size_t)w * Be * sizeof(int));
-    memcpy(e->hY, s->Y.data() + done * Be, (size_t)w * Be * sizeof(int));
-    memcpy(e->hSlot, s->slots.data() + done * Be, (size_t)w * Be * sizeof(int));
-    memcpy(e->hF, s->F.data() + done * Be, (size_t)w * Be);
+    for (int64_t i = 0; i < w; i++) {   // the window arrays are strided by the engine's scoring lanes
+      memcpy(e->hX + i * Be, s->X.data() + (done + i) * Bs, (size_t)Bs * sizeof(int));
+      memcpy(e->hY + i * Be, s->Y.data() + (done + i) * Bs, (size_t)Bs * sizeof(int));
+      memcpy(e->hSlot + i * Be, s->slots.data() + (done + i) * Bs, (size_t)Bs * sizeof(int));
+      memcpy(e->hF + i * Be, s->F.data() + (done + i) * Bs, (size_t)Bs);
+    }
     memcpy(e->hM, s->M.data() + done, (size_t)w * sizeof(int));
     for (int64_t i = 0; i < w; i++) {
       e->hSti[i] = -1; e->hG[i] = 0;
@@ -251,9 +262,9 @@ extern "C" int g4r_eval_schedule(g4r_handle* h, const g4r_schedule* s, const int
     CK(cudaMemcpyAsync(e->dG, e->hG, (size_t)w * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     for (int64_t i = 0; i < w; i++) {
       eval_forward(h, e, (int)i);
-      k_eval_tgt<<<(Be + 127) / 128, 128, 0, st>>>(e->mde, (int)i, h->dTgt, h->dRankCnt);
-      k_eval_score<false><<<(I + EV_IT - 1) / EV_IT, EV_THREADS, eval_smem_bytes(), st>>>(e->mde, (int)i, h->dTgt, h->dRankCnt, nullptr);
-      k_eval_rank<<<1, 32, 0, st>>>(e->mde, (int)i, h->dRankCnt, e->dCut, n_cut, mode, e->dSums);
+      k_eval_tgt<<<(Be + 127) / 128, 128, 0, st>>>(e->slot, (int)i, h->dTgt, h->dRankCnt);
+      k_eval_score<false><<<(I + EV_IT - 1) / EV_IT, EV_THREADS, eval_smem_bytes(), st>>>(e->slot, (int)i, h->dTgt, h->dRankCnt, nullptr);
+      k_eval_rank<<<1, 32, 0, st>>>(e->slot, (int)i, h->dRankCnt, e->dCut, n_cut, mode, e->dSums);
       h->launches += 3;
     }
     CK(cudaGetLastError());
@@ -292,8 +303,8 @@ extern "C" int g4r_predict(g4r_handle* h, const int32_t* X, int32_t batch, const
   const size_t need = (size_t)batch * I;
   if (e->out_cap < need) { if (e->dOut) cudaFree(e->dOut); CK(cudaMalloc(&e->dOut, need * sizeof(float))); e->out_cap = need; }
   eval_forward(h, e, 0);
-  k_eval_score<true><<<(I + EV_IT - 1) / EV_IT, EV_THREADS, eval_smem_bytes(), st>>>(e->mde, 0, nullptr, nullptr, e->dOut);
-  k_predict_act<<<batch, 256, 0, st>>>(e->mde, e->dOut, batch);
+  k_eval_score<true><<<(I + EV_IT - 1) / EV_IT, EV_THREADS, eval_smem_bytes(), st>>>(e->slot, 0, nullptr, nullptr, e->dOut);
+  k_predict_act<<<batch, 256, 0, st>>>(e->slot, e->dOut, batch);
   h->launches += 2;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, e->dOut, need * sizeof(float), cudaMemcpyDeviceToHost, st));

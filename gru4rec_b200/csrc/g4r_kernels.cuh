@@ -23,6 +23,7 @@
 #define G4R_NSTAT 8
 
 struct ActSpec { int kind; float p1, p2; };
+struct GridBar { unsigned int count; unsigned int gen; unsigned int pad[30]; };   // grid barrier state (persistent mode)
 
 struct LayerDev {
   int L, ldL, ld2, ld3;
@@ -354,7 +355,13 @@ __device__ void phase_score(const ModelDev& md, int s, int chunk, float* smem) {
   const int N = M + (sti >= 0 ? md.S : 0);
   const int* cbeg = md.pCbeg + (size_t)s * (md.NCH + 1);
   const int cb = cbeg[chunk], ce = cbeg[chunk + 1];
-  if (cb >= ce) return;
+  if (cb >= ce) {   // empty chunk: neutral partial statistics
+    for (int b = threadIdx.x; b < M; b += blockDim.x) {
+      float* st = md.stat + ((size_t)chunk * md.B + b) * G4R_NSTAT;
+      st[0] = -INFINITY; st[1] = 0.f; st[2] = 0.f; st[3] = 0.f; st[4] = 0.f; st[5] = 0.f; st[6] = 0.f; st[7] = 0.f;
+    }
+    return;
+  }
   const int L = md.L, ldL = md.ldL;
   const float* Y = md.layer[md.n_layers - 1].y;
   const int* pItem = md.pItem + (size_t)s * md.NP;
@@ -492,12 +499,11 @@ __device__ void phase_stats(const ModelDev& md, int s, float* smem) {
   for (int b = warp; b < M; b += nwarp) {
     float m = -INFINITY, Z = 0.f, A = 0.f, Q = 0.f, D = 0.f, T = 0.f, tt = 0.f;
     for (int c = lane; c < md.NCH; c += 32) {
-      if (cbeg[c] >= cbeg[c + 1]) continue;
       const float* st = md.stat + ((size_t)c * md.B + b) * G4R_NSTAT;
       if (md.loss == G4R_LOSS_BPR || md.loss == G4R_LOSS_TOP1) { A += st[2]; D += st[4]; }
       else stat_merge(m, Z, A, Q, D, st[0], st[1], st[2], st[3], st[4]);
       if (st[6] > 0.f) T = st[5];
-      tt = st[7];
+      if (c == 0) tt = st[7];      // chunk 0 is never empty
     }
     // butterfly merge across lanes
 #pragma unroll
@@ -611,7 +617,11 @@ __device__ void phase_lossgrad(const ModelDev& md, int s, int chunk, float* smem
   const int N = M + (sti >= 0 ? md.S : 0);
   const int* cbeg = md.pCbeg + (size_t)s * (md.NCH + 1);
   const int cb = cbeg[chunk], ce = cbeg[chunk + 1];
-  if (cb >= ce) return;
+  if (cb >= ce) {   // empty chunk: its partial dL/dh must read as zero
+    float* pz = md.part + (size_t)chunk * md.B * md.ldL;
+    for (int i = threadIdx.x; i < M * md.ldL; i += blockDim.x) pz[i] = 0.f;
+    return;
+  }
   const int L = md.L, ldL = md.ldL;
   (void)L;
   const float* Y = md.layer[md.n_layers - 1].y;
@@ -764,8 +774,14 @@ __device__ void phase_b1(const ModelDev& md, int li, int s, int cta, int ncta) {
     float dy;
     if (last) {
       dy = 0.f;
-      for (int ch = 0; ch < md.NCH; ch++)
-        if (cbeg[ch] < cbeg[ch + 1]) dy += md.part[((size_t)ch * md.B + b) * ldL + c];
+      // fixed-order sum of the per-chunk partials, four independent loads in flight
+      const float* pp = md.part + (size_t)b * ldL + c;
+      const size_t cs = (size_t)md.B * ldL;
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+      int ch = 0;
+      for (; ch + 4 <= md.NCH; ch += 4) { d0 += pp[(size_t)ch * cs]; d1 += pp[(size_t)(ch + 1) * cs]; d2 += pp[(size_t)(ch + 2) * cs]; d3 += pp[(size_t)(ch + 3) * cs]; }
+      for (; ch < md.NCH; ch++) d0 += pp[(size_t)ch * cs];
+      dy = (d0 + d1) + (d2 + d3);
     } else dy = ly.dy[(size_t)b * ldL + c];
     float dh = dy;
     if (md.p_drop_h > 0.f) dh *= drop_scale(md.drop_seed, gstep, (uint32_t)li, (uint32_t)(b * L + c), retain);

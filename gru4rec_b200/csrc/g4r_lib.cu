@@ -55,7 +55,11 @@ struct g4r_handle {
   int64_t launches = 0;
   int npow2 = 0;
   // per-phase profiling (g4r_profile_uploaded)
-  bool prof = false;
+  int slot = -1;
+  cudaGraphExec_t graphU = nullptr, graph1 = nullptr; int graph_unroll = 16;
+  bool use_graph = true;
+  GridBar* dGridBar = nullptr; unsigned long long* dStamp = nullptr; int pk_blocks = 0; size_t pk_smem = 0;
+  bool prof = false; bool stamp_on = false;
   std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_phase;
 };
 
@@ -188,6 +192,8 @@ static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
   md.pItem = cv.take<int>((size_t)CAP * NP); md.pPos = cv.take<int>((size_t)CAP * NP);
   md.pTcol = cv.take<int>((size_t)CAP * B); md.pCbeg = cv.take<int>((size_t)CAP * (NCH + 1));
   int* dStepBase = cv.take<int>(4);
+  GridBar* dGridBar = cv.take<GridBar>(1);
+  unsigned long long* dStamp = cv.take<unsigned long long>((size_t)CAP * 16);
   // sampling
   float* dP = cv.take<float>(c.n_items); float* dL0t = cv.take<float>(c.n_items); float* dL0s = cv.take<float>(c.n_items);
   int* dST = store ? cv.take<int>((size_t)gen_len * c.n_sample) : nullptr;
@@ -200,6 +206,7 @@ static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
     md.ST = dST; md.logP0t = dL0t; md.logP0s = dL0s;
     h->md = md; h->Bmax = Bmax; h->CAP = CAP; h->gen_len = store ? gen_len : 0;
     h->dX = dX; h->dY = dY; h->dSlot = dSlot; h->dM = dM; h->dSti = dSti; h->dXnext = dXnext; h->dF = dF; h->dXflag = dXflag; h->dG = dG;
+    h->dGridBar = dGridBar; h->dStamp = dStamp;
     h->dStepBase = dStepBase; h->dP = dP; h->dLogP0t = dL0t; h->dLogP0s = dL0s; h->dST = dST; h->dU = dU; h->dMrgState = dMrg;
     h->dRankCnt = dRank; h->dTgt = dTgt;
     h->npow2 = next_pow2(B + S);
@@ -209,43 +216,56 @@ static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
 // ------------------------------------------------------------------------------------------------
 // kernels: one per phase (thin wrappers around the phase functions)
 // ------------------------------------------------------------------------------------------------
+// Model descriptors live in constant memory (one slot per handle / per scoring context) so that kernel launches
+// carry a few scalars instead of a 2 KB by-value struct (the by-value launch cost 16 us of CPU time each).
+#define G4R_MAX_SLOTS 24
+__constant__ ModelDev c_models[G4R_MAX_SLOTS];
+static bool g_slot_used[G4R_MAX_SLOTS] = {};
+static int slot_alloc() { for (int i = 0; i < G4R_MAX_SLOTS; i++) if (!g_slot_used[i]) { g_slot_used[i] = true; return i; } return -1; }
+static void slot_free(int i) { if (i >= 0 && i < G4R_MAX_SLOTS) g_slot_used[i] = false; }
+static cudaError_t slot_upload(int slot, const ModelDev& md, cudaStream_t st) {
+  return cudaMemcpyToSymbolAsync(c_models, &md, sizeof(ModelDev), (size_t)slot * sizeof(ModelDev), cudaMemcpyHostToDevice, st);
+}
+#define MD (c_models[slot])
 #define STEP_IDX (base ? (*base + off) : off)
-__global__ void __launch_bounds__(256) k_gather_in(ModelDev md, const int* base, int off, int train) { phase_gather_in(md, STEP_IDX, train != 0, blockIdx.x, gridDim.x); }
-__global__ void __launch_bounds__(GEMM_THREADS) k_f1(ModelDev md, const int* base, int off, int li, float* Hsrc) {
+__global__ void __launch_bounds__(256) k_gather_in(int slot, const int* base, int off, int train) { phase_gather_in(MD, STEP_IDX, train != 0, blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(GEMM_THREADS) k_f1(int slot, const int* base, int off, int li, float* Hsrc) {
   __shared__ float sA[GK * (GB + 1)], sB[GK * (GB + 1)];
-  phase_f1(md, li, STEP_IDX, Hsrc, blockIdx.x, sA, sB);
+  phase_f1(MD, li, STEP_IDX, Hsrc, blockIdx.x, sA, sB);
 }
-__global__ void __launch_bounds__(GEMM_THREADS) k_f2(ModelDev md, const int* base, int off, int li, float* Hsrc, int train) {
+__global__ void __launch_bounds__(GEMM_THREADS) k_f2(int slot, const int* base, int off, int li, float* Hsrc, int train) {
   __shared__ float sA[GK * (GB + 1)], sB[GK * (GB + 1)];
-  phase_f2(md, li, STEP_IDX, Hsrc, train != 0, blockIdx.x, sA, sB);
+  phase_f2(MD, li, STEP_IDX, Hsrc, train != 0, blockIdx.x, sA, sB);
 }
-__global__ void __launch_bounds__(SC_THREADS) k_score(ModelDev md, const int* base, int off) {
+__global__ void __launch_bounds__(SC_THREADS) k_score(int slot, const int* base, int off) {
   extern __shared__ __align__(16) float smem[];
-  phase_score(md, STEP_IDX, blockIdx.x, smem);
+  phase_score(MD, STEP_IDX, blockIdx.x, smem);
 }
-__global__ void __launch_bounds__(256) k_stats(ModelDev md, const int* base, int off) {
+__global__ void __launch_bounds__(256) k_stats(int slot, const int* base, int off) {
   extern __shared__ __align__(16) float smem[];
-  phase_stats(md, STEP_IDX, smem);
+  phase_stats(MD, STEP_IDX, smem);
 }
-__global__ void __launch_bounds__(SC_THREADS) k_lossgrad(ModelDev md, const int* base, int off) {
+__global__ void __launch_bounds__(SC_THREADS) k_lossgrad(int slot, const int* base, int off) {
   extern __shared__ __align__(16) float smem[];
-  phase_lossgrad(md, STEP_IDX, blockIdx.x, smem);
+  phase_lossgrad(MD, STEP_IDX, blockIdx.x, smem);
 }
-__global__ void __launch_bounds__(256) k_b1(ModelDev md, const int* base, int off, int li) { phase_b1(md, li, STEP_IDX, blockIdx.x, gridDim.x); }
-__global__ void __launch_bounds__(GEMM_THREADS) k_b2(ModelDev md, const int* base, int off, int li) {
+__global__ void __launch_bounds__(256) k_b1(int slot, const int* base, int off, int li) { phase_b1(MD, li, STEP_IDX, blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(GEMM_THREADS) k_b2(int slot, const int* base, int off, int li) {
   __shared__ float sA[GK * (GB + 1)], sB[GK * (GB + 1)];
-  phase_b2(md, li, STEP_IDX, blockIdx.x, sA, sB);
+  phase_b2(MD, li, STEP_IDX, blockIdx.x, sA, sB);
 }
-__global__ void __launch_bounds__(GEMM_THREADS) k_b3(ModelDev md, const int* base, int off, int li) {
+__global__ void __launch_bounds__(GEMM_THREADS) k_b3(int slot, const int* base, int off, int li) {
   __shared__ float sA[GK * (GB + 1)], sB[GK * (GB + 1)];
-  phase_b3(md, li, STEP_IDX, blockIdx.x, sA, sB);
+  phase_b3(MD, li, STEP_IDX, blockIdx.x, sA, sB);
 }
-__global__ void __launch_bounds__(GEMM_THREADS) k_dense(ModelDev md, const int* base, int off, int li) {
+__global__ void __launch_bounds__(GEMM_THREADS) k_dense(int slot, const int* base, int off, int li) {
   __shared__ float sA[GK * (GB + 1)], sB[GK * (GB + 1)];
-  phase_dense(md, li, STEP_IDX, blockIdx.x, sA, sB);
+  phase_dense(MD, li, STEP_IDX, blockIdx.x, sA, sB);
 }
-__global__ void __launch_bounds__(128) k_sparse_in(ModelDev md, const int* base, int off) { phase_sparse_in(md, STEP_IDX, blockIdx.x); }
+__global__ void __launch_bounds__(128) k_sparse_in(int slot, const int* base, int off) { phase_sparse_in(MD, STEP_IDX, blockIdx.x); }
 __global__ void k_advance(int* base, int n) { if (threadIdx.x == 0 && blockIdx.x == 0) *base += n; }
+
+#include "g4r_persistent.cuh"
 
 static int tiles2(int cols, int rows) { return ((cols + GB - 1) / GB) * ((rows + GB - 1) / GB); }
 
@@ -254,24 +274,24 @@ static int enqueue_train_step(g4r_handle* h, const int* base, int off) {
   const ModelDev& md = h->md;
   cudaStream_t st = h->stream;
   const int B = md.B;
-  if (md.mode != 0) LAUNCH(PH_GATHER, k_gather_in<<<std::max(1, (B + 7) / 8), 256, 0, st>>>(md, base, off, 1));
+  if (md.mode != 0) LAUNCH(PH_GATHER, k_gather_in<<<std::max(1, (B + 7) / 8), 256, 0, st>>>(h->slot, base, off, 1));
   for (int li = 0; li < md.n_layers; li++) {
     const LayerDev& ly = md.layer[li];
-    LAUNCH(PH_F1, k_f1<<<tiles2(2 * ly.L, B), GEMM_THREADS, 0, st>>>(md, base, off, li, ly.H));
-    LAUNCH(PH_F2, k_f2<<<tiles2(ly.L, B), GEMM_THREADS, 0, st>>>(md, base, off, li, ly.H, 1));
+    LAUNCH(PH_F1, k_f1<<<tiles2(2 * ly.L, B), GEMM_THREADS, 0, st>>>(h->slot, base, off, li, ly.H));
+    LAUNCH(PH_F2, k_f2<<<tiles2(ly.L, B), GEMM_THREADS, 0, st>>>(h->slot, base, off, li, ly.H, 1));
   }
-  LAUNCH(PH_SCORE, k_score<<<md.NCH, SC_THREADS, score_smem_bytes(h->Bmax), st>>>(md, base, off));
-  LAUNCH(PH_STATS, k_stats<<<1, 256, (size_t)(h->Bmax + 32) * sizeof(float), st>>>(md, base, off));
-  LAUNCH(PH_LOSSGRAD, k_lossgrad<<<md.NCH, SC_THREADS, lossgrad_smem_bytes(md.Bld), st>>>(md, base, off));
+  LAUNCH(PH_SCORE, k_score<<<md.NCH, SC_THREADS, score_smem_bytes(h->Bmax), st>>>(h->slot, base, off));
+  LAUNCH(PH_STATS, k_stats<<<1, 256, (size_t)(h->Bmax + 32) * sizeof(float), st>>>(h->slot, base, off));
+  LAUNCH(PH_LOSSGRAD, k_lossgrad<<<md.NCH, SC_THREADS, lossgrad_smem_bytes(md.Bld), st>>>(h->slot, base, off));
   for (int li = md.n_layers - 1; li >= 0; li--) {
     const LayerDev& ly = md.layer[li];
-    LAUNCH(PH_B1, k_b1<<<std::max(1, std::min(h->n_sm, (B * ly.L + 255) / 256)), 256, 0, st>>>(md, base, off, li));
-    LAUNCH(PH_B2, k_b2<<<tiles2(ly.L, B), GEMM_THREADS, 0, st>>>(md, base, off, li));
-    if (ly.in_dim > 0) LAUNCH(PH_B3, k_b3<<<tiles2(ly.in_dim, B), GEMM_THREADS, 0, st>>>(md, base, off, li));
+    LAUNCH(PH_B1, k_b1<<<std::max(1, std::min(h->n_sm, (B * ly.L + 255) / 256)), 256, 0, st>>>(h->slot, base, off, li));
+    LAUNCH(PH_B2, k_b2<<<tiles2(ly.L, B), GEMM_THREADS, 0, st>>>(h->slot, base, off, li));
+    if (ly.in_dim > 0) LAUNCH(PH_B3, k_b3<<<tiles2(ly.in_dim, B), GEMM_THREADS, 0, st>>>(h->slot, base, off, li));
     const DenseJobs dj = dense_jobs(ly.L, ly.in_dim);
-    LAUNCH(PH_DENSE, k_dense<<<dj.nWh + dj.nWrz + dj.nWx + dj.nBh, GEMM_THREADS, 0, st>>>(md, base, off, li));
+    LAUNCH(PH_DENSE, k_dense<<<dj.nWh + dj.nWrz + dj.nWx + dj.nBh, GEMM_THREADS, 0, st>>>(h->slot, base, off, li));
   }
-  LAUNCH(PH_SPARSE_IN, k_sparse_in<<<B, 128, 0, st>>>(md, base, off));
+  LAUNCH(PH_SPARSE_IN, k_sparse_in<<<B, 128, 0, st>>>(h->slot, base, off));
   return G4R_OK;
 }
 
@@ -303,6 +323,9 @@ extern "C" int g4r_destroy(g4r_handle* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   eval_release(h);
+  if (h->graphU) cudaGraphExecDestroy(h->graphU);
+  if (h->graph1) cudaGraphExecDestroy(h->graph1);
+  slot_free(h->slot);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->hX) cudaFreeHost(h->hX);
@@ -354,6 +377,9 @@ extern "C" int g4r_create(const g4r_config* cfg, void* device_workspace, size_t 
   char* base = (char*)align_up((size_t)h->ws, 256);
   Carver cv{base, 0, false};
   layout(*cfg, cv, h, h->n_sm);
+  h->slot = slot_alloc();
+  if (h->slot < 0) return bail(G4R_ERR_STATE, "too many live g4r handles in this process");
+  if (slot_upload(h->slot, h->md, h->stream) != cudaSuccess) return bail(G4R_ERR_CUDA, "constant upload failed");
   const int B = cfg->batch_size, CAP = h->CAP;
   bool ok = true;
   ok &= cudaMallocHost(&h->hX, (size_t)CAP * B * sizeof(int)) == cudaSuccess;
@@ -369,6 +395,15 @@ extern "C" int g4r_create(const g4r_config* cfg, void* device_workspace, size_t 
   cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)score_smem_bytes(h->Bmax));
   cudaFuncSetAttribute(k_lossgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lossgrad_smem_bytes(h->md.Bld));
   cudaFuncSetAttribute(k_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)h->npow2 * 8 + 1024));
+  h->pk_smem = std::max(std::max(score_smem_bytes(h->Bmax), lossgrad_smem_bytes(h->md.Bld)), (size_t)2 * GK * (GB + 1) * sizeof(float));
+  cudaFuncSetAttribute(k_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->pk_smem);
+  {
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent, PK_THREADS, h->pk_smem);
+    int coop = 0; cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device);
+    h->pk_blocks = (per_sm >= 1 && coop) ? h->n_sm : 0;
+  }
+  if (cfg->step_mode == 1 && h->pk_blocks == 0) return bail(G4R_ERR_INVALID, "persistent mode unavailable (cooperative launch / shared memory)");
   if (cudaStreamSynchronize(h->stream) != cudaSuccess) return bail(G4R_ERR_CUDA, "init sync failed");
   *out = h;
   return G4R_OK;
@@ -725,8 +760,41 @@ static int upload_window(g4r_handle* h, int64_t n) {
   return G4R_OK;
 }
 
+static int build_graph(g4r_handle* h, int unroll, cudaGraphExec_t* out) {
+  cudaGraph_t g = nullptr;
+  CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  const int64_t l0 = h->launches;
+  for (int i = 0; i < unroll; i++) enqueue_train_step(h, h->dStepBase, i);
+  k_advance<<<1, 32, 0, h->stream>>>(h->dStepBase, unroll);
+  h->launches = l0;
+  CK(cudaStreamEndCapture(h->stream, &g));
+  CK(cudaGraphInstantiate(out, g, 0));
+  cudaGraphDestroy(g);
+  return G4R_OK;
+}
+static int64_t launches_per_step(const g4r_handle* h) {
+  const ModelDev& md = h->md;
+  int64_t n = (md.mode != 0 ? 1 : 0) + 4;        // gather + score/stats/lossgrad + sparse_in
+  for (int li = 0; li < md.n_layers; li++) n += 2 + 2 + (md.layer[li].in_dim > 0 ? 1 : 0) + 1;
+  return n;
+}
+
 static int run_window(g4r_handle* h, int64_t n) {
-  for (int64_t i = 0; i < n; i++) enqueue_train_step(h, nullptr, (int)i);
+  if (h->cfg.step_mode == 1 && !h->prof) {
+    int slot = h->slot, nst = (int)n; GridBar* gb = h->dGridBar; unsigned long long* ts = h->stamp_on ? h->dStamp : nullptr;
+    void* args[] = {&slot, &nst, &gb, &ts};
+    CK(cudaLaunchCooperativeKernel((void*)k_persistent, dim3(h->pk_blocks), dim3(PK_THREADS), args, h->pk_smem, h->stream));
+    h->launches += 1;
+  } else if (h->prof || !h->use_graph) {
+    for (int64_t i = 0; i < n; i++) enqueue_train_step(h, nullptr, (int)i);
+  } else {
+    if (!h->graphU) { int rc = build_graph(h, h->graph_unroll, &h->graphU); if (rc) return rc; rc = build_graph(h, 1, &h->graph1); if (rc) return rc; }
+    CK(cudaMemsetAsync(h->dStepBase, 0, sizeof(int), h->stream));
+    int64_t i = 0;
+    for (; i + h->graph_unroll <= n; i += h->graph_unroll) CK(cudaGraphLaunch(h->graphU, h->stream));
+    for (; i < n; i++) CK(cudaGraphLaunch(h->graph1, h->stream));
+    h->launches += n * launches_per_step(h) + (n / h->graph_unroll) + (n % h->graph_unroll);
+  }
   CK(cudaGetLastError());
   if (h->gen_len > 0) h->sample_ptr += n;
   h->global_step += (uint32_t)n;
@@ -779,6 +847,18 @@ extern "C" int g4r_profile_uploaded(g4r_handle* h, float* phase_ms, int32_t* pha
     cudaEventDestroy(h->prof_ev[2 * k]); cudaEventDestroy(h->prof_ev[2 * k + 1]);
   }
   h->prof_ev.clear(); h->prof_phase.clear();
+  return G4R_OK;
+}
+// persistent mode: globaltimer stamps at phase boundaries of every step of the last window (6 per step, ns)
+extern "C" int g4r_persistent_stamps(g4r_handle* h, int32_t enable, unsigned long long* out, int64_t n_steps) {
+  if (!h) return G4R_ERR_INVALID;
+  h->stamp_on = enable != 0;
+  if (out && n_steps > 0) {
+    if (n_steps > h->CAP) FAIL(G4R_ERR_INVALID, "n_steps exceeds window capacity");
+    cudaSetDevice(h->cfg.device);
+    CK(cudaMemcpyAsync(out, h->dStamp, (size_t)n_steps * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
   return G4R_OK;
 }
 extern "C" const char* g4r_phase_name(int32_t i) { return (i >= 0 && i < PH_COUNT) ? kPhaseNames[i] : ""; }

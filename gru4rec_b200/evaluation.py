@@ -28,9 +28,6 @@ def evaluate_gpu(gru, test_data, items=None, session_key='SessionId', item_key='
     offset_sessions = np.zeros(test_data[session_key].nunique() + 1, dtype=np.int32)
     offset_sessions[1:] = test_data.groupby(session_key).size().cumsum()
     eng = gru._ensure_engine(batch_size)
-    if eng.cfg.eval_batch_size != batch_size:
-        # the scoring lanes are a property of the engine; rebuild with exactly this many
-        eng = gru._build_engine(sample_store=0, eval_lanes=batch_size)
     sched = _lib.Schedule(test_data_items, offset_sessions, None, batch_size, 0, mode=1)
     rec, mrr, n = eng.eval_schedule(sched, cuts, _MODES[mode])
     recall = [float(r) / n for r in rec]

@@ -138,6 +138,10 @@ int g4r_run_uploaded(g4r_handle* h, float* cost_out /* may be NULL */, float* de
  * roofline: achieved bytes/s of the dominant kernel = its algorithmic bytes / its mean duration. */
 int g4r_profile_uploaded(g4r_handle* h, float* phase_ms, int32_t* phase_launches, int32_t n_phases);
 const char* g4r_phase_name(int32_t i);
+/* Persistent mode (step_mode 1): enable %globaltimer stamps at the phase boundaries of every step and/or read
+ * the stamps of the last window (16 uint64 slots per step; slots 0..5 used: start, after GRU forward, after scores,
+ * after statistics, after loss-gradient/update, end). */
+int g4r_persistent_stamps(g4r_handle* h, int32_t enable, unsigned long long* out, int64_t n_steps);
 int g4r_phase_count(void);
 /* Counters for bench.py: kernels launched by this handle so far. */
 int64_t g4r_kernel_launches(const g4r_handle* h);

@@ -4,38 +4,7 @@ import gru4rec_oracle as orc
 from gru4rec_b200 import _lib
 
 
-def make_cfg(n_items, mk, sample_store=0, eval_lanes=0, max_resident_steps=0, step_mode=0):
-    cfg = _lib.G4RConfig()
-    layers = mk.get('layers', [100])
-    cfg.n_items = n_items
-    cfg.n_layers = len(layers)
-    for i, l in enumerate(layers):
-        cfg.layers[i] = l
-    cfg.batch_size = mk.get('batch_size', 32)
-    cfg.constrained_embedding = 1 if mk.get('constrained_embedding') else 0
-    cfg.embedding = 0 if mk.get('constrained_embedding') else int(mk.get('embedding', 0) or 0)
-    cfg.loss = _lib.LOSS[mk.get('loss', 'bpr-max')]
-    cfg.final_act, cfg.final_act_p1, cfg.final_act_p2 = _lib.parse_act(mk.get('final_act', 'linear'))
-    cfg.hidden_act, cfg.hidden_act_p1, cfg.hidden_act_p2 = _lib.parse_act(mk.get('hidden_act', 'tanh'))
-    cfg.dropout_p_hidden = mk.get('dropout_p_hidden', 0.0)
-    cfg.dropout_p_embed = mk.get('dropout_p_embed', 0.0)
-    cfg.learning_rate = mk.get('learning_rate', 0.1)
-    cfg.momentum = mk.get('momentum', 0.0)
-    cfg.lmbd = mk.get('lmbd', 0.0)
-    cfg.n_sample = mk.get('n_sample', 2048)
-    cfg.sample_alpha = mk.get('sample_alpha', 0.75)
-    cfg.smoothing = mk.get('smoothing', 0.0)
-    cfg.bpreg = mk.get('bpreg', 1.0)
-    cfg.logq = mk.get('logq', 0.0)
-    cfg.adapt = _lib.ADAPT[mk.get('adapt', 'adagrad')]
-    cfg.sample_store = sample_store
-    cfg.dropout_seed = mk.get('dropout_seed', 0)
-    cfg.mrg_seed = 12345
-    cfg.max_resident_steps = max_resident_steps
-    cfg.world_size, cfg.rank = 1, 0
-    cfg.eval_batch_size = eval_lanes
-    cfg.step_mode = step_mode
-    return cfg
+make_cfg = _lib.make_config
 
 
 def param_names(m):

@@ -89,13 +89,14 @@ CASES = {
 }
 
 
+@pytest.mark.parametrize('step_mode', [0, 1])
 @pytest.mark.parametrize('name', sorted(CASES))
-def test_train_steps_match_oracle(name):
+def test_train_steps_match_oracle(name, step_mode):
     mk = CASES[name]
     n_items = 120
     B = mk['batch_size']
     rows = 12
-    eng, m, store, rs = make_pair(n_items, mk, n_store_rows=rows if mk['n_sample'] else 0, seed=11)
+    eng, m, store, rs = make_pair(n_items, mk, n_store_rows=rows if mk['n_sample'] else 0, seed=11, step_mode=step_mode)
     costs_d, costs_o = [], []
     for t in range(rows - 1 if mk['n_sample'] else 10):
         X = rs.randint(0, n_items, B); Y = rs.randint(0, n_items, B)
@@ -115,13 +116,14 @@ def test_train_steps_match_oracle(name):
         np.testing.assert_allclose(eng.get('H%d' % i), m.H[i], rtol=1e-3, atol=1e-5)
 
 
-def test_shrinking_batch_and_slots():
+@pytest.mark.parametrize('step_mode', [0, 1])
+def test_shrinking_batch_and_slots(step_mode):
     """epoch tail: M < B with lane compaction (gru4rec.py:644-651) through a real schedule."""
     from gru4rec_b200.synth import make_sessions
     mk = dict(layers=[16], batch_size=8, n_sample=16, loss='bpr-max', final_act='elu-0.5', learning_rate=0.1, momentum=0.1)
     df = make_sessions(n_items=80, n_events=400, seed=5)
     d = orc.prepare_fit_data(df)
-    eng, m, store, rs = make_pair(d['n_items'], mk, n_store_rows=400, seed=4, randomize_state=False)
+    eng, m, store, rs = make_pair(d['n_items'], mk, n_store_rows=400, seed=4, randomize_state=False, step_mode=step_mode)
     sched = _lib.Schedule(d['data_items'], d['offset_sessions'], d['base_order'], 8, 16, mode=0)
     steps = orc.build_train_schedule(d['data_items'], d['offset_sessions'], d['base_order'], 8, 16)
     assert sched.n_steps == len(steps) and steps[-1]['M'] < 8

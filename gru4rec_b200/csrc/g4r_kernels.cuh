@@ -133,22 +133,47 @@ __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<floa
 template <int BM, int BN, int BK, int TM, int TN, bool A_KFAST, bool B_NFAST, class FA, class FB>
 __device__ __forceinline__ void gemm_tile_acc(float (&acc)[TM][TN], int K, FA fa, FB fb, float* sA, float* sB) {
   constexpr int NT = (BM / TM) * (BN / TN);
+  constexpr int NA = BM * BK / NT, NB = BK * BN / NT;
+  static_assert(BM * BK % NT == 0 && BK * BN % NT == 0, "tile must divide evenly over the threads");
   const int tid = threadIdx.x;
   const int tx = tid % (BN / TN), ty = tid / (BN / TN);
   for (int k0 = 0; k0 < K; k0 += BK) {
-    for (int i = tid; i < BM * BK; i += NT) {
+    // all global loads of the slab are issued into registers BEFORE the first shared-memory store: a store after
+    // each load would serialise one memory round trip per element (~0.5 us each on B200)
+    float ra[NA], rb[NB];
+#pragma unroll
+    for (int j = 0; j < NA; j++) {
+      const int i = tid + j * NT;
       int m, k;
       if (A_KFAST) { k = i % BK; m = i / BK; } else { m = i % BM; k = i / BM; }
-      sA[k * (BM + 1) + m] = (k0 + k < K) ? fa(m, k0 + k) : 0.f;
+      ra[j] = (k0 + k < K) ? fa(m, k0 + k) : 0.f;
     }
-    for (int i = tid; i < BK * BN; i += NT) {
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+      const int i = tid + j * NT;
       int n, k;
       if (B_NFAST) { n = i % BN; k = i / BN; } else { k = i % BK; n = i / BK; }
-      sB[k * (BN + 1) + n] = (k0 + k < K) ? fb(k0 + k, n) : 0.f;
+      rb[j] = (k0 + k < K) ? fb(k0 + k, n) : 0.f;
+    }
+    if (k0 > 0) __syncthreads();
+#pragma unroll
+    for (int j = 0; j < NA; j++) {
+      const int i = tid + j * NT;
+      int m, k;
+      if (A_KFAST) { k = i % BK; m = i / BK; } else { m = i % BM; k = i / BM; }
+      sA[k * (BM + 1) + m] = ra[j];
+    }
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+      const int i = tid + j * NT;
+      int n, k;
+      if (B_NFAST) { n = i % BN; k = i / BN; } else { k = i % BK; n = i / BK; }
+      sB[k * (BN + 1) + n] = rb[j];
     }
     __syncthreads();
-#pragma unroll 8
-    for (int k = 0; k < BK; k++) {
+    const int kmax = min(BK, K - k0);
+#pragma unroll 4
+    for (int k = 0; k < kmax; k++) {
       float a[TM], b[TN];
 #pragma unroll
       for (int i = 0; i < TM; i++) a[i] = sA[k * (BM + 1) + ty * TM + i];
@@ -159,11 +184,30 @@ __device__ __forceinline__ void gemm_tile_acc(float (&acc)[TM][TN], int K, FA fa
 #pragma unroll
         for (int j = 0; j < TN; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
-    __syncthreads();
+  }
+  __syncthreads();
+}
+// stage `nrows` rows of `kw` float4 into shared memory, four 16-byte loads in flight per thread before any store
+template <class FRow>
+__device__ __forceinline__ void stage_rows4(float* sdst, int sld, int nrows, int kw, FRow rowptr) {
+  const int total = nrows * kw;
+  for (int i0 = 0; i0 < total; i0 += 4 * (int)blockDim.x) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * (int)blockDim.x + (int)threadIdx.x;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < total) { const float* rp = rowptr(i / kw); if (rp) v[u] = ld4(rp + (i % kw) * 4); }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * (int)blockDim.x + (int)threadIdx.x;
+      if (i < total) st4(sdst + (i / kw) * sld + (i % kw) * 4, v[u]);
+    }
   }
 }
 constexpr int GB = 32;   // CTA tile edge of the small-GEMM phases
-constexpr int GK = 32;
+constexpr int GK = 128;  // K slab: the GRU widths of the shipped configurations (100, 224 -> 2 slabs, 512 -> 4) load in few batches
 constexpr int GT = 2;    // micro tile
 constexpr int GEMM_THREADS = (GB / GT) * (GB / GT);   // 256
 
@@ -230,23 +274,48 @@ __device__ void phase_f1(const ModelDev& md, int li, int s, float* Hsrc, int til
   const int tn = tile % ntn, tm = tile / ntn;
   const int m0 = tm * GB, n0 = tn * GB;
   if (m0 >= M) return;
-  const int* slot = md.wSlot + (size_t)s * md.B;
-  const uint8_t* fl = md.wF + (size_t)s * md.B;
+  __shared__ int sSlot[GB], sXi[GB];
+  const float* __restrict__ Hs = Hsrc;
+  const float* __restrict__ Wrz = ly.Wrz;
+  const float* __restrict__ Wx = ly.Wx;
+  const float* __restrict__ Bh = ly.Bh;
+  const bool gathered = ly.in_dim == 0;
+  // row metadata once (index -> data chains would otherwise repeat inside every load loop)
+  if (threadIdx.x < GB) {
+    const int b = m0 + threadIdx.x;
+    int sl = -1, x = 0;
+    if (b < M) {
+      sl = (md.wF[(size_t)s * md.B + b] & 2) ? -1 : md.wSlot[(size_t)s * md.B + b];
+      if (gathered) x = md.wX[(size_t)s * md.B + b];
+    }
+    sSlot[threadIdx.x] = sl; sXi[threadIdx.x] = x;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x % (GB / GT), ty = threadIdx.x / (GB / GT);
+  // epilogue operands are independent of the GEMM: issue their loads first
+  float pre[GT][GT];
+#pragma unroll
+  for (int i = 0; i < GT; i++)
+#pragma unroll
+    for (int j = 0; j < GT; j++) {
+      const int b = m0 + ty * GT + i, c = n0 + tx * GT + j;
+      float v = 0.f;
+      if (b < M && c < 2 * L) {
+        v = Bh[L + c];
+        if (gathered) v += Wx[(size_t)sXi[ty * GT + i] * ly.ld3 + L + c];
+      }
+      pre[i][j] = v;
+    }
   float acc[GT][GT] = {};
-  auto fa_h = [&](int m, int k) -> float {
-    int b = m0 + m;
-    if (b >= M) return 0.f;
-    if (fl[b] & 2) return 0.f;
-    return Hsrc[(size_t)slot[b] * ly.ldL + k];
-  };
-  auto fb_rz = [&](int k, int n) -> float { int c = n0 + n; return c < 2 * L ? ly.Wrz[(size_t)k * ly.ld2 + c] : 0.f; };
+  auto fa_h = [&](int m, int k) -> float { const int sl = sSlot[m]; return sl >= 0 ? Hs[(size_t)sl * ly.ldL + k] : 0.f; };
+  auto fb_rz = [&](int k, int n) -> float { const int c = n0 + n; return c < 2 * L ? Wrz[(size_t)k * ly.ld2 + c] : 0.f; };
   gemm_tile_acc<GB, GB, GK, GT, GT, true, true>(acc, L, fa_h, fb_rz, sA, sB);
-  if (ly.in_dim > 0) {
-    auto fa_in = [&](int m, int k) -> float { int b = m0 + m; return b < M ? ly.in[(size_t)b * ly.ld_in + k] : 0.f; };
-    auto fb_wx = [&](int k, int n) -> float { int c = n0 + n; return c < 2 * L ? ly.Wx[(size_t)k * ly.ld3 + L + c] : 0.f; };
+  if (!gathered) {
+    const float* __restrict__ In = ly.in;
+    auto fa_in = [&](int m, int k) -> float { const int b = m0 + m; return b < M ? In[(size_t)b * ly.ld_in + k] : 0.f; };
+    auto fb_wx = [&](int k, int n) -> float { const int c = n0 + n; return c < 2 * L ? Wx[(size_t)k * ly.ld3 + L + c] : 0.f; };
     gemm_tile_acc<GB, GB, GK, GT, GT, true, true>(acc, ly.in_dim, fa_in, fb_wx, sA, sB);
   }
-  const int tx = threadIdx.x % (GB / GT), ty = threadIdx.x / (GB / GT);
 #pragma unroll
   for (int i = 0; i < GT; i++) {
     const int b = m0 + ty * GT + i;
@@ -255,17 +324,27 @@ __device__ void phase_f1(const ModelDev& md, int li, int s, float* Hsrc, int til
     for (int j = 0; j < GT; j++) {
       const int c = n0 + tx * GT + j;
       if (c >= 2 * L) continue;
-      float v = acc[i][j] + ly.Bh[L + c];
-      if (ly.in_dim == 0) v += ly.Wx[(size_t)md.wX[(size_t)s * md.B + b] * ly.ld3 + L + c];
-      const float g = sigmoidf_(v);
+      const float g = sigmoidf_(acc[i][j] + pre[i][j]);
       if (c < L) ly.r[(size_t)b * ly.ldL + c] = g; else ly.z[(size_t)b * ly.ldL + (c - L)] = g;
     }
   }
-  // the tiles of column block 0 also materialise the compact copy of the old hidden state
+  // the tiles of column block 0 also materialise the compact copy of the old hidden state (16-byte vectors)
   if (tn == 0) {
-    for (int i = threadIdx.x; i < GB * ly.ldL; i += blockDim.x) {
-      const int b = m0 + i / ly.ldL, k = i % ly.ldL;
-      if (b < M) ly.Hold[(size_t)b * ly.ldL + k] = (fl[b] & 2) ? 0.f : Hsrc[(size_t)slot[b] * ly.ldL + k];
+    float* __restrict__ Ho = ly.Hold;
+    const int q4 = ly.ldL / 4;
+    for (int i0 = 0; i0 < GB * q4; i0 += 4 * (int)blockDim.x) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int i = i0 + u * (int)blockDim.x + (int)threadIdx.x;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < GB * q4) { const int sl = sSlot[i / q4]; if (sl >= 0) v[u] = ld4(Hs + (size_t)sl * ly.ldL + (i % q4) * 4); }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int i = i0 + u * (int)blockDim.x + (int)threadIdx.x;
+        if (i < GB * q4 && m0 + i / q4 < M) st4(Ho + (size_t)(m0 + i / q4) * ly.ldL + (i % q4) * 4, v[u]);
+      }
     }
   }
 }
@@ -284,21 +363,50 @@ __device__ void phase_f2(const ModelDev& md, int li, int s, float* Hsrc, bool tr
   const int tn = tile % ntn, tm = tile / ntn;
   const int m0 = tm * GB, n0 = tn * GB;
   if (m0 >= M) return;
-  const int* slot = md.wSlot + (size_t)s * md.B;
-  const uint8_t* fl = md.wF + (size_t)s * md.B;
+  __shared__ int sSlot2[GB], sXi2[GB], sFl2[GB];
+  const float* __restrict__ Hold = ly.Hold;
+  const float* __restrict__ Rr = ly.r;
+  const float* __restrict__ Zz = ly.z;
+  const float* __restrict__ Wh = ly.Wh;
+  const float* __restrict__ Wx = ly.Wx;
+  const float* __restrict__ Bh = ly.Bh;
+  const bool gathered = ly.in_dim == 0;
+  if (threadIdx.x < GB) {
+    const int b = m0 + threadIdx.x;
+    int sl = 0, x = 0, f = 0;
+    if (b < M) { sl = md.wSlot[(size_t)s * md.B + b]; f = md.wF[(size_t)s * md.B + b]; if (gathered) x = md.wX[(size_t)s * md.B + b]; }
+    sSlot2[threadIdx.x] = sl; sXi2[threadIdx.x] = x; sFl2[threadIdx.x] = f;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x % (GB / GT), ty = threadIdx.x / (GB / GT);
+  float pre[GT][GT], pz[GT][GT], ph[GT][GT];
+#pragma unroll
+  for (int i = 0; i < GT; i++)
+#pragma unroll
+    for (int j = 0; j < GT; j++) {
+      const int b = m0 + ty * GT + i, c = n0 + tx * GT + j;
+      float v = 0.f, z = 0.f, ho = 0.f;
+      if (b < M && c < L) {
+        v = Bh[c];
+        if (gathered) v += Wx[(size_t)sXi2[ty * GT + i] * ly.ld3 + c];
+        z = Zz[(size_t)b * ly.ldL + c];
+        ho = Hold[(size_t)b * ly.ldL + c];
+      }
+      pre[i][j] = v; pz[i][j] = z; ph[i][j] = ho;
+    }
   float acc[GT][GT] = {};
   auto fa_hr = [&](int m, int k) -> float {
-    int b = m0 + m;
-    return b < M ? ly.Hold[(size_t)b * ly.ldL + k] * ly.r[(size_t)b * ly.ldL + k] : 0.f;
+    const int b = m0 + m;
+    return b < M ? Hold[(size_t)b * ly.ldL + k] * Rr[(size_t)b * ly.ldL + k] : 0.f;
   };
-  auto fb_wh = [&](int k, int n) -> float { int c = n0 + n; return c < L ? ly.Wh[(size_t)k * ly.ldL + c] : 0.f; };
+  auto fb_wh = [&](int k, int n) -> float { const int c = n0 + n; return c < L ? Wh[(size_t)k * ly.ldL + c] : 0.f; };
   gemm_tile_acc<GB, GB, GK, GT, GT, true, true>(acc, L, fa_hr, fb_wh, sA, sB);
-  if (ly.in_dim > 0) {
-    auto fa_in = [&](int m, int k) -> float { int b = m0 + m; return b < M ? ly.in[(size_t)b * ly.ld_in + k] : 0.f; };
-    auto fb_wx = [&](int k, int n) -> float { int c = n0 + n; return c < L ? ly.Wx[(size_t)k * ly.ld3 + c] : 0.f; };
+  if (!gathered) {
+    const float* __restrict__ In = ly.in;
+    auto fa_in = [&](int m, int k) -> float { const int b = m0 + m; return b < M ? In[(size_t)b * ly.ld_in + k] : 0.f; };
+    auto fb_wx = [&](int k, int n) -> float { const int c = n0 + n; return c < L ? Wx[(size_t)k * ly.ld3 + c] : 0.f; };
     gemm_tile_acc<GB, GB, GK, GT, GT, true, true>(acc, ly.in_dim, fa_in, fb_wx, sA, sB);
   }
-  const int tx = threadIdx.x % (GB / GT), ty = threadIdx.x / (GB / GT);
   const uint32_t gstep = md.wG[s];
   const float retain = 1.0f - md.p_drop_h;
 #pragma unroll
@@ -309,17 +417,15 @@ __device__ void phase_f2(const ModelDev& md, int li, int s, float* Hsrc, bool tr
     for (int j = 0; j < GT; j++) {
       const int c = n0 + tx * GT + j;
       if (c >= L) continue;
-      float v = acc[i][j] + ly.Bh[c];
-      if (ly.in_dim == 0) v += ly.Wx[(size_t)md.wX[(size_t)s * md.B + b] * ly.ld3 + c];
+      const float v = acc[i][j] + pre[i][j];
       const float ht = act_fwd(md.hact, v);
-      const float z = ly.z[(size_t)b * ly.ldL + c];
-      const float ho = ly.Hold[(size_t)b * ly.ldL + c];
-      float h = (1.0f - z) * ho + z * ht;
+      const float z = pz[i][j];
+      float h = (1.0f - z) * ph[i][j] + z * ht;
       if (train && md.p_drop_h > 0.f) h *= drop_scale(md.drop_seed, gstep, (uint32_t)li, (uint32_t)(b * L + c), retain);
       ly.ah[(size_t)b * ly.ldL + c] = v;
       ly.ht[(size_t)b * ly.ldL + c] = ht;
       ly.y[(size_t)b * ly.ldL + c] = h;
-      Hsrc[(size_t)slot[b] * ly.ldL + c] = (train && (fl[b] & 1)) ? 0.f : h;
+      Hsrc[(size_t)sSlot2[ty * GT + i] * ly.ldL + c] = (train && (sFl2[ty * GT + i] & 1)) ? 0.f : h;
     }
   }
 }
@@ -349,10 +455,38 @@ __device__ __forceinline__ void stat_merge(float& m, float& Z, float& A, float& 
   Z = Z * e1 + Z2 * e2; A = A * e1 + A2 * e2; Q = Q * e1 + Q2 * e2; D = D * e1 + D2 * e2; m = mn;
 }
 
+// accumulate one score column into a row's running statistics (online softmax-style merge)
+__device__ __forceinline__ void stat_add_elem(const ModelDev& md, float o, bool is_t, float t, float& m, float& Z, float& A, float& Q, float& D, float& T, float& has) {
+  if (md.loss == G4R_LOSS_XE || md.loss == G4R_LOSS_XE_LOGIT) {
+    stat_merge(m, Z, A, Q, D, o, 1.f, 0.f, 0.f, 0.f);
+    if (is_t) { T = o; has = 1.f; }
+    return;
+  }
+  const float y = act_fwd(md.fact, o);
+  if (is_t) has = 1.f;
+  if (md.loss == G4R_LOSS_BPR_MAX) {
+    if (!is_t) { const float sg = sigmoidf_(t - y); stat_merge(m, Z, A, Q, D, y, 1.f, sg, y * y, sg * (1.f - sg)); }
+  } else if (md.loss == G4R_LOSS_TOP1_MAX) {
+    if (!is_t) { const float a1 = sigmoidf_(y - t), b1 = sigmoidf_(y * y); stat_merge(m, Z, A, Q, D, y, 1.f, a1 + b1, 0.f, a1 * (1.f - a1)); }
+  } else if (md.loss == G4R_LOSS_BPR) {
+    const float sg = sigmoidf_(t - y);
+    A += -logf(sg);
+    if (!is_t) D += 1.f - sg;
+  } else {  // TOP1
+    const float a1 = sigmoidf_(y - t), b1 = sigmoidf_(y * y);
+    A += a1 + b1;
+    if (!is_t) D += a1 * (1.f - a1);
+  }
+}
+__device__ __forceinline__ void stat_combine(const ModelDev& md, float& m, float& Z, float& A, float& Q, float& D, float& T, float& has,
+                                             float m2, float Z2, float A2, float Q2, float D2, float T2, float has2) {
+  if (md.loss == G4R_LOSS_BPR || md.loss == G4R_LOSS_TOP1) { A += A2; D += D2; }
+  else stat_merge(m, Z, A, Q, D, m2, Z2, A2, Q2, D2);
+  if (has2 > 0.f) { T = T2; has = 1.f; }
+}
+
 __device__ void phase_score(const ModelDev& md, int s, int chunk, float* smem) {
   const int M = md.wM[s];
-  const int sti = md.wSti[s];
-  const int N = M + (sti >= 0 ? md.S : 0);
   const int* cbeg = md.pCbeg + (size_t)s * (md.NCH + 1);
   const int cb = cbeg[chunk], ce = cbeg[chunk + 1];
   if (cb >= ce) {   // empty chunk: neutral partial statistics
@@ -362,51 +496,77 @@ __device__ void phase_score(const ModelDev& md, int s, int chunk, float* smem) {
     }
     return;
   }
-  const int L = md.L, ldL = md.ldL;
-  const float* Y = md.layer[md.n_layers - 1].y;
-  const int* pItem = md.pItem + (size_t)s * md.NP;
-  const int* pPos = md.pPos + (size_t)s * md.NP;
+  const int ldL = md.ldL;
+  const float* __restrict__ Y = md.layer[md.n_layers - 1].y;
+  const float* __restrict__ Wy = md.Wy;
+  const float* __restrict__ By = md.By;
+  const int* __restrict__ pItem = md.pItem + (size_t)s * md.NP;
+  const int* __restrict__ pPos = md.pPos + (size_t)s * md.NP;
+  const int* __restrict__ tcol = md.pTcol + (size_t)s * md.B;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* sY = smem;                              // [SC_TB][SC_LDS]
   float* sS = sY + SC_TB * SC_LDS;               // [SC_CT][SC_LDS]
   float* sT = sS + SC_CT * SC_LDS;               // [Bmax] target activations (pairwise losses)
-  // --- target activations for pairwise losses: every chunk needs t_b = f(o_b,target) of every lane
+  float* sRun = sT + md.Bld;                     // [Bmax][8] running row statistics of this chunk
+  float* sPart = sRun + (size_t)md.Bld * 8;      // [8][SC_TB][8] per-warp statistics of the current tile
+  float* sBias = sPart + 8 * SC_TB * 8;          // [SC_CT] bias (- logq correction) of the sub tile's columns
+  int* sIt = reinterpret_cast<int*>(sBias + SC_CT);   // [SC_CT] items, [SC_CT] positions
   const bool pw = loss_pairwise(md.loss);
+  for (int b = tid; b < M; b += SC_THREADS) {
+    float* r = sRun + b * 8;
+    r[0] = -INFINITY; r[1] = 0.f; r[2] = 0.f; r[3] = 0.f; r[4] = 0.f; r[5] = 0.f; r[6] = 0.f; r[7] = 0.f;
+  }
+  // --- target activations t_b = f(o_b,target) for pairwise losses; four rows per warp in flight
   if (pw) {
-    for (int b = warp; b < M; b += SC_THREADS / 32) {
-      const int item = md.wY[(size_t)s * md.B + b];
-      const float* wr = md.Wy + (size_t)item * ldL;
-      const float* yr = Y + (size_t)b * ldL;
-      float a = 0.f;
+    for (int bq = warp * 4; bq < M; bq += (SC_THREADS / 32) * 4) {
+      int item[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) item[q] = (bq + q < M) ? md.wY[(size_t)s * md.B + bq + q] : -1;
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
       for (int c4 = lane; c4 < ldL / 4; c4 += 32) {
-        const float4 w = ld4(wr + c4 * 4), y = ld4(yr + c4 * 4);
-        a = fmaf(w.x, y.x, a); a = fmaf(w.y, y.y, a); a = fmaf(w.z, y.z, a); a = fmaf(w.w, y.w, a);
+        float4 w[4], y[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          w[q] = make_float4(0.f, 0.f, 0.f, 0.f); y[q] = w[q];
+          if (item[q] >= 0) { w[q] = ld4(Wy + (size_t)item[q] * ldL + c4 * 4); y[q] = ld4(Y + (size_t)(bq + q) * ldL + c4 * 4); }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) { a[q] = fmaf(w[q].x, y[q].x, a[q]); a[q] = fmaf(w[q].y, y[q].y, a[q]); a[q] = fmaf(w[q].z, y[q].z, a[q]); a[q] = fmaf(w[q].w, y[q].w, a[q]); }
       }
-      a = warp_sum(a);
-      if (lane == 0) {
-        float o = a + md.By[item];
-        if (md.logq > 0.f) o -= md.logP0t[item];
-        sT[b] = act_fwd(md.fact, o);
+      float bias[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        bias[q] = 0.f;
+        if (lane == 0 && item[q] >= 0) { bias[q] = By[item[q]]; if (md.logq > 0.f) bias[q] -= md.logP0t[item[q]]; }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const float v = warp_sum(a[q]);
+        if (lane == 0 && item[q] >= 0) sT[bq + q] = act_fwd(md.fact, v + bias[q]);
       }
     }
   }
-  __syncthreads();
-  // --- scores
+  // --- scores, sub tile by sub tile
   for (int j0 = cb; j0 < ce; j0 += SC_CT) {
     const int nj = min(SC_CT, ce - j0);
+    __syncthreads();
+    if (tid < nj) {
+      const int item = pItem[j0 + tid], pos = pPos[j0 + tid];
+      float bz = By[item];
+      if (md.logq > 0.f) bz -= (pos < M) ? md.logP0t[item] : md.logP0s[item];
+      sIt[tid] = item; sBias[tid] = bz;
+    }
+    __syncthreads();
     for (int b0 = 0; b0 < M; b0 += SC_TB) {
       float acc0 = 0.f, acc1 = 0.f;
       for (int k0 = 0; k0 < ldL; k0 += SC_KT) {
         const int kw = min(SC_KT, ldL - k0) / 4;       // float4 per row in this slab
-        for (int i = tid; i < SC_TB * kw; i += SC_THREADS) {
-          const int rr = i / kw, c4 = i % kw;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (b0 + rr < M) v = ld4(Y + (size_t)(b0 + rr) * ldL + k0 + c4 * 4);
-          st4(sY + rr * SC_LDS + c4 * 4, v);
-        }
-        for (int i = tid; i < nj * kw; i += SC_THREADS) {
-          const int rr = i / kw, c4 = i % kw;
-          st4(sS + rr * SC_LDS + c4 * 4, ld4(md.Wy + (size_t)pItem[j0 + rr] * ldL + k0 + c4 * 4));
+        if (k0 > 0) __syncthreads();
+        {
+          int myit[4];   // item ids of the rows this thread stages (read before any shared store)
+          stage_rows4(sY, SC_LDS, SC_TB, kw, [&](int rr) -> const float* { return (b0 + rr < M) ? Y + (size_t)(b0 + rr) * ldL + k0 : nullptr; });
+          (void)myit;
+          stage_rows4(sS, SC_LDS, nj, kw, [&](int rr) -> const float* { return Wy + (size_t)sIt[rr] * ldL + k0; });
         }
         __syncthreads();
         const float* yr = sY + lane * SC_LDS;
@@ -418,103 +578,83 @@ __device__ void phase_score(const ModelDev& md, int s, int chunk, float* smem) {
           if (h0) { const float4 w = ld4(s0 + c4 * 4); acc0 = fmaf(y.x, w.x, acc0); acc0 = fmaf(y.y, w.y, acc0); acc0 = fmaf(y.z, w.z, acc0); acc0 = fmaf(y.w, w.w, acc0); }
           if (h1) { const float4 w = ld4(s1 + c4 * 4); acc1 = fmaf(y.x, w.x, acc1); acc1 = fmaf(y.y, w.y, acc1); acc1 = fmaf(y.z, w.z, acc1); acc1 = fmaf(y.w, w.w, acc1); }
         }
-        __syncthreads();
       }
+      // this thread: lane b = b0 + lane, columns warp and warp + 8 of the sub tile
       const int b = b0 + lane;
+      float m = -INFINITY, Z = 0.f, A = 0.f, Q = 0.f, D = 0.f, T = 0.f, has = 0.f;
       if (b < M) {
+        const int tc = tcol[b];
+        const float t = pw ? sT[b] : 0.f;
 #pragma unroll
         for (int q = 0; q < 2; q++) {
           const int jj = warp + q * 8;
           if (jj < nj) {
-            const int j = j0 + jj, item = pItem[j];
-            float o = (q ? acc1 : acc0) + md.By[item];
-            if (md.logq > 0.f) o -= (pPos[j] < M) ? md.logP0t[item] : md.logP0s[item];
-            md.O[(size_t)j * md.Bld + b] = o;
+            const float o = (q ? acc1 : acc0) + sBias[jj];
+            md.O[(size_t)(j0 + jj) * md.Bld + b] = o;
+            stat_add_elem(md, o, tc == j0 + jj, t, m, Z, A, Q, D, T, has);
           }
         }
       }
+      float* pp = sPart + ((size_t)warp * SC_TB + lane) * 8;
+      pp[0] = m; pp[1] = Z; pp[2] = A; pp[3] = Q; pp[4] = D; pp[5] = T; pp[6] = has;
+      __syncthreads();
+      if (tid < SC_TB && b0 + tid < M) {
+        float* r = sRun + (size_t)(b0 + tid) * 8;
+        float rm = r[0], rZ = r[1], rA = r[2], rQ = r[3], rD = r[4], rT = r[5], rh = r[6];
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+          const float* q = sPart + ((size_t)w * SC_TB + tid) * 8;
+          stat_combine(md, rm, rZ, rA, rQ, rD, rT, rh, q[0], q[1], q[2], q[3], q[4], q[5], q[6]);
+        }
+        r[0] = rm; r[1] = rZ; r[2] = rA; r[3] = rQ; r[4] = rD; r[5] = rT; r[6] = rh;
+      }
+      __syncthreads();
     }
   }
-  __syncthreads();   // O of this chunk written by this CTA is visible to it
-  // --- partial row statistics over this chunk's columns: warp per lane b, lanes over columns
-  const int* tcol = md.pTcol + (size_t)s * md.B;
-  for (int b = warp; b < M; b += SC_THREADS / 32) {
-    float m = -INFINITY, Z = 0.f, A = 0.f, Q = 0.f, D = 0.f, T = 0.f;
-    const int tc = tcol[b];
-    const float t = pw ? sT[b] : 0.f;
-    // pass 1: max
-    if (md.loss == G4R_LOSS_XE || md.loss == G4R_LOSS_XE_LOGIT || loss_softmaxneg(md.loss)) {
-      for (int j = cb + lane; j < ce; j += 32) {
-        const float o = md.O[(size_t)j * md.Bld + b];
-        if (loss_softmaxneg(md.loss)) { if (j != tc) m = fmaxf(m, act_fwd(md.fact, o)); }
-        else m = fmaxf(m, o);
-      }
-      m = warp_max(m);
-      if (loss_softmaxneg(md.loss)) m = fmaxf(m, 0.f);   // the zeroed diagonal takes part in the max (gru4rec.py:200-202)
-    }
-    for (int j = cb + lane; j < ce; j += 32) {
-      const float o = md.O[(size_t)j * md.Bld + b];
-      if (md.loss == G4R_LOSS_XE || md.loss == G4R_LOSS_XE_LOGIT) {
-        Z += expf(o - m);
-        if (j == tc) T = o;
-      } else {
-        const float y = act_fwd(md.fact, o);
-        if (md.loss == G4R_LOSS_BPR_MAX) {
-          if (j != tc) { const float e = expf(y - m), sg = sigmoidf_(t - y); Z += e; A += sg * e; Q += y * y * e; D += sg * (1.f - sg) * e; }
-        } else if (md.loss == G4R_LOSS_TOP1_MAX) {
-          if (j != tc) { const float e = expf(y - m), a1 = sigmoidf_(y - t), b1 = sigmoidf_(y * y); Z += e; A += (a1 + b1) * e; D += a1 * (1.f - a1) * e; }
-        } else if (md.loss == G4R_LOSS_BPR) {
-          const float sg = sigmoidf_(t - y);
-          A += -logf(sg);
-          if (j != tc) D += 1.f - sg;
-        } else {  // TOP1
-          const float a1 = sigmoidf_(y - t), b1 = sigmoidf_(y * y);
-          A += a1 + b1;
-          if (j != tc) D += a1 * (1.f - a1);
-        }
-      }
-    }
-    Z = warp_sum(Z); A = warp_sum(A); Q = warp_sum(Q); D = warp_sum(D); T = warp_sum(T);
-    if (lane == 0) {
-      float* st = md.stat + ((size_t)chunk * md.B + b) * G4R_NSTAT;
-      st[0] = m; st[1] = Z; st[2] = A; st[3] = Q; st[4] = D; st[5] = T;
-      st[6] = (tc >= cb && tc < ce) ? 1.f : 0.f;
-      if (pw) st[7] = t;
-    }
+  for (int b = tid; b < M; b += SC_THREADS) {
+    float* st = md.stat + ((size_t)chunk * md.B + b) * G4R_NSTAT;
+    const float* r = sRun + (size_t)b * 8;
+    st4(st, make_float4(r[0], r[1], r[2], r[3]));
+    st4(st + 4, make_float4(r[4], r[5], r[6], pw ? sT[b] : 0.f));
   }
 }
-__host__ __device__ inline size_t score_smem_bytes(int Bmax) { return (size_t)(SC_TB * SC_LDS + SC_CT * SC_LDS + Bmax + 32) * sizeof(float); }
+__host__ __device__ inline size_t score_smem_bytes(int Bld) {
+  return (size_t)(SC_TB * SC_LDS + SC_CT * SC_LDS + Bld + Bld * 8 + 8 * SC_TB * 8 + SC_CT + 2 * SC_CT + 32) * sizeof(float);
+}
 
 // ------------------------------------------------------------------------------------------------
-// phase S2: combine chunk statistics -> final row statistics, per-row loss, cost (single CTA, deterministic)
+// phase S2: combine the chunk statistics of lane b (one CTA per lane; fixed combine order => deterministic)
 // RS[b] = {m, Z, A', Q', D', t_or_targetO, loss_b}
 // ------------------------------------------------------------------------------------------------
-__device__ void phase_stats(const ModelDev& md, int s, float* smem) {
+__device__ void phase_stats(const ModelDev& md, int s, int cta, int ncta, float* smem) {
   const int M = md.wM[s];
   const int sti = md.wSti[s];
   const int N = M + (sti >= 0 ? md.S : 0);
-  const int* cbeg = md.pCbeg + (size_t)s * (md.NCH + 1);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  float* sLoss = smem;   // [Bmax]
-  for (int b = warp; b < M; b += nwarp) {
-    float m = -INFINITY, Z = 0.f, A = 0.f, Q = 0.f, D = 0.f, T = 0.f, tt = 0.f;
-    for (int c = lane; c < md.NCH; c += 32) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  float* sW = smem;   // [nwarp][8]
+  for (int b = cta; b < M; b += ncta) {
+    float m = -INFINITY, Z = 0.f, A = 0.f, Q = 0.f, D = 0.f, T = 0.f, has = 0.f, tt = 0.f;
+    for (int c = tid; c < md.NCH; c += blockDim.x) {
       const float* st = md.stat + ((size_t)c * md.B + b) * G4R_NSTAT;
-      if (md.loss == G4R_LOSS_BPR || md.loss == G4R_LOSS_TOP1) { A += st[2]; D += st[4]; }
-      else stat_merge(m, Z, A, Q, D, st[0], st[1], st[2], st[3], st[4]);
-      if (st[6] > 0.f) T = st[5];
-      if (c == 0) tt = st[7];      // chunk 0 is never empty
+      const float4 u = ld4(st), v = ld4(st + 4);
+      stat_combine(md, m, Z, A, Q, D, T, has, u.x, u.y, u.z, u.w, v.x, v.y, v.z);
+      if (c == 0) tt = v.w;      // chunk 0 is never empty
     }
-    // butterfly merge across lanes
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = 1; o < 32; o <<= 1) {   // fixed butterfly order
       const float m2 = __shfl_xor_sync(0xffffffffu, m, o), Z2 = __shfl_xor_sync(0xffffffffu, Z, o), A2 = __shfl_xor_sync(0xffffffffu, A, o),
-                  Q2 = __shfl_xor_sync(0xffffffffu, Q, o), D2 = __shfl_xor_sync(0xffffffffu, D, o), T2 = __shfl_xor_sync(0xffffffffu, T, o);
-      if (md.loss == G4R_LOSS_BPR || md.loss == G4R_LOSS_TOP1) { A += A2; D += D2; }
-      else stat_merge(m, Z, A, Q, D, m2, Z2, A2, Q2, D2);
-      T += T2;     // exactly one chunk owns the target column
+                  Q2 = __shfl_xor_sync(0xffffffffu, Q, o), D2 = __shfl_xor_sync(0xffffffffu, D, o), T2 = __shfl_xor_sync(0xffffffffu, T, o),
+                  h2 = __shfl_xor_sync(0xffffffffu, has, o);
+      stat_combine(md, m, Z, A, Q, D, T, has, m2, Z2, A2, Q2, D2, T2, h2);
     }
-    if (lane == 0) {
+    tt = __shfl_sync(0xffffffffu, tt, 0);
+    __syncthreads();
+    if (lane == 0) { float* w = sW + warp * 8; w[0] = m; w[1] = Z; w[2] = A; w[3] = Q; w[4] = D; w[5] = T; w[6] = has; w[7] = tt; }
+    __syncthreads();
+    if (tid == 0) {
+      tt = sW[7];
+      for (int w = 1; w < nwarp; w++) { const float* q = sW + w * 8; stat_combine(md, m, Z, A, Q, D, T, has, q[0], q[1], q[2], q[3], q[4], q[5], q[6]); }
+      if (loss_softmaxneg(md.loss)) stat_merge(m, Z, A, Q, D, 0.f, 0.f, 0.f, 0.f, 0.f);   // the zeroed diagonal takes part in the max (gru4rec.py:200-202)
       float* rs = md.RS + (size_t)b * G4R_NSTAT;
       float loss = 0.f;
       if (md.loss == G4R_LOSS_XE) {
@@ -541,16 +681,8 @@ __device__ void phase_stats(const ModelDev& md, int s, float* smem) {
         rs[4] = D; rs[5] = tt;
       }
       rs[6] = loss;
-      sLoss[b] = loss;
     }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float c = 0.f;
-    for (int b = 0; b < M; b++) c += sLoss[b];
-    c = __fdiv_rn(c, (float)md.B);            // cost = loss / batch_size (gru4rec.py:577)
-    md.cost[s] = c;
-    if (c != c) atomicExch(md.nanflag, 1);
+    __syncthreads();
   }
 }
 
@@ -611,75 +743,118 @@ __device__ __forceinline__ float loss_grad_elem(const ModelDev& md, const float*
 // Duplicates of an item are adjacent (sorted plan) and handled sequentially in position order:
 // acc / velocity keep the LAST occurrence (set_subtensor), the parameter accumulates all (inc_subtensor).
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sparse_row_update(const ModelDev& md, float* __restrict__ prow, float* __restrict__ arow, float* __restrict__ vrow,
+                                                  const float* gsrc, int gstride, int n_members, int lane, int ld, bool ada, bool mom) {
+  // one item, n_members duplicate positions (in position order): gsrc + k*gstride is the gradient row of member k
+  for (int c4 = lane; c4 < ld / 4; c4 += 32) {
+    const float4 p0 = ld4(prow + c4 * 4);
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), v0 = a0, al = a0, vl = a0;
+    if (ada) a0 = ld4(arow + c4 * 4);
+    if (mom) v0 = ld4(vrow + c4 * 4);
+    float4 ps = p0;
+    for (int k = 0; k < n_members; k++) {
+      const float4 g = ld4(gsrc + (size_t)k * gstride + c4 * 4);
+      float4 gs = g;
+      if (ada) {
+        al.x = a0.x + g.x * g.x; al.y = a0.y + g.y * g.y; al.z = a0.z + g.z * g.z; al.w = a0.w + g.w * g.w;
+        gs.x = __fdiv_rn(g.x, sqrtf(al.x + G4R_EPS_ADA)); gs.y = __fdiv_rn(g.y, sqrtf(al.y + G4R_EPS_ADA));
+        gs.z = __fdiv_rn(g.z, sqrtf(al.z + G4R_EPS_ADA)); gs.w = __fdiv_rn(g.w, sqrtf(al.w + G4R_EPS_ADA));
+      }
+      float4 d;
+      if (md.lmbd > 0.f) { d.x = md.lr * (gs.x + md.lmbd * p0.x); d.y = md.lr * (gs.y + md.lmbd * p0.y); d.z = md.lr * (gs.z + md.lmbd * p0.z); d.w = md.lr * (gs.w + md.lmbd * p0.w); }
+      else { d.x = md.lr * gs.x; d.y = md.lr * gs.y; d.z = md.lr * gs.z; d.w = md.lr * gs.w; }
+      if (mom) {
+        vl.x = md.mom * v0.x - d.x; vl.y = md.mom * v0.y - d.y; vl.z = md.mom * v0.z - d.z; vl.w = md.mom * v0.w - d.w;
+        ps.x += vl.x; ps.y += vl.y; ps.z += vl.z; ps.w += vl.w;
+      } else { ps.x -= d.x; ps.y -= d.y; ps.z -= d.z; ps.w -= d.w; }
+    }
+    st4(prow + c4 * 4, ps);
+    if (ada) st4(arow + c4 * 4, al);
+    if (mom) st4(vrow + c4 * 4, vl);
+  }
+}
+
 __device__ void phase_lossgrad(const ModelDev& md, int s, int chunk, float* smem) {
   const int M = md.wM[s];
   const int sti = md.wSti[s];
   const int N = M + (sti >= 0 ? md.S : 0);
   const int* cbeg = md.pCbeg + (size_t)s * (md.NCH + 1);
   const int cb = cbeg[chunk], ce = cbeg[chunk + 1];
-  if (cb >= ce) {   // empty chunk: its partial dL/dh must read as zero
-    float* pz = md.part + (size_t)chunk * md.B * md.ldL;
-    for (int i = threadIdx.x; i < M * md.ldL; i += blockDim.x) pz[i] = 0.f;
-    return;
-  }
-  const int L = md.L, ldL = md.ldL;
-  (void)L;
-  const float* Y = md.layer[md.n_layers - 1].y;
-  const int* pItem = md.pItem + (size_t)s * md.NP;
-  const int* pPos = md.pPos + (size_t)s * md.NP;
-  const int* tcol = md.pTcol + (size_t)s * md.B;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ldL = md.ldL;
   const int Bp = md.Bld;
   float* sY = smem;                              // [SC_TB][SC_LDS]
   float* sS = sY + SC_TB * SC_LDS;               // [SC_CT][SC_LDS]
   float* sG = sS + SC_CT * SC_LDS;               // [SC_CT][Bp]
+  float* sRS = sG + (size_t)SC_CT * Bp;          // [Bp][8] final row statistics
+  float* sD = sRS + (size_t)Bp * 8;              // [SC_CT][ldL] dSy rows of the current sub tile
+  float* sDby = sD + (size_t)SC_CT * ldL;        // [SC_CT]
+  int* sIt = reinterpret_cast<int*>(sDby + SC_CT);   // [SC_CT] items of the sub tile
+  int* sTc = sIt + SC_CT;                        // [Bp] target column of each lane
+  // final row statistics (+ the step's cost, by chunk 0 in fixed order)
+  for (int i = tid; i < M * 2; i += SC_THREADS) st4(sRS + i * 4, ld4(md.RS + i * 4));
+  for (int b = tid; b < M; b += SC_THREADS) sTc[b] = md.pTcol[(size_t)s * md.B + b];
+  __syncthreads();
+  if (chunk == 0 && tid == 0) {
+    float c = 0.f;
+    for (int b = 0; b < M; b++) c += sRS[b * 8 + 6];
+    c = __fdiv_rn(c, (float)md.B);            // cost = loss / batch_size (gru4rec.py:577)
+    md.cost[s] = c;
+    if (c != c) atomicExch(md.nanflag, 1);
+  }
   float* part = md.part + (size_t)chunk * md.B * ldL;
+  if (cb >= ce) {   // empty chunk: its partial dL/dh must read as zero
+    for (int i = tid; i < M * ldL; i += SC_THREADS) part[i] = 0.f;
+    return;
+  }
+  const float* __restrict__ Y = md.layer[md.n_layers - 1].y;
+  const float* __restrict__ Wy = md.Wy;
+  const int* __restrict__ pItem = md.pItem + (size_t)s * md.NP;
+  const bool single = (ce - cb) <= SC_CT;        // whole chunk in one sub tile: the dSy rows stay in shared memory
   for (int j0 = cb; j0 < ce; j0 += SC_CT) {
     const int nj = min(SC_CT, ce - j0);
-    // gradients of the sub tile
-    for (int i = tid; i < SC_CT * Bp; i += SC_THREADS) {
-      const int jj = i / Bp, b = i % Bp;
-      float g = 0.f;
-      if (jj < nj && b < M) g = loss_grad_elem(md, md.RS + (size_t)b * G4R_NSTAT, md.O[(size_t)(j0 + jj) * Bp + b], tcol[b] == j0 + jj, M, N);
-      sG[i] = g;
+    __syncthreads();
+    if (tid < SC_CT) sIt[tid] = tid < nj ? pItem[j0 + tid] : 0;
+    // gradients of the sub tile: g[b][jj] = dL/do
+    for (int i0 = 0; i0 < SC_CT * Bp; i0 += 4 * SC_THREADS) {
+      float ov[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int i = i0 + u * SC_THREADS + tid;
+        const int jj = i / Bp, b = i % Bp;
+        ov[u] = (i < SC_CT * Bp && jj < nj && b < M) ? md.O[(size_t)(j0 + jj) * Bp + b] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int i = i0 + u * SC_THREADS + tid;
+        const int jj = i / Bp, b = i % Bp;
+        if (i < SC_CT * Bp) sG[i] = (jj < nj && b < M) ? loss_grad_elem(md, sRS + (size_t)b * 8, ov[u], sTc[b] == j0 + jj, M, N) : 0.f;
+      }
     }
     __syncthreads();
-    // dby
-    for (int jj = warp; jj < nj; jj += SC_THREADS / 32) {
+    for (int jj = warp; jj < nj; jj += SC_THREADS / 32) {    // dby
       float a = 0.f;
       for (int b = lane; b < M; b += 32) a += sG[jj * Bp + b];
       a = warp_sum(a);
-      if (lane == 0) md.DBY[j0 + jj] = a;
+      if (lane == 0) { sDby[jj] = a; md.DBY[j0 + jj] = a; }
     }
     for (int k0 = 0; k0 < ldL; k0 += SC_KT) {
       const int kw = min(SC_KT, ldL - k0) / 4;
-      // stage Sy slab
-      for (int i = tid; i < nj * kw; i += SC_THREADS) {
-        const int rr = i / kw, c4 = i % kw;
-        st4(sS + rr * SC_LDS + c4 * 4, ld4(md.Wy + (size_t)pItem[j0 + rr] * ldL + k0 + c4 * 4));
-      }
+      stage_rows4(sS, SC_LDS, nj, kw, [&](int rr) -> const float* { return Wy + (size_t)sIt[rr] * ldL + k0; });
       float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0;     // dSy for columns warp, warp+8 at feature quad `lane`
       for (int b0 = 0; b0 < M; b0 += SC_TB) {
+        if (b0 > 0) __syncthreads();
+        stage_rows4(sY, SC_LDS, SC_TB, kw, [&](int rr) -> const float* { return (b0 + rr < M) ? Y + (size_t)(b0 + rr) * ldL + k0 : nullptr; });
         __syncthreads();
-        for (int i = tid; i < SC_TB * kw; i += SC_THREADS) {
-          const int rr = i / kw, c4 = i % kw;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (b0 + rr < M) v = ld4(Y + (size_t)(b0 + rr) * ldL + k0 + c4 * 4);
-          st4(sY + rr * SC_LDS + c4 * 4, v);
-        }
-        __syncthreads();
-        // dSy_j[k] += sum_b g[b][j] * y[b][k]
         if (lane < kw) {
           const int nb = min(SC_TB, M - b0);
-          for (int bb = 0; bb < nb; bb++) {
+          for (int bb = 0; bb < nb; bb++) {     // dSy_j[k] += sum_b g[b][j] * y[b][k]
             const float4 y = ld4(sY + bb * SC_LDS + lane * 4);
             const float g0 = sG[warp * Bp + b0 + bb], g1 = sG[(warp + 8) * Bp + b0 + bb];
             d0.x = fmaf(g0, y.x, d0.x); d0.y = fmaf(g0, y.y, d0.y); d0.z = fmaf(g0, y.z, d0.z); d0.w = fmaf(g0, y.w, d0.w);
             d1.x = fmaf(g1, y.x, d1.x); d1.y = fmaf(g1, y.y, d1.y); d1.z = fmaf(g1, y.z, d1.z); d1.w = fmaf(g1, y.w, d1.w);
           }
-        }
-        // partial dL/dh[b][k] (+)= sum_j g[b][j] * Sy_j[k] : warp handles lanes b = b0 + warp + 8*q
-        if (lane < kw) {
+          // partial dL/dh[b][k] (+)= sum_j g[b][j] * Sy_j[k] : this warp handles lanes b0 + warp + 8*q
           for (int bb = warp; bb < SC_TB && b0 + bb < M; bb += SC_THREADS / 32) {
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int jj = 0; jj < nj; jj++) {
@@ -694,14 +869,14 @@ __device__ void phase_lossgrad(const ModelDev& md, int s, int chunk, float* smem
         }
       }
       if (lane < kw) {
-        if (warp < nj) st4(md.DSY + (size_t)(j0 + warp) * ldL + k0 + lane * 4, d0);
-        if (warp + 8 < nj) st4(md.DSY + (size_t)(j0 + warp + 8) * ldL + k0 + lane * 4, d1);
+        if (warp < nj) { st4(sD + (size_t)warp * ldL + k0 + lane * 4, d0); if (!single) st4(md.DSY + (size_t)(j0 + warp) * ldL + k0 + lane * 4, d0); }
+        if (warp + 8 < nj) { st4(sD + (size_t)(warp + 8) * ldL + k0 + lane * 4, d1); if (!single) st4(md.DSY + (size_t)(j0 + warp + 8) * ldL + k0 + lane * 4, d1); }
       }
       __syncthreads();
     }
   }
   __syncthreads();
-  // ---- sparse update of this chunk's item groups; one warp per group
+  // ---- sparse update of this chunk's item groups; one warp per group, members in position order
   const bool ada = md.adapt == G4R_ADAPT_ADAGRAD;
   const bool mom = md.mom > 0.f;
   for (int j = cb + warp; j < ce; j += SC_THREADS / 32) {
@@ -709,42 +884,14 @@ __device__ void phase_lossgrad(const ModelDev& md, int s, int chunk, float* smem
     if (j > cb && pItem[j - 1] == item) continue;          // not a group start
     int je = j + 1;
     while (je < ce && pItem[je] == item) je++;
-    {
-      float* prow = md.Wy + (size_t)item * ldL;
-      float* arow = md.Wy_acc ? md.Wy_acc + (size_t)item * ldL : nullptr;
-      float* vrow = md.Wy_vel ? md.Wy_vel + (size_t)item * ldL : nullptr;
-      for (int c4 = lane; c4 < ldL / 4; c4 += 32) {
-        const float4 p0 = ld4(prow + c4 * 4);
-        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), v0 = a0, al = a0, vl = a0;
-        if (ada) a0 = ld4(arow + c4 * 4);
-        if (mom) v0 = ld4(vrow + c4 * 4);
-        float4 ps = p0;
-        for (int jj = j; jj < je; jj++) {
-          const float4 g = ld4(md.DSY + (size_t)jj * ldL + c4 * 4);
-          float4 gs = g;
-          if (ada) {
-            al.x = a0.x + g.x * g.x; al.y = a0.y + g.y * g.y; al.z = a0.z + g.z * g.z; al.w = a0.w + g.w * g.w;
-            gs.x = __fdiv_rn(g.x, sqrtf(al.x + G4R_EPS_ADA)); gs.y = __fdiv_rn(g.y, sqrtf(al.y + G4R_EPS_ADA));
-            gs.z = __fdiv_rn(g.z, sqrtf(al.z + G4R_EPS_ADA)); gs.w = __fdiv_rn(g.w, sqrtf(al.w + G4R_EPS_ADA));
-          }
-          float4 d;
-          if (md.lmbd > 0.f) { d.x = md.lr * (gs.x + md.lmbd * p0.x); d.y = md.lr * (gs.y + md.lmbd * p0.y); d.z = md.lr * (gs.z + md.lmbd * p0.z); d.w = md.lr * (gs.w + md.lmbd * p0.w); }
-          else { d.x = md.lr * gs.x; d.y = md.lr * gs.y; d.z = md.lr * gs.z; d.w = md.lr * gs.w; }
-          if (mom) {
-            vl.x = md.mom * v0.x - d.x; vl.y = md.mom * v0.y - d.y; vl.z = md.mom * v0.z - d.z; vl.w = md.mom * v0.w - d.w;
-            ps.x += vl.x; ps.y += vl.y; ps.z += vl.z; ps.w += vl.w;
-          } else { ps.x -= d.x; ps.y -= d.y; ps.z -= d.z; ps.w -= d.w; }
-        }
-        st4(prow + c4 * 4, ps);
-        if (ada) st4(arow + c4 * 4, al);
-        if (mom) st4(vrow + c4 * 4, vl);
-      }
-    }
+    const float* gsrc = single ? (sD + (size_t)(j - cb) * ldL) : (md.DSY + (size_t)j * ldL);
+    sparse_row_update(md, md.Wy + (size_t)item * ldL, md.Wy_acc ? md.Wy_acc + (size_t)item * ldL : nullptr,
+                      md.Wy_vel ? md.Wy_vel + (size_t)item * ldL : nullptr, gsrc, ldL, je - j, lane, ldL, ada, mom);
     if (lane == 0) {   // By (gru4rec.py:486-489)
       const float p0 = md.By[item];
       float a0 = ada ? md.By_acc[item] : 0.f, v0 = mom ? md.By_vel[item] : 0.f, al = 0.f, vl = 0.f, ps = p0;
       for (int jj = j; jj < je; jj++) {
-        const float g = md.DBY[jj];
+        const float g = single ? sDby[jj - cb] : md.DBY[jj];
         float gs = g;
         if (ada) { al = a0 + g * g; gs = __fdiv_rn(g, sqrtf(al + G4R_EPS_ADA)); }
         const float d = md.lmbd > 0.f ? md.lr * (gs + md.lmbd * p0) : md.lr * gs;
@@ -756,7 +903,9 @@ __device__ void phase_lossgrad(const ModelDev& md, int s, int chunk, float* smem
     }
   }
 }
-__host__ __device__ inline size_t lossgrad_smem_bytes(int Bld) { return (size_t)(SC_TB * SC_LDS + SC_CT * SC_LDS + SC_CT * Bld + 32) * sizeof(float); }
+__host__ __device__ inline size_t lossgrad_smem_bytes(int Bld, int ldL) {
+  return (size_t)(SC_TB * SC_LDS + SC_CT * SC_LDS + SC_CT * Bld + Bld * 8 + SC_CT * ldL + SC_CT + SC_CT + Bld + 32) * sizeof(float);
+}
 
 // ------------------------------------------------------------------------------------------------
 // phase B1: elementwise part of the GRU backward: dh, dz, dh~, da_h, da_z
@@ -766,32 +915,46 @@ __device__ void phase_b1(const ModelDev& md, int li, int s, int cta, int ncta) {
   const int M = md.wM[s];
   const int L = ly.L, ldL = ly.ldL;
   const bool last = (li == md.n_layers - 1);
-  const int* cbeg = md.pCbeg + (size_t)s * (md.NCH + 1);
   const uint32_t gstep = md.wG[s];
   const float retain = 1.0f - md.p_drop_h;
-  for (int i = cta * blockDim.x + threadIdx.x; i < M * L; i += ncta * blockDim.x) {
-    const int b = i / L, c = i % L;
-    float dy;
-    if (last) {
-      dy = 0.f;
-      // fixed-order sum of the per-chunk partials, four independent loads in flight
-      const float* pp = md.part + (size_t)b * ldL + c;
-      const size_t cs = (size_t)md.B * ldL;
-      float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-      int ch = 0;
-      for (; ch + 4 <= md.NCH; ch += 4) { d0 += pp[(size_t)ch * cs]; d1 += pp[(size_t)(ch + 1) * cs]; d2 += pp[(size_t)(ch + 2) * cs]; d3 += pp[(size_t)(ch + 3) * cs]; }
-      for (; ch < md.NCH; ch++) d0 += pp[(size_t)ch * cs];
-      dy = (d0 + d1) + (d2 + d3);
-    } else dy = ly.dy[(size_t)b * ldL + c];
-    float dh = dy;
-    if (md.p_drop_h > 0.f) dh *= drop_scale(md.drop_seed, gstep, (uint32_t)li, (uint32_t)(b * L + c), retain);
+  const float* __restrict__ part = md.part;
+  const float* __restrict__ Ht = ly.ht;
+  const float* __restrict__ Ho = ly.Hold;
+  const float* __restrict__ Zz = ly.z;
+  const float* __restrict__ Ah = ly.ah;
+  const float* __restrict__ Dy = ly.dy;
+  // eight lanes cooperate on one element: each sums every 8th chunk partial (independent loads), fixed-order tree
+  const int sub = threadIdx.x & 7;
+  const int grp = (cta * blockDim.x + threadIdx.x) >> 3, ngrp = (ncta * blockDim.x) >> 3;
+  const size_t cs = (size_t)md.B * ldL;
+  const int E = M * L;
+  for (int e0 = 0; e0 < E; e0 += ngrp) {
+    const int e = e0 + grp;
+    const bool ok = e < E;
+    const int b = ok ? e / L : 0, c = ok ? e % L : 0;
     const size_t o = (size_t)b * ldL + c;
-    const float ht = ly.ht[o], ho = ly.Hold[o], z = ly.z[o];
-    const float dz = dh * (ht - ho);
-    const float dht = dh * z;
-    const float dah = dht * act_der(md.hact, ly.ah[o], ht);
-    ly.dvec[(size_t)b * ly.ld3 + c] = dah;
-    ly.dvec[(size_t)b * ly.ld3 + 2 * L + c] = dz * z * (1.f - z);
+    float ht = 0.f, ho = 0.f, z = 0.f, ah = 0.f, dy = 0.f;
+    if (ok && sub == 0) { ht = Ht[o]; ho = Ho[o]; z = Zz[o]; ah = Ah[o]; if (!last) dy = Dy[o]; }
+    if (last) {
+      float d0 = 0.f, d1 = 0.f;
+      if (ok) {
+        int ch = sub;
+        for (; ch + 8 < md.NCH; ch += 16) { d0 += part[(size_t)ch * cs + o]; d1 += part[(size_t)(ch + 8) * cs + o]; }
+        if (ch < md.NCH) d0 += part[(size_t)ch * cs + o];
+      }
+      float d = d0 + d1;
+      d += __shfl_xor_sync(0xffffffffu, d, 4); d += __shfl_xor_sync(0xffffffffu, d, 2); d += __shfl_xor_sync(0xffffffffu, d, 1);
+      dy = d;
+    }
+    if (ok && sub == 0) {
+      float dh = dy;
+      if (md.p_drop_h > 0.f) dh *= drop_scale(md.drop_seed, gstep, (uint32_t)li, (uint32_t)(b * L + c), retain);
+      const float dz = dh * (ht - ho);
+      const float dht = dh * z;
+      const float dah = dht * act_der(md.hact, ah, ht);
+      ly.dvec[(size_t)b * ly.ld3 + c] = dah;
+      ly.dvec[(size_t)b * ly.ld3 + 2 * L + c] = dz * z * (1.f - z);
+    }
   }
 }
 

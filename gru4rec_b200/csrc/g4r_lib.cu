@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_score(int slot, const int* base,
 }
 __global__ void __launch_bounds__(256) k_stats(int slot, const int* base, int off) {
   extern __shared__ __align__(16) float smem[];
-  phase_stats(MD, STEP_IDX, smem);
+  phase_stats(MD, STEP_IDX, blockIdx.x, gridDim.x, smem);
 }
 __global__ void __launch_bounds__(SC_THREADS) k_lossgrad(int slot, const int* base, int off) {
   extern __shared__ __align__(16) float smem[];
@@ -280,12 +280,12 @@ static int enqueue_train_step(g4r_handle* h, const int* base, int off) {
     LAUNCH(PH_F1, k_f1<<<tiles2(2 * ly.L, B), GEMM_THREADS, 0, st>>>(h->slot, base, off, li, ly.H));
     LAUNCH(PH_F2, k_f2<<<tiles2(ly.L, B), GEMM_THREADS, 0, st>>>(h->slot, base, off, li, ly.H, 1));
   }
-  LAUNCH(PH_SCORE, k_score<<<md.NCH, SC_THREADS, score_smem_bytes(h->Bmax), st>>>(h->slot, base, off));
-  LAUNCH(PH_STATS, k_stats<<<1, 256, (size_t)(h->Bmax + 32) * sizeof(float), st>>>(h->slot, base, off));
-  LAUNCH(PH_LOSSGRAD, k_lossgrad<<<md.NCH, SC_THREADS, lossgrad_smem_bytes(md.Bld), st>>>(h->slot, base, off));
+  LAUNCH(PH_SCORE, k_score<<<md.NCH, SC_THREADS, score_smem_bytes(md.Bld), st>>>(h->slot, base, off));
+  LAUNCH(PH_STATS, k_stats<<<B, 256, 256 * sizeof(float), st>>>(h->slot, base, off));
+  LAUNCH(PH_LOSSGRAD, k_lossgrad<<<md.NCH, SC_THREADS, lossgrad_smem_bytes(md.Bld, md.ldL), st>>>(h->slot, base, off));
   for (int li = md.n_layers - 1; li >= 0; li--) {
     const LayerDev& ly = md.layer[li];
-    LAUNCH(PH_B1, k_b1<<<std::max(1, std::min(h->n_sm, (B * ly.L + 255) / 256)), 256, 0, st>>>(h->slot, base, off, li));
+    LAUNCH(PH_B1, k_b1<<<std::max(1, std::min(h->n_sm, (B * ly.L * 8 + 255) / 256)), 256, 0, st>>>(h->slot, base, off, li));
     LAUNCH(PH_B2, k_b2<<<tiles2(ly.L, B), GEMM_THREADS, 0, st>>>(h->slot, base, off, li));
     if (ly.in_dim > 0) LAUNCH(PH_B3, k_b3<<<tiles2(ly.in_dim, B), GEMM_THREADS, 0, st>>>(h->slot, base, off, li));
     const DenseJobs dj = dense_jobs(ly.L, ly.in_dim);
@@ -392,10 +392,10 @@ extern "C" int g4r_create(const g4r_config* cfg, void* device_workspace, size_t 
   ok &= cudaMallocHost(&h->hCost, (size_t)CAP * sizeof(float)) == cudaSuccess;
   if (!ok) return bail(G4R_ERR_CUDA, "pinned host allocation failed");
   // opt in to large dynamic shared memory where needed
-  cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)score_smem_bytes(h->Bmax));
-  cudaFuncSetAttribute(k_lossgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lossgrad_smem_bytes(h->md.Bld));
+  cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)score_smem_bytes(h->md.Bld));
+  cudaFuncSetAttribute(k_lossgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lossgrad_smem_bytes(h->md.Bld, h->md.ldL));
   cudaFuncSetAttribute(k_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)h->npow2 * 8 + 1024));
-  h->pk_smem = std::max(std::max(score_smem_bytes(h->Bmax), lossgrad_smem_bytes(h->md.Bld)), (size_t)2 * GK * (GB + 1) * sizeof(float));
+  h->pk_smem = std::max(std::max(score_smem_bytes(h->md.Bld), lossgrad_smem_bytes(h->md.Bld, h->md.ldL)), (size_t)2 * GK * (GB + 1) * sizeof(float));
   cudaFuncSetAttribute(k_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->pk_smem);
   {
     int per_sm = 0;
@@ -783,6 +783,7 @@ static int run_window(g4r_handle* h, int64_t n) {
   if (h->cfg.step_mode == 1 && !h->prof) {
     int slot = h->slot, nst = (int)n; GridBar* gb = h->dGridBar; unsigned long long* ts = h->stamp_on ? h->dStamp : nullptr;
     void* args[] = {&slot, &nst, &gb, &ts};
+    CK(cudaMemsetAsync(h->dGridBar, 0, sizeof(GridBar), h->stream));
     CK(cudaLaunchCooperativeKernel((void*)k_persistent, dim3(h->pk_blocks), dim3(PK_THREADS), args, h->pk_smem, h->stream));
     h->launches += 1;
   } else if (h->prof || !h->use_graph) {

@@ -152,7 +152,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=200)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--step-mode', type=int, default=-1)
+    ap.add_argument('--step-mode', type=int, default=2, help='0 per-phase kernels (CUDA graph), 1 persistent kernel, 2 role-specialised persistent kernel (default)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -173,7 +173,7 @@ def main():
     make_cfg = _lib.make_config
     mk = dict(WORKLOAD['model'])
     cfg = make_cfg(WORKLOAD['n_items'], mk, sample_store=WORKLOAD['sample_store'], eval_lanes=0,
-                   max_resident_steps=max(K, W) + 8, step_mode=max(args.step_mode, 0))
+                   max_resident_steps=max(K, W) + 8, step_mode=args.step_mode)
     eng = _lib.Engine(cfg, device=local_rank)
     # parameters: the reference's initialisation (gru4rec.py:254-294); data: synthetic RSC15-shaped sessions, disjoint per rank
     import gru4rec as g4
@@ -245,7 +245,7 @@ def main():
         'config': {'workload': WORKLOAD['name'], 'n_items': WORKLOAD['n_items'], 'global_batch': B * world, 'n_sample': mk['n_sample'],
                    'layers': mk['layers'], 'params': 'param_samples/rsc15_bpr-max.py', 'parallelism': 'dp%d' % world,
                    'l2': 'working set (item tables + Adagrad/momentum state = 180 MB) larger than L2; rows touched change every step',
-                   'step_mode': int(cfg.step_mode), 'events_per_sec': value * B},
+                   'step_mode': int(cfg.step_mode), 'fast_windows': list(eng.fast_windows()), 'events_per_sec': value * B},
         'e2e': {'value': e2e_value, 'unit': 'mb/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches),
         'clocks': clocks.summary(),

@@ -38,7 +38,7 @@ EXPORTS = [
     'g4r_mrg_uniform', 'g4r_searchsorted', 'g4r_gather_rows',
     'g4r_schedule_build', 'g4r_schedule_free', 'g4r_schedule_steps', 'g4r_schedule_events', 'g4r_schedule_export',
     'g4r_train_step', 'g4r_train_steps', 'g4r_upload_steps', 'g4r_run_uploaded', 'g4r_kernel_launches',
-    'g4r_profile_uploaded', 'g4r_phase_name', 'g4r_phase_count', 'g4r_persistent_stamps',
+    'g4r_profile_uploaded', 'g4r_phase_name', 'g4r_phase_count', 'g4r_persistent_stamps', 'g4r_fast_windows',
     'g4r_eval_schedule', 'g4r_predict', 'g4r_reset_eval_hidden',
 ]
 
@@ -91,6 +91,7 @@ def load():
     lib.g4r_phase_name.argtypes = [i32]; lib.g4r_phase_name.restype = C.c_char_p
     lib.g4r_phase_count.restype = C.c_int
     lib.g4r_persistent_stamps.argtypes = [vp, i32, vp, i64]
+    lib.g4r_fast_windows.argtypes = [vp, C.POINTER(i64)]; lib.g4r_fast_windows.restype = i64
     lib.g4r_eval_schedule.argtypes = [vp, vp, vp, i32, i32, vp, vp, C.POINTER(i64)]
     lib.g4r_predict.argtypes = [vp, vp, i32, vp, vp]
     lib.g4r_reset_eval_hidden.argtypes = [vp]
@@ -356,6 +357,11 @@ class Engine(object):
         out = np.zeros((n_steps, 16), dtype=np.uint64) if n_steps > 0 else None
         self._check(self.lib.g4r_persistent_stamps(self.h, 1 if enable else 0, _ptr(out), n_steps))
         return out
+
+    def fast_windows(self):
+        fb = C.c_int64()
+        n = self.lib.g4r_fast_windows(self.h, C.byref(fb))
+        return n, fb.value
 
     def kernel_launches(self):
         return self.lib.g4r_kernel_launches(self.h)

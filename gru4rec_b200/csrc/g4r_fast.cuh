@@ -1,0 +1,712 @@
+// g4r_fast.cuh -- role-specialised persistent kernel for the headline shape family:
+//   no-embedding mode, one GRU layer, L <= 128, batch <= 32, every score-column chunk <= 16 columns.
+// (step_mode 2; anything else runs k_persistent / the per-phase kernels, which share all numerics.)
+//
+// Why: at B=32, L=100 a mini-batch is ~8 dependent phases over ~6 MB; time is memory/barrier latency.  This kernel
+//  * keeps every CTA a "column CTA" owning one chunk of score columns; the chunk's Wy / Adagrad / momentum rows and
+//    the target rows are PREFETCHED with TMA bulk copies (cp.async.bulk -> mbarrier complete_tx) while the GRU
+//    phases of the previous step run, so the score phase starts with its operands already in shared memory;
+//  * folds the row-statistics combine into the score->gradient barrier (the last CTA to arrive combines);
+//  * runs the GRU phases on a group of G CTAs with group barriers; the other CTAs only wait for `h_ready`;
+//  * uses monotonic release/acquire counters (no resets, no separate fences) for all synchronisation.
+#pragma once
+
+constexpr int FK_THREADS = 512;
+constexpr int FK_NW = FK_THREADS / 32;   // warps per CTA
+constexpr int FK_G = 48;            // CTAs that run the GRU phases
+constexpr int FK_CT = 32;           // max columns per chunk
+constexpr int FK_Q = FK_CT / FK_NW;  // columns per warp
+constexpr int FK_B = 32;            // max lanes
+constexpr int FK_LDS = 132;         // shared row stride (floats) for L <= 128: conflict-free 16-byte accesses
+
+
+__device__ __forceinline__ void red_release_add(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int atom_acqrel_add(unsigned int* p, unsigned int v) {
+  unsigned int old;
+  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void wait_ge(const unsigned int* p, unsigned int target) {
+  while (ld_acquire_u32(p) < target) { }
+}
+// ---- mbarrier + TMA bulk copy (1-D, no tensor map): rows of ld*4 bytes, 16-byte aligned ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned int parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_row(void* sdst, const void* gsrc, unsigned int bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct FastSmem {
+  // column role
+  alignas(128) float sY[FK_B * FK_LDS];          // h of the step (all lanes)
+  float sS[FK_CT * FK_LDS];         // Wy rows of the chunk (TMA)
+  float sAcc[FK_CT * FK_LDS];       // Adagrad rows (TMA)
+  float sVel[FK_CT * FK_LDS];       // momentum rows (TMA)
+  float sTW[FK_B * FK_LDS];         // target rows (TMA; pairwise losses)
+  float sD[FK_CT * FK_LDS];         // dSy rows
+  float sG[FK_CT * FK_B];           // dL/do
+  float sO[FK_CT * FK_B];           // scores o
+  float sRS[FK_B * 8];
+  float sPart[FK_NW * FK_B * 8];
+  float sT[FK_B];                   // target activations
+  float sBias[FK_CT], sByP[FK_CT], sByA[FK_CT], sByV[FK_CT], sDby[FK_CT], sTB[FK_B];
+  int sIt[2][FK_CT], sPos[2][FK_CT], sTc[2][FK_B], sYit[2][FK_B], sCb[2][2];
+  int sFlag[4];
+  alignas(8) unsigned long long mbar;
+  // GRU role: thin-slab phases (every GRU CTA owns a few output columns / rows and stages the full 32-lane operand)
+  alignas(16) float gA[FK_B * 388];             // staged [32 x <=384] operand (H, Hold*r, da_h, dvec)
+  alignas(16) float gW[8 * FK_LDS + FK_NW * FK_B * 5];      // this CTA's weight slab (<= 8 columns/rows of length <= 128) + reduction scratch
+  int gIdx[3 * FK_B];               // slot, item, flags of the lanes
+};
+
+// loads the index metadata of step s into buffer `buf` (plain loads; consumed much later)
+__device__ __forceinline__ void fk_load_idx(const ModelDev& md, FastSmem& sm, int s, int n_steps, int chunk, int buf) {
+  const int tid = threadIdx.x;
+  if (s >= n_steps) return;
+  const int M = md.wM[s];
+  const int* cbeg = md.pCbeg + (size_t)s * (md.NCH + 1);
+  const bool hc = chunk < md.NCH;
+  const int cb = hc ? cbeg[chunk] : 0, ce = hc ? cbeg[chunk + 1] : 0;
+  if (tid < FK_CT) {
+    int it = 0, pos = 0;
+    if (cb + tid < ce) { it = md.pItem[(size_t)s * md.NP + cb + tid]; pos = md.pPos[(size_t)s * md.NP + cb + tid]; }
+    sm.sIt[buf][tid] = it; sm.sPos[buf][tid] = pos;
+  }
+  if (tid >= 32 && tid < 32 + FK_B) {
+    const int b = tid - 32;
+    sm.sTc[buf][b] = b < M ? md.pTcol[(size_t)s * md.B + b] : -1;
+    sm.sYit[buf][b] = b < M ? md.wY[(size_t)s * md.B + b] : 0;
+  }
+  if (tid == 64) { sm.sCb[buf][0] = cb; sm.sCb[buf][1] = ce; }
+}
+
+// issue the TMA prefetch of step s (rows are final once the previous step's updates are complete)
+__device__ __forceinline__ void fk_prefetch_rows(const ModelDev& md, FastSmem& sm, int s, int n_steps, int buf, bool pw) {
+  if (s >= n_steps) return;
+  const int tid = threadIdx.x;
+  const int M = md.wM[s];
+  const int cb = sm.sCb[buf][0], ce = sm.sCb[buf][1];
+  const int nj = ce - cb;
+  const bool ada = md.adapt == G4R_ADAPT_ADAGRAD, mom = md.mom > 0.f;
+  const unsigned int rowb = (unsigned int)md.ldL * 4u;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(&sm.mbar);
+  if (tid < 32) {
+    if (tid == 0) {
+      const unsigned int total = rowb * (unsigned int)(nj * (1 + (ada ? 1 : 0) + (mom ? 1 : 0)) + (pw ? M : 0));
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      if (total > 0) mbar_expect_tx(bar, total);
+      else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+    }
+    __syncwarp();
+    if (tid < nj) {
+      const size_t off = (size_t)sm.sIt[buf][tid] * md.ldL;
+      tma_row(sm.sS + tid * FK_LDS, md.Wy + off, rowb, bar);
+      if (ada) tma_row(sm.sAcc + tid * FK_LDS, md.Wy_acc + off, rowb, bar);
+      if (mom) tma_row(sm.sVel + tid * FK_LDS, md.Wy_vel + off, rowb, bar);
+    }
+    if (pw && tid < M) tma_row(sm.sTW + tid * FK_LDS, md.Wy + (size_t)sm.sYit[buf][tid] * md.ldL, rowb, bar);
+  } else if (tid >= 64 && tid < 64 + FK_CT) {
+    const int j = tid - 64;
+    if (j < nj) {
+      const int it = sm.sIt[buf][j];
+      float bz = md.By[it];
+      sm.sByP[j] = bz;
+      if (md.logq > 0.f) bz -= (sm.sPos[buf][j] < M) ? md.logP0t[it] : md.logP0s[it];
+      sm.sBias[j] = bz;
+      sm.sByA[j] = ada ? md.By_acc[it] : 0.f;
+      sm.sByV[j] = mom ? md.By_vel[it] : 0.f;
+    }
+  } else if (tid >= 96 && tid < 96 + FK_B) {
+    const int b = tid - 96;
+    if (pw && b < M) {
+      const int it = sm.sYit[buf][b];
+      float bz = md.By[it];
+      if (md.logq > 0.f) bz -= md.logP0t[it];
+      sm.sTB[b] = bz;
+    }
+  }
+}
+
+__device__ __forceinline__ void fk_group_barrier(FastSync* fs, unsigned int& gepoch) {
+  __syncthreads();
+  gepoch += 1;
+  if (threadIdx.x == 0) { red_release_add(&fs->grp, 1u); wait_ge(&fs->grp, gepoch * FK_G); }
+  __syncthreads();
+}
+
+// ---------------- thin-slab GRU phases (no-embedding mode, one layer, M <= 32, L <= 128) ----------------
+// ncu on the 32x32-tile kernels showed ~2000 instructions per warp at ~8.6 cycles each (2 warps per scheduler):
+// the GRU phases are instruction-latency bound.  Here the work of a phase is spread over all FK_G CTAs (a few
+// output columns each), the reduction dimension is split over the 8 warps, and every thread issues a few dozen FMAs.
+__device__ __forceinline__ void fk_stage_lanes(const ModelDev& md, FastSmem& sm, int s, int M) {
+  if (threadIdx.x < FK_B) {
+    const int b = threadIdx.x;
+    sm.gIdx[b] = b < M ? md.wSlot[(size_t)s * md.B + b] : -1;
+    sm.gIdx[FK_B + b] = b < M ? md.wX[(size_t)s * md.B + b] : 0;
+    sm.gIdx[2 * FK_B + b] = b < M ? md.wF[(size_t)s * md.B + b] : 0;
+  }
+  __syncthreads();
+}
+// acc[j] (j < W) for lane b = tid % 32 over the k-slice of warp tid / 32: sum_k A[b][k] * Wt[j][k]
+template <int W>
+__device__ __forceinline__ void fk_slab_dot(float (&acc)[W], const float* sAop, int lda, const float* sWt, int K) {
+  const int b = threadIdx.x & 31, ks = threadIdx.x >> 5;
+  const int kq = (K + 3) / 4;                      // float4 count along k
+  const int per = (kq + FK_NW - 1) / FK_NW;
+  const int q0 = ks * per, q1 = min(kq, q0 + per);
+#pragma unroll
+  for (int j = 0; j < W; j++) acc[j] = 0.f;
+  for (int q = q0; q < q1; q++) {
+    const float4 a = ld4(sAop + b * lda + q * 4);
+#pragma unroll
+    for (int j = 0; j < W; j++) {
+      const float4 w = ld4(sWt + j * FK_LDS + q * 4);
+      acc[j] = fmaf(a.x, w.x, acc[j]); acc[j] = fmaf(a.y, w.y, acc[j]); acc[j] = fmaf(a.z, w.z, acc[j]); acc[j] = fmaf(a.w, w.w, acc[j]);
+    }
+  }
+}
+// cross-warp reduction of acc[W] per lane: red[ks][b][j] -> thread (b, j) sums the 8 slices in fixed order
+template <int W>
+__device__ __forceinline__ float fk_slab_reduce(const float (&acc)[W], float* red, int jsel) {
+  const int b = threadIdx.x & 31, ks = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < W; j++) red[(ks * FK_B + b) * W + j] = acc[j];
+  __syncthreads();
+  float v = 0.f;
+  if (jsel < W) {
+#pragma unroll
+    for (int k = 0; k < FK_NW; k++) v += red[(k * FK_B + b) * W + jsel];
+  }
+  return v;
+}
+constexpr int FK_W1 = 5;    // rz columns per CTA   (ceil(2*128 / 48) = 6 would also fit; 2L <= 240 with 48 CTAs)
+constexpr int FK_W2 = 3;    // h / dHr columns per CTA (L <= 144)
+
+// F1: rz = sigmoid(Wx0[X][L:3L] + Bh[L:3L] + H @ Wrz) for this CTA's FK_W1 columns; CTA 0 also writes Hold
+__device__ void fk_f1(const ModelDev& md, FastSmem& sm, int s, int cta) {
+  const LayerDev& ly = md.layer[0];
+  const int M = md.wM[s], L = ly.L, ldL = ly.ldL, tid = threadIdx.x;
+  const int c0 = cta * FK_W1;
+  if (c0 >= 2 * L) return;
+  const int W = min(FK_W1, 2 * L - c0);
+  fk_stage_lanes(md, sm, s, M);
+  const int kw = ldL / 4;
+  // stage H rows (zero for out-of-range lanes) and the transposed weight slab Wt[j][k] = Wrz[k][c0 + j]
+  stage_rows4(sm.gA, FK_LDS, FK_B, kw, [&](int rr) -> const float* { const int sl = sm.gIdx[rr]; return sl >= 0 ? ly.H + (size_t)sl * ldL : nullptr; });
+  for (int i = tid; i < FK_W1 * FK_LDS; i += FK_THREADS) {
+    const int j = i / FK_LDS, k = i % FK_LDS;
+    sm.gW[i] = (j < W && k < L) ? ly.Wrz[(size_t)k * ly.ld2 + c0 + j] : 0.f;
+  }
+  // epilogue operands of thread (b, j): gathered input row element + bias
+  const int b = tid & 31, jsel = tid >> 5;
+  float pre = 0.f;
+  if (jsel < W && b < M) pre = ly.Wx[(size_t)sm.gIdx[FK_B + b] * ly.ld3 + L + c0 + jsel] + ly.Bh[L + c0 + jsel];
+  __syncthreads();
+  float acc[FK_W1];
+  fk_slab_dot<FK_W1>(acc, sm.gA, FK_LDS, sm.gW, L);
+  const float v = fk_slab_reduce<FK_W1>(acc, sm.gW + 8 * FK_LDS, jsel);
+  if (jsel < W && b < M) {
+    const int c = c0 + jsel;
+    const float g = sigmoidf_(v + pre);
+    if (c < L) ly.r[(size_t)b * ldL + c] = g; else ly.z[(size_t)b * ldL + (c - L)] = g;
+  }
+  if (cta == 0) {
+    for (int i = tid; i < FK_B * kw; i += FK_THREADS) {
+      const int rr = i / kw, c4 = i % kw;
+      if (rr < M) st4(ly.Hold + (size_t)rr * ldL + c4 * 4, ld4(sm.gA + rr * FK_LDS + c4 * 4));
+    }
+  }
+}
+// F2: h~ = act(Wx0[X][0:L] + Bh[0:L] + (H*r) @ Wh), h, dropout, H_new for this CTA's FK_W2 columns
+__device__ void fk_f2(const ModelDev& md, FastSmem& sm, int s, int cta) {
+  const LayerDev& ly = md.layer[0];
+  const int M = md.wM[s], L = ly.L, ldL = ly.ldL, tid = threadIdx.x;
+  const int c0 = cta * FK_W2;
+  if (c0 >= L) return;
+  const int W = min(FK_W2, L - c0);
+  fk_stage_lanes(md, sm, s, M);
+  const int kw = ldL / 4;
+  // stage H*r
+  for (int i0 = 0; i0 < FK_B * kw; i0 += 2 * FK_THREADS) {
+    float4 hv[2], rv[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int i = i0 + u * FK_THREADS + tid;
+      hv[u] = make_float4(0.f, 0.f, 0.f, 0.f); rv[u] = hv[u];
+      if (i < FK_B * kw) {
+        const int rr = i / kw, c4 = i % kw;   // Hold (compact copy written by CTA 0 in F1): H itself is being overwritten
+        if (rr < M) { hv[u] = ld4(ly.Hold + (size_t)rr * ldL + c4 * 4); rv[u] = ld4(ly.r + (size_t)rr * ldL + c4 * 4); }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int i = i0 + u * FK_THREADS + tid;
+      if (i < FK_B * kw) st4(sm.gA + (i / kw) * FK_LDS + (i % kw) * 4, make_float4(hv[u].x * rv[u].x, hv[u].y * rv[u].y, hv[u].z * rv[u].z, hv[u].w * rv[u].w));
+    }
+  }
+  for (int i = tid; i < FK_W2 * FK_LDS; i += FK_THREADS) {
+    const int j = i / FK_LDS, k = i % FK_LDS;
+    sm.gW[i] = (j < W && k < L) ? ly.Wh[(size_t)k * ldL + c0 + j] : 0.f;
+  }
+  const int b = tid & 31, jsel = tid >> 5;
+  float pre = 0.f, z = 0.f, ho = 0.f;
+  if (jsel < W && b < M) {
+    const int c = c0 + jsel;
+    pre = ly.Wx[(size_t)sm.gIdx[FK_B + b] * ly.ld3 + c] + ly.Bh[c];
+    z = ly.z[(size_t)b * ldL + c];
+    ho = ly.Hold[(size_t)b * ldL + c];
+  }
+  __syncthreads();
+  float acc[FK_W2];
+  fk_slab_dot<FK_W2>(acc, sm.gA, FK_LDS, sm.gW, L);
+  const float v0 = fk_slab_reduce<FK_W2>(acc, sm.gW + 8 * FK_LDS, jsel);
+  if (jsel < W && b < M) {
+    const int c = c0 + jsel;
+    const float v = v0 + pre;
+    const float ht = act_fwd(md.hact, v);
+    float h = (1.0f - z) * ho + z * ht;
+    if (md.p_drop_h > 0.f) h *= drop_scale(md.drop_seed, md.wG[s], 0u, (uint32_t)(b * L + c), 1.0f - md.p_drop_h);
+    ly.ah[(size_t)b * ldL + c] = v;
+    ly.ht[(size_t)b * ldL + c] = ht;
+    ly.y[(size_t)b * ldL + c] = h;
+    ly.H[(size_t)sm.gIdx[b] * ldL + c] = (sm.gIdx[2 * FK_B + b] & 1) ? 0.f : h;
+  }
+}
+// B2: d(H*r)[b][c] = sum_j da_h[b][j] Wh[c][j]; da_r = d(H*r) * Hold * r (1-r) for this CTA's FK_W2 columns
+__device__ void fk_b2(const ModelDev& md, FastSmem& sm, int s, int cta) {
+  const LayerDev& ly = md.layer[0];
+  const int M = md.wM[s], L = ly.L, ldL = ly.ldL, tid = threadIdx.x;
+  const int c0 = cta * FK_W2;
+  if (c0 >= L) return;
+  const int W = min(FK_W2, L - c0);
+  const int kw = ldL / 4;
+  __syncthreads();
+  stage_rows4(sm.gA, FK_LDS, FK_B, kw, [&](int rr) -> const float* { return rr < M ? ly.dvec + (size_t)rr * ly.ld3 : nullptr; });
+  stage_rows4(sm.gW, FK_LDS, W, kw, [&](int rr) -> const float* { return ly.Wh + (size_t)(c0 + rr) * ldL; });
+  const int b = tid & 31, jsel = tid >> 5;
+  float ho = 0.f, r = 0.f;
+  if (jsel < W && b < M) { ho = ly.Hold[(size_t)b * ldL + c0 + jsel]; r = ly.r[(size_t)b * ldL + c0 + jsel]; }
+  __syncthreads();
+  float acc[FK_W2];
+  fk_slab_dot<FK_W2>(acc, sm.gA, FK_LDS, sm.gW, L);
+  const float v = fk_slab_reduce<FK_W2>(acc, sm.gW + 8 * FK_LDS, jsel);
+  if (jsel < W && b < M) ly.dvec[(size_t)b * ly.ld3 + L + c0 + jsel] = v * ho * r * (1.f - r);
+}
+// D: dense gradients of this CTA's row slab of Wh / Wrz (and a slice of Bh) fused with their Adagrad(+momentum) update
+__device__ void fk_dense(const ModelDev& md, FastSmem& sm, int s, int cta) {
+  const LayerDev& ly = md.layer[0];
+  const int M = md.wM[s], L = ly.L, ldL = ly.ldL, ld3 = ly.ld3, tid = threadIdx.x;
+  const int R = (L + FK_G - 1) / FK_G;            // rows of Wh / Wrz per CTA
+  const int k0 = cta * R;
+  const int nr = max(0, min(R, L - k0));
+  const int CB = (3 * L + FK_G - 1) / FK_G;       // Bh entries per CTA
+  const int cb0 = cta * CB, ncb = max(0, min(CB, 3 * L - cb0));
+  if (nr == 0 && ncb == 0) return;
+  __syncthreads();
+  // stage dvec [32 x 3L] and the (Hold, Hold*r) columns of this slab
+  stage_rows4(sm.gA, 388, FK_B, ld3 / 4, [&](int rr) -> const float* { return rr < M ? ly.dvec + (size_t)rr * ld3 : nullptr; });
+  float* sHo = sm.gW;                  // [R][32]
+  float* sHr = sm.gW + 8 * FK_B;       // [R][32]
+  for (int i = tid; i < nr * FK_B; i += FK_THREADS) {
+    const int rr = i / FK_B, b = i % FK_B;
+    float ho = 0.f, r = 0.f;
+    if (b < M) { ho = ly.Hold[(size_t)b * ldL + k0 + rr]; r = ly.r[(size_t)b * ldL + k0 + rr]; }
+    sHo[i] = ho; sHr[i] = ho * r;
+  }
+  __syncthreads();
+  // outputs: nr x L (Wh), nr x 2L (Wrz), ncb (Bh).  Each thread owns U outputs at a time: their parameter / Adagrad /
+  // momentum values are loaded first, the U batch reductions (<= 32 lanes) run interleaved, then the updates are stored.
+  const int nWh = nr * L, nWrz = nr * 2 * L, total = nWh + nWrz + ncb;
+  constexpr int U = 2;
+  const bool ada = md.adapt == G4R_ADAPT_ADAGRAD, mom = md.mom > 0.f;
+  for (int o0 = 0; o0 < total; o0 += U * FK_THREADS) {
+    float* p[U]; float* pa[U]; float* pv[U]; const float* av[U]; const float* bv[U]; bool ok[U]; bool bias[U];
+    float p0[U], a0[U], v0[U], g[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int o = o0 + u * FK_THREADS + tid;
+      ok[u] = o < total; bias[u] = false; p[u] = nullptr; pa[u] = nullptr; pv[u] = nullptr; av[u] = sHo; bv[u] = sm.gA;
+      if (ok[u]) {
+        if (o < nWh) {
+          const int rr = o / L, c = o % L;
+          const size_t off = (size_t)(k0 + rr) * ldL + c;
+          p[u] = ly.Wh + off; pa[u] = ly.Wh_acc ? ly.Wh_acc + off : nullptr; pv[u] = ly.Wh_vel ? ly.Wh_vel + off : nullptr;
+          av[u] = sHr + rr * FK_B; bv[u] = sm.gA + c;
+        } else if (o < nWh + nWrz) {
+          const int q = o - nWh, rr = q / (2 * L), c = q % (2 * L);
+          const size_t off = (size_t)(k0 + rr) * ly.ld2 + c;
+          p[u] = ly.Wrz + off; pa[u] = ly.Wrz_acc ? ly.Wrz_acc + off : nullptr; pv[u] = ly.Wrz_vel ? ly.Wrz_vel + off : nullptr;
+          av[u] = sHo + rr * FK_B; bv[u] = sm.gA + L + c;
+        } else {
+          const int c = cb0 + (o - nWh - nWrz);
+          p[u] = ly.Bh + c; pa[u] = ly.Bh_acc ? ly.Bh_acc + c : nullptr; pv[u] = ly.Bh_vel ? ly.Bh_vel + c : nullptr;
+          bias[u] = true; bv[u] = sm.gA + c;
+        }
+      }
+      p0[u] = ok[u] ? *p[u] : 0.f;
+      a0[u] = (ok[u] && ada && pa[u]) ? *pa[u] : 0.f;
+      v0[u] = (ok[u] && mom && pv[u]) ? *pv[u] : 0.f;
+      g[u] = 0.f;
+    }
+    for (int b = 0; b < M; b++) {
+#pragma unroll
+      for (int u = 0; u < U; u++) g[u] = bias[u] ? g[u] + bv[u][b * 388] : fmaf(av[u][b], bv[u][b * 388], g[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (!ok[u]) continue;
+      float gs = g[u];
+      if (ada) { const float a = a0[u] + g[u] * g[u]; *pa[u] = a; gs = __fdiv_rn(g[u], sqrtf(a + G4R_EPS_ADA)); }
+      if (mom) { const float v2 = md.mom * v0[u] - md.lr * (gs + md.lmbd * p0[u]); *pv[u] = v2; *p[u] = p0[u] + v2; }
+      else *p[u] = p0[u] * (1.0f - md.lr * md.lmbd) - md.lr * gs;
+    }
+  }
+}
+
+// B1 (fast kernel): every CTA reduces a contiguous run of dL/dh elements; lanes = consecutive elements (coalesced),
+// warps = slices of the chunk partials, cross-warp sum in shared memory in fixed order; then da_h / da_z.
+__device__ void fk_b1(const ModelDev& md, FastSmem& sm, int s, int cta, int ncta) {
+  const LayerDev& ly = md.layer[0];
+  const int M = md.wM[s], L = ly.L, ldL = ly.ldL;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int E = M * ldL;                                  // padded elements (padding columns are zero everywhere)
+  const int per = ((E + ncta - 1) / ncta + 31) / 32 * 32; // elements per CTA, multiple of 32
+  const int e0 = cta * per;
+  float* red = sm.sPart;                                  // [FK_NW][per]  (per <= 128 for M*ldL <= 4096*... checked on host)
+  const size_t cs = (size_t)md.B * ldL;
+  for (int eb = 0; eb < per; eb += 32) {
+    const int e = e0 + eb + lane;
+    float d = 0.f;
+    if (e < E) {
+      float v[10];
+#pragma unroll
+      for (int u = 0; u < 10; u++) { const int ch = warp + FK_NW * u; v[u] = ch < md.NCH ? md.part[(size_t)ch * cs + e] : 0.f; }
+      d = (((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]))) + (v[8] + v[9]);
+    }
+    red[warp * per + eb + lane] = d;
+  }
+  __syncthreads();
+  for (int i = tid; i < per; i += FK_THREADS) {
+    const int e = e0 + i;
+    if (e >= E) continue;
+    const int b = e / ldL, c = e % ldL;
+    if (c >= L) continue;
+    float dy = 0.f;
+#pragma unroll
+    for (int w = 0; w < FK_NW; w++) dy += red[w * per + i];
+    const size_t o = (size_t)b * ldL + c;
+    const float ht = ly.ht[o], ho = ly.Hold[o], z = ly.z[o], ah = ly.ah[o];
+    float dh = dy;
+    if (md.p_drop_h > 0.f) dh *= drop_scale(md.drop_seed, md.wG[s], 0u, (uint32_t)(b * L + c), 1.0f - md.p_drop_h);
+    const float dz = dh * (ht - ho);
+    const float dah = dh * z * act_der(md.hact, ah, ht);
+    ly.dvec[(size_t)b * ly.ld3 + c] = dah;
+    ly.dvec[(size_t)b * ly.ld3 + 2 * L + c] = dz * z * (1.f - z);
+  }
+}
+
+__global__ void __launch_bounds__(FK_THREADS, 1) k_fast(int slot, int n_steps, FastSync* fs, unsigned long long* tstamp) {
+  extern __shared__ __align__(128) unsigned char fk_raw[];
+  FastSmem& sm = *reinterpret_cast<FastSmem*>(fk_raw);
+  const ModelDev& md = MD;
+  const LayerDev& ly = md.layer[0];
+  const int cta = blockIdx.x, ncta = gridDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int chunk = cta;                       // CTAs beyond the number of chunks own no columns
+  const bool has_chunk = chunk < md.NCH;
+  const bool gru = cta < FK_G;
+  const bool pw = loss_pairwise(md.loss);
+  const bool ada = md.adapt == G4R_ADAPT_ADAGRAD, mom = md.mom > 0.f;
+  const int L = md.L, ldL = md.ldL, B = md.B;
+  const int kw = ldL / 4;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(&sm.mbar);
+  unsigned int bar_epoch = 0, gepoch = 0, stats_target = 0;
+#define FK_STAMP(k) do { if (tstamp && cta == 0 && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tstamp[(size_t)s * 16 + (k)] = t_; } } while (0)
+  if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  fk_load_idx(md, sm, 0, n_steps, chunk, 0);
+  __syncthreads();
+  fk_prefetch_rows(md, sm, 0, n_steps, 0, pw);
+  // GRU forward of step 0
+  if (gru) {
+    fk_f1(md, sm, 0, cta);
+    fk_group_barrier(fs, gepoch);
+    fk_f2(md, sm, 0, cta);
+    __syncthreads();
+    if (tid == 0) red_release_add(&fs->h_ready, 1u);
+  }
+  for (int s = 0; s < n_steps; s++) {
+    const int buf = s & 1;
+    const int M = md.wM[s];
+    const int sti = md.wSti[s];
+    const int N = M + (sti >= 0 ? md.S : 0);
+    FK_STAMP(0);
+    // indices of the NEXT step (consumed after this step's last barrier)
+    fk_load_idx(md, sm, s + 1, n_steps, chunk, buf ^ 1);
+    // ---- wait for h(s), stage it ----
+    if (tid == 0) wait_ge(&fs->h_ready, (unsigned int)(s + 1) * FK_G);
+    __syncthreads();
+    stage_rows4(sm.sY, FK_LDS, FK_B, kw, [&](int rr) -> const float* { return rr < M ? ly.y + (size_t)rr * ldL : nullptr; });
+    mbar_wait(bar, (unsigned int)(s & 1));      // prefetched rows of this step have landed
+    __syncthreads();
+    FK_STAMP(1);
+    const int cb = sm.sCb[buf][0], ce = sm.sCb[buf][1];
+    const int nj = ce - cb;
+    // ---- scores + partial statistics ----
+    if (pw) {                                   // target activations: warp per 4 lanes
+      for (int b = warp; b < FK_B; b += FK_NW) {
+        if (b < M) {
+          float a = 0.f;
+          if (lane < kw) {
+            const float4 y = ld4(sm.sY + b * FK_LDS + lane * 4), w = ld4(sm.sTW + b * FK_LDS + lane * 4);
+            a = fmaf(w.x, y.x, a); a = fmaf(w.y, y.y, a); a = fmaf(w.z, y.z, a); a = fmaf(w.w, y.w, a);
+          }
+          a = warp_sum(a);
+          if (lane == 0) sm.sT[b] = act_fwd(md.fact, a + sm.sTB[b]);
+        }
+      }
+    }
+    {
+      float accq[FK_Q];
+#pragma unroll
+      for (int q = 0; q < FK_Q; q++) accq[q] = 0.f;
+      const float* yr = sm.sY + lane * FK_LDS;
+      for (int c4 = 0; c4 < kw; c4++) {
+        const float4 y = ld4(yr + c4 * 4);
+#pragma unroll
+        for (int q = 0; q < FK_Q; q++) {
+          if (warp + FK_NW * q < nj) {
+            const float4 w = ld4(sm.sS + (warp + FK_NW * q) * FK_LDS + c4 * 4);
+            accq[q] = fmaf(y.x, w.x, accq[q]); accq[q] = fmaf(y.y, w.y, accq[q]); accq[q] = fmaf(y.z, w.z, accq[q]); accq[q] = fmaf(y.w, w.w, accq[q]);
+          }
+        }
+      }
+      FK_STAMP(9);
+      __syncthreads();                          // sT complete
+      const int b = lane;
+      float m = -INFINITY, Z = 0.f, A = 0.f, Q = 0.f, D = 0.f, T = 0.f, has = 0.f;
+      if (b < M) {
+        const int tc = sm.sTc[buf][b];
+        const float t = pw ? sm.sT[b] : 0.f;
+#pragma unroll
+        for (int q = 0; q < FK_Q; q++) {
+          const int jj = warp + q * FK_NW;
+          if (jj < nj) {
+            const float o = accq[q] + sm.sBias[jj];
+            sm.sO[jj * FK_B + b] = o;
+            stat_add_elem(md, o, tc == cb + jj, t, m, Z, A, Q, D, T, has);
+          }
+        }
+      }
+      float* pp = sm.sPart + ((size_t)warp * FK_B + lane) * 8;
+      pp[0] = m; pp[1] = Z; pp[2] = A; pp[3] = Q; pp[4] = D; pp[5] = T; pp[6] = has;
+      __syncthreads();
+      if (has_chunk && tid < FK_B && tid < M) {
+        float rm = -INFINITY, rZ = 0.f, rA = 0.f, rQ = 0.f, rD = 0.f, rT = 0.f, rh = 0.f;
+#pragma unroll
+        for (int w = 0; w < FK_NW; w++) {
+          const float* q = sm.sPart + ((size_t)w * FK_B + tid) * 8;
+          stat_combine(md, rm, rZ, rA, rQ, rD, rT, rh, q[0], q[1], q[2], q[3], q[4], q[5], q[6]);
+        }
+        float* st = md.stat + ((size_t)chunk * md.B + tid) * G4R_NSTAT;
+        st4(st, make_float4(rm, rZ, rA, rQ));
+        st4(st + 4, make_float4(rD, rT, rh, pw ? sm.sT[tid] : 0.f));
+      }
+    }
+    // ---- barrier B2, then lane b's statistics are combined by CTA b (all lanes in parallel, fixed merge order) ----
+    __syncthreads();
+    FK_STAMP(10);
+    bar_epoch += 1;
+    if (tid == 0) { red_release_add(&fs->bar, 1u); wait_ge(&fs->bar, bar_epoch * (unsigned int)ncta); }
+    __syncthreads();
+    if (cta < M) {
+      const int b = cta;
+      float m = -INFINITY, Z = 0.f, A = 0.f, Q = 0.f, D = 0.f, T = 0.f, has = 0.f, tt = 0.f;
+      if (tid < md.NCH) {
+        const float* st = md.stat + ((size_t)tid * md.B + b) * G4R_NSTAT;
+        const float4 u = ld4(st), v = ld4(st + 4);
+        m = u.x; Z = u.y; A = u.z; Q = u.w; D = v.x; T = v.y; has = v.z;
+        if (tid == 0) tt = v.w;
+      }
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, o), Z2 = __shfl_xor_sync(0xffffffffu, Z, o), A2 = __shfl_xor_sync(0xffffffffu, A, o),
+                    Q2 = __shfl_xor_sync(0xffffffffu, Q, o), D2 = __shfl_xor_sync(0xffffffffu, D, o), T2 = __shfl_xor_sync(0xffffffffu, T, o),
+                    h2 = __shfl_xor_sync(0xffffffffu, has, o);
+        stat_combine(md, m, Z, A, Q, D, T, has, m2, Z2, A2, Q2, D2, T2, h2);
+      }
+      if (lane == 0) { float* w = sm.sPart + warp * 8; w[0] = m; w[1] = Z; w[2] = A; w[3] = Q; w[4] = D; w[5] = T; w[6] = has; w[7] = tt; }
+      __syncthreads();
+      if (tid == 0) {
+        tt = sm.sPart[7];
+        for (int w = 1; w < FK_THREADS / 32; w++) { const float* q = sm.sPart + w * 8; stat_combine(md, m, Z, A, Q, D, T, has, q[0], q[1], q[2], q[3], q[4], q[5], q[6]); }
+        if (loss_softmaxneg(md.loss)) stat_merge(m, Z, A, Q, D, 0.f, 0.f, 0.f, 0.f, 0.f);
+        float* rs = md.RS + (size_t)b * G4R_NSTAT;
+        float loss = 0.f, r0 = m, r1 = Z, r2 = 0.f, r3 = 0.f, r4 = 0.f, r5 = tt;
+        if (md.loss == G4R_LOSS_XE) { const float pt = __fdiv_rn(expf(T - m), Z); loss = -logf(pt + G4R_EPS_LOG); r2 = pt; r5 = T; }
+        else if (md.loss == G4R_LOSS_XE_LOGIT) { loss = logf(Z) - (T - m); r5 = T; }
+        else if (md.loss == G4R_LOSS_BPR_MAX) { r2 = __fdiv_rn(A, Z); r3 = __fdiv_rn(Q, Z); r4 = __fdiv_rn(D, Z); loss = -logf(r2 + G4R_EPS_LOG) + md.bpreg * r3; }
+        else if (md.loss == G4R_LOSS_TOP1_MAX) { r2 = __fdiv_rn(A, Z); r4 = __fdiv_rn(D, Z); loss = r2; }
+        else if (md.loss == G4R_LOSS_BPR) { loss = A; r4 = D; }
+        else { const float c = sigmoidf_(tt * tt); loss = __fdiv_rn(A, (float)N) - __fdiv_rn(c, (float)(M + md.S_cfg)); r4 = D; }
+        st4(rs, make_float4(r0, r1, r2, r3));
+        st4(rs + 4, make_float4(r4, r5, loss, 0.f));
+        red_release_add(&fs->stats, 1u);
+      }
+    }
+    stats_target += (unsigned int)M;
+    if (tid == 0) wait_ge(&fs->stats, stats_target);
+    __syncthreads();
+    FK_STAMP(2);
+    // ---- loss gradient, dSy, partial dL/dh, sparse update of this chunk's rows ----
+    if (tid < M * 2) st4(sm.sRS + tid * 4, ld4(md.RS + tid * 4));
+    __syncthreads();
+    if (chunk == 0 && tid == 0) {
+      float c = 0.f;
+      for (int b = 0; b < M; b++) c += sm.sRS[b * 8 + 6];
+      c = __fdiv_rn(c, (float)md.B);
+      md.cost[s] = c;
+      if (c != c) atomicExch(md.nanflag, 1);
+    }
+    FK_STAMP(11);
+    for (int i = tid; i < FK_CT * FK_B; i += FK_THREADS) {
+      const int jj = i / FK_B, b = i % FK_B;
+      sm.sG[i] = (jj < nj && b < M) ? loss_grad_elem(md, sm.sRS + (size_t)b * 8, sm.sO[i], sm.sTc[buf][b] == cb + jj, M, N) : 0.f;
+    }
+    __syncthreads();
+    for (int jj = warp; jj < nj; jj += FK_THREADS / 32) {
+      float a = (lane < M) ? sm.sG[jj * FK_B + lane] : 0.f;
+      a = warp_sum(a);
+      if (lane == 0) sm.sDby[jj] = a;
+    }
+    FK_STAMP(12);
+    float* part = md.part + (size_t)(has_chunk ? chunk : 0) * md.B * ldL;
+    if (has_chunk && lane < kw) {
+      float4 dq[FK_Q];
+#pragma unroll
+      for (int q = 0; q < FK_Q; q++) dq[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int bb = 0; bb < M; bb++) {
+        const float4 y = ld4(sm.sY + bb * FK_LDS + lane * 4);
+#pragma unroll
+        for (int q = 0; q < FK_Q; q++) {
+          const float g = sm.sG[(warp + FK_NW * q) * FK_B + bb];
+          dq[q].x = fmaf(g, y.x, dq[q].x); dq[q].y = fmaf(g, y.y, dq[q].y); dq[q].z = fmaf(g, y.z, dq[q].z); dq[q].w = fmaf(g, y.w, dq[q].w);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < FK_Q; q++) if (warp + FK_NW * q < nj) st4(sm.sD + (warp + FK_NW * q) * FK_LDS + lane * 4, dq[q]);
+      for (int bb = warp; bb < M; bb += FK_THREADS / 32) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int jj = 0; jj < nj; jj++) {
+          const float g = sm.sG[jj * FK_B + bb];
+          const float4 w = ld4(sm.sS + jj * FK_LDS + lane * 4);
+          a.x = fmaf(g, w.x, a.x); a.y = fmaf(g, w.y, a.y); a.z = fmaf(g, w.z, a.z); a.w = fmaf(g, w.w, a.w);
+        }
+        st4(part + (size_t)bb * ldL + lane * 4, a);
+      }
+    }
+    __syncthreads();
+    FK_STAMP(13);
+    // sparse update from shared memory (rows prefetched before the step): one warp per duplicate group
+    for (int j = warp; j < nj; j += FK_THREADS / 32) {
+      const int item = sm.sIt[buf][j];
+      if (j > 0 && sm.sIt[buf][j - 1] == item) continue;
+      int je = j + 1;
+      while (je < nj && sm.sIt[buf][je] == item) je++;
+      if (lane < kw) {
+        const float4 p0 = ld4(sm.sS + j * FK_LDS + lane * 4);
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), v0 = a0, al = a0, vl = a0;
+        if (ada) a0 = ld4(sm.sAcc + j * FK_LDS + lane * 4);
+        if (mom) v0 = ld4(sm.sVel + j * FK_LDS + lane * 4);
+        float4 ps = p0;
+        for (int k = j; k < je; k++) {
+          const float4 g = ld4(sm.sD + k * FK_LDS + lane * 4);
+          float4 gs = g;
+          if (ada) {
+            al.x = a0.x + g.x * g.x; al.y = a0.y + g.y * g.y; al.z = a0.z + g.z * g.z; al.w = a0.w + g.w * g.w;
+            gs.x = __fdiv_rn(g.x, sqrtf(al.x + G4R_EPS_ADA)); gs.y = __fdiv_rn(g.y, sqrtf(al.y + G4R_EPS_ADA));
+            gs.z = __fdiv_rn(g.z, sqrtf(al.z + G4R_EPS_ADA)); gs.w = __fdiv_rn(g.w, sqrtf(al.w + G4R_EPS_ADA));
+          }
+          float4 d;
+          if (md.lmbd > 0.f) { d.x = md.lr * (gs.x + md.lmbd * p0.x); d.y = md.lr * (gs.y + md.lmbd * p0.y); d.z = md.lr * (gs.z + md.lmbd * p0.z); d.w = md.lr * (gs.w + md.lmbd * p0.w); }
+          else { d.x = md.lr * gs.x; d.y = md.lr * gs.y; d.z = md.lr * gs.z; d.w = md.lr * gs.w; }
+          if (mom) {
+            vl.x = md.mom * v0.x - d.x; vl.y = md.mom * v0.y - d.y; vl.z = md.mom * v0.z - d.z; vl.w = md.mom * v0.w - d.w;
+            ps.x += vl.x; ps.y += vl.y; ps.z += vl.z; ps.w += vl.w;
+          } else { ps.x -= d.x; ps.y -= d.y; ps.z -= d.z; ps.w -= d.w; }
+        }
+        const size_t off = (size_t)item * ldL + lane * 4;
+        st4(md.Wy + off, ps);
+        if (ada) st4(md.Wy_acc + off, al);
+        if (mom) st4(md.Wy_vel + off, vl);
+      }
+      if (lane == 0) {
+        const float p0 = sm.sByP[j];
+        float a0 = sm.sByA[j], v0 = sm.sByV[j], al = 0.f, vl = 0.f, ps = p0;
+        for (int k = j; k < je; k++) {
+          const float g = sm.sDby[k];
+          float gs = g;
+          if (ada) { al = a0 + g * g; gs = __fdiv_rn(g, sqrtf(al + G4R_EPS_ADA)); }
+          const float d = md.lmbd > 0.f ? md.lr * (gs + md.lmbd * p0) : md.lr * gs;
+          if (mom) { vl = md.mom * v0 - d; ps += vl; } else ps -= d;
+        }
+        md.By[item] = ps;
+        if (ada) md.By_acc[item] = al;
+        if (mom) md.By_vel[item] = vl;
+      }
+    }
+    if (has_chunk && nj == 0) for (int i = tid; i < M * ldL; i += FK_THREADS) part[i] = 0.f;
+    // ---- barrier B3: all updates and partial dL/dh complete ----
+    __syncthreads();
+    FK_STAMP(14);
+    bar_epoch += 1;
+    if (tid == 0) { red_release_add(&fs->bar, 1u); wait_ge(&fs->bar, bar_epoch * (unsigned int)ncta); }
+    __syncthreads();
+    FK_STAMP(3);
+    // ---- b1 on every CTA, then prefetch the next step's rows ----
+    fk_b1(md, sm, s, cta, ncta);
+    __syncthreads();
+    if (tid == 0) red_release_add(&fs->b1_done, 1u);
+    FK_STAMP(15);
+    fk_prefetch_rows(md, sm, s + 1, n_steps, buf ^ 1, pw);
+    FK_STAMP(4);
+    // ---- GRU group: backward, dense update, forward of the next step ----
+    if (gru) {
+      if (tid == 0) wait_ge(&fs->b1_done, (unsigned int)(s + 1) * (unsigned int)ncta);
+      __syncthreads();
+      fk_b2(md, sm, s, cta);
+      fk_group_barrier(fs, gepoch);
+      FK_STAMP(5);
+      fk_dense(md, sm, s, cta);
+      for (int b = FK_G - 1 - cta; b < B; b += FK_G) phase_sparse_in(md, s, b);
+      fk_group_barrier(fs, gepoch);
+      FK_STAMP(6);
+      if (s + 1 < n_steps) {
+        fk_f1(md, sm, s + 1, cta);
+        fk_group_barrier(fs, gepoch);
+        FK_STAMP(7);
+        fk_f2(md, sm, s + 1, cta);
+        __syncthreads();
+        if (tid == 0) red_release_add(&fs->h_ready, 1u);
+      }
+      FK_STAMP(8);
+    }
+  }
+#undef FK_STAMP
+}

@@ -23,6 +23,14 @@
 #define G4R_NSTAT 8
 
 struct ActSpec { int kind; float p1, p2; };
+// synchronisation counters of the role-specialised kernel (g4r_fast.cuh), one per 128-byte line
+struct FastSync {                   // one counter per 128-byte line
+  unsigned int bar;      unsigned int p0[31];
+  unsigned int stats;    unsigned int p1[31];
+  unsigned int h_ready;  unsigned int p2[31];
+  unsigned int b1_done;  unsigned int p3[31];
+  unsigned int grp;      unsigned int p4[31];
+};
 struct GridBar { unsigned int count; unsigned int gen; unsigned int pad[30]; };   // grid barrier state (persistent mode)
 
 struct LayerDev {
@@ -130,63 +138,72 @@ __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<floa
 // generic CTA-tile GEMM accumulate: acc[TM][TN] += sum_k A(m,k) * B(k,n) for the thread's micro tile of a
 // BM x BN CTA tile.  A(m,k), B(k,n) are fetched through functors (bounds handled by the functor).
 // ------------------------------------------------------------------------------------------------
-template <int BM, int BN, int BK, int TM, int TN, bool A_KFAST, bool B_NFAST, class FA, class FB>
-__device__ __forceinline__ void gemm_tile_acc(float (&acc)[TM][TN], int K, FA fa, FB fb, float* sA, float* sB) {
-  constexpr int NT = (BM / TM) * (BN / TN);
-  constexpr int NA = BM * BK / NT, NB = BK * BN / NT;
-  static_assert(BM * BK % NT == 0 && BK * BN % NT == 0, "tile must divide evenly over the threads");
+// ------------------------------------------------------------------------------------------------
+// CTA-tile GEMM pieces.  A tile operand is always "32 x 128": 32 = the tile's M (or N) extent, 128 = a K slab,
+// stored in shared memory as [128][33].  ONE non-inlined loader serves every operand of every phase (the
+// persistent kernels execute each phase once per mini-batch, so code size == instruction-cache misses).
+//   element(i32, i128) = base[row(i32) * s32 + (o128 + i128) * s128] * (mul ? mul[same index] : 1)
+//   row(i32) = rowidx ? rowidx[i32] (negative -> 0.0) : o32 + i32 ;   masked outside lim32 / lim128
+// All 16 global loads of a thread are issued into registers before the first shared-memory store.
+// ------------------------------------------------------------------------------------------------
+constexpr int GB = 32;    // tile edge
+constexpr int GK = 128;   // K slab
+constexpr int GT = 2;     // micro tile
+constexpr int GEMM_THREADS = (GB / GT) * (GB / GT);   // 256
+struct TileSrc {
+  const float* base; const float* mul; const int* rowidx;
+  long long s32, s128; int o32, o128, lim32, lim128; int fast128;
+};
+__device__ __forceinline__ void tile_load(float* sdst, const TileSrc t) {
+  constexpr int NE = GB * GK / GEMM_THREADS;   // 16
   const int tid = threadIdx.x;
-  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
-  for (int k0 = 0; k0 < K; k0 += BK) {
-    // all global loads of the slab are issued into registers BEFORE the first shared-memory store: a store after
-    // each load would serialise one memory round trip per element (~0.5 us each on B200)
-    float ra[NA], rb[NB];
+  float r[NE];
 #pragma unroll
-    for (int j = 0; j < NA; j++) {
-      const int i = tid + j * NT;
-      int m, k;
-      if (A_KFAST) { k = i % BK; m = i / BK; } else { m = i % BM; k = i / BM; }
-      ra[j] = (k0 + k < K) ? fa(m, k0 + k) : 0.f;
+  for (int j = 0; j < NE; j++) {
+    const int i = tid + j * GEMM_THREADS;
+    const int i32 = t.fast128 ? i / GK : i % GB;
+    const int i128 = t.fast128 ? i % GK : i / GB;
+    long long row = t.rowidx ? (long long)t.rowidx[i32] : (long long)(t.o32 + i32);
+    const bool ok = row >= 0 && (t.rowidx ? true : (t.o32 + i32 < t.lim32)) && (t.o128 + i128 < t.lim128);
+    float v = 0.f;
+    if (ok) {
+      const long long off = row * t.s32 + (long long)(t.o128 + i128) * t.s128;
+      v = t.base[off];
+      if (t.mul) v *= t.mul[off];
     }
-#pragma unroll
-    for (int j = 0; j < NB; j++) {
-      const int i = tid + j * NT;
-      int n, k;
-      if (B_NFAST) { n = i % BN; k = i / BN; } else { k = i % BK; n = i / BK; }
-      rb[j] = (k0 + k < K) ? fb(k0 + k, n) : 0.f;
-    }
-    if (k0 > 0) __syncthreads();
-#pragma unroll
-    for (int j = 0; j < NA; j++) {
-      const int i = tid + j * NT;
-      int m, k;
-      if (A_KFAST) { k = i % BK; m = i / BK; } else { m = i % BM; k = i / BM; }
-      sA[k * (BM + 1) + m] = ra[j];
-    }
-#pragma unroll
-    for (int j = 0; j < NB; j++) {
-      const int i = tid + j * NT;
-      int n, k;
-      if (B_NFAST) { n = i % BN; k = i / BN; } else { k = i % BK; n = i / BK; }
-      sB[k * (BN + 1) + n] = rb[j];
-    }
-    __syncthreads();
-    const int kmax = min(BK, K - k0);
-#pragma unroll 4
-    for (int k = 0; k < kmax; k++) {
-      float a[TM], b[TN];
-#pragma unroll
-      for (int i = 0; i < TM; i++) a[i] = sA[k * (BM + 1) + ty * TM + i];
-#pragma unroll
-      for (int j = 0; j < TN; j++) b[j] = sB[k * (BN + 1) + tx * TN + j];
-#pragma unroll
-      for (int i = 0; i < TM; i++)
-#pragma unroll
-        for (int j = 0; j < TN; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
+    r[j] = v;
   }
-  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < NE; j++) {
+    const int i = tid + j * GEMM_THREADS;
+    const int i32 = t.fast128 ? i / GK : i % GB;
+    const int i128 = t.fast128 ? i % GK : i / GB;
+    sdst[i128 * (GB + 1) + i32] = r[j];
+  }
 }
+// acc[2][2] += A-tile x B-tile over kmax slab entries (A: 32 = m, B: 32 = n)
+__device__ __forceinline__ void tile_mma(float (&acc)[GT][GT], const float* sA, const float* sB, int kmax) {
+  const int tx = threadIdx.x % (GB / GT), ty = threadIdx.x / (GB / GT);
+#pragma unroll 2
+  for (int k = 0; k < kmax; k++) {
+    const float a0 = sA[k * (GB + 1) + ty * GT], a1 = sA[k * (GB + 1) + ty * GT + 1];
+    const float b0 = sB[k * (GB + 1) + tx * GT], b1 = sB[k * (GB + 1) + tx * GT + 1];
+    acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
+    acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+  }
+}
+// full K loop: acc += A x B with both operands described by TileSrc (o128 is advanced per slab)
+__device__ __forceinline__ void tile_gemm(float (&acc)[GT][GT], TileSrc a, TileSrc b, int K, float* sA, float* sB) {
+  for (int k0 = 0; k0 < K; k0 += GK) {
+    a.o128 = k0; b.o128 = k0;
+    __syncthreads();
+    tile_load(sA, a);
+    tile_load(sB, b);
+    __syncthreads();
+    tile_mma(acc, sA, sB, min(GK, K - k0));
+  }
+}
+
 // stage `nrows` rows of `kw` float4 into shared memory, four 16-byte loads in flight per thread before any store
 template <class FRow>
 __device__ __forceinline__ void stage_rows4(float* sdst, int sld, int nrows, int kw, FRow rowptr) {
@@ -206,11 +223,6 @@ __device__ __forceinline__ void stage_rows4(float* sdst, int sld, int nrows, int
     }
   }
 }
-constexpr int GB = 32;   // CTA tile edge of the small-GEMM phases
-constexpr int GK = 128;  // K slab: the GRU widths of the shipped configurations (100, 224 -> 2 slabs, 512 -> 4) load in few batches
-constexpr int GT = 2;    // micro tile
-constexpr int GEMM_THREADS = (GB / GT) * (GB / GT);   // 256
-
 // dense Adagrad(+momentum) on one element (gru4rec.py:330-340,390-406)
 __device__ __forceinline__ void dense_update(const ModelDev& md, float* p, float* acc, float* vel, float g) {
   float gs = g;
@@ -307,15 +319,10 @@ __device__ void phase_f1(const ModelDev& md, int li, int s, float* Hsrc, int til
       pre[i][j] = v;
     }
   float acc[GT][GT] = {};
-  auto fa_h = [&](int m, int k) -> float { const int sl = sSlot[m]; return sl >= 0 ? Hs[(size_t)sl * ly.ldL + k] : 0.f; };
-  auto fb_rz = [&](int k, int n) -> float { const int c = n0 + n; return c < 2 * L ? Wrz[(size_t)k * ly.ld2 + c] : 0.f; };
-  gemm_tile_acc<GB, GB, GK, GT, GT, true, true>(acc, L, fa_h, fb_rz, sA, sB);
-  if (!gathered) {
-    const float* __restrict__ In = ly.in;
-    auto fa_in = [&](int m, int k) -> float { const int b = m0 + m; return b < M ? In[(size_t)b * ly.ld_in + k] : 0.f; };
-    auto fb_wx = [&](int k, int n) -> float { const int c = n0 + n; return c < 2 * L ? Wx[(size_t)k * ly.ld3 + L + c] : 0.f; };
-    gemm_tile_acc<GB, GB, GK, GT, GT, true, true>(acc, ly.in_dim, fa_in, fb_wx, sA, sB);
-  }
+  tile_gemm(acc, TileSrc{Hs, nullptr, sSlot, ly.ldL, 1, 0, 0, GB, L, 1}, TileSrc{Wrz, nullptr, nullptr, 1, ly.ld2, n0, 0, 2 * L, L, 0}, L, sA, sB);
+  if (!gathered)
+    tile_gemm(acc, TileSrc{ly.in, nullptr, nullptr, ly.ld_in, 1, m0, 0, M, ly.in_dim, 1},
+              TileSrc{Wx + L, nullptr, nullptr, 1, ly.ld3, n0, 0, 2 * L, ly.in_dim, 0}, ly.in_dim, sA, sB);
 #pragma unroll
   for (int i = 0; i < GT; i++) {
     const int b = m0 + ty * GT + i;
@@ -395,18 +402,10 @@ __device__ void phase_f2(const ModelDev& md, int li, int s, float* Hsrc, bool tr
       pre[i][j] = v; pz[i][j] = z; ph[i][j] = ho;
     }
   float acc[GT][GT] = {};
-  auto fa_hr = [&](int m, int k) -> float {
-    const int b = m0 + m;
-    return b < M ? Hold[(size_t)b * ly.ldL + k] * Rr[(size_t)b * ly.ldL + k] : 0.f;
-  };
-  auto fb_wh = [&](int k, int n) -> float { const int c = n0 + n; return c < L ? Wh[(size_t)k * ly.ldL + c] : 0.f; };
-  gemm_tile_acc<GB, GB, GK, GT, GT, true, true>(acc, L, fa_hr, fb_wh, sA, sB);
-  if (!gathered) {
-    const float* __restrict__ In = ly.in;
-    auto fa_in = [&](int m, int k) -> float { const int b = m0 + m; return b < M ? In[(size_t)b * ly.ld_in + k] : 0.f; };
-    auto fb_wx = [&](int k, int n) -> float { const int c = n0 + n; return c < L ? Wx[(size_t)k * ly.ld3 + c] : 0.f; };
-    gemm_tile_acc<GB, GB, GK, GT, GT, true, true>(acc, ly.in_dim, fa_in, fb_wx, sA, sB);
-  }
+  tile_gemm(acc, TileSrc{Hold, Rr, nullptr, ly.ldL, 1, m0, 0, M, L, 1}, TileSrc{Wh, nullptr, nullptr, 1, ly.ldL, n0, 0, L, L, 0}, L, sA, sB);
+  if (!gathered)
+    tile_gemm(acc, TileSrc{ly.in, nullptr, nullptr, ly.ld_in, 1, m0, 0, M, ly.in_dim, 1},
+              TileSrc{Wx, nullptr, nullptr, 1, ly.ld3, n0, 0, L, ly.in_dim, 0}, ly.in_dim, sA, sB);
   const uint32_t gstep = md.wG[s];
   const float retain = 1.0f - md.p_drop_h;
 #pragma unroll
@@ -936,13 +935,15 @@ __device__ void phase_b1(const ModelDev& md, int li, int s, int cta, int ncta) {
     float ht = 0.f, ho = 0.f, z = 0.f, ah = 0.f, dy = 0.f;
     if (ok && sub == 0) { ht = Ht[o]; ho = Ho[o]; z = Zz[o]; ah = Ah[o]; if (!last) dy = Dy[o]; }
     if (last) {
-      float d0 = 0.f, d1 = 0.f;
+      float d = 0.f;
       if (ok) {
-        int ch = sub;
-        for (; ch + 8 < md.NCH; ch += 16) { d0 += part[(size_t)ch * cs + o]; d1 += part[(size_t)(ch + 8) * cs + o]; }
-        if (ch < md.NCH) d0 += part[(size_t)ch * cs + o];
+        for (int c0 = 0; c0 < md.NCH; c0 += 64) {      // 8 independent loads in flight per lane, fixed summation order
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) { const int ch = c0 + sub + 8 * u; v[u] = ch < md.NCH ? part[(size_t)ch * cs + o] : 0.f; }
+          d += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+        }
       }
-      float d = d0 + d1;
       d += __shfl_xor_sync(0xffffffffu, d, 4); d += __shfl_xor_sync(0xffffffffu, d, 2); d += __shfl_xor_sync(0xffffffffu, d, 1);
       dy = d;
     }
@@ -970,9 +971,7 @@ __device__ void phase_b2(const ModelDev& md, int li, int s, int tile, float* sA,
   const int m0 = tm * GB, n0 = tn * GB;
   if (m0 >= M) return;
   float acc[GT][GT] = {};
-  auto fa = [&](int m, int k) -> float { int b = m0 + m; return b < M ? ly.dvec[(size_t)b * ly.ld3 + k] : 0.f; };
-  auto fb = [&](int k, int n) -> float { int c = n0 + n; return c < L ? ly.Wh[(size_t)c * ly.ldL + k] : 0.f; };   // Wh^T
-  gemm_tile_acc<GB, GB, GK, GT, GT, true, false>(acc, L, fa, fb, sA, sB);
+  tile_gemm(acc, TileSrc{ly.dvec, nullptr, nullptr, ly.ld3, 1, m0, 0, M, L, 1}, TileSrc{ly.Wh, nullptr, nullptr, ly.ldL, 1, n0, 0, L, L, 1}, L, sA, sB);   // Wh^T
   const int tx = threadIdx.x % (GB / GT), ty = threadIdx.x / (GB / GT);
 #pragma unroll
   for (int i = 0; i < GT; i++) {
@@ -1002,9 +1001,7 @@ __device__ void phase_b3(const ModelDev& md, int li, int s, int tile, float* sA,
   const int m0 = tm * GB, n0 = tn * GB;
   if (m0 >= M) return;
   float acc[GT][GT] = {};
-  auto fa = [&](int m, int k) -> float { int b = m0 + m; return b < M ? ly.dvec[(size_t)b * ly.ld3 + k] : 0.f; };
-  auto fb = [&](int k, int n) -> float { int c = n0 + n; return c < IN ? ly.Wx[(size_t)c * ly.ld3 + k] : 0.f; };   // Wx^T
-  gemm_tile_acc<GB, GB, GK, GT, GT, true, false>(acc, K, fa, fb, sA, sB);
+  tile_gemm(acc, TileSrc{ly.dvec, nullptr, nullptr, ly.ld3, 1, m0, 0, M, K, 1}, TileSrc{ly.Wx, nullptr, nullptr, ly.ld3, 1, n0, 0, IN, K, 1}, K, sA, sB);   // Wx^T
   const int tx = threadIdx.x % (GB / GT), ty = threadIdx.x / (GB / GT);
   const uint32_t gstep = md.wG[s];
   const float retain = 1.0f - md.p_drop_e;
@@ -1054,9 +1051,7 @@ __device__ void phase_dense(const ModelDev& md, int li, int s, int job, float* s
   if (job < dj.nWh) {
     const int ntn = (L + GB - 1) / GB;
     const int m0 = (job / ntn) * GB, n0 = (job % ntn) * GB;
-    auto fa = [&](int m, int k) -> float { int kk = m0 + m; return kk < L ? ly.Hold[(size_t)k * ly.ldL + kk] * ly.r[(size_t)k * ly.ldL + kk] : 0.f; };
-    auto fb = [&](int k, int n) -> float { int c = n0 + n; return c < L ? ly.dvec[(size_t)k * ly.ld3 + c] : 0.f; };
-    gemm_tile_acc<GB, GB, GK, GT, GT, false, true>(acc, M, fa, fb, sA, sB);
+    tile_gemm(acc, TileSrc{ly.Hold, ly.r, nullptr, 1, ly.ldL, m0, 0, L, M, 0}, TileSrc{ly.dvec, nullptr, nullptr, 1, ly.ld3, n0, 0, L, M, 0}, M, sA, sB);
 #pragma unroll
     for (int i = 0; i < GT; i++)
 #pragma unroll
@@ -1070,9 +1065,7 @@ __device__ void phase_dense(const ModelDev& md, int li, int s, int job, float* s
   if (job < dj.nWrz) {
     const int ntn = (2 * L + GB - 1) / GB;
     const int m0 = (job / ntn) * GB, n0 = (job % ntn) * GB;
-    auto fa = [&](int m, int k) -> float { int kk = m0 + m; return kk < L ? ly.Hold[(size_t)k * ly.ldL + kk] : 0.f; };
-    auto fb = [&](int k, int n) -> float { int c = n0 + n; return c < 2 * L ? ly.dvec[(size_t)k * ly.ld3 + L + c] : 0.f; };
-    gemm_tile_acc<GB, GB, GK, GT, GT, false, true>(acc, M, fa, fb, sA, sB);
+    tile_gemm(acc, TileSrc{ly.Hold, nullptr, nullptr, 1, ly.ldL, m0, 0, L, M, 0}, TileSrc{ly.dvec + L, nullptr, nullptr, 1, ly.ld3, n0, 0, 2 * L, M, 0}, M, sA, sB);
 #pragma unroll
     for (int i = 0; i < GT; i++)
 #pragma unroll
@@ -1087,9 +1080,7 @@ __device__ void phase_dense(const ModelDev& md, int li, int s, int job, float* s
     const int IN = ly.in_dim;
     const int ntn = (3 * L + GB - 1) / GB;
     const int m0 = (job / ntn) * GB, n0 = (job % ntn) * GB;
-    auto fa = [&](int m, int k) -> float { int kk = m0 + m; return kk < IN ? ly.in[(size_t)k * ly.ld_in + kk] : 0.f; };
-    auto fb = [&](int k, int n) -> float { int c = n0 + n; return c < 3 * L ? ly.dvec[(size_t)k * ly.ld3 + c] : 0.f; };
-    gemm_tile_acc<GB, GB, GK, GT, GT, false, true>(acc, M, fa, fb, sA, sB);
+    tile_gemm(acc, TileSrc{ly.in, nullptr, nullptr, 1, ly.ld_in, m0, 0, IN, M, 0}, TileSrc{ly.dvec, nullptr, nullptr, 1, ly.ld3, n0, 0, 3 * L, M, 0}, M, sA, sB);
 #pragma unroll
     for (int i = 0; i < GT; i++)
 #pragma unroll

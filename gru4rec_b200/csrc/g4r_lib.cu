@@ -59,6 +59,7 @@ struct g4r_handle {
   cudaGraphExec_t graphU = nullptr, graph1 = nullptr; int graph_unroll = 16;
   bool use_graph = true;
   GridBar* dGridBar = nullptr; unsigned long long* dStamp = nullptr; int pk_blocks = 0; size_t pk_smem = 0;
+  FastSync* dFastSync = nullptr; bool fast_ok = false; int* hFlags = nullptr; int64_t fast_windows = 0, slow_windows = 0;
   bool prof = false; bool stamp_on = false;
   std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_phase;
 };
@@ -193,6 +194,7 @@ static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
   md.pTcol = cv.take<int>((size_t)CAP * B); md.pCbeg = cv.take<int>((size_t)CAP * (NCH + 1));
   int* dStepBase = cv.take<int>(4);
   GridBar* dGridBar = cv.take<GridBar>(1);
+  FastSync* dFastSync = cv.take<FastSync>(1);
   unsigned long long* dStamp = cv.take<unsigned long long>((size_t)CAP * 16);
   // sampling
   float* dP = cv.take<float>(c.n_items); float* dL0t = cv.take<float>(c.n_items); float* dL0s = cv.take<float>(c.n_items);
@@ -206,7 +208,7 @@ static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
     md.ST = dST; md.logP0t = dL0t; md.logP0s = dL0s;
     h->md = md; h->Bmax = Bmax; h->CAP = CAP; h->gen_len = store ? gen_len : 0;
     h->dX = dX; h->dY = dY; h->dSlot = dSlot; h->dM = dM; h->dSti = dSti; h->dXnext = dXnext; h->dF = dF; h->dXflag = dXflag; h->dG = dG;
-    h->dGridBar = dGridBar; h->dStamp = dStamp;
+    h->dGridBar = dGridBar; h->dStamp = dStamp; h->dFastSync = dFastSync;
     h->dStepBase = dStepBase; h->dP = dP; h->dLogP0t = dL0t; h->dLogP0s = dL0s; h->dST = dST; h->dU = dU; h->dMrgState = dMrg;
     h->dRankCnt = dRank; h->dTgt = dTgt;
     h->npow2 = next_pow2(B + S);
@@ -266,6 +268,7 @@ __global__ void __launch_bounds__(128) k_sparse_in(int slot, const int* base, in
 __global__ void k_advance(int* base, int n) { if (threadIdx.x == 0 && blockIdx.x == 0) *base += n; }
 
 #include "g4r_persistent.cuh"
+#include "g4r_fast.cuh"
 
 static int tiles2(int cols, int rows) { return ((cols + GB - 1) / GB) * ((rows + GB - 1) / GB); }
 
@@ -336,6 +339,7 @@ extern "C" int g4r_destroy(g4r_handle* h) {
   if (h->hF) cudaFreeHost(h->hF);
   if (h->hG) cudaFreeHost(h->hG);
   if (h->hCost) cudaFreeHost(h->hCost);
+  if (h->hFlags) cudaFreeHost(h->hFlags);
   if (h->own_ws && h->ws) cudaFree(h->ws);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -402,6 +406,15 @@ extern "C" int g4r_create(const g4r_config* cfg, void* device_workspace, size_t 
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent, PK_THREADS, h->pk_smem);
     int coop = 0; cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device);
     h->pk_blocks = (per_sm >= 1 && coop) ? h->n_sm : 0;
+  }
+  {
+    const ModelDev& m = h->md;
+    cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastSmem));
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fast, FK_THREADS, sizeof(FastSmem));
+    h->fast_ok = h->pk_blocks > 0 && per_sm >= 1 && m.mode == 0 && m.n_layers == 1 && m.ldL <= 128 && m.B <= FK_B && h->n_sm >= FK_G && m.NCH <= 160 &&
+                 (m.adapt == G4R_ADAPT_ADAGRAD ? m.Wy_acc != nullptr : true);
+    cudaMallocHost(&h->hFlags, 4 * sizeof(int));
   }
   if (cfg->step_mode == 1 && h->pk_blocks == 0) return bail(G4R_ERR_INVALID, "persistent mode unavailable (cooperative launch / shared memory)");
   if (cudaStreamSynchronize(h->stream) != cudaSuccess) return bail(G4R_ERR_CUDA, "init sync failed");
@@ -753,6 +766,7 @@ static int upload_window(g4r_handle* h, int64_t n) {
   CK(cudaMemcpyAsync(h->dM, h->hM, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(h->dSti, h->hSti, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(h->dG, h->hG, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(h->md.nanflag + 2, 0, sizeof(int), st));
   k_plan<<<(unsigned)n, 256, (size_t)h->npow2 * 8 + 1024, st>>>(h->md, h->dXnext, h->dXflag, h->npow2);
   h->launches++;
   CK(cudaGetLastError());
@@ -780,7 +794,21 @@ static int64_t launches_per_step(const g4r_handle* h) {
 }
 
 static int run_window(g4r_handle* h, int64_t n) {
-  if (h->cfg.step_mode == 1 && !h->prof) {
+  bool fast = false;
+  if (h->cfg.step_mode == 2 && !h->prof && h->fast_ok) {
+    // the plan kernel recorded the widest chunk of the window; the role-specialised kernel needs <= 16 columns
+    CK(cudaMemcpyAsync(h->hFlags, h->md.nanflag, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    fast = h->hFlags[2] <= FK_CT;
+  }
+  if (fast) {
+    int slot = h->slot, nst = (int)n; FastSync* fsp = h->dFastSync; unsigned long long* ts = h->stamp_on ? h->dStamp : nullptr;
+    void* args[] = {&slot, &nst, &fsp, &ts};
+    CK(cudaMemsetAsync(h->dFastSync, 0, sizeof(FastSync), h->stream));
+    CK(cudaLaunchCooperativeKernel((void*)k_fast, dim3(h->pk_blocks), dim3(FK_THREADS), args, sizeof(FastSmem), h->stream));
+    h->launches += 1; h->fast_windows++;
+  } else if ((h->cfg.step_mode == 1 || h->cfg.step_mode == 2) && !h->prof && h->pk_blocks > 0) {
+    if (h->cfg.step_mode == 2) h->slow_windows++;
     int slot = h->slot, nst = (int)n; GridBar* gb = h->dGridBar; unsigned long long* ts = h->stamp_on ? h->dStamp : nullptr;
     void* args[] = {&slot, &nst, &gb, &ts};
     CK(cudaMemsetAsync(h->dGridBar, 0, sizeof(GridBar), h->stream));
@@ -861,6 +889,11 @@ extern "C" int g4r_persistent_stamps(g4r_handle* h, int32_t enable, unsigned lon
     CK(cudaStreamSynchronize(h->stream));
   }
   return G4R_OK;
+}
+extern "C" int64_t g4r_fast_windows(const g4r_handle* h, int64_t* fallback_windows) {
+  if (!h) return 0;
+  if (fallback_windows) *fallback_windows = h->slow_windows;
+  return h->fast_windows;
 }
 extern "C" const char* g4r_phase_name(int32_t i) { return (i >= 0 && i < PH_COUNT) ? kPhaseNames[i] : ""; }
 extern "C" int g4r_phase_count(void) { return PH_COUNT; }

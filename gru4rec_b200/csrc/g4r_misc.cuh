@@ -118,6 +118,12 @@ __global__ void __launch_bounds__(256) k_plan(ModelDev md, int* xnext, uint8_t* 
     while (j > 0 && j < N && (keys[j] >> 32) == (keys[j - 1] >> 32)) j++;
     md.pCbeg[(size_t)s * (md.NCH + 1) + c] = min(j, N);
   }
+  __syncthreads();
+  // largest chunk of the window (the role-specialised kernel handles chunks of at most 32 columns)
+  for (int c = tid; c < md.NCH; c += blockDim.x) {
+    const int w = md.pCbeg[(size_t)s * (md.NCH + 1) + c + 1] - md.pCbeg[(size_t)s * (md.NCH + 1) + c];
+    if (w > 32) atomicMax(md.nanflag + 2, w);
+  }
   for (int b = tid; b < M; b += blockDim.x) {
     const int x = Xp[b];
     uint8_t f = 1; int nx = -1;

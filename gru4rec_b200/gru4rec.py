@@ -87,7 +87,7 @@ class GRU4Rec:
         self.device = 0
         self.dropout_seed = 0
         self.eval_lanes = 512            # run.py evaluates with batch_size=512 (run.py:127)
-        self.step_mode = 0
+        self.step_mode = 2               # role-specialised persistent kernel where the shape allows, else generic persistent
         self._engine = None
         self._host = None                # numpy copies of the parameters when no engine is alive
 
@@ -423,7 +423,7 @@ class GRU4Rec:
         self._host = host
         self._engine = None
         self.predict = None
-        for k, v in (('device', 0), ('dropout_seed', 0), ('eval_lanes', 512), ('step_mode', 0)):
+        for k, v in (('device', 0), ('dropout_seed', 0), ('eval_lanes', 512), ('step_mode', 2)):
             if not hasattr(self, k):
                 setattr(self, k, v)
 

@@ -63,7 +63,8 @@ typedef struct g4r_config {
   int32_t device;                 /* CUDA device ordinal */
   int32_t world_size, rank;       /* data-parallel geometry (1,0 for single GPU) */
   int32_t eval_batch_size;        /* lanes reserved for the scoring path (evaluation.py batch_size); 0 = batch_size */
-  int32_t step_mode;              /* 0: one kernel per phase (CUDA-graph replay); 1: persistent cooperative kernel */
+  int32_t step_mode;              /* 0: one kernel per phase (CUDA-graph replay); 1: persistent cooperative kernel;
+                                     2: role-specialised persistent kernel where the shape allows, else 1 */
   int32_t reserved[7];
 } g4r_config;
 
@@ -138,6 +139,9 @@ int g4r_run_uploaded(g4r_handle* h, float* cost_out /* may be NULL */, float* de
  * roofline: achieved bytes/s of the dominant kernel = its algorithmic bytes / its mean duration. */
 int g4r_profile_uploaded(g4r_handle* h, float* phase_ms, int32_t* phase_launches, int32_t n_phases);
 const char* g4r_phase_name(int32_t i);
+/* step_mode 2: number of windows run by the role-specialised kernel, and (out) windows that fell back to the
+ * generic persistent kernel because a chunk of score columns was wider than 16. */
+int64_t g4r_fast_windows(const g4r_handle* h, int64_t* fallback_windows);
 /* Persistent mode (step_mode 1): enable %globaltimer stamps at the phase boundaries of every step and/or read
  * the stamps of the last window (16 uint64 slots per step; slots 0..5 used: start, after GRU forward, after scores,
  * after statistics, after loss-gradient/update, end). */

@@ -89,7 +89,7 @@ CASES = {
 }
 
 
-@pytest.mark.parametrize('step_mode', [0, 1])
+@pytest.mark.parametrize('step_mode', [0, 1, 2])
 @pytest.mark.parametrize('name', sorted(CASES))
 def test_train_steps_match_oracle(name, step_mode):
     mk = CASES[name]
@@ -116,7 +116,7 @@ def test_train_steps_match_oracle(name, step_mode):
         np.testing.assert_allclose(eng.get('H%d' % i), m.H[i], rtol=1e-3, atol=1e-5)
 
 
-@pytest.mark.parametrize('step_mode', [0, 1])
+@pytest.mark.parametrize('step_mode', [0, 1, 2])
 def test_shrinking_batch_and_slots(step_mode):
     """epoch tail: M < B with lane compaction (gru4rec.py:644-651) through a real schedule."""
     from gru4rec_b200.synth import make_sessions
@@ -131,6 +131,40 @@ def test_shrinking_batch_and_slots(step_mode):
     ref = [m.train_step(st['X'], st['Y'], st['R'], samples=store[k], slots=st['slots']) for k, st in enumerate(steps)]
     np.testing.assert_allclose(costs, ref, rtol=2e-4, atol=1e-6)
     compare_weights(eng, m, rtol=3e-3, atol=3e-5)
+
+
+@pytest.mark.parametrize('loss,fact,alpha', [('bpr-max', 'elu-0.5', 0.0), ('cross-entropy', 'softmax', 0.75), ('top1-max', 'tanh', 1.0)])
+def test_headline_shape_role_specialised_kernel(loss, fact, alpha):
+    """B=32, GRU(100), 2048 samples (BASELINE configs[1] shape) through step_mode 2; heavy duplicates with alpha=1."""
+    from gru4rec_b200.synth import make_session_arrays
+    n_items = 3000
+    mk = dict(layers=[100], batch_size=32, n_sample=2048, loss=loss, final_act=fact, learning_rate=0.05, momentum=0.3, sample_alpha=alpha,
+              dropout_p_hidden=0.1 if loss == 'top1-max' else 0.0)
+    items, offset, order, supports = make_session_arrays(n_items, 40000, seed=5)
+    rows = 20
+    eng, m, _, rs = make_pair(n_items, mk, n_store_rows=0, seed=3, randomize_state=False, step_mode=2)
+    eng.close()
+    eng = _lib.Engine(make_cfg(n_items, mk, sample_store=rows * 2048, step_mode=2))
+    from gpu_utils import push_weights
+    push_weights(eng, m)
+    P = orc.sampling_cdf(supports, alpha).astype(np.float32)
+    u = rs.rand(rows * 2048).astype(np.float32)
+    eng.set_sampling_cdf(P)
+    eng.generate_samples_from_uniform(u)
+    store = orc.searchsorted_k2(P, u).reshape(rows, 2048)
+    np.testing.assert_array_equal(eng.get_sample_store(), store)
+    sched = _lib.Schedule(items, offset, order, 32, 2048, mode=0)
+    steps = orc.build_train_schedule(items, offset, order, 32, 2048)
+    n = 14
+    costs = eng.train_steps(sched, 0, n)
+    ref = [m.train_step(st['X'], st['Y'], st['R'], samples=store[k], slots=st['slots']) for k, st in enumerate(steps[:n])]
+    np.testing.assert_allclose(costs, ref, rtol=2e-4, atol=1e-6)
+    compare_weights(eng, m, rtol=2e-3, atol=2e-5, what='headline shape')
+    fast, fallback = eng.fast_windows()
+    if alpha == 0.0:
+        assert fast >= 1 and fallback == 0
+    else:
+        assert fast + fallback >= 1      # popularity sampling can create duplicate groups wider than a chunk -> generic kernel
 
 
 def test_index_errors_and_nan():

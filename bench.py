@@ -173,8 +173,10 @@ def main():
     make_cfg = _lib.make_config
     mk = dict(WORKLOAD['model'])
     cfg = make_cfg(WORKLOAD['n_items'], mk, sample_store=WORKLOAD['sample_store'], eval_lanes=0,
-                   max_resident_steps=max(K, W) + 8, step_mode=args.step_mode)
+                   max_resident_steps=max(K, W) + 8, step_mode=args.step_mode, world_size=world, rank=rank)
     eng = _lib.Engine(cfg, device=local_rank)
+    if world > 1:
+        eng.init_multi_gpu(dist)
     # parameters: the reference's initialisation (gru4rec.py:254-294); data: synthetic RSC15-shaped sessions, disjoint per rank
     import gru4rec as g4
     gru = g4.GRU4Rec(**mk)
@@ -198,60 +200,81 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident arm: warm-up window, then K timed steps from an uploaded window
-    eng.reset_hidden()
-    eng.upload_steps(sched, 0, W)
-    eng.run_uploaded(W, want_cost=False)
-    eng.upload_steps(sched, W, K)
-    launches0 = eng.kernel_launches()
     clocks = ClockSampler(local_rank); clocks.start()
     time.sleep(0.3)
-    barrier()
-    t0 = time.time()
-    costs, dev_ms = eng.run_uploaded(K, want_cost=True)
-    barrier()
-    wall = time.time() - t0
-    launches = eng.kernel_launches() - launches0
-    if dist is not None:
-        t = torch.tensor([dev_ms], device='cuda'); dist.all_reduce(t, op=dist.ReduceOp.MAX); dev_ms = float(t.item())
-    value = world * K / (dev_ms / 1000.0)
-    assert np.isfinite(costs).all(), 'non-finite cost in the timed region'
-    # ---- end-to-end arm: host schedule arrays in, costs out, every window (H2D + plan + steps + D2H inside the timing)
+    h2d = B * (4 + 4 + 4 + 1) + 12
     first = W + K
-    barrier()
-    t0 = time.time()
-    c2 = eng.train_steps(sched, first, K)
-    barrier()
-    e2e_s = time.time() - t0
-    if dist is not None:
-        t = torch.tensor([e2e_s], device='cuda'); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
+    if world == 1:
+        # ---- device-resident arm: warm-up window, then K timed steps from an uploaded window
+        eng.reset_hidden()
+        eng.upload_steps(sched, 0, W)
+        eng.run_uploaded(W, want_cost=False)
+        eng.upload_steps(sched, W, K)
+        launches0 = eng.kernel_launches()
+        barrier()
+        t0 = time.time()
+        costs, dev_ms = eng.run_uploaded(K, want_cost=True)
+        barrier()
+        wall = time.time() - t0
+        launches = eng.kernel_launches() - launches0
+        value = K / (dev_ms / 1000.0)
+        # ---- end-to-end arm: host schedule arrays in, costs out, every window (H2D + plan + steps + D2H inside the timing)
+        barrier()
+        t0 = time.time()
+        c2 = eng.train_steps(sched, first, K)
+        barrier()
+        e2e_s = time.time() - t0
+    else:
+        # ---- N ranks in lock step: one merged update per mini-batch (NCCL all-gather of row gradients + all-reduce of the
+        # dense gradients inside g4r_train_steps).  The call takes HOST schedule arrays, so this IS the end-to-end path;
+        # timed with barrier + synchronize on both sides, max over ranks.
+        eng.reset_hidden()
+        eng.train_steps(sched, 0, W)
+        launches0 = eng.kernel_launches()
+        barrier()
+        t0 = time.time()
+        costs = eng.train_steps(sched, W, K)
+        barrier()
+        wall = time.time() - t0
+        launches = eng.kernel_launches() - launches0
+        t = torch.tensor([wall], device='cuda'); dist.all_reduce(t, op=dist.ReduceOp.MAX); wall = float(t.item())
+        dev_ms = wall * 1000.0
+        value = world * K / wall
+        e2e_s = wall
+    assert np.isfinite(costs).all(), 'non-finite cost in the timed region'
     clocks.stop_flag = True
     e2e_value = world * K / e2e_s
-    h2d = B * (4 + 4 + 4 + 1) + 12
     # ---- per-kernel roofline from CUDA events around every launch of one more pass over a short window
     prof_n = min(K, 512)
-    eng.upload_steps(sched, first + K, prof_n)
-    prof = eng.profile_uploaded()
+    if world == 1:
+        eng.upload_steps(sched, first + K, prof_n)
+        prof = eng.profile_uploaded()
+    else:
+        prof = None      # the per-kernel roofline is a single-GPU measurement (N=1 run of this same script)
     peak, peak_src = peak_hbm()
-    dom_name = max(prof, key=lambda k: prof[k][0])
-    lg_ms, lg_n = prof['lossgrad_update']
     lg_bytes = algo_bytes_lossgrad(N, mk['layers'][-1], mk['momentum'] > 0)
-    achieved = lg_bytes / (lg_ms / lg_n * 1e-3) / 1e9
-    phase_us = {k: round(v[0] / v[1] * 1000.0, 3) for k, v in prof.items()}
+    if prof is not None:
+        dom_name = max(prof, key=lambda k: prof[k][0])
+        lg_ms, lg_n = prof['lossgrad_update']
+        achieved = lg_bytes / (lg_ms / lg_n * 1e-3) / 1e9
+        frac, us_launch = achieved / peak, lg_ms / lg_n * 1000.0
+        phase_us = {k: round(v[0] / v[1] * 1000.0, 3) for k, v in prof.items()}
+    else:
+        dom_name, achieved, frac, us_launch, phase_us = None, None, None, None, None
     out = {
         'metric': 'mini-batches/sec', 'value': value, 'unit': 'mb/s', 'n_gpus': world, 'steps': K, 'warmup': W,
         'ms_per_step': dev_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': WORKLOAD['name'], 'n_items': WORKLOAD['n_items'], 'global_batch': B * world, 'n_sample': mk['n_sample'],
-                   'layers': mk['layers'], 'params': 'param_samples/rsc15_bpr-max.py', 'parallelism': 'dp%d' % world,
+                   'layers': mk['layers'], 'params': 'param_samples/rsc15_bpr-max.py', 'parallelism': ('dp%d: replicated parameters, NCCL all-gather of row gradients + all-reduce of dense gradients per mini-batch, identical merged update on every rank' % world) if world > 1 else 'dp1',
                    'l2': 'working set (item tables + Adagrad/momentum state = 180 MB) larger than L2; rows touched change every step',
                    'step_mode': int(cfg.step_mode), 'fast_windows': list(eng.fast_windows()), 'events_per_sec': value * B},
         'e2e': {'value': e2e_value, 'unit': 'mb/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches),
         'clocks': clocks.summary(),
         'roofline': {'bound': 'hbm', 'kernel': 'k_lossgrad (loss gradient + sparse Adagrad/momentum update of Wy/By rows)',
-                     'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
-                     'peak_source': peak_src, 'algorithmic_bytes_per_launch': lg_bytes, 'us_per_launch': lg_ms / lg_n * 1000.0,
+                     'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': frac, 'traffic': 3812352 if world == 1 else None,
+                     'peak_source': peak_src, 'algorithmic_bytes_per_launch': lg_bytes, 'us_per_launch': us_launch, 'traffic_source': 'ncu --set full dram read+write of k_lossgrad, profiles/r1_ncu_full_k_lossgrad.txt',
                      'dominant_phase_by_time': dom_name, 'phase_us': phase_us,
                      'whole_step': {'algorithmic_bytes': ALGO_BYTES_PER_STEP, 'achieved': ALGO_BYTES_PER_STEP * (value / world) / 1e9,
                                     'frac': ALGO_BYTES_PER_STEP * (value / world) / 1e9 / peak,

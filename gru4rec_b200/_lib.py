@@ -38,7 +38,7 @@ EXPORTS = [
     'g4r_mrg_uniform', 'g4r_searchsorted', 'g4r_gather_rows',
     'g4r_schedule_build', 'g4r_schedule_free', 'g4r_schedule_steps', 'g4r_schedule_events', 'g4r_schedule_export',
     'g4r_train_step', 'g4r_train_steps', 'g4r_upload_steps', 'g4r_run_uploaded', 'g4r_kernel_launches',
-    'g4r_profile_uploaded', 'g4r_phase_name', 'g4r_phase_count', 'g4r_persistent_stamps', 'g4r_fast_windows',
+    'g4r_profile_uploaded', 'g4r_phase_name', 'g4r_phase_count', 'g4r_persistent_stamps', 'g4r_fast_windows', 'g4r_mg_unique_id', 'g4r_mg_init',
     'g4r_eval_schedule', 'g4r_predict', 'g4r_reset_eval_hidden',
 ]
 
@@ -92,6 +92,8 @@ def load():
     lib.g4r_phase_count.restype = C.c_int
     lib.g4r_persistent_stamps.argtypes = [vp, i32, vp, i64]
     lib.g4r_fast_windows.argtypes = [vp, C.POINTER(i64)]; lib.g4r_fast_windows.restype = i64
+    lib.g4r_mg_unique_id.argtypes = [vp]
+    lib.g4r_mg_init.argtypes = [vp, vp]
     lib.g4r_eval_schedule.argtypes = [vp, vp, vp, i32, i32, vp, vp, C.POINTER(i64)]
     lib.g4r_predict.argtypes = [vp, vp, i32, vp, vp]
     lib.g4r_reset_eval_hidden.argtypes = [vp]
@@ -123,7 +125,7 @@ def parse_act(name):
     raise NotImplementedError
 
 
-def make_config(n_items, mk, sample_store=0, eval_lanes=0, max_resident_steps=0, step_mode=0):
+def make_config(n_items, mk, sample_store=0, eval_lanes=0, max_resident_steps=0, step_mode=0, world_size=1, rank=0):
     cfg = G4RConfig()
     layers = mk.get('layers', [100])
     cfg.n_items = n_items
@@ -151,7 +153,7 @@ def make_config(n_items, mk, sample_store=0, eval_lanes=0, max_resident_steps=0,
     cfg.dropout_seed = mk.get('dropout_seed', 0)
     cfg.mrg_seed = 12345
     cfg.max_resident_steps = max_resident_steps
-    cfg.world_size, cfg.rank = 1, 0
+    cfg.world_size, cfg.rank = world_size, rank
     cfg.eval_batch_size = eval_lanes
     cfg.step_mode = step_mode
     return cfg
@@ -168,7 +170,11 @@ class Schedule(object):
         off = np.ascontiguousarray(offset_sessions, dtype=np.int32)
         order = None if session_order is None else np.ascontiguousarray(session_order, dtype=np.int64)
         h = C.c_void_p()
-        rc = lib.g4r_schedule_build(_ptr(di), len(di), _ptr(off), len(off) - 1, _ptr(order), batch_size, n_sample, mode, C.byref(h))
+        # n_sessions = number of sessions this schedule walks: all of them, or the entries of a (possibly sharded) order
+        n_sess = len(off) - 1 if order is None else len(order)
+        if order is not None and len(order) and (order.min() < 0 or order.max() >= len(off) - 1):
+            raise IndexError('session_order refers to a session that does not exist')
+        rc = lib.g4r_schedule_build(_ptr(di), len(di), _ptr(off), n_sess, _ptr(order), batch_size, n_sample, mode, C.byref(h))
         if rc == G4R_ERR_INDEX:
             raise IndexError(lib.g4r_last_error(None).decode())
         if rc != 0:
@@ -357,6 +363,20 @@ class Engine(object):
         out = np.zeros((n_steps, 16), dtype=np.uint64) if n_steps > 0 else None
         self._check(self.lib.g4r_persistent_stamps(self.h, 1 if enable else 0, _ptr(out), n_steps))
         return out
+
+    def init_multi_gpu(self, dist):
+        """Create the NCCL communicator of this handle: rank 0's unique id is broadcast through torch.distributed."""
+        import torch
+        buf = (C.c_char * 128)()
+        if dist.get_rank() == 0:
+            rc = self.lib.g4r_mg_unique_id(buf)
+            if rc != 0:
+                raise RuntimeError('ncclGetUniqueId failed')
+        t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device='cuda' if dist.get_backend() == 'nccl' else 'cpu')
+        dist.broadcast(t, 0)
+        raw = bytes(t.cpu().tolist())
+        idbuf = (C.c_char * 128).from_buffer_copy(raw)
+        self._check(self.lib.g4r_mg_init(self.h, idbuf))
 
     def fast_windows(self):
         fb = C.c_int64()

@@ -23,6 +23,18 @@
 #define G4R_NSTAT 8
 
 struct ActSpec { int kind; float p1, p2; };
+constexpr int MG_CAP = 256;          // steps per multi-GPU window (g4r_multi.cuh)
+struct MgDev {                       // device pointers of the multi-GPU state
+  int R, rank;
+  int *gItem, *gPos, *gM, *gX;       // gathered per-rank sorted columns [R][MG_CAP][NP], batch sizes [R][MG_CAP], inputs [R][MG_CAP][B]
+  int *mEnt, *mItem, *mCbeg;         // merged columns per step: entry = rank << 20 | col ; [MG_CAP][R*NP], chunks [MG_CAP][NCH+1]
+  int *mTot;                         // [MG_CAP] merged length
+  int *xEnt, *xItem, *xTot;          // merged input rows per step: entry = rank << 16 | lane ; [MG_CAP][R*B]
+  float *DSYall, *DBYall, *INall;    // gathered gradients of one step [R][NP][ldL], [R][NP], [R][B][ldin]
+  float* gradFlat; size_t gradCount; // dense gradients, contiguous (all-reduced in place)
+};
+
+struct MgTensor { float *p, *acc, *vel; size_t goff; int count; };
 // synchronisation counters of the role-specialised kernel (g4r_fast.cuh), one per 128-byte line
 struct FastSync {                   // one counter per 128-byte line
   unsigned int bar;      unsigned int p0[31];
@@ -40,6 +52,7 @@ struct LayerDev {
   float *Wh, *Wh_acc, *Wh_vel;
   float *Wrz, *Wrz_acc, *Wrz_vel;
   float *Bh, *Bh_acc, *Bh_vel;
+  float *Wx_g, *Wh_g, *Wrz_g, *Bh_g;   // multi-GPU: dense gradients are exported here (all-reduced) instead of applied
   float *H;                // training hidden state, physical lanes [B x ldL]
   float *Hold, *r, *z, *ah, *ht, *y;   // forward saves, compact lanes [Bmax x ldL]
   float *dvec;             // [Bmax x ld3]  (da_h | da_r | da_z)
@@ -57,6 +70,7 @@ struct ModelDev {
   float p_drop_h, p_drop_e, lr, mom, lmbd, bpreg, logq, alpha;
   int adapt; int nn_top1;                   // nn_top1 = M + n_sample term handled at run time (uses S_cfg)
   int S_cfg;
+  int export_only;                          // multi-GPU: compute gradients only; the merged update is applied after the exchange
   uint32_t drop_seed;
   LayerDev layer[G4R_MAX_LAYERS];
   float *Wy, *Wy_acc, *Wy_vel; float *By, *By_acc, *By_vel;
@@ -809,7 +823,7 @@ __device__ void phase_lossgrad(const ModelDev& md, int s, int chunk, float* smem
   const float* __restrict__ Y = md.layer[md.n_layers - 1].y;
   const float* __restrict__ Wy = md.Wy;
   const int* __restrict__ pItem = md.pItem + (size_t)s * md.NP;
-  const bool single = (ce - cb) <= SC_CT;        // whole chunk in one sub tile: the dSy rows stay in shared memory
+  const bool single = (ce - cb) <= SC_CT && !md.export_only;   // whole chunk in one sub tile: the dSy rows stay in shared memory
   for (int j0 = cb; j0 < ce; j0 += SC_CT) {
     const int nj = min(SC_CT, ce - j0);
     __syncthreads();
@@ -875,6 +889,7 @@ __device__ void phase_lossgrad(const ModelDev& md, int s, int chunk, float* smem
     }
   }
   __syncthreads();
+  if (md.export_only) return;     // multi-GPU: DSY / DBY are exchanged and the merged update is applied by k_mg_apply_rows
   // ---- sparse update of this chunk's item groups; one warp per group, members in position order
   const bool ada = md.adapt == G4R_ADAPT_ADAGRAD;
   const bool mom = md.mom > 0.f;
@@ -1057,7 +1072,7 @@ __device__ void phase_dense(const ModelDev& md, int li, int s, int job, float* s
 #pragma unroll
       for (int j = 0; j < GT; j++) {
         const int rr = m0 + ty * GT + i, c = n0 + tx * GT + j;
-        if (rr < L && c < L) { const size_t o = (size_t)rr * ly.ldL + c; dense_update(md, ly.Wh + o, ly.Wh_acc ? ly.Wh_acc + o : nullptr, ly.Wh_vel ? ly.Wh_vel + o : nullptr, acc[i][j]); }
+        if (rr < L && c < L) { const size_t o = (size_t)rr * ly.ldL + c; if (md.export_only) ly.Wh_g[o] = acc[i][j]; else dense_update(md, ly.Wh + o, ly.Wh_acc ? ly.Wh_acc + o : nullptr, ly.Wh_vel ? ly.Wh_vel + o : nullptr, acc[i][j]); }
       }
     return;
   }
@@ -1071,7 +1086,7 @@ __device__ void phase_dense(const ModelDev& md, int li, int s, int job, float* s
 #pragma unroll
       for (int j = 0; j < GT; j++) {
         const int rr = m0 + ty * GT + i, c = n0 + tx * GT + j;
-        if (rr < L && c < 2 * L) { const size_t o = (size_t)rr * ly.ld2 + c; dense_update(md, ly.Wrz + o, ly.Wrz_acc ? ly.Wrz_acc + o : nullptr, ly.Wrz_vel ? ly.Wrz_vel + o : nullptr, acc[i][j]); }
+        if (rr < L && c < 2 * L) { const size_t o = (size_t)rr * ly.ld2 + c; if (md.export_only) ly.Wrz_g[o] = acc[i][j]; else dense_update(md, ly.Wrz + o, ly.Wrz_acc ? ly.Wrz_acc + o : nullptr, ly.Wrz_vel ? ly.Wrz_vel + o : nullptr, acc[i][j]); }
       }
     return;
   }
@@ -1086,7 +1101,7 @@ __device__ void phase_dense(const ModelDev& md, int li, int s, int job, float* s
 #pragma unroll
       for (int j = 0; j < GT; j++) {
         const int rr = m0 + ty * GT + i, c = n0 + tx * GT + j;
-        if (rr < IN && c < 3 * L) { const size_t o = (size_t)rr * ly.ld3 + c; dense_update(md, ly.Wx + o, ly.Wx_acc ? ly.Wx_acc + o : nullptr, ly.Wx_vel ? ly.Wx_vel + o : nullptr, acc[i][j]); }
+        if (rr < IN && c < 3 * L) { const size_t o = (size_t)rr * ly.ld3 + c; if (md.export_only) ly.Wx_g[o] = acc[i][j]; else dense_update(md, ly.Wx + o, ly.Wx_acc ? ly.Wx_acc + o : nullptr, ly.Wx_vel ? ly.Wx_vel + o : nullptr, acc[i][j]); }
       }
     return;
   }
@@ -1096,7 +1111,7 @@ __device__ void phase_dense(const ModelDev& md, int li, int s, int job, float* s
     if (c < 3 * L) {
       float g = 0.f;
       for (int b = 0; b < M; b++) g += ly.dvec[(size_t)b * ly.ld3 + c];
-      dense_update(md, ly.Bh + c, ly.Bh_acc ? ly.Bh_acc + c : nullptr, ly.Bh_vel ? ly.Bh_vel + c : nullptr, g);
+      if (md.export_only) ly.Bh_g[c] = g; else dense_update(md, ly.Bh + c, ly.Bh_acc ? ly.Bh_acc + c : nullptr, ly.Bh_vel ? ly.Bh_vel + c : nullptr, g);
     }
   }
 }
@@ -1107,7 +1122,7 @@ __device__ void phase_dense(const ModelDev& md, int li, int s, int job, float* s
 // ------------------------------------------------------------------------------------------------
 __device__ void phase_sparse_in(const ModelDev& md, int s, int b) {
   const int M = md.wM[s];
-  if (b >= M) return;
+  if (b >= M || md.export_only) return;
   const uint8_t xf = md.wXflag[(size_t)s * md.B + b];
   if (!(xf & 1)) return;                      // not the first position of its group
   const int item = md.wX[(size_t)s * md.B + b];

@@ -16,6 +16,7 @@
 static thread_local std::string g_create_error;
 struct g4r_handle;
 static void eval_release(g4r_handle* h);
+static void mg_release(g4r_handle* h);
 
 struct TensorInfo { float* ptr; int64_t rows, cols, ld; };
 
@@ -59,6 +60,7 @@ struct g4r_handle {
   cudaGraphExec_t graphU = nullptr, graph1 = nullptr; int graph_unroll = 16;
   bool use_graph = true;
   GridBar* dGridBar = nullptr; unsigned long long* dStamp = nullptr; int pk_blocks = 0; size_t pk_smem = 0;
+  bool mg_alloc = false; MgDev mgdev; std::vector<MgTensor> mg_tensors;
   FastSync* dFastSync = nullptr; bool fast_ok = false; int* hFlags = nullptr; int64_t fast_windows = 0, slow_windows = 0;
   bool prof = false; bool stamp_on = false;
   std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_phase;
@@ -130,7 +132,8 @@ static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
   const int S = store ? c.n_sample : 0;
   const int NP = round4(B + S);
   const int NCH = std::max(1, std::min(n_sm, (NP + 3) / 4));
-  const int CAP = c.max_resident_steps > 0 ? c.max_resident_steps : 2048;
+  const int R = c.world_size > 1 ? c.world_size : 1;
+  const int CAP = std::max(c.max_resident_steps > 0 ? c.max_resident_steps : 2048, R > 1 ? MG_CAP : 1);
   ModelDev md; memset(&md, 0, sizeof(md));
   md.n_items = c.n_items; md.n_layers = nl; md.B = B; md.Bld = round4(Bmax); md.S = S; md.mode = mode; md.L = Llast; md.ldL = ldL;
   md.NP = NP; md.NCH = NCH; md.CAP = CAP; md.S_cfg = c.n_sample;
@@ -201,12 +204,40 @@ static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
   int* dST = store ? cv.take<int>((size_t)gen_len * c.n_sample) : nullptr;
   float* dU = store ? cv.take<float>((size_t)gen_len * c.n_sample) : nullptr;
   int32_t* dMrg = cv.take<int32_t>((size_t)15360 * 6);
+  // multi-GPU: dense-gradient twins (one flat all-reduce buffer) and the gathered / merged per-window state
+  MgDev mgd; memset(&mgd, 0, sizeof(mgd));
+  std::vector<MgTensor> mgt;
+  if (R > 1) {
+    size_t cnt = 0;
+    for (int i = 0; i < nl; i++) {
+      const LayerDev& ly = md.layer[i];
+      if (ly.in_dim > 0) cnt += (size_t)ly.in_dim * ly.ld3;
+      cnt += (size_t)ly.L * ly.ldL + (size_t)ly.L * ly.ld2 + ly.ld3;
+    }
+    float* gf = cv.take<float>(cnt);
+    size_t off = 0;
+    for (int i = 0; i < nl; i++) {
+      LayerDev& ly = md.layer[i];
+      if (ly.in_dim > 0) { ly.Wx_g = gf ? gf + off : nullptr; mgt.push_back(MgTensor{ly.Wx, ly.Wx_acc, ly.Wx_vel, off, ly.in_dim * ly.ld3}); off += (size_t)ly.in_dim * ly.ld3; }
+      ly.Wh_g = gf ? gf + off : nullptr; mgt.push_back(MgTensor{ly.Wh, ly.Wh_acc, ly.Wh_vel, off, ly.L * ly.ldL}); off += (size_t)ly.L * ly.ldL;
+      ly.Wrz_g = gf ? gf + off : nullptr; mgt.push_back(MgTensor{ly.Wrz, ly.Wrz_acc, ly.Wrz_vel, off, ly.L * ly.ld2}); off += (size_t)ly.L * ly.ld2;
+      ly.Bh_g = gf ? gf + off : nullptr; mgt.push_back(MgTensor{ly.Bh, ly.Bh_acc, ly.Bh_vel, off, ly.ld3}); off += ly.ld3;
+    }
+    mgd.R = R; mgd.rank = c.rank; mgd.gradFlat = gf; mgd.gradCount = cnt;
+    mgd.gItem = cv.take<int>((size_t)R * MG_CAP * NP); mgd.gPos = nullptr;
+    mgd.gM = cv.take<int>((size_t)R * MG_CAP); mgd.gX = cv.take<int>((size_t)R * MG_CAP * B);
+    mgd.mEnt = cv.take<int>((size_t)MG_CAP * R * NP); mgd.mItem = cv.take<int>((size_t)MG_CAP * R * NP);
+    mgd.mCbeg = cv.take<int>((size_t)MG_CAP * (NCH + 1)); mgd.mTot = cv.take<int>(MG_CAP);
+    mgd.xEnt = cv.take<int>((size_t)MG_CAP * R * B); mgd.xItem = cv.take<int>((size_t)MG_CAP * R * B); mgd.xTot = cv.take<int>(MG_CAP);
+    const int in_ld = mode == 0 ? md.layer[0].ld3 : md.ld_in0;
+    mgd.DSYall = cv.take<float>((size_t)R * NP * ldL); mgd.DBYall = cv.take<float>((size_t)R * NP); mgd.INall = cv.take<float>((size_t)R * B * in_ld);
+  }
   // evaluation
   int* dRank = cv.take<int>((size_t)Be * 4); float* dTgt = cv.take<float>(Be);
   if (!cv.dry) {
     md.wX = dX; md.wY = dY; md.wSlot = dSlot; md.wM = dM; md.wSti = dSti; md.wXnext = dXnext; md.wF = dF; md.wXflag = dXflag; md.wG = dG;
     md.ST = dST; md.logP0t = dL0t; md.logP0s = dL0s;
-    h->md = md; h->Bmax = Bmax; h->CAP = CAP; h->gen_len = store ? gen_len : 0;
+    h->md = md; h->Bmax = Bmax; h->CAP = CAP; h->mg_alloc = R > 1; h->mgdev = mgd; h->mg_tensors = mgt; h->gen_len = store ? gen_len : 0;
     h->dX = dX; h->dY = dY; h->dSlot = dSlot; h->dM = dM; h->dSti = dSti; h->dXnext = dXnext; h->dF = dF; h->dXflag = dXflag; h->dG = dG;
     h->dGridBar = dGridBar; h->dStamp = dStamp; h->dFastSync = dFastSync;
     h->dStepBase = dStepBase; h->dP = dP; h->dLogP0t = dL0t; h->dLogP0s = dL0s; h->dST = dST; h->dU = dU; h->dMrgState = dMrg;
@@ -326,6 +357,7 @@ extern "C" int g4r_destroy(g4r_handle* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   eval_release(h);
+  mg_release(h);
   if (h->graphU) cudaGraphExecDestroy(h->graphU);
   if (h->graph1) cudaGraphExecDestroy(h->graph1);
   slot_free(h->slot);
@@ -830,6 +862,9 @@ static int run_window(g4r_handle* h, int64_t n) {
   return G4R_OK;
 }
 
+#include "g4r_multi.cuh"
+static bool mg_is_ready(g4r_handle* h) { auto it = g_mg.find(h); return it != g_mg.end() && it->second.ready; }
+
 extern "C" int g4r_upload_steps(g4r_handle* h, const g4r_schedule* s, int64_t first, int64_t n) {
   if (!h || !s) return G4R_ERR_INVALID;
   if (s->B != h->md.B) FAIL(G4R_ERR_INVALID, "schedule batch size != model batch size");
@@ -910,11 +945,15 @@ extern "C" int g4r_train_steps(g4r_handle* h, const g4r_schedule* s, int64_t fir
       int rc = g4r_generate_samples(h);
       if (rc) return rc;
     }
-    const int64_t w = stage_window(h, s, first + done, n - done);
+    const bool multi = h->cfg.world_size > 1;
+    const int64_t w = stage_window(h, s, first + done, multi ? std::min<int64_t>(n - done, MG_CAP) : n - done);
     if (w <= 0) FAIL(G4R_ERR_STATE, "empty window");
     int rc = upload_window(h, w);
     if (rc) return rc;
-    rc = run_window(h, w);
+    if (multi) {
+      if (!mg_is_ready(h)) FAIL(G4R_ERR_STATE, "multi-GPU handle: call g4r_mg_init first");
+      rc = mg_run_window(h, w);
+    } else rc = run_window(h, w);
     if (rc) return rc;
     CK(cudaMemcpyAsync(h->hCost, h->md.cost, (size_t)w * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));

@@ -210,10 +210,21 @@ class GRU4Rec:
         cfg.dropout_seed = self.dropout_seed
         cfg.mrg_seed = 12345
         cfg.max_resident_steps = 0
-        cfg.world_size, cfg.rank = 1, 0
+        cfg.world_size, cfg.rank = self._world()
         cfg.eval_batch_size = eval_lanes
         cfg.step_mode = self.step_mode
         return cfg
+
+    @staticmethod
+    def _world():
+        """(world_size, rank) of the torch.distributed job this process belongs to, or (1, 0)."""
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                return dist.get_world_size(), dist.get_rank()
+        except Exception:
+            pass
+        return 1, 0
 
     def _build_engine(self, sample_store=0, eval_lanes=None):
         eval_lanes = self.eval_lanes if eval_lanes is None else eval_lanes
@@ -221,9 +232,16 @@ class GRU4Rec:
         if self._engine is not None:
             self._engine.close()
             self._engine = None
+        world, rank = self._world()
+        if world > 1:
+            import torch
+            self.device = torch.cuda.current_device()
         eng = _lib.Engine(self._make_config(sample_store, eval_lanes), device=self.device)
         for name in self._param_names():
             eng.set(name, host[name])
+        if world > 1:
+            import torch.distributed as dist
+            eng.init_multi_gpu(dist)
         self._engine = eng
         self._engine_eval_lanes = eval_lanes
         self._host = None
@@ -322,6 +340,7 @@ class GRU4Rec:
                 eng.set_sample_store(self.generate_neg_samples(pop, generate_length))
         base_order = np.argsort(data.groupby(self.session_key)[self.time_key].min().values) if self.time_sort else np.arange(len(offset_sessions) - 1)
         data_items = data.ItemIdx.values
+        world, rank = self._world()       # under torchrun: synchronous data parallelism, every rank trains a shard of the sessions
         sched = None
         n_sample_eff = self.n_sample if use_store else (self.n_sample if store_type == 'cpu' else self.n_sample)
         for epoch in range(self.n_epochs):
@@ -329,13 +348,19 @@ class GRU4Rec:
             eng.reset_hidden()
             session_idx_arr = np.random.permutation(len(offset_sessions) - 1) if self.train_random_order else base_order
             if sched is None or self.train_random_order:
+                n_steps = None
+                if world > 1:
+                    import torch.distributed as dist
+                    from .parallel import shard_sessions, common_steps
+                    session_idx_arr = shard_sessions(session_idx_arr, rank, world)
                 sched = _lib.Schedule(data_items, offset_sessions, session_idx_arr, self.batch_size, n_sample_eff, mode=0)
-                cc = sched.export()['M'].astype(np.float64)
+                n_steps = sched.n_steps if world == 1 else common_steps(sched.n_steps, dist)
+                cc = sched.export()['M'][:n_steps].astype(np.float64)
             try:
                 if use_store and store_type == 'cpu':
                     c = self._train_epoch_cpu_store(eng, sched, pop, generate_length)
                 else:
-                    c = eng.train_steps(sched, 0, sched.n_steps)
+                    c = eng.train_steps(sched, 0, n_steps)
             except _lib.NaNError:
                 print(str(epoch) + ': NaN error!')
                 self.error_during_train = True

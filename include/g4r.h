@@ -115,7 +115,8 @@ int g4r_gather_rows(g4r_handle* h, const float* table, int64_t rows, int64_t col
 /* ---- session-parallel schedule (gru4rec.py:585-651; evaluation.py:90-139) -------------------------- */
 /* Builds every mini-batch of one epoch on the host: X/Y item indices, reset flags, batch sizes, lane slots.
  * mode 0 = training order semantics (reset-after flags), 1 = evaluation (zero-before flags).
- * session_order: permutation of sessions (gru4rec.py:585/593) or NULL for identity. */
+ * session_order: n_sessions session ids (gru4rec.py:585/593; a rank's shard in the multi-GPU path) or NULL for identity;
+ * offset_sessions must cover every id that occurs in it. */
 int g4r_schedule_build(const int64_t* data_items, int64_t n_events, const int32_t* offset_sessions, int64_t n_sessions,
                        const int64_t* session_order, int32_t batch_size, int32_t n_sample, int32_t mode, g4r_schedule** out);
 int g4r_schedule_free(g4r_schedule* s);
@@ -149,6 +150,14 @@ int g4r_persistent_stamps(g4r_handle* h, int32_t enable, unsigned long long* out
 int g4r_phase_count(void);
 /* Counters for bench.py: kernels launched by this handle so far. */
 int64_t g4r_kernel_launches(const g4r_handle* h);
+
+/* ---- multi-GPU (one process per GPU) -------------------------------------------------------
+ * Handles created with world_size > 1 compute gradients only; g4r_train_steps then exchanges them over NCCL
+ * (all-gather of row gradients, all-reduce of dense gradients) and applies the merged update on every rank.
+ * Rank 0 obtains a 128-byte NCCL unique id, the caller broadcasts it (e.g. torch.distributed), every rank calls
+ * g4r_mg_init.  All ranks must call g4r_train_steps with the same number of steps. */
+int g4r_mg_unique_id(char* out128);
+int g4r_mg_init(g4r_handle* h, const char* id128);
 
 /* ---- scoring path: evaluate(X, Y, M) (evaluation.py:76,108) and predict (gru4rec.py:706-710) ------- */
 /* Runs a whole evaluation schedule: full-catalogue scores, rank of the target, per-cutoff hit counts and

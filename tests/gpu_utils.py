@@ -71,3 +71,30 @@ def make_pair(n_items, mk, n_store_rows=0, seed=0, eval_lanes=0, randomize_state
         m.P0 = P0
         eng.set_logq_support(P0)
     return eng, m, store, rs
+
+
+def oracle_multi_step(m, Hs, inputs):
+    """One synchronous data-parallel step of R ranks on the oracle: every rank's forward/backward with the shared
+    weights and its own hidden state, then ONE merged update -- row gradients of all ranks concatenated in
+    (rank, position) order, dense gradients summed (the stated multi-GPU semantics, gru4rec_b200/csrc/g4r_multi.cuh)."""
+    Cs, Gs, costs = [], [], []
+    for r, inp in enumerate(inputs):
+        M = len(inp['X'])
+        masks = m.make_masks(M)
+        Hr = [h[inp['slots']] for h in Hs[r]]
+        X = np.asarray(inp['X'], dtype=np.int64); Y = np.asarray(inp['Y'], dtype=np.int64)
+        yhat, C = m.forward(X, Y, M, R=inp['R'], samples=inp.get('samples'), masks=masks, H=Hr)
+        cost, G = m.backward(C, M)
+        Cs.append(C); Gs.append(G); costs.append(cost)
+    nl = len(m.layers)
+    Cm = dict(mode=Cs[0]['mode'], X=np.concatenate([C['X'] for C in Cs]), Y=np.concatenate([C['Y'] for C in Cs]),
+              Sx=np.vstack([C['Sx'] for C in Cs]), Sy=np.vstack([C['Sy'] for C in Cs]))
+    Gm = dict(dSx=np.vstack([G['dSx'] for G in Gs]), dSy=np.vstack([G['dSy'] for G in Gs]), dSBy=np.vstack([G['dSBy'] for G in Gs]))
+    for key in ('dWx', 'dWh', 'dWrz', 'dBh'):
+        Gm[key] = [None if Gs[0][key][i] is None else sum(G[key][i] for G in Gs) for i in range(nl)]
+    m.apply_updates(Cm, Gm, sum(len(i['X']) for i in inputs))
+    for r, inp in enumerate(inputs):
+        for i in range(nl):
+            Hs[r][i][inp['slots']] = Cs[r]['H_new'][i]
+    m.step_count += 1
+    return costs

@@ -17,6 +17,7 @@ constexpr int FK_G = 48;            // CTAs that run the GRU phases
 constexpr int FK_CT = 32;           // max columns per chunk
 constexpr int FK_Q = FK_CT / FK_NW;  // columns per warp
 constexpr int FK_B = 32;            // max lanes
+static_assert(FK_THREADS / 16 == FK_B, "statistics mapping: 16 threads per lane");
 constexpr int FK_LDS = 132;         // shared row stride (floats) for L <= 128: conflict-free 16-byte accesses
 
 
@@ -107,21 +108,31 @@ __device__ __forceinline__ void fk_prefetch_rows(const ModelDev& md, FastSmem& s
   const bool ada = md.adapt == G4R_ADAPT_ADAGRAD, mom = md.mom > 0.f;
   const unsigned int rowb = (unsigned int)md.ldL * 4u;
   uint64_t* bar = reinterpret_cast<uint64_t*>(&sm.mbar);
-  if (tid < 32) {
-    if (tid == 0) {
-      const unsigned int total = rowb * (unsigned int)(nj * (1 + (ada ? 1 : 0) + (mom ? 1 : 0)) + (pw ? M : 0));
-      asm volatile("fence.proxy.async.global;" ::: "memory");
-      if (total > 0) mbar_expect_tx(bar, total);
-      else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+  // bulk copies are issued one per thread-instruction; spreading them over the warps (lane 0 of each) keeps the issue
+  // off the critical path (one warp issuing ~80 copies took 2.3 us)
+  const int ntab = 1 + (ada ? 1 : 0) + (mom ? 1 : 0);
+  const int ncopy = nj * ntab + (pw ? M : 0);
+  if (tid == 0) {
+    const unsigned int total = rowb * (unsigned int)ncopy;
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+    if (total > 0) mbar_expect_tx(bar, total);
+    else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+  }
+  if ((tid & 31) == 0) {
+    for (int i = tid >> 5; i < ncopy; i += FK_NW) {
+      if (i < nj * ntab) {
+        const int j = i / ntab, t = i % ntab;
+        const size_t off = (size_t)sm.sIt[buf][j] * md.ldL;
+        if (t == 0) tma_row(sm.sS + j * FK_LDS, md.Wy + off, rowb, bar);
+        else if (t == 1 && ada) tma_row(sm.sAcc + j * FK_LDS, md.Wy_acc + off, rowb, bar);
+        else tma_row(sm.sVel + j * FK_LDS, md.Wy_vel + off, rowb, bar);
+      } else {
+        const int b = i - nj * ntab;
+        tma_row(sm.sTW + b * FK_LDS, md.Wy + (size_t)sm.sYit[buf][b] * md.ldL, rowb, bar);
+      }
     }
-    __syncwarp();
-    if (tid < nj) {
-      const size_t off = (size_t)sm.sIt[buf][tid] * md.ldL;
-      tma_row(sm.sS + tid * FK_LDS, md.Wy + off, rowb, bar);
-      if (ada) tma_row(sm.sAcc + tid * FK_LDS, md.Wy_acc + off, rowb, bar);
-      if (mom) tma_row(sm.sVel + tid * FK_LDS, md.Wy_vel + off, rowb, bar);
-    }
-    if (pw && tid < M) tma_row(sm.sTW + tid * FK_LDS, md.Wy + (size_t)sm.sYit[buf][tid] * md.ldL, rowb, bar);
+  }
+  if (false) {
   } else if (tid >= 64 && tid < 64 + FK_CT) {
     const int j = tid - 64;
     if (j < nj) {
@@ -200,7 +211,7 @@ constexpr int FK_W1 = 5;    // rz columns per CTA   (ceil(2*128 / 48) = 6 would 
 constexpr int FK_W2 = 3;    // h / dHr columns per CTA (L <= 144)
 
 // F1: rz = sigmoid(Wx0[X][L:3L] + Bh[L:3L] + H @ Wrz) for this CTA's FK_W1 columns; CTA 0 also writes Hold
-__device__ void fk_f1(const ModelDev& md, FastSmem& sm, int s, int cta) {
+__device__ void fk_f1(const ModelDev& md, FastSmem& sm, int s, int cta, const unsigned int* wait_ctr, unsigned int wait_target) {
   const LayerDev& ly = md.layer[0];
   const int M = md.wM[s], L = ly.L, ldL = ly.ldL, tid = threadIdx.x;
   const int c0 = cta * FK_W1;
@@ -214,14 +225,16 @@ __device__ void fk_f1(const ModelDev& md, FastSmem& sm, int s, int cta) {
     const int j = i / FK_LDS, k = i % FK_LDS;
     sm.gW[i] = (j < W && k < L) ? ly.Wrz[(size_t)k * ly.ld2 + c0 + j] : 0.f;
   }
-  // epilogue operands of thread (b, j): gathered input row element + bias
   const int b = tid & 31, jsel = tid >> 5;
-  float pre = 0.f;
-  if (jsel < W && b < M) pre = ly.Wx[(size_t)sm.gIdx[FK_B + b] * ly.ld3 + L + c0 + jsel] + ly.Bh[L + c0 + jsel];
   __syncthreads();
   float acc[FK_W1];
   fk_slab_dot<FK_W1>(acc, sm.gA, FK_LDS, sm.gW, L);
   const float v = fk_slab_reduce<FK_W1>(acc, sm.gW + 8 * FK_LDS, jsel);
+  // the gathered input rows may still be in flight on the helper CTAs (previous step's update): wait only now, after
+  // the H @ Wrz part, then fetch the epilogue operands (gathered row element + bias)
+  if (wait_ctr) { if (tid == 0) wait_ge(wait_ctr, wait_target); __syncthreads(); }
+  float pre = 0.f;
+  if (jsel < W && b < M) pre = ly.Wx[(size_t)sm.gIdx[FK_B + b] * ly.ld3 + L + c0 + jsel] + ly.Bh[L + c0 + jsel];
   if (jsel < W && b < M) {
     const int c = c0 + jsel;
     const float g = sigmoidf_(v + pre);
@@ -380,6 +393,80 @@ __device__ void fk_dense(const ModelDev& md, FastSmem& sm, int s, int cta) {
   }
 }
 
+// Input-row update of lane b on a non-GRU CTA, concurrent with the GRU backward: the CTA derives the da_r part of the
+// row gradient itself (da_r = (da_h @ Wh^T) * Hold * r (1-r), 100x100 MACs per row) so it only depends on B1.
+__device__ void fk_sparse_in(const ModelDev& md, FastSmem& sm, int s, int b) {
+  const LayerDev& ly = md.layer[0];
+  const int M = md.wM[s];
+  if (b >= M) return;
+  const uint8_t xf = md.wXflag[(size_t)s * md.B + b];
+  if (!(xf & 1)) return;                                // not the first position of its duplicate group
+  const int L = ly.L, ldL = ly.ldL, ld3 = ly.ld3, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int item = md.wX[(size_t)s * md.B + b];
+  const int* xnext = md.wXnext + (size_t)s * md.B;
+  if (tid == 0) { int n = 0; for (int bb = b; bb >= 0 && n < FK_B; bb = xnext[bb]) sm.gIdx[n++] = bb; sm.gIdx[FK_B] = n; }
+  __syncthreads();
+  const int nmem = sm.gIdx[FK_B];
+  for (int k = 0; k < nmem; k++) {                       // stage the members' gradient rows [da_h | . | da_z]
+    const int bb = sm.gIdx[k];
+    for (int c4 = tid; c4 < ld3 / 4; c4 += FK_THREADS) st4(sm.gA + k * 388 + c4 * 4, ld4(ly.dvec + (size_t)bb * ld3 + c4 * 4));
+  }
+  __syncthreads();
+  const int kq = ldL / 4;
+  for (int k = 0; k < nmem; k++) {
+    const int bb = sm.gIdx[k];
+    // this warp's rows c = warp + 16 u (u < 8 covers L <= 128): all Wh loads and the (Hold, r) scalars are issued first
+    float4 w[8]; float hr[8];
+    const float4 d = lane < kq ? ld4(sm.gA + k * 388 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int c = warp + FK_NW * u;
+      w[u] = (c < L && lane < kq) ? ld4(ly.Wh + (size_t)c * ldL + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      hr[u] = 0.f;
+      if (c < L && lane == 0) { const float r = ly.r[(size_t)bb * ldL + c]; hr[u] = ly.Hold[(size_t)bb * ldL + c] * r * (1.f - r); }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int c = warp + FK_NW * u;
+      float a = w[u].x * d.x;
+      a = fmaf(w[u].y, d.y, a); a = fmaf(w[u].z, d.z, a); a = fmaf(w[u].w, d.w, a);
+      a = warp_sum(a);
+      if (c < L && lane == 0) sm.gW[k * FK_LDS + c] = a * hr[u];
+    }
+  }
+  __syncthreads();
+  for (int k = 0; k < nmem; k++) for (int c = tid; c < L; c += FK_THREADS) sm.gA[k * 388 + L + c] = sm.gW[k * FK_LDS + c];
+  __syncthreads();
+  const bool ada = md.adapt == G4R_ADAPT_ADAGRAD, mom = md.mom > 0.f;
+  float* prow = ly.Wx + (size_t)item * ld3;
+  for (int c4 = tid; c4 < ld3 / 4; c4 += FK_THREADS) {
+    const float4 p0 = ld4(prow + c4 * 4);
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), v0 = a0, al = a0, vl = a0;
+    if (ada) a0 = ld4(ly.Wx_acc + (size_t)item * ld3 + c4 * 4);
+    if (mom) v0 = ld4(ly.Wx_vel + (size_t)item * ld3 + c4 * 4);
+    float4 ps = p0;
+    for (int k = 0; k < nmem; k++) {
+      const float4 g = ld4(sm.gA + k * 388 + c4 * 4);
+      float4 gs = g;
+      if (ada) {
+        al.x = a0.x + g.x * g.x; al.y = a0.y + g.y * g.y; al.z = a0.z + g.z * g.z; al.w = a0.w + g.w * g.w;
+        gs.x = __fdiv_rn(g.x, sqrtf(al.x + G4R_EPS_ADA)); gs.y = __fdiv_rn(g.y, sqrtf(al.y + G4R_EPS_ADA));
+        gs.z = __fdiv_rn(g.z, sqrtf(al.z + G4R_EPS_ADA)); gs.w = __fdiv_rn(g.w, sqrtf(al.w + G4R_EPS_ADA));
+      }
+      float4 d;
+      if (md.lmbd > 0.f) { d.x = md.lr * (gs.x + md.lmbd * p0.x); d.y = md.lr * (gs.y + md.lmbd * p0.y); d.z = md.lr * (gs.z + md.lmbd * p0.z); d.w = md.lr * (gs.w + md.lmbd * p0.w); }
+      else { d.x = md.lr * gs.x; d.y = md.lr * gs.y; d.z = md.lr * gs.z; d.w = md.lr * gs.w; }
+      if (mom) {
+        vl.x = md.mom * v0.x - d.x; vl.y = md.mom * v0.y - d.y; vl.z = md.mom * v0.z - d.z; vl.w = md.mom * v0.w - d.w;
+        ps.x += vl.x; ps.y += vl.y; ps.z += vl.z; ps.w += vl.w;
+      } else { ps.x -= d.x; ps.y -= d.y; ps.z -= d.z; ps.w -= d.w; }
+    }
+    st4(prow + c4 * 4, ps);
+    if (ada) st4(ly.Wx_acc + (size_t)item * ld3 + c4 * 4, al);
+    if (mom) st4(ly.Wx_vel + (size_t)item * ld3 + c4 * 4, vl);
+  }
+}
+
 // B1 (fast kernel): every CTA reduces a contiguous run of dL/dh elements; lanes = consecutive elements (coalesced),
 // warps = slices of the chunk partials, cross-warp sum in shared memory in fixed order; then da_h / da_z.
 __device__ void fk_b1(const ModelDev& md, FastSmem& sm, int s, int cta, int ncta) {
@@ -438,6 +525,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) k_fast(int slot, int n_steps, F
   const int kw = ldL / 4;
   uint64_t* bar = reinterpret_cast<uint64_t*>(&sm.mbar);
   unsigned int bar_epoch = 0, gepoch = 0, stats_target = 0;
+  const int in_ctas = min(B, ncta - FK_G);     // helper CTAs [FK_G, FK_G + in_ctas) update the gathered input rows
 #define FK_STAMP(k) do { if (tstamp && cta == 0 && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tstamp[(size_t)s * 16 + (k)] = t_; } } while (0)
   if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   fk_load_idx(md, sm, 0, n_steps, chunk, 0);
@@ -445,7 +533,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) k_fast(int slot, int n_steps, F
   fk_prefetch_rows(md, sm, 0, n_steps, 0, pw);
   // GRU forward of step 0
   if (gru) {
-    fk_f1(md, sm, 0, cta);
+    fk_f1(md, sm, 0, cta, nullptr, 0u);
     fk_group_barrier(fs, gepoch);
     fk_f2(md, sm, 0, cta);
     __syncthreads();
@@ -498,35 +586,55 @@ __global__ void __launch_bounds__(FK_THREADS, 1) k_fast(int slot, int n_steps, F
         }
       }
       FK_STAMP(9);
-      __syncthreads();                          // sT complete
-      const int b = lane;
-      float m = -INFINITY, Z = 0.f, A = 0.f, Q = 0.f, D = 0.f, T = 0.f, has = 0.f;
-      if (b < M) {
-        const int tc = sm.sTc[buf][b];
-        const float t = pw ? sm.sT[b] : 0.f;
 #pragma unroll
-        for (int q = 0; q < FK_Q; q++) {
-          const int jj = warp + q * FK_NW;
-          if (jj < nj) {
-            const float o = accq[q] + sm.sBias[jj];
-            sm.sO[jj * FK_B + b] = o;
-            stat_add_elem(md, o, tc == cb + jj, t, m, Z, A, Q, D, T, has);
-          }
-        }
+      for (int q = 0; q < FK_Q; q++) {
+        const int jj = warp + q * FK_NW;
+        if (jj < nj && lane < M) sm.sO[jj * FK_B + lane] = accq[q] + sm.sBias[jj];
       }
-      float* pp = sm.sPart + ((size_t)warp * FK_B + lane) * 8;
-      pp[0] = m; pp[1] = Z; pp[2] = A; pp[3] = Q; pp[4] = D; pp[5] = T; pp[6] = has;
-      __syncthreads();
-      if (has_chunk && tid < FK_B && tid < M) {
-        float rm = -INFINITY, rZ = 0.f, rA = 0.f, rQ = 0.f, rD = 0.f, rT = 0.f, rh = 0.f;
+      __syncthreads();                          // sT and sO complete
+      // chunk statistics of lane b by 16 threads (column jj = sub, sub + 16): row max first, then plain sums -- one expf
+      // per column instead of an exp-rescaling merge per element
+      {
+        const int b = tid >> 4, sub = tid & 15;            // FK_THREADS / 16 == FK_B lanes
+        const bool okb = b < M;
+        const int tc = okb ? sm.sTc[buf][b] : -1;
+        const float t = (pw && okb) ? sm.sT[b] : 0.f;
+        float yv[2]; bool use[2], ist[2];
+        float mloc = -INFINITY;
+        const bool smx = loss_softmaxneg(md.loss), xe = (md.loss == G4R_LOSS_XE || md.loss == G4R_LOSS_XE_LOGIT);
 #pragma unroll
-        for (int w = 0; w < FK_NW; w++) {
-          const float* q = sm.sPart + ((size_t)w * FK_B + tid) * 8;
-          stat_combine(md, rm, rZ, rA, rQ, rD, rT, rh, q[0], q[1], q[2], q[3], q[4], q[5], q[6]);
+        for (int q = 0; q < 2; q++) {
+          const int jj = sub + 16 * q;
+          use[q] = okb && jj < nj;
+          ist[q] = use[q] && (tc == cb + jj);
+          const float o = use[q] ? sm.sO[jj * FK_B + b] : 0.f;
+          yv[q] = xe ? o : act_fwd(md.fact, o);
+          if (use[q] && (xe || (smx && !ist[q]))) mloc = fmaxf(mloc, yv[q]);
         }
-        float* st = md.stat + ((size_t)chunk * md.B + tid) * G4R_NSTAT;
-        st4(st, make_float4(rm, rZ, rA, rQ));
-        st4(st + 4, make_float4(rD, rT, rh, pw ? sm.sT[tid] : 0.f));
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, o));
+        float Z = 0.f, A = 0.f, Q = 0.f, D = 0.f, T = 0.f, has = 0.f;
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          if (!use[q]) continue;
+          const float y = yv[q];
+          if (ist[q]) has = 1.f;
+          if (xe) { Z += expf(y - mloc); if (ist[q]) T = y; }
+          else if (md.loss == G4R_LOSS_BPR_MAX) { if (!ist[q]) { const float e = expf(y - mloc), sg = sigmoidf_(t - y); Z += e; A += sg * e; Q += y * y * e; D += sg * (1.f - sg) * e; } }
+          else if (md.loss == G4R_LOSS_TOP1_MAX) { if (!ist[q]) { const float e = expf(y - mloc), a1 = sigmoidf_(y - t), b1 = sigmoidf_(y * y); Z += e; A += (a1 + b1) * e; D += a1 * (1.f - a1) * e; } }
+          else if (md.loss == G4R_LOSS_BPR) { const float sg = sigmoidf_(t - y); A += -logf(sg); if (!ist[q]) D += 1.f - sg; }
+          else { const float a1 = sigmoidf_(y - t), b1 = sigmoidf_(y * y); A += a1 + b1; if (!ist[q]) D += a1 * (1.f - a1); }
+        }
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+          Z += __shfl_xor_sync(0xffffffffu, Z, o); A += __shfl_xor_sync(0xffffffffu, A, o); Q += __shfl_xor_sync(0xffffffffu, Q, o);
+          D += __shfl_xor_sync(0xffffffffu, D, o); T += __shfl_xor_sync(0xffffffffu, T, o); has += __shfl_xor_sync(0xffffffffu, has, o);
+        }
+        if (has_chunk && okb && sub == 0) {
+          float* st = md.stat + ((size_t)chunk * md.B + b) * G4R_NSTAT;
+          st4(st, make_float4(mloc, Z, A, Q));
+          st4(st + 4, make_float4(D, T, has > 0.f ? 1.f : 0.f, pw ? t : 0.f));
+        }
       }
     }
     // ---- barrier B2, then lane b's statistics are combined by CTA b (all lanes in parallel, fixed merge order) ----
@@ -694,11 +802,10 @@ __global__ void __launch_bounds__(FK_THREADS, 1) k_fast(int slot, int n_steps, F
       fk_group_barrier(fs, gepoch);
       FK_STAMP(5);
       fk_dense(md, sm, s, cta);
-      for (int b = FK_G - 1 - cta; b < B; b += FK_G) phase_sparse_in(md, s, b);
       fk_group_barrier(fs, gepoch);
       FK_STAMP(6);
       if (s + 1 < n_steps) {
-        fk_f1(md, sm, s + 1, cta);
+        fk_f1(md, sm, s + 1, cta, &fs->in_done, (unsigned int)(s + 1) * (unsigned int)in_ctas);   // waits for the helper CTAs' input-row updates
         fk_group_barrier(fs, gepoch);
         FK_STAMP(7);
         fk_f2(md, sm, s + 1, cta);
@@ -706,6 +813,12 @@ __global__ void __launch_bounds__(FK_THREADS, 1) k_fast(int slot, int n_steps, F
         if (tid == 0) red_release_add(&fs->h_ready, 1u);
       }
       FK_STAMP(8);
+    } else if (cta < FK_G + in_ctas) {
+      if (tid == 0) wait_ge(&fs->b1_done, (unsigned int)(s + 1) * (unsigned int)ncta);
+      __syncthreads();
+      for (int b = cta - FK_G; b < B; b += in_ctas) { fk_sparse_in(md, sm, s, b); __syncthreads(); }
+      __syncthreads();
+      if (tid == 0) red_release_add(&fs->in_done, 1u);
     }
   }
 #undef FK_STAMP

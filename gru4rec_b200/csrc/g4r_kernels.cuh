@@ -42,6 +42,7 @@ struct FastSync {                   // one counter per 128-byte line
   unsigned int h_ready;  unsigned int p2[31];
   unsigned int b1_done;  unsigned int p3[31];
   unsigned int grp;      unsigned int p4[31];
+  unsigned int in_done;  unsigned int p5[31];
 };
 struct GridBar { unsigned int count; unsigned int gen; unsigned int pad[30]; };   // grid barrier state (persistent mode)
 

@@ -444,7 +444,7 @@ extern "C" int g4r_create(const g4r_config* cfg, void* device_workspace, size_t 
     cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastSmem));
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fast, FK_THREADS, sizeof(FastSmem));
-    h->fast_ok = h->pk_blocks > 0 && per_sm >= 1 && m.mode == 0 && m.n_layers == 1 && m.ldL <= 128 && m.B <= FK_B && h->n_sm >= FK_G && m.NCH <= 160 &&
+    h->fast_ok = h->pk_blocks > 0 && per_sm >= 1 && m.mode == 0 && m.n_layers == 1 && m.ldL <= 128 && m.B <= FK_B && h->n_sm >= FK_G + 1 && m.NCH <= 160 &&
                  (m.adapt == G4R_ADAPT_ADAGRAD ? m.Wy_acc != nullptr : true);
     cudaMallocHost(&h->hFlags, 4 * sizeof(int));
   }

@@ -10,7 +10,39 @@
 // the device by rank arithmetic (k_mg_plan), off the critical path.
 // Included from g4r_lib.cu.  Modes: no-embedding and separate-embedding (constrained embedding: next round).
 #pragma once
-#include <nccl.h>
+#include <nccl.h>     // types only: the library is resolved at run time (dlopen) so that libg4r.so has no load-time
+#include <dlfcn.h>    // dependency on a particular libnccl (PyTorch bundles its own libnccl.so.2)
+
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static bool nccl_load() {
+  if (g_nccl.lib) return true;
+  void* l = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);     // already-loaded copy (e.g. PyTorch's) is reused by SONAME
+  if (!l) l = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!l) return false;
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(l, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(l, "ncclCommInitRank");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(l, "ncclCommDestroy");
+  g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(l, "ncclAllGather");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(l, "ncclAllReduce");
+  g_nccl.GroupStart = (decltype(g_nccl.GroupStart))dlsym(l, "ncclGroupStart");
+  g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))dlsym(l, "ncclGroupEnd");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(l, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllGather || !g_nccl.AllReduce || !g_nccl.GroupStart ||
+      !g_nccl.GroupEnd || !g_nccl.GetErrorString) return false;
+  g_nccl.lib = l;
+  return true;
+}
 
 
 // merged position of every (rank, column): own index + for each other rank the number of its columns that sort before
@@ -225,11 +257,12 @@ struct MgHost {
 };
 static std::map<g4r_handle*, MgHost> g_mg;
 
-#define NC(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) { h->err = std::string(#call) + ": " + ncclGetErrorString(r_); return G4R_ERR_CUDA; } } while (0)
+#define NC(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) { h->err = std::string(#call) + ": " + g_nccl.GetErrorString(r_); return G4R_ERR_CUDA; } } while (0)
 
 extern "C" int g4r_mg_unique_id(char* out128) {
+  if (!nccl_load()) return G4R_ERR_STATE;
   ncclUniqueId id;
-  if (ncclGetUniqueId(&id) != ncclSuccess) return G4R_ERR_CUDA;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return G4R_ERR_CUDA;
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
   memcpy(out128, &id, 128);
   return G4R_OK;
@@ -241,10 +274,11 @@ extern "C" int g4r_mg_init(g4r_handle* h, const char* id128) {
   if (R < 2) FAIL(G4R_ERR_INVALID, "world_size < 2");
   if (h->md.mode == 2) FAIL(G4R_ERR_INVALID, "multi-GPU with constrained_embedding is not implemented yet");
   if (!h->mg_alloc) FAIL(G4R_ERR_STATE, "handle was created without multi-GPU buffers");
+  if (!nccl_load()) FAIL(G4R_ERR_STATE, "libnccl.so.2 could not be loaded");
   cudaSetDevice(h->cfg.device);
   MgHost& m = g_mg[h];
   ncclUniqueId id; memcpy(&id, id128, 128);
-  NC(ncclCommInitRank(&m.comm, R, id, rank));
+  NC(g_nccl.CommInitRank(&m.comm, R, id, rank));
   m.dev = h->mgdev;
   m.ready = true;
   h->md.export_only = 1;
@@ -257,7 +291,7 @@ static void mg_release(g4r_handle* h) {
   if (it != g_mg.end()) {
     if (it->second.graphU) cudaGraphExecDestroy(it->second.graphU);
     if (it->second.graph1) cudaGraphExecDestroy(it->second.graph1);
-    if (it->second.comm) ncclCommDestroy(it->second.comm);
+    if (it->second.comm) g_nccl.CommDestroy(it->second.comm);
     g_mg.erase(it);
   }
 }
@@ -270,11 +304,11 @@ static int mg_run_window(g4r_handle* h, int64_t n) {
   cudaStream_t st = h->stream;
   const int R = mg.R, NP = md.NP, B = md.B;
   // window metadata of all ranks (model independent): sorted columns, batch sizes, inputs
-  NC(ncclGroupStart());
-  NC(ncclAllGather(md.pItem, mg.gItem, (size_t)MG_CAP * NP, ncclInt32, m.comm, st));
-  NC(ncclAllGather(md.wM, mg.gM, (size_t)MG_CAP, ncclInt32, m.comm, st));
-  NC(ncclAllGather(md.wX, mg.gX, (size_t)MG_CAP * B, ncclInt32, m.comm, st));
-  NC(ncclGroupEnd());
+  NC(g_nccl.GroupStart());
+  NC(g_nccl.AllGather(md.pItem, mg.gItem, (size_t)MG_CAP * NP, ncclInt32, m.comm, st));
+  NC(g_nccl.AllGather(md.wM, mg.gM, (size_t)MG_CAP, ncclInt32, m.comm, st));
+  NC(g_nccl.AllGather(md.wX, mg.gX, (size_t)MG_CAP * B, ncclInt32, m.comm, st));
+  NC(g_nccl.GroupEnd());
   k_mg_plan<<<dim3((R * NP + 255) / 256, (unsigned)n), 256, 0, st>>>(md, mg, (int)n);
   int npow2 = 1; while (npow2 < R * B) npow2 <<= 1;
   k_mg_plan2<<<(unsigned)n, 256, (size_t)npow2 * 8, st>>>(md, mg, (int)n);
@@ -287,12 +321,12 @@ static int mg_run_window(g4r_handle* h, int64_t n) {
   // one lock-step mini-batch: local gradients -> NCCL exchange -> merged update (window-relative step = *base + off)
   auto enqueue = [&](const int* base, int off) -> int {
     enqueue_train_step(h, base, off);                     // export mode: gradients only
-    NC(ncclGroupStart());
-    NC(ncclAllGather(md.DSY, mg.DSYall, (size_t)NP * md.ldL, ncclFloat32, m.comm, st));
-    NC(ncclAllGather(md.DBY, mg.DBYall, (size_t)NP, ncclFloat32, m.comm, st));
-    NC(ncclAllGather(in_local, mg.INall, (size_t)B * in_ld, ncclFloat32, m.comm, st));
-    NC(ncclAllReduce(mg.gradFlat, mg.gradFlat, mg.gradCount, ncclFloat32, ncclSum, m.comm, st));
-    NC(ncclGroupEnd());
+    NC(g_nccl.GroupStart());
+    NC(g_nccl.AllGather(md.DSY, mg.DSYall, (size_t)NP * md.ldL, ncclFloat32, m.comm, st));
+    NC(g_nccl.AllGather(md.DBY, mg.DBYall, (size_t)NP, ncclFloat32, m.comm, st));
+    NC(g_nccl.AllGather(in_local, mg.INall, (size_t)B * in_ld, ncclFloat32, m.comm, st));
+    NC(g_nccl.AllReduce(mg.gradFlat, mg.gradFlat, mg.gradCount, ncclFloat32, ncclSum, m.comm, st));
+    NC(g_nccl.GroupEnd());
     k_mg_apply_rows<<<md.NCH, 256, 0, st>>>(h->slot, mg, base, off);
     k_mg_apply_in<<<R * B, 128, 0, st>>>(h->slot, mg, base, off);
     for (const MgTensor& t : tens) k_mg_apply_dense<<<(t.count + 255) / 256, 256, 0, st>>>(h->slot, t.p, t.acc, t.vel, mg.gradFlat + t.goff, t.count);

@@ -337,6 +337,16 @@ class Engine(object):
 
     def train_steps(self, sched, first=0, n=None):
         n = sched.n_steps - first if n is None else n
+        if self.cfg.world_size > 1:
+            # ranks advance in lock step (one merged update per mini-batch): a different n would dead-lock the collectives
+            import torch
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                dev = 'cuda' if dist.get_backend() == 'nccl' else 'cpu'
+                t = torch.tensor([n, -n], dtype=torch.int64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                if int(t[0]) != n or int(-t[1]) != n:
+                    raise ValueError('train_steps: every rank must run the same number of steps (got %d, range %d..%d)' % (n, int(t[0]), int(-t[1])))
         costs = np.empty(n, dtype=np.float32)
         nan_step = C.c_int64(-1)
         rc = self.lib.g4r_train_steps(self.h, sched.h, first, n, _ptr(costs), C.byref(nan_step))

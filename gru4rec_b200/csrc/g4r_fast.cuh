@@ -73,7 +73,7 @@ struct FastSmem {
   alignas(8) unsigned long long mbar;
   // GRU role: thin-slab phases (every GRU CTA owns a few output columns / rows and stages the full 32-lane operand)
   alignas(16) float gA[FK_B * 388];             // staged [32 x <=384] operand (H, Hold*r, da_h, dvec)
-  alignas(16) float gW[8 * FK_LDS + FK_NW * FK_B * 5];      // this CTA's weight slab (<= 8 columns/rows of length <= 128) + reduction scratch
+  alignas(16) float gW[8 * FK_LDS + FK_NW * FK_B * 5 + 16 * FK_B];      // this CTA's weight slab (<= 8 columns/rows of length <= 128) + reduction scratch
   int gIdx[3 * FK_B];               // slot, item, flags of the lanes
 };
 
@@ -393,50 +393,20 @@ __device__ void fk_dense(const ModelDev& md, FastSmem& sm, int s, int cta) {
   }
 }
 
-// Input-row update of lane b on a non-GRU CTA, concurrent with the GRU backward: the CTA derives the da_r part of the
-// row gradient itself (da_r = (da_h @ Wh^T) * Hold * r (1-r), 100x100 MACs per row) so it only depends on B1.
+// Input-row update of lane b on a helper (non-GRU) CTA, concurrent with the dense update of the GRU group: it starts when
+// the GRU group has passed its B2 barrier (dvec complete) and only touches Wx0 rows, which the dense phase never reads.
 __device__ void fk_sparse_in(const ModelDev& md, FastSmem& sm, int s, int b) {
   const LayerDev& ly = md.layer[0];
   const int M = md.wM[s];
   if (b >= M) return;
   const uint8_t xf = md.wXflag[(size_t)s * md.B + b];
   if (!(xf & 1)) return;                                // not the first position of its duplicate group
-  const int L = ly.L, ldL = ly.ldL, ld3 = ly.ld3, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ld3 = ly.ld3, tid = threadIdx.x;
   const int item = md.wX[(size_t)s * md.B + b];
   const int* xnext = md.wXnext + (size_t)s * md.B;
   if (tid == 0) { int n = 0; for (int bb = b; bb >= 0 && n < FK_B; bb = xnext[bb]) sm.gIdx[n++] = bb; sm.gIdx[FK_B] = n; }
   __syncthreads();
   const int nmem = sm.gIdx[FK_B];
-  for (int k = 0; k < nmem; k++) {                       // stage the members' gradient rows [da_h | . | da_z]
-    const int bb = sm.gIdx[k];
-    for (int c4 = tid; c4 < ld3 / 4; c4 += FK_THREADS) st4(sm.gA + k * 388 + c4 * 4, ld4(ly.dvec + (size_t)bb * ld3 + c4 * 4));
-  }
-  __syncthreads();
-  const int kq = ldL / 4;
-  for (int k = 0; k < nmem; k++) {
-    const int bb = sm.gIdx[k];
-    // this warp's rows c = warp + 16 u (u < 8 covers L <= 128): all Wh loads and the (Hold, r) scalars are issued first
-    float4 w[8]; float hr[8];
-    const float4 d = lane < kq ? ld4(sm.gA + k * 388 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-      const int c = warp + FK_NW * u;
-      w[u] = (c < L && lane < kq) ? ld4(ly.Wh + (size_t)c * ldL + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      hr[u] = 0.f;
-      if (c < L && lane == 0) { const float r = ly.r[(size_t)bb * ldL + c]; hr[u] = ly.Hold[(size_t)bb * ldL + c] * r * (1.f - r); }
-    }
-#pragma unroll
-    for (int u = 0; u < 8; u++) {
-      const int c = warp + FK_NW * u;
-      float a = w[u].x * d.x;
-      a = fmaf(w[u].y, d.y, a); a = fmaf(w[u].z, d.z, a); a = fmaf(w[u].w, d.w, a);
-      a = warp_sum(a);
-      if (c < L && lane == 0) sm.gW[k * FK_LDS + c] = a * hr[u];
-    }
-  }
-  __syncthreads();
-  for (int k = 0; k < nmem; k++) for (int c = tid; c < L; c += FK_THREADS) sm.gA[k * 388 + L + c] = sm.gW[k * FK_LDS + c];
-  __syncthreads();
   const bool ada = md.adapt == G4R_ADAPT_ADAGRAD, mom = md.mom > 0.f;
   float* prow = ly.Wx + (size_t)item * ld3;
   for (int c4 = tid; c4 < ld3 / 4; c4 += FK_THREADS) {
@@ -446,7 +416,7 @@ __device__ void fk_sparse_in(const ModelDev& md, FastSmem& sm, int s, int b) {
     if (mom) v0 = ld4(ly.Wx_vel + (size_t)item * ld3 + c4 * 4);
     float4 ps = p0;
     for (int k = 0; k < nmem; k++) {
-      const float4 g = ld4(sm.gA + k * 388 + c4 * 4);
+      const float4 g = ld4(ly.dvec + (size_t)sm.gIdx[k] * ld3 + c4 * 4);
       float4 gs = g;
       if (ada) {
         al.x = a0.x + g.x * g.x; al.y = a0.y + g.y * g.y; al.z = a0.z + g.z * g.z; al.w = a0.w + g.w * g.w;
@@ -799,7 +769,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) k_fast(int slot, int n_steps, F
       if (tid == 0) wait_ge(&fs->b1_done, (unsigned int)(s + 1) * (unsigned int)ncta);
       __syncthreads();
       fk_b2(md, sm, s, cta);
-      fk_group_barrier(fs, gepoch);
+      fk_group_barrier(fs, gepoch);      // epoch 3*s + 2: all of dvec (da_r included) is complete -> the helper CTAs poll this counter
       FK_STAMP(5);
       fk_dense(md, sm, s, cta);
       fk_group_barrier(fs, gepoch);
@@ -814,7 +784,8 @@ __global__ void __launch_bounds__(FK_THREADS, 1) k_fast(int slot, int n_steps, F
       }
       FK_STAMP(8);
     } else if (cta < FK_G + in_ctas) {
-      if (tid == 0) wait_ge(&fs->b1_done, (unsigned int)(s + 1) * (unsigned int)ncta);
+      // the GRU group's barrier after B2 is its (3 s + 2)-th group barrier (1 in the prologue, then B2 / dense / f1 per step)
+      if (tid == 0) wait_ge(&fs->grp, (unsigned int)(3 * s + 2) * FK_G);
       __syncthreads();
       for (int b = cta - FK_G; b < B; b += in_ctas) { fk_sparse_in(md, sm, s, b); __syncthreads(); }
       __syncthreads();

@@ -133,13 +133,17 @@ def test_shrinking_batch_and_slots(step_mode):
     compare_weights(eng, m, rtol=3e-3, atol=3e-5)
 
 
-@pytest.mark.parametrize('loss,fact,alpha', [('bpr-max', 'elu-0.5', 0.0), ('cross-entropy', 'softmax', 0.75), ('top1-max', 'tanh', 1.0)])
-def test_headline_shape_role_specialised_kernel(loss, fact, alpha):
+@pytest.mark.parametrize('loss,fact,alpha,extra', [('bpr-max', 'elu-0.5', 0.0, {}), ('cross-entropy', 'softmax', 0.75, {}), ('top1-max', 'tanh', 1.0, {}),
+                                                   ('bpr-max', 'elu-1', 0.0, dict(dropout_p_hidden=0.25, lmbd=0.0005)),
+                                                   ('cross-entropy', 'softmax', 0.0, dict(logq=1.0, momentum=0.0)),
+                                                   ('bpr', 'linear', 0.0, dict(adapt=None, learning_rate=0.01))])
+def test_headline_shape_role_specialised_kernel(loss, fact, alpha, extra):
     """B=32, GRU(100), 2048 samples (BASELINE configs[1] shape) through step_mode 2; heavy duplicates with alpha=1."""
     from gru4rec_b200.synth import make_session_arrays
     n_items = 3000
     mk = dict(layers=[100], batch_size=32, n_sample=2048, loss=loss, final_act=fact, learning_rate=0.05, momentum=0.3, sample_alpha=alpha,
               dropout_p_hidden=0.1 if loss == 'top1-max' else 0.0)
+    mk.update(extra)
     items, offset, order, supports = make_session_arrays(n_items, 40000, seed=5)
     rows = 20
     eng, m, _, rs = make_pair(n_items, mk, n_store_rows=0, seed=3, randomize_state=False, step_mode=2)
@@ -147,6 +151,10 @@ def test_headline_shape_role_specialised_kernel(loss, fact, alpha):
     eng = _lib.Engine(make_cfg(n_items, mk, sample_store=rows * 2048, step_mode=2))
     from gpu_utils import push_weights
     push_weights(eng, m)
+    if mk.get('logq', 0):
+        P0 = np.maximum(supports, 1).astype(np.float32)
+        m.P0 = P0
+        eng.set_logq_support(P0)
     P = orc.sampling_cdf(supports, alpha).astype(np.float32)
     u = rs.rand(rows * 2048).astype(np.float32)
     eng.set_sampling_cdf(P)

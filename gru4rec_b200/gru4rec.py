@@ -91,6 +91,34 @@ class GRU4Rec:
         self._engine = None
         self._host = None                # numpy copies of the parameters when no engine is alive
 
+
+    # ---- names that pickles written by the reference class refer to (gru4rec.py:136-161, 189-248) ----------------------
+    # The reference pickles `self` including bound methods (loss_function = self.bpr_max, final_activation =
+    # self.Elu(a).execute, ...).  These stubs make such pickles load into this class; the Theano graph builders themselves
+    # have no counterpart here (the device kernels are selected from the `loss` / `final_act` / `hidden_act` strings).
+    def _graph_builder_stub(self, *a, **k):
+        raise NotImplementedError('Theano graph builders are not part of the B200 implementation')
+    cross_entropy = cross_entropy_logits = bpr = bpr_max = top1 = top1_max = _graph_builder_stub
+    linear = tanh = softmax = softmax_logit = softmax_neg = relu = sigmoid = _graph_builder_stub
+
+    class Selu:
+        def __init__(self, lmbd=1.0, alpha=1.0):
+            self.lmbd = lmbd; self.alpha = alpha
+        def execute(self, X):
+            raise NotImplementedError('Theano graph builders are not part of the B200 implementation')
+
+    class Elu:
+        def __init__(self, alpha=1.0):
+            self.alpha = alpha
+        def execute(self, X):
+            raise NotImplementedError('Theano graph builders are not part of the B200 implementation')
+
+    class LeakyReLU:
+        def __init__(self, leak=0.0):
+            self.leak = leak
+        def execute(self, X):
+            raise NotImplementedError('Theano graph builders are not part of the B200 implementation')
+
     # ---- same validation behaviour as the reference setters (gru4rec.py:136-161) ----
     def set_loss_function(self, loss):
         if loss not in ('cross-entropy', 'bpr', 'bpr-max', 'top1', 'top1-max', 'xe_logit'):
@@ -433,6 +461,9 @@ class GRU4Rec:
         return st
 
     def __setstate__(self, st):
+        st = dict(st)
+        for k in ('loss_function', 'final_activation', 'hidden_activation'):   # bound Theano graph builders in reference pickles
+            st.pop(k, None)
         self.__dict__.update(st)
         n = len(self.layers)
         host = {}

@@ -155,6 +155,9 @@ def run_one(name, dkw, mkw, fkw):
             arr[s, :mk.shape[0]] = mk
         out['dropmask_site%d' % j] = arr
     out['epoch_loss'] = np.array(epoch_loss, dtype=np.float64)
+    if name == 'bprmax_none':      # a model pickle written by the REFERENCE class (gru4rec.py:742-767), for the loadmodel compatibility test
+        del gru.init                # instance attribute installed above to capture the initial weights (not picklable)
+        gru.savemodel(os.path.join(ROOT, 'tests', 'golden', name + '.refmodel.pickle'))
     # evaluation through the reference's evaluate_gpu (batch_size chosen small to exercise lane replacement)
     for mode in ('standard', 'conservative'):
         buf = io.StringIO()

@@ -186,3 +186,17 @@ def test_run_py_cli(tmp_path):
     r1 = [l for l in out.stdout.splitlines() if l.startswith('Recall@20')][0]
     r2 = [l for l in out2.stdout.splitlines() if l.startswith('Recall@20')][0]
     assert r1 == r2
+
+
+def test_reference_written_pickle_evaluates_on_device():
+    """loadmodel() of a pickle written by the reference class, then evaluate_gpu: the reference's own Recall/MRR."""
+    import gru4rec
+    import evaluation
+    from golden_utils import GOLDEN_DIR
+    g = load_golden('bprmax_none')
+    _, te = frames(g)
+    m = gru4rec.GRU4Rec.loadmodel(os.path.join(GOLDEN_DIR, 'bprmax_none.refmodel.pickle'))
+    with contextlib.redirect_stdout(io.StringIO()):
+        rec, mrr = evaluation.evaluate_gpu(m, te.copy(), cut_off=[1, 5, 20], batch_size=7, mode='standard')
+    np.testing.assert_allclose(rec, g['eval_standard_recall'], rtol=1e-4, atol=1e-9)
+    np.testing.assert_allclose(mrr, g['eval_standard_mrr'], rtol=1e-4, atol=1e-9)

@@ -107,3 +107,18 @@ def test_mrg_constants_self_consistency():
     assert (mpow(A2, 2 ** 72, orc.M2) == orc.A2p72.astype(object)).all()
     assert (mpow(A1, 2 ** 134, orc.M1) == orc.A1p134.astype(object)).all()
     assert (mpow(A2, 2 ** 134, orc.M2) == orc.A2p134.astype(object)).all()
+
+
+def test_loadmodel_reads_reference_written_pickle():
+    """A pickle written by the REFERENCE class (tests/golden/bprmax_none.refmodel.pickle, made by oracle/make_golden.py
+    under the Theano shim: class path gru4rec.GRU4Rec, bound graph-builder methods, NumPy weights) loads into this class."""
+    import gru4rec
+    from golden_utils import load_golden, GOLDEN_DIR
+    g = load_golden('bprmax_none')
+    m = gru4rec.GRU4Rec.loadmodel(os.path.join(GOLDEN_DIR, 'bprmax_none.refmodel.pickle'))
+    assert type(m).__module__ == 'gru4rec_b200.gru4rec'
+    assert m.layers == [12] and m.loss == 'bpr-max' and m.final_act == 'elu-0.5' and m.n_items == int(g['n_items'])
+    np.testing.assert_array_equal(m._host['Wy'], g['final_Wy'])
+    np.testing.assert_array_equal(m._host['Wx0'], g['final_Wx0'])
+    assert list(m.itemidmap.index.values) == list(g['itemidmap_index'])
+    assert m._engine is None          # no device work until predict / evaluate is called

@@ -96,10 +96,17 @@ class GRU4Rec:
     # The reference pickles `self` including bound methods (loss_function = self.bpr_max, final_activation =
     # self.Elu(a).execute, ...).  These stubs make such pickles load into this class; the Theano graph builders themselves
     # have no counterpart here (the device kernels are selected from the `loss` / `final_act` / `hidden_act` strings).
-    def _graph_builder_stub(self, *a, **k):
-        raise NotImplementedError('Theano graph builders are not part of the B200 implementation')
-    cross_entropy = cross_entropy_logits = bpr = bpr_max = top1 = top1_max = _graph_builder_stub
-    linear = tanh = softmax = softmax_logit = softmax_neg = relu = sigmoid = _graph_builder_stub
+    def _make_stub(name):
+        def stub(self, *a, **k):
+            raise NotImplementedError('Theano graph builders are not part of the B200 implementation')
+        stub.__name__ = name            # bound methods are pickled by name: it must be the reference's method name
+        stub.__qualname__ = 'GRU4Rec.' + name
+        return stub
+    cross_entropy = _make_stub('cross_entropy'); cross_entropy_logits = _make_stub('cross_entropy_logits')
+    bpr = _make_stub('bpr'); bpr_max = _make_stub('bpr_max'); top1 = _make_stub('top1'); top1_max = _make_stub('top1_max')
+    linear = _make_stub('linear'); tanh = _make_stub('tanh'); softmax = _make_stub('softmax'); softmax_logit = _make_stub('softmax_logit')
+    softmax_neg = _make_stub('softmax_neg'); relu = _make_stub('relu'); sigmoid = _make_stub('sigmoid')
+    del _make_stub
 
     class Selu:
         def __init__(self, lmbd=1.0, alpha=1.0):
@@ -458,7 +465,22 @@ class GRU4Rec:
         st['By'] = host['By']
         if 'E' in host:
             st['E'] = host['E']
+        # what the reference class needs after unpickling (its __init__ is not run): the bound graph builders, pickled by
+        # name (gru4rec.py:136-161) -- with this class registered as gru4rec.GRU4Rec the reference resolves its own methods
+        st['loss_function'] = getattr(self, {'cross-entropy': 'cross_entropy', 'bpr': 'bpr', 'bpr-max': 'bpr_max', 'top1': 'top1',
+                                             'top1-max': 'top1_max', 'xe_logit': 'cross_entropy_logits'}[self.loss])
+        st['final_activation'] = self._act_object(self.final_act)
+        st['hidden_activation'] = self._act_object(self.hidden_act)
+        for k in ('device', 'dropout_seed', 'eval_lanes', 'step_mode', '_engine_eval_lanes', 'predict', 'predict_batch', 'current_session'):
+            st.pop(k, None)
+        st['predict'] = None
         return st
+
+    def _act_object(self, name):
+        if name.startswith('leaky-'): return self.LeakyReLU(float(name.split('-')[1])).execute
+        if name.startswith('elu-'): return self.Elu(float(name.split('-')[1])).execute
+        if name.startswith('selu-'): return self.Selu(*[float(x) for x in name.split('-')[1:]]).execute
+        return getattr(self, name)
 
     def __setstate__(self, st):
         st = dict(st)
@@ -490,3 +512,19 @@ class GRU4Rec:
     @classmethod
     def loadmodel(cls, fname):
         return pd.read_pickle(fname)
+
+
+# Pickles name the class by module path.  The reference's models are `gru4rec.GRU4Rec`; registering this class under the
+# same path makes pickles interchangeable in both directions (reference-written pickles load here; pickles written here
+# load into the reference class, whose own graph builders are resolved by name).
+GRU4Rec.__module__ = 'gru4rec'
+GRU4Rec.__qualname__ = 'GRU4Rec'
+for _n in ('Selu', 'Elu', 'LeakyReLU'):
+    getattr(GRU4Rec, _n).__module__ = 'gru4rec'
+    getattr(GRU4Rec, _n).__qualname__ = 'GRU4Rec.' + _n
+import sys as _sys
+if 'gru4rec' not in _sys.modules:
+    import types as _types
+    _m = _types.ModuleType('gru4rec')
+    _m.GRU4Rec = GRU4Rec
+    _sys.modules['gru4rec'] = _m

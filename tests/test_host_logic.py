@@ -116,9 +116,50 @@ def test_loadmodel_reads_reference_written_pickle():
     from golden_utils import load_golden, GOLDEN_DIR
     g = load_golden('bprmax_none')
     m = gru4rec.GRU4Rec.loadmodel(os.path.join(GOLDEN_DIR, 'bprmax_none.refmodel.pickle'))
-    assert type(m).__module__ == 'gru4rec_b200.gru4rec'
+    from gru4rec_b200.gru4rec import GRU4Rec as B200Class
+    assert type(m) is B200Class
     assert m.layers == [12] and m.loss == 'bpr-max' and m.final_act == 'elu-0.5' and m.n_items == int(g['n_items'])
     np.testing.assert_array_equal(m._host['Wy'], g['final_Wy'])
     np.testing.assert_array_equal(m._host['Wx0'], g['final_Wx0'])
     assert list(m.itemidmap.index.values) == list(g['itemidmap_index'])
     assert m._engine is None          # no device work until predict / evaluate is called
+
+
+def test_pickle_written_here_loads_into_the_reference_class(tmp_path):
+    """savemodel() of this class -> the REFERENCE's GRU4Rec.loadmodel + evaluate_gpu (run on the Theano shim) reproduce the
+    oracle's Recall/MRR.  Needs /root/reference (not present on the GPU box)."""
+    import subprocess, sys, json
+    if not os.path.exists('/root/reference/gru4rec.py'):
+        pytest.skip('reference tree not available')
+    import gru4rec
+    import pandas as pd
+    from golden_utils import load_golden, frames, init_weights
+    g = load_golden('bprmax_none')
+    mk = g['model_kwargs']
+    _, te = frames(g)
+    m = gru4rec.GRU4Rec(**mk)
+    m.n_items = int(g['n_items'])
+    m.itemidmap = pd.Series(data=np.arange(m.n_items), index=g['itemidmap_index'], name='ItemIdx')
+    fw = init_weights(g, 'final_')
+    m._host = {'Wx0': fw['Wx'][0], 'Wh0': fw['Wh'][0], 'Wrz0': fw['Wrz'][0], 'Bh0': fw['Bh'][0], 'Wy': fw['Wy'], 'By': fw['By']}
+    m.error_during_train = False
+    fn = str(tmp_path / 'b200_model.pickle')
+    m.savemodel(fn)
+    te_fn = str(tmp_path / 'test.pickle'); te.to_pickle(te_fn)
+    code = (
+        "import sys, os, io, json, contextlib\n"
+        "sys.path.insert(0, %r); import theano_shim; theano_shim.install()\n"
+        "sys.path.insert(0, '/root/reference'); cwd = os.getcwd()\n"
+        "import gru4rec as ref, evaluation as ev, pandas as pd; os.chdir(cwd)\n"
+        "g = ref.GRU4Rec.loadmodel(%r)\n"
+        "assert type(g).__module__ == 'gru4rec' and hasattr(g.Wy, 'get_value')\n"
+        "te = pd.read_pickle(%r)\n"
+        "buf = io.StringIO()\n"
+        "with contextlib.redirect_stdout(buf): rec, mrr = ev.evaluate_gpu(g, te, cut_off=[1, 5, 20], batch_size=7)\n"
+        "print(json.dumps([[float(x) for x in rec], [float(x) for x in mrr]]))\n"
+    ) % (os.path.join(ROOT, 'oracle'), fn, te_fn)
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert out.returncode == 0, out.stderr[-2000:]
+    rec, mrr = json.loads(out.stdout.strip().splitlines()[-1])
+    np.testing.assert_allclose(rec, g['eval_standard_recall'], rtol=1e-6)
+    np.testing.assert_allclose(mrr, g['eval_standard_mrr'], rtol=1e-6)

@@ -173,7 +173,7 @@ def main():
     make_cfg = _lib.make_config
     mk = dict(WORKLOAD['model'])
     cfg = make_cfg(WORKLOAD['n_items'], mk, sample_store=WORKLOAD['sample_store'], eval_lanes=0,
-                   max_resident_steps=max(K, W) + 8, step_mode=args.step_mode, world_size=world, rank=rank)
+                   max_resident_steps=min(max(K, W), WORKLOAD['sample_store'] // mk['n_sample']) + 8, step_mode=args.step_mode, world_size=world, rank=rank)
     eng = _lib.Engine(cfg, device=local_rank)
     if world > 1:
         eng.init_multi_gpu(dist)
@@ -205,17 +205,28 @@ def main():
     h2d = B * (4 + 4 + 4 + 1) + 12
     first = W + K
     if world == 1:
-        # ---- device-resident arm: warm-up window, then K timed steps from an uploaded window
+        # ---- device-resident arm: warm-up, then K timed steps from uploaded windows.  A window never crosses a refill of the
+        # negative-sample store (4882 mini-batches at the headline shape): uploads and refills happen between the timed
+        # windows; `value` sums the CUDA-event times of the windows (the e2e arm below times everything, refills included).
         eng.reset_hidden()
         eng.upload_steps(sched, 0, W)
         eng.run_uploaded(W, want_cost=False)
-        eng.upload_steps(sched, W, K)
+        gen_len = eng.sample_store_rows()
+        cap = int(cfg.max_resident_steps)
         launches0 = eng.kernel_launches()
         barrier()
         t0 = time.time()
-        costs, dev_ms = eng.run_uploaded(K, want_cost=True)
+        dev_ms, done, cost_parts = 0.0, 0, []
+        while done < K:
+            if eng.get_sample_pointer() >= gen_len:
+                eng.generate_samples()
+            n = min(K - done, gen_len - eng.get_sample_pointer(), cap)
+            eng.upload_steps(sched, W + done, n)
+            c, ms = eng.run_uploaded(n, want_cost=True)
+            dev_ms += ms; done += n; cost_parts.append(c)
         barrier()
         wall = time.time() - t0
+        costs = np.concatenate(cost_parts)
         launches = eng.kernel_launches() - launches0
         value = K / (dev_ms / 1000.0)
         # ---- end-to-end arm: host schedule arrays in, costs out, every window (H2D + plan + steps + D2H inside the timing)
@@ -247,6 +258,8 @@ def main():
     # ---- per-kernel roofline from CUDA events around every launch of one more pass over a short window
     prof_n = min(K, 512)
     if world == 1:
+        if eng.get_sample_pointer() + prof_n > eng.sample_store_rows():
+            eng.generate_samples()
         eng.upload_steps(sched, first + K, prof_n)
         prof = eng.profile_uploaded()
     else:

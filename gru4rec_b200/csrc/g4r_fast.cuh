@@ -614,27 +614,40 @@ __global__ void __launch_bounds__(FK_THREADS, 1) k_fast(int slot, int n_steps, F
     if (tid == 0) { red_release_add(&fs->bar, 1u); wait_ge(&fs->bar, bar_epoch * (unsigned int)ncta); }
     __syncthreads();
     if (cta < M) {
+      // lane b = cta: row max over the chunk maxima, one rescale exp per chunk, then plain sums (fixed shuffle / warp order)
       const int b = cta;
-      float m = -INFINITY, Z = 0.f, A = 0.f, Q = 0.f, D = 0.f, T = 0.f, has = 0.f, tt = 0.f;
+      const bool maxed = !(md.loss == G4R_LOSS_BPR || md.loss == G4R_LOSS_TOP1);
+      float mc = -INFINITY, Z = 0.f, A = 0.f, Q = 0.f, D = 0.f, T = 0.f, has = 0.f, tt = 0.f;
       if (tid < md.NCH) {
         const float* st = md.stat + ((size_t)tid * md.B + b) * G4R_NSTAT;
         const float4 u = ld4(st), v = ld4(st + 4);
-        m = u.x; Z = u.y; A = u.z; Q = u.w; D = v.x; T = v.y; has = v.z;
+        mc = u.x; Z = u.y; A = u.z; Q = u.w; D = v.x; T = v.y; has = v.z;
         if (tid == 0) tt = v.w;
+      }
+      float mg = mc;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, o));
+      if (lane == 0) sm.sPart[warp] = mg;
+      __syncthreads();
+      mg = sm.sPart[0];
+      for (int w = 1; w < FK_NW; w++) mg = fmaxf(mg, sm.sPart[w]);
+      if (loss_softmaxneg(md.loss)) mg = fmaxf(mg, 0.f);          // the zeroed diagonal takes part in the max (gru4rec.py:200-202)
+      if (maxed) {
+        const float sc = (mc == -INFINITY) ? 0.f : expf(mc - mg);
+        Z *= sc; A *= sc; Q *= sc; D *= sc;
       }
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const float m2 = __shfl_xor_sync(0xffffffffu, m, o), Z2 = __shfl_xor_sync(0xffffffffu, Z, o), A2 = __shfl_xor_sync(0xffffffffu, A, o),
-                    Q2 = __shfl_xor_sync(0xffffffffu, Q, o), D2 = __shfl_xor_sync(0xffffffffu, D, o), T2 = __shfl_xor_sync(0xffffffffu, T, o),
-                    h2 = __shfl_xor_sync(0xffffffffu, has, o);
-        stat_combine(md, m, Z, A, Q, D, T, has, m2, Z2, A2, Q2, D2, T2, h2);
+        Z += __shfl_xor_sync(0xffffffffu, Z, o); A += __shfl_xor_sync(0xffffffffu, A, o); Q += __shfl_xor_sync(0xffffffffu, Q, o);
+        D += __shfl_xor_sync(0xffffffffu, D, o); T += __shfl_xor_sync(0xffffffffu, T, o); has += __shfl_xor_sync(0xffffffffu, has, o);
       }
-      if (lane == 0) { float* w = sm.sPart + warp * 8; w[0] = m; w[1] = Z; w[2] = A; w[3] = Q; w[4] = D; w[5] = T; w[6] = has; w[7] = tt; }
+      __syncthreads();
+      if (lane == 0) { float* w = sm.sPart + 32 + warp * 8; w[0] = Z; w[1] = A; w[2] = Q; w[3] = D; w[4] = T; w[5] = has; w[6] = tt; }
       __syncthreads();
       if (tid == 0) {
-        tt = sm.sPart[7];
-        for (int w = 1; w < FK_THREADS / 32; w++) { const float* q = sm.sPart + w * 8; stat_combine(md, m, Z, A, Q, D, T, has, q[0], q[1], q[2], q[3], q[4], q[5], q[6]); }
-        if (loss_softmaxneg(md.loss)) stat_merge(m, Z, A, Q, D, 0.f, 0.f, 0.f, 0.f, 0.f);
+        tt = sm.sPart[32 + 6];
+        for (int w = 1; w < FK_NW; w++) { const float* q = sm.sPart + 32 + w * 8; Z += q[0]; A += q[1]; Q += q[2]; D += q[3]; T += q[4]; }
+        const float m = mg;
         float* rs = md.RS + (size_t)b * G4R_NSTAT;
         float loss = 0.f, r0 = m, r1 = Z, r2 = 0.f, r3 = 0.f, r4 = 0.f, r5 = tt;
         if (md.loss == G4R_LOSS_XE) { const float pt = __fdiv_rn(expf(T - m), Z); loss = -logf(pt + G4R_EPS_LOG); r2 = pt; r5 = T; }
@@ -675,28 +688,28 @@ __global__ void __launch_bounds__(FK_THREADS, 1) k_fast(int slot, int n_steps, F
     }
     FK_STAMP(12);
     float* part = md.part + (size_t)(has_chunk ? chunk : 0) * md.B * ldL;
-    if (has_chunk && lane < kw) {
-      float4 dq[FK_Q];
-#pragma unroll
-      for (int q = 0; q < FK_Q; q++) dq[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int bb = 0; bb < M; bb++) {
-        const float4 y = ld4(sm.sY + bb * FK_LDS + lane * 4);
-#pragma unroll
-        for (int q = 0; q < FK_Q; q++) {
-          const float g = sm.sG[(warp + FK_NW * q) * FK_B + bb];
-          dq[q].x = fmaf(g, y.x, dq[q].x); dq[q].y = fmaf(g, y.y, dq[q].y); dq[q].z = fmaf(g, y.z, dq[q].z); dq[q].w = fmaf(g, y.w, dq[q].w);
+    if (has_chunk) {
+      // dSy[j][quad] = sum_b g[b][j] y[b][quad]: one thread per (column, 16-byte feature quad), all nj*kw pairs in parallel
+      for (int t = tid; t < nj * kw; t += FK_THREADS) {
+        const int jj = t / kw, q4 = t % kw;
+        float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int bb = 0; bb < M; bb++) {
+          const float4 y = ld4(sm.sY + bb * FK_LDS + q4 * 4);
+          const float g = sm.sG[jj * FK_B + bb];
+          d.x = fmaf(g, y.x, d.x); d.y = fmaf(g, y.y, d.y); d.z = fmaf(g, y.z, d.z); d.w = fmaf(g, y.w, d.w);
         }
+        st4(sm.sD + jj * FK_LDS + q4 * 4, d);
       }
-#pragma unroll
-      for (int q = 0; q < FK_Q; q++) if (warp + FK_NW * q < nj) st4(sm.sD + (warp + FK_NW * q) * FK_LDS + lane * 4, dq[q]);
-      for (int bb = warp; bb < M; bb += FK_THREADS / 32) {
+      // partial dL/dh[b][quad] = sum_j g[b][j] Sy_j[quad]: one thread per (lane, quad)
+      for (int t = tid; t < M * kw; t += FK_THREADS) {
+        const int bb = t / kw, q4 = t % kw;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int jj = 0; jj < nj; jj++) {
           const float g = sm.sG[jj * FK_B + bb];
-          const float4 w = ld4(sm.sS + jj * FK_LDS + lane * 4);
+          const float4 w = ld4(sm.sS + jj * FK_LDS + q4 * 4);
           a.x = fmaf(g, w.x, a.x); a.y = fmaf(g, w.y, a.y); a.z = fmaf(g, w.z, a.z); a.w = fmaf(g, w.w, a.w);
         }
-        st4(part + (size_t)bb * ldL + lane * 4, a);
+        st4(part + (size_t)bb * ldL + q4 * 4, a);
       }
     }
     __syncthreads();

@@ -169,22 +169,20 @@ struct EvalCtx {
   int cap = 0;
   int slot = -1;
 };
-static std::map<g4r_handle*, EvalCtx> g_eval;
 
 static void eval_release(g4r_handle* h) {
-  auto it = g_eval.find(h);
-  if (it == g_eval.end()) return;
-  EvalCtx& e = it->second;
+  if (!h->eval_ctx) return;
+  EvalCtx& e = *static_cast<EvalCtx*>(h->eval_ctx);
   cudaFreeHost(e.hX); cudaFreeHost(e.hY); cudaFreeHost(e.hSlot); cudaFreeHost(e.hF); cudaFreeHost(e.hM); cudaFreeHost(e.hSti); cudaFreeHost(e.hG);
   cudaFree(e.dX); cudaFree(e.dY); cudaFree(e.dSlot); cudaFree(e.dF); cudaFree(e.dM); cudaFree(e.dSti); cudaFree(e.dG);
   cudaFree(e.dCut); cudaFree(e.dSums); if (e.dOut) cudaFree(e.dOut);
   slot_free(e.slot);
-  g_eval.erase(it);
+  delete static_cast<EvalCtx*>(h->eval_ctx);
+  h->eval_ctx = nullptr;
 }
 
 static int eval_ctx(g4r_handle* h, EvalCtx** out) {
-  auto it = g_eval.find(h);
-  if (it != g_eval.end()) { *out = &it->second; return G4R_OK; }
+  if (h->eval_ctx) { *out = static_cast<EvalCtx*>(h->eval_ctx); return G4R_OK; }
   EvalCtx e;
   e.Be = h->cfg.eval_batch_size > 0 ? h->cfg.eval_batch_size : h->cfg.batch_size;
   e.cap = 512;
@@ -202,8 +200,8 @@ static int eval_ctx(g4r_handle* h, EvalCtx** out) {
   CK(slot_upload(e.slot, e.mde, h->stream));
   cudaFuncSetAttribute(k_eval_score<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eval_smem_bytes());
   cudaFuncSetAttribute(k_eval_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eval_smem_bytes());
-  g_eval[h] = e;
-  *out = &g_eval[h];
+  h->eval_ctx = new EvalCtx(e);
+  *out = static_cast<EvalCtx*>(h->eval_ctx);
   return G4R_OK;
 }
 

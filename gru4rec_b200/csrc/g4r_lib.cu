@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "g4r_kernels.cuh"
@@ -61,6 +62,8 @@ struct g4r_handle {
   bool use_graph = true;
   GridBar* dGridBar = nullptr; unsigned long long* dStamp = nullptr; int pk_blocks = 0; size_t pk_smem = 0;
   bool mg_alloc = false; MgDev mgdev; std::vector<MgTensor> mg_tensors;
+  void* eval_ctx = nullptr;      // EvalCtx* (g4r_eval.cuh), owned by the handle
+  void* mg_host = nullptr;       // MgHost*  (g4r_multi.cuh), owned by the handle
   FastSync* dFastSync = nullptr; bool fast_ok = false; int* hFlags = nullptr; int64_t fast_windows = 0, slow_windows = 0;
   bool prof = false; bool stamp_on = false;
   std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_phase;
@@ -254,8 +257,9 @@ static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
 #define G4R_MAX_SLOTS 24
 __constant__ ModelDev c_models[G4R_MAX_SLOTS];
 static bool g_slot_used[G4R_MAX_SLOTS] = {};
-static int slot_alloc() { for (int i = 0; i < G4R_MAX_SLOTS; i++) if (!g_slot_used[i]) { g_slot_used[i] = true; return i; } return -1; }
-static void slot_free(int i) { if (i >= 0 && i < G4R_MAX_SLOTS) g_slot_used[i] = false; }
+static std::mutex g_slot_mutex;      // handles are single-threaded, but several handles may live in several threads
+static int slot_alloc() { std::lock_guard<std::mutex> lk(g_slot_mutex); for (int i = 0; i < G4R_MAX_SLOTS; i++) if (!g_slot_used[i]) { g_slot_used[i] = true; return i; } return -1; }
+static void slot_free(int i) { std::lock_guard<std::mutex> lk(g_slot_mutex); if (i >= 0 && i < G4R_MAX_SLOTS) g_slot_used[i] = false; }
 static cudaError_t slot_upload(int slot, const ModelDev& md, cudaStream_t st) {
   return cudaMemcpyToSymbolAsync(c_models, &md, sizeof(ModelDev), (size_t)slot * sizeof(ModelDev), cudaMemcpyHostToDevice, st);
 }
@@ -863,7 +867,7 @@ static int run_window(g4r_handle* h, int64_t n) {
 }
 
 #include "g4r_multi.cuh"
-static bool mg_is_ready(g4r_handle* h) { auto it = g_mg.find(h); return it != g_mg.end() && it->second.ready; }
+static bool mg_is_ready(g4r_handle* h) { return h->mg_host && static_cast<MgHost*>(h->mg_host)->ready; }
 
 extern "C" int g4r_upload_steps(g4r_handle* h, const g4r_schedule* s, int64_t first, int64_t n) {
   if (!h || !s) return G4R_ERR_INVALID;

@@ -255,7 +255,6 @@ struct MgHost {
   bool ready = false;
   cudaGraphExec_t graphU = nullptr, graph1 = nullptr; int64_t launches_per_step = 0;
 };
-static std::map<g4r_handle*, MgHost> g_mg;
 
 #define NC(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) { h->err = std::string(#call) + ": " + g_nccl.GetErrorString(r_); return G4R_ERR_CUDA; } } while (0)
 
@@ -276,7 +275,8 @@ extern "C" int g4r_mg_init(g4r_handle* h, const char* id128) {
   if (!h->mg_alloc) FAIL(G4R_ERR_STATE, "handle was created without multi-GPU buffers");
   if (!nccl_load()) FAIL(G4R_ERR_STATE, "libnccl.so.2 could not be loaded");
   cudaSetDevice(h->cfg.device);
-  MgHost& m = g_mg[h];
+  if (!h->mg_host) h->mg_host = new MgHost();
+  MgHost& m = *static_cast<MgHost*>(h->mg_host);
   ncclUniqueId id; memcpy(&id, id128, 128);
   NC(g_nccl.CommInitRank(&m.comm, R, id, rank));
   m.dev = h->mgdev;
@@ -287,18 +287,18 @@ extern "C" int g4r_mg_init(g4r_handle* h, const char* id128) {
   return G4R_OK;
 }
 static void mg_release(g4r_handle* h) {
-  auto it = g_mg.find(h);
-  if (it != g_mg.end()) {
-    if (it->second.graphU) cudaGraphExecDestroy(it->second.graphU);
-    if (it->second.graph1) cudaGraphExecDestroy(it->second.graph1);
-    if (it->second.comm) g_nccl.CommDestroy(it->second.comm);
-    g_mg.erase(it);
-  }
+  if (!h->mg_host) return;
+  MgHost* m = static_cast<MgHost*>(h->mg_host);
+  if (m->graphU) cudaGraphExecDestroy(m->graphU);
+  if (m->graph1) cudaGraphExecDestroy(m->graph1);
+  if (m->comm) g_nccl.CommDestroy(m->comm);
+  delete m;
+  h->mg_host = nullptr;
 }
 
 // one window of n steps (n <= MG_CAP; identical n on every rank)
 static int mg_run_window(g4r_handle* h, int64_t n) {
-  MgHost& m = g_mg[h];
+  MgHost& m = *static_cast<MgHost*>(h->mg_host);
   const ModelDev& md = h->md;
   const MgDev& mg = m.dev;
   cudaStream_t st = h->stream;

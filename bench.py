@@ -152,7 +152,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=200)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--step-mode', type=int, default=2, help='0 per-phase kernels (CUDA graph), 1 persistent kernel, 2 role-specialised persistent kernel (default)')
+    ap.add_argument('--step-mode', type=int, default=2, help='0 per-phase kernels (CUDA graph), 1 persistent kernel, 2 role-specialised persistent kernel (default), 3 = 2 with the GRU phases on one thread-block cluster')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -266,6 +266,19 @@ def main():
         prof = None      # the per-kernel roofline is a single-GPU measurement (N=1 run of this same script)
     peak, peak_src = peak_hbm()
     lg_bytes = algo_bytes_lossgrad(N, mk['layers'][-1], mk['momentum'] > 0)
+    fast_phase = None
+    if world == 1 and int(cfg.step_mode) in (2, 3) and eng.fast_windows()[0] > 0:
+        # the same update phase INSIDE the production kernel k_fast, from %globaltimer stamps of CTA 0 (slot 2 = row statistics
+        # ready, slot 14 = chunk's rows updated): loss gradient + dSy + partial dL/dh + sparse update of the chunk's rows
+        eng.persistent_stamps(True)
+        if eng.get_sample_pointer() + prof_n > eng.sample_store_rows():
+            eng.generate_samples()
+        eng.upload_steps(sched, first + K, prof_n)
+        eng.run_uploaded(prof_n, want_cost=False)
+        st = eng.persistent_stamps(False, prof_n).astype(np.int64)
+        seg_us = float(np.mean((st[8:, 14] - st[8:, 2]) / 1000.0))
+        fast_phase = {'us': seg_us, 'achieved_GBs': lg_bytes / (seg_us * 1e-6) / 1e9, 'frac': lg_bytes / (seg_us * 1e-6) / 1e9 / peak,
+                      'note': 'k_fast: statistics-ready -> rows-updated segment of a chunk CTA (globaltimer), same algorithmic bytes'}
     if prof is not None:
         dom_name = max(prof, key=lambda k: prof[k][0])
         lg_ms, lg_n = prof['lossgrad_update']
@@ -288,7 +301,7 @@ def main():
         'roofline': {'bound': 'hbm', 'kernel': 'k_lossgrad (loss gradient + sparse Adagrad/momentum update of Wy/By rows)',
                      'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': frac, 'traffic': 3812352 if world == 1 else None,
                      'peak_source': peak_src, 'algorithmic_bytes_per_launch': lg_bytes, 'us_per_launch': us_launch, 'traffic_source': 'ncu --set full dram read+write of k_lossgrad, profiles/r1_ncu_full_k_lossgrad.txt',
-                     'dominant_phase_by_time': dom_name, 'phase_us': phase_us,
+                     'dominant_phase_by_time': dom_name, 'phase_us': phase_us, 'k_fast_update_phase': fast_phase,
                      'whole_step': {'algorithmic_bytes': ALGO_BYTES_PER_STEP, 'achieved': ALGO_BYTES_PER_STEP * (value / world) / 1e9,
                                     'frac': ALGO_BYTES_PER_STEP * (value / world) / 1e9 / peak,
                                     'note': 'latency-bound: dependent phases per mini-batch, working set near L2 size'}},

@@ -78,7 +78,8 @@ struct FastSmem {
 };
 
 // loads the index metadata of step s into buffer `buf` (plain loads; consumed much later)
-__device__ __forceinline__ void fk_load_idx(const ModelDev& md, FastSmem& sm, int s, int n_steps, int chunk, int buf) {
+template <class SM>
+__device__ __forceinline__ void fk_load_idx(const ModelDev& md, SM& sm, int s, int n_steps, int chunk, int buf) {
   const int tid = threadIdx.x;
   if (s >= n_steps) return;
   const int M = md.wM[s];
@@ -99,7 +100,8 @@ __device__ __forceinline__ void fk_load_idx(const ModelDev& md, FastSmem& sm, in
 }
 
 // issue the TMA prefetch of step s (rows are final once the previous step's updates are complete)
-__device__ __forceinline__ void fk_prefetch_rows(const ModelDev& md, FastSmem& sm, int s, int n_steps, int buf, bool pw) {
+template <class SM>
+__device__ __forceinline__ void fk_prefetch_rows(const ModelDev& md, SM& sm, int s, int n_steps, int buf, bool pw) {
   if (s >= n_steps) return;
   const int tid = threadIdx.x;
   const int M = md.wM[s];
@@ -166,7 +168,8 @@ __device__ __forceinline__ void fk_group_barrier(FastSync* fs, unsigned int& gep
 // ncu on the 32x32-tile kernels showed ~2000 instructions per warp at ~8.6 cycles each (2 warps per scheduler):
 // the GRU phases are instruction-latency bound.  Here the work of a phase is spread over all FK_G CTAs (a few
 // output columns each), the reduction dimension is split over the 8 warps, and every thread issues a few dozen FMAs.
-__device__ __forceinline__ void fk_stage_lanes(const ModelDev& md, FastSmem& sm, int s, int M) {
+template <class SM>
+__device__ __forceinline__ void fk_stage_lanes(const ModelDev& md, SM& sm, int s, int M) {
   if (threadIdx.x < FK_B) {
     const int b = threadIdx.x;
     sm.gIdx[b] = b < M ? md.wSlot[(size_t)s * md.B + b] : -1;
@@ -395,7 +398,8 @@ __device__ void fk_dense(const ModelDev& md, FastSmem& sm, int s, int cta) {
 
 // Input-row update of lane b on a helper (non-GRU) CTA, concurrent with the dense update of the GRU group: it starts when
 // the GRU group has passed its B2 barrier (dvec complete) and only touches Wx0 rows, which the dense phase never reads.
-__device__ void fk_sparse_in(const ModelDev& md, FastSmem& sm, int s, int b) {
+template <class SM>
+__device__ void fk_sparse_in(const ModelDev& md, SM& sm, int s, int b) {
   const LayerDev& ly = md.layer[0];
   const int M = md.wM[s];
   if (b >= M) return;
@@ -437,9 +441,60 @@ __device__ void fk_sparse_in(const ModelDev& md, FastSmem& sm, int s, int b) {
   }
 }
 
+// Same update when the CTA owns exactly one lane: everything that does not depend on this step's gradients (duplicate
+// chain, parameter / Adagrad / momentum row) is fetched BEFORE waiting for the dvec rows, so that only one load round trip
+// separates the GRU role's "dvec complete" signal from the row update.
+template <class SM>
+__device__ void fk_sparse_in_one(const ModelDev& md, SM& sm, int s, int b, const unsigned int* ctr, unsigned int target) {
+  const LayerDev& ly = md.layer[0];
+  const int M = md.wM[s], ld3 = ly.ld3, tid = threadIdx.x;
+  const bool act = b < M && (md.wXflag[(size_t)s * md.B + b] & 1);       // first position of its duplicate group
+  const int item = act ? md.wX[(size_t)s * md.B + b] : 0;
+  const bool ada = md.adapt == G4R_ADAPT_ADAGRAD, mom = md.mom > 0.f;
+  if (act && tid == 0) {
+    const int* xnext = md.wXnext + (size_t)s * md.B;
+    int n = 0; for (int bb = b; bb >= 0 && n < FK_B; bb = xnext[bb]) sm.gIdx[n++] = bb; sm.gIdx[FK_B] = n;
+  }
+  float* prow = ly.Wx + (size_t)item * ld3;
+  const int c4 = tid;
+  const bool mine = act && c4 < ld3 / 4;                                   // ld3 / 4 <= 96 quads: one pass
+  float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), a0 = p0, v0 = p0;
+  if (mine) {
+    p0 = ld4(prow + c4 * 4);
+    if (ada) a0 = ld4(ly.Wx_acc + (size_t)item * ld3 + c4 * 4);
+    if (mom) v0 = ld4(ly.Wx_vel + (size_t)item * ld3 + c4 * 4);
+  }
+  if (tid == 0) wait_ge(ctr, target);
+  __syncthreads();
+  if (mine) {
+    const int nmem = sm.gIdx[FK_B];
+    float4 al = a0, vl = v0, ps = p0;
+    for (int k = 0; k < nmem; k++) {
+      const float4 g = ld4(ly.dvec + (size_t)sm.gIdx[k] * ld3 + c4 * 4);
+      float4 gs = g;
+      if (ada) {
+        al.x = a0.x + g.x * g.x; al.y = a0.y + g.y * g.y; al.z = a0.z + g.z * g.z; al.w = a0.w + g.w * g.w;
+        gs.x = __fdiv_rn(g.x, sqrtf(al.x + G4R_EPS_ADA)); gs.y = __fdiv_rn(g.y, sqrtf(al.y + G4R_EPS_ADA));
+        gs.z = __fdiv_rn(g.z, sqrtf(al.z + G4R_EPS_ADA)); gs.w = __fdiv_rn(g.w, sqrtf(al.w + G4R_EPS_ADA));
+      }
+      float4 d;
+      if (md.lmbd > 0.f) { d.x = md.lr * (gs.x + md.lmbd * p0.x); d.y = md.lr * (gs.y + md.lmbd * p0.y); d.z = md.lr * (gs.z + md.lmbd * p0.z); d.w = md.lr * (gs.w + md.lmbd * p0.w); }
+      else { d.x = md.lr * gs.x; d.y = md.lr * gs.y; d.z = md.lr * gs.z; d.w = md.lr * gs.w; }
+      if (mom) {
+        vl.x = md.mom * v0.x - d.x; vl.y = md.mom * v0.y - d.y; vl.z = md.mom * v0.z - d.z; vl.w = md.mom * v0.w - d.w;
+        ps.x += vl.x; ps.y += vl.y; ps.z += vl.z; ps.w += vl.w;
+      } else { ps.x -= d.x; ps.y -= d.y; ps.z -= d.z; ps.w -= d.w; }
+    }
+    st4(prow + c4 * 4, ps);
+    if (ada) st4(ly.Wx_acc + (size_t)item * ld3 + c4 * 4, al);
+    if (mom) st4(ly.Wx_vel + (size_t)item * ld3 + c4 * 4, vl);
+  }
+}
+
 // B1 (fast kernel): every CTA reduces a contiguous run of dL/dh elements; lanes = consecutive elements (coalesced),
 // warps = slices of the chunk partials, cross-warp sum in shared memory in fixed order; then da_h / da_z.
-__device__ void fk_b1(const ModelDev& md, FastSmem& sm, int s, int cta, int ncta) {
+template <bool CL, class SM>
+__device__ void fk_b1(const ModelDev& md, SM& sm, int s, int cta, int ncta) {
   const LayerDev& ly = md.layer[0];
   const int M = md.wM[s], L = ly.L, ldL = ly.ldL;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -469,6 +524,7 @@ __device__ void fk_b1(const ModelDev& md, FastSmem& sm, int s, int cta, int ncta
 #pragma unroll
     for (int w = 0; w < FK_NW; w++) dy += red[w * per + i];
     const size_t o = (size_t)b * ldL + c;
+    if (CL) { ly.dy[o] = dy; continue; }     // cluster variant: the GRU cluster owns ht / z / ah and derives da_h, da_z itself
     const float ht = ly.ht[o], ho = ly.Hold[o], z = ly.z[o], ah = ly.ah[o];
     float dh = dy;
     if (md.p_drop_h > 0.f) dh *= drop_scale(md.drop_seed, md.wG[s], 0u, (uint32_t)(b * L + c), 1.0f - md.p_drop_h);
@@ -479,35 +535,64 @@ __device__ void fk_b1(const ModelDev& md, FastSmem& sm, int s, int cta, int ncta
   }
 }
 
-__global__ void __launch_bounds__(FK_THREADS, 1) k_fast(int slot, int n_steps, FastSync* fs, unsigned long long* tstamp) {
+#include "g4r_fastc.cuh"
+
+// CL = false: GRU phases on a 48-CTA group with global group barriers (step_mode 2).
+// CL = true : launched with thread-block clusters; the GRU phases run on cluster 0 (g4r_fastc.cuh, step_mode 3).
+template <bool CL>
+__global__ void __launch_bounds__(FK_THREADS, 1) k_fast_t(int slot, int n_steps, FastSync* fs, unsigned long long* tstamp) {
+  using SM = typename std::conditional<CL, FastSmemC, FastSmem>::type;
   extern __shared__ __align__(128) unsigned char fk_raw[];
-  FastSmem& sm = *reinterpret_cast<FastSmem*>(fk_raw);
+  SM& sm = *reinterpret_cast<SM*>(fk_raw);
   const ModelDev& md = MD;
   const LayerDev& ly = md.layer[0];
   const int cta = blockIdx.x, ncta = gridDim.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int chunk = cta;                       // CTAs beyond the number of chunks own no columns
   const bool has_chunk = chunk < md.NCH;
-  const bool gru = cta < FK_G;
+  const int G = CL ? (int)cl_size() : FK_G;    // CTAs of the GRU role
+  const bool gru = cta < G;
   const bool pw = loss_pairwise(md.loss);
   const bool ada = md.adapt == G4R_ADAPT_ADAGRAD, mom = md.mom > 0.f;
   const int L = md.L, ldL = md.ldL, B = md.B;
   const int kw = ldL / 4;
   uint64_t* bar = reinterpret_cast<uint64_t*>(&sm.mbar);
   unsigned int bar_epoch = 0, gepoch = 0, stats_target = 0;
-  const int in_ctas = min(B, ncta - FK_G);     // helper CTAs [FK_G, FK_G + in_ctas) update the gathered input rows
-#define FK_STAMP(k) do { if (tstamp && cta == 0 && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tstamp[(size_t)s * 16 + (k)] = t_; } } while (0)
+  const int in_ctas = min(B, ncta - G);        // helper CTAs [G, G + in_ctas) update the gathered input rows
+#ifdef G4R_CF_FINE
+#define FK_FTS(s_) ((tstamp && cta == 0 && (s_) < 500 && n_steps >= 1000) ? tstamp + (size_t)((s_) + 500) * 16 : nullptr)
+#define FK_STAMP_OK(s_) ((s_) < 500)
+#else
+#define FK_FTS(s_) ((unsigned long long*)nullptr)
+#define FK_STAMP_OK(s_) true
+#endif
+#define FK_STAMP(k) do { if (tstamp && cta == 0 && tid == 0 && FK_STAMP_OK(s)) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tstamp[(size_t)s * 16 + (k)] = t_; } } while (0)
   if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   fk_load_idx(md, sm, 0, n_steps, chunk, 0);
   __syncthreads();
   fk_prefetch_rows(md, sm, 0, n_steps, 0, pw);
   // GRU forward of step 0
-  if (gru) {
-    fk_f1(md, sm, 0, cta, nullptr, 0u);
-    fk_group_barrier(fs, gepoch);
-    fk_f2(md, sm, 0, cta);
-    __syncthreads();
-    if (tid == 0) red_release_add(&fs->h_ready, 1u);
+  ClusterCtx cc = {0, 1, 0, 0};
+  if constexpr (CL) {
+    if (gru) {
+      cc = cf_init(md, sm);
+      cf_load_resident(md, sm, cc);
+      if (n_steps > 0) {
+        fk_stage_lanes(md, sm, 0, md.wM[0]);
+        cf_f1(md, sm, cc, 0, false, nullptr, 0u, nullptr);
+        cf_f2(md, sm, cc, 0, nullptr);
+        __syncthreads();
+        if (tid == 0) red_release_add(&fs->h_ready, 1u);
+      }
+    }
+  } else {
+    if (gru) {
+      fk_f1(md, sm, 0, cta, nullptr, 0u);
+      fk_group_barrier(fs, gepoch);
+      fk_f2(md, sm, 0, cta);
+      __syncthreads();
+      if (tid == 0) red_release_add(&fs->h_ready, 1u);
+    }
   }
   for (int s = 0; s < n_steps; s++) {
     const int buf = s & 1;
@@ -518,7 +603,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) k_fast(int slot, int n_steps, F
     // indices of the NEXT step (consumed after this step's last barrier)
     fk_load_idx(md, sm, s + 1, n_steps, chunk, buf ^ 1);
     // ---- wait for h(s), stage it ----
-    if (tid == 0) wait_ge(&fs->h_ready, (unsigned int)(s + 1) * FK_G);
+    if (tid == 0) wait_ge(&fs->h_ready, (unsigned int)(s + 1) * (unsigned int)G);
     __syncthreads();
     stage_rows4(sm.sY, FK_LDS, FK_B, kw, [&](int rr) -> const float* { return rr < M ? ly.y + (size_t)rr * ldL : nullptr; });
     mbar_wait(bar, (unsigned int)(s & 1));      // prefetched rows of this step have landed
@@ -771,14 +856,40 @@ __global__ void __launch_bounds__(FK_THREADS, 1) k_fast(int slot, int n_steps, F
     __syncthreads();
     FK_STAMP(3);
     // ---- b1 on every CTA, then prefetch the next step's rows ----
-    fk_b1(md, sm, s, cta, ncta);
+    fk_b1<CL>(md, sm, s, cta, ncta);
     __syncthreads();
     if (tid == 0) red_release_add(&fs->b1_done, 1u);
     FK_STAMP(15);
     fk_prefetch_rows(md, sm, s + 1, n_steps, buf ^ 1, pw);
     FK_STAMP(4);
-    // ---- GRU group: backward, dense update, forward of the next step ----
-    if (gru) {
+    // ---- GRU role: backward, dense update, forward of the next step ----
+    if constexpr (CL) {
+      if (gru) {
+        if (s + 1 < n_steps) fk_stage_lanes(md, sm, s + 1, md.wM[s + 1]);
+        cf_backward(md, sm, cc, fs, s, ncta, s + 1 < n_steps, (tstamp && cta == 0 && FK_STAMP_OK(s)) ? tstamp + (size_t)s * 16 : nullptr, FK_FTS(s));
+        FK_STAMP(6);
+        if (s + 1 < n_steps) {
+          cf_f1(md, sm, cc, s + 1, true, &fs->in_done, (unsigned int)(s + 1) * (unsigned int)in_ctas, FK_FTS(s));
+          FK_STAMP(7);
+          cf_f2(md, sm, cc, s + 1, FK_FTS(s));
+          __syncthreads();
+          if (tid == 0) red_release_add(&fs->h_ready, 1u);
+        } else {
+          cl_wait();                                   // matches the arrive left pending by cf_backward
+        }
+        FK_STAMP(8);
+      } else if (cta < G + in_ctas) {
+        const unsigned int tgt = (unsigned int)(s + 1) * (unsigned int)G;           // dvec rows of the step complete
+        if (in_ctas == B && ly.ld3 / 4 <= FK_THREADS) fk_sparse_in_one(md, sm, s, cta - G, &fs->grp, tgt);
+        else {
+          if (tid == 0) wait_ge(&fs->grp, tgt);
+          __syncthreads();
+          for (int b = cta - G; b < B; b += in_ctas) { fk_sparse_in(md, sm, s, b); __syncthreads(); }
+        }
+        __syncthreads();
+        if (tid == 0) red_release_add(&fs->in_done, 1u);
+      }
+    } else if (gru) {
       if (tid == 0) wait_ge(&fs->b1_done, (unsigned int)(s + 1) * (unsigned int)ncta);
       __syncthreads();
       fk_b2(md, sm, s, cta);
@@ -805,5 +916,6 @@ __global__ void __launch_bounds__(FK_THREADS, 1) k_fast(int slot, int n_steps, F
       if (tid == 0) red_release_add(&fs->in_done, 1u);
     }
   }
+  if constexpr (CL) { if (gru) cf_store_resident(md, sm, cc); }
 #undef FK_STAMP
 }

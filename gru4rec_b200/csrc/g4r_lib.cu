@@ -64,7 +64,7 @@ struct g4r_handle {
   bool mg_alloc = false; MgDev mgdev; std::vector<MgTensor> mg_tensors;
   void* eval_ctx = nullptr;      // EvalCtx* (g4r_eval.cuh), owned by the handle
   void* mg_host = nullptr;       // MgHost*  (g4r_multi.cuh), owned by the handle
-  FastSync* dFastSync = nullptr; bool fast_ok = false; int* hFlags = nullptr; int64_t fast_windows = 0, slow_windows = 0;
+  FastSync* dFastSync = nullptr; bool fast_ok = false; bool fastc_ok = false; int fastc_grid = 0; int* hFlags = nullptr; int64_t fast_windows = 0, slow_windows = 0;
   bool prof = false; bool stamp_on = false;
   std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_phase;
 };
@@ -305,6 +305,41 @@ __global__ void k_advance(int* base, int n) { if (threadIdx.x == 0 && blockIdx.x
 #include "g4r_persistent.cuh"
 #include "g4r_fast.cuh"
 
+// ---- cluster launch of the role-specialised kernel (step_mode 3) ----
+constexpr int FC_CLUSTER = 8;      // portable cluster size; cRed in FastSmemC is sized for <= 8 ranks
+static cudaError_t fastc_config(cudaLaunchConfig_t& lc, cudaLaunchAttribute* attrs, int n_attr_coop, int grid, cudaStream_t st) {
+  lc = cudaLaunchConfig_t{};
+  lc.gridDim = dim3(grid); lc.blockDim = dim3(FK_THREADS); lc.dynamicSmemBytes = sizeof(FastSmemC); lc.stream = st;
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = FC_CLUSTER; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeCooperative; attrs[1].val.cooperative = 1;
+  lc.attrs = attrs; lc.numAttrs = 1 + n_attr_coop;
+  return cudaSuccess;
+}
+// largest grid (multiple of the cluster size, at most one CTA per SM) whose clusters are all co-resident; 0 if unsupported
+static int fastc_max_grid(int n_sm) {
+  if (cudaFuncSetAttribute(k_fast_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastSmemC)) != cudaSuccess) { cudaGetLastError(); return 0; }
+  cudaLaunchConfig_t lc; cudaLaunchAttribute attrs[2];
+  fastc_config(lc, attrs, 0, (n_sm / FC_CLUSTER) * FC_CLUSTER, nullptr);
+  int ncl = 0;
+  if (cudaOccupancyMaxActiveClusters(&ncl, k_fast_t<true>, &lc) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return std::min(ncl, n_sm / FC_CLUSTER) * FC_CLUSTER;
+}
+static cudaError_t fastc_launch(int grid, cudaStream_t st, void** args) {
+  static int coop_ok = 1;          // cooperative + cluster attributes together; dropped if the runtime rejects the pair
+  cudaLaunchConfig_t lc; cudaLaunchAttribute attrs[2];
+  if (coop_ok) {
+    fastc_config(lc, attrs, 1, grid, st);
+    cudaError_t e = cudaLaunchKernelExC(&lc, (const void*)k_fast_t<true>, args);
+    if (e == cudaSuccess) return e;
+    cudaGetLastError();
+    coop_ok = 0;
+  }
+  // co-residency is still guaranteed: grid <= cudaOccupancyMaxActiveClusters * cluster size, one CTA per SM
+  fastc_config(lc, attrs, 0, grid, st);
+  return cudaLaunchKernelExC(&lc, (const void*)k_fast_t<true>, args);
+}
+
 static int tiles2(int cols, int rows) { return ((cols + GB - 1) / GB) * ((rows + GB - 1) / GB); }
 
 // enqueue the kernels of one training step (window-relative index = *base + off when base != nullptr)
@@ -400,8 +435,15 @@ extern "C" int g4r_create(const g4r_config* cfg, void* device_workspace, size_t 
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return bail(G4R_ERR_CUDA, "cudaGetDeviceProperties failed");
   h->n_sm = prop.multiProcessorCount;
+  // step_mode 3: the role-specialised kernel is launched as thread-block clusters of FC_CLUSTER CTAs; the number of
+  // co-resident clusters bounds the grid and therefore the number of column chunks (one chunk per CTA)
+  int chunk_cap = h->n_sm;
+  if (cfg->step_mode == 3) {
+    h->fastc_grid = fastc_max_grid(h->n_sm);
+    if (h->fastc_grid >= FC_CLUSTER * 2) chunk_cap = std::min(chunk_cap, h->fastc_grid);
+  }
   size_t need = 0;
-  { Carver cv{nullptr, 0, true}; layout(*cfg, cv, nullptr, h->n_sm); need = align_up(cv.off, 256) + 256; }
+  { Carver cv{nullptr, 0, true}; layout(*cfg, cv, nullptr, chunk_cap); need = align_up(cv.off, 256) + 256; }
   if (device_workspace) {
     if (workspace_bytes < need) return bail(G4R_ERR_INVALID, "workspace too small");
     h->ws = (char*)device_workspace; h->own_ws = false;
@@ -416,7 +458,7 @@ extern "C" int g4r_create(const g4r_config* cfg, void* device_workspace, size_t 
   // 256-byte align the carve base
   char* base = (char*)align_up((size_t)h->ws, 256);
   Carver cv{base, 0, false};
-  layout(*cfg, cv, h, h->n_sm);
+  layout(*cfg, cv, h, chunk_cap);
   h->slot = slot_alloc();
   if (h->slot < 0) return bail(G4R_ERR_STATE, "too many live g4r handles in this process");
   if (slot_upload(h->slot, h->md, h->stream) != cudaSuccess) return bail(G4R_ERR_CUDA, "constant upload failed");
@@ -445,11 +487,13 @@ extern "C" int g4r_create(const g4r_config* cfg, void* device_workspace, size_t 
   }
   {
     const ModelDev& m = h->md;
-    cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastSmem));
+    cudaFuncSetAttribute(k_fast_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastSmem));
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fast, FK_THREADS, sizeof(FastSmem));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fast_t<false>, FK_THREADS, sizeof(FastSmem));
     h->fast_ok = h->pk_blocks > 0 && per_sm >= 1 && m.mode == 0 && m.n_layers == 1 && m.ldL <= 128 && m.B <= FK_B && h->n_sm >= FK_G + 1 && m.NCH <= 160 &&
                  (m.adapt == G4R_ADAPT_ADAGRAD ? m.Wy_acc != nullptr : true);
+    h->fastc_ok = cfg->step_mode == 3 && h->fastc_grid >= FC_CLUSTER * 2 && m.mode == 0 && m.n_layers == 1 && m.ldL <= 128 && m.B <= FK_B &&
+                  m.NCH <= h->fastc_grid && (m.adapt == G4R_ADAPT_ADAGRAD ? m.Wy_acc != nullptr : true);
     cudaMallocHost(&h->hFlags, 4 * sizeof(int));
   }
   if (cfg->step_mode == 1 && h->pk_blocks == 0) return bail(G4R_ERR_INVALID, "persistent mode unavailable (cooperative launch / shared memory)");
@@ -830,21 +874,31 @@ static int64_t launches_per_step(const g4r_handle* h) {
 }
 
 static int run_window(g4r_handle* h, int64_t n) {
-  bool fast = false;
-  if (h->cfg.step_mode == 2 && !h->prof && h->fast_ok) {
-    // the plan kernel recorded the widest chunk of the window; the role-specialised kernel needs <= 16 columns
-    CK(cudaMemcpyAsync(h->hFlags, h->md.nanflag, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    fast = h->hFlags[2] <= FK_CT;
+  bool fast = false, fastc = false;
+  if ((h->cfg.step_mode == 3 && h->fastc_ok) || (h->cfg.step_mode == 2 && h->fast_ok)) {
+    if (!h->prof) {
+      // the plan kernel recorded the widest chunk of the window; the role-specialised kernels handle <= FK_CT columns per chunk
+      CK(cudaMemcpyAsync(h->hFlags, h->md.nanflag, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      const bool fits = h->hFlags[2] <= FK_CT;
+      fastc = fits && h->cfg.step_mode == 3;
+      fast = fits && h->cfg.step_mode == 2;
+    }
   }
-  if (fast) {
+  if (fastc) {
     int slot = h->slot, nst = (int)n; FastSync* fsp = h->dFastSync; unsigned long long* ts = h->stamp_on ? h->dStamp : nullptr;
     void* args[] = {&slot, &nst, &fsp, &ts};
     CK(cudaMemsetAsync(h->dFastSync, 0, sizeof(FastSync), h->stream));
-    CK(cudaLaunchCooperativeKernel((void*)k_fast, dim3(h->pk_blocks), dim3(FK_THREADS), args, sizeof(FastSmem), h->stream));
+    CK(fastc_launch(h->fastc_grid, h->stream, args));
     h->launches += 1; h->fast_windows++;
-  } else if ((h->cfg.step_mode == 1 || h->cfg.step_mode == 2) && !h->prof && h->pk_blocks > 0) {
-    if (h->cfg.step_mode == 2) h->slow_windows++;
+  } else if (fast) {
+    int slot = h->slot, nst = (int)n; FastSync* fsp = h->dFastSync; unsigned long long* ts = h->stamp_on ? h->dStamp : nullptr;
+    void* args[] = {&slot, &nst, &fsp, &ts};
+    CK(cudaMemsetAsync(h->dFastSync, 0, sizeof(FastSync), h->stream));
+    CK(cudaLaunchCooperativeKernel((void*)k_fast_t<false>, dim3(h->pk_blocks), dim3(FK_THREADS), args, sizeof(FastSmem), h->stream));
+    h->launches += 1; h->fast_windows++;
+  } else if (h->cfg.step_mode >= 1 && !h->prof && h->pk_blocks > 0) {
+    if (h->cfg.step_mode >= 2) h->slow_windows++;
     int slot = h->slot, nst = (int)n; GridBar* gb = h->dGridBar; unsigned long long* ts = h->stamp_on ? h->dStamp : nullptr;
     void* args[] = {&slot, &nst, &gb, &ts};
     CK(cudaMemsetAsync(h->dGridBar, 0, sizeof(GridBar), h->stream));

@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 NODROP = [n for n in golden_names() if not (load_golden(n)['model_kwargs'].get('dropout_p_hidden', 0) or load_golden(n)['model_kwargs'].get('dropout_p_embed', 0))]
 
 
-@pytest.mark.parametrize('step_mode', [0, 1, 2])
+@pytest.mark.parametrize('step_mode', [0, 1, 2, 3])
 @pytest.mark.parametrize('name', NODROP)
 def test_golden_trajectory_through_cuda(name, step_mode):
     """Costs of every mini-batch and the final weights the REFERENCE produced vs. the CUDA path on the same inputs."""

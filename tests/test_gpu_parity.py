@@ -89,7 +89,7 @@ CASES = {
 }
 
 
-@pytest.mark.parametrize('step_mode', [0, 1, 2])
+@pytest.mark.parametrize('step_mode', [0, 1, 2, 3])
 @pytest.mark.parametrize('name', sorted(CASES))
 def test_train_steps_match_oracle(name, step_mode):
     mk = CASES[name]
@@ -116,7 +116,7 @@ def test_train_steps_match_oracle(name, step_mode):
         np.testing.assert_allclose(eng.get('H%d' % i), m.H[i], rtol=1e-3, atol=1e-5)
 
 
-@pytest.mark.parametrize('step_mode', [0, 1, 2])
+@pytest.mark.parametrize('step_mode', [0, 1, 2, 3])
 def test_shrinking_batch_and_slots(step_mode):
     """epoch tail: M < B with lane compaction (gru4rec.py:644-651) through a real schedule."""
     from gru4rec_b200.synth import make_sessions
@@ -137,8 +137,11 @@ def test_shrinking_batch_and_slots(step_mode):
                                                    ('bpr-max', 'elu-1', 0.0, dict(dropout_p_hidden=0.25, lmbd=0.0005)),
                                                    ('cross-entropy', 'softmax', 0.0, dict(logq=1.0, momentum=0.0)),
                                                    ('bpr', 'linear', 0.0, dict(adapt=None, learning_rate=0.01))])
-def test_headline_shape_role_specialised_kernel(loss, fact, alpha, extra):
-    """B=32, GRU(100), 2048 samples (BASELINE configs[1] shape) through step_mode 2; heavy duplicates with alpha=1."""
+@pytest.mark.parametrize('step_mode', [2, 3])
+def test_headline_shape_role_specialised_kernel(loss, fact, alpha, extra, step_mode):
+    """B=32, GRU(100), 2048 samples (BASELINE configs[1] shape) through step_mode 2 (48-CTA GRU group) and 3 (GRU on one
+    thread-block cluster, weights resident in shared memory); two windows, so the resident weights are written back and
+    re-read; heavy duplicates with alpha=1."""
     from gru4rec_b200.synth import make_session_arrays
     n_items = 3000
     mk = dict(layers=[100], batch_size=32, n_sample=2048, loss=loss, final_act=fact, learning_rate=0.05, momentum=0.3, sample_alpha=alpha,
@@ -146,9 +149,9 @@ def test_headline_shape_role_specialised_kernel(loss, fact, alpha, extra):
     mk.update(extra)
     items, offset, order, supports = make_session_arrays(n_items, 40000, seed=5)
     rows = 20
-    eng, m, _, rs = make_pair(n_items, mk, n_store_rows=0, seed=3, randomize_state=False, step_mode=2)
+    eng, m, _, rs = make_pair(n_items, mk, n_store_rows=0, seed=3, randomize_state=False, step_mode=step_mode)
     eng.close()
-    eng = _lib.Engine(make_cfg(n_items, mk, sample_store=rows * 2048, step_mode=2))
+    eng = _lib.Engine(make_cfg(n_items, mk, sample_store=rows * 2048, step_mode=step_mode))
     from gpu_utils import push_weights
     push_weights(eng, m)
     if mk.get('logq', 0):
@@ -164,7 +167,7 @@ def test_headline_shape_role_specialised_kernel(loss, fact, alpha, extra):
     sched = _lib.Schedule(items, offset, order, 32, 2048, mode=0)
     steps = orc.build_train_schedule(items, offset, order, 32, 2048)
     n = 14
-    costs = eng.train_steps(sched, 0, n)
+    costs = np.concatenate([eng.train_steps(sched, 0, 9), eng.train_steps(sched, 9, n - 9)])
     ref = [m.train_step(st['X'], st['Y'], st['R'], samples=store[k], slots=st['slots']) for k, st in enumerate(steps[:n])]
     np.testing.assert_allclose(costs, ref, rtol=2e-4, atol=1e-6)
     compare_weights(eng, m, rtol=2e-3, atol=2e-5, what='headline shape')

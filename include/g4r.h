@@ -64,7 +64,9 @@ typedef struct g4r_config {
   int32_t world_size, rank;       /* data-parallel geometry (1,0 for single GPU) */
   int32_t eval_batch_size;        /* lanes reserved for the scoring path (evaluation.py batch_size); 0 = batch_size */
   int32_t step_mode;              /* 0: one kernel per phase (CUDA-graph replay); 1: persistent cooperative kernel;
-                                     2: role-specialised persistent kernel where the shape allows, else 1 */
+                                     2: role-specialised persistent kernel where the shape allows, else 1;
+                                     3: as 2, launched as thread-block clusters: the GRU phases run on one cluster with the
+                                        dense weights and optimizer state resident in shared memory (else 1) */
   int32_t reserved[7];
 } g4r_config;
 

@@ -39,7 +39,7 @@ EXPORTS = [
     'g4r_schedule_build', 'g4r_schedule_free', 'g4r_schedule_steps', 'g4r_schedule_events', 'g4r_schedule_export',
     'g4r_train_step', 'g4r_train_steps', 'g4r_upload_steps', 'g4r_run_uploaded', 'g4r_kernel_launches',
     'g4r_profile_uploaded', 'g4r_phase_name', 'g4r_phase_count', 'g4r_persistent_stamps', 'g4r_fast_windows', 'g4r_mg_unique_id', 'g4r_mg_init',
-    'g4r_eval_schedule', 'g4r_predict', 'g4r_reset_eval_hidden',
+    'g4r_eval_schedule', 'g4r_set_eval_items', 'g4r_predict', 'g4r_reset_eval_hidden',
 ]
 
 _lib = None
@@ -95,6 +95,7 @@ def load():
     lib.g4r_mg_unique_id.argtypes = [vp]
     lib.g4r_mg_init.argtypes = [vp, vp]
     lib.g4r_eval_schedule.argtypes = [vp, vp, vp, i32, i32, vp, vp, C.POINTER(i64)]
+    lib.g4r_set_eval_items.argtypes = [vp, vp, i64]
     lib.g4r_predict.argtypes = [vp, vp, i32, vp, vp]
     lib.g4r_reset_eval_hidden.argtypes = [vp]
     _lib = lib
@@ -406,6 +407,14 @@ class Engine(object):
         n = C.c_int64()
         self._check(self.lib.g4r_eval_schedule(self.h, sched.h, _ptr(cut), len(cut), mode, _ptr(rec), _ptr(mrr), C.byref(n)))
         return rec, mrr, n.value
+
+    def set_eval_items(self, items=None):
+        """Candidate item indices for eval_schedule (evaluate_gpu(items=...)); None / empty restores the whole catalogue."""
+        if items is None or len(items) == 0:
+            self._check(self.lib.g4r_set_eval_items(self.h, None, 0))
+            return
+        it = np.ascontiguousarray(items, dtype=np.int64)
+        self._check(self.lib.g4r_set_eval_items(self.h, _ptr(it), it.size))
 
     def predict(self, X, reset_mask=None):
         X = np.ascontiguousarray(X, dtype=np.int32)

@@ -30,17 +30,20 @@ __global__ void __launch_bounds__(128) k_eval_tgt(int slot, int s, float* tgt, i
   cnt[b * 2 + 0] = 0; cnt[b * 2 + 1] = 0;
 }
 
+// `subset` (evaluate_gpu(items=...), evaluation.py:52-56): the competitors are the n_cand listed items instead of the catalogue
 template <bool WRITE>
-__global__ void __launch_bounds__(EV_THREADS) k_eval_score(int slot, int s, const float* __restrict__ tgt, int* cnt, float* out) {
+__global__ void __launch_bounds__(EV_THREADS) k_eval_score(int slot, int s, const float* __restrict__ tgt, int* cnt, float* out,
+                                                           const int* __restrict__ subset, int n_cand) {
   const ModelDev& md = MD;
   extern __shared__ __align__(16) float smem[];
   float* sY = smem;                        // [EV_TB][EV_LDS]
   float* sW = sY + EV_TB * EV_LDS;         // [EV_IT][EV_LDS]
   int* sCnt = reinterpret_cast<int*>(sW + EV_IT * EV_LDS);   // [EV_TB][2]
   const int M = md.wM[s];
-  const int I = md.n_items, ldL = md.ldL;
+  const int I = subset ? n_cand : md.n_items, ldL = md.ldL;
   const int i0 = blockIdx.x * EV_IT;
   const int ni = min(EV_IT, I - i0);
+  auto item_of = [&](int pos) -> int { return subset ? subset[pos] : pos; };
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* Y = md.layer[md.n_layers - 1].y;
   const bool hoist = ldL <= EV_KT;
@@ -49,7 +52,7 @@ __global__ void __launch_bounds__(EV_THREADS) k_eval_score(int slot, int s, cons
     for (int i = tid; i < EV_IT * kw; i += EV_THREADS) {
       const int rr = i / kw, c4 = i % kw;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (rr < ni) v = ld4(md.Wy + (size_t)(i0 + rr) * ldL + c4 * 4);
+      if (rr < ni) v = ld4(md.Wy + (size_t)item_of(i0 + rr) * ldL + c4 * 4);
       st4(sW + rr * EV_LDS + c4 * 4, v);
     }
   }
@@ -71,7 +74,7 @@ __global__ void __launch_bounds__(EV_THREADS) k_eval_score(int slot, int s, cons
         for (int i = tid; i < EV_IT * kw; i += EV_THREADS) {
           const int rr = i / kw, c4 = i % kw;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (rr < ni) v = ld4(md.Wy + (size_t)(i0 + rr) * ldL + k0 + c4 * 4);
+          if (rr < ni) v = ld4(md.Wy + (size_t)item_of(i0 + rr) * ldL + k0 + c4 * 4);
           st4(sW + rr * EV_LDS + c4 * 4, v);
         }
       }
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(EV_THREADS) k_eval_score(int slot, int s, cons
       for (int q = 0; q < 8; q++) {
         const int it = i0 + warp + 8 * q;
         if (warp + 8 * q < ni) {
-          float sc = acc[q] + md.By[it];
+          float sc = acc[q] + md.By[item_of(it)];
           if (WRITE) out[(size_t)b * I + it] = sc;
           else {
             if (md.fact.kind <= G4R_ACT_SELU) sc = act_fwd(md.fact, sc);
@@ -168,6 +171,7 @@ struct EvalCtx {
   int* dCut = nullptr; double* dSums = nullptr; float* dOut = nullptr; size_t out_cap = 0;
   int cap = 0;
   int slot = -1;
+  int* dCand = nullptr; int n_cand = 0; size_t cand_cap = 0;     // candidate subset of evaluate_gpu(items=...), item indices
 };
 
 static void eval_release(g4r_handle* h) {
@@ -175,7 +179,7 @@ static void eval_release(g4r_handle* h) {
   EvalCtx& e = *static_cast<EvalCtx*>(h->eval_ctx);
   cudaFreeHost(e.hX); cudaFreeHost(e.hY); cudaFreeHost(e.hSlot); cudaFreeHost(e.hF); cudaFreeHost(e.hM); cudaFreeHost(e.hSti); cudaFreeHost(e.hG);
   cudaFree(e.dX); cudaFree(e.dY); cudaFree(e.dSlot); cudaFree(e.dF); cudaFree(e.dM); cudaFree(e.dSti); cudaFree(e.dG);
-  cudaFree(e.dCut); cudaFree(e.dSums); if (e.dOut) cudaFree(e.dOut);
+  cudaFree(e.dCut); cudaFree(e.dSums); if (e.dOut) cudaFree(e.dOut); if (e.dCand) cudaFree(e.dCand);
   slot_free(e.slot);
   delete static_cast<EvalCtx*>(h->eval_ctx);
   h->eval_ctx = nullptr;
@@ -261,7 +265,8 @@ extern "C" int g4r_eval_schedule(g4r_handle* h, const g4r_schedule* s, const int
     for (int64_t i = 0; i < w; i++) {
       eval_forward(h, e, (int)i);
       k_eval_tgt<<<(Be + 127) / 128, 128, 0, st>>>(e->slot, (int)i, h->dTgt, h->dRankCnt);
-      k_eval_score<false><<<(I + EV_IT - 1) / EV_IT, EV_THREADS, eval_smem_bytes(), st>>>(e->slot, (int)i, h->dTgt, h->dRankCnt, nullptr);
+      const int n_comp = e->n_cand > 0 ? e->n_cand : I;
+      k_eval_score<false><<<(n_comp + EV_IT - 1) / EV_IT, EV_THREADS, eval_smem_bytes(), st>>>(e->slot, (int)i, h->dTgt, h->dRankCnt, nullptr, e->n_cand > 0 ? e->dCand : nullptr, e->n_cand);
       k_eval_rank<<<1, 32, 0, st>>>(e->slot, (int)i, h->dRankCnt, e->dCut, n_cut, mode, e->dSums);
       h->launches += 3;
     }
@@ -273,6 +278,28 @@ extern "C" int g4r_eval_schedule(g4r_handle* h, const g4r_schedule* s, const int
   CK(cudaStreamSynchronize(st));
   for (int j = 0; j < n_cut; j++) { recall_sum[j] = sums[j]; mrr_sum[j] = sums[n_cut + j]; }
   if (n_events) *n_events = s->n_events;
+  return G4R_OK;
+}
+
+// evaluate_gpu(items=...) (evaluation.py:52-56,84-100): the targets are ranked against this candidate list (item indices,
+// duplicates allowed as in the reference) instead of the whole catalogue; n = 0 restores the full-catalogue ranking.
+extern "C" int g4r_set_eval_items(g4r_handle* h, const int64_t* items, int64_t n) {
+  if (!h || n < 0 || (n > 0 && !items)) return G4R_ERR_INVALID;
+  cudaSetDevice(h->cfg.device);
+  EvalCtx* e = nullptr;
+  int rc = eval_ctx(h, &e);
+  if (rc) return rc;
+  if (n == 0) { e->n_cand = 0; return G4R_OK; }
+  if (n > (int64_t)1 << 30) FAIL(G4R_ERR_INVALID, "too many candidate items");
+  std::vector<int> tmp((size_t)n);
+  for (int64_t i = 0; i < n; i++) {
+    if (items[i] < 0 || items[i] >= h->md.n_items) FAIL(G4R_ERR_INDEX, "Index out of bounds");
+    tmp[(size_t)i] = (int)items[i];
+  }
+  if (e->cand_cap < (size_t)n) { if (e->dCand) cudaFree(e->dCand); e->dCand = nullptr; e->cand_cap = 0; CK(cudaMalloc(&e->dCand, (size_t)n * sizeof(int))); e->cand_cap = (size_t)n; }
+  CK(cudaMemcpyAsync(e->dCand, tmp.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  e->n_cand = (int)n;
   return G4R_OK;
 }
 
@@ -301,7 +328,7 @@ extern "C" int g4r_predict(g4r_handle* h, const int32_t* X, int32_t batch, const
   const size_t need = (size_t)batch * I;
   if (e->out_cap < need) { if (e->dOut) cudaFree(e->dOut); CK(cudaMalloc(&e->dOut, need * sizeof(float))); e->out_cap = need; }
   eval_forward(h, e, 0);
-  k_eval_score<true><<<(I + EV_IT - 1) / EV_IT, EV_THREADS, eval_smem_bytes(), st>>>(e->slot, 0, nullptr, nullptr, e->dOut);
+  k_eval_score<true><<<(I + EV_IT - 1) / EV_IT, EV_THREADS, eval_smem_bytes(), st>>>(e->slot, 0, nullptr, nullptr, e->dOut, nullptr, 0);
   k_predict_act<<<batch, 256, 0, st>>>(e->slot, e->dOut, batch);
   h->launches += 2;
   CK(cudaGetLastError());

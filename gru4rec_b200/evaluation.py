@@ -12,13 +12,12 @@ def evaluate_gpu(gru, test_data, items=None, session_key='SessionId', item_key='
     Recall@N and MRR@N of next-item prediction, session-parallel (evaluation.py:15-147).
     Returns (recall_list, mrr_list), one entry per cut-off.  `mode` as in the reference; 'tiebreaking' adds
     U(0,1)*1e-10 noise in the reference, which is below float32 resolution for scores > 1e-3 -- it is evaluated as
-    'standard' here.  `items` (ranking against a subset) is not implemented on the device path.
+    'standard' here.  `items`: the targets are ranked against these item ids only (evaluation.py:52-56,84-100); as in the
+    reference the target's own score competes only if the target is listed, so 'conservative' can give rank 0 (MRR = inf).
     '''
     if gru.error_during_train: raise Exception
     if mode not in _MODES:
         raise NotImplementedError
-    if items is not None:
-        raise NotImplementedError('evaluate_gpu(items=...) is not implemented on the device path')
     multi_cut_off = (type(cut_off) == list) or (type(cut_off) == tuple)
     cuts = list(cut_off) if multi_cut_off else [cut_off]
     print('Measuring Recall@{} and MRR@{}'.format(','.join([str(c) for c in cuts]), ','.join([str(c) for c in cuts])))
@@ -29,7 +28,13 @@ def evaluate_gpu(gru, test_data, items=None, session_key='SessionId', item_key='
     offset_sessions[1:] = test_data.groupby(session_key).size().cumsum()
     eng = gru._ensure_engine(batch_size)
     sched = _lib.Schedule(test_data_items, offset_sessions, None, batch_size, 0, mode=1)
-    rec, mrr, n = eng.eval_schedule(sched, cuts, _MODES[mode])
+    if items is not None:
+        eng.set_eval_items(gru.itemidmap[items].values)       # KeyError for unknown ids, as the reference's gru.itemidmap[items]
+    try:
+        rec, mrr, n = eng.eval_schedule(sched, cuts, _MODES[mode])
+    finally:
+        if items is not None:
+            eng.set_eval_items(None)
     recall = [float(r) / n for r in rec]
     mrrs = [float(m) / n for m in mrr]
     return recall, mrrs

@@ -167,6 +167,11 @@ int g4r_mg_init(g4r_handle* h, const char* id128);
  * recall_sum/mrr_sum: n_cut doubles each (sums, not yet divided by the number of events). */
 int g4r_eval_schedule(g4r_handle* h, const g4r_schedule* s, const int32_t* cut_off, int32_t n_cut, int32_t mode,
                       double* recall_sum, double* mrr_sum, int64_t* n_events);
+/* evaluate_gpu(items=...) (evaluation.py:15,52-56,84-100): rank the targets against the `n` candidate item indices instead of
+ * the whole catalogue for subsequent g4r_eval_schedule calls (the target's own score competes only if the target is listed,
+ * as in the reference); n = 0 restores the full-catalogue ranking.  G4R_ERR_INDEX on an out-of-range index. */
+int g4r_set_eval_items(g4r_handle* h, const int64_t* items, int64_t n);
+
 /* predict_next_batch's device call: scores of all items for `batch` lanes; reset_mask zeroes lanes first
  * (gru4rec.py:712-717).  out: [batch x n_items] row-major. */
 int g4r_predict(g4r_handle* h, const int32_t* X, int32_t batch, const uint8_t* reset_mask, float* out);

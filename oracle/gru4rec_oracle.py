@@ -818,8 +818,9 @@ class OracleGRU4Rec:
         return cost
 
     # ---- scoring path (gru4rec.py:729-741 + evaluation.py:57-75) ----
-    def predict_step(self, X, H, slots=None, zero=None):
-        """symbolic_predict with items=None: full-catalogue scores; H (physical lanes) updated, no reset.
+    def predict_step(self, X, H, slots=None, zero=None, Y=None):
+        """symbolic_predict: full-catalogue scores (Y=None) or the scores of the columns Y, with the final activation taken
+        over exactly those columns as the reference does (gru4rec.py:735-736); H (physical lanes) updated, no reset.
         `zero`: lanes whose state is zeroed before the step (evaluation.py:136-139)."""
         M = len(X)
         slots = np.arange(M) if slots is None else np.asarray(slots)
@@ -827,17 +828,24 @@ class OracleGRU4Rec:
             zs = slots[np.asarray(zero, dtype=bool)]
             for h in H:
                 h[zs] = 0
-        yhat, C = self.forward(np.asarray(X, dtype=np.int64), None, M, predict=True, H=[h[slots] for h in H])
+        yhat, C = self.forward(np.asarray(X, dtype=np.int64), None if Y is None else np.asarray(Y, dtype=np.int64), M, predict=True, H=[h[slots] for h in H])
         for i in range(len(self.layers)):
             H[i][slots] = C['H_new'][i]
         return yhat
 
     @staticmethod
-    def ranks(yhat, Y, mode='standard'):
-        """evaluation.py:57-65 (items=None)."""
+    def ranks(yhat, Y, mode='standard', items=None):
+        """evaluation.py:52-65.  items=None: yhat is [M x n_items] and the target competes with the whole catalogue (itself
+        included).  items given: yhat is [M x (M + len(items))] over the columns concat(targets, items) (evaluation.py:94-97);
+        `others` are the candidate columns only (evaluation.py:55-56) -- the target's own score takes part only if the
+        target is in the subset, so 'conservative' can produce rank 0."""
         M = len(Y)
-        targets = yhat[np.arange(M), Y]
-        others = yhat
+        if items is None:
+            targets = yhat[np.arange(M), Y]
+            others = yhat
+        else:
+            targets = yhat[np.arange(M), np.arange(M)]
+            others = yhat[:, M:]
         if mode == 'standard' or mode == 'tiebreaking':
             return (others > targets[:, None]).sum(axis=1) + 1
         if mode == 'conservative':
@@ -846,17 +854,22 @@ class OracleGRU4Rec:
             return (others > targets[:, None]).sum(axis=1) + 0.5 * ((others == targets[:, None]).sum(axis=1) - 1) + 1
         raise NotImplementedError
 
-    def evaluate(self, test_items, offset_sessions, batch_size=100, cut_off=(20,), mode='standard'):
-        """evaluate_gpu (evaluation.py:15-147), items=None.  Returns (recall list, mrr list)."""
+    def evaluate(self, test_items, offset_sessions, batch_size=100, cut_off=(20,), mode='standard', items=None):
+        """evaluate_gpu (evaluation.py:15-147).  `items`: item INDICES of the candidate subset or None.
+        Returns (recall list, mrr list)."""
         H = [np.zeros((batch_size, L), dtype=self.dtype) for L in self.layers]
         steps = build_eval_schedule(test_items, offset_sessions, batch_size)
         rec = np.zeros(len(cut_off)); mrr = np.zeros(len(cut_off)); n = 0
+        if items is not None:
+            items = np.asarray(items, dtype=np.int64)
         for st in steps:
-            yhat = self.predict_step(st['X'], H, slots=st['slots'], zero=st['Z'])
-            rk = self.ranks(yhat, st['Y'], mode)
-            for j, c in enumerate(cut_off):
-                rec[j] += (rk <= c).sum()
-                mrr[j] += ((rk <= c) / rk).sum()
+            ycols = None if items is None else np.concatenate([np.asarray(st['Y'], dtype=np.int64), items])
+            yhat = self.predict_step(st['X'], H, slots=st['slots'], zero=st['Z'], Y=ycols)
+            rk = self.ranks(yhat, st['Y'], mode, items)
+            with np.errstate(divide='ignore', invalid='ignore'):
+                for j, c in enumerate(cut_off):
+                    rec[j] += (rk <= c).sum()
+                    mrr[j] += ((rk <= c) / rk).sum()
             n += st['M']
         return list(rec / n), list(mrr / n)
 

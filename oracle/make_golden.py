@@ -165,6 +165,17 @@ def run_one(name, dkw, mkw, fkw):
             rec, mrr = ref_evaluation.evaluate_gpu(gru, test.copy(), cut_off=[1, 5, 20], batch_size=7, mode=mode)
         out['eval_%s_recall' % mode] = np.array([float(r) for r in rec])
         out['eval_%s_mrr' % mode] = np.array([float(r) for r in mrr])
+    # the same with a candidate subset (`items=`, evaluation.py:52-56,84-100): every third item id; targets outside the subset
+    # give rank 0 in conservative mode (the reference then reports MRR = inf) -- kept as the reference computes it
+    sub_ids = gru.itemidmap.index.values[::3].copy()
+    out['eval_items_ids'] = sub_ids
+    # ('median' cannot be generated: `others == targets` is a Python bool under Theano's operator overloading, evaluation.py:64)
+    for mode in ('standard', 'conservative'):
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf), np.errstate(divide='ignore', invalid='ignore'):
+            rec, mrr = ref_evaluation.evaluate_gpu(gru, test.copy(), items=sub_ids, cut_off=[1, 5, 20], batch_size=7, mode=mode)
+        out['eval_items_%s_recall' % mode] = np.array([float(r) for r in rec])
+        out['eval_items_%s_mrr' % mode] = np.array([float(r) for r in mrr])
     # predict_next_batch on a fixed probe (reference serving path, gru4rec.py:665-728)
     probe_items = gru.itemidmap.index.values[:5]
     sess = np.arange(5)

@@ -91,6 +91,17 @@ def test_golden_evaluation_through_cuda(name):
             rec, mrr = evaluation.evaluate_gpu(gru, te.copy(), cut_off=[1, 5, 20], batch_size=7, mode=mode)
         np.testing.assert_allclose(rec, g['eval_%s_recall' % mode], rtol=1e-4, atol=1e-9)
         np.testing.assert_allclose(mrr, g['eval_%s_mrr' % mode], rtol=1e-4, atol=1e-9)
+    # candidate subset (evaluate_gpu(items=...)): the reference's own numbers; one rank flip allowed where the reference takes
+    # the softmax over the subset columns only (see tests/test_oracle_golden.py)
+    n_ev = len(te) - te['SessionId'].nunique()
+    for mode in ('standard', 'conservative'):
+        with contextlib.redirect_stdout(io.StringIO()):
+            rec, mrr = evaluation.evaluate_gpu(gru, te.copy(), items=g['eval_items_ids'], cut_off=[1, 5, 20], batch_size=7, mode=mode)
+        np.testing.assert_allclose(rec, g['eval_items_%s_recall' % mode], rtol=1e-4, atol=1.0 / n_ev + 1e-9)
+        np.testing.assert_allclose(mrr, g['eval_items_%s_mrr' % mode], rtol=1e-4, atol=0.5 / n_ev + 1e-9)
+    with contextlib.redirect_stdout(io.StringIO()):      # the subset is cleared after the call
+        rec, mrr = evaluation.evaluate_gpu(gru, te.copy(), cut_off=[1, 5, 20], batch_size=7, mode='standard')
+    np.testing.assert_allclose(rec, g['eval_standard_recall'], rtol=1e-4, atol=1e-9)
     probe = g['predict_probe_items']
     p1 = gru.predict_next_batch(np.arange(5), probe, None, batch=5)
     p2 = gru.predict_next_batch(np.arange(5), probe[::-1].copy(), None, batch=5)

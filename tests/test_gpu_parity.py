@@ -212,6 +212,20 @@ def test_eval_matches_oracle(mode_kw):
         assert n == sched.n_events
         np.testing.assert_allclose(rec / n, r0, rtol=1e-4, atol=1e-9)
         np.testing.assert_allclose(mrr / n, m0, rtol=1e-4, atol=1e-9)
+    # candidate subset with duplicates and items that never occur as targets (evaluate_gpu(items=...))
+    sub = np.concatenate([np.arange(0, d['n_items'], 4), [3, 3, 7]])
+    eng.set_eval_items(sub)
+    for mode, code in (('standard', 0), ('conservative', 1), ('median', 2)):
+        rec, mrr, n = eng.eval_schedule(sched, [1, 5, 20], code)
+        r0, m0 = m.evaluate(d['data_items'], d['offset_sessions'], batch_size=11, cut_off=(1, 5, 20), mode=mode, items=sub)
+        np.testing.assert_allclose(rec / n, r0, rtol=1e-4, atol=1e-9)
+        np.testing.assert_allclose(mrr / n, m0, rtol=1e-4, atol=1e-9)
+    with pytest.raises(IndexError):
+        eng.set_eval_items([0, d['n_items']])
+    eng.set_eval_items(None)
+    rec, mrr, n = eng.eval_schedule(sched, [1, 5, 20], 0)
+    r0, m0 = m.evaluate(d['data_items'], d['offset_sessions'], batch_size=11, cut_off=(1, 5, 20), mode='standard')
+    np.testing.assert_allclose(rec / n, r0, rtol=1e-4, atol=1e-9)
 
 
 def test_predict_matches_oracle():

@@ -221,6 +221,9 @@ __device__ void fk_f1(const ModelDev& md, FastSmem& sm, int s, int cta, const un
   if (c0 >= 2 * L) return;
   const int W = min(FK_W1, 2 * L - c0);
   fk_stage_lanes(md, sm, s, M);
+  // if the helper CTAs' input-row updates are already complete (the usual case), the epilogue operand is fetched before the
+  // product instead of after it
+  if (tid == 0) sm.sFlag[3] = (!wait_ctr || ld_acquire_u32(wait_ctr) >= wait_target) ? 1 : 0;
   const int kw = ldL / 4;
   // stage H rows (zero for out-of-range lanes) and the transposed weight slab Wt[j][k] = Wrz[k][c0 + j]
   stage_rows4(sm.gA, FK_LDS, FK_B, kw, [&](int rr) -> const float* { const int sl = sm.gIdx[rr]; return sl >= 0 ? ly.H + (size_t)sl * ldL : nullptr; });
@@ -230,14 +233,19 @@ __device__ void fk_f1(const ModelDev& md, FastSmem& sm, int s, int cta, const un
   }
   const int b = tid & 31, jsel = tid >> 5;
   __syncthreads();
+  const bool early = sm.sFlag[3] != 0;
+  float pre = 0.f;
+  if (early && jsel < W && b < M) pre = ly.Wx[(size_t)sm.gIdx[FK_B + b] * ly.ld3 + L + c0 + jsel] + ly.Bh[L + c0 + jsel];
   float acc[FK_W1];
   fk_slab_dot<FK_W1>(acc, sm.gA, FK_LDS, sm.gW, L);
   const float v = fk_slab_reduce<FK_W1>(acc, sm.gW + 8 * FK_LDS, jsel);
-  // the gathered input rows may still be in flight on the helper CTAs (previous step's update): wait only now, after
+  // otherwise the gathered input rows are still in flight on the helper CTAs (previous step's update): wait now, after
   // the H @ Wrz part, then fetch the epilogue operands (gathered row element + bias)
-  if (wait_ctr) { if (tid == 0) wait_ge(wait_ctr, wait_target); __syncthreads(); }
-  float pre = 0.f;
-  if (jsel < W && b < M) pre = ly.Wx[(size_t)sm.gIdx[FK_B + b] * ly.ld3 + L + c0 + jsel] + ly.Bh[L + c0 + jsel];
+  if (!early) {
+    if (tid == 0) wait_ge(wait_ctr, wait_target);
+    __syncthreads();
+    if (jsel < W && b < M) pre = ly.Wx[(size_t)sm.gIdx[FK_B + b] * ly.ld3 + L + c0 + jsel] + ly.Bh[L + c0 + jsel];
+  }
   if (jsel < W && b < M) {
     const int c = c0 + jsel;
     const float g = sigmoidf_(v + pre);
@@ -335,26 +343,16 @@ __device__ void fk_dense(const ModelDev& md, FastSmem& sm, int s, int cta) {
   const int CB = (3 * L + FK_G - 1) / FK_G;       // Bh entries per CTA
   const int cb0 = cta * CB, ncb = max(0, min(CB, 3 * L - cb0));
   if (nr == 0 && ncb == 0) return;
-  __syncthreads();
-  // stage dvec [32 x 3L] and the (Hold, Hold*r) columns of this slab
-  stage_rows4(sm.gA, 388, FK_B, ld3 / 4, [&](int rr) -> const float* { return rr < M ? ly.dvec + (size_t)rr * ld3 : nullptr; });
   float* sHo = sm.gW;                  // [R][32]
   float* sHr = sm.gW + 8 * FK_B;       // [R][32]
-  for (int i = tid; i < nr * FK_B; i += FK_THREADS) {
-    const int rr = i / FK_B, b = i % FK_B;
-    float ho = 0.f, r = 0.f;
-    if (b < M) { ho = ly.Hold[(size_t)b * ldL + k0 + rr]; r = ly.r[(size_t)b * ldL + k0 + rr]; }
-    sHo[i] = ho; sHr[i] = ho * r;
-  }
-  __syncthreads();
   // outputs: nr x L (Wh), nr x 2L (Wrz), ncb (Bh).  Each thread owns U outputs at a time: their parameter / Adagrad /
   // momentum values are loaded first, the U batch reductions (<= 32 lanes) run interleaved, then the updates are stored.
   const int nWh = nr * L, nWrz = nr * 2 * L, total = nWh + nWrz + ncb;
   constexpr int U = 2;
   const bool ada = md.adapt == G4R_ADAPT_ADAGRAD, mom = md.mom > 0.f;
-  for (int o0 = 0; o0 < total; o0 += U * FK_THREADS) {
-    float* p[U]; float* pa[U]; float* pv[U]; const float* av[U]; const float* bv[U]; bool ok[U]; bool bias[U];
-    float p0[U], a0[U], v0[U], g[U];
+  float* p[U]; float* pa[U]; float* pv[U]; const float* av[U]; const float* bv[U]; bool ok[U]; bool bias[U];
+  float p0[U], a0[U], v0[U], g[U];
+  auto load_ops = [&](int o0) {
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const int o = o0 + u * FK_THREADS + tid;
@@ -381,6 +379,22 @@ __device__ void fk_dense(const ModelDev& md, FastSmem& sm, int s, int cta) {
       v0[u] = (ok[u] && mom && pv[u]) ? *pv[u] : 0.f;
       g[u] = 0.f;
     }
+  };
+  // this CTA's rows of Wh / Wrz / Bh are written by nobody else: the operands of the first pass are fetched before the
+  // dvec rows are staged, so the two global round trips overlap
+  load_ops(0);
+  __syncthreads();
+  // stage dvec [32 x 3L] and the (Hold, Hold*r) columns of this slab
+  stage_rows4(sm.gA, 388, FK_B, ld3 / 4, [&](int rr) -> const float* { return rr < M ? ly.dvec + (size_t)rr * ld3 : nullptr; });
+  for (int i = tid; i < nr * FK_B; i += FK_THREADS) {
+    const int rr = i / FK_B, b = i % FK_B;
+    float ho = 0.f, r = 0.f;
+    if (b < M) { ho = ly.Hold[(size_t)b * ldL + k0 + rr]; r = ly.r[(size_t)b * ldL + k0 + rr]; }
+    sHo[i] = ho; sHr[i] = ho * r;
+  }
+  __syncthreads();
+  for (int o0 = 0; o0 < total; o0 += U * FK_THREADS) {
+    if (o0 > 0) load_ops(o0);
     for (int b = 0; b < M; b++) {
 #pragma unroll
       for (int u = 0; u < U; u++) g[u] = bias[u] ? g[u] + bv[u][b * 388] : fmaf(av[u][b], bv[u][b * 388], g[u]);

@@ -385,7 +385,8 @@ __device__ void fk_dense(const ModelDev& md, FastSmem& sm, int s, int cta) {
   load_ops(0);
   __syncthreads();
   // stage dvec [32 x 3L] and the (Hold, Hold*r) columns of this slab
-  stage_rows4(sm.gA, 388, FK_B, ld3 / 4, [&](int rr) -> const float* { return rr < M ? ly.dvec + (size_t)rr * ld3 : nullptr; });
+  // 32 x 75 quads at L = 100: five loads in flight per thread cover the whole block in one round trip
+  stage_rows_n<5>(sm.gA, 388, FK_B, ld3 / 4, [&](int rr) -> const float* { return rr < M ? ly.dvec + (size_t)rr * ld3 : nullptr; });
   for (int i = tid; i < nr * FK_B; i += FK_THREADS) {
     const int rr = i / FK_B, b = i % FK_B;
     float ho = 0.f, r = 0.f;
@@ -517,6 +518,13 @@ __device__ void fk_b1(const ModelDev& md, SM& sm, int s, int cta, int ncta) {
   const int e0 = cta * per;
   float* red = sm.sPart;                                  // [FK_NW][per]  (per <= 128 for M*ldL <= 4096*... checked on host)
   const size_t cs = (size_t)md.B * ldL;
+  // forward saves of this thread's output element (per <= 128 <= FK_THREADS: at most one element per thread), fetched up
+  // front so that their round trip overlaps the loads of the chunk partials
+  float pht = 0.f, pho = 0.f, pz = 0.f, pah = 0.f;
+  if (!CL && tid < per && e0 + tid < E && (e0 + tid) % ldL < L) {
+    const size_t o = (size_t)((e0 + tid) / ldL) * ldL + (e0 + tid) % ldL;
+    pht = ly.ht[o]; pho = ly.Hold[o]; pz = ly.z[o]; pah = ly.ah[o];
+  }
   for (int eb = 0; eb < per; eb += 32) {
     const int e = e0 + eb + lane;
     float d = 0.f;
@@ -539,7 +547,7 @@ __device__ void fk_b1(const ModelDev& md, SM& sm, int s, int cta, int ncta) {
     for (int w = 0; w < FK_NW; w++) dy += red[w * per + i];
     const size_t o = (size_t)b * ldL + c;
     if (CL) { ly.dy[o] = dy; continue; }     // cluster variant: the GRU cluster owns ht / z / ah and derives da_h, da_z itself
-    const float ht = ly.ht[o], ho = ly.Hold[o], z = ly.z[o], ah = ly.ah[o];
+    const float ht = pht, ho = pho, z = pz, ah = pah;
     float dh = dy;
     if (md.p_drop_h > 0.f) dh *= drop_scale(md.drop_seed, md.wG[s], 0u, (uint32_t)(b * L + c), 1.0f - md.p_drop_h);
     const float dz = dh * (ht - ho);

@@ -219,7 +219,25 @@ __device__ __forceinline__ void tile_gemm(float (&acc)[GT][GT], TileSrc a, TileS
   }
 }
 
-// stage `nrows` rows of `kw` float4 into shared memory, four 16-byte loads in flight per thread before any store
+// stage `nrows` rows of `kw` float4 into shared memory, NU 16-byte loads in flight per thread before any store
+template <int NU, class FRow>
+__device__ __forceinline__ void stage_rows_n(float* sdst, int sld, int nrows, int kw, FRow rowptr) {
+  const int total = nrows * kw;
+  for (int i0 = 0; i0 < total; i0 += NU * (int)blockDim.x) {
+    float4 v[NU];
+#pragma unroll
+    for (int u = 0; u < NU; u++) {
+      const int i = i0 + u * (int)blockDim.x + (int)threadIdx.x;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < total) { const float* rp = rowptr(i / kw); if (rp) v[u] = ld4(rp + (i % kw) * 4); }
+    }
+#pragma unroll
+    for (int u = 0; u < NU; u++) {
+      const int i = i0 + u * (int)blockDim.x + (int)threadIdx.x;
+      if (i < total) st4(sdst + (i / kw) * sld + (i % kw) * 4, v[u]);
+    }
+  }
+}
 template <class FRow>
 __device__ __forceinline__ void stage_rows4(float* sdst, int sld, int nrows, int kw, FRow rowptr) {
   const int total = nrows * kw;

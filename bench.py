@@ -302,6 +302,7 @@ def main():
                      'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': frac, 'traffic': 3812352 if world == 1 else None,
                      'peak_source': peak_src, 'algorithmic_bytes_per_launch': lg_bytes, 'us_per_launch': us_launch, 'traffic_source': 'ncu --set full dram read+write of k_lossgrad, profiles/r1_ncu_full_k_lossgrad.txt',
                      'dominant_phase_by_time': dom_name, 'phase_us': phase_us, 'k_fast_update_phase': fast_phase,
+                     'k_fast_dram_traffic_per_step': {'bytes': 228705, 'source': 'ncu --set full of the timed window (2000 mini-batches in one launch): 202.3 MB read + 255.1 MB written, profiles/r1_ncu_full_k_fast_steady.txt; the touched rows stay in the 126 MB L2'},
                      'whole_step': {'algorithmic_bytes': ALGO_BYTES_PER_STEP, 'achieved': ALGO_BYTES_PER_STEP * (value / world) / 1e9,
                                     'frac': ALGO_BYTES_PER_STEP * (value / world) / 1e9 / peak,
                                     'note': 'latency-bound: dependent phases per mini-batch, working set near L2 size'}},

@@ -762,7 +762,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) k_fast_t(int slot, int n_steps,
         else if (md.loss == G4R_LOSS_BPR_MAX) { r2 = __fdiv_rn(A, Z); r3 = __fdiv_rn(Q, Z); r4 = __fdiv_rn(D, Z); loss = -logf(r2 + G4R_EPS_LOG) + md.bpreg * r3; }
         else if (md.loss == G4R_LOSS_TOP1_MAX) { r2 = __fdiv_rn(A, Z); r4 = __fdiv_rn(D, Z); loss = r2; }
         else if (md.loss == G4R_LOSS_BPR) { loss = A; r4 = D; }
-        else { const float c = sigmoidf_(tt * tt); loss = __fdiv_rn(A, (float)N) - __fdiv_rn(c, (float)(M + md.S_cfg)); r4 = D; }
+        else { const float c = sigmoidf_(tt * tt); loss = (float)M * (__fdiv_rn(A, (float)N) - __fdiv_rn(c, (float)(M + md.S_cfg))); r4 = D; }
         st4(rs, make_float4(r0, r1, r2, r3));
         st4(rs + 4, make_float4(r4, r5, loss, 0.f));
         red_release_add(&fs->stats, 1u);

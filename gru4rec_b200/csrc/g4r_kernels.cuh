@@ -707,9 +707,10 @@ __device__ void phase_stats(const ModelDev& md, int s, int cta, int ncta, float*
       } else if (md.loss == G4R_LOSS_BPR) {
         loss = A;
         rs[4] = D; rs[5] = tt;
-      } else {  // TOP1 (gru4rec.py:242-244): mean over the N columns, last term over M + n_sample
+      } else {  // TOP1 (gru4rec.py:242-244): mean over the N columns, last term over M + n_sample; the reference subtracts a
+        // COLUMN from the row-mean vector, which broadcasts to [M x M] before the sum: everything is M times the row expression
         const float c = sigmoidf_(tt * tt);
-        loss = __fdiv_rn(A, (float)N) - __fdiv_rn(c, (float)(M + md.S_cfg));
+        loss = (float)M * (__fdiv_rn(A, (float)N) - __fdiv_rn(c, (float)(M + md.S_cfg)));
         rs[4] = D; rs[5] = tt;
       }
       rs[6] = loss;
@@ -756,7 +757,7 @@ __device__ __forceinline__ float loss_grad_elem(const ModelDev& md, const float*
   } else if (md.loss == G4R_LOSS_BPR) {
     if (is_t) dy = -rs[4];
     else dy = 1.f - sigmoidf_(t - y);
-  } else {  // TOP1
+  } else {  // TOP1 (M times the row expression, see the statistics phase)
     const float invN = __fdiv_rn(1.0f, (float)N);
     if (is_t) {
       const float c = sigmoidf_(t * t);
@@ -765,6 +766,7 @@ __device__ __forceinline__ float loss_grad_elem(const ModelDev& md, const float*
       const float a1 = sigmoidf_(y - t), b1 = sigmoidf_(y * y);
       dy = (a1 * (1.f - a1) + b1 * (1.f - b1) * 2.f * y) * invN;
     }
+    dy *= (float)M;
   }
   return dy * fd * invB;
 }

@@ -214,12 +214,18 @@ class GRU4Rec:
             names.append('E')
         return names
 
-    def _make_config(self, sample_store, eval_lanes):
+    def _make_config(self, sample_store, eval_lanes, training=True):
+        """`training=False`: an engine for the scoring path only (evaluate_gpu / predict_next_batch of a loaded model): the
+        optimiser options are irrelevant there, so a model the reference trained with adam / rmsprop / adadelta, grad_cap or
+        smoothing can still be scored; fit() with those options raises NotImplementedError."""
         cfg = _lib.G4RConfig()
-        if self.adapt not in _lib.ADAPT:
-            raise NotImplementedError('adapt=%r is not implemented on the device path' % (self.adapt,))
-        if self.grad_cap:
-            raise NotImplementedError('grad_cap is not implemented on the device path')
+        if training:
+            if self.adapt not in _lib.ADAPT:
+                raise NotImplementedError('adapt=%r is not implemented on the device path' % (self.adapt,))
+            if self.grad_cap:
+                raise NotImplementedError('grad_cap is not implemented on the device path')
+            if self.smoothing:
+                raise NotImplementedError('smoothing is not implemented on the device path')
         cfg.n_items = self.n_items
         cfg.n_layers = len(self.layers)
         for i, l in enumerate(self.layers):
@@ -237,10 +243,10 @@ class GRU4Rec:
         cfg.lmbd = self.lmbd
         cfg.n_sample = self.n_sample
         cfg.sample_alpha = self.sample_alpha
-        cfg.smoothing = self.smoothing
+        cfg.smoothing = self.smoothing if training else 0.0
         cfg.bpreg = self.bpreg
         cfg.logq = self.logq
-        cfg.adapt = _lib.ADAPT[self.adapt]
+        cfg.adapt = _lib.ADAPT[self.adapt] if training else _lib.ADAPT[None]
         cfg.sample_store = int(sample_store)
         cfg.dropout_seed = self.dropout_seed
         cfg.mrg_seed = 12345
@@ -261,7 +267,7 @@ class GRU4Rec:
             pass
         return 1, 0
 
-    def _build_engine(self, sample_store=0, eval_lanes=None):
+    def _build_engine(self, sample_store=0, eval_lanes=None, training=True):
         eval_lanes = self.eval_lanes if eval_lanes is None else eval_lanes
         host = self._host if self._host is not None else self._pull_host()
         if self._engine is not None:
@@ -271,7 +277,7 @@ class GRU4Rec:
         if world > 1:
             import torch
             self.device = torch.cuda.current_device()
-        eng = _lib.Engine(self._make_config(sample_store, eval_lanes), device=self.device)
+        eng = _lib.Engine(self._make_config(sample_store, eval_lanes, training), device=self.device)
         for name in self._param_names():
             eng.set(name, host[name])
         if world > 1:
@@ -312,7 +318,7 @@ class GRU4Rec:
 
     def _ensure_engine(self, eval_lanes):
         if self._engine is None or self._engine_eval_lanes < eval_lanes:
-            self._build_engine(sample_store=0, eval_lanes=max(eval_lanes, self.eval_lanes))
+            self._build_engine(sample_store=0, eval_lanes=max(eval_lanes, self.eval_lanes), training=False)
         return self._engine
 
     def generate_neg_samples(self, pop, length):

@@ -162,16 +162,20 @@ def loss_and_grad(loss, yhat, M, n_sample, bpreg=1.0, smoothing=0.0):
         g[ar, ar] += np.sum(-invA[:, None] * s * dsg, axis=1)
         return dt(L), g
     if loss == 'top1':  # gru4rec.py:242-244
+        # NB the reference subtracts a COLUMN (gpu_diag(..., keepdims=True), broadcastable (False, True), custom_theano_ops.py:39)
+        # from the row-mean VECTOR, which broadcasts to an [M x M] matrix before T.sum: the loss -- and every gradient -- is
+        # M times the per-row expression.  Pinned by tests/golden/top1_embed_selu.npz (the shim reproduces the broadcast).
         nn_ = dt(M + n_sample)
         a = sigmoid(yhat - diag[:, None])
         b = sigmoid(yhat * yhat)
         c = sigmoid(diag * diag)
-        L = np.sum(np.mean(a + b, axis=1) - c / nn_)
+        Mf = dt(m)
+        L = Mf * np.sum(np.mean(a + b, axis=1) - c / nn_)
         da = a * (dt(1) - a) / dt(n)
         db = b * (dt(1) - b) * 2 * yhat / dt(n)
         g = da + db
         g[ar, ar] += -da.sum(axis=1) - c * (dt(1) - c) * 2 * diag / nn_
-        return dt(L), g
+        return dt(L), Mf * g
     if loss == 'top1-max':  # gru4rec.py:245-248
         s, hm = softmax_neg(yhat)
         a = sigmoid(yhat - diag[:, None])

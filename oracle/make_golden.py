@@ -58,6 +58,37 @@ CONFIGS = {
     'xe_none_default': (dict(n_items=100, n_events=900, seed=6),        # BASELINE configs[0] shape, shrunk
                         dict(loss='cross-entropy', final_act='softmax', layers=[16], batch_size=8, n_epochs=1, n_sample=32),
                         dict(sample_store=32 * 20)),
+    # ---- the rest of the option surface ----
+    'bpr_none_relu': (dict(n_items=50, n_events=600, seed=7),
+                      dict(loss='bpr', final_act='linear', hidden_act='relu', layers=[10], batch_size=5, n_epochs=1,
+                           learning_rate=0.05, momentum=0.0, n_sample=12, sample_alpha=0.5),
+                      dict(sample_store=12 * 30)),
+    'top1_embed_selu': (dict(n_items=55, n_events=650, seed=8),
+                        dict(loss='top1', final_act='selu-1.05-1.67', hidden_act='elu-1.0', layers=[9], batch_size=6, n_epochs=1,
+                             embedding=6, learning_rate=0.05, momentum=0.2, n_sample=10, sample_alpha=0.75, lmbd=0.0005),
+                        dict(sample_store=10 * 30)),
+    'xelogit_shared_leaky': (dict(n_items=45, n_events=600, seed=9),
+                             dict(loss='xe_logit', final_act='softmax_logit', hidden_act='leaky-0.2', layers=[10], batch_size=5, n_epochs=1,
+                                  constrained_embedding=True, learning_rate=0.1, momentum=0.1, n_sample=14, sample_alpha=0.5,
+                                  dropout_p_embed=0.2),
+                             dict(sample_store=14 * 30)),
+    'bprmax_none_cpustore': (dict(n_items=60, n_events=700, seed=10),       # legacy host-side sample store (gru4rec.py:507-514,551-554,605-615)
+                             dict(loss='bpr-max', final_act='elu-0.5', layers=[12], batch_size=6, n_epochs=2, learning_rate=0.1,
+                                  momentum=0.2, n_sample=16, sample_alpha=0.75, bpreg=0.5),
+                             dict(sample_store=16 * 40, store_type='cpu')),
+    # optimiser variants / clipping / smoothing: implemented by the oracle only (the device path raises NotImplementedError)
+    'xe_none_adam': (dict(n_items=50, n_events=500, seed=11),
+                     dict(loss='cross-entropy', final_act='softmax', layers=[8], batch_size=5, n_epochs=1, n_sample=10,
+                          adapt='adam', adapt_params=[0.9, 0.999], learning_rate=0.01, momentum=0.0),
+                     dict(sample_store=10 * 30)),
+    'bprmax_none_rmsprop_cap': (dict(n_items=50, n_events=500, seed=12),
+                                dict(loss='bpr-max', final_act='elu-0.5', layers=[8], batch_size=5, n_epochs=1, n_sample=10,
+                                     adapt='rmsprop', adapt_params=[0.9], learning_rate=0.01, momentum=0.1, grad_cap=0.05),
+                                dict(sample_store=10 * 30)),
+    'xe_embed_adadelta_smooth': (dict(n_items=50, n_events=500, seed=13),
+                                 dict(loss='cross-entropy', final_act='softmax', layers=[8], batch_size=5, n_epochs=1, n_sample=10,
+                                      embedding=6, adapt='adadelta', adapt_params=[0.9], learning_rate=1.0, momentum=0.0, smoothing=0.1),
+                                 dict(sample_store=10 * 30)),
 }
 
 
@@ -131,6 +162,19 @@ def run_one(name, dkw, mkw, fkw):
         X[s, :m] = c[1][0]; Y[s, :m] = c[1][1][:m]; R[s, :m] = np.asarray(c[1][3]).reshape(-1)
         cost[s] = c[2][0]
     out.update(step_X=X, step_Y=Y, step_R=R, step_M=M, step_cost=cost)
+    if fkw.get('store_type', 'gpu') == 'cpu' and mkw['n_sample']:
+        # host-side store (gru4rec.py:551-554,605-615): the samples travel in the Y input of every call; regroup them into the
+        # stores generate_neg_samples() produced (generate_length rows each, the pointer is not reset between epochs)
+        glen = fkw['sample_store'] // mkw['n_sample']
+        neg = np.stack([np.asarray(c[1][1][int(c[1][2]):], dtype=np.int64) for c in tr])
+        n_st = (n + glen - 1) // glen
+        st_all = np.zeros((n_st, glen, mkw['n_sample']), dtype=np.int64)
+        for k in range(n):
+            st_all[k // glen, k % glen] = neg[k]
+        out['sample_stores'] = st_all
+        out['store_first_step'] = np.arange(n_st, dtype=np.int64) * glen
+        out['store_rows_used'] = np.minimum(glen, n - np.arange(n_st) * glen).astype(np.int64)
+        out['host_sampler'] = np.array(1)
     # sample stores, and the index of the first train step served by each store
     stores = []
     first_step = []

@@ -85,6 +85,7 @@ class Var(object):
     def __rtruediv__(self, o): return self._bin(o, _div, True)
     def __floordiv__(self, o): return self._bin(o, lambda a, b: a // b)
     def __pow__(self, o): return self._bin(o, lambda a, b: a ** b)
+    def __rpow__(self, o): return self._bin(o, lambda a, b: a ** b, True)
     def __neg__(self): return Var(lambda a: -a, [self])
     def __lt__(self, o): return self._bin(o, lambda a, b: a < b)
     def __le__(self, o): return self._bin(o, lambda a, b: a <= b)
@@ -219,7 +220,9 @@ def _index(a, idx):
 # ---- theano.tensor functions ----
 def tsum(x, axis=None, keepdims=False):
     if isinstance(x, (list, tuple)):
-        return Var(lambda *xs: torch.stack([torch.as_tensor(v) for v in xs]).sum(), list(x))
+        if len(x) == 0:                                    # as_tensor_variable([]) -> empty vector, whose sum is 0.0
+            return Var(lambda: torch.zeros((), dtype=torch.float32), [])
+        return Var(lambda *xs: torch.stack([torch.as_tensor(v, dtype=torch.float32) if not torch.is_tensor(v) else v for v in xs]).sum(), list(x))
 
     def f(a):
         if a.dtype == torch.bool:

@@ -16,7 +16,14 @@ from gpu_utils import make_cfg
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-NODROP = [n for n in golden_names() if not (load_golden(n)['model_kwargs'].get('dropout_p_hidden', 0) or load_golden(n)['model_kwargs'].get('dropout_p_embed', 0))]
+def _oracle_only(mk):
+    """training options only the oracle implements: the device path raises NotImplementedError in fit()"""
+    return mk.get('adapt', 'adagrad') not in ('adagrad', None) or bool(mk.get('grad_cap', 0)) or bool(mk.get('smoothing', 0))
+
+
+ORACLE_ONLY = [n for n in golden_names() if _oracle_only(load_golden(n)['model_kwargs'])]
+NODROP = [n for n in golden_names() if n not in ORACLE_ONLY and
+          not (load_golden(n)['model_kwargs'].get('dropout_p_hidden', 0) or load_golden(n)['model_kwargs'].get('dropout_p_embed', 0))]
 
 
 @pytest.mark.parametrize('step_mode', [0, 1, 2, 3])
@@ -211,3 +218,37 @@ def test_reference_written_pickle_evaluates_on_device():
         rec, mrr = evaluation.evaluate_gpu(m, te.copy(), cut_off=[1, 5, 20], batch_size=7, mode='standard')
     np.testing.assert_allclose(rec, g['eval_standard_recall'], rtol=1e-4, atol=1e-9)
     np.testing.assert_allclose(mrr, g['eval_standard_mrr'], rtol=1e-4, atol=1e-9)
+
+
+@pytest.mark.parametrize('name', ORACLE_ONLY)
+def test_unimplemented_training_options_raise_in_fit(name):
+    """adam / rmsprop / adadelta, grad_cap and smoothing exist in the oracle only; fit() must fail loudly (no silent fallback),
+    while a model the reference trained with them can still be scored (test_golden_evaluation_through_cuda covers that)."""
+    import gru4rec
+    g = load_golden(name)
+    tr, _ = frames(g)
+    gru = gru4rec.GRU4Rec(**g['model_kwargs'])
+    with contextlib.redirect_stdout(io.StringIO()):
+        with pytest.raises(NotImplementedError):
+            gru.fit(tr.copy(), **g['fit_kwargs'])
+
+
+def test_fit_from_scratch_reproduces_the_reference_run():
+    """store_type='cpu' makes the whole run a function of NumPy's global stream (seed 42 in init, gru4rec.py:254; samples from
+    np.random.rand, :507-514): GRU4Rec.fit() from scratch must reproduce the REFERENCE's epoch losses and final weights."""
+    import gru4rec
+    g = load_golden('bprmax_none_cpustore')
+    tr, _ = frames(g)
+    gru = gru4rec.GRU4Rec(**g['model_kwargs'])
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        gru.fit(tr.copy(), **g['fit_kwargs'])
+    assert not gru.error_during_train
+    import re
+    losses = [float(x) for x in re.findall(r'loss: ([0-9.]+)', buf.getvalue())]
+    np.testing.assert_allclose(losses, g['epoch_loss'], rtol=2e-4, atol=2e-6)
+    fw = init_weights(g, 'final_')
+    np.testing.assert_allclose(gru.Wy.get_value(), fw['Wy'], rtol=5e-3, atol=1e-4)
+    np.testing.assert_allclose(gru.By.get_value().reshape(-1), fw['By'].reshape(-1), rtol=5e-3, atol=1e-4)
+    np.testing.assert_allclose(gru.Wh[0].get_value(), fw['Wh'][0], rtol=5e-3, atol=1e-4)
+    np.testing.assert_allclose(gru.Wx[0].get_value(), fw['Wx'][0], rtol=5e-3, atol=1e-4)

@@ -54,6 +54,18 @@ def test_sample_store_matches_reference(name):
     tr, _ = frames(g)
     mk = g['model_kwargs']
     d = orc.prepare_fit_data(tr)
+    if 'host_sampler' in g:
+        # store_type='cpu' (gru4rec.py:507-514): np.searchsorted(pop, np.random.rand(...)) (side='left', float64 CDF) on the global
+        # NumPy stream that init() seeded with 42 -- reproduced by seeding, replaying init()'s draws and sampling store by store
+        m = _model(g)
+        m.init(int(g['n_items']))                          # np.random.seed(42) + the weight draws, as the reference's init()
+        pop = orc.sampling_cdf(d['supports'], mk.get('sample_alpha', 0.75))
+        glen = g['sample_stores'].shape[1]
+        for k in range(len(g['sample_stores'])):
+            st = np.searchsorted(pop, np.random.rand(mk['n_sample'] * glen)).reshape(glen, mk['n_sample'])
+            used = int(g['store_rows_used'][k])
+            np.testing.assert_array_equal(st[:used], g['sample_stores'][k][:used])
+        return
     P = orc.sampling_cdf(d['supports'], mk.get('sample_alpha', 0.75)).astype(np.float32)
     for k in range(len(g['sample_stores'])):
         st = orc.searchsorted_k2(P, g['sample_uniforms'][k]).reshape(g['sample_stores'][k].shape)

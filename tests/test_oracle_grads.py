@@ -47,7 +47,9 @@ def t_loss(loss, yhat, M, n_sample, bpreg, smoothing):
         s = t_softmax_neg(yhat)
         return torch.sum(-torch.log(torch.sum(torch.sigmoid(diag[:, None] - yhat) * s, dim=1) + 1e-24) + bpreg * torch.sum((yhat ** 2) * s, dim=1))
     if loss == 'top1':
-        return torch.sum(torch.mean(torch.sigmoid(-diag[:, None] + yhat) + torch.sigmoid(yhat ** 2), dim=1) - torch.sigmoid(diag ** 2) / (M + n_sample))
+        # as written in the reference (gru4rec.py:242-244): ydiag is a COLUMN, so the difference broadcasts to [M x M]
+        ydiag = diag[:, None]
+        return torch.sum(torch.mean(torch.sigmoid(-ydiag + yhat) + torch.sigmoid(yhat ** 2), dim=1) - torch.sigmoid(ydiag ** 2) / (M + n_sample))
     if loss == 'top1-max':
         s = t_softmax_neg(yhat)
         return torch.sum(s * (torch.sigmoid(-diag[:, None] + yhat) + torch.sigmoid(yhat ** 2)))

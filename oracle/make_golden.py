@@ -76,6 +76,15 @@ CONFIGS = {
                              dict(loss='bpr-max', final_act='elu-0.5', layers=[12], batch_size=6, n_epochs=2, learning_rate=0.1,
                                   momentum=0.2, n_sample=16, sample_alpha=0.75, bpreg=0.5),
                              dict(sample_store=16 * 40, store_type='cpu')),
+    'bprmax_randorder_normalinit': (dict(n_items=50, n_events=600, seed=14),   # session order drawn per epoch, no time sort, N(0, sigma) init
+                                    dict(loss='bpr-max', final_act='leaky-0.1', hidden_act='selu-1.05-1.67', layers=[10], batch_size=5,
+                                         n_epochs=2, learning_rate=0.05, momentum=0.0, n_sample=12, sample_alpha=0.75,
+                                         train_random_order=True, time_sort=False, sigma=0.15, init_as_normal=True),
+                                    dict(sample_store=12 * 30)),
+    'top1max_cpustore_randorder': (dict(n_items=55, n_events=650, seed=15),   # host store with uniform sampling (np.random.choice) + random session order
+                                   dict(loss='top1-max', final_act='tanh', layers=[9], batch_size=6, n_epochs=2, learning_rate=0.1,
+                                        momentum=0.1, n_sample=12, sample_alpha=0.0, train_random_order=True),
+                                   dict(sample_store=12 * 35, store_type='cpu')),
     # optimiser variants / clipping / smoothing: implemented by the oracle only (the device path raises NotImplementedError)
     'xe_none_adam': (dict(n_items=50, n_events=500, seed=11),
                      dict(loss='cross-entropy', final_act='softmax', layers=[8], batch_size=5, n_epochs=1, n_sample=10,
@@ -126,8 +135,19 @@ def run_one(name, dkw, mkw, fkw):
         return r
     gru.init = init_and_capture
     buf = io.StringIO()
-    with contextlib.redirect_stdout(buf):
-        gru.fit(train, **fkw)
+    perms = []
+    orig_perm = np.random.permutation
+
+    def recording_permutation(x):          # train_random_order (gru4rec.py:593): record the session order of every epoch
+        r = orig_perm(x)
+        perms.append(np.array(r))
+        return r
+    np.random.permutation = recording_permutation
+    try:
+        with contextlib.redirect_stdout(buf):
+            gru.fit(train, **fkw)
+    finally:
+        np.random.permutation = orig_perm
     log = buf.getvalue()
     assert not gru.error_during_train, log
     epoch_loss = [float(x) for x in re.findall(r'loss: ([0-9.]+)', log)]
@@ -141,6 +161,8 @@ def run_one(name, dkw, mkw, fkw):
     out['test_SessionId'] = test['SessionId'].values
     out['test_ItemId'] = test['ItemId'].values
     out['test_Time'] = test['Time'].values
+    if mkw.get('train_random_order'):
+        out['epoch_orders'] = np.stack(perms)
     out['itemidmap_index'] = gru.itemidmap.index.values
     out['n_items'] = gru.n_items
     for k, v in init_w.items():

@@ -63,3 +63,13 @@ def step_samples(g, s):
     fs = g['store_first_step']
     k = int(np.searchsorted(fs, s, side='right') - 1)
     return g['sample_stores'][k][s - fs[k]]
+
+
+def fit_data(orc, g, tr):
+    """prepare_fit_data with the model's time_sort option (gru4rec.py:585)."""
+    return orc.prepare_fit_data(tr, time_sort=g['model_kwargs'].get('time_sort', True))
+
+
+def epoch_order(g, d, e):
+    """session order of epoch e: recorded np.random.permutation for train_random_order (gru4rec.py:593), else base_order"""
+    return g['epoch_orders'][e] if 'epoch_orders' in g else d['base_order']

@@ -11,7 +11,7 @@ import pytest
 import gru4rec_oracle as orc
 from gru4rec_b200 import _lib
 from gru4rec_b200.synth import make_sessions, train_test_split
-from golden_utils import golden_names, load_golden, frames, init_weights, step_samples
+from golden_utils import golden_names, load_golden, frames, init_weights, step_samples, fit_data, epoch_order
 from gpu_utils import make_cfg
 
 pytestmark = pytest.mark.gpu
@@ -33,7 +33,7 @@ def test_golden_trajectory_through_cuda(name, step_mode):
     g = load_golden(name)
     tr, _ = frames(g)
     mk = g['model_kwargs']
-    d = orc.prepare_fit_data(tr)
+    d = fit_data(orc, g, tr)
     S = mk['n_sample']
     rows = g['sample_stores'].shape[1] if 'sample_stores' in g else 0
     eng = _lib.Engine(make_cfg(int(g['n_items']), mk, sample_store=rows * S, step_mode=step_mode))
@@ -45,11 +45,11 @@ def test_golden_trajectory_through_cuda(name, step_mode):
         eng.set('E', w['E'])
     if mk.get('logq', 0):
         eng.set_logq_support(d['supports'].astype(np.float32))
-    sched = _lib.Schedule(d['data_items'], d['offset_sessions'], d['base_order'], mk['batch_size'], S, mode=0)
     costs = []
-    per = sched.n_steps
     k = 0
     for e in range(mk['n_epochs']):
+        sched = _lib.Schedule(d['data_items'], d['offset_sessions'], epoch_order(g, d, e), mk['batch_size'], S, mode=0)
+        per = sched.n_steps
         eng.reset_hidden()
         done = 0
         while done < per:
@@ -233,11 +233,13 @@ def test_unimplemented_training_options_raise_in_fit(name):
             gru.fit(tr.copy(), **g['fit_kwargs'])
 
 
-def test_fit_from_scratch_reproduces_the_reference_run():
+@pytest.mark.parametrize('name', [n for n in golden_names() if 'host_sampler' in load_golden(n)])
+def test_fit_from_scratch_reproduces_the_reference_run(name):
     """store_type='cpu' makes the whole run a function of NumPy's global stream (seed 42 in init, gru4rec.py:254; samples from
-    np.random.rand, :507-514): GRU4Rec.fit() from scratch must reproduce the REFERENCE's epoch losses and final weights."""
+    np.random.rand / np.random.choice, :507-514; session permutations, :593): GRU4Rec.fit() from scratch must reproduce the
+    REFERENCE's epoch losses and final weights."""
     import gru4rec
-    g = load_golden('bprmax_none_cpustore')
+    g = load_golden(name)
     tr, _ = frames(g)
     gru = gru4rec.GRU4Rec(**g['model_kwargs'])
     buf = io.StringIO()

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 import gru4rec_oracle as orc
-from golden_utils import golden_names, load_golden, frames, init_weights, step_masks, step_samples
+from golden_utils import golden_names, load_golden, frames, init_weights, step_masks, step_samples, fit_data, epoch_order
 
 NAMES = golden_names()
 
@@ -31,20 +31,27 @@ def test_schedule_matches_reference(name):
     g = load_golden(name)
     tr, _ = frames(g)
     mk = g['model_kwargs']
-    d = orc.prepare_fit_data(tr)
+    d = fit_data(orc, g, tr)
     assert list(d['itemids']) == list(g['itemidmap_index'])
     n_sample = mk['n_sample'] if g['fit_kwargs'].get('sample_store', 1) else mk['n_sample']
-    steps = orc.build_train_schedule(d['data_items'], d['offset_sessions'], d['base_order'], mk['batch_size'], mk['n_sample'])
     n_ep = mk['n_epochs']
-    assert len(steps) * n_ep == len(g['step_M'])
+    if 'epoch_orders' in g and 'host_sampler' not in g:
+        # train_random_order: the orders are np.random.permutation draws on the stream init() seeded (gru4rec.py:254,593)
+        m = _model(g)
+        m.init(int(g['n_items']))
+        for e in range(n_ep):
+            np.testing.assert_array_equal(np.random.permutation(len(d['offset_sessions']) - 1), g['epoch_orders'][e])
+    k = 0
     for e in range(n_ep):
+        steps = orc.build_train_schedule(d['data_items'], d['offset_sessions'], epoch_order(g, d, e), mk['batch_size'], mk['n_sample'])
         for s, st in enumerate(steps):
-            k = e * len(steps) + s
+            k += 1
             M = st['M']
-            assert M == g['step_M'][k]
-            np.testing.assert_array_equal(st['X'], g['step_X'][k, :M])
-            np.testing.assert_array_equal(st['Y'], g['step_Y'][k, :M])
-            np.testing.assert_array_equal(st['R'].astype(np.int8), g['step_R'][k, :M])
+            assert M == g['step_M'][k - 1]
+            np.testing.assert_array_equal(st['X'], g['step_X'][k - 1, :M])
+            np.testing.assert_array_equal(st['Y'], g['step_Y'][k - 1, :M])
+            np.testing.assert_array_equal(st['R'].astype(np.int8), g['step_R'][k - 1, :M])
+    assert k == len(g['step_M'])
 
 
 @pytest.mark.parametrize('name', [n for n in NAMES if 'nosample' not in n])
@@ -53,16 +60,34 @@ def test_sample_store_matches_reference(name):
     g = load_golden(name)
     tr, _ = frames(g)
     mk = g['model_kwargs']
-    d = orc.prepare_fit_data(tr)
+    d = fit_data(orc, g, tr)
     if 'host_sampler' in g:
         # store_type='cpu' (gru4rec.py:507-514): np.searchsorted(pop, np.random.rand(...)) (side='left', float64 CDF) on the global
         # NumPy stream that init() seeded with 42 -- reproduced by seeding, replaying init()'s draws and sampling store by store
         m = _model(g)
         m.init(int(g['n_items']))                          # np.random.seed(42) + the weight draws, as the reference's init()
-        pop = orc.sampling_cdf(d['supports'], mk.get('sample_alpha', 0.75))
+        alpha = mk.get('sample_alpha', 0.75)
+        pop = orc.sampling_cdf(d['supports'], alpha)
         glen = g['sample_stores'].shape[1]
-        for k in range(len(g['sample_stores'])):
-            st = np.searchsorted(pop, np.random.rand(mk['n_sample'] * glen)).reshape(glen, mk['n_sample'])
+        n_sess = len(d['offset_sessions']) - 1
+        # chronological order of the draws: a store when the pointer reaches its end, a session permutation at every epoch start
+        events = [(int(fs), 0, k) for k, fs in enumerate(g['store_first_step'])]
+        if 'epoch_orders' in g:
+            first = 0
+            for e in range(mk['n_epochs']):
+                events.append((first, 1, e))
+                first += len(orc.build_train_schedule(d['data_items'], d['offset_sessions'], g['epoch_orders'][e], mk['batch_size'], mk['n_sample']))
+        # at the same step the store created before the epoch loop comes first (step 0); later a permutation (epoch start)
+        # precedes the refresh that happens inside the epoch
+        events.sort(key=lambda t: (t[0], t[1] if t[0] == 0 else 1 - t[1]))
+        for step, kind, k in events:
+            if kind == 1:
+                np.testing.assert_array_equal(np.random.permutation(n_sess), g['epoch_orders'][k])
+                continue
+            if alpha:
+                st = np.searchsorted(pop, np.random.rand(mk['n_sample'] * glen)).reshape(glen, mk['n_sample'])
+            else:
+                st = np.random.choice(int(g['n_items']), size=mk['n_sample'] * glen).reshape(glen, mk['n_sample'])
             used = int(g['store_rows_used'][k])
             np.testing.assert_array_equal(st[:used], g['sample_stores'][k][:used])
         return
@@ -79,15 +104,17 @@ def test_training_trajectory_matches_reference(name):
     g = load_golden(name)
     tr, _ = frames(g)
     mk = g['model_kwargs']
-    d = orc.prepare_fit_data(tr)
+    d = fit_data(orc, g, tr)
     m = _model(g)
     m.init(int(g['n_items']))
     if mk.get('logq', 0):
         m.P0 = d['supports'].astype(np.float32)
-    steps = orc.build_train_schedule(d['data_items'], d['offset_sessions'], d['base_order'], mk['batch_size'], mk['n_sample'])
     costs = []
     k = 0
+    bounds = [0]
     for e in range(mk['n_epochs']):
+        steps = orc.build_train_schedule(d['data_items'], d['offset_sessions'], epoch_order(g, d, e), mk['batch_size'], mk['n_sample'])
+        bounds.append(bounds[-1] + len(steps))
         for h in m.H:
             h[:] = 0
         for st in steps:
@@ -109,9 +136,8 @@ def test_training_trajectory_matches_reference(name):
     # epoch loss as printed by the reference (gru4rec.py:654,661)
     cc = g['step_M'].astype(np.float64)
     n_ep = mk['n_epochs']
-    per = len(steps)
     for e in range(n_ep):
-        sl = slice(e * per, (e + 1) * per)
+        sl = slice(bounds[e], bounds[e + 1])
         avgc = np.sum(costs[sl] * cc[sl]) / np.sum(cc[sl])
         assert abs(avgc - g['epoch_loss'][e]) < 2e-4 * max(1, abs(avgc))
 
@@ -121,7 +147,7 @@ def test_evaluation_matches_reference(name):
     g = load_golden(name)
     tr, te = frames(g)
     mk = g['model_kwargs']
-    d = orc.prepare_fit_data(tr)
+    d = fit_data(orc, g, tr)
     m = _model(g)
     m.set_weights(**init_weights(g, 'final_'))
     m.batch_size = mk['batch_size']
@@ -139,7 +165,7 @@ def test_evaluation_with_candidate_items_matches_reference(name):
     g = load_golden(name)
     tr, te = frames(g)
     mk = g['model_kwargs']
-    d = orc.prepare_fit_data(tr)
+    d = fit_data(orc, g, tr)
     m = _model(g)
     m.set_weights(**init_weights(g, 'final_'))
     m.batch_size = mk['batch_size']

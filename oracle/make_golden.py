@@ -85,6 +85,15 @@ CONFIGS = {
                                    dict(loss='top1-max', final_act='tanh', layers=[9], batch_size=6, n_epochs=2, learning_rate=0.1,
                                         momentum=0.1, n_sample=12, sample_alpha=0.0, train_random_order=True),
                                    dict(sample_store=12 * 35, store_type='cpu')),
+    'xe_none_logq_nosample': (dict(n_items=60, n_events=650, seed=16),        # logQ correction without constrained embedding, in-batch negatives only
+                              dict(loss='cross-entropy', final_act='softmax', layers=[10], batch_size=7, n_epochs=1, learning_rate=0.1,
+                                   momentum=0.1, n_sample=0, logq=0.7),
+                              dict(sample_store=0)),
+    'bprmax_shared_3layer_drop': (dict(n_items=60, n_events=800, seed=17),    # paramfiles/retailrocket_bprmax_shared_best.py shape, shrunk
+                                  dict(loss='bpr-max', final_act='elu-0.5', layers=[8, 8, 8], batch_size=6, n_epochs=2, learning_rate=0.05,
+                                       momentum=0.4, n_sample=20, sample_alpha=0.4, bpreg=1.95, constrained_embedding=True,
+                                       dropout_p_embed=0.5, dropout_p_hidden=0.05),
+                                  dict(sample_store=20 * 30)),
     # optimiser variants / clipping / smoothing: implemented by the oracle only (the device path raises NotImplementedError)
     'xe_none_adam': (dict(n_items=50, n_events=500, seed=11),
                      dict(loss='cross-entropy', final_act='softmax', layers=[8], batch_size=5, n_epochs=1, n_sample=10,

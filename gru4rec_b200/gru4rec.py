@@ -369,7 +369,15 @@ class GRU4Rec:
                     raise NotImplementedError
             else:
                 print('No example store was used')
-        eng = self._build_engine(sample_store=(sample_store if use_store else 0))
+        per_step_sampling = False
+        if self.n_sample and not use_store:
+            if store_type == 'cpu':
+                # gru4rec.py:612-613: without a store every mini-batch draws its own row on the host (generate_neg_samples(pop, 1))
+                per_step_sampling = True
+            else:
+                # the reference's device path has no per-step sampler: its loop dereferences an undefined sample pointer here
+                raise NotImplementedError('n_sample > 0 needs a sample store when store_type is \'gpu\' (sample_store >= 2 * n_sample)')
+        eng = self._build_engine(sample_store=(sample_store if use_store else (2 * self.n_sample if per_step_sampling else 0)))
         if P0 is not None:
             eng.set_logq_support(P0)
         if use_store:
@@ -398,7 +406,9 @@ class GRU4Rec:
                 n_steps = sched.n_steps if world == 1 else common_steps(sched.n_steps, dist)
                 cc = sched.export()['M'][:n_steps].astype(np.float64)
             try:
-                if use_store and store_type == 'cpu':
+                if per_step_sampling:
+                    c = self._train_epoch_per_step_samples(eng, sched, pop)
+                elif use_store and store_type == 'cpu':
                     c = self._train_epoch_cpu_store(eng, sched, pop, generate_length)
                 else:
                     c = eng.train_steps(sched, 0, n_steps)
@@ -425,6 +435,16 @@ class GRU4Rec:
             n = min(sched.n_steps - done, generate_length - eng.get_sample_pointer())
             costs.append(eng.train_steps(sched, done, n))
             done += n
+        return np.concatenate(costs)
+
+    def _train_epoch_per_step_samples(self, eng, sched, pop):
+        """store_type='cpu' without a store (gru4rec.py:612-613): one host draw of n_sample items per mini-batch."""
+        costs = []
+        for k in range(sched.n_steps):
+            row = np.asarray(self.generate_neg_samples(pop, 1)).reshape(1, self.n_sample)
+            eng.set_sample_store(np.vstack([row, row]))
+            eng.set_sample_pointer(0)
+            costs.append(eng.train_steps(sched, k, 1))
         return np.concatenate(costs)
 
     # ---- serving (gru4rec.py:665-728) ----

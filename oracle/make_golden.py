@@ -94,6 +94,10 @@ CONFIGS = {
                                        momentum=0.4, n_sample=20, sample_alpha=0.4, bpreg=1.95, constrained_embedding=True,
                                        dropout_p_embed=0.5, dropout_p_hidden=0.05),
                                   dict(sample_store=20 * 30)),
+    'xe_none_cpu_nostore': (dict(n_items=50, n_events=500, seed=18),          # no store: one host draw per mini-batch (gru4rec.py:612-613)
+                            dict(loss='cross-entropy', final_act='softmax', layers=[8], batch_size=5, n_epochs=1, learning_rate=0.1,
+                                 momentum=0.0, n_sample=9, sample_alpha=0.5),
+                            dict(sample_store=0, store_type='cpu')),
     # optimiser variants / clipping / smoothing: implemented by the oracle only (the device path raises NotImplementedError)
     'xe_none_adam': (dict(n_items=50, n_events=500, seed=11),
                      dict(loss='cross-entropy', final_act='softmax', layers=[8], batch_size=5, n_epochs=1, n_sample=10,
@@ -197,6 +201,8 @@ def run_one(name, dkw, mkw, fkw):
         # host-side store (gru4rec.py:551-554,605-615): the samples travel in the Y input of every call; regroup them into the
         # stores generate_neg_samples() produced (generate_length rows each, the pointer is not reset between epochs)
         glen = fkw['sample_store'] // mkw['n_sample']
+        if glen <= 1:
+            glen = 1                                        # no store: generate_neg_samples(pop, 1) per mini-batch
         neg = np.stack([np.asarray(c[1][1][int(c[1][2]):], dtype=np.int64) for c in tr])
         n_st = (n + glen - 1) // glen
         st_all = np.zeros((n_st, glen, mkw['n_sample']), dtype=np.int64)

@@ -36,7 +36,7 @@ def test_golden_trajectory_through_cuda(name, step_mode):
     d = fit_data(orc, g, tr)
     S = mk['n_sample']
     rows = g['sample_stores'].shape[1] if 'sample_stores' in g else 0
-    eng = _lib.Engine(make_cfg(int(g['n_items']), mk, sample_store=rows * S, step_mode=step_mode))
+    eng = _lib.Engine(make_cfg(int(g['n_items']), mk, sample_store=max(rows, 2 if rows else 0) * S, step_mode=step_mode))
     w = init_weights(g)
     for i in range(len(mk['layers'])):
         eng.set('Wx%d' % i, w['Wx'][i]); eng.set('Wh%d' % i, w['Wh'][i]); eng.set('Wrz%d' % i, w['Wrz'][i]); eng.set('Bh%d' % i, w['Bh'][i])
@@ -55,7 +55,8 @@ def test_golden_trajectory_through_cuda(name, step_mode):
         while done < per:
             if rows:
                 si = int(np.searchsorted(g['store_first_step'], k, side='right') - 1)
-                eng.set_sample_store(g['sample_stores'][si])
+                st = g['sample_stores'][si]
+                eng.set_sample_store(st if st.shape[0] > 1 else np.vstack([st, st]))    # one draw per mini-batch: a 2-row store
                 eng.set_sample_pointer(k - int(g['store_first_step'][si]))
                 nxt = int(g['store_first_step'][si + 1]) if si + 1 < len(g['store_first_step']) else 10 ** 9
                 n = min(per - done, nxt - k)

@@ -267,6 +267,17 @@ def run_one(name, dkw, mkw, fkw):
     out['predict_probe_items'] = probe_items
     out['predict_out1'] = p1.values
     out['predict_out2'] = p2.values
+    # the same probe restricted to a list of items (predict_for_item_ids, gru4rec.py:699-703,719-723): a fresh predict function
+    # (the reference compiles it once, for whichever form the first call used)
+    gru.predict = None
+    sub_pred = sub_ids[:7].copy()
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        p3 = gru.predict_next_batch(sess, probe_items, sub_pred, batch=5)
+        p4 = gru.predict_next_batch(sess, probe_items[::-1].copy(), sub_pred, batch=5)
+    out['predict_sub_items'] = sub_pred
+    out['predict_sub_out1'] = p3.values
+    out['predict_sub_out2'] = p4.values
     out['model_kwargs'] = np.array(repr(mkw))
     out['fit_kwargs'] = np.array(repr(fkw))
     path = os.path.join(ROOT, 'tests', 'golden', name + '.npz')

@@ -117,6 +117,12 @@ def test_golden_evaluation_through_cuda(name):
     np.testing.assert_allclose(p2.values, g['predict_out2'], rtol=2e-4, atol=1e-6)
     sub = gru.predict_next_batch(np.arange(5) + 100, probe, probe[:3], batch=5)
     assert sub.shape == (3, 5) and list(sub.index) == list(probe[:3])
+    # predict_for_item_ids against the reference's own output (fresh sessions -> state reset, as its fresh predict function)
+    s1 = gru.predict_next_batch(np.arange(5) + 200, probe, g['predict_sub_items'], batch=5)
+    s2 = gru.predict_next_batch(np.arange(5) + 200, probe[::-1].copy(), g['predict_sub_items'], batch=5)
+    assert list(s1.index) == list(g['predict_sub_items'])
+    np.testing.assert_allclose(s1.values, g['predict_sub_out1'], rtol=2e-4, atol=1e-6)
+    np.testing.assert_allclose(s2.values, g['predict_sub_out2'], rtol=2e-4, atol=1e-6)
 
 
 def _oracle_fit(train, mk, sample_store):

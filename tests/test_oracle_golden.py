@@ -179,3 +179,24 @@ def test_evaluation_with_candidate_items_matches_reference(name):
         # bound is ONE rank flip: 1/n in recall, (1/r - 1/(r+1)) / n <= 0.5/n in MRR
         np.testing.assert_allclose(rec, g['eval_items_%s_recall' % mode], rtol=1e-6, atol=1.0 / n_ev + 1e-9)
         np.testing.assert_allclose(mrr, g['eval_items_%s_mrr' % mode], rtol=1e-6, atol=0.5 / n_ev + 1e-9)
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_predict_next_batch_matches_reference(name):
+    """predict_next_batch (gru4rec.py:665-728) on the reference's final weights: all items, and a list of items
+    (predict_for_item_ids: the final activation is taken over the listed columns only)."""
+    g = load_golden(name)
+    tr, _ = frames(g)
+    mk = g['model_kwargs']
+    d = fit_data(orc, g, tr)
+    m = _model(g)
+    m.set_weights(**init_weights(g, 'final_'))
+    m.batch_size = mk['batch_size']
+    probe = d['itemidmap'][g['predict_probe_items']].values
+    sub = d['itemidmap'][g['predict_sub_items']].values
+    for cols, k1, k2 in ((None, 'predict_out1', 'predict_out2'), (sub, 'predict_sub_out1', 'predict_sub_out2')):
+        H = [np.zeros((5, L), dtype=np.float32) for L in mk['layers']]
+        y1 = m.predict_step(probe, H, Y=cols)
+        y2 = m.predict_step(probe[::-1].copy(), H, Y=cols)
+        np.testing.assert_allclose(y1.T, g[k1], rtol=2e-4, atol=1e-6)
+        np.testing.assert_allclose(y2.T, g[k2], rtol=2e-4, atol=1e-6)

@@ -163,3 +163,40 @@ def test_pickle_written_here_loads_into_the_reference_class(tmp_path):
     rec, mrr = json.loads(out.stdout.strip().splitlines()[-1])
     np.testing.assert_allclose(rec, g['eval_standard_recall'], rtol=1e-6)
     np.testing.assert_allclose(mrr, g['eval_standard_mrr'], rtol=1e-6)
+
+
+def test_datatools_behaves_like_the_reference_module():
+    """gru4rec_b200/datatools.py is an independent implementation; wherever the reference checkout is available (this container,
+    not the GPU box) its datatools.py -- plain pandas/NumPy, importable without Theano -- is run side by side on random frames:
+    same printed decision, same in-place result, same int32 offsets."""
+    import io, contextlib, importlib.util
+    import pandas as pd
+    ref_path = '/root/reference/datatools.py'
+    if not os.path.exists(ref_path):
+        pytest.skip('reference checkout not available')
+    spec = importlib.util.spec_from_file_location('ref_datatools', ref_path)
+    ref = importlib.util.module_from_spec(spec); spec.loader.exec_module(ref)
+    from gru4rec_b200 import datatools as mine
+    rs = np.random.RandomState(0)
+    n_cases = 0
+    for n in (1, 2, 50, 300):
+        for trial in range(8):
+            df = pd.DataFrame({'SessionId': rs.randint(0, max(2, n // 4), n), 'Time': rs.randint(0, 40, n), 'ItemId': rs.randint(0, 9, n)})
+            if trial % 4 == 1: df = df.sort_values(['SessionId', 'Time']).reset_index(drop=True)
+            if trial % 4 == 2: df = df.sort_values(['SessionId', 'Time', 'ItemId']).reset_index(drop=True)
+            if trial % 4 == 3:      # sessions grouped but in arbitrary order
+                df = df.sort_values(['SessionId', 'Time']).reset_index(drop=True)
+                df = pd.concat([df[df.SessionId == s] for s in rs.permutation(df['SessionId'].unique())]).reset_index(drop=True)
+            for cols in (['SessionId', 'Time'], ['SessionId', 'Time', 'ItemId'], ['SessionId']):
+                for any_order in (False, True):
+                    a, b = df.copy(), df.copy()
+                    out_a, out_b = io.StringIO(), io.StringIO()
+                    with contextlib.redirect_stdout(out_a): ref.sort_if_needed(a, cols, any_order)
+                    with contextlib.redirect_stdout(out_b): mine.sort_if_needed(b, cols, any_order)
+                    keep = lambda t: [l for l in t.getvalue().splitlines() if not l.startswith('Data is sorted in')]
+                    assert keep(out_a) == keep(out_b)
+                    assert a.equals(b)
+                    oa, ob = ref.compute_offset(a, 'SessionId'), mine.compute_offset(b, 'SessionId')
+                    assert oa.dtype == ob.dtype and np.array_equal(oa, ob)
+                    n_cases += 1
+    assert n_cases == 192

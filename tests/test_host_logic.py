@@ -200,3 +200,28 @@ def test_datatools_behaves_like_the_reference_module():
                     assert oa.dtype == ob.dtype and np.array_equal(oa, ob)
                     n_cases += 1
     assert n_cases == 192
+
+
+def test_set_params_matches_the_reference_class():
+    """set_params (gru4rec.py:162-187) of the reference, run through the shim by oracle/make_set_params_golden.py: same printed
+    lines, same attribute values and types, same exception -- including string coercions, `layers=100/50`, `embedding=layersize`,
+    bool strings, unknown keys and invalid values."""
+    import io, json, contextlib
+    import gru4rec
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'set_params_cases.json')))
+    assert len(cases) >= 12
+    for case in cases:
+        g = gru4rec.GRU4Rec()
+        buf = io.StringIO()
+        exc = None
+        with contextlib.redirect_stdout(buf):
+            try:
+                g.set_params(**case['kwargs'])
+            except BaseException as e:       # noqa: BLE001
+                exc = type(e).__name__
+        assert exc == case['exception'], (case['kwargs'], exc)
+        assert buf.getvalue() == case['stdout'], (case['kwargs'], buf.getvalue(), case['stdout'])
+        for a, v in case['attrs'].items():
+            mine = getattr(g, a)
+            assert type(mine).__name__ == case['attr_types'][a], (case['kwargs'], a, type(mine).__name__, case['attr_types'][a])
+            assert (list(mine) if isinstance(mine, (list, tuple)) else mine) == v, (case['kwargs'], a, mine, v)

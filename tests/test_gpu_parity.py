@@ -136,7 +136,10 @@ def test_shrinking_batch_and_slots(step_mode):
 @pytest.mark.parametrize('loss,fact,alpha,extra', [('bpr-max', 'elu-0.5', 0.0, {}), ('cross-entropy', 'softmax', 0.75, {}), ('top1-max', 'tanh', 1.0, {}),
                                                    ('bpr-max', 'elu-1', 0.0, dict(dropout_p_hidden=0.25, lmbd=0.0005)),
                                                    ('cross-entropy', 'softmax', 0.0, dict(logq=1.0, momentum=0.0)),
-                                                   ('bpr', 'linear', 0.0, dict(adapt=None, learning_rate=0.01))])
+                                                   ('bpr', 'linear', 0.0, dict(adapt=None, learning_rate=0.01)),
+                                                   ('bpr-max', 'elu-0.5', 0.0, dict(layers=[128])),                    # widest GRU the kernel takes
+                                                   ('top1', 'tanh', 0.25, dict(layers=[50], batch_size=13)),           # L not a multiple of 4, odd batch
+                                                   ('xe_logit', 'softmax_logit', 0.0, dict(layers=[64], batch_size=16, momentum=0.0))])
 @pytest.mark.parametrize('step_mode', [2, 3])
 def test_headline_shape_role_specialised_kernel(loss, fact, alpha, extra, step_mode):
     """B=32, GRU(100), 2048 samples (BASELINE configs[1] shape) through step_mode 2 (48-CTA GRU group) and 3 (GRU on one
@@ -164,8 +167,8 @@ def test_headline_shape_role_specialised_kernel(loss, fact, alpha, extra, step_m
     eng.generate_samples_from_uniform(u)
     store = orc.searchsorted_k2(P, u).reshape(rows, 2048)
     np.testing.assert_array_equal(eng.get_sample_store(), store)
-    sched = _lib.Schedule(items, offset, order, 32, 2048, mode=0)
-    steps = orc.build_train_schedule(items, offset, order, 32, 2048)
+    sched = _lib.Schedule(items, offset, order, mk['batch_size'], 2048, mode=0)
+    steps = orc.build_train_schedule(items, offset, order, mk['batch_size'], 2048)
     n = 14
     costs = np.concatenate([eng.train_steps(sched, 0, 9), eng.train_steps(sched, 9, n - 9)])
     ref = [m.train_step(st['X'], st['Y'], st['R'], samples=store[k], slots=st['slots']) for k, st in enumerate(steps[:n])]

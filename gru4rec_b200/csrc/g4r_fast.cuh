@@ -1,5 +1,5 @@
 // g4r_fast.cuh -- role-specialised persistent kernel for the headline shape family:
-//   no-embedding mode, one GRU layer, L <= 128, batch <= 32, every score-column chunk <= 16 columns.
+//   no-embedding mode, one GRU layer, L <= 120 (step_mode 3: L <= 128), batch <= 32, every score-column chunk <= 32 columns.
 // (step_mode 2; anything else runs k_persistent / the per-phase kernels, which share all numerics.)
 //
 // Why: at B=32, L=100 a mini-batch is ~8 dependent phases over ~6 MB; time is memory/barrier latency.  This kernel

@@ -491,6 +491,7 @@ extern "C" int g4r_create(const g4r_config* cfg, void* device_workspace, size_t 
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fast_t<false>, FK_THREADS, sizeof(FastSmem));
     h->fast_ok = h->pk_blocks > 0 && per_sm >= 1 && m.mode == 0 && m.n_layers == 1 && m.ldL <= 128 && m.B <= FK_B && h->n_sm >= FK_G + 1 && m.NCH <= 160 &&
+                 2 * m.L <= FK_W1 * FK_G && m.L <= FK_W2 * FK_G &&     // the 48-CTA GRU group covers FK_W1 gate / FK_W2 candidate columns per CTA (L <= 120)
                  (m.adapt == G4R_ADAPT_ADAGRAD ? m.Wy_acc != nullptr : true);
     h->fastc_ok = cfg->step_mode == 3 && h->fastc_grid >= FC_CLUSTER * 2 && m.mode == 0 && m.n_layers == 1 && m.ldL <= 128 && m.B <= FK_B &&
                   m.NCH <= h->fastc_grid && (m.adapt == G4R_ADAPT_ADAGRAD ? m.Wy_acc != nullptr : true);

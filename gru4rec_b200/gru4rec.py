@@ -254,6 +254,8 @@ class GRU4Rec:
         cfg.world_size, cfg.rank = self._world()
         cfg.eval_batch_size = eval_lanes
         cfg.step_mode = self.step_mode
+        if self.step_mode == 2 and len(self.layers) == 1 and 120 < self.layers[0] <= 128 and not self.constrained_embedding and not self.embedding and self.batch_size <= 32:
+            cfg.step_mode = 3        # the 48-CTA GRU group of step_mode 2 covers 120 hidden units; the cluster variant takes up to 128
         return cfg
 
     @staticmethod

@@ -28,6 +28,9 @@ WORKLOAD = dict(name='rsc15_bprmax_gru100_b32_ns2048', n_items=37483,
                            constrained_embedding=False),
                 sample_store=10000000)
 ALGO_BYTES_PER_STEP = 6041792
+# the reference's published mini-batches/s for this configuration (BPR-max, B=32, GRU(100), n_sample=2048, with
+# momentum) -- read off its training-time chart, measured on an A30 (img/training_time_bprmax_batch_size.png, README.md:302)
+BASELINE_PUBLISHED_MBS = 1235.0
 
 
 def algo_bytes_lossgrad(N, L, mom=True):
@@ -133,7 +136,7 @@ def run_reference(args, rank):
     v, done, cores = oracle_steps_per_sec(items, offset, order, supports, args.warmup, n, budget_s=150.0)
     out = {
         'metric': 'mini-batches/sec', 'value': v, 'unit': 'mb/s', 'n_gpus': args.gpus, 'steps': done, 'warmup': args.warmup,
-        'ms_per_step': 1000.0 / v, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'ms_per_step': 1000.0 / v, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': v / BASELINE_PUBLISHED_MBS, 'dtype': 'f32', 'data': 'synthetic',
         'impl': 'reference',
         'config': {'workload': WORKLOAD['name'], 'n_items': WORKLOAD['n_items'], 'global_batch': WORKLOAD['model']['batch_size'],
                    'note': 'reference CPU path = NumPy restatement of gru4rec.py (oracle/); Theano is not installable offline'},
@@ -289,12 +292,13 @@ def main():
         dom_name, achieved, frac, us_launch, phase_us = None, None, None, None, None
     out = {
         'metric': 'mini-batches/sec', 'value': value, 'unit': 'mb/s', 'n_gpus': world, 'steps': K, 'warmup': W,
-        'ms_per_step': dev_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'ms_per_step': dev_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': value / BASELINE_PUBLISHED_MBS,
         'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': WORKLOAD['name'], 'n_items': WORKLOAD['n_items'], 'global_batch': B * world, 'n_sample': mk['n_sample'],
                    'layers': mk['layers'], 'params': 'param_samples/rsc15_bpr-max.py', 'parallelism': ('dp%d: replicated parameters, NCCL all-gather of row gradients + all-reduce of dense gradients per mini-batch, identical merged update on every rank' % world) if world > 1 else 'dp1',
                    'l2': 'inputs larger than L2: item tables + Adagrad/momentum state = 180 MB, rows touched change every step (no flush between steps; ncu shows the uniformly sampled Wy rows, 45 MB with their state, staying L2-resident in steady state: 0.23 MB DRAM traffic per step)',
-                   'step_mode': int(cfg.step_mode), 'fast_windows': list(eng.fast_windows()), 'events_per_sec': value * B},
+                   'step_mode': int(cfg.step_mode), 'fast_windows': list(eng.fast_windows()), 'events_per_sec': value * B,
+                   'vs_baseline_source': 'BASELINE.md: ~1235 mb/s published by the reference for this configuration on an A30 (chart reading)'},
         'e2e': {'value': e2e_value, 'unit': 'mb/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches),
         'clocks': clocks.summary(),

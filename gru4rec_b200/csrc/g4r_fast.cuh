@@ -9,6 +9,15 @@
 //  * folds the row-statistics combine into the score->gradient barrier (the last CTA to arrive combines);
 //  * runs the GRU phases on a group of G CTAs with group barriers; the other CTAs only wait for `h_ready`;
 //  * uses monotonic release/acquire counters (no resets, no separate fences) for all synchronisation.
+//
+// What is computed (reference hidasib/GRU4Rec, same formulas as the generic phases in g4r_kernels.cuh):
+//   F1 / F2   GRU layer in no-embedding mode, gru4rec.py:459-466 (vec = Wx0[X] + Bh, column blocks h~ | r | z, :460-462),
+//             hidden dropout and the reset of finished sessions (:464-466)
+//   scores    o = h Sy^T + by (- logq log P), gru4rec.py:480-496; final activations :189-223
+//   stats     row statistics of the losses, gru4rec.py:225-248 (softmax_neg with the zeroed diagonal :199-203)
+//   lossgrad  dL/do of SURVEY appendix A (the reference differentiates symbolically, :383-384), dSy, dby, partial dL/dh
+//   update    sparse Adagrad (+momentum) with the duplicate rules of gru4rec.py:335-340,407-431 on the chunk's rows,
+//             dense Adagrad (+momentum) of Wh / Wrz / Bh, :330-334,390-406, input rows Wx0[X] :407-431
 #pragma once
 
 constexpr int FK_THREADS = 512;

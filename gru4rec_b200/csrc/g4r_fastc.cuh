@@ -9,6 +9,11 @@
 //    barriers (barrier.cluster, ~0.2 us) instead of L2 + global counters;
 //  * per mini-batch: reduce-scatter of d(H*r) partials (1 barrier), all-gather of H*r (1 barrier + 1 split barrier).
 // Column CTAs, helper CTAs (input-row update) and all numerics formulas are shared with k_fast.
+//
+// Reference formulas (hidasib/GRU4Rec): cf_f1 = rz gates, gru4rec.py:460-462 (r | z column blocks of Wrz, vec[:, L:]);
+// cf_f2 = candidate, new state, dropout, reset, :463-466; cf_backward = GRU backward of SURVEY appendix A (the reference uses
+// T.grad, :383-384: dh -> dz, dh~ -> da_h; d(H*r) = da_h Wh^T -> da_r) followed by the dense Adagrad (+momentum) update of
+// gru4rec.py:330-334,390-406 on the resident columns.
 #pragma once
 
 constexpr int FC_SL = 17;        // row stride of the [32 x <=16] slice buffers (conflict-free with lane = batch row)

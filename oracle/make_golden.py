@@ -98,6 +98,10 @@ CONFIGS = {
                             dict(loss='cross-entropy', final_act='softmax', layers=[8], batch_size=5, n_epochs=1, learning_rate=0.1,
                                  momentum=0.0, n_sample=9, sample_alpha=0.5),
                             dict(sample_store=0, store_type='cpu')),
+    'xe_none_messy_data': (dict(n_items=45, n_events=500, seed=19, item_as_str=True, messy=True),   # single-event sessions, shuffled rows, tied
+                           dict(loss='cross-entropy', final_act='softmax', layers=[8], batch_size=6, n_epochs=2, learning_rate=0.1,       # timestamps, string ids
+                                momentum=0.0, n_sample=8, sample_alpha=0.75),
+                           dict(sample_store=8 * 30)),
     # optimiser variants / clipping / smoothing: implemented by the oracle only (the device path raises NotImplementedError)
     'xe_none_adam': (dict(n_items=50, n_events=500, seed=11),
                      dict(loss='cross-entropy', final_act='softmax', layers=[8], batch_size=5, n_epochs=1, n_sample=10,
@@ -128,8 +132,31 @@ def weights_of(gru):
     return w
 
 
+def messy(df, seed):
+    """Data the reference's preprocessing has to cope with: sessions with a single event (they occupy a lane for zero steps,
+    gru4rec.py:596-601,630-636), equal timestamps inside a session, rows in random order."""
+    import pandas as pd
+    rs = np.random.RandomState(seed + 1000)
+    n_sess = int(df['SessionId'].max()) + 1
+    extra = pd.DataFrame({'SessionId': (n_sess + np.arange(25)).astype(np.int32),
+                          'ItemId': rs.choice(df['ItemId'].unique(), size=25),
+                          'Time': rs.uniform(df['Time'].min(), df['Time'].max(), size=25)})
+    df = pd.concat([df, extra], ignore_index=True)
+    tie = rs.rand(len(df)) < 0.15
+    df.loc[tie, 'Time'] = np.floor(df.loc[tie, 'Time'])           # ties: the sort falls back on the input order
+    # renumber the sessions by start time so that the train/test split by session id stays a split in time
+    first = df.groupby('SessionId')['Time'].min().sort_values(kind='stable')
+    remap = pd.Series(np.arange(len(first), dtype=np.int32), index=first.index)
+    df['SessionId'] = remap[df['SessionId'].values].values
+    return df.iloc[rs.permutation(len(df))].reset_index(drop=True)
+
+
 def run_one(name, dkw, mkw, fkw):
+    dkw = dict(dkw)
+    is_messy = dkw.pop('messy', False)
     df = make_sessions(**dkw)
+    if is_messy:
+        df = messy(df, dkw['seed'])
     train, test = train_test_split(df, 0.25)
     train_in = train.copy()
     gru = ref_gru4rec.GRU4Rec(**mkw)

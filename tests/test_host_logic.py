@@ -225,3 +225,59 @@ def test_set_params_matches_the_reference_class():
             mine = getattr(g, a)
             assert type(mine).__name__ == case['attr_types'][a], (case['kwargs'], a, type(mine).__name__, case['attr_types'][a])
             assert (list(mine) if isinstance(mine, (list, tuple)) else mine) == v, (case['kwargs'], a, mine, v)
+
+
+@pytest.mark.parametrize('seed', range(12))
+def test_schedules_equal_oracle_on_random_session_structures(seed):
+    """Randomised sweep of the C++ schedule builder against the oracle's literal restatement of the reference loops
+    (gru4rec.py:585-651, evaluation.py:84-147): single-event sessions (they occupy a lane for zero steps), very long sessions,
+    batch sizes from 2 up to almost the number of sessions, arbitrary session orders, with and without samples."""
+    rs = np.random.RandomState(100 + seed)
+    n_sess = int(rs.randint(12, 80))
+    kind = seed % 4
+    if kind == 0:
+        lens = rs.randint(1, 4, n_sess)                       # many single-event sessions
+    elif kind == 1:
+        lens = np.minimum(1 + rs.geometric(0.4, n_sess), 30)
+    elif kind == 2:
+        lens = rs.randint(2, 6, n_sess); lens[rs.randint(0, n_sess, 3)] = rs.randint(40, 90, 3)   # a few very long ones
+    else:
+        lens = rs.randint(1, 12, n_sess)
+    offset = np.zeros(n_sess + 1, dtype=np.int32); offset[1:] = np.cumsum(lens)
+    items = rs.randint(0, 37, int(offset[-1])).astype(np.int64)
+    order = rs.permutation(n_sess) if seed % 2 else np.arange(n_sess)
+    usable = int((lens > 1).sum())
+    for B in sorted(set([2, 3, max(2, usable // 3), max(2, min(usable - 1, n_sess - 1))])):
+        for n_sample in (0, 5):
+            try:
+                steps = orc.build_train_schedule(items, offset, order, B, n_sample)
+            except IndexError:
+                with pytest.raises(IndexError):
+                    _lib.Schedule(items, offset, order, B, n_sample, mode=0)
+                continue
+            s = _lib.Schedule(items, offset, order, B, n_sample, mode=0)
+            e = s.export()
+            assert s.n_steps == len(steps), (seed, B, n_sample)
+            for k, st in enumerate(steps):
+                M = st['M']
+                assert e['M'][k] == M
+                np.testing.assert_array_equal(e['X'][k, :M], st['X'])
+                np.testing.assert_array_equal(e['Y'][k, :M], st['Y'])
+                np.testing.assert_array_equal(e['F'][k, :M] & 1, st['R'].astype(np.uint8))
+                np.testing.assert_array_equal(e['slots'][k, :M], st['slots'])
+        try:
+            steps = orc.build_eval_schedule(items, offset, B)
+        except IndexError:
+            with pytest.raises(IndexError):
+                _lib.Schedule(items, offset, None, B, 0, mode=1)
+            continue
+        s = _lib.Schedule(items, offset, None, B, 0, mode=1)
+        e = s.export()
+        assert s.n_steps == len(steps), (seed, B, 'eval')
+        for k, st in enumerate(steps):
+            M = st['M']
+            assert e['M'][k] == M
+            np.testing.assert_array_equal(e['X'][k, :M], st['X'])
+            np.testing.assert_array_equal(e['Y'][k, :M], st['Y'])
+            np.testing.assert_array_equal((e['F'][k, :M] >> 1) & 1, st['Z'].astype(np.uint8))
+            np.testing.assert_array_equal(e['slots'][k, :M], st['slots'])

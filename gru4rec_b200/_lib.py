@@ -39,6 +39,7 @@ EXPORTS = [
     'g4r_schedule_build', 'g4r_schedule_free', 'g4r_schedule_steps', 'g4r_schedule_events', 'g4r_schedule_export',
     'g4r_train_step', 'g4r_train_steps', 'g4r_upload_steps', 'g4r_run_uploaded', 'g4r_kernel_launches',
     'g4r_profile_uploaded', 'g4r_phase_name', 'g4r_phase_count', 'g4r_persistent_stamps', 'g4r_fast_windows', 'g4r_mg_unique_id', 'g4r_mg_init',
+    'g4r_mg_sharded', 'g4r_mg_ipc_handle', 'g4r_mg_ipc_open', 'g4r_mg_owner', 'g4r_mg_local_row', 'g4r_mg_shard_rows', 'g4r_mg_segment_bytes',
     'g4r_eval_schedule', 'g4r_set_eval_items', 'g4r_predict', 'g4r_reset_eval_hidden',
 ]
 
@@ -94,6 +95,13 @@ def load():
     lib.g4r_fast_windows.argtypes = [vp, C.POINTER(i64)]; lib.g4r_fast_windows.restype = i64
     lib.g4r_mg_unique_id.argtypes = [vp]
     lib.g4r_mg_init.argtypes = [vp, vp]
+    lib.g4r_mg_sharded.argtypes = [vp]
+    lib.g4r_mg_ipc_handle.argtypes = [vp, vp]
+    lib.g4r_mg_ipc_open.argtypes = [vp, vp, i32]
+    lib.g4r_mg_owner.argtypes = [i64, i32]
+    lib.g4r_mg_local_row.argtypes = [i64, i32]; lib.g4r_mg_local_row.restype = i64
+    lib.g4r_mg_shard_rows.argtypes = [i64, i32, i32]; lib.g4r_mg_shard_rows.restype = i64
+    lib.g4r_mg_segment_bytes.argtypes = [C.POINTER(G4RConfig), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     lib.g4r_eval_schedule.argtypes = [vp, vp, vp, i32, i32, vp, vp, C.POINTER(i64)]
     lib.g4r_set_eval_items.argtypes = [vp, vp, i64]
     lib.g4r_predict.argtypes = [vp, vp, i32, vp, vp]
@@ -126,7 +134,7 @@ def parse_act(name):
     raise NotImplementedError
 
 
-def make_config(n_items, mk, sample_store=0, eval_lanes=0, max_resident_steps=0, step_mode=0, world_size=1, rank=0):
+def make_config(n_items, mk, sample_store=0, eval_lanes=0, max_resident_steps=0, step_mode=0, world_size=1, rank=0, replicated=False, eval_tc=None):
     cfg = G4RConfig()
     layers = mk.get('layers', [100])
     cfg.n_items = n_items
@@ -157,6 +165,8 @@ def make_config(n_items, mk, sample_store=0, eval_lanes=0, max_resident_steps=0,
     cfg.world_size, cfg.rank = world_size, rank
     cfg.eval_batch_size = eval_lanes
     cfg.step_mode = step_mode
+    cfg.reserved[0] = 1 if replicated else 0      # multi-GPU: replicated tables + NCCL exchange instead of row sharding
+    cfg.reserved[1] = 0 if eval_tc is None else (2 if eval_tc else 1)   # scoring path: auto / force tcgen05 tiles / force fp32 FFMA tiles
     return cfg
 
 
@@ -268,6 +278,8 @@ class Engine(object):
 
     def get(self, name):
         r, c = self.shape(name)
+        if name.split('.')[0] in ('Wy', 'By', 'Wx0'):
+            self._quiesce()
         a = np.empty((r, c), dtype=np.float32)
         self._check(self.lib.g4r_get_tensor(self.h, name.encode(), _ptr(a), r, c))
         return a
@@ -388,6 +400,30 @@ class Engine(object):
         raw = bytes(t.cpu().tolist())
         idbuf = (C.c_char * 128).from_buffer_copy(raw)
         self._check(self.lib.g4r_mg_init(self.h, idbuf))
+        self._dist = dist
+        if self.sharded():
+            # row-sharded tables: every rank maps the segments of all peers (cudaIpc); the 64-byte handles travel by all-gather
+            mh = (C.c_char * 64)()
+            self._check(self.lib.g4r_mg_ipc_handle(self.h, mh))
+            dev = 'cuda' if dist.get_backend() == 'nccl' else 'cpu'
+            mine = torch.tensor(list(bytes(mh)), dtype=torch.uint8, device=dev)
+            allh = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+            dist.all_gather(allh, mine)
+            raw = b''.join(bytes(t.cpu().tolist()) for t in allh)
+            buf2 = (C.c_char * len(raw)).from_buffer_copy(raw)
+            self._check(self.lib.g4r_mg_ipc_open(self.h, buf2, dist.get_world_size()))
+            dist.barrier()
+
+    def sharded(self):
+        return bool(self.lib.g4r_mg_sharded(self.h))
+
+    def _quiesce(self):
+        """sharded tensors are assembled from all ranks' memory: every rank must have finished its device work"""
+        d = getattr(self, '_dist', None)
+        if d is not None and self.sharded():
+            import torch
+            torch.cuda.synchronize()
+            d.barrier()
 
     def fast_windows(self):
         fb = C.c_int64()

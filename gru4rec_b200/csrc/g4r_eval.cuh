@@ -3,6 +3,7 @@
 // consecutive items against all lanes and counts how many beat / tie the lane's target score.
 // Included at the end of g4r_lib.cu (uses its handle type and helper macros).
 #pragma once
+#include "g4r_eval_tc.cuh"
 
 constexpr int EV_IT = 64;     // items per CTA tile
 constexpr int EV_TB = 32;     // lanes per row tile
@@ -204,6 +205,7 @@ static int eval_ctx(g4r_handle* h, EvalCtx** out) {
   CK(slot_upload(e.slot, e.mde, h->stream));
   cudaFuncSetAttribute(k_eval_score<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eval_smem_bytes());
   cudaFuncSetAttribute(k_eval_score<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eval_smem_bytes());
+  if (cudaFuncSetAttribute(k_eval_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcSmem)) != cudaSuccess) cudaGetLastError();
   h->eval_ctx = new EvalCtx(e);
   *out = static_cast<EvalCtx*>(h->eval_ctx);
   return G4R_OK;
@@ -266,7 +268,12 @@ extern "C" int g4r_eval_schedule(g4r_handle* h, const g4r_schedule* s, const int
       eval_forward(h, e, (int)i);
       k_eval_tgt<<<(Be + 127) / 128, 128, 0, st>>>(e->slot, (int)i, h->dTgt, h->dRankCnt);
       const int n_comp = e->n_cand > 0 ? e->n_cand : I;
-      k_eval_score<false><<<(n_comp + EV_IT - 1) / EV_IT, EV_THREADS, eval_smem_bytes(), st>>>(e->slot, (int)i, h->dTgt, h->dRankCnt, nullptr, e->n_cand > 0 ? e->dCand : nullptr, e->n_cand);
+      // full-catalogue ranking of a wide batch: the [items x lanes] score tiles go through the tensor cores (tcgen05, 3xTF32);
+      // small batches / candidate subsets stay on the fp32 FFMA tiles.  cfg.reserved[1]: 1 forces FFMA, 2 forces tcgen05.
+      const int M_i = e->hM[i];
+      const bool tc = e->n_cand == 0 && h->cfg.reserved[1] != 1 && (h->cfg.reserved[1] == 2 || (M_i >= 64 && I >= 2048));
+      if (tc) k_eval_tc<<<std::min((I + TC_M - 1) / TC_M, h->n_sm), TC_THREADS, sizeof(TcSmem), st>>>(e->slot, (int)i, h->dTgt, h->dRankCnt);
+      else k_eval_score<false><<<(n_comp + EV_IT - 1) / EV_IT, EV_THREADS, eval_smem_bytes(), st>>>(e->slot, (int)i, h->dTgt, h->dRankCnt, nullptr, e->n_cand > 0 ? e->dCand : nullptr, e->n_cand);
       k_eval_rank<<<1, 32, 0, st>>>(e->slot, (int)i, h->dRankCnt, e->dCut, n_cut, mode, e->dSums);
       h->launches += 3;
     }

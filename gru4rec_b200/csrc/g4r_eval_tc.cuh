@@ -1,0 +1,252 @@
+// g4r_eval_tc.cuh -- full-catalogue scoring of evaluate_gpu on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// What is computed (reference: yhat = h Wy^T + By, gru4rec.py:502; ranks = (others > targets).sum + 1, evaluation.py:57-64):
+// for every lane b of the evaluation batch the number of catalogue items whose score beats / ties the score of the lane's
+// target.  The [items x lanes] score matrix (37,483 x 512 at the RSC15 shape: 3.8 GFLOP per mini-batch, the largest dense
+// contraction of the whole path) is never written: each 128-item x 256-lane tile is accumulated in TMEM by UMMA
+// (tcgen05.mma kind::tf32, M = 128, N = 256, K = 8), read back with tcgen05.ld, and reduced to the two counters in registers.
+//
+// fp32 fidelity on TF32 tensor cores: 3xTF32 -- every fp32 operand x is split as hi = tf32(x), lo = tf32(x - hi) and the
+// product is accumulated as lo*hi + hi*lo + hi*hi (the dropped lo*lo term and the roundings are ~2^-21 relative), i.e. ~1e-6
+// relative on the scores, far inside the 1e-4 bar on Recall / MRR.  The target's own column is excluded explicitly (it is
+// the one comparison that must be exact), so a rank can only move where two DIFFERENT items' scores differ by < 1e-6 relative.
+//
+// Structure (one CTA per SM, 256 threads, persistent over its item tiles):
+//   warps 4-7  producers: load a 32-wide K chunk of the item rows (A) and of the hidden states (B) with 16-byte loads,
+//              split into hi / lo, store in the canonical K-major no-swizzle UMMA layout (8 x 16-byte core matrices);
+//              one elected thread issues the 12 MMAs of the chunk and tcgen05.commit-s the stage back (2 stages, 96 KB each)
+//   warps 0-3  epilogue: wait for the accumulator (2 x 256 TMEM columns, double buffered), tcgen05.ld 32 columns at a time,
+//              bias + final activation + compare with the lane's target score, warp ballots -> per-lane counters
+// All waits are mbarrier try_wait loops with a time-out that sets an error flag (a wrong phase must not hang the box).
+#pragma once
+
+constexpr int TC_M = 128;            // items per tile (UMMA M, TMEM lanes)
+constexpr int TC_N = 256;            // evaluation lanes per tile (UMMA N, TMEM columns per accumulator)
+constexpr int TC_KC = 32;            // K chunk per pipeline stage (floats)
+constexpr int TC_THREADS = 256;
+constexpr int TC_STAGES = 2;
+constexpr uint32_t TC_A_BYTES = TC_M * TC_KC * 4;       // 16 KB per hi / lo array
+constexpr uint32_t TC_B_BYTES = TC_N * TC_KC * 4;       // 32 KB
+constexpr uint32_t TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // 96 KB
+constexpr unsigned long long TC_TIMEOUT_NS = 2000000000ull;
+
+struct TcSmem {
+  alignas(1024) unsigned char stage[TC_STAGES][TC_STAGE_BYTES];   // [A hi | A lo | B hi | B lo]
+  alignas(8) unsigned long long full_unused;
+  unsigned long long stage_free[TC_STAGES];    // MMAs that read the stage have completed (tcgen05.commit)
+  unsigned long long acc_full[2];              // all MMAs of the tile have completed (tcgen05.commit)
+  unsigned long long acc_free[2];              // epilogue has drained the accumulator (128 arrivals)
+  uint32_t tmem_base;
+  int err;
+  float sTgt[TC_N];                            // target scores of the lane block
+  int sYit[TC_N];                              // target items of the lane block
+};
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tc_mbar_init(unsigned long long* bar, unsigned int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(tc_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(tc_smem_u32(bar)) : "memory");
+}
+// a wait that does not complete within TC_TIMEOUT_NS is a protocol bug: trap (the launch fails with an error) rather than hang
+__device__ __forceinline__ bool tc_mbar_wait(unsigned long long* bar, unsigned int parity, int* err) {
+  const uint32_t a = tc_smem_u32(bar);
+  unsigned long long t0 = 0; unsigned int spins = 0;
+  while (true) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (ok) return true;
+    if ((++spins & 63u) == 0) {
+      unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      if (t - t0 > TC_TIMEOUT_NS) { *(volatile int*)err = 1; asm volatile("trap;"); }
+    }
+  }
+}
+__device__ __forceinline__ uint32_t tc_tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+// K-major, no swizzle: 8-row x 16-byte core matrices; LBO (next core matrix along K) = 128 B, SBO (next 8 rows) = 1024 B
+__device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+               :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(tc_smem_u32(bar)) : "memory");
+}
+
+// stage rows [r0, r0 + nrows) x k [k0, k0 + 32) of a row-major fp32 matrix as hi / lo TF32 in the core-matrix layout
+// rowptr(r) -> pointer to the row (nullptr: zeros); executed by the 128 producer threads (pt = 0..127)
+template <class FRow>
+__device__ __forceinline__ void tc_stage_operand(unsigned char* hi, unsigned char* lo, int nrows, int k0, int K, int pt, FRow rowptr) {
+  // item = (row, 16-byte chunk c of 8); thread mapping: rows fastest -> conflict-free 16-byte shared stores
+  const int total = nrows * 8;
+  for (int i0 = 0; i0 < total; i0 += 4 * 128) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * 128 + pt;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < total) {
+        const int r = i % nrows, c = i / nrows;
+        const float* rp = rowptr(r);
+        if (rp && k0 + c * 4 < K) v[u] = ld4(rp + k0 + c * 4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * 128 + pt;
+      if (i < total) {
+        const int r = i % nrows, c = i / nrows;
+        const uint32_t off = (uint32_t)(((r >> 3) * 8 + c) * 128 + (r & 7) * 16);
+        uint4 h, l;
+        h.x = tc_tf32(v[u].x); h.y = tc_tf32(v[u].y); h.z = tc_tf32(v[u].z); h.w = tc_tf32(v[u].w);
+        l.x = tc_tf32(v[u].x - __uint_as_float(h.x)); l.y = tc_tf32(v[u].y - __uint_as_float(h.y));
+        l.z = tc_tf32(v[u].z - __uint_as_float(h.z)); l.w = tc_tf32(v[u].w - __uint_as_float(h.w));
+        *reinterpret_cast<uint4*>(hi + off) = h;
+        *reinterpret_cast<uint4*>(lo + off) = l;
+      }
+    }
+  }
+}
+
+// cnt[b*2 + 0] += #items with score > target score of lane b; cnt[b*2 + 1] += #items with score == target (the target itself
+// counts as one tie, exactly as in the fp32 kernel where its score equals the target score bit for bit)
+__global__ void __launch_bounds__(TC_THREADS, 1) k_eval_tc(int slot, int s, const float* __restrict__ tgt, int* cnt) {
+  extern __shared__ __align__(1024) unsigned char tc_raw[];
+  TcSmem& sm = *reinterpret_cast<TcSmem*>(tc_raw);
+  const ModelDev& md = MD;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int M = md.wM[s], I = md.n_items, ldL = md.ldL, K = md.L;
+  const float* __restrict__ Y = md.layer[md.n_layers - 1].y;
+  const int n_tiles = (I + TC_M - 1) / TC_M;
+  const int n_half = (M + TC_N - 1) / TC_N;
+  const int n_chunk = (K + TC_KC - 1) / TC_KC;
+  if (tid == 0) {
+    for (int i = 0; i < TC_STAGES; i++) tc_mbar_init(&sm.stage_free[i], 1);
+    for (int i = 0; i < 2; i++) { tc_mbar_init(&sm.acc_full[i], 1); tc_mbar_init(&sm.acc_free[i], 128); }
+    sm.err = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 4) {   // TMEM: 512 columns = two 128 x 256 fp32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tc_smem_u32(&sm.tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = sm.tmem_base;
+  // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 256, M = 128
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+  if (warp >= 4) {
+    // ================= producers + MMA issue =================
+    const int pt = tid - 128;
+    unsigned int it = 0;          // chunk counter -> stage = it % 2, use = it / 2
+    unsigned int wi = 0;          // work item counter -> accumulator = wi % 2
+    bool ok = true;
+    for (int h = 0; h < n_half && ok; h++) {
+      const int b0 = h * TC_N;
+      for (int t = blockIdx.x; t < n_tiles && ok; t += gridDim.x, wi++) {
+        const int i0 = t * TC_M;
+        const uint32_t acc = wi & 1u;
+        for (int c = 0; c < n_chunk && ok; c++, it++) {
+          const uint32_t st = it & 1u, use = it >> 1;
+          if (use > 0) ok = tc_mbar_wait(&sm.stage_free[st], (use - 1) & 1u, &sm.err);    // the MMAs of the previous use are done
+          if (!ok) break;
+          unsigned char* base = sm.stage[st];
+          const int k0 = c * TC_KC;
+          tc_stage_operand(base, base + TC_A_BYTES, TC_M, k0, K, pt, [&](int r) -> const float* { return i0 + r < I ? md.Wy + (size_t)(i0 + r) * ldL : nullptr; });
+          tc_stage_operand(base + 2 * TC_A_BYTES, base + 2 * TC_A_BYTES + TC_B_BYTES, TC_N, k0, K, pt, [&](int r) -> const float* { return b0 + r < M ? Y + (size_t)(b0 + r) * ldL : nullptr; });
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (pt == 0) {
+            if (c == 0 && wi >= 2) ok = tc_mbar_wait(&sm.acc_free[acc], ((wi >> 1) - 1) & 1u, &sm.err);   // epilogue drained this accumulator
+            if (ok) {
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              const uint32_t a_hi = tc_smem_u32(base), a_lo = a_hi + TC_A_BYTES, b_hi = a_hi + 2 * TC_A_BYTES, b_lo = b_hi + TC_B_BYTES;
+              const uint32_t d = tmem + acc * TC_N;
+              const int ksteps = (min(TC_KC, K - k0) + 7) / 8;
+              for (int j = 0; j < ksteps; j++) {
+                const uint32_t o = (uint32_t)j * 256u;     // 8 floats along K = 2 core matrices
+                const uint32_t first = (c == 0 && j == 0) ? 0u : 1u;
+                tc_mma_tf32(d, tc_desc(a_lo + o), tc_desc(b_hi + o), idesc, first);
+                tc_mma_tf32(d, tc_desc(a_hi + o), tc_desc(b_lo + o), idesc, 1u);
+                tc_mma_tf32(d, tc_desc(a_hi + o), tc_desc(b_hi + o), idesc, 1u);
+              }
+              tc_commit(&sm.stage_free[st]);
+              if (c == n_chunk - 1) tc_commit(&sm.acc_full[acc]);
+            }
+          }
+          // the other producer threads run ahead to the next chunk (bounded by the stage_free wait)
+        }
+      }
+    }
+  } else {
+    // ================= epilogue: TMEM -> registers -> counters =================
+    unsigned int wi = 0;
+    bool ok = true;
+    const bool elem_act = md.fact.kind <= G4R_ACT_SELU;
+    for (int h = 0; h < n_half && ok; h++) {
+      const int b0 = h * TC_N;
+      asm volatile("bar.sync 2, 128;" ::: "memory");      // previous lane block's sTgt / sYit no longer read
+      for (int i = tid; i < TC_N; i += 128) {
+        const bool v = b0 + i < M;
+        sm.sTgt[i] = v ? tgt[b0 + i] : 0.f;
+        sm.sYit[i] = v ? md.wY[(size_t)s * md.B + b0 + i] : -1;
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      int cgt[TC_N / 32], ceq[TC_N / 32];
+#pragma unroll
+      for (int q = 0; q < TC_N / 32; q++) { cgt[q] = 0; ceq[q] = 0; }
+      for (int t = blockIdx.x; t < n_tiles && ok; t += gridDim.x, wi++) {
+        const uint32_t acc = wi & 1u;
+        const int item = t * TC_M + warp * 32 + lane;      // this thread's row of the tile (TMEM lane 32 * warp + lane)
+        const bool vrow = item < I;
+        const float by = vrow ? md.By[item] : 0.f;
+        ok = tc_mbar_wait(&sm.acc_full[acc], (wi >> 1) & 1u, &sm.err);
+        if (!ok) break;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < TC_N / 32; q++) {
+          uint32_t r[32];
+          const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + acc * TC_N + q * 32;
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                       "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+                         "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+                         "=r"(r[30]), "=r"(r[31]) : "r"(taddr) : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const int n = q * 32 + j;
+            float sc = __uint_as_float(r[j]) + by;
+            if (elem_act) sc = act_fwd(md.fact, sc);
+            const float tg = sm.sTgt[n];
+            const bool self = vrow && sm.sYit[n] == item;
+            const bool live = vrow && !self && (b0 + n < M);
+            const unsigned int mg = __ballot_sync(0xffffffffu, live && sc > tg);
+            const unsigned int me = __ballot_sync(0xffffffffu, self || (live && sc == tg));
+            if (lane == j) { cgt[q] += __popc(mg); ceq[q] += __popc(me); }
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        tc_mbar_arrive(&sm.acc_free[acc]);
+      }
+#pragma unroll
+      for (int q = 0; q < TC_N / 32; q++) {
+        const int b = b0 + q * 32 + lane;
+        if (b < M) { if (cgt[q]) atomicAdd(&cnt[b * 2], cgt[q]); if (ceq[q]) atomicAdd(&cnt[b * 2 + 1], ceq[q]); }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
+  }
+}

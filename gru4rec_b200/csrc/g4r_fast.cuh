@@ -223,7 +223,8 @@ constexpr int FK_W1 = 5;    // rz columns per CTA   (ceil(2*128 / 48) = 6 would 
 constexpr int FK_W2 = 3;    // h / dHr columns per CTA (L <= 144)
 
 // F1: rz = sigmoid(Wx0[X][L:3L] + Bh[L:3L] + H @ Wrz) for this CTA's FK_W1 columns; CTA 0 also writes Hold
-__device__ void fk_f1(const ModelDev& md, FastSmem& sm, int s, int cta, const unsigned int* wait_ctr, unsigned int wait_target) {
+// inrows != nullptr (row-sharded multi-GPU): the gathered input rows Wx0[X] of the step sit in a local [B x ld3] buffer
+__device__ void fk_f1(const ModelDev& md, FastSmem& sm, int s, int cta, const unsigned int* wait_ctr, unsigned int wait_target, const float* inrows = nullptr) {
   const LayerDev& ly = md.layer[0];
   const int M = md.wM[s], L = ly.L, ldL = ly.ldL, tid = threadIdx.x;
   const int c0 = cta * FK_W1;
@@ -244,7 +245,7 @@ __device__ void fk_f1(const ModelDev& md, FastSmem& sm, int s, int cta, const un
   __syncthreads();
   const bool early = sm.sFlag[3] != 0;
   float pre = 0.f;
-  if (early && jsel < W && b < M) pre = ly.Wx[(size_t)sm.gIdx[FK_B + b] * ly.ld3 + L + c0 + jsel] + ly.Bh[L + c0 + jsel];
+  if (early && jsel < W && b < M) pre = (inrows ? inrows[(size_t)b * ly.ld3 + L + c0 + jsel] : ly.Wx[(size_t)sm.gIdx[FK_B + b] * ly.ld3 + L + c0 + jsel]) + ly.Bh[L + c0 + jsel];
   float acc[FK_W1];
   fk_slab_dot<FK_W1>(acc, sm.gA, FK_LDS, sm.gW, L);
   const float v = fk_slab_reduce<FK_W1>(acc, sm.gW + 8 * FK_LDS, jsel);
@@ -253,7 +254,7 @@ __device__ void fk_f1(const ModelDev& md, FastSmem& sm, int s, int cta, const un
   if (!early) {
     if (tid == 0) wait_ge(wait_ctr, wait_target);
     __syncthreads();
-    if (jsel < W && b < M) pre = ly.Wx[(size_t)sm.gIdx[FK_B + b] * ly.ld3 + L + c0 + jsel] + ly.Bh[L + c0 + jsel];
+    if (jsel < W && b < M) pre = (inrows ? inrows[(size_t)b * ly.ld3 + L + c0 + jsel] : ly.Wx[(size_t)sm.gIdx[FK_B + b] * ly.ld3 + L + c0 + jsel]) + ly.Bh[L + c0 + jsel];
   }
   if (jsel < W && b < M) {
     const int c = c0 + jsel;
@@ -268,7 +269,7 @@ __device__ void fk_f1(const ModelDev& md, FastSmem& sm, int s, int cta, const un
   }
 }
 // F2: h~ = act(Wx0[X][0:L] + Bh[0:L] + (H*r) @ Wh), h, dropout, H_new for this CTA's FK_W2 columns
-__device__ void fk_f2(const ModelDev& md, FastSmem& sm, int s, int cta) {
+__device__ void fk_f2(const ModelDev& md, FastSmem& sm, int s, int cta, const float* inrows = nullptr) {
   const LayerDev& ly = md.layer[0];
   const int M = md.wM[s], L = ly.L, ldL = ly.ldL, tid = threadIdx.x;
   const int c0 = cta * FK_W2;
@@ -302,7 +303,7 @@ __device__ void fk_f2(const ModelDev& md, FastSmem& sm, int s, int cta) {
   float pre = 0.f, z = 0.f, ho = 0.f;
   if (jsel < W && b < M) {
     const int c = c0 + jsel;
-    pre = ly.Wx[(size_t)sm.gIdx[FK_B + b] * ly.ld3 + c] + ly.Bh[c];
+    pre = (inrows ? inrows[(size_t)b * ly.ld3 + c] : ly.Wx[(size_t)sm.gIdx[FK_B + b] * ly.ld3 + c]) + ly.Bh[c];
     z = ly.z[(size_t)b * ldL + c];
     ho = ly.Hold[(size_t)b * ldL + c];
   }

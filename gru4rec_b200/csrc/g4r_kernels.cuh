@@ -35,6 +35,30 @@ struct MgDev {                       // device pointers of the multi-GPU state
 };
 
 struct MgTensor { float *p, *acc, *vel; size_t goff; int count; };
+
+// ---- row-sharded multi-GPU state (g4r_shard.cuh): item tables live only on their owner (row i -> rank i % R, local row i / R);
+// peers read parameter rows and write gradient rows through peer-mapped pointers (cudaIpc) inside the persistent kernel ----
+constexpr int MGS_MAXR = 8;            // ranks of one NVSwitch box
+constexpr int MGS_FLAG_STRIDE = 32;    // one cross-GPU flag per 128-byte line
+constexpr int MGS_GRU_CTAS = 48;       // == FK_G (g4r_fast.cuh)
+enum { MGF_ROWS = 0, MGF_APPLIED = MGS_MAXR, MGF_IN = 2 * MGS_MAXR, MGF_INAPPLIED = 3 * MGS_MAXR, MGF_DENSE = 4 * MGS_MAXR,
+       MGF_COUNT = 4 * MGS_MAXR + MGS_MAXR * MGS_GRU_CTAS };
+struct ShardDev {
+  int R, rank, rows_local, ldW;        // ldW = ldL + 4: a table row is [Wy row | By | 0 0 0] so that one bulk copy brings both
+  int NA, DSL;                         // CTAs that apply the owned rows; capacity (floats) of one GRU CTA's dense-gradient slice
+  float* W[MGS_MAXR];                  // [rows_local x ldW] parameter shard of every rank (index = rank; own entry = local memory)
+  float* Wx[MGS_MAXR];                 // [rows_local x ld3] input-side table shard (no-embedding mode)
+  float* inbox[MGS_MAXR];              // [2][R][NP][ldW] gradient rows (dSy | dby) written by rank r for the columns it scored
+  float* inboxIn[MGS_MAXR];            // [2][R][B][ld3]  gradient rows of the gathered input rows
+  float* denseIn[MGS_MAXR];            // [2][R][MGS_GRU_CTAS][DSL] dense-gradient slices
+  unsigned int* flags[MGS_MAXR];       // [MGF_COUNT][MGS_FLAG_STRIDE] sequence flags, written by peers, polled locally
+  float *W_acc, *W_vel, *Wx_acc, *Wx_vel;   // optimizer state of the owned rows (local)
+  float* mgIn;                         // [B][ld3] input rows of the current mini-batch, gathered from their owners
+  const int *aEnt, *aItem, *aCbeg;     // merged plan of the rows this rank owns: entries (rank << 20 | column) [CAP][R*NP], chunks [CAP][NA+1]
+  const int *xEnt, *xItem, *xTot;      // owned input rows: entries (rank << 16 | lane) [CAP][R*B], count [CAP]
+  const int *gX, *gM;                  // all ranks' inputs / batch sizes of the window [R][MG_CAP][B], [R][MG_CAP]
+  int* abort;                          // set when a cross-GPU wait timed out
+};
 // synchronisation counters of the role-specialised kernel (g4r_fast.cuh), one per 128-byte line
 struct FastSync {                   // one counter per 128-byte line
   unsigned int bar;      unsigned int p0[31];
@@ -91,6 +115,8 @@ struct ModelDev {
   int CAP;
   const int *wX, *wY, *wSlot, *wM, *wSti, *wXnext; const uint8_t *wF, *wXflag; const uint32_t* wG;
   int *pItem, *pPos, *pTcol, *pCbeg;
+  int* pKey;                                // sharded multi-GPU: owner-major sort key (owner * n_items + item) of every sorted column
+  int shardR;                               // > 0: tables are row-sharded over shardR ranks (columns sorted owner-major, equal chunks)
   const int* ST;                            // sample store [rows x S] int32
 };
 

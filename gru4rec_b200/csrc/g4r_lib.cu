@@ -18,8 +18,18 @@ static thread_local std::string g_create_error;
 struct g4r_handle;
 static void eval_release(g4r_handle* h);
 static void mg_release(g4r_handle* h);
+static void shard_release(g4r_handle* h);
+static bool shard_eligible(const g4r_config& c, int n_sm);
+static int shard_create(g4r_handle* h);
+struct TensorInfo;
+static int shard_set_tensor(g4r_handle* h, const TensorInfo& t, const float* host);
+static int shard_get_tensor(g4r_handle* h, const TensorInfo& t, float* host);
+static int mgs_run_window(g4r_handle* h, int64_t n);
+static int mgs_plan_window(g4r_handle* h, int64_t n);
 
-struct TensorInfo { float* ptr; int64_t rows, cols, ld; };
+// sharded: row i of the logical [rows x cols] tensor lives on rank i % R at local row i / R; seg_off = byte offset of element
+// (0, 0) inside every rank's peer-mapped segment (g4r_shard.cuh)
+struct TensorInfo { float* ptr; int64_t rows, cols, ld; bool sharded = false; size_t seg_off = 0; };
 
 struct g4r_schedule {
   int B = 0, mode = 0;
@@ -64,6 +74,9 @@ struct g4r_handle {
   bool mg_alloc = false; MgDev mgdev; std::vector<MgTensor> mg_tensors;
   void* eval_ctx = nullptr;      // EvalCtx* (g4r_eval.cuh), owned by the handle
   void* mg_host = nullptr;       // MgHost*  (g4r_multi.cuh), owned by the handle
+  void* shard = nullptr;         // ShardHost* (g4r_shard.cuh): row-sharded item tables + in-kernel exchange, owned by the handle
+  char* shard_ws = nullptr;      // workspace carve-outs of the sharded path (plans, device descriptor, counters, gathered input rows)
+  size_t shard_ws_bytes = 0;
   FastSync* dFastSync = nullptr; bool fast_ok = false; bool fastc_ok = false; int fastc_grid = 0; int* hFlags = nullptr; int64_t fast_windows = 0, slow_windows = 0;
   bool prof = false; bool stamp_on = false;
   std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_phase;
@@ -122,6 +135,7 @@ static int model_mode(const g4r_config& c) { return c.constrained_embedding ? 2 
 static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
+  const bool shard = shard_eligible(c, n_sm);     // multi-GPU with row-sharded item tables: they live in the peer-mapped segment
   const int mode = model_mode(c);
   const int nl = c.n_layers;
   const int B = c.batch_size;
@@ -134,15 +148,16 @@ static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
   const bool store = gen_len > 1;
   const int S = store ? c.n_sample : 0;
   const int NP = round4(B + S);
-  const int NCH = std::max(1, std::min(n_sm, (NP + 3) / 4));
+  const int NCH = std::max(1, std::min(shard ? n_sm - MGS_GRU_CTAS : n_sm, (NP + 3) / 4));   // sharded: the GRU CTAs own no columns
   const int R = c.world_size > 1 ? c.world_size : 1;
   const int CAP = std::max(c.max_resident_steps > 0 ? c.max_resident_steps : 2048, R > 1 ? MG_CAP : 1);
   ModelDev md; memset(&md, 0, sizeof(md));
   md.n_items = c.n_items; md.n_layers = nl; md.B = B; md.Bld = round4(Bmax); md.S = S; md.mode = mode; md.L = Llast; md.ldL = ldL;
-  md.NP = NP; md.NCH = NCH; md.CAP = CAP; md.S_cfg = c.n_sample;
+  md.NP = NP; md.NCH = NCH; md.CAP = CAP; md.S_cfg = c.n_sample; md.shardR = shard ? R : 0;
   md.loss = c.loss; md.fact = {c.final_act, c.final_act_p1, c.final_act_p2}; md.hact = {c.hidden_act, c.hidden_act_p1, c.hidden_act_p2};
   md.p_drop_h = c.dropout_p_hidden; md.p_drop_e = c.dropout_p_embed; md.lr = c.learning_rate; md.mom = c.momentum; md.lmbd = c.lmbd;
-  md.bpreg = c.bpreg; md.logq = c.logq; md.alpha = c.sample_alpha; md.adapt = c.adapt; md.drop_seed = c.dropout_seed;
+  md.bpreg = c.bpreg; md.logq = c.logq; md.alpha = c.sample_alpha; md.adapt = c.adapt;
+  md.drop_seed = c.dropout_seed + (c.world_size > 1 ? (uint32_t)c.rank * 0x9E3779B1u : 0u);   // multi-GPU: independent masks per rank
   md.in0_dim = mode == 2 ? Llast : (mode == 1 ? c.embedding : 0);
   md.ld_in0 = round4(md.in0_dim);
   auto reg = [&](const std::string& name, float* p, int64_t rows, int64_t cols, int64_t ld) { if (!cv.dry) h->tensors[name] = TensorInfo{p, rows, cols, ld}; };
@@ -153,8 +168,10 @@ static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
     *v = mom ? cv.take<float>((size_t)rows * ld) : nullptr; if (mom) reg(name + ".vel", *v, rows, cols, ld);
   };
   // item tables
-  table3("Wy", c.n_items, Llast, &md.Wy, &md.Wy_acc, &md.Wy_vel);
-  table3("By", c.n_items, 1, &md.By, &md.By_acc, &md.By_vel, 1);   // dense [I] vector
+  if (!shard) {
+    table3("Wy", c.n_items, Llast, &md.Wy, &md.Wy_acc, &md.Wy_vel);
+    table3("By", c.n_items, 1, &md.By, &md.By_acc, &md.By_vel, 1);   // dense [I] vector
+  }
   if (mode == 1) table3("E", c.n_items, c.embedding, &md.E, &md.E_acc, &md.E_vel);
   for (int i = 0; i < nl; i++) {
     LayerDev& ly = md.layer[i];
@@ -164,7 +181,7 @@ static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
     if (i == 0) { in_rows = mode == 0 ? c.n_items : md.in0_dim; ly.in_dim = mode == 0 ? 0 : md.in0_dim; ly.ld_in = md.ld_in0; }
     else { in_rows = c.layers[i - 1]; ly.in_dim = c.layers[i - 1]; ly.ld_in = round4(c.layers[i - 1]); }
     const std::string si = std::to_string(i);
-    table3("Wx" + si, in_rows, 3 * L, &ly.Wx, &ly.Wx_acc, &ly.Wx_vel);
+    if (!(shard && i == 0)) table3("Wx" + si, in_rows, 3 * L, &ly.Wx, &ly.Wx_acc, &ly.Wx_vel);
     table3("Wh" + si, L, L, &ly.Wh, &ly.Wh_acc, &ly.Wh_vel);
     table3("Wrz" + si, L, 2 * L, &ly.Wrz, &ly.Wrz_acc, &ly.Wrz_vel);
     table3("Bh" + si, 1, 3 * L, &ly.Bh, &ly.Bh_acc, &ly.Bh_vel);
@@ -198,6 +215,7 @@ static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
   int* dM = cv.take<int>(CAP); int* dSti = cv.take<int>(CAP); uint32_t* dG = cv.take<uint32_t>(CAP);
   md.pItem = cv.take<int>((size_t)CAP * NP); md.pPos = cv.take<int>((size_t)CAP * NP);
   md.pTcol = cv.take<int>((size_t)CAP * B); md.pCbeg = cv.take<int>((size_t)CAP * (NCH + 1));
+  md.pKey = shard ? cv.take<int>((size_t)CAP * NP) : nullptr;
   int* dStepBase = cv.take<int>(4);
   GridBar* dGridBar = cv.take<GridBar>(1);
   FastSync* dFastSync = cv.take<FastSync>(1);
@@ -230,10 +248,18 @@ static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
     mgd.gItem = cv.take<int>((size_t)R * MG_CAP * NP); mgd.gPos = nullptr;
     mgd.gM = cv.take<int>((size_t)R * MG_CAP); mgd.gX = cv.take<int>((size_t)R * MG_CAP * B);
     mgd.mEnt = cv.take<int>((size_t)MG_CAP * R * NP); mgd.mItem = cv.take<int>((size_t)MG_CAP * R * NP);
-    mgd.mCbeg = cv.take<int>((size_t)MG_CAP * (NCH + 1)); mgd.mTot = cv.take<int>(MG_CAP);
+    mgd.mCbeg = cv.take<int>((size_t)MG_CAP * (n_sm + 1)); mgd.mTot = cv.take<int>(MG_CAP);
     mgd.xEnt = cv.take<int>((size_t)MG_CAP * R * B); mgd.xItem = cv.take<int>((size_t)MG_CAP * R * B); mgd.xTot = cv.take<int>(MG_CAP);
-    const int in_ld = mode == 0 ? md.layer[0].ld3 : md.ld_in0;
-    mgd.DSYall = cv.take<float>((size_t)R * NP * ldL); mgd.DBYall = cv.take<float>((size_t)R * NP); mgd.INall = cv.take<float>((size_t)R * B * in_ld);
+    if (!shard) {
+      const int in_ld = mode == 0 ? md.layer[0].ld3 : md.ld_in0;
+      mgd.DSYall = cv.take<float>((size_t)R * NP * ldL); mgd.DBYall = cv.take<float>((size_t)R * NP); mgd.INall = cv.take<float>((size_t)R * B * in_ld);
+    }
+  }
+  // sharded path: owner bounds of the gathered lists, device descriptor, counters, gathered input rows
+  char* shard_ws = nullptr; size_t shard_ws_bytes = 0;
+  if (shard) {
+    shard_ws_bytes = (size_t)2 * MG_CAP * R * sizeof(int) + 4096 + (size_t)B * md.layer[0].ld3 * sizeof(float) + 1024;
+    shard_ws = cv.take<char>(shard_ws_bytes);
   }
   // evaluation
   int* dRank = cv.take<int>((size_t)Be * 4); float* dTgt = cv.take<float>(Be);
@@ -246,6 +272,7 @@ static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
     h->dStepBase = dStepBase; h->dP = dP; h->dLogP0t = dL0t; h->dLogP0s = dL0s; h->dST = dST; h->dU = dU; h->dMrgState = dMrg;
     h->dRankCnt = dRank; h->dTgt = dTgt;
     h->npow2 = next_pow2(B + S);
+    h->shard_ws = shard_ws; h->shard_ws_bytes = shard_ws_bytes;
   }
 }
 
@@ -340,6 +367,19 @@ static cudaError_t fastc_launch(int grid, cudaStream_t st, void** args) {
   return cudaLaunchKernelExC(&lc, (const void*)k_fast_t<true>, args);
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per-function, process-global state: several handles (models of different shapes)
+// may be alive at once, so the limit of a kernel is only ever raised (a smaller request of a later handle must not lower it)
+static std::mutex g_smem_mutex;
+static std::map<const void*, int> g_smem_limit;
+static cudaError_t raise_smem_limit(const void* func, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_smem_mutex);
+  int& cur = g_smem_limit[func];
+  if ((int)bytes <= cur) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) cur = (int)bytes;
+  return e;
+}
+
 static int tiles2(int cols, int rows) { return ((cols + GB - 1) / GB) * ((rows + GB - 1) / GB); }
 
 // enqueue the kernels of one training step (window-relative index = *base + off when base != nullptr)
@@ -396,6 +436,7 @@ extern "C" int g4r_destroy(g4r_handle* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   eval_release(h);
+  shard_release(h);
   mg_release(h);
   if (h->graphU) cudaGraphExecDestroy(h->graphU);
   if (h->graph1) cudaGraphExecDestroy(h->graph1);
@@ -474,11 +515,12 @@ extern "C" int g4r_create(const g4r_config* cfg, void* device_workspace, size_t 
   ok &= cudaMallocHost(&h->hCost, (size_t)CAP * sizeof(float)) == cudaSuccess;
   if (!ok) return bail(G4R_ERR_CUDA, "pinned host allocation failed");
   // opt in to large dynamic shared memory where needed
-  cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)score_smem_bytes(h->md.Bld));
-  cudaFuncSetAttribute(k_lossgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lossgrad_smem_bytes(h->md.Bld, h->md.ldL));
-  cudaFuncSetAttribute(k_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)h->npow2 * 8 + 1024));
   h->pk_smem = std::max(std::max(score_smem_bytes(h->md.Bld), lossgrad_smem_bytes(h->md.Bld, h->md.ldL)), (size_t)2 * GK * (GB + 1) * sizeof(float));
-  cudaFuncSetAttribute(k_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->pk_smem);
+  if (raise_smem_limit((const void*)k_score, score_smem_bytes(h->md.Bld)) != cudaSuccess ||
+      raise_smem_limit((const void*)k_lossgrad, lossgrad_smem_bytes(h->md.Bld, h->md.ldL)) != cudaSuccess ||
+      raise_smem_limit((const void*)k_plan, (size_t)h->npow2 * 8 + 1024) != cudaSuccess ||
+      raise_smem_limit((const void*)k_persistent, h->pk_smem) != cudaSuccess)
+    return bail(G4R_ERR_INVALID, "this shape needs more shared memory per block than the device offers (batch_size / layer width / n_sample too large for the step scratch)");
   {
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_persistent, PK_THREADS, h->pk_smem);
@@ -487,7 +529,7 @@ extern "C" int g4r_create(const g4r_config* cfg, void* device_workspace, size_t 
   }
   {
     const ModelDev& m = h->md;
-    cudaFuncSetAttribute(k_fast_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastSmem));
+    raise_smem_limit((const void*)k_fast_t<false>, sizeof(FastSmem));
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fast_t<false>, FK_THREADS, sizeof(FastSmem));
     h->fast_ok = h->pk_blocks > 0 && per_sm >= 1 && m.mode == 0 && m.n_layers == 1 && m.ldL <= 128 && m.B <= FK_B && h->n_sm >= FK_G + 1 && m.NCH <= 160 &&
@@ -498,6 +540,11 @@ extern "C" int g4r_create(const g4r_config* cfg, void* device_workspace, size_t 
     cudaMallocHost(&h->hFlags, 4 * sizeof(int));
   }
   if (cfg->step_mode == 1 && h->pk_blocks == 0) return bail(G4R_ERR_INVALID, "persistent mode unavailable (cooperative launch / shared memory)");
+  if (h->md.shardR > 0) {
+    const int src = shard_create(h);
+    if (src) return bail(src, h->err);
+    h->fast_ok = false; h->fastc_ok = false;       // the single-GPU kernels never run on a sharded handle
+  }
   if (cudaStreamSynchronize(h->stream) != cudaSuccess) return bail(G4R_ERR_CUDA, "init sync failed");
   *out = h;
   return G4R_OK;
@@ -527,6 +574,7 @@ extern "C" int g4r_set_tensor(g4r_handle* h, const char* name, const float* host
   if (!t) FAIL(G4R_ERR_INVALID, std::string("unknown tensor ") + (name ? name : "(null)"));
   if (rows != t->rows || cols != t->cols) FAIL(G4R_ERR_INVALID, std::string("shape mismatch for ") + name);
   cudaSetDevice(h->cfg.device);
+  if (t->sharded) return shard_set_tensor(h, *t, host);
   CK(cudaMemcpy2DAsync(t->ptr, t->ld * sizeof(float), host, cols * sizeof(float), cols * sizeof(float), rows, cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return G4R_OK;
@@ -537,6 +585,7 @@ extern "C" int g4r_get_tensor(g4r_handle* h, const char* name, float* host, int6
   if (!t) FAIL(G4R_ERR_INVALID, std::string("unknown tensor ") + (name ? name : "(null)"));
   if (rows != t->rows || cols != t->cols) FAIL(G4R_ERR_INVALID, std::string("shape mismatch for ") + name);
   cudaSetDevice(h->cfg.device);
+  if (t->sharded) return shard_get_tensor(h, *t, host);
   CK(cudaMemcpy2DAsync(host, cols * sizeof(float), t->ptr, t->ld * sizeof(float), cols * sizeof(float), rows, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return G4R_OK;
@@ -672,6 +721,9 @@ static void mrg_host_init(g4r_handle* h) {
   int64_t r = n; if (r > 6) r = r / 6;
   h->n_streams = (int)std::min<int64_t>(r, 15360);
   for (int i = 0; i < 6; i++) h->mrg_rstate[i] = h->cfg.mrg_seed ? h->cfg.mrg_seed : 12345;
+  // multi-GPU: every rank draws its own negatives -- rank r takes the r-th block of substreams (the block a further
+  // uniform() call of the same generator would have taken: the base state advances by 2^134 per call)
+  for (int r = 0; r < (h->cfg.world_size > 1 ? h->cfg.rank : 0); r++) { int64_t nb[6]; mrg_ff(h->mrg_rstate, A1p134, A2p134, nb); memcpy(h->mrg_rstate, nb, sizeof(nb)); }
   std::vector<int32_t> st((size_t)h->n_streams * 6);
   int64_t cur[6]; memcpy(cur, h->mrg_rstate, sizeof(cur));
   for (int i = 0; i < h->n_streams; i++) {
@@ -852,6 +904,7 @@ static int upload_window(g4r_handle* h, int64_t n) {
   h->launches++;
   CK(cudaGetLastError());
   h->win_steps = (int)n;
+  if (h->shard) return mgs_plan_window(h, n);
   return G4R_OK;
 }
 
@@ -922,10 +975,12 @@ static int run_window(g4r_handle* h, int64_t n) {
 }
 
 #include "g4r_multi.cuh"
+#include "g4r_shard.cuh"
 static bool mg_is_ready(g4r_handle* h) { return h->mg_host && static_cast<MgHost*>(h->mg_host)->ready; }
 
 extern "C" int g4r_upload_steps(g4r_handle* h, const g4r_schedule* s, int64_t first, int64_t n) {
   if (!h || !s) return G4R_ERR_INVALID;
+  if (h->shard && n > MG_CAP) FAIL(G4R_ERR_INVALID, "row-sharded handle: at most MG_CAP steps per uploaded window");
   if (s->B != h->md.B) FAIL(G4R_ERR_INVALID, "schedule batch size != model batch size");
   if (first < 0 || n <= 0 || first + n > s->n_steps) FAIL(G4R_ERR_INVALID, "step range out of schedule");
   if (n > h->CAP) FAIL(G4R_ERR_INVALID, "n exceeds the resident window capacity");
@@ -941,12 +996,16 @@ extern "C" int g4r_run_uploaded(g4r_handle* h, float* cost_out, float* device_ms
   if (h->win_steps <= 0) FAIL(G4R_ERR_STATE, "no uploaded window");
   cudaSetDevice(h->cfg.device);
   const int n = h->win_steps;
+  if (h->cfg.world_size > 1 && !mg_is_ready(h)) FAIL(G4R_ERR_STATE, "multi-GPU handle: call g4r_mg_init first");
+  if (h->cfg.world_size > 1 && !h->shard) FAIL(G4R_ERR_STATE, "g4r_run_uploaded on a multi-GPU handle needs the row-sharded path");
   CK(cudaEventRecord(h->ev0, h->stream));
-  int rc = run_window(h, n);
+  int rc = h->shard ? mgs_run_window(h, n) : run_window(h, n);
   if (rc) return rc;
   CK(cudaEventRecord(h->ev1, h->stream));
   if (cost_out) CK(cudaMemcpyAsync(h->hCost, h->md.cost, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  if (h->shard) CK(cudaMemcpyAsync(h->hFlags, h->md.nanflag, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  if (h->shard && h->hFlags[3]) FAIL(G4R_ERR_STATE, "multi-GPU: a cross-GPU wait timed out (a peer rank stopped or never started its window)");
   if (cost_out) memcpy(cost_out, h->hCost, (size_t)n * sizeof(float));
   if (device_ms) CK(cudaEventElapsedTime(device_ms, h->ev0, h->ev1));
   // re-running the same window is allowed for benchmarking: undo the pointer advance only on request (not here)
@@ -955,6 +1014,7 @@ extern "C" int g4r_run_uploaded(g4r_handle* h, float* cost_out, float* device_ms
 
 extern "C" int g4r_profile_uploaded(g4r_handle* h, float* phase_ms, int32_t* phase_launches, int32_t n_phases) {
   if (!h || !phase_ms || !phase_launches || n_phases < PH_COUNT) return G4R_ERR_INVALID;
+  if (h->shard) FAIL(G4R_ERR_STATE, "per-phase profiling is a single-GPU measurement (row-sharded handle)");
   if (h->win_steps <= 0) FAIL(G4R_ERR_STATE, "no uploaded window");
   cudaSetDevice(h->cfg.device);
   h->prof = true; h->prof_ev.clear(); h->prof_phase.clear();
@@ -1011,11 +1071,13 @@ extern "C" int g4r_train_steps(g4r_handle* h, const g4r_schedule* s, int64_t fir
     if (rc) return rc;
     if (multi) {
       if (!mg_is_ready(h)) FAIL(G4R_ERR_STATE, "multi-GPU handle: call g4r_mg_init first");
-      rc = mg_run_window(h, w);
+      rc = h->shard ? mgs_run_window(h, w) : mg_run_window(h, w);
     } else rc = run_window(h, w);
     if (rc) return rc;
     CK(cudaMemcpyAsync(h->hCost, h->md.cost, (size_t)w * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (h->shard) CK(cudaMemcpyAsync(h->hFlags, h->md.nanflag, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (h->shard && h->hFlags[3]) FAIL(G4R_ERR_STATE, "multi-GPU: a cross-GPU wait timed out (a peer rank stopped or never started its window)");
     for (int64_t i = 0; i < w; i++) {
       if (cost_out) cost_out[done + i] = h->hCost[i];
       if (h->hCost[i] != h->hCost[i]) {
@@ -1032,6 +1094,7 @@ extern "C" int g4r_train_step(g4r_handle* h, const int32_t* X, const int32_t* Y,
   if (!h || !X || !Y) return G4R_ERR_INVALID;
   const int B = h->md.B;
   if (M <= 0 || M > B) FAIL(G4R_ERR_INVALID, "M out of range");
+  if (h->shard) FAIL(G4R_ERR_STATE, "g4r_train_step: not available on a row-sharded multi-GPU handle (use g4r_train_steps)");
   cudaSetDevice(h->cfg.device);
   if (h->gen_len > 0 && (!h->have_store || h->sample_ptr >= h->gen_len)) {
     int rc = g4r_generate_samples(h);

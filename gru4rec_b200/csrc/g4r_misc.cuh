@@ -86,7 +86,10 @@ __global__ void __launch_bounds__(256) k_plan(ModelDev md, int* xnext, uint8_t* 
     if (i < M) item = Yp[i]; else if (i < N) item = smp[i - M];
     if (item >= 0) {
       if (item >= md.n_items) { atomicExch(md.nanflag + 1, 1); item = md.n_items - 1; }
-      key = ((unsigned long long)(unsigned)item << 32) | (unsigned)i;
+      // row-sharded tables: owner-major order (owner = item % R), so that every owner's columns are contiguous in the
+      // sorted list of every rank and the lists can be merged per owner (g4r_shard.cuh)
+      const unsigned hi = md.shardR > 0 ? (unsigned)(item % md.shardR) * (unsigned)md.n_items + (unsigned)item : (unsigned)item;
+      key = ((unsigned long long)hi << 32) | (unsigned)i;
     }
     keys[i] = key;
   }
@@ -108,14 +111,18 @@ __global__ void __launch_bounds__(256) k_plan(ModelDev md, int* xnext, uint8_t* 
   int* pPos = md.pPos + (size_t)s * md.NP;
   for (int j = tid; j < N; j += blockDim.x) {
     const unsigned long long key = keys[j];
-    const int item = (int)(key >> 32), pos = (int)(key & 0xffffffffu);
+    const int hi = (int)(key >> 32), pos = (int)(key & 0xffffffffu);
+    const int item = md.shardR > 0 ? hi % md.n_items : hi;
     pItem[j] = item; pPos[j] = pos;
+    if (md.shardR > 0) md.pKey[(size_t)s * md.NP + j] = hi;
     if (pos < M) md.pTcol[(size_t)s * B + pos] = j;
   }
   for (int c = tid; c <= md.NCH; c += blockDim.x) {
     int j = (int)(((long long)c * N + md.NCH - 1) / md.NCH);
     if (c == md.NCH) j = N;
-    while (j > 0 && j < N && (keys[j] >> 32) == (keys[j - 1] >> 32)) j++;
+    // single GPU: a chunk never splits a duplicate group (its CTA owns the item's row update).  Sharded: the rows are updated by
+    // their owner from the merged plan, so the chunks are plain equal splits.
+    if (md.shardR == 0) while (j > 0 && j < N && (keys[j] >> 32) == (keys[j - 1] >> 32)) j++;
     md.pCbeg[(size_t)s * (md.NCH + 1) + c] = min(j, N);
   }
   __syncthreads();
@@ -129,7 +136,7 @@ __global__ void __launch_bounds__(256) k_plan(ModelDev md, int* xnext, uint8_t* 
     uint8_t f = 1; int nx = -1;
     for (int q = 0; q < b; q++) if (Xp[q] == x) { f = 0; break; }
     for (int q = b + 1; q < M; q++) if (Xp[q] == x) { nx = q; break; }
-    if (md.mode == 2) {   // does the item also occur among the score columns?
+    if (md.mode == 2 && md.shardR == 0) {   // does the item also occur among the score columns?
       int lo = 0, hi = N;
       while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)(keys[mid] >> 32) < x) lo = mid + 1; else hi = mid; }
       if (lo < N && (int)(keys[lo] >> 32) == x) f |= 2;

@@ -281,7 +281,7 @@ extern "C" int g4r_mg_init(g4r_handle* h, const char* id128) {
   NC(g_nccl.CommInitRank(&m.comm, R, id, rank));
   m.dev = h->mgdev;
   m.ready = true;
-  h->md.export_only = 1;
+  if (!h->shard) h->md.export_only = 1;      // replicated path: gradients only, merged update after the NCCL exchange
   CK(slot_upload(h->slot, h->md, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return G4R_OK;

@@ -35,6 +35,8 @@ def evaluate_gpu(gru, test_data, items=None, session_key='SessionId', item_key='
     finally:
         if items is not None:
             eng.set_eval_items(None)
+    # the scoring hidden state is shared with predict_next_batch (gru4rec.py:696-697 keeps separate buffers): force its reset
+    gru.predict = None
     recall = [float(r) / n for r in rec]
     mrrs = [float(m) / n for m in mrr]
     return recall, mrrs

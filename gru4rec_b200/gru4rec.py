@@ -214,7 +214,7 @@ class GRU4Rec:
             names.append('E')
         return names
 
-    def _make_config(self, sample_store, eval_lanes, training=True):
+    def _make_config(self, sample_store, eval_lanes, training=True, single=False):
         """`training=False`: an engine for the scoring path only (evaluate_gpu / predict_next_batch of a loaded model): the
         optimiser options are irrelevant there, so a model the reference trained with adam / rmsprop / adadelta, grad_cap or
         smoothing can still be scored; fit() with those options raises NotImplementedError."""
@@ -251,7 +251,7 @@ class GRU4Rec:
         cfg.dropout_seed = self.dropout_seed
         cfg.mrg_seed = 12345
         cfg.max_resident_steps = 0
-        cfg.world_size, cfg.rank = self._world()
+        cfg.world_size, cfg.rank = (1, 0) if single else self._world()
         cfg.eval_batch_size = eval_lanes
         cfg.step_mode = self.step_mode
         if self.step_mode == 2 and len(self.layers) == 1 and 120 < self.layers[0] <= 128 and not self.constrained_embedding and not self.embedding and self.batch_size <= 32:
@@ -269,17 +269,18 @@ class GRU4Rec:
             pass
         return 1, 0
 
-    def _build_engine(self, sample_store=0, eval_lanes=None, training=True):
+    def _build_engine(self, sample_store=0, eval_lanes=None, training=True, single=False):
+        """`single`: a one-GPU engine even under torchrun (the scoring path of every rank works on a full replica)."""
         eval_lanes = self.eval_lanes if eval_lanes is None else eval_lanes
         host = self._host if self._host is not None else self._pull_host()
         if self._engine is not None:
             self._engine.close()
             self._engine = None
-        world, rank = self._world()
-        if world > 1:
+        world, rank = (1, 0) if single else self._world()
+        if self._world()[0] > 1:
             import torch
             self.device = torch.cuda.current_device()
-        eng = _lib.Engine(self._make_config(sample_store, eval_lanes, training), device=self.device)
+        eng = _lib.Engine(self._make_config(sample_store, eval_lanes, training, single=single), device=self.device)
         for name in self._param_names():
             eng.set(name, host[name])
         if world > 1:
@@ -319,8 +320,10 @@ class GRU4Rec:
         return {name: self._get_param(name) for name in self._param_names()}
 
     def _ensure_engine(self, eval_lanes):
-        if self._engine is None or self._engine_eval_lanes < eval_lanes:
-            self._build_engine(sample_store=0, eval_lanes=max(eval_lanes, self.eval_lanes), training=False)
+        """Engine for the scoring path (evaluate_gpu / predict_next_batch).  After a multi-GPU fit() the training engine holds
+        1/world of the item tables: the parameters are assembled on the host and every rank scores on its own full replica."""
+        if self._engine is None or self._engine_eval_lanes < eval_lanes or int(self._engine.cfg.world_size) > 1:
+            self._build_engine(sample_store=0, eval_lanes=max(eval_lanes, self.eval_lanes), training=False, single=True)
         return self._engine
 
     def generate_neg_samples(self, pop, length):
@@ -379,7 +382,14 @@ class GRU4Rec:
             else:
                 # the reference's device path has no per-step sampler: its loop dereferences an undefined sample pointer here
                 raise NotImplementedError('n_sample > 0 needs a sample store when store_type is \'gpu\' (sample_store >= 2 * n_sample)')
-        eng = self._build_engine(sample_store=(sample_store if use_store else (2 * self.n_sample if per_step_sampling else 0)))
+        world, rank = self._world()
+        if world > 1 and store_type == 'cpu':
+            # the host-side sampler draws from one NumPy stream and refills at rank-local step counts: the lock-step ranks
+            # would diverge (different numbers of collectives) -- only the device store is defined for multi-GPU training
+            raise NotImplementedError("store_type='cpu' is not available for multi-GPU training; use the device sample store")
+        # the training engine carries no scoring lanes: the step scratch keeps the leading dimension of the mini-batch
+        # (the scoring engine with `eval_lanes` lanes is created on the first evaluate_gpu / predict_next_batch call)
+        eng = self._build_engine(sample_store=(sample_store if use_store else (2 * self.n_sample if per_step_sampling else 0)), eval_lanes=0)
         if P0 is not None:
             eng.set_logq_support(P0)
         if use_store:
@@ -391,7 +401,7 @@ class GRU4Rec:
                 eng.set_sample_store(self.generate_neg_samples(pop, generate_length))
         base_order = np.argsort(data.groupby(self.session_key)[self.time_key].min().values) if self.time_sort else np.arange(len(offset_sessions) - 1)
         data_items = data.ItemIdx.values
-        world, rank = self._world()       # under torchrun: synchronous data parallelism, every rank trains a shard of the sessions
+        # under torchrun: synchronous data parallelism, every rank trains a shard of the sessions
         sched = None
         n_sample_eff = self.n_sample if use_store else (self.n_sample if store_type == 'cpu' else self.n_sample)
         for epoch in range(self.n_epochs):

@@ -18,3 +18,40 @@ def common_steps(n_steps, dist):
     t = torch.tensor([int(n_steps)], dtype=torch.int64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     return int(t.item())
+
+
+# ---- row-sharded item tables (csrc/g4r_shard.cuh): host restatement of the ownership map and of the merged owner plan ----
+def owner_of(item, world):
+    """rank that holds row `item` of Wy / By / Wx0 (and of their optimizer state)"""
+    return int(item) % int(world)
+
+
+def local_row(item, world):
+    """row index inside the owner's shard"""
+    return int(item) // int(world)
+
+
+def shard_rows(n_items, world, rank):
+    """number of rows rank `rank` owns"""
+    return (int(n_items) - int(rank) + int(world) - 1) // int(world)
+
+
+def sort_columns_owner_major(items, n_items, world):
+    """order in which a rank processes the score columns of one mini-batch in the sharded layout: by (owner, item, position);
+    returns (keys, positions) with key = owner * n_items + item (what k_plan writes to pKey)"""
+    items = np.asarray(items, dtype=np.int64)
+    keys = (items % world) * n_items + items
+    order = np.lexsort((np.arange(len(items)), keys))
+    return keys[order], order
+
+
+def merged_owner_plan(keys_per_rank, n_items, world, me):
+    """entries (rank, sorted column index) of all ranks whose item is owned by `me`, in (item, rank, position) order -- the
+    list k_mgs_plan builds on the device and the apply CTAs walk; the gradient row of entry (r, j) is slot [r][j] of the inbox"""
+    ent = []
+    for r, keys in enumerate(keys_per_rank):
+        keys = np.asarray(keys)
+        lo, hi = np.searchsorted(keys, me * n_items, 'left'), np.searchsorted(keys, (me + 1) * n_items, 'left')
+        ent += [(int(keys[j]) - me * n_items, r, j) for j in range(lo, hi)]
+    ent.sort()
+    return ent

@@ -67,7 +67,7 @@ typedef struct g4r_config {
                                      2: role-specialised persistent kernel where the shape allows, else 1;
                                      3: as 2, launched as thread-block clusters: the GRU phases run on one cluster with the
                                         dense weights and optimizer state resident in shared memory (else 1) */
-  int32_t reserved[7];
+  int32_t reserved[7];            /* reserved[0] = 1: multi-GPU with replicated tables + NCCL exchange instead of row sharding */
 } g4r_config;
 
 typedef struct g4r_handle g4r_handle;
@@ -160,6 +160,24 @@ int64_t g4r_kernel_launches(const g4r_handle* h);
  * g4r_mg_init.  All ranks must call g4r_train_steps with the same number of steps. */
 int g4r_mg_unique_id(char* out128);
 int g4r_mg_init(g4r_handle* h, const char* id128);
+/* Row-sharded layout (the default for world_size > 1 when the role-specialised kernel covers the shape: no-embedding mode, one
+ * layer of <= 120 units, batch <= 32; cfg.reserved[0] = 1 forces the replicated NCCL path above).  Row i of Wy / By / Wx0 and
+ * of their optimizer state lives only on rank i % world_size (local row i / world_size) in a library-owned segment that the
+ * peers map with cudaIpc; parameter rows are fetched from their owners and gradient rows are stored into the owners' inboxes
+ * over NVLink INSIDE the persistent kernel, the owners apply the merged update to their 1/world_size of the rows, and the
+ * dense GRU gradients are pushed to all peers and summed in rank order.  NCCL only carries the per-window all-gather of the
+ * sorted column lists.  Call order: g4r_create -> g4r_mg_init -> g4r_mg_ipc_handle (all-gather the 64-byte handles in rank
+ * order) -> g4r_mg_ipc_open.  g4r_set_tensor / g4r_get_tensor keep the single-GPU shapes ("Wy" is n_items x L): set scatters
+ * the caller's full matrix to this rank's rows, get assembles the full matrix from all shards (all ranks idle).
+ * There is no reference counterpart (the reference is single-device, .theanorc_gru4rec:3); SURVEY section 8e is the spec. */
+int g4r_mg_sharded(const g4r_handle* h);                               /* 1 if the handle uses the row-sharded layout */
+int g4r_mg_ipc_handle(g4r_handle* h, char* out64);                    /* cudaIpcMemHandle_t of this rank's segment */
+int g4r_mg_ipc_open(g4r_handle* h, const char* handles, int32_t world);   /* world x 64 bytes, rank order */
+/* Ownership arithmetic and buffer sizing of the sharded layout (pure host functions, usable without a device). */
+int g4r_mg_owner(int64_t item, int32_t world);
+int64_t g4r_mg_local_row(int64_t item, int32_t world);
+int64_t g4r_mg_shard_rows(int64_t n_items, int32_t world, int32_t rank);
+int g4r_mg_segment_bytes(const g4r_config* cfg, size_t* total, size_t* inbox_bytes, size_t* inbox_in_bytes, size_t* dense_bytes);
 
 /* ---- scoring path: evaluate(X, Y, M) (evaluation.py:76,108) and predict (gru4rec.py:706-710) ------- */
 /* Runs a whole evaluation schedule: full-catalogue scores, rank of the target, per-cutoff hit counts and

@@ -78,9 +78,12 @@ def oracle_multi_step(m, Hs, inputs):
     weights and its own hidden state, then ONE merged update -- row gradients of all ranks concatenated in
     (rank, position) order, dense gradients summed (the stated multi-GPU semantics, gru4rec_b200/csrc/g4r_multi.cuh)."""
     Cs, Gs, costs = [], [], []
+    base_seed = m.dropout_seed
     for r, inp in enumerate(inputs):
         M = len(inp['X'])
+        m.dropout_seed = (base_seed + r * 0x9E3779B1) & 0xffffffff      # independent dropout masks per rank (g4r_lib.cu layout())
         masks = m.make_masks(M)
+        m.dropout_seed = base_seed
         Hr = [h[inp['slots']] for h in Hs[r]]
         X = np.asarray(inp['X'], dtype=np.int64); Y = np.asarray(inp['Y'], dtype=np.int64)
         yhat, C = m.forward(X, Y, M, R=inp['R'], samples=inp.get('samples'), masks=masks, H=Hr)

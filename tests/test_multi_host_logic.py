@@ -48,6 +48,43 @@ def _worker(rank, world, port, q):
     w = [None] * world
     dist.all_gather_object(w, m.Wy.tobytes())
     assert all(x == w[0] for x in w)
+    # ---- row-sharded layout: ownership map, shard sizes, inbox sizing, merged owner plan (host arithmetic of g4r_shard.cuh) ----
+    from gru4rec_b200.parallel import owner_of, local_row, shard_rows, sort_columns_owner_major, merged_owner_plan
+    lib = _lib.load()
+    I = 37483
+    rows = [None] * world
+    dist.all_gather_object(rows, int(lib.g4r_mg_shard_rows(I, world, rank)))
+    assert sum(rows) == I and rows[rank] == shard_rows(I, world, rank)
+    for item in (0, 1, 2, 3, I - 1, 12345):
+        assert lib.g4r_mg_owner(item, world) == owner_of(item, world)
+        assert lib.g4r_mg_local_row(item, world) == local_row(item, world) < rows[owner_of(item, world)]
+        assert owner_of(item, world) + world * local_row(item, world) == item
+    import ctypes as C
+    cfg = _lib.make_config(I, dict(layers=[100], batch_size=32, n_sample=2048, loss='bpr-max', final_act='elu-0.5', momentum=0.3),
+                           sample_store=10000000, step_mode=2, world_size=world, rank=rank)
+    tot, inbox, inbox_in, dense = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+    assert lib.g4r_mg_segment_bytes(C.byref(cfg), C.byref(tot), C.byref(inbox), C.byref(inbox_in), C.byref(dense)) == 0
+    NP, ldW, ld3 = 2080, 104, 300
+    assert inbox.value >= 2 * world * NP * ldW * 4          # double-buffered slot [rank][sorted column] per peer: dSy row | dby
+    assert inbox_in.value >= 2 * world * 32 * ld3 * 4       # input-row gradients [rank][lane]
+    assert dense.value >= 2 * world * 48 * 4 * (3 * 300 + 7)
+    assert tot.value >= 3 * rows[rank] * (ldW + ld3) * 4    # parameter + Adagrad + momentum shards of both tables
+    # merged owner plan: every (rank, column) of every rank lands in exactly one owner's list, duplicates in (rank, position) order
+    rs2 = np.random.RandomState(100 + rank)
+    cols = rs2.randint(0, 50, size=40)
+    keys, order = sort_columns_owner_major(cols, 50, world)
+    allk = [None] * world
+    dist.all_gather_object(allk, keys.tolist())
+    plan = merged_owner_plan(allk, 50, world, rank)
+    counts = [None] * world
+    dist.all_gather_object(counts, len(plan))
+    assert sum(counts) == 40 * world                          # expected arrivals over all owners == columns scored by all ranks
+    assert all(owner_of(it, world) == rank for it, _, _ in plan)
+    assert plan == sorted(plan)
+    seen = [None] * world
+    dist.all_gather_object(seen, [(r, j) for _, r, j in plan])
+    flat2 = [x for lst in seen for x in lst]
+    assert len(set(flat2)) == len(flat2) == 40 * world
     q.put((rank, 'ok'))
     dist.destroy_process_group()
 

@@ -321,6 +321,8 @@ def main():
             t = torch.tensor([dev_ms], device='cuda'); dist.all_reduce(t, op=dist.ReduceOp.MAX); dev_ms = float(t.item())
         value = world * K / (dev_ms / 1000.0)
         # ---- end-to-end arm: host schedule arrays in, costs out, every window (H2D + plans + steps + D2H inside the timing)
+        if dist is not None:
+            eng.train_steps(sched, first + K, 4)     # first use of this entry point (its step-count agreement is a fresh NCCL collective)
         barrier()
         clocks.timed = True
         t0 = time.time()

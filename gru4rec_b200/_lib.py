@@ -11,7 +11,7 @@ G4R_MAX_LAYERS = 8
 G4R_OK, G4R_ERR_INVALID, G4R_ERR_INDEX, G4R_ERR_CUDA, G4R_ERR_NAN, G4R_ERR_STATE = 0, -1, -2, -3, -4, -5
 LOSS = {'cross-entropy': 0, 'bpr-max': 1, 'top1-max': 2, 'bpr': 3, 'top1': 4, 'xe_logit': 5}
 ACT = {'linear': 0, 'relu': 1, 'tanh': 2, 'leaky': 3, 'elu': 4, 'selu': 5, 'softmax': 6, 'softmax_logit': 7}
-ADAPT = {None: 0, 'adagrad': 1}
+ADAPT = {None: 0, 'adagrad': 1, 'rmsprop': 2, 'adadelta': 3, 'adam': 4}
 
 
 class G4RConfig(C.Structure):
@@ -26,7 +26,8 @@ class G4RConfig(C.Structure):
         ('smoothing', C.c_float), ('bpreg', C.c_float), ('logq', C.c_float),
         ('adapt', C.c_int32), ('sample_store', C.c_int32), ('dropout_seed', C.c_uint32), ('mrg_seed', C.c_uint32),
         ('max_resident_steps', C.c_int32), ('device', C.c_int32), ('world_size', C.c_int32), ('rank', C.c_int32),
-        ('eval_batch_size', C.c_int32), ('step_mode', C.c_int32), ('reserved', C.c_int32 * 7),
+        ('eval_batch_size', C.c_int32), ('step_mode', C.c_int32), ('mg_replicated', C.c_int32), ('eval_tc', C.c_int32),
+        ('adapt_p1', C.c_float), ('adapt_p1c', C.c_float), ('adapt_p2', C.c_float), ('adapt_p2c', C.c_float), ('grad_cap', C.c_float),
     ]
 
 
@@ -134,6 +135,18 @@ def parse_act(name):
     raise NotImplementedError
 
 
+def set_adapt_params(cfg, adapt, adapt_params, grad_cap):
+    """adapt_params as the reference uses them (gru4rec.py:301-304,342-343,368-369); the complements are taken in double like there"""
+    ap = [float(x) for x in (adapt_params or [])]
+    if adapt in ('rmsprop', 'adadelta') and len(ap) < 1 or adapt == 'adam' and len(ap) < 2:
+        raise IndexError('list index out of range')          # what the reference raises when adapt_params is too short
+    cfg.adapt_p1 = ap[0] if len(ap) > 0 else 0.0
+    cfg.adapt_p1c = (1.0 - ap[0]) if len(ap) > 0 else 0.0
+    cfg.adapt_p2 = ap[1] if len(ap) > 1 else 0.0
+    cfg.adapt_p2c = (1.0 - ap[1]) if len(ap) > 1 else 0.0
+    cfg.grad_cap = float(grad_cap or 0.0)
+
+
 def make_config(n_items, mk, sample_store=0, eval_lanes=0, max_resident_steps=0, step_mode=0, world_size=1, rank=0, replicated=False, eval_tc=None):
     cfg = G4RConfig()
     layers = mk.get('layers', [100])
@@ -165,8 +178,9 @@ def make_config(n_items, mk, sample_store=0, eval_lanes=0, max_resident_steps=0,
     cfg.world_size, cfg.rank = world_size, rank
     cfg.eval_batch_size = eval_lanes
     cfg.step_mode = step_mode
-    cfg.reserved[0] = 1 if replicated else 0      # multi-GPU: replicated tables + NCCL exchange instead of row sharding
-    cfg.reserved[1] = 0 if eval_tc is None else (2 if eval_tc else 1)   # scoring path: auto / force tcgen05 tiles / force fp32 FFMA tiles
+    cfg.mg_replicated = 1 if replicated else 0     # multi-GPU: replicated tables + NCCL exchange instead of row sharding
+    cfg.eval_tc = 0 if eval_tc is None else (2 if eval_tc else 1)   # scoring path: auto / force tcgen05 tiles / force fp32 FFMA tiles
+    set_adapt_params(cfg, mk.get('adapt', 'adagrad'), mk.get('adapt_params', []), mk.get('grad_cap', 0.0))
     return cfg
 
 

@@ -11,8 +11,17 @@ constexpr int EV_KT = 128;    // feature slab
 constexpr int EV_LDS = EV_KT + 4;
 constexpr int EV_THREADS = 256;
 
+// mode 'tiebreaking' (evaluation.py:55,65): yhat += U(0,1) * 1e-10 before the standard ranking.  The reference draws the noise
+// from Theano's MRG stream (not reproducible offline); here it is a counter hash of (evaluation step, lane, score column), so
+// the target's own column carries the same noise in the target score and in the tile and never beats itself.
+__device__ __forceinline__ float tie_noise(unsigned int seed, int s, int b, unsigned int col) {
+  unsigned int k = mix32(seed ^ (0x9E3779B9U * (unsigned int)(s + 1)));
+  k = mix32(k + (unsigned int)b * 0x85EBCA6BU);
+  return (float)(mix32(k + col) >> 8) * (1.0f / 16777216.0f) * 1e-10f;
+}
+
 // target score of every lane, computed with the same sequential k order as the tile kernel (bitwise equal)
-__global__ void __launch_bounds__(128) k_eval_tgt(int slot, int s, float* tgt, int* cnt) {
+__global__ void __launch_bounds__(128) k_eval_tgt(int slot, int s, float* tgt, int* cnt, unsigned int tie, int subset_mode) {
   const ModelDev& md = MD;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   const int M = md.wM[s];
@@ -27,6 +36,7 @@ __global__ void __launch_bounds__(128) k_eval_tgt(int slot, int s, float* tgt, i
   }
   float sc = a + md.By[item];
   if (md.fact.kind <= G4R_ACT_SELU) sc = act_fwd(md.fact, sc);
+  if (tie) sc += tie_noise(tie, s, b, subset_mode ? 0x40000000U + (unsigned int)b : (unsigned int)item);
   tgt[b] = sc;
   cnt[b * 2 + 0] = 0; cnt[b * 2 + 1] = 0;
 }
@@ -34,7 +44,7 @@ __global__ void __launch_bounds__(128) k_eval_tgt(int slot, int s, float* tgt, i
 // `subset` (evaluate_gpu(items=...), evaluation.py:52-56): the competitors are the n_cand listed items instead of the catalogue
 template <bool WRITE>
 __global__ void __launch_bounds__(EV_THREADS) k_eval_score(int slot, int s, const float* __restrict__ tgt, int* cnt, float* out,
-                                                           const int* __restrict__ subset, int n_cand) {
+                                                           const int* __restrict__ subset, int n_cand, unsigned int tie = 0u) {
   const ModelDev& md = MD;
   extern __shared__ __align__(16) float smem[];
   float* sY = smem;                        // [EV_TB][EV_LDS]
@@ -102,6 +112,7 @@ __global__ void __launch_bounds__(EV_THREADS) k_eval_score(int slot, int s, cons
           if (WRITE) out[(size_t)b * I + it] = sc;
           else {
             if (md.fact.kind <= G4R_ACT_SELU) sc = act_fwd(md.fact, sc);
+            if (tie) sc += tie_noise(tie, s, b, (unsigned int)it);
             gt += sc > t; eq += sc == t;
           }
         }
@@ -118,18 +129,31 @@ __global__ void __launch_bounds__(EV_THREADS) k_eval_score(int slot, int s, cons
 static size_t eval_smem_bytes() { return (size_t)(EV_TB * EV_LDS + EV_IT * EV_LDS) * sizeof(float) + EV_TB * 2 * sizeof(int) + 64; }
 
 // ranks + per-cutoff sums (evaluation.py:60-75), accumulated in double on the device
-__global__ void k_eval_rank(int slot, int s, const int* cnt, const int* cut, int n_cut, int mode, double* sums) {
+__global__ void __launch_bounds__(256) k_eval_rank(int slot, int s, const int* cnt, const int* cut, int n_cut, int mode, double* sums) {
   const ModelDev& md = MD;
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (blockIdx.x != 0) return;
   const int M = md.wM[s];
-  for (int b = 0; b < M; b++) {
-    const int gt = cnt[b * 2], eq = cnt[b * 2 + 1];
-    double rank;
-    if (mode == 1) rank = (double)(gt + eq);
-    else if (mode == 2) rank = (double)gt + 0.5 * (double)(eq - 1) + 1.0;
-    else rank = (double)(gt + 1);
-    for (int j = 0; j < n_cut; j++) {
-      if (rank <= (double)cut[j]) { sums[j] += 1.0; sums[n_cut + j] += 1.0 / rank; }
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ double red[8][2];
+  // one cut-off at a time: lanes strided over the threads, double sums reduced in a fixed order (deterministic)
+  for (int j = 0; j < n_cut; j++) {
+    double hit = 0.0, rr = 0.0;
+    for (int b = tid; b < M; b += blockDim.x) {
+      const int gt = cnt[b * 2], eq = cnt[b * 2 + 1];
+      double rank;
+      if (mode == 1) rank = (double)(gt + eq);
+      else if (mode == 2) rank = (double)gt + 0.5 * (double)(eq - 1) + 1.0;
+      else rank = (double)(gt + 1);
+      if (rank <= (double)cut[j]) { hit += 1.0; rr += 1.0 / rank; }
+    }
+    for (int o = 16; o > 0; o >>= 1) { hit += __shfl_xor_sync(0xffffffffu, hit, o); rr += __shfl_xor_sync(0xffffffffu, rr, o); }
+    __syncthreads();
+    if (lane == 0) { red[warp][0] = hit; red[warp][1] = rr; }
+    __syncthreads();
+    if (tid == 0) {
+      double h = 0.0, r = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) { h += red[w][0]; r += red[w][1]; }
+      sums[j] += h; sums[n_cut + j] += r;
     }
   }
 }
@@ -173,6 +197,7 @@ struct EvalCtx {
   int cap = 0;
   int slot = -1;
   int* dCand = nullptr; int n_cand = 0; size_t cand_cap = 0;     // candidate subset of evaluate_gpu(items=...), item indices
+  unsigned char *dAsplit = nullptr, *dBsplit = nullptr;           // tcgen05 path: hi / lo TF32 operand blocks (g4r_eval_tc.cuh)
 };
 
 static void eval_release(g4r_handle* h) {
@@ -181,6 +206,7 @@ static void eval_release(g4r_handle* h) {
   cudaFreeHost(e.hX); cudaFreeHost(e.hY); cudaFreeHost(e.hSlot); cudaFreeHost(e.hF); cudaFreeHost(e.hM); cudaFreeHost(e.hSti); cudaFreeHost(e.hG);
   cudaFree(e.dX); cudaFree(e.dY); cudaFree(e.dSlot); cudaFree(e.dF); cudaFree(e.dM); cudaFree(e.dSti); cudaFree(e.dG);
   cudaFree(e.dCut); cudaFree(e.dSums); if (e.dOut) cudaFree(e.dOut); if (e.dCand) cudaFree(e.dCand);
+  if (e.dAsplit) cudaFree(e.dAsplit); if (e.dBsplit) cudaFree(e.dBsplit);
   slot_free(e.slot);
   delete static_cast<EvalCtx*>(h->eval_ctx);
   h->eval_ctx = nullptr;
@@ -227,7 +253,8 @@ static int eval_forward(g4r_handle* h, EvalCtx* e, int s) {
 extern "C" int g4r_eval_schedule(g4r_handle* h, const g4r_schedule* s, const int32_t* cut_off, int32_t n_cut, int32_t mode,
                                  double* recall_sum, double* mrr_sum, int64_t* n_events) {
   if (!h || !s || !cut_off || n_cut <= 0 || n_cut > 64 || !recall_sum || !mrr_sum) return G4R_ERR_INVALID;
-  if (mode < 0 || mode > 2) FAIL(G4R_ERR_INVALID, "eval mode must be 0 (standard), 1 (conservative) or 2 (median)");
+  if (mode < 0 || mode > 3) FAIL(G4R_ERR_INVALID, "eval mode must be 0 (standard), 1 (conservative), 2 (median) or 3 (tiebreaking)");
+  const unsigned int tie = mode == 3 ? 0x5bd1e995u : 0u;
   cudaSetDevice(h->cfg.device);
   EvalCtx* e = nullptr;
   int rc = eval_ctx(h, &e);
@@ -238,6 +265,16 @@ extern "C" int g4r_eval_schedule(g4r_handle* h, const g4r_schedule* s, const int
   for (int i = 0; i < h->md.n_layers; i++) CK(cudaMemsetAsync(h->He[i], 0, (size_t)Be * h->md.layer[i].ldL * sizeof(float), st));   // gru4rec.py:731-733
   CK(cudaMemcpyAsync(e->dCut, cut_off, n_cut * sizeof(int), cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(e->dSums, 0, 128 * sizeof(double), st));
+  // tensor-core scoring (full-catalogue ranking of a wide batch): the item table is split once per evaluation into hi / lo
+  // TF32 operand blocks; cfg.eval_tc: 1 forces the fp32 FFMA tiles, 2 forces tcgen05
+  const int tc_chunks = (h->md.L + TC_KC - 1) / TC_KC, tc_tiles = (I + TC_M - 1) / TC_M, tc_halves = (Be + TC_N - 1) / TC_N;
+  const bool tc_possible = e->n_cand == 0 && mode != 3 && h->cfg.eval_tc != 1 && (h->cfg.eval_tc == 2 || (Bs >= 64 && I >= 2048));
+  if (tc_possible) {
+    if (!e->dAsplit) CK(cudaMalloc(&e->dAsplit, (size_t)tc_tiles * tc_chunks * 2 * TC_A_BYTES));
+    if (!e->dBsplit) CK(cudaMalloc(&e->dBsplit, (size_t)tc_halves * tc_chunks * 2 * TC_B_BYTES));
+    k_tc_split<TC_M><<<dim3(tc_tiles, tc_chunks), 256, 0, st>>>(h->md.Wy, I, h->md.ldL, h->md.L, e->dAsplit, tc_chunks);
+    h->launches++;
+  }
   int64_t done = 0;
   while (done < s->n_steps) {
     const int64_t w = std::min<int64_t>(e->cap, s->n_steps - done);
@@ -266,15 +303,16 @@ extern "C" int g4r_eval_schedule(g4r_handle* h, const g4r_schedule* s, const int
     CK(cudaMemcpyAsync(e->dG, e->hG, (size_t)w * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     for (int64_t i = 0; i < w; i++) {
       eval_forward(h, e, (int)i);
-      k_eval_tgt<<<(Be + 127) / 128, 128, 0, st>>>(e->slot, (int)i, h->dTgt, h->dRankCnt);
+      k_eval_tgt<<<(Be + 127) / 128, 128, 0, st>>>(e->slot, (int)i, h->dTgt, h->dRankCnt, tie, e->n_cand > 0 ? 1 : 0);
       const int n_comp = e->n_cand > 0 ? e->n_cand : I;
-      // full-catalogue ranking of a wide batch: the [items x lanes] score tiles go through the tensor cores (tcgen05, 3xTF32);
-      // small batches / candidate subsets stay on the fp32 FFMA tiles.  cfg.reserved[1]: 1 forces FFMA, 2 forces tcgen05.
       const int M_i = e->hM[i];
-      const bool tc = e->n_cand == 0 && h->cfg.reserved[1] != 1 && (h->cfg.reserved[1] == 2 || (M_i >= 64 && I >= 2048));
-      if (tc) k_eval_tc<<<std::min((I + TC_M - 1) / TC_M, h->n_sm), TC_THREADS, sizeof(TcSmem), st>>>(e->slot, (int)i, h->dTgt, h->dRankCnt);
-      else k_eval_score<false><<<(n_comp + EV_IT - 1) / EV_IT, EV_THREADS, eval_smem_bytes(), st>>>(e->slot, (int)i, h->dTgt, h->dRankCnt, nullptr, e->n_cand > 0 ? e->dCand : nullptr, e->n_cand);
-      k_eval_rank<<<1, 32, 0, st>>>(e->slot, (int)i, h->dRankCnt, e->dCut, n_cut, mode, e->dSums);
+      const bool tc = tc_possible && (h->cfg.eval_tc == 2 || M_i >= 64);
+      if (tc) {
+        k_tc_split<TC_N><<<dim3((M_i + TC_N - 1) / TC_N, tc_chunks), 256, 0, st>>>(h->md.layer[h->md.n_layers - 1].y, M_i, h->md.ldL, h->md.L, e->dBsplit, tc_chunks);
+        k_eval_tc<<<std::min(tc_tiles, h->n_sm), TC_THREADS, sizeof(TcSmem), st>>>(e->slot, (int)i, h->dTgt, h->dRankCnt, e->dAsplit, e->dBsplit);
+        h->launches++;
+      } else k_eval_score<false><<<(n_comp + EV_IT - 1) / EV_IT, EV_THREADS, eval_smem_bytes(), st>>>(e->slot, (int)i, h->dTgt, h->dRankCnt, nullptr, e->n_cand > 0 ? e->dCand : nullptr, e->n_cand, tie);
+      k_eval_rank<<<1, 256, 0, st>>>(e->slot, (int)i, h->dRankCnt, e->dCut, n_cut, mode, e->dSums);
       h->launches += 3;
     }
     CK(cudaGetLastError());

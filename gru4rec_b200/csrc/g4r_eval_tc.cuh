@@ -12,9 +12,11 @@
 // the one comparison that must be exact), so a rank can only move where two DIFFERENT items' scores differ by < 1e-6 relative.
 //
 // Structure (one CTA per SM, 256 threads, persistent over its item tiles):
-//   warps 4-7  producers: load a 32-wide K chunk of the item rows (A) and of the hidden states (B) with 16-byte loads,
-//              split into hi / lo, store in the canonical K-major no-swizzle UMMA layout (8 x 16-byte core matrices);
-//              one elected thread issues the 12 MMAs of the chunk and tcgen05.commit-s the stage back (2 stages, 96 KB each)
+//   pre-pass   k_tc_split writes the operands as hi / lo TF32 blocks in the canonical K-major no-swizzle UMMA layout (8 x 16-byte
+//              core matrices): the item table once per evaluation, the hidden states once per mini-batch
+//   warp 4     TMA producer (one thread): two bulk copies (cp.async.bulk -> mbarrier complete_tx) per 32-wide K chunk fill a
+//              96 KB stage [A hi | A lo | B hi | B lo]; two stages
+//   warp 5     MMA issuer (one thread): 12 tcgen05.mma per chunk, tcgen05.commit hands the stage back / publishes the accumulator
 //   warps 0-3  epilogue: wait for the accumulator (2 x 256 TMEM columns, double buffered), tcgen05.ld 32 columns at a time,
 //              bias + final activation + compare with the lane's target score, warp ballots -> per-lane counters
 // All waits are mbarrier try_wait loops with a time-out that sets an error flag (a wrong phase must not hang the box).
@@ -32,7 +34,7 @@ constexpr unsigned long long TC_TIMEOUT_NS = 2000000000ull;
 
 struct TcSmem {
   alignas(1024) unsigned char stage[TC_STAGES][TC_STAGE_BYTES];   // [A hi | A lo | B hi | B lo]
-  alignas(8) unsigned long long full_unused;
+  alignas(8) unsigned long long stage_full[TC_STAGES];    // operand blocks of the stage have landed (TMA complete_tx)
   unsigned long long stage_free[TC_STAGES];    // MMAs that read the stage have completed (tcgen05.commit)
   unsigned long long acc_full[2];              // all MMAs of the tile have completed (tcgen05.commit)
   unsigned long long acc_free[2];              // epilogue has drained the accumulator (128 arrivals)
@@ -77,55 +79,49 @@ __device__ __forceinline__ void tc_commit(unsigned long long* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(tc_smem_u32(bar)) : "memory");
 }
 
-// stage rows [r0, r0 + nrows) x k [k0, k0 + 32) of a row-major fp32 matrix as hi / lo TF32 in the core-matrix layout
-// rowptr(r) -> pointer to the row (nullptr: zeros); executed by the 128 producer threads (pt = 0..127)
-template <class FRow>
-__device__ __forceinline__ void tc_stage_operand(unsigned char* hi, unsigned char* lo, int nrows, int k0, int K, int pt, FRow rowptr) {
-  // item = (row, 16-byte chunk c of 8); thread mapping: rows fastest -> conflict-free 16-byte shared stores
-  const int total = nrows * 8;
-  for (int i0 = 0; i0 < total; i0 += 4 * 128) {
-    float4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int i = i0 + u * 128 + pt;
-      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i < total) {
-        const int r = i % nrows, c = i / nrows;
-        const float* rp = rowptr(r);
-        if (rp && k0 + c * 4 < K) v[u] = ld4(rp + k0 + c * 4);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int i = i0 + u * 128 + pt;
-      if (i < total) {
-        const int r = i % nrows, c = i / nrows;
-        const uint32_t off = (uint32_t)(((r >> 3) * 8 + c) * 128 + (r & 7) * 16);
-        uint4 h, l;
-        h.x = tc_tf32(v[u].x); h.y = tc_tf32(v[u].y); h.z = tc_tf32(v[u].z); h.w = tc_tf32(v[u].w);
-        l.x = tc_tf32(v[u].x - __uint_as_float(h.x)); l.y = tc_tf32(v[u].y - __uint_as_float(h.y));
-        l.z = tc_tf32(v[u].z - __uint_as_float(h.z)); l.w = tc_tf32(v[u].w - __uint_as_float(h.w));
-        *reinterpret_cast<uint4*>(hi + off) = h;
-        *reinterpret_cast<uint4*>(lo + off) = l;
-      }
-    }
+// Pre-split operand blocks in global memory (written once per evaluation for the item table, once per mini-batch for the hidden
+// states): block (rb, c) = rows [rb * RB, +RB) x k [32 c, +32) as [hi | lo], each in the K-major no-swizzle core-matrix layout
+// (8 rows x 16 bytes per core matrix, core (r / 8, k / 4) at ((r / 8) * 8 + k / 4) * 128 bytes).  The scoring kernel then feeds
+// the tensor cores with plain bulk copies (TMA) -- no register staging on the critical path.
+template <int RB>
+__global__ void __launch_bounds__(256) k_tc_split(const float* __restrict__ src, int nrows, int ld, int K, unsigned char* __restrict__ dst, int n_chunk) {
+  const int rb = blockIdx.x, c = blockIdx.y;
+  unsigned char* hi = dst + ((size_t)rb * n_chunk + c) * 2 * (RB * TC_KC * 4);
+  unsigned char* lo = hi + RB * TC_KC * 4;
+  const int k0 = c * TC_KC;
+  for (int i = threadIdx.x; i < RB * 8; i += blockDim.x) {
+    const int r = i % RB, cc = i / RB;            // rows fastest: consecutive threads write consecutive 16-byte pieces
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int row = rb * RB + r;
+    if (row < nrows && k0 + cc * 4 < K) v = ld4(src + (size_t)row * ld + k0 + cc * 4);
+    const uint32_t off = (uint32_t)(((r >> 3) * 8 + cc) * 128 + (r & 7) * 16);
+    uint4 h, l;
+    h.x = tc_tf32(v.x); h.y = tc_tf32(v.y); h.z = tc_tf32(v.z); h.w = tc_tf32(v.w);
+    l.x = tc_tf32(v.x - __uint_as_float(h.x)); l.y = tc_tf32(v.y - __uint_as_float(h.y));
+    l.z = tc_tf32(v.z - __uint_as_float(h.z)); l.w = tc_tf32(v.w - __uint_as_float(h.w));
+    *reinterpret_cast<uint4*>(hi + off) = h;
+    *reinterpret_cast<uint4*>(lo + off) = l;
   }
+}
+__device__ __forceinline__ void tc_bulk_copy(void* sdst, const void* gsrc, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(tc_smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(tc_smem_u32(bar)) : "memory");
 }
 
 // cnt[b*2 + 0] += #items with score > target score of lane b; cnt[b*2 + 1] += #items with score == target (the target itself
 // counts as one tie, exactly as in the fp32 kernel where its score equals the target score bit for bit)
-__global__ void __launch_bounds__(TC_THREADS, 1) k_eval_tc(int slot, int s, const float* __restrict__ tgt, int* cnt) {
+__global__ void __launch_bounds__(TC_THREADS, 1) k_eval_tc(int slot, int s, const float* __restrict__ tgt, int* cnt,
+                                                           const unsigned char* __restrict__ Asplit, const unsigned char* __restrict__ Bsplit) {
   extern __shared__ __align__(1024) unsigned char tc_raw[];
   TcSmem& sm = *reinterpret_cast<TcSmem*>(tc_raw);
   const ModelDev& md = MD;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int M = md.wM[s], I = md.n_items, ldL = md.ldL, K = md.L;
-  const float* __restrict__ Y = md.layer[md.n_layers - 1].y;
+  const int M = md.wM[s], I = md.n_items, K = md.L;
   const int n_tiles = (I + TC_M - 1) / TC_M;
   const int n_half = (M + TC_N - 1) / TC_N;
   const int n_chunk = (K + TC_KC - 1) / TC_KC;
   if (tid == 0) {
-    for (int i = 0; i < TC_STAGES; i++) tc_mbar_init(&sm.stage_free[i], 1);
+    for (int i = 0; i < TC_STAGES; i++) { tc_mbar_init(&sm.stage_free[i], 1); tc_mbar_init(&sm.stage_full[i], 1); }
     for (int i = 0; i < 2; i++) { tc_mbar_init(&sm.acc_full[i], 1); tc_mbar_init(&sm.acc_free[i], 128); }
     sm.err = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -141,49 +137,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_eval_tc(int slot, int s, cons
   const uint32_t tmem = sm.tmem_base;
   // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 256, M = 128
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-  if (warp >= 4) {
-    // ================= producers + MMA issue =================
-    const int pt = tid - 128;
-    unsigned int it = 0;          // chunk counter -> stage = it % 2, use = it / 2
-    unsigned int wi = 0;          // work item counter -> accumulator = wi % 2
-    bool ok = true;
-    for (int h = 0; h < n_half && ok; h++) {
-      const int b0 = h * TC_N;
-      for (int t = blockIdx.x; t < n_tiles && ok; t += gridDim.x, wi++) {
-        const int i0 = t * TC_M;
-        const uint32_t acc = wi & 1u;
-        for (int c = 0; c < n_chunk && ok; c++, it++) {
-          const uint32_t st = it & 1u, use = it >> 1;
-          if (use > 0) ok = tc_mbar_wait(&sm.stage_free[st], (use - 1) & 1u, &sm.err);    // the MMAs of the previous use are done
-          if (!ok) break;
-          unsigned char* base = sm.stage[st];
-          const int k0 = c * TC_KC;
-          tc_stage_operand(base, base + TC_A_BYTES, TC_M, k0, K, pt, [&](int r) -> const float* { return i0 + r < I ? md.Wy + (size_t)(i0 + r) * ldL : nullptr; });
-          tc_stage_operand(base + 2 * TC_A_BYTES, base + 2 * TC_A_BYTES + TC_B_BYTES, TC_N, k0, K, pt, [&](int r) -> const float* { return b0 + r < M ? Y + (size_t)(b0 + r) * ldL : nullptr; });
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (pt == 0) {
-            if (c == 0 && wi >= 2) ok = tc_mbar_wait(&sm.acc_free[acc], ((wi >> 1) - 1) & 1u, &sm.err);   // epilogue drained this accumulator
-            if (ok) {
-              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              const uint32_t a_hi = tc_smem_u32(base), a_lo = a_hi + TC_A_BYTES, b_hi = a_hi + 2 * TC_A_BYTES, b_lo = b_hi + TC_B_BYTES;
-              const uint32_t d = tmem + acc * TC_N;
-              const int ksteps = (min(TC_KC, K - k0) + 7) / 8;
-              for (int j = 0; j < ksteps; j++) {
-                const uint32_t o = (uint32_t)j * 256u;     // 8 floats along K = 2 core matrices
-                const uint32_t first = (c == 0 && j == 0) ? 0u : 1u;
-                tc_mma_tf32(d, tc_desc(a_lo + o), tc_desc(b_hi + o), idesc, first);
-                tc_mma_tf32(d, tc_desc(a_hi + o), tc_desc(b_lo + o), idesc, 1u);
-                tc_mma_tf32(d, tc_desc(a_hi + o), tc_desc(b_hi + o), idesc, 1u);
-              }
-              tc_commit(&sm.stage_free[st]);
-              if (c == n_chunk - 1) tc_commit(&sm.acc_full[acc]);
-            }
+  if (warp == 4) {
+    // ================= TMA producer (one thread): operand blocks -> shared memory stages =================
+    if (lane == 0) {
+      unsigned int it = 0;
+      for (int h = 0; h < n_half; h++)
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
+          for (int c = 0; c < n_chunk; c++, it++) {
+            const uint32_t st = it & 1u, use = it >> 1;
+            if (use > 0) tc_mbar_wait(&sm.stage_free[st], (use - 1) & 1u, &sm.err);     // the MMAs of the previous use are done
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(tc_smem_u32(&sm.stage_full[st])), "r"(TC_STAGE_BYTES) : "memory");
+            tc_bulk_copy(sm.stage[st], Asplit + ((size_t)t * n_chunk + c) * 2 * TC_A_BYTES, 2 * TC_A_BYTES, &sm.stage_full[st]);
+            tc_bulk_copy(sm.stage[st] + 2 * TC_A_BYTES, Bsplit + ((size_t)h * n_chunk + c) * 2 * TC_B_BYTES, 2 * TC_B_BYTES, &sm.stage_full[st]);
           }
-          // the other producer threads run ahead to the next chunk (bounded by the stage_free wait)
-        }
-      }
     }
+  } else if (warp == 5) {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      unsigned int it = 0, wi = 0;
+      for (int h = 0; h < n_half; h++)
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, wi++) {
+          const uint32_t acc = wi & 1u;
+          if (wi >= 2) tc_mbar_wait(&sm.acc_free[acc], ((wi >> 1) - 1) & 1u, &sm.err);   // epilogue drained this accumulator
+          for (int c = 0; c < n_chunk; c++, it++) {
+            const uint32_t st = it & 1u, use = it >> 1;
+            tc_mbar_wait(&sm.stage_full[st], use & 1u, &sm.err);                         // operand blocks have landed
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = tc_smem_u32(sm.stage[st]), a_lo = a_hi + TC_A_BYTES, b_hi = a_hi + 2 * TC_A_BYTES, b_lo = b_hi + TC_B_BYTES;
+            const uint32_t d = tmem + acc * TC_N;
+            const int ksteps = (min(TC_KC, K - c * TC_KC) + 7) / 8;
+            for (int j = 0; j < ksteps; j++) {
+              const uint32_t o = (uint32_t)j * 256u;     // 8 floats along K = 2 core matrices
+              tc_mma_tf32(d, tc_desc(a_lo + o), tc_desc(b_hi + o), idesc, (c == 0 && j == 0) ? 0u : 1u);
+              tc_mma_tf32(d, tc_desc(a_hi + o), tc_desc(b_lo + o), idesc, 1u);
+              tc_mma_tf32(d, tc_desc(a_hi + o), tc_desc(b_hi + o), idesc, 1u);
+            }
+            tc_commit(&sm.stage_free[st]);
+            if (c == n_chunk - 1) tc_commit(&sm.acc_full[acc]);
+          }
+        }
+    }
+  } else if (warp >= 6) {
+    // idle warps
   } else {
     // ================= epilogue: TMEM -> registers -> counters =================
     unsigned int wi = 0;

@@ -48,9 +48,11 @@ struct ShardDev {
   int NA, DSL;                         // CTAs that apply the owned rows; capacity (floats) of one GRU CTA's dense-gradient slice
   float* W[MGS_MAXR];                  // [rows_local x ldW] parameter shard of every rank (index = rank; own entry = local memory)
   float* Wx[MGS_MAXR];                 // [rows_local x ld3] input-side table shard (no-embedding mode)
-  float* inbox[MGS_MAXR];              // [2][R][NP][ldW] gradient rows (dSy | dby) written by rank r for the columns it scored
-  float* inboxIn[MGS_MAXR];            // [2][R][B][ld3]  gradient rows of the gathered input rows
-  float* denseIn[MGS_MAXR];            // [2][R][MGS_GRU_CTAS][DSL] dense-gradient slices
+  // exchange buffers: every float travels as an 8-byte (value, lock-step sequence) pair -- data and flag in one store
+  float* inbox[MGS_MAXR];              // [2][R][NP][ldW] pairs: gradient rows (dSy | dby) written by rank r for the columns it scored
+  float* inboxIn[MGS_MAXR];            // [2][R][B][ld3] pairs: gradient rows of the gathered input rows
+  float* denseIn[MGS_MAXR];            // [2][R][MGS_GRU_CTAS][DSL] pairs: dense-gradient slices
+  float* mgInLL[MGS_MAXR];             // [2][B][ld3] pairs: input rows of the next mini-batch, pushed by their owners
   unsigned int* flags[MGS_MAXR];       // [MGF_COUNT][MGS_FLAG_STRIDE] sequence flags, written by peers, polled locally
   float *W_acc, *W_vel, *Wx_acc, *Wx_vel;   // optimizer state of the owned rows (local)
   float* mgIn;                         // [B][ld3] input rows of the current mini-batch, gathered from their owners
@@ -94,6 +96,11 @@ struct ModelDev {
   int loss; ActSpec fact, hact;
   float p_drop_h, p_drop_e, lr, mom, lmbd, bpreg, logq, alpha;
   int adapt; int nn_top1;                   // nn_top1 = M + n_sample term handled at run time (uses S_cfg)
+  float ap1, ap1c, ap2, ap2c;               // adapt_params[0], 1 - [0], [1], 1 - [1] (rmsprop / adadelta / adam, gru4rec.py:300-381)
+  float grad_cap, smoothing;                // gru4rec.py:386-389, 226-228 / 232-234
+  const float* gscale;                      // grad_cap > 0: device scalar every gradient is multiplied with before its update (else nullptr)
+  float* gnorm2;                            // grad_cap > 0: sum of squares of all gradients of the step
+  float* stat2;                             // smoothing > 0: [NCH x B x 2] partial (sum -log(p + eps), sum p / (p + eps)) per chunk
   int S_cfg;
   int export_only;                          // multi-GPU: compute gradients only; the merged update is applied after the exchange
   uint32_t drop_seed;
@@ -282,8 +289,100 @@ __device__ __forceinline__ void stage_rows4(float* sdst, int sld, int nrows, int
     }
   }
 }
+// ------------------------------------------------------------------------------------------------
+// Adaptive scalers other than Adagrad (gru4rec.py:300-329 adam, 341-366 adadelta, 367-381 rmsprop) and the update that follows
+// (gru4rec.py:390-431), for ONE element of a parameter with n gradient contributions in position order (n = 1: dense).
+// Sparse ("sampled") parameters use the reference's duplicate-accurate forms: the decayed state receives the squared
+// gradients of ALL duplicates, every duplicate is scaled with that common state (and adam's sparse first moment accumulates
+// grad**2 -- sic, gru4rec.py:325); velocity: last duplicate wins; parameter: all duplicates accumulate.
+// States of an element: s0 = acc, s1 = upd (adadelta) | meang (adam), s2 = countt (adam).
+// ------------------------------------------------------------------------------------------------
+struct OptE { float p, s0, s1, s2, v; };
+__device__ __forceinline__ float grad_scale(const ModelDev& md) { return md.gscale ? *md.gscale : 1.0f; }
+template <bool SPARSE, class FG>
+__device__ __forceinline__ void opt_elem(const ModelDev& md, OptE& e, float p0l, int n, FG gk) {
+  const float gsc = grad_scale(md);
+  const int ad = md.adapt;
+  const bool mom = md.mom > 0.f;
+  float A = e.s0, sclr = 1.f, common = 0.f;
+  if (ad == G4R_ADAPT_RMSPROP || ad == G4R_ADAPT_ADADELTA) {
+    A = e.s0 * md.ap1;
+    for (int k = 0; k < n; k++) { const float g = gk(k) * gsc; A += md.ap1c * g * g; }
+    if (ad == G4R_ADAPT_ADADELTA) {
+      sclr = __fdiv_rn(e.s1 + G4R_EPS_ADA, A + G4R_EPS_ADA);
+      float U = e.s1 * md.ap1;
+      for (int k = 0; k < n; k++) { const float g = gk(k) * gsc; U += md.ap1c * sclr * g * g; }
+      e.s1 = U;
+      sclr = sqrtf(sclr);
+    } else sclr = __fdiv_rn(1.0f, sqrtf(A + G4R_EPS_ADA));
+    e.s0 = A;
+  } else if (ad == G4R_ADAPT_ADAM) {
+    A = e.s0 * md.ap2;
+    float Mg = e.s1 * md.ap1;
+    for (int k = 0; k < n; k++) { const float g = gk(k) * gsc; A += md.ap2c * g * g; Mg += md.ap1c * (SPARSE ? g * g : g); }
+    const float ct = e.s2 + 1.0f;
+    const float bias = 1.0f - powf(md.ap1, ct);
+    common = __fdiv_rn(__fdiv_rn(Mg, bias), sqrtf(__fdiv_rn(A, bias)) + G4R_EPS_ADA);
+    e.s0 = A; e.s1 = Mg; e.s2 = ct;
+  }
+  const float v0 = e.v, a0 = e.s0;
+  float ps = e.p, vl = e.v, al = e.s0;
+  for (int k = 0; k < n; k++) {
+    const float g = gk(k) * gsc;
+    float gs;
+    if (ad == G4R_ADAPT_ADAGRAD) { al = a0 + g * g; gs = __fdiv_rn(g, sqrtf(al + G4R_EPS_ADA)); }
+    else if (ad == G4R_ADAPT_RMSPROP) gs = g * sclr;
+    else if (ad == G4R_ADAPT_ADADELTA) gs = g * sclr;
+    else if (ad == G4R_ADAPT_ADAM) gs = common;
+    else gs = g;
+    if (SPARSE) {
+      const float d = md.lmbd > 0.f ? md.lr * (gs + md.lmbd * p0l) : md.lr * gs;
+      if (mom) { vl = md.mom * v0 - d; ps += vl; } else ps -= d;
+    } else {
+      if (mom) { vl = md.mom * v0 - md.lr * (gs + md.lmbd * e.p); ps = e.p + vl; }
+      else ps = e.p * (1.0f - md.lr * md.lmbd) - md.lr * gs;
+    }
+  }
+  if (ad == G4R_ADAPT_ADAGRAD) e.s0 = al;
+  e.p = ps; e.v = vl;
+}
+// number of adaptive state arrays per parameter (they sit one after the other, `stride` elements apart, behind `*.acc`)
+__host__ __device__ inline int opt_states(int adapt) { return adapt == G4R_ADAPT_ADAM ? 3 : (adapt == G4R_ADAPT_ADADELTA ? 2 : (adapt == G4R_ADAPT_NONE ? 0 : 1)); }
+// generic (any scaler) row update: one row of `ld` elements, n members, element-wise over the lanes of a warp / threads of a CTA
+template <class FG>
+__device__ __forceinline__ void opt_row_generic(const ModelDev& md, float* prow, float* arow, size_t ast, float* vrow, const float* p0row, int ld,
+                                                int n, int t0, int tstep, bool write_state, FG grow /* (member k, column c) -> gradient */) {
+  const int ns = opt_states(md.adapt);
+  for (int c = t0; c < ld; c += tstep) {
+    OptE e;
+    e.p = prow[c];
+    e.s0 = ns > 0 ? arow[c] : 0.f; e.s1 = ns > 1 ? arow[ast + c] : 0.f; e.s2 = ns > 2 ? arow[2 * ast + c] : 0.f;
+    e.v = vrow ? vrow[c] : 0.f;
+    opt_elem<true>(md, e, p0row ? p0row[c] : e.p, n, [&](int k) { return grow(k, c); });
+    prow[c] = e.p;
+    if (write_state) {
+      if (ns > 0) arow[c] = e.s0;
+      if (ns > 1) arow[ast + c] = e.s1;
+      if (ns > 2) arow[2 * ast + c] = e.s2;
+      if (vrow) vrow[c] = e.v;
+    }
+  }
+}
+
 // dense Adagrad(+momentum) on one element (gru4rec.py:330-340,390-406)
-__device__ __forceinline__ void dense_update(const ModelDev& md, float* p, float* acc, float* vel, float g) {
+__device__ __forceinline__ void dense_update(const ModelDev& md, float* p, float* acc, float* vel, float g, size_t ast = 0) {
+  if (md.adapt > G4R_ADAPT_ADAGRAD) {
+    const int ns = opt_states(md.adapt);
+    OptE e;
+    e.p = *p; e.s0 = acc[0]; e.s1 = ns > 1 ? acc[ast] : 0.f; e.s2 = ns > 2 ? acc[2 * ast] : 0.f; e.v = vel ? *vel : 0.f;
+    opt_elem<false>(md, e, e.p, 1, [&](int) { return g; });
+    *p = e.p; acc[0] = e.s0;
+    if (ns > 1) acc[ast] = e.s1;
+    if (ns > 2) acc[2 * ast] = e.s2;
+    if (vel) *vel = e.v;
+    return;
+  }
+  g *= grad_scale(md);
   float gs = g;
   if (md.adapt == G4R_ADAPT_ADAGRAD) {
     float a = *acc + g * g;
@@ -745,9 +844,92 @@ __device__ void phase_stats(const ModelDev& md, int s, int cta, int ncta, float*
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// label smoothing (cross-entropy losses): second statistics pass over the scores once the row maximum / normaliser are final
+//   S2a  per chunk and lane: sum_j l(j) (l = -log(p_j + eps) for softmax outputs, the log-softmax itself for xe_logit) and
+//        sum_j p_j / (p_j + eps)
+//   S2b  one CTA per lane merges the chunks in a fixed order and rewrites the lane's loss
+// ------------------------------------------------------------------------------------------------
+__device__ void phase_stats2a(const ModelDev& md, int s, int chunk) {
+  const int M = md.wM[s];
+  const int* cbeg = md.pCbeg + (size_t)s * (md.NCH + 1);
+  const int cb = cbeg[chunk], ce = cbeg[chunk + 1];
+  for (int b = threadIdx.x; b < M; b += blockDim.x) {
+    const float m = md.RS[(size_t)b * G4R_NSTAT], Z = md.RS[(size_t)b * G4R_NSTAT + 1];
+    float s1 = 0.f, f = 0.f;
+    for (int j = cb; j < ce; j++) {
+      const float o = md.O[(size_t)j * md.Bld + b];
+      if (md.loss == G4R_LOSS_XE) { const float p = __fdiv_rn(expf(o - m), Z); s1 += -logf(p + G4R_EPS_LOG); f += __fdiv_rn(p, p + G4R_EPS_LOG); }
+      else s1 += logf(Z) - (o - m);
+    }
+    md.stat2[((size_t)chunk * md.B + b) * 2] = s1;
+    md.stat2[((size_t)chunk * md.B + b) * 2 + 1] = f;
+  }
+}
+__device__ void phase_stats2b(const ModelDev& md, int s, int cta, int ncta, float* smem) {
+  const int M = md.wM[s];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  for (int b = cta; b < M; b += ncta) {
+    float s1 = 0.f, f = 0.f;
+    for (int c = tid; c < md.NCH; c += blockDim.x) { s1 += md.stat2[((size_t)c * md.B + b) * 2]; f += md.stat2[((size_t)c * md.B + b) * 2 + 1]; }
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); f += __shfl_xor_sync(0xffffffffu, f, o); }
+    __syncthreads();
+    if (lane == 0) { smem[warp * 2] = s1; smem[warp * 2 + 1] = f; }
+    __syncthreads();
+    if (tid == 0) {
+      s1 = 0.f; f = 0.f;
+      for (int w = 0; w < nwarp; w++) { s1 += smem[w * 2]; f += smem[w * 2 + 1]; }
+      float* rs = md.RS + (size_t)b * G4R_NSTAT;
+      const float n_out = (float)(M + md.S_cfg);
+      const float c1 = 1.0f - __fdiv_rn(n_out, n_out - 1.0f) * md.smoothing, c2 = __fdiv_rn(md.smoothing, n_out - 1.0f);
+      rs[3] = f;
+      if (md.loss == G4R_LOSS_XE) rs[6] = c1 * (-logf(rs[2] + G4R_EPS_LOG)) + c2 * s1;
+      else rs[6] = c1 * (logf(rs[1]) - (rs[5] - rs[0])) + c2 * s1;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// grad_cap (gru4rec.py:386-389): global L2 norm over the dense gradients and the per-position gradients of the gathered rows;
+// every gradient is scaled by cap / norm when norm >= cap.  One CTA, fixed summation order.
+// ------------------------------------------------------------------------------------------------
+__device__ void phase_gradnorm(const ModelDev& md, int s, const float* dense_flat, size_t dense_count, float* gscale, float* smem) {
+  const int M = md.wM[s];
+  const int N = M + (md.wSti[s] >= 0 ? md.S : 0);
+  float a = 0.f;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (size_t i = tid; i < (size_t)N * md.ldL; i += nt) { const float g = md.DSY[i]; a += g * g; }
+  for (int i = tid; i < N; i += nt) { const float g = md.DBY[i]; a += g * g; }
+  const float* G = md.mode == 0 ? md.layer[0].dvec : md.dSx;
+  const int ldg = md.mode == 0 ? md.layer[0].ld3 : md.ld_in0;
+  for (int i = tid; i < M * ldg; i += nt) { const float g = G[i]; a += g * g; }
+  for (size_t i = tid; i < dense_count; i += nt) { const float g = dense_flat[i]; a += g * g; }
+  a = warp_sum(a);
+  if ((tid & 31) == 0) smem[tid >> 5] = a;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (nt >> 5); w++) t += smem[w];
+    const float norm = sqrtf(t);
+    gscale[0] = norm >= md.grad_cap ? __fdiv_rn(md.grad_cap, norm) : 1.0f;
+  }
+}
+
 // dL/do for element (b, column j) given final row statistics (already divided by batch_size)
 __device__ __forceinline__ float loss_grad_elem(const ModelDev& md, const float* rs, float o, bool is_t, int M, int N) {
   const float invB = __fdiv_rn(1.0f, (float)md.B);
+  if (md.smoothing > 0.f && (md.loss == G4R_LOSS_XE || md.loss == G4R_LOSS_XE_LOGIT)) {
+    // label smoothing (gru4rec.py:226-228, 232-234): loss_i = c1 * l(target) + c2 * sum_j l(j), n_out = M + n_sample
+    const float n_out = (float)(M + md.S_cfg);
+    const float c1 = 1.0f - __fdiv_rn(n_out, n_out - 1.0f) * md.smoothing, c2 = __fdiv_rn(md.smoothing, n_out - 1.0f);
+    const float p = __fdiv_rn(expf(o - rs[0]), rs[1]);
+    if (md.loss == G4R_LOSS_XE) {
+      const float f = __fdiv_rn(p, p + G4R_EPS_LOG), ft = __fdiv_rn(rs[2], rs[2] + G4R_EPS_LOG);
+      return (-c2 * f - (is_t ? c1 * ft : 0.f) + p * (c2 * rs[3] + c1 * ft)) * invB;       // rs[3] = sum_j p_j / (p_j + eps)
+    }
+    return (-(c2 + (is_t ? c1 : 0.f)) + p * (c2 * (float)N + c1)) * invB;
+  }
   if (md.loss == G4R_LOSS_XE) {
     const float p = __fdiv_rn(expf(o - rs[0]), rs[1]);
     const float fac = __fdiv_rn(rs[2], rs[2] + G4R_EPS_LOG);
@@ -804,8 +986,13 @@ __device__ __forceinline__ float loss_grad_elem(const ModelDev& md, const float*
 // acc / velocity keep the LAST occurrence (set_subtensor), the parameter accumulates all (inc_subtensor).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void sparse_row_update(const ModelDev& md, float* __restrict__ prow, float* __restrict__ arow, float* __restrict__ vrow,
-                                                  const float* gsrc, int gstride, int n_members, int lane, int ld, bool ada, bool mom) {
+                                                  const float* gsrc, int gstride, int n_members, int lane, int ld, bool ada, bool mom, size_t ast = 0) {
   // one item, n_members duplicate positions (in position order): gsrc + k*gstride is the gradient row of member k
+  if (md.adapt > G4R_ADAPT_ADAGRAD) {
+    opt_row_generic(md, prow, arow, ast, vrow, nullptr, ld, n_members, lane, 32, true, [&](int k, int c) { return gsrc[(size_t)k * gstride + c]; });
+    return;
+  }
+  const float gsc = grad_scale(md);
   for (int c4 = lane; c4 < ld / 4; c4 += 32) {
     const float4 p0 = ld4(prow + c4 * 4);
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), v0 = a0, al = a0, vl = a0;
@@ -813,7 +1000,8 @@ __device__ __forceinline__ void sparse_row_update(const ModelDev& md, float* __r
     if (mom) v0 = ld4(vrow + c4 * 4);
     float4 ps = p0;
     for (int k = 0; k < n_members; k++) {
-      const float4 g = ld4(gsrc + (size_t)k * gstride + c4 * 4);
+      float4 g = ld4(gsrc + (size_t)k * gstride + c4 * 4);
+      g.x *= gsc; g.y *= gsc; g.z *= gsc; g.w *= gsc;
       float4 gs = g;
       if (ada) {
         al.x = a0.x + g.x * g.x; al.y = a0.y + g.y * g.y; al.z = a0.z + g.z * g.z; al.w = a0.w + g.w * g.w;
@@ -831,6 +1019,44 @@ __device__ __forceinline__ void sparse_row_update(const ModelDev& md, float* __r
     st4(prow + c4 * 4, ps);
     if (ada) st4(arow + c4 * 4, al);
     if (mom) st4(vrow + c4 * 4, vl);
+  }
+}
+
+// sparse update of the Wy / By rows of column chunk `chunk` (gru4rec.py:407-431): one warp per item group, members in position
+// order.  gD / gDby: gradient rows of the chunk's columns (row j - cb of a shared-memory block, or the global DSY / DBY arrays)
+__device__ __forceinline__ void chunk_rows_update(const ModelDev& md, const int* __restrict__ pItem, int cb, int ce, const float* gD, int gDld, int gDoff,
+                                                  const float* gDby) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int ldL = md.ldL;
+  const bool ada = md.adapt == G4R_ADAPT_ADAGRAD;
+  const bool mom = md.mom > 0.f;
+  const size_t astW = (size_t)md.n_items * ldL, astB = (size_t)md.n_items;
+  for (int j = cb + warp; j < ce; j += nwarp) {
+    const int item = pItem[j];
+    if (j > cb && pItem[j - 1] == item) continue;          // not a group start
+    int je = j + 1;
+    while (je < ce && pItem[je] == item) je++;
+    const float* gsrc = gD + (size_t)(j - gDoff) * gDld;
+    sparse_row_update(md, md.Wy + (size_t)item * ldL, md.Wy_acc ? md.Wy_acc + (size_t)item * ldL : nullptr,
+                      md.Wy_vel ? md.Wy_vel + (size_t)item * ldL : nullptr, gsrc, gDld, je - j, lane, ldL, ada, mom, astW);
+    if (md.adapt > G4R_ADAPT_ADAGRAD) {
+      if (lane == 0) opt_row_generic(md, md.By + item, md.By_acc + item, astB, md.By_vel ? md.By_vel + item : nullptr, nullptr, 1, je - j, 0, 1, true,
+                                     [&](int k, int) { return gDby[j - gDoff + k]; });
+    } else if (lane == 0) {   // By (gru4rec.py:486-489)
+      const float gsc = grad_scale(md);
+      const float p0 = md.By[item];
+      float a0 = ada ? md.By_acc[item] : 0.f, v0 = mom ? md.By_vel[item] : 0.f, al = 0.f, vl = 0.f, ps = p0;
+      for (int jj = j; jj < je; jj++) {
+        const float g = gDby[jj - gDoff] * gsc;
+        float gs = g;
+        if (ada) { al = a0 + g * g; gs = __fdiv_rn(g, sqrtf(al + G4R_EPS_ADA)); }
+        const float d = md.lmbd > 0.f ? md.lr * (gs + md.lmbd * p0) : md.lr * gs;
+        if (mom) { vl = md.mom * v0 - d; ps += vl; } else ps -= d;
+      }
+      md.By[item] = ps;
+      if (ada) md.By_acc[item] = al;
+      if (mom) md.By_vel[item] = vl;
+    }
   }
 }
 
@@ -937,32 +1163,16 @@ __device__ void phase_lossgrad(const ModelDev& md, int s, int chunk, float* smem
   }
   __syncthreads();
   if (md.export_only) return;     // multi-GPU: DSY / DBY are exchanged and the merged update is applied by k_mg_apply_rows
-  // ---- sparse update of this chunk's item groups; one warp per group, members in position order
-  const bool ada = md.adapt == G4R_ADAPT_ADAGRAD;
-  const bool mom = md.mom > 0.f;
-  for (int j = cb + warp; j < ce; j += SC_THREADS / 32) {
-    const int item = pItem[j];
-    if (j > cb && pItem[j - 1] == item) continue;          // not a group start
-    int je = j + 1;
-    while (je < ce && pItem[je] == item) je++;
-    const float* gsrc = single ? (sD + (size_t)(j - cb) * ldL) : (md.DSY + (size_t)j * ldL);
-    sparse_row_update(md, md.Wy + (size_t)item * ldL, md.Wy_acc ? md.Wy_acc + (size_t)item * ldL : nullptr,
-                      md.Wy_vel ? md.Wy_vel + (size_t)item * ldL : nullptr, gsrc, ldL, je - j, lane, ldL, ada, mom);
-    if (lane == 0) {   // By (gru4rec.py:486-489)
-      const float p0 = md.By[item];
-      float a0 = ada ? md.By_acc[item] : 0.f, v0 = mom ? md.By_vel[item] : 0.f, al = 0.f, vl = 0.f, ps = p0;
-      for (int jj = j; jj < je; jj++) {
-        const float g = single ? sDby[jj - cb] : md.DBY[jj];
-        float gs = g;
-        if (ada) { al = a0 + g * g; gs = __fdiv_rn(g, sqrtf(al + G4R_EPS_ADA)); }
-        const float d = md.lmbd > 0.f ? md.lr * (gs + md.lmbd * p0) : md.lr * gs;
-        if (mom) { vl = md.mom * v0 - d; ps += vl; } else ps -= d;
-      }
-      md.By[item] = ps;
-      if (ada) md.By_acc[item] = al;
-      if (mom) md.By_vel[item] = vl;
-    }
-  }
+  // ---- sparse update of this chunk's item groups
+  if (single) chunk_rows_update(md, pItem, cb, ce, sD, ldL, cb, sDby);
+  else chunk_rows_update(md, pItem, cb, ce, md.DSY, ldL, 0, md.DBY);
+}
+// grad_cap: second pass -- the rows of the chunk are updated from the exported gradient rows, scaled by the global-norm factor
+__device__ void phase_apply_rows(const ModelDev& md, int s, int chunk) {
+  const int* cbeg = md.pCbeg + (size_t)s * (md.NCH + 1);
+  const int cb = cbeg[chunk], ce = cbeg[chunk + 1];
+  if (cb >= ce) return;
+  chunk_rows_update(md, md.pItem + (size_t)s * md.NP, cb, ce, md.DSY, md.ldL, 0, md.DBY);
 }
 __host__ __device__ inline size_t lossgrad_smem_bytes(int Bld, int ldL) {
   return (size_t)(SC_TB * SC_LDS + SC_CT * SC_LDS + SC_CT * Bld + Bld * 8 + SC_CT * ldL + SC_CT + SC_CT + Bld + 32) * sizeof(float);
@@ -1119,7 +1329,7 @@ __device__ void phase_dense(const ModelDev& md, int li, int s, int job, float* s
 #pragma unroll
       for (int j = 0; j < GT; j++) {
         const int rr = m0 + ty * GT + i, c = n0 + tx * GT + j;
-        if (rr < L && c < L) { const size_t o = (size_t)rr * ly.ldL + c; if (md.export_only) ly.Wh_g[o] = acc[i][j]; else dense_update(md, ly.Wh + o, ly.Wh_acc ? ly.Wh_acc + o : nullptr, ly.Wh_vel ? ly.Wh_vel + o : nullptr, acc[i][j]); }
+        if (rr < L && c < L) { const size_t o = (size_t)rr * ly.ldL + c; if (md.export_only) ly.Wh_g[o] = acc[i][j]; else dense_update(md, ly.Wh + o, ly.Wh_acc ? ly.Wh_acc + o : nullptr, ly.Wh_vel ? ly.Wh_vel + o : nullptr, acc[i][j], (size_t)L * ly.ldL); }
       }
     return;
   }
@@ -1133,7 +1343,7 @@ __device__ void phase_dense(const ModelDev& md, int li, int s, int job, float* s
 #pragma unroll
       for (int j = 0; j < GT; j++) {
         const int rr = m0 + ty * GT + i, c = n0 + tx * GT + j;
-        if (rr < L && c < 2 * L) { const size_t o = (size_t)rr * ly.ld2 + c; if (md.export_only) ly.Wrz_g[o] = acc[i][j]; else dense_update(md, ly.Wrz + o, ly.Wrz_acc ? ly.Wrz_acc + o : nullptr, ly.Wrz_vel ? ly.Wrz_vel + o : nullptr, acc[i][j]); }
+        if (rr < L && c < 2 * L) { const size_t o = (size_t)rr * ly.ld2 + c; if (md.export_only) ly.Wrz_g[o] = acc[i][j]; else dense_update(md, ly.Wrz + o, ly.Wrz_acc ? ly.Wrz_acc + o : nullptr, ly.Wrz_vel ? ly.Wrz_vel + o : nullptr, acc[i][j], (size_t)L * ly.ld2); }
       }
     return;
   }
@@ -1148,7 +1358,7 @@ __device__ void phase_dense(const ModelDev& md, int li, int s, int job, float* s
 #pragma unroll
       for (int j = 0; j < GT; j++) {
         const int rr = m0 + ty * GT + i, c = n0 + tx * GT + j;
-        if (rr < IN && c < 3 * L) { const size_t o = (size_t)rr * ly.ld3 + c; if (md.export_only) ly.Wx_g[o] = acc[i][j]; else dense_update(md, ly.Wx + o, ly.Wx_acc ? ly.Wx_acc + o : nullptr, ly.Wx_vel ? ly.Wx_vel + o : nullptr, acc[i][j]); }
+        if (rr < IN && c < 3 * L) { const size_t o = (size_t)rr * ly.ld3 + c; if (md.export_only) ly.Wx_g[o] = acc[i][j]; else dense_update(md, ly.Wx + o, ly.Wx_acc ? ly.Wx_acc + o : nullptr, ly.Wx_vel ? ly.Wx_vel + o : nullptr, acc[i][j], (size_t)IN * ly.ld3); }
       }
     return;
   }
@@ -1158,7 +1368,7 @@ __device__ void phase_dense(const ModelDev& md, int li, int s, int job, float* s
     if (c < 3 * L) {
       float g = 0.f;
       for (int b = 0; b < M; b++) g += ly.dvec[(size_t)b * ly.ld3 + c];
-      if (md.export_only) ly.Bh_g[c] = g; else dense_update(md, ly.Bh + c, ly.Bh_acc ? ly.Bh_acc + c : nullptr, ly.Bh_vel ? ly.Bh_vel + c : nullptr, g);
+      if (md.export_only) ly.Bh_g[c] = g; else dense_update(md, ly.Bh + c, ly.Bh_acc ? ly.Bh_acc + c : nullptr, ly.Bh_vel ? ly.Bh_vel + c : nullptr, g, (size_t)ly.ld3);
     }
   }
 }
@@ -1167,9 +1377,9 @@ __device__ void phase_dense(const ModelDev& md, int li, int s, int job, float* s
 // phase X: sparse update of the gathered INPUT rows (gru4rec.py:407-431 applied to Wx0[X] / E[X] / Wy[X]).
 // One CTA per duplicate group of X (chain through wXnext); members processed in position order.
 // ------------------------------------------------------------------------------------------------
-__device__ void phase_sparse_in(const ModelDev& md, int s, int b) {
+__device__ void phase_sparse_in(const ModelDev& md, int s, int b, bool apply_pass = false) {
   const int M = md.wM[s];
-  if (b >= M || md.export_only) return;
+  if (b >= M || (md.export_only && !apply_pass)) return;
   const uint8_t xf = md.wXflag[(size_t)s * md.B + b];
   if (!(xf & 1)) return;                      // not the first position of its group
   const int item = md.wX[(size_t)s * md.B + b];
@@ -1182,6 +1392,17 @@ __device__ void phase_sparse_in(const ModelDev& md, int s, int b) {
   const bool shared = md.mode == 2;
   const bool write_state = !(shared && (xf & 2));     // shared: a later (Y / sample) occurrence owns acc / velocity
   float* prow = tab + (size_t)item * ld;
+  if (md.adapt > G4R_ADAPT_ADAGRAD) {                 // rmsprop / adadelta / adam (no-embedding and separate-embedding modes)
+    __shared__ int s_mem[64];
+    __shared__ int s_n;
+    if (threadIdx.x == 0) { int n = 0; for (int bb = b; bb >= 0 && n < 64; bb = xnext[bb]) s_mem[n++] = bb; s_n = n; }
+    __syncthreads();
+    opt_row_generic(md, prow, tacc + (size_t)item * ld, (size_t)md.n_items * ld, tvel ? tvel + (size_t)item * ld : nullptr, nullptr, ld, s_n,
+                    (int)threadIdx.x, (int)blockDim.x, true, [&](int k, int c) { return G[(size_t)s_mem[k] * ldg + c]; });
+    __syncthreads();
+    return;
+  }
+  const float gsc = grad_scale(md);
   for (int c4 = threadIdx.x; c4 < ld / 4; c4 += blockDim.x) {
     const float4 pcur = ld4(prow + c4 * 4);
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), v0 = a0, al = a0, vl = a0, p0 = pcur;
@@ -1195,7 +1416,8 @@ __device__ void phase_sparse_in(const ModelDev& md, int s, int b) {
     }
     float4 ps = pcur;
     for (int bb = b; bb >= 0; bb = xnext[bb]) {
-      const float4 g = ld4(G + (size_t)bb * ldg + c4 * 4);
+      float4 g = ld4(G + (size_t)bb * ldg + c4 * 4);
+      g.x *= gsc; g.y *= gsc; g.z *= gsc; g.w *= gsc;
       float4 gs = g;
       if (ada) {
         al.x = a0.x + g.x * g.x; al.y = a0.y + g.y * g.y; al.z = a0.z + g.z * g.z; al.w = a0.w + g.w * g.w;

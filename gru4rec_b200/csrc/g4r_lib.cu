@@ -79,11 +79,15 @@ struct g4r_handle {
   size_t shard_ws_bytes = 0;
   FastSync* dFastSync = nullptr; bool fast_ok = false; bool fastc_ok = false; int fastc_grid = 0; int* hFlags = nullptr; int64_t fast_windows = 0, slow_windows = 0;
   bool prof = false; bool stamp_on = false;
+  bool two_pass = false;         // grad_cap: gradients are exported, the global norm is taken, then a second pass applies them scaled
+  bool phase_only = false;       // grad_cap / smoothing add phases that only the per-phase launch sequence has
+  float* dGscale = nullptr;
   std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_phase;
 };
 
-enum { PH_GATHER = 0, PH_F1, PH_F2, PH_SCORE, PH_STATS, PH_LOSSGRAD, PH_B1, PH_B2, PH_B3, PH_DENSE, PH_SPARSE_IN, PH_COUNT };
-static const char* kPhaseNames[PH_COUNT] = {"gather_in", "gru_rz", "gru_h", "score", "stats", "lossgrad_update", "gru_bwd_elem", "gru_bwd_dHr", "gru_bwd_din", "dense_update", "sparse_in_update"};
+enum { PH_GATHER = 0, PH_F1, PH_F2, PH_SCORE, PH_STATS, PH_LOSSGRAD, PH_B1, PH_B2, PH_B3, PH_DENSE, PH_SPARSE_IN, PH_STATS2, PH_GRADCAP, PH_COUNT };
+static const char* kPhaseNames[PH_COUNT] = {"gather_in", "gru_rz", "gru_h", "score", "stats", "lossgrad_update", "gru_bwd_elem", "gru_bwd_dHr", "gru_bwd_din", "dense_update", "sparse_in_update",
+                                            "smoothing_stats", "grad_cap_norm_apply"};
 
 // LAUNCH(phase, kernel<<<...>>>(...)): counts the launch and, when profiling, brackets it with CUDA events
 #define LAUNCH(ph, ...) do { \
@@ -116,7 +120,15 @@ struct Carver {
 static int validate_config(const g4r_config& c, std::string& err) {
   if (c.n_items <= 0 || c.n_layers <= 0 || c.n_layers > G4R_MAX_LAYERS || c.batch_size <= 0) { err = "invalid sizes"; return G4R_ERR_INVALID; }
   for (int i = 0; i < c.n_layers; i++) if (c.layers[i] <= 0) { err = "invalid layer width"; return G4R_ERR_INVALID; }
-  if (c.adapt != G4R_ADAPT_ADAGRAD && c.adapt != G4R_ADAPT_NONE) { err = "adapt: only adagrad / None run on the device path"; return G4R_ERR_INVALID; }
+  if (c.adapt < G4R_ADAPT_NONE || c.adapt > G4R_ADAPT_ADAM) { err = "adapt: unknown optimizer"; return G4R_ERR_INVALID; }
+  if (c.adapt > G4R_ADAPT_ADAGRAD && c.constrained_embedding) {
+    // the reference's duplicate-accurate state update couples the input and the output occurrences of an item in one scatter
+    err = "adapt = rmsprop / adadelta / adam with constrained_embedding is not implemented on the device path"; return G4R_ERR_INVALID;
+  }
+  if (c.grad_cap < 0.f) { err = "grad_cap < 0"; return G4R_ERR_INVALID; }
+  if ((c.adapt > G4R_ADAPT_ADAGRAD || c.grad_cap > 0.f || c.smoothing != 0.f) && c.world_size > 1) {
+    err = "adapt other than adagrad, grad_cap and smoothing are single-GPU options"; return G4R_ERR_INVALID;
+  }
   if (c.hidden_act < G4R_ACT_LINEAR || c.hidden_act > G4R_ACT_SELU) { err = "hidden_act unsupported"; return G4R_ERR_INVALID; }
   const bool elem = c.final_act >= G4R_ACT_LINEAR && c.final_act <= G4R_ACT_SELU;
   bool ok = false;
@@ -124,7 +136,7 @@ static int validate_config(const g4r_config& c, std::string& err) {
   if (c.loss == G4R_LOSS_XE_LOGIT && c.final_act == G4R_ACT_SOFTMAX_LOGIT) ok = true;
   if ((c.loss == G4R_LOSS_BPR_MAX || c.loss == G4R_LOSS_TOP1_MAX || c.loss == G4R_LOSS_BPR || c.loss == G4R_LOSS_TOP1) && elem) ok = true;
   if (!ok) { err = "loss / final_act combination not implemented on the device path"; return G4R_ERR_INVALID; }
-  if (c.smoothing != 0.f) { err = "smoothing not implemented on the device path"; return G4R_ERR_INVALID; }
+  if (c.smoothing < 0.f) { err = "smoothing < 0"; return G4R_ERR_INVALID; }
   if (c.constrained_embedding && c.embedding) { /* reference: constrained wins (gru4rec.py:272) */ }
   if (c.n_sample < 0) { err = "n_sample < 0"; return G4R_ERR_INVALID; }
   return G4R_OK;
@@ -143,7 +155,8 @@ static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
   const int Bmax = std::max(B, Be);
   const int Llast = c.layers[nl - 1], ldL = round4(Llast);
   const bool mom = c.momentum > 0.f;
-  const bool ada = c.adapt == G4R_ADAPT_ADAGRAD;
+  const bool ada = c.adapt != G4R_ADAPT_NONE;            // at least one adaptive state array ("acc")
+  const int nacc = opt_states(c.adapt);                  // acc | acc, upd | acc, meang, countt -- stacked behind `*.acc`
   const int gen_len = (c.n_sample > 0 && c.sample_store > 0) ? c.sample_store / c.n_sample : 0;
   const bool store = gen_len > 1;
   const int S = store ? c.n_sample : 0;
@@ -157,6 +170,8 @@ static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
   md.loss = c.loss; md.fact = {c.final_act, c.final_act_p1, c.final_act_p2}; md.hact = {c.hidden_act, c.hidden_act_p1, c.hidden_act_p2};
   md.p_drop_h = c.dropout_p_hidden; md.p_drop_e = c.dropout_p_embed; md.lr = c.learning_rate; md.mom = c.momentum; md.lmbd = c.lmbd;
   md.bpreg = c.bpreg; md.logq = c.logq; md.alpha = c.sample_alpha; md.adapt = c.adapt;
+  md.ap1 = c.adapt_p1; md.ap1c = c.adapt_p1c; md.ap2 = c.adapt_p2; md.ap2c = c.adapt_p2c; md.grad_cap = c.grad_cap;
+  md.smoothing = (c.loss == G4R_LOSS_XE || c.loss == G4R_LOSS_XE_LOGIT) ? c.smoothing : 0.f;    // the other losses ignore it (gru4rec.py:237-248)
   md.drop_seed = c.dropout_seed + (c.world_size > 1 ? (uint32_t)c.rank * 0x9E3779B1u : 0u);   // multi-GPU: independent masks per rank
   md.in0_dim = mode == 2 ? Llast : (mode == 1 ? c.embedding : 0);
   md.ld_in0 = round4(md.in0_dim);
@@ -164,7 +179,9 @@ static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
   auto table3 = [&](const std::string& name, int64_t rows, int64_t cols, float** p, float** a, float** v, int64_t ld_override = 0) {
     const int64_t ld = ld_override > 0 ? ld_override : round4((int)cols);
     *p = cv.take<float>((size_t)rows * ld); reg(name, *p, rows, cols, ld);
-    *a = ada ? cv.take<float>((size_t)rows * ld) : nullptr; if (ada) reg(name + ".acc", *a, rows, cols, ld);
+    *a = ada ? cv.take<float>((size_t)rows * ld * nacc) : nullptr; if (ada) reg(name + ".acc", *a, rows, cols, ld);
+    if (nacc > 1) reg(name + (c.adapt == G4R_ADAPT_ADAM ? ".meang" : ".upd"), *a + (size_t)rows * ld, rows, cols, ld);
+    if (nacc > 2) reg(name + ".countt", *a + 2 * (size_t)rows * ld, rows, cols, ld);
     *v = mom ? cv.take<float>((size_t)rows * ld) : nullptr; if (mom) reg(name + ".vel", *v, rows, cols, ld);
   };
   // item tables
@@ -205,6 +222,9 @@ static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
   md.part = cv.take<float>((size_t)NCH * B * ldL);
   md.stat = cv.take<float>((size_t)NCH * B * G4R_NSTAT);
   md.RS = cv.take<float>((size_t)Bmax * G4R_NSTAT);
+  md.stat2 = md.smoothing > 0.f ? cv.take<float>((size_t)NCH * B * 2) : nullptr;
+  float* gsc = c.grad_cap > 0.f ? cv.take<float>(8) : nullptr;
+  md.gscale = gsc;
   md.cost = cv.take<float>((size_t)CAP);
   md.nanflag = cv.take<int>(4);
   reg("O", md.O, NP, Bmax, md.Bld); reg("DSY", md.DSY, NP, Llast, ldL);
@@ -228,7 +248,8 @@ static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
   // multi-GPU: dense-gradient twins (one flat all-reduce buffer) and the gathered / merged per-window state
   MgDev mgd; memset(&mgd, 0, sizeof(mgd));
   std::vector<MgTensor> mgt;
-  if (R > 1) {
+  const bool twins = R > 1 || c.grad_cap > 0.f;      // dense gradients are exported (all-reduced / norm-capped) before they are applied
+  if (twins) {
     size_t cnt = 0;
     for (int i = 0; i < nl; i++) {
       const LayerDev& ly = md.layer[i];
@@ -245,6 +266,8 @@ static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
       ly.Bh_g = gf ? gf + off : nullptr; mgt.push_back(MgTensor{ly.Bh, ly.Bh_acc, ly.Bh_vel, off, ly.ld3}); off += ly.ld3;
     }
     mgd.R = R; mgd.rank = c.rank; mgd.gradFlat = gf; mgd.gradCount = cnt;
+  }
+  if (R > 1) {
     mgd.gItem = cv.take<int>((size_t)R * MG_CAP * NP); mgd.gPos = nullptr;
     mgd.gM = cv.take<int>((size_t)R * MG_CAP); mgd.gX = cv.take<int>((size_t)R * MG_CAP * B);
     mgd.mEnt = cv.take<int>((size_t)MG_CAP * R * NP); mgd.mItem = cv.take<int>((size_t)MG_CAP * R * NP);
@@ -273,6 +296,7 @@ static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
     h->dRankCnt = dRank; h->dTgt = dTgt;
     h->npow2 = next_pow2(B + S);
     h->shard_ws = shard_ws; h->shard_ws_bytes = shard_ws_bytes;
+    h->dGscale = gsc; h->two_pass = c.grad_cap > 0.f; h->phase_only = c.grad_cap > 0.f || md.smoothing > 0.f;
   }
 }
 
@@ -326,7 +350,21 @@ __global__ void __launch_bounds__(GEMM_THREADS) k_dense(int slot, const int* bas
   __shared__ float sA[GK * (GB + 1)], sB[GK * (GB + 1)];
   phase_dense(MD, li, STEP_IDX, blockIdx.x, sA, sB);
 }
-__global__ void __launch_bounds__(128) k_sparse_in(int slot, const int* base, int off) { phase_sparse_in(MD, STEP_IDX, blockIdx.x); }
+__global__ void __launch_bounds__(128) k_sparse_in(int slot, const int* base, int off, int apply_pass) { phase_sparse_in(MD, STEP_IDX, blockIdx.x, apply_pass != 0); }
+__global__ void __launch_bounds__(256) k_stats2a(int slot, const int* base, int off) { phase_stats2a(MD, STEP_IDX, blockIdx.x); }
+__global__ void __launch_bounds__(256) k_stats2b(int slot, const int* base, int off) {
+  __shared__ float smem[64];
+  phase_stats2b(MD, STEP_IDX, blockIdx.x, gridDim.x, smem);
+}
+__global__ void __launch_bounds__(1024) k_gradnorm(int slot, const int* base, int off, const float* dense_flat, size_t dense_count, float* gscale) {
+  __shared__ float smem[32];
+  phase_gradnorm(MD, STEP_IDX, dense_flat, dense_count, gscale, smem);
+}
+__global__ void __launch_bounds__(SC_THREADS) k_apply_rows(int slot, const int* base, int off) { phase_apply_rows(MD, STEP_IDX, blockIdx.x); }
+__global__ void __launch_bounds__(256) k_apply_dense(int slot, float* p, float* acc, float* vel, const float* g, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dense_update(MD, p + i, acc ? acc + i : nullptr, vel ? vel + i : nullptr, g[i], (size_t)n);
+}
 __global__ void k_advance(int* base, int n) { if (threadIdx.x == 0 && blockIdx.x == 0) *base += n; }
 
 #include "g4r_persistent.cuh"
@@ -395,6 +433,10 @@ static int enqueue_train_step(g4r_handle* h, const int* base, int off) {
   }
   LAUNCH(PH_SCORE, k_score<<<md.NCH, SC_THREADS, score_smem_bytes(md.Bld), st>>>(h->slot, base, off));
   LAUNCH(PH_STATS, k_stats<<<B, 256, 256 * sizeof(float), st>>>(h->slot, base, off));
+  if (md.smoothing > 0.f) {      // label smoothing: second statistics pass once the row maxima / normalisers are final
+    LAUNCH(PH_STATS2, k_stats2a<<<md.NCH, 256, 0, st>>>(h->slot, base, off));
+    LAUNCH(PH_STATS2, k_stats2b<<<B, 256, 0, st>>>(h->slot, base, off));
+  }
   LAUNCH(PH_LOSSGRAD, k_lossgrad<<<md.NCH, SC_THREADS, lossgrad_smem_bytes(md.Bld, md.ldL), st>>>(h->slot, base, off));
   for (int li = md.n_layers - 1; li >= 0; li--) {
     const LayerDev& ly = md.layer[li];
@@ -404,7 +446,15 @@ static int enqueue_train_step(g4r_handle* h, const int* base, int off) {
     const DenseJobs dj = dense_jobs(ly.L, ly.in_dim);
     LAUNCH(PH_DENSE, k_dense<<<dj.nWh + dj.nWrz + dj.nWx + dj.nBh, GEMM_THREADS, 0, st>>>(h->slot, base, off, li));
   }
-  LAUNCH(PH_SPARSE_IN, k_sparse_in<<<B, 128, 0, st>>>(h->slot, base, off));
+  LAUNCH(PH_SPARSE_IN, k_sparse_in<<<B, 128, 0, st>>>(h->slot, base, off, 0));
+  if (h->two_pass) {
+    // grad_cap: the phases above ran in export mode (gradients only); global norm, then the updates with the scaled gradients
+    const MgDev& mg = h->mgdev;
+    LAUNCH(PH_GRADCAP, k_gradnorm<<<1, 1024, 0, st>>>(h->slot, base, off, mg.gradFlat, mg.gradCount, h->dGscale));
+    LAUNCH(PH_GRADCAP, k_apply_rows<<<md.NCH, SC_THREADS, 0, st>>>(h->slot, base, off));
+    for (const MgTensor& t : h->mg_tensors) LAUNCH(PH_GRADCAP, k_apply_dense<<<(t.count + 255) / 256, 256, 0, st>>>(h->slot, t.p, t.acc, t.vel, mg.gradFlat + t.goff, t.count));
+    LAUNCH(PH_GRADCAP, k_sparse_in<<<B, 128, 0, st>>>(h->slot, base, off, 1));
+  }
   return G4R_OK;
 }
 
@@ -502,6 +552,7 @@ extern "C" int g4r_create(const g4r_config* cfg, void* device_workspace, size_t 
   layout(*cfg, cv, h, chunk_cap);
   h->slot = slot_alloc();
   if (h->slot < 0) return bail(G4R_ERR_STATE, "too many live g4r handles in this process");
+  if (h->two_pass) h->md.export_only = 1;       // grad_cap: every update waits for the global gradient norm
   if (slot_upload(h->slot, h->md, h->stream) != cudaSuccess) return bail(G4R_ERR_CUDA, "constant upload failed");
   const int B = cfg->batch_size, CAP = h->CAP;
   bool ok = true;
@@ -532,10 +583,11 @@ extern "C" int g4r_create(const g4r_config* cfg, void* device_workspace, size_t 
     raise_smem_limit((const void*)k_fast_t<false>, sizeof(FastSmem));
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fast_t<false>, FK_THREADS, sizeof(FastSmem));
-    h->fast_ok = h->pk_blocks > 0 && per_sm >= 1 && m.mode == 0 && m.n_layers == 1 && m.ldL <= 128 && m.B <= FK_B && h->n_sm >= FK_G + 1 && m.NCH <= 160 &&
+    const bool plain_opt = m.adapt <= G4R_ADAPT_ADAGRAD && !h->phase_only;    // the role-specialised kernels implement SGD / Adagrad (+momentum) only
+    h->fast_ok = plain_opt && h->pk_blocks > 0 && per_sm >= 1 && m.mode == 0 && m.n_layers == 1 && m.ldL <= 128 && m.B <= FK_B && h->n_sm >= FK_G + 1 && m.NCH <= 160 &&
                  2 * m.L <= FK_W1 * FK_G && m.L <= FK_W2 * FK_G &&     // the 48-CTA GRU group covers FK_W1 gate / FK_W2 candidate columns per CTA (L <= 120)
                  (m.adapt == G4R_ADAPT_ADAGRAD ? m.Wy_acc != nullptr : true);
-    h->fastc_ok = cfg->step_mode == 3 && h->fastc_grid >= FC_CLUSTER * 2 && m.mode == 0 && m.n_layers == 1 && m.ldL <= 128 && m.B <= FK_B &&
+    h->fastc_ok = plain_opt && cfg->step_mode == 3 && h->fastc_grid >= FC_CLUSTER * 2 && m.mode == 0 && m.n_layers == 1 && m.ldL <= 128 && m.B <= FK_B &&
                   m.NCH <= h->fastc_grid && (m.adapt == G4R_ADAPT_ADAGRAD ? m.Wy_acc != nullptr : true);
     cudaMallocHost(&h->hFlags, 4 * sizeof(int));
   }
@@ -924,6 +976,8 @@ static int64_t launches_per_step(const g4r_handle* h) {
   const ModelDev& md = h->md;
   int64_t n = (md.mode != 0 ? 1 : 0) + 4;        // gather + score/stats/lossgrad + sparse_in
   for (int li = 0; li < md.n_layers; li++) n += 2 + 2 + (md.layer[li].in_dim > 0 ? 1 : 0) + 1;
+  if (md.smoothing > 0.f) n += 2;
+  if (h->two_pass) n += 3 + (int64_t)h->mg_tensors.size();
   return n;
 }
 
@@ -951,7 +1005,7 @@ static int run_window(g4r_handle* h, int64_t n) {
     CK(cudaMemsetAsync(h->dFastSync, 0, sizeof(FastSync), h->stream));
     CK(cudaLaunchCooperativeKernel((void*)k_fast_t<false>, dim3(h->pk_blocks), dim3(FK_THREADS), args, sizeof(FastSmem), h->stream));
     h->launches += 1; h->fast_windows++;
-  } else if (h->cfg.step_mode >= 1 && !h->prof && h->pk_blocks > 0) {
+  } else if (h->cfg.step_mode >= 1 && !h->prof && h->pk_blocks > 0 && !h->phase_only) {
     if (h->cfg.step_mode >= 2) h->slow_windows++;
     int slot = h->slot, nst = (int)n; GridBar* gb = h->dGridBar; unsigned long long* ts = h->stamp_on ? h->dStamp : nullptr;
     void* args[] = {&slot, &nst, &gb, &ts};

@@ -61,6 +61,44 @@ __device__ __forceinline__ void mgs_wait_flags(const ShardDev& sh, int first, in
     __syncwarp();
   }
 }
+// ---- "LL" exchange: 8-byte (value, sequence) pairs.  A pair is written by ONE store, so data and flag travel together over
+// NVLink: the receiver polls the data itself -- no system-scope fence, no separate flag, one one-way latency per exchange.
+// The sequence is the lock-step number (>= 1, strictly increasing per slot), the slots are double buffered by its parity.
+__device__ __forceinline__ void ll_store4(float* dst_pairs, float4 v, unsigned int seq) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(dst_pairs), "r"(__float_as_uint(v.x)), "r"(seq), "r"(__float_as_uint(v.y)), "r"(seq) : "memory");
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(dst_pairs + 4), "r"(__float_as_uint(v.z)), "r"(seq), "r"(__float_as_uint(v.w)), "r"(seq) : "memory");
+}
+__device__ __forceinline__ float4 ll_load4(const float* src_pairs, unsigned int seq, int* abort) {
+  uint4 a, b;
+  unsigned int spins = 0; unsigned long long t0 = 0;
+  while (true) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(src_pairs) : "memory");
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(src_pairs + 4) : "memory");
+    if (a.y == seq && a.w == seq && b.y == seq && b.w == seq) break;
+    if ((++spins & 127u) == 0) {
+      if (*(volatile int*)abort) break;
+      const unsigned long long t = mgs_timer();
+      if (t0 == 0) t0 = t;
+      if (t - t0 > MGS_TIMEOUT_NS) { atomicExch(abort, 1); break; }
+    }
+  }
+  return make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
+}
+__device__ __forceinline__ float ll_load1(const float* src_pair, unsigned int seq, int* abort) {
+  uint2 a;
+  unsigned int spins = 0; unsigned long long t0 = 0;
+  while (true) {
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(a.x), "=r"(a.y) : "l"(src_pair) : "memory");
+    if (a.y == seq) break;
+    if ((++spins & 127u) == 0) {
+      if (*(volatile int*)abort) break;
+      const unsigned long long t = mgs_timer();
+      if (t0 == 0) t0 = t;
+      if (t - t0 > MGS_TIMEOUT_NS) { atomicExch(abort, 1); break; }
+    }
+  }
+  return __uint_as_float(a.x);
+}
 // local counter wait that also gives up when the step was aborted
 __device__ __forceinline__ void wait_ge_abortable(const unsigned int* p, unsigned int target, int* abort) {
   unsigned int spins = 0;
@@ -147,7 +185,7 @@ struct QuadUpd {
 };
 
 // owner side: merged update of the rows of apply-chunk `a` (one warp per item group, members in (rank, position) order)
-__device__ void mgs_apply_rows(const ModelDev& md, FastSmemMG& sm, int s, int a, int par) {
+__device__ void mgs_apply_rows(const ModelDev& md, FastSmemMG& sm, int s, int a, int par, unsigned int T) {
   const ShardDev& sh = sm.sh;
   const int R = sh.R, ldW = sh.ldW, nq = ldW / 4;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -156,7 +194,7 @@ __device__ void mgs_apply_rows(const ModelDev& md, FastSmemMG& sm, int s, int a,
   const int* ent = sh.aEnt + (size_t)s * R * md.NP;
   const int* it = sh.aItem + (size_t)s * R * md.NP;
   const bool ada = md.adapt == G4R_ADAPT_ADAGRAD, mom = md.mom > 0.f;
-  const float* inb = sh.inbox[sh.rank] + (size_t)par * R * md.NP * ldW;
+  const float* inb = sh.inbox[sh.rank] + (size_t)par * R * md.NP * ldW * 2;      // (value, sequence) pairs
   float* W = sh.W[sh.rank];
   for (int j = cb + warp; j < ce; j += FK_NW) {
     const int item = it[j];
@@ -170,7 +208,7 @@ __device__ void mgs_apply_rows(const ModelDev& md, FastSmemMG& sm, int s, int a,
       u.begin(ld4(W + ro + q4 * 4), ada ? ld4(sh.W_acc + ro + q4 * 4) : z, mom ? ld4(sh.W_vel + ro + q4 * 4) : z);
       for (int k = j; k < je; k++) {
         const int e = ent[k];
-        u.add(md, __ldcg(reinterpret_cast<const float4*>(inb + ((size_t)(e >> 20) * md.NP + (size_t)(e & 0xfffff)) * ldW + q4 * 4)), ada, mom);
+        u.add(md, ll_load4(inb + (((size_t)(e >> 20) * md.NP + (size_t)(e & 0xfffff)) * ldW + q4 * 4) * 2, T, sh.abort), ada, mom);
       }
       st4(W + ro + q4 * 4, u.ps);
       if (ada) st4(sh.W_acc + ro + q4 * 4, u.al);
@@ -179,7 +217,7 @@ __device__ void mgs_apply_rows(const ModelDev& md, FastSmemMG& sm, int s, int a,
   }
 }
 // owner side: merged update of the owned input rows; helper `hb` of `nh` takes the groups that start at j = hb, hb + nh, ...
-__device__ void mgs_apply_inputs(const ModelDev& md, FastSmemMG& sm, int s, int hb, int nh, int par) {
+__device__ void mgs_apply_inputs(const ModelDev& md, FastSmemMG& sm, int s, int hb, int nh, int par, unsigned int T) {
   const ShardDev& sh = sm.sh;
   const LayerDev& ly = md.layer[0];
   const int R = sh.R, ld3 = ly.ld3, B = md.B, tid = threadIdx.x;
@@ -187,8 +225,8 @@ __device__ void mgs_apply_inputs(const ModelDev& md, FastSmemMG& sm, int s, int 
   const int* ent = sh.xEnt + (size_t)s * R * B;
   const int* it = sh.xItem + (size_t)s * R * B;
   const bool ada = md.adapt == G4R_ADAPT_ADAGRAD, mom = md.mom > 0.f;
-  const float* inb = sh.inboxIn[sh.rank] + (size_t)par * R * B * ld3;
-  float* T = sh.Wx[sh.rank];
+  const float* inb = sh.inboxIn[sh.rank] + (size_t)par * R * B * ld3 * 2;       // (value, sequence) pairs
+  float* Tb = sh.Wx[sh.rank];
   for (int j = hb; j < xt; j += nh) {
     const int item = it[j];
     if (j > 0 && it[j - 1] == item) continue;
@@ -198,12 +236,12 @@ __device__ void mgs_apply_inputs(const ModelDev& md, FastSmemMG& sm, int s, int 
     for (int q4 = tid; q4 < ld3 / 4; q4 += FK_THREADS) {
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
       QuadUpd u;
-      u.begin(ld4(T + ro + q4 * 4), ada ? ld4(sh.Wx_acc + ro + q4 * 4) : z, mom ? ld4(sh.Wx_vel + ro + q4 * 4) : z);
+      u.begin(ld4(Tb + ro + q4 * 4), ada ? ld4(sh.Wx_acc + ro + q4 * 4) : z, mom ? ld4(sh.Wx_vel + ro + q4 * 4) : z);
       for (int k = j; k < je; k++) {
         const int e = ent[k];
-        u.add(md, __ldcg(reinterpret_cast<const float4*>(inb + ((size_t)(e >> 16) * B + (size_t)(e & 0xffff)) * ld3 + q4 * 4)), ada, mom);
+        u.add(md, ll_load4(inb + (((size_t)(e >> 16) * B + (size_t)(e & 0xffff)) * ld3 + q4 * 4) * 2, T, sh.abort), ada, mom);
       }
-      st4(T + ro + q4 * 4, u.ps);
+      st4(Tb + ro + q4 * 4, u.ps);
       if (ada) st4(sh.Wx_acc + ro + q4 * 4, u.al);
       if (mom) st4(sh.Wx_vel + ro + q4 * 4, u.vl);
     }
@@ -217,6 +255,32 @@ __device__ __forceinline__ void mgs_gather_input(const ModelDev& md, FastSmemMG&
   const int x = md.wX[(size_t)s * md.B + b];
   const float* src = sh.Wx[x % sh.R] + (size_t)(x / sh.R) * ld3;
   for (int q4 = threadIdx.x; q4 < ld3 / 4; q4 += FK_THREADS) st4(sh.mgIn + (size_t)b * ld3 + q4 * 4, ld_volatile4(src + q4 * 4));
+}
+
+// owner side, after the input rows of lock step T - 1 are applied: push the rows the ranks need for the NEXT mini-batch (window
+// step s1) straight into their buffers -- the owner knows every rank's inputs of the whole window (gathered schedule)
+__device__ void mgs_push_inputs(const ModelDev& md, FastSmemMG& sm, int s1, int hb, int nh, unsigned int T1) {
+  const ShardDev& sh = sm.sh;
+  const int R = sh.R, ld3 = md.layer[0].ld3, B = md.B, tid = threadIdx.x;
+  const int par1 = (int)(T1 & 1u);
+  const int xt = sh.xTot[s1];
+  const int* ent = sh.xEnt + (size_t)s1 * R * B;
+  const int* it = sh.xItem + (size_t)s1 * R * B;
+  const float* Tb = sh.Wx[sh.rank];
+  for (int j = hb; j < xt; j += nh) {
+    const int e = ent[j], r = e >> 16, b = e & 0xffff;
+    const float* row = Tb + (size_t)(it[j] / R) * ld3;
+    float* dst = sh.mgInLL[r] + ((size_t)par1 * B + b) * ld3 * 2;
+    for (int q4 = tid; q4 < ld3 / 4; q4 += FK_THREADS) ll_store4(dst + q4 * 8, __ldcg(reinterpret_cast<const float4*>(row + q4 * 4)), T1);
+  }
+}
+// requester side: lane b's input row of lock step T1 arrives in the LL buffer; copy it to the plain buffer the GRU phases read
+__device__ __forceinline__ void mgs_receive_input(const ModelDev& md, FastSmemMG& sm, int s1, int b, unsigned int T1) {
+  const ShardDev& sh = sm.sh;
+  const int ld3 = md.layer[0].ld3;
+  if (b >= md.wM[s1]) return;
+  const float* src = sh.mgInLL[sh.rank] + ((size_t)(T1 & 1u) * md.B + b) * ld3 * 2;
+  for (int q4 = threadIdx.x; q4 < ld3 / 4; q4 += FK_THREADS) st4(sh.mgIn + (size_t)b * ld3 + q4 * 4, ll_load4(src + q4 * 8, T1, sh.abort));
 }
 
 // dense gradients of this GRU CTA's slab, summed over the ranks (pushed to every peer, added in rank order), then Adagrad(+momentum)
@@ -256,19 +320,30 @@ __device__ void fk_dense_mg(const ModelDev& md, FastSmemMG& sm, int s, int cta, 
   const int t4 = (total + 3) / 4;
   for (int i = tid; i < (R - 1) * t4; i += FK_THREADS) {
     const int qi = i / t4, q = qi < me ? qi : qi + 1, c4 = i % t4;
-    st4(sh.denseIn[q] + ((size_t)(par * R + me) * FK_G + cta) * sh.DSL + c4 * 4, ld4(sGd + c4 * 4));
+    ll_store4(sh.denseIn[q] + (((size_t)(par * R + me) * FK_G + cta) * sh.DSL + c4 * 4) * 2, ld4(sGd + c4 * 4), T);
   }
-  __syncthreads();
-  if (tid < 32) {
-    if (tid < R && tid != me) st_release_sys_u32(sh.flags[tid] + (size_t)(MGF_DENSE + me * FK_G + cta) * MGS_FLAG_STRIDE, T);
-    if (tid < R && tid != me) wait_sys_ge(sh.flags[me] + (size_t)(MGF_DENSE + tid * FK_G + cta) * MGS_FLAG_STRIDE, T, sh.abort);
-  }
-  __syncthreads();
   const bool ada = md.adapt == G4R_ADAPT_ADAGRAD, mom = md.mom > 0.f;
-  const float* din = sh.denseIn[me] + (size_t)par * R * FK_G * sh.DSL + (size_t)cta * sh.DSL;
+  const float* din = sh.denseIn[me] + ((size_t)par * R * FK_G * sh.DSL + (size_t)cta * sh.DSL) * 2;
   for (int o = tid; o < total; o += FK_THREADS) {
+    // the R - 1 peer slices of this output: all pair loads are issued back to back (independent), then the sequences are checked;
+    // only the pairs that have not arrived yet are polled again
+    uint2 pr[MGS_MAXR];
+    unsigned int pending = 0;
+#pragma unroll
+    for (int q = 0; q < MGS_MAXR; q++) {
+      pr[q] = make_uint2(0u, T);
+      if (q < R && q != me) asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(pr[q].x), "=r"(pr[q].y) : "l"(din + ((size_t)q * FK_G * sh.DSL + o) * 2) : "memory");
+    }
+#pragma unroll
+    for (int q = 0; q < MGS_MAXR; q++) if (q < R && q != me && pr[q].y != T) pending |= 1u << q;
+    if (pending) {
+#pragma unroll
+      for (int q = 0; q < MGS_MAXR; q++)
+        if (pending & (1u << q)) pr[q].x = __float_as_uint(ll_load1(din + ((size_t)q * FK_G * sh.DSL + o) * 2, T, sh.abort));
+    }
     float g = 0.f;
-    for (int q = 0; q < R; q++) g += (q == me) ? sGd[o] : __ldcg(din + (size_t)q * FK_G * sh.DSL + o);
+#pragma unroll
+    for (int q = 0; q < MGS_MAXR; q++) if (q < R) g += (q == me) ? sGd[o] : __uint_as_float(pr[q].x);      // rank order: identical on every rank
     float *p, *pa, *pv;
     if (o < nWh) { const size_t off = (size_t)(k0 + o / L) * ldL + o % L; p = ly.Wh + off; pa = ly.Wh_acc ? ly.Wh_acc + off : nullptr; pv = ly.Wh_vel ? ly.Wh_vel + off : nullptr; }
     else if (o < nWh + nWrz) { const int q = o - nWh; const size_t off = (size_t)(k0 + q / (2 * L)) * ly.ld2 + q % (2 * L); p = ly.Wrz + off; pa = ly.Wrz_acc ? ly.Wrz_acc + off : nullptr; pv = ly.Wrz_vel ? ly.Wrz_vel + off : nullptr; }
@@ -284,7 +359,7 @@ __device__ void fk_dense_mg(const ModelDev& md, FastSmemMG& sm, int s, int cta, 
 // ---------------------------------------------------------------------------------------------------------------------
 // the sharded role-specialised kernel: one cooperative launch per window on every rank
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(FK_THREADS, 1) k_fast_mg(int slot, int n_steps, FastSync* fs, FastSyncMG* fm, const ShardDev* shp, unsigned int gbase) {
+__global__ void __launch_bounds__(FK_THREADS, 1) k_fast_mg(int slot, int n_steps, FastSync* fs, FastSyncMG* fm, const ShardDev* shp, unsigned int gbase, unsigned long long* tstamp) {
   extern __shared__ __align__(128) unsigned char fk_raw[];
   FastSmemMG& sm = *reinterpret_cast<FastSmemMG*>(fk_raw);
   const ModelDev& md = MD;
@@ -316,6 +391,8 @@ __global__ void __launch_bounds__(FK_THREADS, 1) k_fast_mg(int slot, int n_steps
   const bool applier = cta >= A0;
   uint64_t* bar = reinterpret_cast<uint64_t*>(&sm.mbar);
   unsigned int bar_epoch = 0, gepoch = 0, stats_target = 0;
+  // %globaltimer stamps (16 slots per step): GRU CTA 0 -> 0..6, first helper -> 8..13, first apply CTA -> 14..15
+#define MG_STAMP(c_, k) do { if (tstamp && cta == (c_) && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tstamp[(size_t)s * 16 + (k)] = t_; } } while (0)
   if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   if (!gru) {
     fk_load_idx_mg(md, sm, 0, n_steps, chunk, 0);
@@ -347,6 +424,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) k_fast_mg(int slot, int n_steps
     const unsigned int T = gbase + (unsigned int)s + 1u;        // sequence number of this lock step
     const int par = (int)((gbase + (unsigned int)s) & 1u);      // inbox parity
     int cb = 0, nj = 0;
+    MG_STAMP(0, 0);
     if (!gru) {
     fk_load_idx_mg(md, sm, s + 1, n_steps, chunk, buf ^ 1);
     // ---- wait for h(s), stage it; the prefetched rows have landed ----
@@ -551,7 +629,7 @@ __global__ void __launch_bounds__(FK_THREADS, 1) k_fast_mg(int slot, int n_steps
     for (int t = tid; t < nj * (kw + 1); t += FK_THREADS) {
       const int jj = t / (kw + 1), q4 = t % (kw + 1);
       const float4 v = q4 < kw ? ld4(sm.sD + jj * FK_LDS + q4 * 4) : make_float4(sm.sDby[jj], 0.f, 0.f, 0.f);
-      st4(sh.inbox[sm.sOw[buf][jj]] + ((size_t)(par * R + me) * md.NP + (size_t)(cb + jj)) * ldW + q4 * 4, v);
+      ll_store4(sh.inbox[sm.sOw[buf][jj]] + (((size_t)(par * R + me) * md.NP + (size_t)(cb + jj)) * ldW + q4 * 4) * 2, v, T);
     }
     if (has_chunk && nj == 0) for (int i = tid; i < M * ldL; i += FK_THREADS) part[i] = 0.f;
     }   // !gru
@@ -560,70 +638,66 @@ __global__ void __launch_bounds__(FK_THREADS, 1) k_fast_mg(int slot, int n_steps
     bar_epoch += 1;
     if (tid == 0) { red_release_add(&fs->bar, 1u); wait_ge(&fs->bar, bar_epoch * (unsigned int)ncta); }
     __syncthreads();
+    MG_STAMP(0, 1);
     fk_b1<false>(md, sm, s, cta, ncta);
     __syncthreads();
     if (tid == 0) red_release_add(&fs->b1_done, 1u);
-    if (!gru && tid == 0) { __threadfence_system(); red_release_add(&fm->exp_done, 1u); }
     if (gru) {
       if (tid == 0) wait_ge(&fs->b1_done, (unsigned int)(s + 1) * (unsigned int)ncta);
       __syncthreads();
+      MG_STAMP(0, 2);
       fk_b2(md, sm, s, cta);
       fk_group_barrier(fs, gepoch);      // epoch 3 s + 2: dvec complete -> the helper CTAs poll this counter
+      MG_STAMP(0, 3);
       fk_dense_mg(md, sm, s, cta, T, par);
       fk_group_barrier(fs, gepoch);
+      MG_STAMP(0, 4);
       if (s + 1 < n_steps) {
         fk_f1(md, sm, s + 1, cta, &fs->in_done, (unsigned int)(s + 2) * (unsigned int)in_ctas, sh.mgIn);
         fk_group_barrier(fs, gepoch);
+        MG_STAMP(0, 5);
         fk_f2(md, sm, s + 1, cta, sh.mgIn);
         __syncthreads();
         if (tid == 0) red_release_add(&fs->h_ready, 1u);
       }
+      MG_STAMP(0, 6);
     } else if (helper) {
       const int hb = cta - G;
       // dvec rows of the step are complete when the GRU group has passed its (3 s + 2)-th barrier
       if (tid == 0) wait_ge(&fs->grp, (unsigned int)(3 * s + 2) * FK_G);
       __syncthreads();
+      MG_STAMP(G, 8);
       if (hb < M) {
         const int x = md.wX[(size_t)s * B + hb];
-        float* dst = sh.inboxIn[x % R] + ((size_t)(par * R + me) * B + hb) * ly.ld3;
-        for (int q4 = tid; q4 < ly.ld3 / 4; q4 += FK_THREADS) st4(dst + q4 * 4, ld4(ly.dvec + (size_t)hb * ly.ld3 + q4 * 4));
+        float* dst = sh.inboxIn[x % R] + (((size_t)(par * R + me) * B + hb) * ly.ld3) * 2;
+        for (int q4 = tid; q4 < ly.ld3 / 4; q4 += FK_THREADS) ll_store4(dst + q4 * 8, ld4(ly.dvec + (size_t)hb * ly.ld3 + q4 * 4), T);
       }
+      MG_STAMP(G, 9);
+      mgs_apply_inputs(md, sm, s, hb, in_ctas, par, T);       // polls the (value, sequence) pairs of the rows it needs
       __syncthreads();
-      if (tid == 0) { __threadfence_system(); red_release_add(&fm->h1, 1u); }
-      if (hb < R && tid == 0) {
-        wait_ge_abortable(&fm->h1, (unsigned int)(s + 1) * (unsigned int)in_ctas, sh.abort);
-        st_release_sys_u32(sh.flags[hb] + (size_t)(MGF_IN + me) * MGS_FLAG_STRIDE, T);
-      }
-      mgs_wait_flags(sh, MGF_IN, -1, T);
+      MG_STAMP(G, 10);
+      if (tid == 0) { red_release_add(&fm->h2, 1u); wait_ge_abortable(&fm->h2, (unsigned int)(s + 1) * (unsigned int)in_ctas, sh.abort); }
       __syncthreads();
-      mgs_apply_inputs(md, sm, s, hb, in_ctas, par);
-      __syncthreads();
-      if (tid == 0) red_release_add(&fm->h2, 1u);
-      if (hb < R && tid == 0) {
-        wait_ge_abortable(&fm->h2, (unsigned int)(s + 1) * (unsigned int)in_ctas, sh.abort);
-        st_release_sys_u32(sh.flags[hb] + (size_t)(MGF_INAPPLIED + me) * MGS_FLAG_STRIDE, T);
-      }
+      MG_STAMP(G, 11);
       if (s + 1 < n_steps) {
-        mgs_wait_flags(sh, MGF_INAPPLIED, -1, T);
-        __syncthreads();
-        mgs_gather_input(md, sm, s + 1, hb);
+        mgs_push_inputs(md, sm, s + 1, hb, in_ctas, T + 1u);   // owned rows of the next mini-batch -> their requesters
+        MG_STAMP(G, 12);
+        mgs_receive_input(md, sm, s + 1, hb, T + 1u);
         __syncthreads();
         if (tid == 0) red_release_add(&fs->in_done, 1u);
+        MG_STAMP(G, 13);
       }
+      if (hb < R && tid == 0) st_release_sys_u32(sh.flags[hb] + (size_t)(MGF_INAPPLIED + me) * MGS_FLAG_STRIDE, T);   // next window's prologue gathers after this
       mgs_wait_flags(sh, MGF_APPLIED, -1, T);
       __syncthreads();
       fk_prefetch_mg(md, sm, s + 1, n_steps, buf ^ 1, pw);
     } else if (applier) {
       const int a = cta - A0;
-      if (a < R && tid == 0) {          // all CTAs of this rank have fenced their exports: tell owner `a`
-        wait_ge_abortable(&fm->exp_done, (unsigned int)(s + 1) * (unsigned int)(ncta - G), sh.abort);
-        st_release_sys_u32(sh.flags[a] + (size_t)(MGF_ROWS + me) * MGS_FLAG_STRIDE, T);
-      }
-      mgs_wait_flags(sh, MGF_ROWS, -1, T);
-      __syncthreads();
-      mgs_apply_rows(md, sm, s, a, par);
+      MG_STAMP(A0, 14);
+      mgs_apply_rows(md, sm, s, a, par, T);       // polls the (value, sequence) pairs of the gradient rows it needs
       __syncthreads();
       if (tid == 0) red_release_add(&fm->apply_done, 1u);
+      MG_STAMP(A0, 15);
       if (a < R && tid == 0) {
         wait_ge_abortable(&fm->apply_done, (unsigned int)(s + 1) * (unsigned int)NA, sh.abort);
         st_release_sys_u32(sh.flags[a] + (size_t)(MGF_APPLIED + me) * MGS_FLAG_STRIDE, T);
@@ -740,7 +814,7 @@ __global__ void __launch_bounds__(256) k_mgs_plan2(MgsPlan p, int n_steps) {
 // host side
 // ---------------------------------------------------------------------------------------------------------------------
 struct ShardSeg {                       // offsets (bytes) inside the peer-mapped segment; identical on every rank
-  size_t W = 0, W_acc = 0, W_vel = 0, Wx = 0, Wx_acc = 0, Wx_vel = 0, inbox = 0, inboxIn = 0, denseIn = 0, flags = 0, total = 0;
+  size_t W = 0, W_acc = 0, W_vel = 0, Wx = 0, Wx_acc = 0, Wx_vel = 0, inbox = 0, inboxIn = 0, denseIn = 0, mgInLL = 0, flags = 0, total = 0;
   int rows_local = 0, ldW = 0, DSL = 0;
 };
 struct ShardHost {
@@ -757,7 +831,7 @@ struct ShardHost {
 
 static bool shard_eligible(const g4r_config& c, int n_sm) {
   if (c.world_size < 2 || c.world_size > MGS_MAXR) return false;
-  if (c.reserved[0] == 1) return false;                         // caller forces the replicated NCCL path
+  if (c.mg_replicated == 1) return false;                         // caller forces the replicated NCCL path
   if (c.constrained_embedding || c.embedding > 0 || c.n_layers != 1) return false;
   const int L = c.layers[0], B = c.batch_size, R = c.world_size;
   if (round4(L) > 124 || B > FK_B || 2 * L > FK_W1 * FK_G || L > FK_W2 * FK_G) return false;
@@ -765,6 +839,7 @@ static bool shard_eligible(const g4r_config& c, int n_sm) {
   if (n_sm < FK_G + std::min(B, n_sm - FK_G - R) + R) return false;
   if ((long long)c.world_size * c.n_items >= (1ll << 31)) return false;
   if (c.adapt != G4R_ADAPT_ADAGRAD && c.adapt != G4R_ADAPT_NONE) return false;
+  if (c.grad_cap > 0.f || c.smoothing > 0.f) return false;
   if (c.step_mode != 2) return false;
   const int gen_len = (c.n_sample > 0 && c.sample_store > 0) ? c.sample_store / c.n_sample : 0;
   const int NP = round4(B + (gen_len > 1 ? c.n_sample : 0));
@@ -788,9 +863,10 @@ static ShardSeg shard_segment(const g4r_config& c) {
   const size_t tw = (size_t)sg.rows_local * sg.ldW * 4, tx = (size_t)sg.rows_local * ld3 * 4;
   sg.W = take(tw); sg.W_acc = ada ? take(tw) : 0; sg.W_vel = mom ? take(tw) : 0;
   sg.Wx = take(tx); sg.Wx_acc = ada ? take(tx) : 0; sg.Wx_vel = mom ? take(tx) : 0;
-  sg.inbox = take((size_t)2 * R * NP * sg.ldW * 4);
-  sg.inboxIn = take((size_t)2 * R * B * ld3 * 4);
-  sg.denseIn = take((size_t)2 * R * FK_G * sg.DSL * 4);
+  sg.inbox = take((size_t)2 * R * NP * sg.ldW * 8);          // (value, sequence) pairs
+  sg.inboxIn = take((size_t)2 * R * B * ld3 * 8);
+  sg.denseIn = take((size_t)2 * R * FK_G * sg.DSL * 8);
+  sg.mgInLL = take((size_t)2 * B * ld3 * 8);
   sg.flags = take((size_t)MGF_COUNT * MGS_FLAG_STRIDE * 4);
   sg.total = align_up(off, 256);
   return sg;
@@ -841,6 +917,7 @@ extern "C" int g4r_mg_ipc_open(g4r_handle* h, const char* handles, int32_t world
     d.W[q] = (float*)(sh->peer[q] + sh->seg.W); d.Wx[q] = (float*)(sh->peer[q] + sh->seg.Wx);
     d.inbox[q] = (float*)(sh->peer[q] + sh->seg.inbox); d.inboxIn[q] = (float*)(sh->peer[q] + sh->seg.inboxIn);
     d.denseIn[q] = (float*)(sh->peer[q] + sh->seg.denseIn); d.flags[q] = (unsigned int*)(sh->peer[q] + sh->seg.flags);
+    d.mgInLL[q] = (float*)(sh->peer[q] + sh->seg.mgInLL);
   }
   CK(cudaMemcpyAsync(sh->dDev, &d, sizeof(ShardDev), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -858,7 +935,7 @@ extern "C" int g4r_mg_segment_bytes(const g4r_config* cfg, size_t* total, size_t
   if (total) *total = sg.total;
   if (inbox_bytes) *inbox_bytes = sg.inboxIn - sg.inbox;
   if (inbox_in_bytes) *inbox_in_bytes = sg.denseIn - sg.inboxIn;
-  if (dense_bytes) *dense_bytes = sg.flags - sg.denseIn;
+  if (dense_bytes) *dense_bytes = sg.mgInLL - sg.denseIn;
   return G4R_OK;
 }
 
@@ -893,7 +970,8 @@ static int mgs_run_window(g4r_handle* h, int64_t n) {
   CK(cudaMemsetAsync(h->dFastSync, 0, sizeof(FastSync), st));
   CK(cudaMemsetAsync(sh->dSync, 0, sizeof(FastSyncMG), st));
   int slot = h->slot, nst = (int)n; FastSync* fsp = h->dFastSync; FastSyncMG* fmp = sh->dSync; const ShardDev* sdp = sh->dDev; unsigned int gbase = sh->lock_steps;
-  void* args[] = {&slot, &nst, &fsp, &fmp, &sdp, &gbase};
+  unsigned long long* ts = h->stamp_on ? h->dStamp : nullptr;
+  void* args[] = {&slot, &nst, &fsp, &fmp, &sdp, &gbase, &ts};
   CK(cudaLaunchCooperativeKernel((void*)k_fast_mg, dim3(h->pk_blocks), dim3(FK_THREADS), args, sizeof(FastSmemMG), st));
   h->launches += 1; h->fast_windows++;
   sh->lock_steps += (unsigned int)n;

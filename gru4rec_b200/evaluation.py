@@ -4,15 +4,15 @@ import pandas as pd
 
 from . import _lib
 
-_MODES = {'standard': 0, 'conservative': 1, 'median': 2, 'tiebreaking': 0}
+_MODES = {'standard': 0, 'conservative': 1, 'median': 2, 'tiebreaking': 3}
 
 
 def evaluate_gpu(gru, test_data, items=None, session_key='SessionId', item_key='ItemId', time_key='Time', cut_off=[20], batch_size=100, mode='standard'):
     '''
     Recall@N and MRR@N of next-item prediction, session-parallel (evaluation.py:15-147).
-    Returns (recall_list, mrr_list), one entry per cut-off.  `mode` as in the reference; 'tiebreaking' adds
-    U(0,1)*1e-10 noise in the reference, which is below float32 resolution for scores > 1e-3 -- it is evaluated as
-    'standard' here.  `items`: the targets are ranked against these item ids only (evaluation.py:52-56,84-100); as in the
+    Returns (recall_list, mrr_list), one entry per cut-off.  `mode` as in the reference; 'tiebreaking' adds U(0,1)*1e-10 to
+    every score before the standard ranking (evaluation.py:55,65) -- it only matters where scores saturate at (near) zero; the
+    noise is a counter hash on the device (the reference's comes from Theano's MRG stream).  `items`: the targets are ranked against these item ids only (evaluation.py:52-56,84-100); as in the
     reference the target's own score competes only if the target is listed, so 'conservative' can give rank 0 (MRR = inf).
     '''
     if gru.error_during_train: raise Exception

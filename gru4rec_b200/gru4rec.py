@@ -38,10 +38,10 @@ class GRU4Rec:
                  adapt='adagrad', adapt_params=[], grad_cap=0.0, bpreg=1.0, logq=0.0,
                  sigma=0.0, init_as_normal=False, train_random_order=False, time_sort=True,
                  session_key='SessionId', item_key='ItemId', time_key='Time')
-    Same parameters as the reference class (gru4rec.py:28-96).  Options that only exist as Theano graph variants
-    and are unused by every shipped parameter file (adapt in {'rmsprop','adam','adadelta'}, grad_cap, smoothing,
-    loss/final_act pairs other than {cross-entropy+softmax, xe_logit+softmax_logit, pairwise losses + elementwise
-    activations}) raise NotImplementedError when fit() builds the engine.
+    Same parameters as the reference class (gru4rec.py:28-96), all optimizers (adagrad / rmsprop / adadelta / adam / None),
+    grad_cap and smoothing included.  Not on the device path (NotImplementedError when fit() builds the engine): loss /
+    final_act pairs other than {cross-entropy+softmax, xe_logit+softmax_logit, pairwise losses + elementwise activations},
+    and rmsprop / adadelta / adam together with constrained_embedding.
     '''
 
     def __init__(self, loss='bpr-max', final_act='linear', hidden_act='tanh', layers=[100],
@@ -219,13 +219,8 @@ class GRU4Rec:
         optimiser options are irrelevant there, so a model the reference trained with adam / rmsprop / adadelta, grad_cap or
         smoothing can still be scored; fit() with those options raises NotImplementedError."""
         cfg = _lib.G4RConfig()
-        if training:
-            if self.adapt not in _lib.ADAPT:
-                raise NotImplementedError('adapt=%r is not implemented on the device path' % (self.adapt,))
-            if self.grad_cap:
-                raise NotImplementedError('grad_cap is not implemented on the device path')
-            if self.smoothing:
-                raise NotImplementedError('smoothing is not implemented on the device path')
+        if training and self.adapt not in _lib.ADAPT:
+            raise NotImplementedError('adapt=%r is not an optimizer of the reference (gru4rec.py:392-399)' % (self.adapt,))
         cfg.n_items = self.n_items
         cfg.n_layers = len(self.layers)
         for i, l in enumerate(self.layers):
@@ -250,6 +245,7 @@ class GRU4Rec:
         cfg.sample_store = int(sample_store)
         cfg.dropout_seed = self.dropout_seed
         cfg.mrg_seed = 12345
+        _lib.set_adapt_params(cfg, self.adapt if training else None, self.adapt_params if training else [], self.grad_cap if training else 0.0)
         cfg.max_resident_steps = 0
         cfg.world_size, cfg.rank = (1, 0) if single else self._world()
         cfg.eval_batch_size = eval_lanes
@@ -382,6 +378,9 @@ class GRU4Rec:
             else:
                 # the reference's device path has no per-step sampler: its loop dereferences an undefined sample pointer here
                 raise NotImplementedError('n_sample > 0 needs a sample store when store_type is \'gpu\' (sample_store >= 2 * n_sample)')
+        if self.adapt == 'adadelta' and self.learning_rate != 1.0:        # gru4rec.py:362-364
+            print('Warn: learning_rate is not 1.0 while using adadelta. Setting learning_rate to 1.0')
+            self.learning_rate = 1.0
         world, rank = self._world()
         if world > 1 and store_type == 'cpu':
             # the host-side sampler draws from one NumPy stream and refills at rank-local step counts: the lock-step ranks

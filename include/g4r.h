@@ -35,7 +35,7 @@ typedef enum { G4R_LOSS_XE = 0, G4R_LOSS_BPR_MAX = 1, G4R_LOSS_TOP1_MAX = 2, G4R
                G4R_LOSS_XE_LOGIT = 5 } g4r_loss;                       /* gru4rec.py:136-143 */
 typedef enum { G4R_ACT_LINEAR = 0, G4R_ACT_RELU = 1, G4R_ACT_TANH = 2, G4R_ACT_LEAKY = 3, G4R_ACT_ELU = 4,
                G4R_ACT_SELU = 5, G4R_ACT_SOFTMAX = 6, G4R_ACT_SOFTMAX_LOGIT = 7 } g4r_act;   /* gru4rec.py:144-161 */
-typedef enum { G4R_ADAPT_NONE = 0, G4R_ADAPT_ADAGRAD = 1 } g4r_adapt;  /* gru4rec.py:392-399 (others: not on device) */
+typedef enum { G4R_ADAPT_NONE = 0, G4R_ADAPT_ADAGRAD = 1, G4R_ADAPT_RMSPROP = 2, G4R_ADAPT_ADADELTA = 3, G4R_ADAPT_ADAM = 4 } g4r_adapt;  /* gru4rec.py:300-381,392-399 */
 
 /* Mirrors the GRU4Rec constructor arguments that shape the compiled step (gru4rec.py:97-135). */
 typedef struct g4r_config {
@@ -67,7 +67,11 @@ typedef struct g4r_config {
                                      2: role-specialised persistent kernel where the shape allows, else 1;
                                      3: as 2, launched as thread-block clusters: the GRU phases run on one cluster with the
                                         dense weights and optimizer state resident in shared memory (else 1) */
-  int32_t reserved[7];            /* reserved[0] = 1: multi-GPU with replicated tables + NCCL exchange instead of row sharding */
+  int32_t mg_replicated;          /* 1: multi-GPU with replicated tables + NCCL exchange instead of row sharding */
+  int32_t eval_tc;                /* scoring path: 0 auto, 1 fp32 FFMA tiles only, 2 tcgen05 (3xTF32) tiles whenever the ranking is full-catalogue */
+  float adapt_p1, adapt_p1c;      /* adapt_params[0] and 1 - adapt_params[0] (rmsprop / adadelta decay; adam beta1), gru4rec.py:301-304,342-343,368-369 */
+  float adapt_p2, adapt_p2c;      /* adapt_params[1] and 1 - adapt_params[1] (adam beta2) */
+  float grad_cap;                 /* > 0: gradients are scaled to this global L2 norm when they exceed it (gru4rec.py:386-389) */
 } g4r_config;
 
 typedef struct g4r_handle g4r_handle;
@@ -161,7 +165,7 @@ int64_t g4r_kernel_launches(const g4r_handle* h);
 int g4r_mg_unique_id(char* out128);
 int g4r_mg_init(g4r_handle* h, const char* id128);
 /* Row-sharded layout (the default for world_size > 1 when the role-specialised kernel covers the shape: no-embedding mode, one
- * layer of <= 120 units, batch <= 32; cfg.reserved[0] = 1 forces the replicated NCCL path above).  Row i of Wy / By / Wx0 and
+ * layer of <= 120 units, batch <= 32; cfg.mg_replicated = 1 forces the replicated NCCL path above).  Row i of Wy / By / Wx0 and
  * of their optimizer state lives only on rank i % world_size (local row i / world_size) in a library-owned segment that the
  * peers map with cudaIpc; parameter rows are fetched from their owners and gradient rows are stored into the owners' inboxes
  * over NVLink INSIDE the persistent kernel, the owners apply the merged update to their 1/world_size of the rows, and the
@@ -181,7 +185,8 @@ int g4r_mg_segment_bytes(const g4r_config* cfg, size_t* total, size_t* inbox_byt
 
 /* ---- scoring path: evaluate(X, Y, M) (evaluation.py:76,108) and predict (gru4rec.py:706-710) ------- */
 /* Runs a whole evaluation schedule: full-catalogue scores, rank of the target, per-cutoff hit counts and
- * reciprocal-rank sums.  mode: 0 standard, 1 conservative, 2 median (evaluation.py:60-64).
+ * reciprocal-rank sums.  mode: 0 standard, 1 conservative, 2 median, 3 tiebreaking (evaluation.py:55,60-65; the tie-breaking noise U(0,1) * 1e-10 is a
+ * counter hash here, Theano's MRG stream in the reference).
  * recall_sum/mrr_sum: n_cut doubles each (sums, not yet divided by the number of events). */
 int g4r_eval_schedule(g4r_handle* h, const g4r_schedule* s, const int32_t* cut_off, int32_t n_cut, int32_t mode,
                       double* recall_sum, double* mrr_sum, int64_t* n_events);

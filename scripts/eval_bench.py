@@ -13,7 +13,7 @@ import gru4rec as g4
 I, LANES = int(os.environ.get('EV_ITEMS', 37483)), int(os.environ.get('EV_LANES', 512))
 for L in [int(x) for x in os.environ.get('EV_L', '100,512').split(',')]:
     mk = dict(layers=[L], loss='bpr-max', final_act='elu-0.5', batch_size=32, n_sample=2048)
-    items, offset, order, supports = make_session_arrays(I, 400000, seed=1)
+    items, offset, order, supports = make_session_arrays(I, int(os.environ.get('EV_EVENTS', 400000)), seed=1)
     out = {}
     for name, tc in (('ffma', False), ('tcgen05', True)):
         eng = _lib.Engine(_lib.make_config(I, mk, sample_store=0, eval_lanes=LANES, step_mode=1, eval_tc=tc))

@@ -17,7 +17,9 @@ CASES = {
     'bprmax_none': (dict(layers=[24], batch_size=8, n_sample=40, loss='bpr-max', final_act='elu-0.5', learning_rate=0.1, momentum=0.3, sample_alpha=0.0), 90, 40, False),
     'xe_none_drop_l2': (dict(layers=[20], batch_size=16, n_sample=64, loss='cross-entropy', final_act='softmax', learning_rate=0.1, dropout_p_hidden=0.2,
                              lmbd=0.001, logq=1.0), 150, 30, False),
-    'headline_shape': (dict(layers=[100], batch_size=32, n_sample=2048, loss='bpr-max', final_act='elu-0.5', learning_rate=0.2, momentum=0.3, sample_alpha=0.0), 3000, 12, False),
+    # learning rate as in the single-GPU headline-shape test: with 3000 items every item collects dozens of duplicate updates per
+    # lock step, at lr = 0.2 the merged run leaves the stable regime (exp overflow in the oracle) and fp32 noise is amplified
+    'headline_shape': (dict(layers=[100], batch_size=32, n_sample=2048, loss='bpr-max', final_act='elu-0.5', learning_rate=0.05, momentum=0.3, sample_alpha=0.0), 3000, 12, False),
     'bprmax_none_replicated': (dict(layers=[24], batch_size=8, n_sample=40, loss='bpr-max', final_act='elu-0.5', learning_rate=0.1, momentum=0.3, sample_alpha=0.0), 90, 20, True),
     'xe_embed_2layer': (dict(layers=[12, 16], batch_size=6, n_sample=30, loss='cross-entropy', final_act='softmax', embedding=12, learning_rate=0.1,
                              dropout_p_hidden=0.2, dropout_p_embed=0.2, lmbd=0.001), 90, 40, False),

@@ -49,3 +49,24 @@ def test_tensor_core_ranking_equals_oracle():
     np.testing.assert_allclose(r1 / n1, rec, rtol=1e-4, atol=2.0 / n1)
     np.testing.assert_allclose(q1 / n1, mrr, rtol=1e-4, atol=2.0 / n1)
     e_ff.close(); e_tc.close()
+
+
+def test_tiebreaking_mode_breaks_saturated_ties():
+    """mode='tiebreaking' (evaluation.py:55,65): with a relu output most scores saturate at exactly 0; 'standard' ranks the target
+    ahead of every tie, 'conservative' behind, the tie-breaking noise puts it in between (about half of the ties ahead)."""
+    n_items, lanes = 600, 40
+    mk = dict(layers=[16], batch_size=8, n_sample=16, loss='bpr-max', final_act='relu')
+    m = orc.OracleGRU4Rec(**mk)
+    m.init(n_items)
+    m.By[:] = -0.35          # pushes most pre-activations below zero
+    df = make_sessions(n_items=n_items, n_events=2500, seed=11)
+    d = orc.prepare_fit_data(df)
+    eng = _lib.Engine(_lib.make_config(n_items, mk, sample_store=0, eval_lanes=lanes, step_mode=1, eval_tc=False))
+    push_weights(eng, m)
+    sched = _lib.Schedule(d['data_items'] % n_items, d['offset_sessions'], None, lanes, 0, mode=1)
+    cuts = [20, 100, 300]
+    std = eng.eval_schedule(sched, cuts, 0); cons = eng.eval_schedule(sched, cuts, 1); tb = eng.eval_schedule(sched, cuts, 3); tb2 = eng.eval_schedule(sched, cuts, 3)
+    np.testing.assert_array_equal(tb[0], tb2[0])          # deterministic
+    assert (cons[0] <= tb[0]).all() and (tb[0] <= std[0]).all()
+    assert tb[0][1] < std[0][1] and tb[0][1] > cons[0][1], (std[0], tb[0], cons[0])
+    eng.close()

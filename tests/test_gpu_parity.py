@@ -196,7 +196,7 @@ def test_index_errors_and_nan():
 
 
 def test_unsupported_configs_raise():
-    for mk in (dict(loss='cross-entropy', final_act='linear'), dict(loss='bpr-max', final_act='softmax'), dict(smoothing=0.1, loss='cross-entropy', final_act='softmax')):
+    for mk in (dict(loss='cross-entropy', final_act='linear'), dict(loss='bpr-max', final_act='softmax'), dict(adapt='adam', adapt_params=[0.9, 0.999], constrained_embedding=True)):
         with pytest.raises(NotImplementedError):
             small_engine(**mk)
 

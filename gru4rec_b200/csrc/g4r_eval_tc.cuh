@@ -3,7 +3,7 @@
 // What is computed (reference: yhat = h Wy^T + By, gru4rec.py:502; ranks = (others > targets).sum + 1, evaluation.py:57-64):
 // for every lane b of the evaluation batch the number of catalogue items whose score beats / ties the score of the lane's
 // target.  The [items x lanes] score matrix (37,483 x 512 at the RSC15 shape: 3.8 GFLOP per mini-batch, the largest dense
-// contraction of the whole path) is never written: each 128-item x 256-lane tile is accumulated in TMEM by UMMA
+// contraction of the whole path) is never written: each 128-lane x 256-item tile is accumulated in TMEM by UMMA
 // (tcgen05.mma kind::tf32, M = 128, N = 256, K = 8), read back with tcgen05.ld, and reduced to the two counters in registers.
 //
 // fp32 fidelity on TF32 tensor cores: 3xTF32 -- every fp32 operand x is split as hi = tf32(x), lo = tf32(x - hi) and the
@@ -14,18 +14,21 @@
 // Structure (one CTA per SM, 256 threads, persistent over its item tiles):
 //   pre-pass   k_tc_split writes the operands as hi / lo TF32 blocks in the canonical K-major no-swizzle UMMA layout (8 x 16-byte
 //              core matrices): the item table once per evaluation, the hidden states once per mini-batch
-//   warp 4     TMA producer (one thread): two bulk copies (cp.async.bulk -> mbarrier complete_tx) per 32-wide K chunk fill a
+//   warp 8     TMA producer (one thread): two bulk copies (cp.async.bulk -> mbarrier complete_tx) per 32-wide K chunk fill a
 //              96 KB stage [A hi | A lo | B hi | B lo]; two stages
-//   warp 5     MMA issuer (one thread): 12 tcgen05.mma per chunk, tcgen05.commit hands the stage back / publishes the accumulator
-//   warps 0-3  epilogue: wait for the accumulator (2 x 256 TMEM columns, double buffered), tcgen05.ld 32 columns at a time,
-//              bias + final activation + compare with the lane's target score, warp ballots -> per-lane counters
+//   warp 9     MMA issuer (one thread): 12 tcgen05.mma per chunk, tcgen05.commit hands the stage back / publishes the accumulator
+//   warps 0-7  epilogue: wait for the accumulator (2 x 256 TMEM columns, double buffered), tcgen05.ld 32 columns at a time,
+//              bias + final activation + compare with the lane's target score -- a thread owns one evaluation lane (TMEM
+//              lane), so the two counters are thread-local; two warps per lane quarter split the tile's columns
 // All waits are mbarrier try_wait loops with a time-out that sets an error flag (a wrong phase must not hang the box).
 #pragma once
 
-constexpr int TC_M = 128;            // items per tile (UMMA M, TMEM lanes)
-constexpr int TC_N = 256;            // evaluation lanes per tile (UMMA N, TMEM columns per accumulator)
+constexpr int TC_M = 128;            // evaluation lanes per tile (UMMA M, TMEM lanes: one per epilogue thread)
+constexpr int TC_N = 256;            // items per tile (UMMA N, TMEM columns per accumulator)
 constexpr int TC_KC = 32;            // K chunk per pipeline stage (floats)
-constexpr int TC_THREADS = 256;
+constexpr int TC_EPI_WARPS = 8;      // two warps per TMEM lane quarter (each takes half of the tile's columns)
+constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
+constexpr int TC_THREADS = TC_EPI_THREADS + 64;     // + TMA producer warp + MMA issuer warp
 constexpr int TC_STAGES = 2;
 constexpr uint32_t TC_A_BYTES = TC_M * TC_KC * 4;       // 16 KB per hi / lo array
 constexpr uint32_t TC_B_BYTES = TC_N * TC_KC * 4;       // 32 KB
@@ -40,8 +43,7 @@ struct TcSmem {
   unsigned long long acc_free[2];              // epilogue has drained the accumulator (128 arrivals)
   uint32_t tmem_base;
   int err;
-  float sTgt[TC_N];                            // target scores of the lane block
-  int sYit[TC_N];                              // target items of the lane block
+  float sBy[2][TC_N];                          // output bias of the tile's items (per accumulator)
 };
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -109,7 +111,9 @@ __device__ __forceinline__ void tc_bulk_copy(void* sdst, const void* gsrc, uint3
 }
 
 // cnt[b*2 + 0] += #items with score > target score of lane b; cnt[b*2 + 1] += #items with score == target (the target itself
-// counts as one tie, exactly as in the fp32 kernel where its score equals the target score bit for bit)
+// counts as one tie, exactly as in the fp32 kernel where its score equals the target score bit for bit).
+// Tile = 128 evaluation lanes (UMMA M, TMEM lanes: one lane per epilogue thread, so the counting is thread-local) x 256 items
+// (UMMA N, TMEM columns).  Asplit: hidden-state blocks of 128 lanes, Bsplit: item-table blocks of 256 items (k_tc_split).
 __global__ void __launch_bounds__(TC_THREADS, 1) k_eval_tc(int slot, int s, const float* __restrict__ tgt, int* cnt,
                                                            const unsigned char* __restrict__ Asplit, const unsigned char* __restrict__ Bsplit) {
   extern __shared__ __align__(1024) unsigned char tc_raw[];
@@ -117,17 +121,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_eval_tc(int slot, int s, cons
   const ModelDev& md = MD;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int M = md.wM[s], I = md.n_items, K = md.L;
-  const int n_tiles = (I + TC_M - 1) / TC_M;
-  const int n_half = (M + TC_N - 1) / TC_N;
+  const int n_tiles = (I + TC_N - 1) / TC_N;         // item tiles
+  const int n_lb = (M + TC_M - 1) / TC_M;            // lane blocks
   const int n_chunk = (K + TC_KC - 1) / TC_KC;
   if (tid == 0) {
     for (int i = 0; i < TC_STAGES; i++) { tc_mbar_init(&sm.stage_free[i], 1); tc_mbar_init(&sm.stage_full[i], 1); }
-    for (int i = 0; i < 2; i++) { tc_mbar_init(&sm.acc_full[i], 1); tc_mbar_init(&sm.acc_free[i], 128); }
+    for (int i = 0; i < 2; i++) { tc_mbar_init(&sm.acc_full[i], 1); tc_mbar_init(&sm.acc_free[i], TC_EPI_THREADS); }
     sm.err = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (warp == 4) {   // TMEM: 512 columns = two 128 x 256 fp32 accumulators
+  if (warp == TC_EPI_WARPS) {   // TMEM: 512 columns = two 128 x 256 fp32 accumulators
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tc_smem_u32(&sm.tmem_base)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -137,25 +141,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_eval_tc(int slot, int s, cons
   const uint32_t tmem = sm.tmem_base;
   // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 256, M = 128
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-  if (warp == 4) {
+  if (warp == TC_EPI_WARPS) {
     // ================= TMA producer (one thread): operand blocks -> shared memory stages =================
     if (lane == 0) {
       unsigned int it = 0;
-      for (int h = 0; h < n_half; h++)
+      for (int lb = 0; lb < n_lb; lb++)
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
           for (int c = 0; c < n_chunk; c++, it++) {
             const uint32_t st = it & 1u, use = it >> 1;
             if (use > 0) tc_mbar_wait(&sm.stage_free[st], (use - 1) & 1u, &sm.err);     // the MMAs of the previous use are done
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(tc_smem_u32(&sm.stage_full[st])), "r"(TC_STAGE_BYTES) : "memory");
-            tc_bulk_copy(sm.stage[st], Asplit + ((size_t)t * n_chunk + c) * 2 * TC_A_BYTES, 2 * TC_A_BYTES, &sm.stage_full[st]);
-            tc_bulk_copy(sm.stage[st] + 2 * TC_A_BYTES, Bsplit + ((size_t)h * n_chunk + c) * 2 * TC_B_BYTES, 2 * TC_B_BYTES, &sm.stage_full[st]);
+            tc_bulk_copy(sm.stage[st], Asplit + ((size_t)lb * n_chunk + c) * 2 * TC_A_BYTES, 2 * TC_A_BYTES, &sm.stage_full[st]);
+            tc_bulk_copy(sm.stage[st] + 2 * TC_A_BYTES, Bsplit + ((size_t)t * n_chunk + c) * 2 * TC_B_BYTES, 2 * TC_B_BYTES, &sm.stage_full[st]);
           }
     }
-  } else if (warp == 5) {
+  } else if (warp == TC_EPI_WARPS + 1) {
     // ================= MMA issuer (one thread) =================
     if (lane == 0) {
       unsigned int it = 0, wi = 0;
-      for (int h = 0; h < n_half; h++)
+      for (int lb = 0; lb < n_lb; lb++)
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, wi++) {
           const uint32_t acc = wi & 1u;
           if (wi >= 2) tc_mbar_wait(&sm.acc_free[acc], ((wi >> 1) - 1) & 1u, &sm.err);   // epilogue drained this accumulator
@@ -177,37 +181,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_eval_tc(int slot, int s, cons
           }
         }
     }
-  } else if (warp >= 6) {
-    // idle warps
-  } else {
-    // ================= epilogue: TMEM -> registers -> counters =================
+  } else if (warp < TC_EPI_WARPS) {
+    // ================= epilogue: TMEM -> registers -> thread-local counters =================
+    // warp w reads TMEM lanes 32 * (w % 4) .. + 31 (its evaluation lanes) and the column half w / 4 of the tile
     unsigned int wi = 0;
-    bool ok = true;
     const bool elem_act = md.fact.kind <= G4R_ACT_SELU;
-    for (int h = 0; h < n_half && ok; h++) {
-      const int b0 = h * TC_N;
-      asm volatile("bar.sync 2, 128;" ::: "memory");      // previous lane block's sTgt / sYit no longer read
-      for (int i = tid; i < TC_N; i += 128) {
-        const bool v = b0 + i < M;
-        sm.sTgt[i] = v ? tgt[b0 + i] : 0.f;
-        sm.sYit[i] = v ? md.wY[(size_t)s * md.B + b0 + i] : -1;
-      }
-      asm volatile("bar.sync 2, 128;" ::: "memory");
-      int cgt[TC_N / 32], ceq[TC_N / 32];
-#pragma unroll
-      for (int q = 0; q < TC_N / 32; q++) { cgt[q] = 0; ceq[q] = 0; }
-      for (int t = blockIdx.x; t < n_tiles && ok; t += gridDim.x, wi++) {
+    const int q4 = warp & 3, half = warp >> 2;
+    for (int lb = 0; lb < n_lb; lb++) {
+      const int b = lb * TC_M + q4 * 32 + lane;
+      const bool vrow = b < M;
+      const float tg = vrow ? tgt[b] : 0.f;
+      const int yit = vrow ? md.wY[(size_t)s * md.B + b] : -1;
+      int cgt = 0, ceq = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, wi++) {
         const uint32_t acc = wi & 1u;
-        const int item = t * TC_M + warp * 32 + lane;      // this thread's row of the tile (TMEM lane 32 * warp + lane)
-        const bool vrow = item < I;
-        const float by = vrow ? md.By[item] : 0.f;
-        ok = tc_mbar_wait(&sm.acc_full[acc], (wi >> 1) & 1u, &sm.err);
-        if (!ok) break;
+        const int i0 = t * TC_N;
+        {   // bias of the tile's items (double buffered with the accumulator)
+          const int e = tid;                     // 256 epilogue threads <-> 256 items
+          sm.sBy[acc][e] = (i0 + e < I) ? md.By[i0 + e] : 0.f;
+        }
+        tc_mbar_wait(&sm.acc_full[acc], (wi >> 1) & 1u, &sm.err);
+        asm volatile("bar.sync 2, 256;" ::: "memory");       // sBy of this tile complete
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-        for (int q = 0; q < TC_N / 32; q++) {
+        const int self_col = yit - i0;                       // the target's own column (if it falls into this tile)
+        const int n_valid = min(TC_N, I - i0);
+#pragma unroll 1
+        for (int q = 0; q < 4; q++) {
+          const int c0 = half * 128 + q * 32;
           uint32_t r[32];
-          const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + acc * TC_N + q * 32;
+          const uint32_t taddr = tmem + ((uint32_t)(q4 * 32) << 16) + acc * TC_N + c0;
           asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
@@ -217,30 +219,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_eval_tc(int slot, int s, cons
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int j = 0; j < 32; j++) {
-            const int n = q * 32 + j;
-            float sc = __uint_as_float(r[j]) + by;
+            const int n = c0 + j;
+            float sc = __uint_as_float(r[j]) + sm.sBy[acc][n];
             if (elem_act) sc = act_fwd(md.fact, sc);
-            const float tg = sm.sTgt[n];
-            const bool self = vrow && sm.sYit[n] == item;
-            const bool live = vrow && !self && (b0 + n < M);
-            const unsigned int mg = __ballot_sync(0xffffffffu, live && sc > tg);
-            const unsigned int me = __ballot_sync(0xffffffffu, self || (live && sc == tg));
-            if (lane == j) { cgt[q] += __popc(mg); ceq[q] += __popc(me); }
+            const bool self = n == self_col;
+            const bool live = !self && n < n_valid;
+            cgt += (live && sc > tg) ? 1 : 0;
+            ceq += (self || (live && sc == tg)) ? 1 : 0;
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         tc_mbar_arrive(&sm.acc_free[acc]);
       }
-#pragma unroll
-      for (int q = 0; q < TC_N / 32; q++) {
-        const int b = b0 + q * 32 + lane;
-        if (b < M) { if (cgt[q]) atomicAdd(&cnt[b * 2], cgt[q]); if (ceq[q]) atomicAdd(&cnt[b * 2 + 1], ceq[q]); }
-      }
+      if (vrow) { if (cgt) atomicAdd(&cnt[b * 2], cgt); if (ceq) atomicAdd(&cnt[b * 2 + 1], ceq); }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 4) {
+  if (warp == TC_EPI_WARPS) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
   }

@@ -8,6 +8,7 @@ only to allocate the device workspace.  There is no CPU fallback.
 """
 import pickle
 import time
+import weakref
 from collections import OrderedDict  # noqa: F401  (param files use it)
 
 import numpy as np
@@ -21,14 +22,14 @@ class _DeviceParam(object):
     """Stand-in for a Theano shared variable: get_value()/set_value() round-trip through the engine."""
 
     def __init__(self, owner, name):
-        self._owner = owner
+        self._owner = weakref.ref(owner)     # no reference cycle: the model (and its device engine) is freed by reference counting
         self.name = name
 
     def get_value(self, borrow=False):
-        return self._owner._get_param(self.name)
+        return self._owner()._get_param(self.name)
 
     def set_value(self, value, borrow=False):
-        self._owner._set_param(self.name, value)
+        self._owner()._set_param(self.name, value)
 
 
 class GRU4Rec:
@@ -340,12 +341,16 @@ class GRU4Rec:
         '''
         self.predict = None
         self.error_during_train = False
-        itemids = data[self.item_key].unique()
+        # id map in order of first appearance, item index column, supports -- one factorize + one bincount (same values as the
+        # reference's unique() / Series lookup / groupby().size() chain, gru4rec.py:534-545)
+        codes, itemids = pd.factorize(data[self.item_key].values)
+        if (codes < 0).any():
+            raise KeyError('missing item id in the training data')
         self.n_items = len(itemids)
         self.itemidmap = pd.Series(data=np.arange(self.n_items), index=itemids, name='ItemIdx')
-        data['ItemIdx'] = self.itemidmap[data[self.item_key].values].values
+        data['ItemIdx'] = codes.astype(np.int64)
         offset_sessions = self.init(data)
-        pop = data.groupby(self.item_key).size()
+        pop = pd.Series(np.bincount(data['ItemIdx'].values, minlength=self.n_items), index=self.itemidmap.index.values)
         P0 = None
         if self.logq:
             P0 = pop[self.itemidmap.index.values].values.astype(np.float32)
@@ -398,7 +403,8 @@ class GRU4Rec:
                 print('Created sample store with {} batches of samples (type=GPU)'.format(generate_length))
             else:
                 eng.set_sample_store(self.generate_neg_samples(pop, generate_length))
-        base_order = np.argsort(data.groupby(self.session_key)[self.time_key].min().values) if self.time_sort else np.arange(len(offset_sessions) - 1)
+        # first event time of every session = the time at its offset (the frame is sorted by session, time) -- gru4rec.py:585
+        base_order = np.argsort(data[self.time_key].values[offset_sessions[:-1]]) if self.time_sort else np.arange(len(offset_sessions) - 1)
         data_items = data.ItemIdx.values
         # under torchrun: synchronous data parallelism, every rank trains a shard of the sessions
         sched = None

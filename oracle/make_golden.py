@@ -33,6 +33,21 @@ from gru4rec_b200.synth import make_sessions, train_test_split
 
 CONFIGS = {
     # name: (data kwargs, model kwargs, fit kwargs)
+    # BASELINE.json configs[1] at its real shape: B = 32, GRU(100), BPR-max, 2048 negative samples (param_samples/rsc15_bpr-max.py), 66 mini-batches
+    'bprmax_headline_shape': (dict(n_items=1500, n_events=3600, seed=21),
+                              dict(loss='bpr-max', final_act='elu-0.5', hidden_act='tanh', layers=[100], batch_size=32, n_epochs=1,
+                                   learning_rate=0.05, momentum=0.3, n_sample=2048, sample_alpha=0.0, bpreg=1.0),     # lr: stable with ~1.4 duplicates per item and step
+                              dict(sample_store=2048 * 80)),
+    # the shape family of configs[2] (paramfiles/rees46_xe_shared_best.py: shared embedding, XE + logQ, momentum 0), dropout off for the CUDA replay
+    'xe_shared_logq_l64_b48': (dict(n_items=300, n_events=2400, seed=22),
+                               dict(loss='cross-entropy', final_act='softmax', layers=[64], batch_size=48, n_epochs=1, constrained_embedding=True,
+                                    learning_rate=0.065, momentum=0.0, n_sample=256, sample_alpha=0.5, bpreg=0.0, logq=1.0),
+                               dict(sample_store=256 * 40)),
+    # the shape family of configs[3] (paramfiles/retailrocket_bprmax_shared_best.py with three layers), dropout off for the CUDA replay
+    'bprmax_shared_3x32_b16': (dict(n_items=200, n_events=1500, seed=23),
+                               dict(loss='bpr-max', final_act='elu-0.5', layers=[32, 32, 32], batch_size=16, n_epochs=1, constrained_embedding=True,
+                                    learning_rate=0.05, momentum=0.4, n_sample=128, sample_alpha=0.4, bpreg=1.95),
+                               dict(sample_store=128 * 70)),
     'bprmax_none': (dict(n_items=60, n_events=700, seed=1),
                     dict(loss='bpr-max', final_act='elu-0.5', hidden_act='tanh', layers=[12], batch_size=6, n_epochs=2,
                          learning_rate=0.2, momentum=0.3, n_sample=16, sample_alpha=0.0, bpreg=1.0),

@@ -27,3 +27,11 @@ def pytest_collection_modifyitems(config, items):
     for it in items:
         if 'gpu' in it.keywords:
             it.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _release_device_engines():
+    """every live g4r handle owns a constant-memory slot of the library (24 per process): drop unreachable engines between tests"""
+    yield
+    import gc
+    gc.collect()

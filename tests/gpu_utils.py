@@ -101,3 +101,11 @@ def oracle_multi_step(m, Hs, inputs):
             Hs[r][i][inp['slots']] = Cs[r]['H_new'][i]
     m.step_count += 1
     return costs
+
+
+def assert_step_costs(costs, ref, err_msg=''):
+    """Per-mini-batch costs of a whole trajectory at the north-star tolerance (1e-4 relative, every step).  fp32 rounding alone
+    stays two orders of magnitude below it (tests/test_oracle_grads.py::test_fp32_trajectory_noise_level)."""
+    costs = np.asarray(costs); ref = np.asarray(ref)
+    assert costs.shape == ref.shape, (costs.shape, ref.shape)
+    np.testing.assert_allclose(costs, ref, rtol=1e-4, atol=1e-6, err_msg=err_msg)

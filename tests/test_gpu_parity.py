@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import gru4rec_oracle as orc
 from gru4rec_b200 import _lib
-from gpu_utils import make_cfg, make_pair, compare_weights, compare_opt_state
+from gpu_utils import assert_step_costs, make_cfg, make_pair, compare_weights, compare_opt_state
 
 pytestmark = pytest.mark.gpu
 
@@ -129,7 +129,7 @@ def test_shrinking_batch_and_slots(step_mode):
     assert sched.n_steps == len(steps) and steps[-1]['M'] < 8
     costs = eng.train_steps(sched, 0, sched.n_steps)
     ref = [m.train_step(st['X'], st['Y'], st['R'], samples=store[k], slots=st['slots']) for k, st in enumerate(steps)]
-    np.testing.assert_allclose(costs, ref, rtol=2e-4, atol=1e-6)
+    assert_step_costs(costs, ref)
     compare_weights(eng, m, rtol=3e-3, atol=3e-5)
 
 
@@ -172,12 +172,45 @@ def test_headline_shape_role_specialised_kernel(loss, fact, alpha, extra, step_m
     n = 14
     costs = np.concatenate([eng.train_steps(sched, 0, 9), eng.train_steps(sched, 9, n - 9)])
     ref = [m.train_step(st['X'], st['Y'], st['R'], samples=store[k], slots=st['slots']) for k, st in enumerate(steps[:n])]
-    np.testing.assert_allclose(costs, ref, rtol=2e-4, atol=1e-6)
+    assert_step_costs(costs, ref)
     compare_weights(eng, m, rtol=2e-3, atol=2e-5, what='headline shape')
     fast, fallback = eng.fast_windows()
     if step_mode == 2 and mk['layers'][0] > 120:
         assert fast == 0 and fallback >= 1   # the 48-CTA GRU group covers 240 gate columns: wider layers run the generic persistent kernel
     elif alpha == 0.0:
+        assert fast >= 1 and fallback == 0
+    else:
+        assert fast + fallback >= 1      # popularity sampling can create duplicate groups wider than a chunk -> generic kernel
+
+
+@pytest.mark.parametrize('alpha', [0.0, 0.5])
+def test_headline_workload_full_catalogue(alpha):
+    """The benched workload itself: I = 37,483 items, B = 32, GRU(100), BPR-max, 2048 samples, momentum (BASELINE configs[1]),
+    negatives drawn by the device sampler from the uniform (alpha = 0) and the popularity-based (alpha = 0.5) distribution."""
+    from gru4rec_b200.synth import make_session_arrays
+    from gpu_utils import push_weights
+    n_items = 37483
+    mk = dict(layers=[100], batch_size=32, n_sample=2048, loss='bpr-max', final_act='elu-0.5', learning_rate=0.2, momentum=0.3, sample_alpha=alpha, bpreg=1.0)
+    items, offset, order, supports = make_session_arrays(n_items, 4 * n_items, seed=2)
+    rows = 16
+    m = orc.OracleGRU4Rec(**mk)
+    m.init(n_items)
+    eng = _lib.Engine(make_cfg(n_items, mk, sample_store=rows * 2048, step_mode=2))
+    push_weights(eng, m)
+    P = orc.sampling_cdf(supports, alpha).astype(np.float32)
+    eng.set_sampling_cdf(P)
+    eng.generate_samples()                          # MRG31k3p uniforms + binary search on the device
+    store = eng.get_sample_store()
+    assert store.min() >= 0 and store.max() < n_items
+    sched = _lib.Schedule(items, offset, order, 32, 2048, mode=0)
+    steps = orc.build_train_schedule(items, offset, order, 32, 2048)
+    n = 10
+    costs = eng.train_steps(sched, 0, n)
+    ref = [m.train_step(st['X'], st['Y'], st['R'], samples=store[k], slots=st['slots']) for k, st in enumerate(steps[:n])]
+    np.testing.assert_allclose(costs, ref, rtol=1e-4, atol=1e-6)
+    compare_weights(eng, m, rtol=2e-3, atol=2e-5, what='headline workload')
+    fast, fallback = eng.fast_windows()
+    if alpha == 0.0:
         assert fast >= 1 and fallback == 0
     else:
         assert fast + fallback >= 1      # popularity sampling can create duplicate groups wider than a chunk -> generic kernel

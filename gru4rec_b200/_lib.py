@@ -39,7 +39,7 @@ EXPORTS = [
     'g4r_mrg_uniform', 'g4r_searchsorted', 'g4r_gather_rows',
     'g4r_schedule_build', 'g4r_schedule_free', 'g4r_schedule_steps', 'g4r_schedule_events', 'g4r_schedule_export',
     'g4r_train_step', 'g4r_train_steps', 'g4r_upload_steps', 'g4r_run_uploaded', 'g4r_kernel_launches',
-    'g4r_profile_uploaded', 'g4r_phase_name', 'g4r_phase_count', 'g4r_persistent_stamps', 'g4r_fast_windows', 'g4r_mg_unique_id', 'g4r_mg_init',
+    'g4r_profile_uploaded', 'g4r_phase_name', 'g4r_phase_count', 'g4r_persistent_stamps', 'g4r_fast_windows', 'g4r_uses_tensor_cores', 'g4r_mg_unique_id', 'g4r_mg_init',
     'g4r_mg_sharded', 'g4r_mg_ipc_handle', 'g4r_mg_ipc_open', 'g4r_mg_owner', 'g4r_mg_local_row', 'g4r_mg_shard_rows', 'g4r_mg_segment_bytes',
     'g4r_eval_schedule', 'g4r_set_eval_items', 'g4r_predict', 'g4r_reset_eval_hidden',
 ]
@@ -94,6 +94,7 @@ def load():
     lib.g4r_phase_count.restype = C.c_int
     lib.g4r_persistent_stamps.argtypes = [vp, i32, vp, i64]
     lib.g4r_fast_windows.argtypes = [vp, C.POINTER(i64)]; lib.g4r_fast_windows.restype = i64
+    lib.g4r_uses_tensor_cores.argtypes = [vp]
     lib.g4r_mg_unique_id.argtypes = [vp]
     lib.g4r_mg_init.argtypes = [vp, vp]
     lib.g4r_mg_sharded.argtypes = [vp]
@@ -438,6 +439,9 @@ class Engine(object):
             import torch
             torch.cuda.synchronize()
             d.barrier()
+
+    def uses_tensor_cores(self):
+        return bool(self.lib.g4r_uses_tensor_cores(self.h))
 
     def fast_windows(self):
         fb = C.c_int64()

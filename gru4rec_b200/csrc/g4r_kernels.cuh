@@ -35,6 +35,15 @@ struct MgDev {                       // device pointers of the multi-GPU state
 };
 
 struct MgTensor { float *p, *acc, *vel; size_t goff; int count; };
+struct TsBuf {                 // device buffers of the tensor-core step (owned by the handle's workspace)
+  unsigned char *A1, *A2, *A3, *A4, *A5, *A6, *A7, *A8;      // left operands  (rows x K) as hi|lo blocks
+  unsigned char *W1, *W2, *W3, *W4, *B3, *B4, *B5, *B8;      // right operands (n x K)
+  float *O, *bias;                                           // scores / dL/do [Bpad x ldO] (lane-major), bias of the sorted columns [NP]
+  int ldO;
+  int Mpad, Lk2, Lk1, Lk3, Nk, Bk;                           // padded extents: lanes; K = 2L, L, 3L, columns, lanes (multiples of 32)
+  int nsplit;                                                // K splits of the dL/dh GEMM
+};
+
 
 // ---- row-sharded multi-GPU state (g4r_shard.cuh): item tables live only on their owner (row i -> rank i % R, local row i / R);
 // peers read parameter rows and write gradient rows through peer-mapped pointers (cudaIpc) inside the persistent kernel ----
@@ -779,6 +788,37 @@ __host__ __device__ inline size_t score_smem_bytes(int Bld) {
   return (size_t)(SC_TB * SC_LDS + SC_CT * SC_LDS + Bld + Bld * 8 + 8 * SC_TB * 8 + SC_CT + 2 * SC_CT + 32) * sizeof(float);
 }
 
+// final row statistics RS[b] = {m, Z, A', Q', D', t or target score, loss_b} from the merged sums (gru4rec.py:225-248)
+__device__ __forceinline__ void stats_finalize(const ModelDev& md, int b, int M, int N, float m, float Z, float A, float Q, float D, float T, float tt) {
+  float* rs = md.RS + (size_t)b * G4R_NSTAT;
+  float loss = 0.f;
+  if (md.loss == G4R_LOSS_XE) {
+    const float pt = __fdiv_rn(expf(T - m), Z);
+    loss = -logf(pt + G4R_EPS_LOG);
+    rs[0] = m; rs[1] = Z; rs[5] = T; rs[2] = pt;
+  } else if (md.loss == G4R_LOSS_XE_LOGIT) {
+    loss = logf(Z) - (T - m);
+    rs[0] = m; rs[1] = Z; rs[5] = T;
+  } else if (md.loss == G4R_LOSS_BPR_MAX) {
+    const float Ap = __fdiv_rn(A, Z), Qp = __fdiv_rn(Q, Z), Dp = __fdiv_rn(D, Z);
+    loss = -logf(Ap + G4R_EPS_LOG) + md.bpreg * Qp;
+    rs[0] = m; rs[1] = Z; rs[2] = Ap; rs[3] = Qp; rs[4] = Dp; rs[5] = tt;
+  } else if (md.loss == G4R_LOSS_TOP1_MAX) {
+    const float Ap = __fdiv_rn(A, Z), Dp = __fdiv_rn(D, Z);
+    loss = Ap;
+    rs[0] = m; rs[1] = Z; rs[2] = Ap; rs[4] = Dp; rs[5] = tt;
+  } else if (md.loss == G4R_LOSS_BPR) {
+    loss = A;
+    rs[4] = D; rs[5] = tt;
+  } else {  // TOP1 (gru4rec.py:242-244): mean over the N columns, last term over M + n_sample; the reference subtracts a
+    // COLUMN from the row-mean vector, which broadcasts to [M x M] before the sum: everything is M times the row expression
+    const float c = sigmoidf_(tt * tt);
+    loss = (float)M * (__fdiv_rn(A, (float)N) - __fdiv_rn(c, (float)(M + md.S_cfg)));
+    rs[4] = D; rs[5] = tt;
+  }
+  rs[6] = loss;
+}
+
 // ------------------------------------------------------------------------------------------------
 // phase S2: combine the chunk statistics of lane b (one CTA per lane; fixed combine order => deterministic)
 // RS[b] = {m, Z, A', Q', D', t_or_targetO, loss_b}
@@ -812,33 +852,7 @@ __device__ void phase_stats(const ModelDev& md, int s, int cta, int ncta, float*
       tt = sW[7];
       for (int w = 1; w < nwarp; w++) { const float* q = sW + w * 8; stat_combine(md, m, Z, A, Q, D, T, has, q[0], q[1], q[2], q[3], q[4], q[5], q[6]); }
       if (loss_softmaxneg(md.loss)) stat_merge(m, Z, A, Q, D, 0.f, 0.f, 0.f, 0.f, 0.f);   // the zeroed diagonal takes part in the max (gru4rec.py:200-202)
-      float* rs = md.RS + (size_t)b * G4R_NSTAT;
-      float loss = 0.f;
-      if (md.loss == G4R_LOSS_XE) {
-        const float pt = __fdiv_rn(expf(T - m), Z);
-        loss = -logf(pt + G4R_EPS_LOG);
-        rs[0] = m; rs[1] = Z; rs[5] = T; rs[2] = pt;
-      } else if (md.loss == G4R_LOSS_XE_LOGIT) {
-        loss = logf(Z) - (T - m);
-        rs[0] = m; rs[1] = Z; rs[5] = T;
-      } else if (md.loss == G4R_LOSS_BPR_MAX) {
-        const float Ap = __fdiv_rn(A, Z), Qp = __fdiv_rn(Q, Z), Dp = __fdiv_rn(D, Z);
-        loss = -logf(Ap + G4R_EPS_LOG) + md.bpreg * Qp;
-        rs[0] = m; rs[1] = Z; rs[2] = Ap; rs[3] = Qp; rs[4] = Dp; rs[5] = tt;
-      } else if (md.loss == G4R_LOSS_TOP1_MAX) {
-        const float Ap = __fdiv_rn(A, Z), Dp = __fdiv_rn(D, Z);
-        loss = Ap;
-        rs[0] = m; rs[1] = Z; rs[2] = Ap; rs[4] = Dp; rs[5] = tt;
-      } else if (md.loss == G4R_LOSS_BPR) {
-        loss = A;
-        rs[4] = D; rs[5] = tt;
-      } else {  // TOP1 (gru4rec.py:242-244): mean over the N columns, last term over M + n_sample; the reference subtracts a
-        // COLUMN from the row-mean vector, which broadcasts to [M x M] before the sum: everything is M times the row expression
-        const float c = sigmoidf_(tt * tt);
-        loss = (float)M * (__fdiv_rn(A, (float)N) - __fdiv_rn(c, (float)(M + md.S_cfg)));
-        rs[4] = D; rs[5] = tt;
-      }
-      rs[6] = loss;
+      stats_finalize(md, b, M, N, m, Z, A, Q, D, T, tt);
     }
     __syncthreads();
   }
@@ -1181,7 +1195,8 @@ __host__ __device__ inline size_t lossgrad_smem_bytes(int Bld, int ldL) {
 // ------------------------------------------------------------------------------------------------
 // phase B1: elementwise part of the GRU backward: dh, dz, dh~, da_h, da_z
 // ------------------------------------------------------------------------------------------------
-__device__ void phase_b1(const ModelDev& md, int li, int s, int cta, int ncta) {
+__device__ void phase_b1(const ModelDev& md, int li, int s, int cta, int ncta, int nch_override = 0) {
+  const int NCHp = nch_override > 0 ? nch_override : md.NCH;      // partial dL/dh blocks to sum (tensor-core step: K splits)
   const LayerDev& ly = md.layer[li];
   const int M = md.wM[s];
   const int L = ly.L, ldL = ly.ldL;
@@ -1209,10 +1224,10 @@ __device__ void phase_b1(const ModelDev& md, int li, int s, int cta, int ncta) {
     if (last) {
       float d = 0.f;
       if (ok) {
-        for (int c0 = 0; c0 < md.NCH; c0 += 64) {      // 8 independent loads in flight per lane, fixed summation order
+        for (int c0 = 0; c0 < NCHp; c0 += 64) {      // 8 independent loads in flight per lane, fixed summation order
           float v[8];
 #pragma unroll
-          for (int u = 0; u < 8; u++) { const int ch = c0 + sub + 8 * u; v[u] = ch < md.NCH ? part[(size_t)ch * cs + o] : 0.f; }
+          for (int u = 0; u < 8; u++) { const int ch = c0 + sub + 8 * u; v[u] = ch < NCHp ? part[(size_t)ch * cs + o] : 0.f; }
           d += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
         }
       }

@@ -21,6 +21,7 @@ static void mg_release(g4r_handle* h);
 static void shard_release(g4r_handle* h);
 static bool shard_eligible(const g4r_config& c, int n_sm);
 static int shard_create(g4r_handle* h);
+static bool tc_eligible(const g4r_config& c);
 struct TensorInfo;
 static int shard_set_tensor(g4r_handle* h, const TensorInfo& t, const float* host);
 static int shard_get_tensor(g4r_handle* h, const TensorInfo& t, float* host);
@@ -82,6 +83,7 @@ struct g4r_handle {
   bool two_pass = false;         // grad_cap: gradients are exported, the global norm is taken, then a second pass applies them scaled
   bool phase_only = false;       // grad_cap / smoothing add phases that only the per-phase launch sequence has
   float* dGscale = nullptr;
+  bool tc_ok = false; void* ts_buf = nullptr;      // tensor-core training step (g4r_tcstep.cuh): TsBuf*
   std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_phase;
 };
 
@@ -284,6 +286,23 @@ static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
     shard_ws_bytes = (size_t)2 * MG_CAP * R * sizeof(int) + 4096 + (size_t)B * md.layer[0].ld3 * sizeof(float) + 1024;
     shard_ws = cv.take<char>(shard_ws_bytes);
   }
+  // tensor-core training step: hi|lo operand blocks (g4r_tcstep.cuh)
+  TsBuf tsb; memset(&tsb, 0, sizeof(tsb));
+  const bool tc = tc_eligible(c);
+  if (tc) {
+    auto r32 = [](int x) { return (x + 31) / 32 * 32; };
+    auto r128 = [](int x) { return (x + 127) / 128 * 128; };
+    const int L = Llast;
+    tsb.Mpad = r128(B); tsb.Lk1 = r32(L); tsb.Lk2 = r32(2 * L); tsb.Lk3 = r32(3 * L); tsb.Nk = r128(NP); tsb.Bk = r32(B);
+    tsb.ldO = tsb.Nk;
+    tsb.nsplit = std::max(1, std::min(NCH, (tsb.Nk / 32 + 3) / 4));
+    auto op = [&](int rows, int K) { return cv.take<unsigned char>((size_t)r128(rows) * K * 8); };   // hi + lo: 8 bytes per element
+    tsb.A1 = op(B, tsb.Lk2); tsb.A2 = op(B, tsb.Lk2); tsb.A3 = op(B, tsb.Lk1); tsb.A4 = op(NP, tsb.Bk); tsb.A5 = op(B, tsb.Nk);
+    tsb.A6 = op(B, tsb.Lk1); tsb.A7 = op(B, tsb.Lk3); tsb.A8 = op(3 * L, tsb.Bk);
+    tsb.W1 = op(2 * L, tsb.Lk2); tsb.W2 = op(L, tsb.Lk2); tsb.W3 = op(L, tsb.Lk1); tsb.W4 = op(L, tsb.Lk3);
+    tsb.B3 = op(NP, tsb.Lk1); tsb.B4 = op(L, tsb.Bk); tsb.B5 = op(L, tsb.Nk); tsb.B8 = op(3 * L, tsb.Bk);
+    tsb.O = cv.take<float>((size_t)tsb.Mpad * tsb.ldO); tsb.bias = cv.take<float>(tsb.Nk);
+  }
   // evaluation
   int* dRank = cv.take<int>((size_t)Be * 4); float* dTgt = cv.take<float>(Be);
   if (!cv.dry) {
@@ -296,6 +315,8 @@ static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
     h->dRankCnt = dRank; h->dTgt = dTgt;
     h->npow2 = next_pow2(B + S);
     h->shard_ws = shard_ws; h->shard_ws_bytes = shard_ws_bytes;
+    h->tc_ok = tc;
+    if (tc) { if (!h->ts_buf) h->ts_buf = new TsBuf(); *static_cast<TsBuf*>(h->ts_buf) = tsb; }
     h->dGscale = gsc; h->two_pass = c.grad_cap > 0.f; h->phase_only = c.grad_cap > 0.f || md.smoothing > 0.f;
   }
 }
@@ -337,7 +358,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_lossgrad(int slot, const int* ba
   extern __shared__ __align__(16) float smem[];
   phase_lossgrad(MD, STEP_IDX, blockIdx.x, smem);
 }
-__global__ void __launch_bounds__(256) k_b1(int slot, const int* base, int off, int li) { phase_b1(MD, li, STEP_IDX, blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(256) k_b1(int slot, const int* base, int off, int li, int nch) { phase_b1(MD, li, STEP_IDX, blockIdx.x, gridDim.x, nch); }
 __global__ void __launch_bounds__(GEMM_THREADS) k_b2(int slot, const int* base, int off, int li) {
   __shared__ float sA[GK * (GB + 1)], sB[GK * (GB + 1)];
   phase_b2(MD, li, STEP_IDX, blockIdx.x, sA, sB);
@@ -420,8 +441,60 @@ static cudaError_t raise_smem_limit(const void* func, size_t bytes) {
 
 static int tiles2(int cols, int rows) { return ((cols + GB - 1) / GB) * ((rows + GB - 1) / GB); }
 
+#include "g4r_eval_tc.cuh"
+#include "g4r_tcstep.cuh"
+// The shapes the tensor-core step takes: constrained embedding, one layer, batch <= 256, SGD / Adagrad (+momentum); chosen
+// automatically for wide layers (L >= 160), or for any such model with step_mode 4.
+static bool tc_eligible(const g4r_config& c) {
+  if (!c.constrained_embedding || c.n_layers != 1 || c.batch_size > 256 || (c.layers[0] & 3)) return false;
+  if (c.adapt > G4R_ADAPT_ADAGRAD || c.grad_cap > 0.f || c.smoothing != 0.f || c.world_size > 1) return false;
+  return c.step_mode == 4 || (c.step_mode >= 1 && c.step_mode <= 3 && c.layers[0] >= 160);
+}
+static int ts_pick_nt(int m_tiles, int N, int ksplit) {       // largest N tile that still gives ~a third of the SMs a tile each
+  for (int nt = 128; nt > 32; nt >>= 1) if (m_tiles * ((N + nt - 1) / nt) * ksplit >= 48) return nt;
+  return 32;
+}
+// one mini-batch on the tensor cores (window-relative step = *base + off when base != nullptr)
+static int enqueue_tc_step(g4r_handle* h, const int* base, int off) {
+  const ModelDev& md = h->md;
+  const TsBuf& tb = *static_cast<TsBuf*>(h->ts_buf);
+  cudaStream_t st = h->stream;
+  const int L = md.L, B = md.B, slot = h->slot;
+  const int mt = tb.Mpad / TS_RB;
+  const int fillg = 2 * h->n_sm;
+  auto gemm = [&](int ph, const unsigned char* A, const unsigned char* Bm, int chunks, int m_tiles, int Ncols, int ksplit, int epi) {
+    TsGemm g; g.A = A; g.Bm = Bm; g.chunks = chunks; g.m_tiles = m_tiles; g.ksplit = ksplit; g.epi = epi;
+    g.NT = ts_pick_nt(m_tiles, Ncols, ksplit); g.n_tiles = (Ncols + g.NT - 1) / g.NT;
+    LAUNCH(ph, k_ts_gemm<<<m_tiles * g.n_tiles * ksplit, TS_THREADS, sizeof(TsSmem), st>>>(slot, base, off, g, tb));
+  };
+  LAUNCH(PH_GATHER, k_gather_in<<<std::max(1, (B + 7) / 8), 256, 0, st>>>(slot, base, off, 1));
+  LAUNCH(PH_F1, k_ts_prep_w<<<dim3(fillg, 4), 256, 0, st>>>(slot, tb));
+  LAUNCH(PH_F1, k_ts_prep_fwd<<<dim3(fillg, 2), 256, 0, st>>>(slot, base, off, tb));
+  gemm(PH_F1, tb.A1, tb.W1, tb.Lk2 / TC_KC, mt, 2 * L, 1, TS_EPI_F1);
+  LAUNCH(PH_F2, k_ts_prep_hr<<<fillg, 256, 0, st>>>(slot, base, off, tb));
+  gemm(PH_F2, tb.A2, tb.W2, tb.Lk2 / TC_KC, mt, L, 1, TS_EPI_F2);
+  LAUNCH(PH_SCORE, k_ts_prep_score<<<dim3(fillg, 5), 256, 0, st>>>(slot, base, off, tb));
+  gemm(PH_SCORE, tb.A3, tb.B3, tb.Lk1 / TC_KC, mt, md.NP, 1, TS_EPI_SCORE);
+  LAUNCH(PH_STATS, k_ts_stats<<<B, 256, 0, st>>>(slot, base, off, tb));
+  LAUNCH(PH_LOSSGRAD, k_ts_lossgrad<<<B, 256, 0, st>>>(slot, base, off, tb));
+  LAUNCH(PH_LOSSGRAD, k_ts_prep_g<<<dim3(fillg, 3), 256, 0, st>>>(slot, base, off, tb));
+  gemm(PH_LOSSGRAD, tb.A4, tb.B4, tb.Bk / TC_KC, tb.Nk / TS_RB, L, 1, TS_EPI_DSY);
+  gemm(PH_LOSSGRAD, tb.A5, tb.B5, tb.Nk / TC_KC, mt, L, tb.nsplit, TS_EPI_DH);
+  LAUNCH(PH_B1, k_b1<<<std::max(1, std::min(h->n_sm, (B * L * 8 + 255) / 256)), 256, 0, st>>>(slot, base, off, 0, tb.nsplit));
+  LAUNCH(PH_B2, k_ts_prep_b2<<<fillg, 256, 0, st>>>(slot, base, off, tb));
+  gemm(PH_B2, tb.A6, tb.W3, tb.Lk1 / TC_KC, mt, L, 1, TS_EPI_B2);
+  LAUNCH(PH_B3, k_ts_prep_bwd<<<dim3(fillg, 3), 256, 0, st>>>(slot, base, off, tb));
+  gemm(PH_B3, tb.A7, tb.W4, tb.Lk3 / TC_KC, mt, L, 1, TS_EPI_B3);
+  gemm(PH_DENSE, tb.A8, tb.B8, tb.Bk / TC_KC, (3 * L + TS_RB - 1) / TS_RB, 3 * L, 1, TS_EPI_DENSE);
+  LAUNCH(PH_DENSE, k_ts_bh<<<(3 * L + 255) / 256, 256, 0, st>>>(slot, base, off));
+  LAUNCH(PH_LOSSGRAD, k_apply_rows<<<md.NCH, SC_THREADS, 0, st>>>(slot, base, off));
+  LAUNCH(PH_SPARSE_IN, k_sparse_in<<<B, 128, 0, st>>>(slot, base, off, 1));
+  return G4R_OK;
+}
+
 // enqueue the kernels of one training step (window-relative index = *base + off when base != nullptr)
 static int enqueue_train_step(g4r_handle* h, const int* base, int off) {
+  if (h->tc_ok) return enqueue_tc_step(h, base, off);
   const ModelDev& md = h->md;
   cudaStream_t st = h->stream;
   const int B = md.B;
@@ -440,7 +513,7 @@ static int enqueue_train_step(g4r_handle* h, const int* base, int off) {
   LAUNCH(PH_LOSSGRAD, k_lossgrad<<<md.NCH, SC_THREADS, lossgrad_smem_bytes(md.Bld, md.ldL), st>>>(h->slot, base, off));
   for (int li = md.n_layers - 1; li >= 0; li--) {
     const LayerDev& ly = md.layer[li];
-    LAUNCH(PH_B1, k_b1<<<std::max(1, std::min(h->n_sm, (B * ly.L * 8 + 255) / 256)), 256, 0, st>>>(h->slot, base, off, li));
+    LAUNCH(PH_B1, k_b1<<<std::max(1, std::min(h->n_sm, (B * ly.L * 8 + 255) / 256)), 256, 0, st>>>(h->slot, base, off, li, 0));
     LAUNCH(PH_B2, k_b2<<<tiles2(ly.L, B), GEMM_THREADS, 0, st>>>(h->slot, base, off, li));
     if (ly.in_dim > 0) LAUNCH(PH_B3, k_b3<<<tiles2(ly.in_dim, B), GEMM_THREADS, 0, st>>>(h->slot, base, off, li));
     const DenseJobs dj = dense_jobs(ly.L, ly.in_dim);
@@ -486,6 +559,7 @@ extern "C" int g4r_destroy(g4r_handle* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   eval_release(h);
+  if (h->ts_buf) { delete static_cast<TsBuf*>(h->ts_buf); h->ts_buf = nullptr; }
   shard_release(h);
   mg_release(h);
   if (h->graphU) cudaGraphExecDestroy(h->graphU);
@@ -590,6 +664,10 @@ extern "C" int g4r_create(const g4r_config* cfg, void* device_workspace, size_t 
     h->fastc_ok = plain_opt && cfg->step_mode == 3 && h->fastc_grid >= FC_CLUSTER * 2 && m.mode == 0 && m.n_layers == 1 && m.ldL <= 128 && m.B <= FK_B &&
                   m.NCH <= h->fastc_grid && (m.adapt == G4R_ADAPT_ADAGRAD ? m.Wy_acc != nullptr : true);
     cudaMallocHost(&h->hFlags, 4 * sizeof(int));
+  }
+  if (h->tc_ok) {
+    if (raise_smem_limit((const void*)k_ts_gemm, sizeof(TsSmem)) != cudaSuccess) return bail(G4R_ERR_CUDA, "k_ts_gemm: shared memory opt-in failed");
+    h->fast_ok = false; h->fastc_ok = false;
   }
   if (cfg->step_mode == 1 && h->pk_blocks == 0) return bail(G4R_ERR_INVALID, "persistent mode unavailable (cooperative launch / shared memory)");
   if (h->md.shardR > 0) {
@@ -974,6 +1052,7 @@ static int build_graph(g4r_handle* h, int unroll, cudaGraphExec_t* out) {
 }
 static int64_t launches_per_step(const g4r_handle* h) {
   const ModelDev& md = h->md;
+  if (h->tc_ok) return 25;
   int64_t n = (md.mode != 0 ? 1 : 0) + 4;        // gather + score/stats/lossgrad + sparse_in
   for (int li = 0; li < md.n_layers; li++) n += 2 + 2 + (md.layer[li].in_dim > 0 ? 1 : 0) + 1;
   if (md.smoothing > 0.f) n += 2;
@@ -1005,7 +1084,7 @@ static int run_window(g4r_handle* h, int64_t n) {
     CK(cudaMemsetAsync(h->dFastSync, 0, sizeof(FastSync), h->stream));
     CK(cudaLaunchCooperativeKernel((void*)k_fast_t<false>, dim3(h->pk_blocks), dim3(FK_THREADS), args, sizeof(FastSmem), h->stream));
     h->launches += 1; h->fast_windows++;
-  } else if (h->cfg.step_mode >= 1 && !h->prof && h->pk_blocks > 0 && !h->phase_only) {
+  } else if (h->cfg.step_mode >= 1 && !h->prof && h->pk_blocks > 0 && !h->phase_only && !h->tc_ok) {
     if (h->cfg.step_mode >= 2) h->slow_windows++;
     int slot = h->slot, nst = (int)n; GridBar* gb = h->dGridBar; unsigned long long* ts = h->stamp_on ? h->dStamp : nullptr;
     void* args[] = {&slot, &nst, &gb, &ts};
@@ -1098,6 +1177,7 @@ extern "C" int g4r_persistent_stamps(g4r_handle* h, int32_t enable, unsigned lon
   }
   return G4R_OK;
 }
+extern "C" int g4r_uses_tensor_cores(const g4r_handle* h) { return (h && h->tc_ok) ? 1 : 0; }
 extern "C" int64_t g4r_fast_windows(const g4r_handle* h, int64_t* fallback_windows) {
   if (!h) return 0;
   if (fallback_windows) *fallback_windows = h->slow_windows;

@@ -1,0 +1,452 @@
+// g4r_tcstep.cuh -- the training step on the 5th-generation tensor cores for the LARGE shared-embedding shapes
+// (constrained_embedding, one GRU layer, hidden size >= 160, batch <= 256: paramfiles/{rees46,coveo,diginetica,yoochoose,
+// retailrocket}_*_best.py of the reference -- B = 48..240, L = 224..512, 2048 negative samples).  At these shapes a mini-batch is
+// ~4 GFLOP of dense contractions (gru4rec.py:460-461 gates, :493 sampled scores, and their gradients from T.grad, :383-384);
+// the generic kernels run them on FP32 FFMA tiles at ~4 TFLOP/s.  Here every contraction is a tcgen05 GEMM:
+//
+//   operands  fp32 values are split into hi = tf32(x), lo = tf32(x - hi) ("3xTF32": lo*hi + hi*lo + hi*hi accumulated in fp32 in
+//             TMEM reproduces the fp32 product to ~2^-21 relative) and stored as [hi | lo] blocks of 128 rows x 32 k-values in the
+//             canonical K-major UMMA layout (8 x 16-byte core matrices) by small "prep" kernels that also do the gathers
+//             (Wy[item] rows of the score columns, H through the lane slots), transposes and elementwise products (H * r);
+//   GEMM      one CTA per 128 x NT output tile (NT = 32..128): a TMA thread streams the operand blocks with bulk copies into a
+//             3-stage shared-memory ring (mbarrier complete_tx), an MMA thread issues tcgen05.mma kind::tf32 (M = 128, N = NT,
+//             K = 8) and hands stages back with tcgen05.commit, four epilogue warps read the accumulator with tcgen05.ld and
+//             apply the fused epilogue (gates + sigmoid, candidate + GRU update + dropout + reset, score + bias, dSy rows,
+//             partial dL/dh per K split, da_r, dL/d(input), dense gradient + Adagrad/momentum update);
+//   the rest  row statistics, dL/do, the partial-sum reduce (b1), and the deterministic sparse updates reuse the generic
+//             phases (g4r_kernels.cuh) -- same numerics, same duplicate rules.
+// Included from g4r_lib.cu after g4r_eval.cuh (uses its mbarrier / UMMA helpers).
+#pragma once
+
+constexpr int TS_RB = 128;                               // rows per operand block
+constexpr uint32_t TS_BLK = TS_RB * TC_KC * 4;           // bytes of one hi (or lo) block: 16 KB
+constexpr int TS_STAGES = 3;
+constexpr int TS_NT_MAX = 128;
+constexpr uint32_t TS_STAGE_BYTES = 2 * TS_BLK + 2 * TS_NT_MAX * TC_KC * 4;   // 64 KB
+constexpr int TS_THREADS = 192;                          // 4 epilogue warps + TMA warp + MMA warp
+
+enum { TS_EPI_F1 = 0, TS_EPI_F2, TS_EPI_SCORE, TS_EPI_DSY, TS_EPI_DH, TS_EPI_B2, TS_EPI_B3, TS_EPI_DENSE };
+
+
+struct TsSmem {
+  alignas(1024) unsigned char stage[TS_STAGES][TS_STAGE_BYTES];
+  alignas(8) unsigned long long stage_full[TS_STAGES];
+  unsigned long long stage_free[TS_STAGES];
+  unsigned long long acc_full;
+  uint32_t tmem_base;
+  int err;
+};
+
+__device__ __forceinline__ void ts_put4(unsigned char* base, int n_chunk, int row, int k, float4 v) {
+  const int rb = row / TS_RB, r = row % TS_RB, c = k / TC_KC, kq = (k % TC_KC) >> 2;
+  unsigned char* hi = base + ((size_t)rb * n_chunk + c) * 2 * TS_BLK + (uint32_t)(((r >> 3) * 8 + kq) * 128 + (r & 7) * 16);
+  uint4 h, l;
+  h.x = tc_tf32(v.x); h.y = tc_tf32(v.y); h.z = tc_tf32(v.z); h.w = tc_tf32(v.w);
+  l.x = tc_tf32(v.x - __uint_as_float(h.x)); l.y = tc_tf32(v.y - __uint_as_float(h.y));
+  l.z = tc_tf32(v.z - __uint_as_float(h.z)); l.w = tc_tf32(v.w - __uint_as_float(h.w));
+  *reinterpret_cast<uint4*>(hi) = h;
+  *reinterpret_cast<uint4*>(hi + TS_BLK) = l;
+}
+// fills a [rows_pad x K_pad] operand: f(row, k) -> the four values (row, k .. k+3); k_fast: consecutive threads walk k (sources
+// with k contiguous in memory) else rows (transposed / gathered sources)
+template <class F>
+__device__ __forceinline__ void ts_fill(unsigned char* base, int rows_pad, int K_pad, bool k_fast, F f) {
+  const int n_chunk = K_pad / TC_KC, kq_n = K_pad / 4;
+  const long long total = (long long)rows_pad * kq_n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int row, kq;
+    if (k_fast) { row = (int)(i / kq_n); kq = (int)(i % kq_n); } else { kq = (int)(i / rows_pad); row = (int)(i % rows_pad); }
+    ts_put4(base, n_chunk, row, kq * 4, f(row, kq * 4));
+  }
+}
+__device__ __forceinline__ float4 ts_zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+// ---- P1: A1 = [in0 | H(slot)] (lanes x 2L), compact copy of the old hidden state (gru4rec.py:459-460 operands) ----
+__global__ void __launch_bounds__(256) k_ts_prep_fwd(int slot, const int* base, int off, TsBuf tb) {
+  const ModelDev& md = MD; const int s = STEP_IDX;
+  const LayerDev& ly = md.layer[0];
+  const int M = md.wM[s], L = ly.L, ldL = ly.ldL;
+  if (blockIdx.y == 0) {
+    ts_fill(tb.A1, tb.Mpad, tb.Lk2, true, [&](int b, int k) -> float4 {
+      if (b >= M) return ts_zero4();
+      if (k < L) return ld4(md.in0 + (size_t)b * md.ld_in0 + k);
+      if (k - L >= L) return ts_zero4();
+      const int sl = (md.wF[(size_t)s * md.B + b] & 2) ? -1 : md.wSlot[(size_t)s * md.B + b];
+      return sl >= 0 ? ld4(ly.H + (size_t)sl * ldL + (k - L)) : ts_zero4();
+    });
+  } else {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M * (ldL / 4); i += gridDim.x * blockDim.x) {
+      const int b = i / (ldL / 4), c4 = i % (ldL / 4);
+      const int sl = (md.wF[(size_t)s * md.B + b] & 2) ? -1 : md.wSlot[(size_t)s * md.B + b];
+      st4(ly.Hold + (size_t)b * ldL + c4 * 4, sl >= 0 ? ld4(ly.H + (size_t)sl * ldL + c4 * 4) : ts_zero4());
+    }
+  }
+}
+// ---- P2: weight operands (they change every step: dense update) ----
+//   W1 (n < 2L, k < 2L): k < L ? Wx[k][L + n] : Wrz[k - L][n]      gates        (gru4rec.py:460)
+//   W2 (n <  L, k < 2L): k < L ? Wx[k][n]     : Wh[k - L][n]       candidate    (gru4rec.py:461)
+//   W3 (n <  L, k <  L): Wh[n][k]                                   d(H*r) = da_h Wh^T
+//   W4 (n <  L, k < 3L): Wx[n][k]                                   dL/d(input) = dvec Wx^T
+__global__ void __launch_bounds__(256) k_ts_prep_w(int slot, TsBuf tb) {
+  const ModelDev& md = MD;
+  const LayerDev& ly = md.layer[0];
+  const int L = ly.L;
+  const float* __restrict__ Wx = ly.Wx; const float* __restrict__ Wh = ly.Wh; const float* __restrict__ Wrz = ly.Wrz;
+  if (blockIdx.y == 0) {
+    ts_fill(tb.W1, (2 * L + TS_RB - 1) / TS_RB * TS_RB, tb.Lk2, false, [&](int n, int k) -> float4 {
+      float v[4];
+      for (int u = 0; u < 4; u++) { const int kk = k + u; v[u] = (n < 2 * L && kk < 2 * L) ? (kk < L ? Wx[(size_t)kk * ly.ld3 + L + n] : Wrz[(size_t)(kk - L) * ly.ld2 + n]) : 0.f; }
+      return make_float4(v[0], v[1], v[2], v[3]);
+    });
+  } else if (blockIdx.y == 1) {
+    ts_fill(tb.W2, (L + TS_RB - 1) / TS_RB * TS_RB, tb.Lk2, false, [&](int n, int k) -> float4 {
+      float v[4];
+      for (int u = 0; u < 4; u++) { const int kk = k + u; v[u] = (n < L && kk < 2 * L) ? (kk < L ? Wx[(size_t)kk * ly.ld3 + n] : Wh[(size_t)(kk - L) * ly.ldL + n]) : 0.f; }
+      return make_float4(v[0], v[1], v[2], v[3]);
+    });
+  } else if (blockIdx.y == 2) {
+    ts_fill(tb.W3, (L + TS_RB - 1) / TS_RB * TS_RB, tb.Lk1, true, [&](int n, int k) -> float4 { return (n < L && k < L) ? ld4(Wh + (size_t)n * ly.ldL + k) : ts_zero4(); });
+  } else {
+    ts_fill(tb.W4, (L + TS_RB - 1) / TS_RB * TS_RB, tb.Lk3, true, [&](int n, int k) -> float4 { return (n < L && k < 3 * L) ? ld4(Wx + (size_t)n * ly.ld3 + k) : ts_zero4(); });
+  }
+}
+// ---- P3: A2 = [in0 | Hold * r] ----
+__global__ void __launch_bounds__(256) k_ts_prep_hr(int slot, const int* base, int off, TsBuf tb) {
+  const ModelDev& md = MD; const int s = STEP_IDX;
+  const LayerDev& ly = md.layer[0];
+  const int M = md.wM[s], L = ly.L, ldL = ly.ldL;
+  ts_fill(tb.A2, tb.Mpad, tb.Lk2, true, [&](int b, int k) -> float4 {
+    if (b >= M) return ts_zero4();
+    if (k < L) return ld4(md.in0 + (size_t)b * md.ld_in0 + k);
+    if (k - L >= L) return ts_zero4();
+    const float4 h = ld4(ly.Hold + (size_t)b * ldL + (k - L)), r = ld4(ly.r + (size_t)b * ldL + (k - L));
+    return make_float4(h.x * r.x, h.y * r.y, h.z * r.z, h.w * r.w);
+  });
+}
+// ---- P4: operands of the score GEMM and of its two gradients ----
+//   A3 (b, k < L) = h[b][k];  B3 (j, k < L) = Wy[item_j][k];  B5 (c < L, k = j) = Wy[item_j][c];  B4 (c < L, k = b) = h[b][c]
+//   bias[j] = By[item_j] - logq * log(P0 ...) (gru4rec.py:486-495)
+__global__ void __launch_bounds__(256) k_ts_prep_score(int slot, const int* base, int off, TsBuf tb) {
+  const ModelDev& md = MD; const int s = STEP_IDX;
+  const LayerDev& ly = md.layer[0];
+  const int M = md.wM[s], L = ly.L, ldL = ly.ldL;
+  const int N = M + (md.wSti[s] >= 0 ? md.S : 0);
+  const int* __restrict__ pItem = md.pItem + (size_t)s * md.NP;
+  const float* __restrict__ Wy = md.Wy;
+  if (blockIdx.y == 0) {
+    ts_fill(tb.A3, tb.Mpad, tb.Lk1, true, [&](int b, int k) -> float4 { return (b < M && k < L) ? ld4(ly.y + (size_t)b * ldL + k) : ts_zero4(); });
+  } else if (blockIdx.y == 1) {
+    ts_fill(tb.B3, tb.Nk, tb.Lk1, true, [&](int j, int k) -> float4 { return (j < N && k < L) ? ld4(Wy + (size_t)pItem[j] * ldL + k) : ts_zero4(); });
+  } else if (blockIdx.y == 2) {
+    ts_fill(tb.B5, (L + TS_RB - 1) / TS_RB * TS_RB, tb.Nk, false, [&](int c, int k) -> float4 {
+      float v[4];
+      for (int u = 0; u < 4; u++) { const int j = k + u; v[u] = (c < L && j < N) ? Wy[(size_t)pItem[j] * ldL + c] : 0.f; }
+      return make_float4(v[0], v[1], v[2], v[3]);
+    });
+  } else if (blockIdx.y == 3) {
+    ts_fill(tb.B4, (L + TS_RB - 1) / TS_RB * TS_RB, tb.Bk, false, [&](int c, int k) -> float4 {
+      float v[4];
+      for (int u = 0; u < 4; u++) { const int b = k + u; v[u] = (c < L && b < M) ? ly.y[(size_t)b * ldL + c] : 0.f; }
+      return make_float4(v[0], v[1], v[2], v[3]);
+    });
+  } else {
+    const int* __restrict__ pPos = md.pPos + (size_t)s * md.NP;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
+      const int item = pItem[j];
+      float bz = md.By[item];
+      if (md.logq > 0.f) bz -= (pPos[j] < M) ? md.logP0t[item] : md.logP0s[item];
+      tb.bias[j] = bz;
+    }
+  }
+}
+
+// ---- row statistics of the losses straight from the lane-major score matrix (same merge as phase_score / phase_stats) ----
+__global__ void __launch_bounds__(256) k_ts_stats(int slot, const int* base, int off, TsBuf tb) {
+  const ModelDev& md = MD; const int s = STEP_IDX;
+  const int M = md.wM[s];
+  const int N = M + (md.wSti[s] >= 0 ? md.S : 0);
+  const int b = blockIdx.x;
+  if (b >= M) return;
+  __shared__ float sW[8 * 8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* orow = tb.O + (size_t)b * tb.ldO;
+  const int tc = md.pTcol[(size_t)s * md.B + b];
+  const bool pw = loss_pairwise(md.loss);
+  const float t = pw ? act_fwd(md.fact, orow[tc]) : 0.f;
+  float m = -INFINITY, Z = 0.f, A = 0.f, Q = 0.f, D = 0.f, T = 0.f, has = 0.f;
+  for (int j = tid; j < N; j += blockDim.x) stat_add_elem(md, orow[j], j == tc, t, m, Z, A, Q, D, T, has);
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {   // fixed butterfly order
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), Z2 = __shfl_xor_sync(0xffffffffu, Z, o), A2 = __shfl_xor_sync(0xffffffffu, A, o),
+                Q2 = __shfl_xor_sync(0xffffffffu, Q, o), D2 = __shfl_xor_sync(0xffffffffu, D, o), T2 = __shfl_xor_sync(0xffffffffu, T, o),
+                h2 = __shfl_xor_sync(0xffffffffu, has, o);
+    stat_combine(md, m, Z, A, Q, D, T, has, m2, Z2, A2, Q2, D2, T2, h2);
+  }
+  if (lane == 0) { float* w = sW + warp * 8; w[0] = m; w[1] = Z; w[2] = A; w[3] = Q; w[4] = D; w[5] = T; w[6] = has; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; w++) { const float* q = sW + w * 8; stat_combine(md, m, Z, A, Q, D, T, has, q[0], q[1], q[2], q[3], q[4], q[5], q[6]); }
+    if (loss_softmaxneg(md.loss)) stat_merge(m, Z, A, Q, D, 0.f, 0.f, 0.f, 0.f, 0.f);   // the zeroed diagonal takes part in the max (gru4rec.py:200-202)
+    stats_finalize(md, b, M, N, m, Z, A, Q, D, T, t);
+  }
+}
+// ---- dL/do in place (lane-major), cost of the step ----
+__global__ void __launch_bounds__(256) k_ts_lossgrad(int slot, const int* base, int off, TsBuf tb) {
+  const ModelDev& md = MD; const int s = STEP_IDX;
+  const int M = md.wM[s];
+  const int N = M + (md.wSti[s] >= 0 ? md.S : 0);
+  const int b = blockIdx.x;
+  if (b >= M) return;
+  __shared__ float sRS[8];
+  if (threadIdx.x < 8) sRS[threadIdx.x] = md.RS[(size_t)b * G4R_NSTAT + threadIdx.x];
+  __syncthreads();
+  const int tc = md.pTcol[(size_t)s * md.B + b];
+  float* orow = tb.O + (size_t)b * tb.ldO;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) orow[j] = loss_grad_elem(md, sRS, orow[j], j == tc, M, N);
+  if (b == 0 && threadIdx.x == 0) {
+    float c = 0.f;
+    for (int bb = 0; bb < M; bb++) c += md.RS[(size_t)bb * G4R_NSTAT + 6];
+    c = __fdiv_rn(c, (float)md.B);            // cost = loss / batch_size (gru4rec.py:577)
+    md.cost[s] = c;
+    if (c != c) atomicExch(md.nanflag, 1);
+  }
+}
+// ---- P5: operands of the two score gradients from G = dL/do: A5 (b, k = j) = G[b][j]; A4 (j, k = b) = G[b][j]; dby[j] = sum_b G[b][j] ----
+__global__ void __launch_bounds__(256) k_ts_prep_g(int slot, const int* base, int off, TsBuf tb) {
+  const ModelDev& md = MD; const int s = STEP_IDX;
+  const int M = md.wM[s];
+  const int N = M + (md.wSti[s] >= 0 ? md.S : 0);
+  const float* __restrict__ G = tb.O;
+  if (blockIdx.y == 0) {
+    ts_fill(tb.A5, tb.Mpad, tb.Nk, true, [&](int b, int k) -> float4 {
+      if (b >= M || k >= N) return ts_zero4();
+      float4 v = ld4(G + (size_t)b * tb.ldO + k);       // ldO, N offsets are multiples of 4
+      if (k + 1 >= N) v.y = 0.f; if (k + 2 >= N) v.z = 0.f; if (k + 3 >= N) v.w = 0.f;
+      return v;
+    });
+  } else if (blockIdx.y == 1) {
+    ts_fill(tb.A4, tb.Nk, tb.Bk, false, [&](int j, int k) -> float4 {
+      float v[4];
+      for (int u = 0; u < 4; u++) { const int b = k + u; v[u] = (j < N && b < M) ? G[(size_t)b * tb.ldO + j] : 0.f; }
+      return make_float4(v[0], v[1], v[2], v[3]);
+    });
+  } else {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
+      float a = 0.f;
+      for (int b = 0; b < M; b++) a += G[(size_t)b * tb.ldO + j];
+      md.DBY[j] = a;
+    }
+  }
+}
+// ---- P6: A6 = da_h (lanes x L) ----
+__global__ void __launch_bounds__(256) k_ts_prep_b2(int slot, const int* base, int off, TsBuf tb) {
+  const ModelDev& md = MD; const int s = STEP_IDX;
+  const LayerDev& ly = md.layer[0];
+  const int M = md.wM[s], L = ly.L;
+  ts_fill(tb.A6, tb.Mpad, tb.Lk1, true, [&](int b, int k) -> float4 { return (b < M && k < L) ? ld4(ly.dvec + (size_t)b * ly.ld3 + k) : ts_zero4(); });
+}
+// ---- P7: A7 = dvec (lanes x 3L); A8 (m < 3L, k = b) = [Hold*r ; Hold ; in0]^T; B8 (n < 3L, k = b) = dvec^T ----
+__global__ void __launch_bounds__(256) k_ts_prep_bwd(int slot, const int* base, int off, TsBuf tb) {
+  const ModelDev& md = MD; const int s = STEP_IDX;
+  const LayerDev& ly = md.layer[0];
+  const int M = md.wM[s], L = ly.L, ldL = ly.ldL;
+  const int R3 = (3 * L + TS_RB - 1) / TS_RB * TS_RB;
+  if (blockIdx.y == 0) {
+    ts_fill(tb.A7, tb.Mpad, tb.Lk3, true, [&](int b, int k) -> float4 { return (b < M && k < 3 * L) ? ld4(ly.dvec + (size_t)b * ly.ld3 + k) : ts_zero4(); });
+  } else if (blockIdx.y == 1) {
+    ts_fill(tb.A8, R3, tb.Bk, false, [&](int mrow, int k) -> float4 {
+      float v[4];
+      for (int u = 0; u < 4; u++) {
+        const int b = k + u;
+        float x = 0.f;
+        if (mrow < 3 * L && b < M) {
+          if (mrow < L) x = ly.Hold[(size_t)b * ldL + mrow] * ly.r[(size_t)b * ldL + mrow];
+          else if (mrow < 2 * L) x = ly.Hold[(size_t)b * ldL + mrow - L];
+          else x = md.in0[(size_t)b * md.ld_in0 + mrow - 2 * L];
+        }
+        v[u] = x;
+      }
+      return make_float4(v[0], v[1], v[2], v[3]);
+    });
+  } else {
+    ts_fill(tb.B8, R3, tb.Bk, false, [&](int n, int k) -> float4 {
+      float v[4];
+      for (int u = 0; u < 4; u++) { const int b = k + u; v[u] = (n < 3 * L && b < M) ? ly.dvec[(size_t)b * ly.ld3 + n] : 0.f; }
+      return make_float4(v[0], v[1], v[2], v[3]);
+    });
+  }
+}
+// ---- dBh = sum_b dvec (gru4rec.py:462 bias gradient) with its update ----
+__global__ void __launch_bounds__(256) k_ts_bh(int slot, const int* base, int off) {
+  const ModelDev& md = MD; const int s = STEP_IDX;
+  const LayerDev& ly = md.layer[0];
+  const int M = md.wM[s];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= 3 * ly.L) return;
+  float g = 0.f;
+  for (int b = 0; b < M; b++) g += ly.dvec[(size_t)b * ly.ld3 + c];
+  dense_update(md, ly.Bh + c, ly.Bh_acc ? ly.Bh_acc + c : nullptr, ly.Bh_vel ? ly.Bh_vel + c : nullptr, g, (size_t)ly.ld3);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// the GEMM: D[128 x NT] (+)= A[128 x K] B[NT x K]^T, 3xTF32, fused epilogue
+// ---------------------------------------------------------------------------------------------------------------------
+struct TsGemm {
+  const unsigned char* A; const unsigned char* Bm;
+  int chunks;            // K_pad / 32 (both operands)
+  int m_tiles, n_tiles, NT, ksplit;
+  int epi;
+};
+__device__ __forceinline__ void ts_epilogue(const ModelDev& md, const TsBuf& tb, int epi, int s, int M, int N, int m, int n, int ks, float v) {
+  const LayerDev& ly = md.layer[0];
+  const int L = ly.L, ldL = ly.ldL;
+  switch (epi) {
+    case TS_EPI_F1: {       // rz = sigmoid(vec[:, L:] + H Wrz) (gru4rec.py:460)
+      if (m >= M || n >= 2 * L) return;
+      const float g = sigmoidf_(v + ly.Bh[L + n]);
+      if (n < L) ly.r[(size_t)m * ldL + n] = g; else ly.z[(size_t)m * ldL + (n - L)] = g;
+    } break;
+    case TS_EPI_F2: {       // h~ = act((H * r) Wh + vec[:, :L]); h = (1 - z) H + z h~; dropout; reset (gru4rec.py:461-466)
+      if (m >= M || n >= L) return;
+      const float a = v + ly.Bh[n];
+      const float ht = act_fwd(md.hact, a);
+      const float z = ly.z[(size_t)m * ldL + n], ho = ly.Hold[(size_t)m * ldL + n];
+      float h = (1.0f - z) * ho + z * ht;
+      if (md.p_drop_h > 0.f) h *= drop_scale(md.drop_seed, md.wG[s], 0u, (uint32_t)(m * L + n), 1.0f - md.p_drop_h);
+      ly.ah[(size_t)m * ldL + n] = a; ly.ht[(size_t)m * ldL + n] = ht; ly.y[(size_t)m * ldL + n] = h;
+      ly.H[(size_t)md.wSlot[(size_t)s * md.B + m] * ldL + n] = (md.wF[(size_t)s * md.B + m] & 1) ? 0.f : h;
+    } break;
+    case TS_EPI_SCORE:      // o = h Sy^T + by (- logq correction) (gru4rec.py:493-495)
+      if (m < M && n < N) tb.O[(size_t)m * tb.ldO + n] = v + tb.bias[n];
+      break;
+    case TS_EPI_DSY:        // dSy_j = sum_b g[b][j] h[b]
+      if (m < N && n < L) md.DSY[(size_t)m * ldL + n] = v;
+      break;
+    case TS_EPI_DH:         // partial dL/dh of K split `ks` (summed in fixed order by phase_b1)
+      if (m < M && n < L) md.part[((size_t)ks * md.B + m) * ldL + n] = v;
+      break;
+    case TS_EPI_B2: {       // da_r = (da_h Wh^T) * H * r (1 - r)
+      if (m >= M || n >= L) return;
+      const float r = ly.r[(size_t)m * ldL + n];
+      ly.dvec[(size_t)m * ly.ld3 + L + n] = v * ly.Hold[(size_t)m * ldL + n] * r * (1.f - r);
+    } break;
+    case TS_EPI_B3: {       // dL/d(gathered input row) = (dvec Wx^T) * embedding-dropout mask
+      if (m >= M || n >= L) return;
+      if (md.p_drop_e > 0.f) v *= drop_scale(md.drop_seed, md.wG[s], G4R_STREAM_EMBED, (uint32_t)(m * L + n), 1.0f - md.p_drop_e);
+      md.dSx[(size_t)m * md.ld_in0 + n] = v;
+    } break;
+    case TS_EPI_DENSE: {    // rows: [H*r | H | in0] features, columns: dvec = [da_h | da_r | da_z]  (dWh, dWrz, dWx + update, gru4rec.py:390-406)
+      if (m >= 3 * L || n >= 3 * L) return;
+      if (m < L) { if (n < L) { const size_t o = (size_t)m * ldL + n; dense_update(md, ly.Wh + o, ly.Wh_acc ? ly.Wh_acc + o : nullptr, ly.Wh_vel ? ly.Wh_vel + o : nullptr, v, (size_t)L * ldL); } }
+      else if (m < 2 * L) { if (n >= L) { const size_t o = (size_t)(m - L) * ly.ld2 + (n - L); dense_update(md, ly.Wrz + o, ly.Wrz_acc ? ly.Wrz_acc + o : nullptr, ly.Wrz_vel ? ly.Wrz_vel + o : nullptr, v, (size_t)L * ly.ld2); } }
+      else { const size_t o = (size_t)(m - 2 * L) * ly.ld3 + n; dense_update(md, ly.Wx + o, ly.Wx_acc ? ly.Wx_acc + o : nullptr, ly.Wx_vel ? ly.Wx_vel + o : nullptr, v, (size_t)L * ly.ld3); }
+    } break;
+  }
+}
+
+__global__ void __launch_bounds__(TS_THREADS, 1) k_ts_gemm(int slot, const int* base, int off, TsGemm g, TsBuf tb) {
+  extern __shared__ __align__(1024) unsigned char ts_raw[];
+  TsSmem& sm = *reinterpret_cast<TsSmem*>(ts_raw);
+  const ModelDev& md = MD; const int s = STEP_IDX;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int M = md.wM[s];
+  const int N = M + (md.wSti[s] >= 0 ? md.S : 0);
+  const int L = md.layer[0].L;
+  const int ks = blockIdx.x % g.ksplit, nt = (blockIdx.x / g.ksplit) % g.n_tiles, mt = blockIdx.x / (g.ksplit * g.n_tiles);
+  const int m0 = mt * TS_RB, n0 = nt * g.NT;
+  // tiles without any live output leave at once (dynamic batch size / column count; unused blocks of the dense-gradient product)
+  {
+    int m_lim, n_lim;
+    switch (g.epi) {
+      case TS_EPI_F1: m_lim = M; n_lim = 2 * L; break;
+      case TS_EPI_SCORE: m_lim = M; n_lim = N; break;
+      case TS_EPI_DSY: m_lim = N; n_lim = L; break;
+      case TS_EPI_DENSE: m_lim = 3 * L; n_lim = 3 * L; break;
+      default: m_lim = M; n_lim = L; break;
+    }
+    if (m0 >= m_lim || n0 >= n_lim) return;
+    if (g.epi == TS_EPI_DENSE) {
+      const int blo = m0 / L, bhi = min(m0 + TS_RB - 1, 3 * L - 1) / L;    // feature blocks the tile's rows touch
+      const bool need_lo = blo == 0 || bhi == 2, need_hi = bhi >= 1;       // columns [0, L) / [L, 3L)
+      if (!((need_lo && n0 < L) || (need_hi && n0 + g.NT > L))) return;
+    }
+  }
+  const int cps = (g.chunks + g.ksplit - 1) / g.ksplit;
+  const int c_beg = ks * cps, c_end = min(g.chunks, c_beg + cps);
+  const bool empty = c_beg >= c_end;           // a K split without chunks contributes zeros
+  if (tid == 0) {
+    for (int i = 0; i < TS_STAGES; i++) { tc_mbar_init(&sm.stage_free[i], 1); tc_mbar_init(&sm.stage_full[i], 1); }
+    tc_mbar_init(&sm.acc_full, 1);
+    sm.err = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tc_smem_u32(&sm.tmem_base)), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = sm.tmem_base;
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.NT >> 3) << 17) | ((uint32_t)(TS_RB >> 4) << 24);
+  const uint32_t b_bytes = (uint32_t)g.NT * TC_KC * 4;        // one hi (or lo) slab of the N tile
+  if (warp == 4) {
+    if (lane == 0) {
+      unsigned int it = 0;
+      const int rbB = n0 / TS_RB;
+      const uint32_t b_off = (uint32_t)((n0 % TS_RB) >> 3) * 1024u;
+      for (int c = c_beg; c < c_end; c++, it++) {
+        const uint32_t st = it % TS_STAGES, use = it / TS_STAGES;
+        if (use > 0) tc_mbar_wait(&sm.stage_free[st], (use - 1) & 1u, &sm.err);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(tc_smem_u32(&sm.stage_full[st])), "r"(2 * TS_BLK + 2 * b_bytes) : "memory");
+        tc_bulk_copy(sm.stage[st], g.A + ((size_t)mt * g.chunks + c) * 2 * TS_BLK, 2 * TS_BLK, &sm.stage_full[st]);
+        const unsigned char* bsrc = g.Bm + ((size_t)rbB * g.chunks + c) * 2 * TS_BLK + b_off;
+        tc_bulk_copy(sm.stage[st] + 2 * TS_BLK, bsrc, b_bytes, &sm.stage_full[st]);
+        tc_bulk_copy(sm.stage[st] + 2 * TS_BLK + b_bytes, bsrc + TS_BLK, b_bytes, &sm.stage_full[st]);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      unsigned int it = 0;
+      for (int c = c_beg; c < c_end; c++, it++) {
+        const uint32_t st = it % TS_STAGES, use = it / TS_STAGES;
+        tc_mbar_wait(&sm.stage_full[st], use & 1u, &sm.err);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = tc_smem_u32(sm.stage[st]), a_lo = a_hi + TS_BLK, b_hi = a_hi + 2 * TS_BLK, b_lo = b_hi + b_bytes;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const uint32_t o = (uint32_t)j * 256u;
+          tc_mma_tf32(tmem, tc_desc(a_lo + o), tc_desc(b_hi + o), idesc, (c == c_beg && j == 0) ? 0u : 1u);
+          tc_mma_tf32(tmem, tc_desc(a_hi + o), tc_desc(b_lo + o), idesc, 1u);
+          tc_mma_tf32(tmem, tc_desc(a_hi + o), tc_desc(b_hi + o), idesc, 1u);
+        }
+        tc_commit(&sm.stage_free[st]);
+      }
+      if (empty) tc_mbar_arrive(&sm.acc_full); else tc_commit(&sm.acc_full);
+    }
+  } else {
+    tc_mbar_wait(&sm.acc_full, 0u, &sm.err);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int m = m0 + warp * 32 + lane;
+    for (int q = 0; q < g.NT / 32; q++) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + q * 32;
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                   "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                     "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+                     "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+                     "=r"(r[30]), "=r"(r[31]) : "r"(taddr) : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; j++) ts_epilogue(md, tb, g.epi, s, M, N, m, n0 + q * 32 + j, ks, empty ? 0.f : __uint_as_float(r[j]));
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(128u) : "memory");
+  }
+}

@@ -66,7 +66,9 @@ typedef struct g4r_config {
   int32_t step_mode;              /* 0: one kernel per phase (CUDA-graph replay); 1: persistent cooperative kernel;
                                      2: role-specialised persistent kernel where the shape allows, else 1;
                                      3: as 2, launched as thread-block clusters: the GRU phases run on one cluster with the
-                                        dense weights and optimizer state resident in shared memory (else 1) */
+                                        dense weights and optimizer state resident in shared memory (else 1);
+                                     4: tensor-core step (tcgen05 GEMMs) whenever the model allows it -- modes 1-3 pick it
+                                        automatically for constrained-embedding models with a layer of >= 160 units */
   int32_t mg_replicated;          /* 1: multi-GPU with replicated tables + NCCL exchange instead of row sharding */
   int32_t eval_tc;                /* scoring path: 0 auto, 1 fp32 FFMA tiles only, 2 tcgen05 (3xTF32) tiles whenever the ranking is full-catalogue */
   float adapt_p1, adapt_p1c;      /* adapt_params[0] and 1 - adapt_params[0] (rmsprop / adadelta decay; adam beta1), gru4rec.py:301-304,342-343,368-369 */
@@ -149,6 +151,9 @@ const char* g4r_phase_name(int32_t i);
 /* step_mode 2: number of windows run by the role-specialised kernel, and (out) windows that fell back to the
  * generic persistent kernel because a chunk of score columns was wider than 16. */
 int64_t g4r_fast_windows(const g4r_handle* h, int64_t* fallback_windows);
+/* 1 if the handle trains with the tensor-core step (tcgen05 3xTF32 GEMMs with fused epilogues, csrc/g4r_tcstep.cuh): constrained
+ * embedding, one layer, batch <= 256, SGD / Adagrad (+momentum); automatic for layers >= 160 units, forced with step_mode 4. */
+int g4r_uses_tensor_cores(const g4r_handle* h);
 /* Persistent mode (step_mode 1): enable %globaltimer stamps at the phase boundaries of every step and/or read
  * the stamps of the last window (16 uint64 slots per step; slots 0..5 used: start, after GRU forward, after scores,
  * after statistics, after loss-gradient/update, end). */

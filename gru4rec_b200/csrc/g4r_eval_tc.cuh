@@ -69,10 +69,15 @@ __device__ __forceinline__ bool tc_mbar_wait(unsigned long long* bar, unsigned i
   }
 }
 __device__ __forceinline__ uint32_t tc_tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
-// K-major, no swizzle: 8-row x 16-byte core matrices; LBO (next core matrix along K) = 128 B, SBO (next 8 rows) = 1024 B
+// K-major operand blocks in the 128-byte-swizzle layout: a row is 32 tf32 values = 128 bytes, eight rows form a 1024-byte atom in
+// which the 16-byte piece c of row r sits at position c ^ (r % 8) (the tensor core reads a whole 128-byte row per access; the
+// unswizzled 8 x 16-byte core-matrix layout measured ~8x slower operand fetch).  SBO (next 8 rows) = 1024 B, LBO unused (1);
+// blocks are 1024-byte aligned, a K step of 8 values advances the start address by 32 bytes inside the atom.
 __device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46);
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// byte offset of the 16-byte piece (row r, k = 4 * kq .. 4 * kq + 3) inside a block of rows x 32 k-values
+__device__ __forceinline__ uint32_t tc_block_off(int r, int kq) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((kq ^ (r & 7)) << 4)); }
 __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
                :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
@@ -82,9 +87,9 @@ __device__ __forceinline__ void tc_commit(unsigned long long* bar) {
 }
 
 // Pre-split operand blocks in global memory (written once per evaluation for the item table, once per mini-batch for the hidden
-// states): block (rb, c) = rows [rb * RB, +RB) x k [32 c, +32) as [hi | lo], each in the K-major no-swizzle core-matrix layout
-// (8 rows x 16 bytes per core matrix, core (r / 8, k / 4) at ((r / 8) * 8 + k / 4) * 128 bytes).  The scoring kernel then feeds
-// the tensor cores with plain bulk copies (TMA) -- no register staging on the critical path.
+// states): block (rb, c) = rows [rb * RB, +RB) x k [32 c, +32) as [hi | lo], each in the K-major 128-byte-swizzle layout
+// (tc_block_off).  The scoring kernel then feeds the tensor cores with plain bulk copies (TMA) -- no register staging on the
+// critical path.
 template <int RB>
 __global__ void __launch_bounds__(256) k_tc_split(const float* __restrict__ src, int nrows, int ld, int K, unsigned char* __restrict__ dst, int n_chunk) {
   const int rb = blockIdx.x, c = blockIdx.y;
@@ -96,7 +101,7 @@ __global__ void __launch_bounds__(256) k_tc_split(const float* __restrict__ src,
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     const int row = rb * RB + r;
     if (row < nrows && k0 + cc * 4 < K) v = ld4(src + (size_t)row * ld + k0 + cc * 4);
-    const uint32_t off = (uint32_t)(((r >> 3) * 8 + cc) * 128 + (r & 7) * 16);
+    const uint32_t off = tc_block_off(r, cc);
     uint4 h, l;
     h.x = tc_tf32(v.x); h.y = tc_tf32(v.y); h.z = tc_tf32(v.z); h.w = tc_tf32(v.w);
     l.x = tc_tf32(v.x - __uint_as_float(h.x)); l.y = tc_tf32(v.y - __uint_as_float(h.y));
@@ -171,7 +176,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_eval_tc(int slot, int s, cons
             const uint32_t d = tmem + acc * TC_N;
             const int ksteps = (min(TC_KC, K - c * TC_KC) + 7) / 8;
             for (int j = 0; j < ksteps; j++) {
-              const uint32_t o = (uint32_t)j * 256u;     // 8 floats along K = 2 core matrices
+              const uint32_t o = (uint32_t)j * 32u;      // 8 values along K = 32 bytes inside the swizzle atom
               tc_mma_tf32(d, tc_desc(a_lo + o), tc_desc(b_hi + o), idesc, (c == 0 && j == 0) ? 0u : 1u);
               tc_mma_tf32(d, tc_desc(a_hi + o), tc_desc(b_lo + o), idesc, 1u);
               tc_mma_tf32(d, tc_desc(a_hi + o), tc_desc(b_hi + o), idesc, 1u);

@@ -480,13 +480,13 @@ static int enqueue_tc_step(g4r_handle* h, const int* base, int off) {
   LAUNCH(PH_LOSSGRAD, k_ts_prep_g<<<dim3(fillg, 3), 256, 0, st>>>(slot, base, off, tb));
   gemm(PH_LOSSGRAD, tb.A4, tb.B4, tb.Bk / TC_KC, tb.Nk / TS_RB, L, 1, TS_EPI_DSY);
   gemm(PH_LOSSGRAD, tb.A5, tb.B5, tb.Nk / TC_KC, mt, L, tb.nsplit, TS_EPI_DH);
-  LAUNCH(PH_B1, k_b1<<<std::max(1, std::min(h->n_sm, (B * L * 8 + 255) / 256)), 256, 0, st>>>(slot, base, off, 0, tb.nsplit));
+  LAUNCH(PH_B1, k_ts_b1<<<std::min(4 * h->n_sm, (B * L + 255) / 256), 256, 0, st>>>(slot, base, off, tb.nsplit));
   LAUNCH(PH_B2, k_ts_prep_b2<<<fillg, 256, 0, st>>>(slot, base, off, tb));
   gemm(PH_B2, tb.A6, tb.W3, tb.Lk1 / TC_KC, mt, L, 1, TS_EPI_B2);
   LAUNCH(PH_B3, k_ts_prep_bwd<<<dim3(fillg, 3), 256, 0, st>>>(slot, base, off, tb));
   gemm(PH_B3, tb.A7, tb.W4, tb.Lk3 / TC_KC, mt, L, 1, TS_EPI_B3);
   gemm(PH_DENSE, tb.A8, tb.B8, tb.Bk / TC_KC, (3 * L + TS_RB - 1) / TS_RB, 3 * L, 1, TS_EPI_DENSE);
-  LAUNCH(PH_DENSE, k_ts_bh<<<(3 * L + 255) / 256, 256, 0, st>>>(slot, base, off));
+  LAUNCH(PH_DENSE, k_ts_bh<<<(3 * L + 31) / 32, 256, 0, st>>>(slot, base, off));
   LAUNCH(PH_LOSSGRAD, k_apply_rows<<<md.NCH, SC_THREADS, 0, st>>>(slot, base, off));
   LAUNCH(PH_SPARSE_IN, k_sparse_in<<<B, 128, 0, st>>>(slot, base, off, 1));
   return G4R_OK;

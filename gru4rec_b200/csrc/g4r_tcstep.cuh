@@ -6,7 +6,7 @@
 //
 //   operands  fp32 values are split into hi = tf32(x), lo = tf32(x - hi) ("3xTF32": lo*hi + hi*lo + hi*hi accumulated in fp32 in
 //             TMEM reproduces the fp32 product to ~2^-21 relative) and stored as [hi | lo] blocks of 128 rows x 32 k-values in the
-//             canonical K-major UMMA layout (8 x 16-byte core matrices) by small "prep" kernels that also do the gathers
+//             K-major 128-byte-swizzle UMMA layout by small "prep" kernels that also do the gathers
 //             (Wy[item] rows of the score columns, H through the lane slots), transposes and elementwise products (H * r);
 //   GEMM      one CTA per 128 x NT output tile (NT = 32..128): a TMA thread streams the operand blocks with bulk copies into a
 //             3-stage shared-memory ring (mbarrier complete_tx), an MMA thread issues tcgen05.mma kind::tf32 (M = 128, N = NT,
@@ -39,7 +39,7 @@ struct TsSmem {
 
 __device__ __forceinline__ void ts_put4(unsigned char* base, int n_chunk, int row, int k, float4 v) {
   const int rb = row / TS_RB, r = row % TS_RB, c = k / TC_KC, kq = (k % TC_KC) >> 2;
-  unsigned char* hi = base + ((size_t)rb * n_chunk + c) * 2 * TS_BLK + (uint32_t)(((r >> 3) * 8 + kq) * 128 + (r & 7) * 16);
+  unsigned char* hi = base + ((size_t)rb * n_chunk + c) * 2 * TS_BLK + tc_block_off(r, kq);
   uint4 h, l;
   h.x = tc_tf32(v.x); h.y = tc_tf32(v.y); h.z = tc_tf32(v.z); h.w = tc_tf32(v.w);
   l.x = tc_tf32(v.x - __uint_as_float(h.x)); l.y = tc_tf32(v.y - __uint_as_float(h.y));
@@ -60,6 +60,22 @@ __device__ __forceinline__ void ts_fill(unsigned char* base, int rows_pad, int K
   }
 }
 __device__ __forceinline__ float4 ts_zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+// column sums over the lanes with 8 row groups per column and a fixed-order merge: out(col) is called once per column
+template <class FLoad, class FOut>
+__device__ __forceinline__ void ts_colsum(int n_cols, int n_rows, FLoad ld, FOut out) {
+  __shared__ float red[8][33];
+  const int cg = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  for (int c0 = blockIdx.x * 32; c0 < n_cols; c0 += gridDim.x * 32) {
+    const int c = c0 + cg;
+    float a = 0.f;
+    if (c < n_cols) for (int b = rg; b < n_rows; b += 8) a += ld(b, c);
+    red[rg][cg] = a;
+    __syncthreads();
+    if (rg == 0 && c < n_cols) { float t = 0.f; for (int k = 0; k < 8; k++) t += red[k][cg]; out(c, t); }
+    __syncthreads();
+  }
+}
+
 
 // ---- P1: A1 = [in0 | H(slot)] (lanes x 2L), compact copy of the old hidden state (gru4rec.py:459-460 operands) ----
 __global__ void __launch_bounds__(256) k_ts_prep_fwd(int slot, const int* base, int off, TsBuf tb) {
@@ -231,11 +247,27 @@ __global__ void __launch_bounds__(256) k_ts_prep_g(int slot, const int* base, in
       return make_float4(v[0], v[1], v[2], v[3]);
     });
   } else {
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
-      float a = 0.f;
-      for (int b = 0; b < M; b++) a += G[(size_t)b * tb.ldO + j];
-      md.DBY[j] = a;
-    }
+    ts_colsum(N, M, [&](int b, int j) { return G[(size_t)b * tb.ldO + j]; }, [&](int j, float t) { md.DBY[j] = t; });
+  }
+}
+// ---- b1: dL/dh = sum of the K-split partials (fixed order), then the elementwise GRU backward ----
+__global__ void __launch_bounds__(256) k_ts_b1(int slot, const int* base, int off, int nsplit) {
+  const ModelDev& md = MD; const int s = STEP_IDX;
+  const LayerDev& ly = md.layer[0];
+  const int M = md.wM[s], L = ly.L, ldL = ly.ldL;
+  const size_t cs = (size_t)md.B * ldL;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < M * L; e += gridDim.x * blockDim.x) {
+    const int b = e / L, c = e % L;
+    const size_t o = (size_t)b * ldL + c;
+    float dy = 0.f;
+    for (int k = 0; k < nsplit; k++) dy += md.part[(size_t)k * cs + o];
+    const float ht = ly.ht[o], ho = ly.Hold[o], z = ly.z[o], ah = ly.ah[o];
+    float dh = dy;
+    if (md.p_drop_h > 0.f) dh *= drop_scale(md.drop_seed, md.wG[s], 0u, (uint32_t)(b * L + c), 1.0f - md.p_drop_h);
+    const float dz = dh * (ht - ho);
+    const float dah = dh * z * act_der(md.hact, ah, ht);
+    ly.dvec[(size_t)b * ly.ld3 + c] = dah;
+    ly.dvec[(size_t)b * ly.ld3 + 2 * L + c] = dz * z * (1.f - z);
   }
 }
 // ---- P6: A6 = da_h (lanes x L) ----
@@ -281,11 +313,8 @@ __global__ void __launch_bounds__(256) k_ts_bh(int slot, const int* base, int of
   const ModelDev& md = MD; const int s = STEP_IDX;
   const LayerDev& ly = md.layer[0];
   const int M = md.wM[s];
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 3 * ly.L) return;
-  float g = 0.f;
-  for (int b = 0; b < M; b++) g += ly.dvec[(size_t)b * ly.ld3 + c];
-  dense_update(md, ly.Bh + c, ly.Bh_acc ? ly.Bh_acc + c : nullptr, ly.Bh_vel ? ly.Bh_vel + c : nullptr, g, (size_t)ly.ld3);
+  ts_colsum(3 * ly.L, M, [&](int b, int c) { return ly.dvec[(size_t)b * ly.ld3 + c]; },
+            [&](int c, float g) { dense_update(md, ly.Bh + c, ly.Bh_acc ? ly.Bh_acc + c : nullptr, ly.Bh_vel ? ly.Bh_vel + c : nullptr, g, (size_t)ly.ld3); });
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -416,7 +445,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_ts_gemm(int slot, const int* 
         const uint32_t a_hi = tc_smem_u32(sm.stage[st]), a_lo = a_hi + TS_BLK, b_hi = a_hi + 2 * TS_BLK, b_lo = b_hi + b_bytes;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          const uint32_t o = (uint32_t)j * 256u;
+          const uint32_t o = (uint32_t)j * 32u;        // 8 values along K = 32 bytes inside the swizzle atom
           tc_mma_tf32(tmem, tc_desc(a_lo + o), tc_desc(b_hi + o), idesc, (c == c_beg && j == 0) ? 0u : 1u);
           tc_mma_tf32(tmem, tc_desc(a_hi + o), tc_desc(b_lo + o), idesc, 1u);
           tc_mma_tf32(tmem, tc_desc(a_hi + o), tc_desc(b_hi + o), idesc, 1u);
@@ -428,7 +457,12 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_ts_gemm(int slot, const int* 
   } else {
     tc_mbar_wait(&sm.acc_full, 0u, &sm.err);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int m = m0 + warp * 32 + lane;
+    // TMEM lane = tile row, so a thread holds one row: the tile is transposed through shared memory (the operand stages are free
+    // once the accumulator is complete) and the epilogue then walks it with consecutive threads on consecutive columns --
+    // coalesced loads / stores of the row-major outputs and of the parameter / optimizer-state rows of the dense update
+    float* sT = reinterpret_cast<float*>(sm.stage);
+    const int ldt = g.NT + 1;
+    const int row = warp * 32 + lane;
     for (int q = 0; q < g.NT / 32; q++) {
       uint32_t r[32];
       const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + q * 32;
@@ -440,7 +474,13 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_ts_gemm(int slot, const int* 
                      "=r"(r[30]), "=r"(r[31]) : "r"(taddr) : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int j = 0; j < 32; j++) ts_epilogue(md, tb, g.epi, s, M, N, m, n0 + q * 32 + j, ks, empty ? 0.f : __uint_as_float(r[j]));
+      for (int j = 0; j < 32; j++) sT[row * ldt + q * 32 + j] = empty ? 0.f : __uint_as_float(r[j]);
+    }
+    asm volatile("bar.sync 3, 128;" ::: "memory");
+    for (int i = 0; i < g.NT; i++) {
+      const int idx = i * 128 + tid;
+      const int rr = idx / g.NT, cc = idx % g.NT;
+      ts_epilogue(md, tb, g.epi, s, M, N, m0 + rr, n0 + cc, ks, sT[rr * ldt + cc]);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

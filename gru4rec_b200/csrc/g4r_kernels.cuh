@@ -38,12 +38,29 @@ struct MgTensor { float *p, *acc, *vel; size_t goff; int count; };
 struct TsBuf {                 // device buffers of the tensor-core step (owned by the handle's workspace)
   unsigned char *A1, *A2, *A3, *A4, *A5, *A6, *A7, *A8;      // left operands  (rows x K) as hi|lo blocks
   unsigned char *W1, *W2, *W3, *W4, *B3, *B4, *B5, *B8;      // right operands (n x K)
+  float *P, *P2;                                             // partial tiles of the split-K products (main / side stream)
   float *O, *bias;                                           // scores / dL/do [Bpad x ldO] (lane-major), bias of the sorted columns [NP]
   int ldO;
   int Mpad, Lk2, Lk1, Lk3, Nk, Bk;                           // padded extents: lanes; K = 2L, L, 3L, columns, lanes (multiples of 32)
-  int nsplit;                                                // K splits of the dL/dh GEMM
 };
 
+
+// tiling of one tensor-core product (g4r_tcstep.cuh): N tile, tile counts, K splits, leading dimension / size of the partial tiles
+struct TsShape { int NT, m_tiles, n_tiles, ksplit, ldP; size_t p_floats; };
+static inline TsShape ts_shape(int rows, int cols, int chunks, int n_sm) {
+  TsShape t;
+  t.NT = cols > 128 ? 256 : 128;
+  t.m_tiles = (rows + 128 - 1) / 128; t.n_tiles = (cols + t.NT - 1) / t.NT;
+  const int tiles = t.m_tiles * t.n_tiles;
+  int ks = (n_sm - 8 + tiles - 1) / tiles;                  // about one CTA per SM
+  if (ks > chunks) ks = chunks;
+  if (ks < 1) ks = 1;
+  const int cps = (chunks + ks - 1) / ks;
+  t.ksplit = (chunks + cps - 1) / cps;                      // no empty splits
+  t.ldP = t.n_tiles * t.NT;
+  t.p_floats = (size_t)t.ksplit * t.m_tiles * 128 * t.ldP;
+  return t;
+}
 
 // ---- row-sharded multi-GPU state (g4r_shard.cuh): item tables live only on their owner (row i -> rank i % R, local row i / R);
 // peers read parameter rows and write gradient rows through peer-mapped pointers (cudaIpc) inside the persistent kernel ----

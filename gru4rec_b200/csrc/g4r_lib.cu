@@ -83,7 +83,7 @@ struct g4r_handle {
   bool two_pass = false;         // grad_cap: gradients are exported, the global norm is taken, then a second pass applies them scaled
   bool phase_only = false;       // grad_cap / smoothing add phases that only the per-phase launch sequence has
   float* dGscale = nullptr;
-  bool tc_ok = false; void* ts_buf = nullptr;      // tensor-core training step (g4r_tcstep.cuh): TsBuf*
+  bool tc_ok = false; void* ts_buf = nullptr; cudaStream_t side = nullptr; cudaEvent_t ts_ev[10] = {};      // tensor-core training step (g4r_tcstep.cuh): TsBuf*
   std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_phase;
 };
 
@@ -92,13 +92,14 @@ static const char* kPhaseNames[PH_COUNT] = {"gather_in", "gru_rz", "gru_h", "sco
                                             "smoothing_stats", "grad_cap_norm_apply"};
 
 // LAUNCH(phase, kernel<<<...>>>(...)): counts the launch and, when profiling, brackets it with CUDA events
-#define LAUNCH(ph, ...) do { \
+#define LAUNCH_ON(strm, ph, ...) do { \
     cudaEvent_t e0_ = nullptr, e1_ = nullptr; \
-    if (h->prof) { cudaEventCreate(&e0_); cudaEventCreate(&e1_); cudaEventRecord(e0_, h->stream); } \
+    if (h->prof) { cudaEventCreate(&e0_); cudaEventCreate(&e1_); cudaEventRecord(e0_, (strm)); } \
     __VA_ARGS__; \
     h->launches++; \
-    if (h->prof) { cudaEventRecord(e1_, h->stream); h->prof_ev.push_back(e0_); h->prof_ev.push_back(e1_); h->prof_phase.push_back(ph); } \
+    if (h->prof) { cudaEventRecord(e1_, (strm)); h->prof_ev.push_back(e0_); h->prof_ev.push_back(e1_); h->prof_phase.push_back(ph); } \
   } while (0)
+#define LAUNCH(ph, ...) LAUNCH_ON(h->stream, ph, __VA_ARGS__)
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return G4R_ERR_CUDA; } } while (0)
 #define FAIL(code, msg) do { h->err = (msg); return (code); } while (0)
@@ -295,12 +296,16 @@ static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
     const int L = Llast;
     tsb.Mpad = r128(B); tsb.Lk1 = r32(L); tsb.Lk2 = r32(2 * L); tsb.Lk3 = r32(3 * L); tsb.Nk = r128(NP); tsb.Bk = r32(B);
     tsb.ldO = tsb.Nk;
-    tsb.nsplit = std::max(1, std::min(NCH, (tsb.Nk / 32 + 3) / 4));
-    auto op = [&](int rows, int K) { return cv.take<unsigned char>((size_t)r128(rows) * K * 8); };   // hi + lo: 8 bytes per element
+    auto op = [&](int rows, int K) { return cv.take<unsigned char>((size_t)((rows + 255) / 256 * 256) * K * 8); };   // hi + lo: 8 bytes per element; rows padded to a 256-wide N tile
     tsb.A1 = op(B, tsb.Lk2); tsb.A2 = op(B, tsb.Lk2); tsb.A3 = op(B, tsb.Lk1); tsb.A4 = op(NP, tsb.Bk); tsb.A5 = op(B, tsb.Nk);
     tsb.A6 = op(B, tsb.Lk1); tsb.A7 = op(B, tsb.Lk3); tsb.A8 = op(3 * L, tsb.Bk);
     tsb.W1 = op(2 * L, tsb.Lk2); tsb.W2 = op(L, tsb.Lk2); tsb.W3 = op(L, tsb.Lk1); tsb.W4 = op(L, tsb.Lk3);
     tsb.B3 = op(NP, tsb.Lk1); tsb.B4 = op(L, tsb.Bk); tsb.B5 = op(L, tsb.Nk); tsb.B8 = op(3 * L, tsb.Bk);
+    size_t pf = 0;          // partial-tile buffer: the largest of the eight products (they run one after the other)
+    for (const TsShape& t : {ts_shape(B, 2 * L, tsb.Lk2 / 32, n_sm), ts_shape(B, L, tsb.Lk2 / 32, n_sm), ts_shape(B, NP, tsb.Lk1 / 32, n_sm),
+                             ts_shape(tsb.Nk, L, tsb.Bk / 32, n_sm), ts_shape(B, L, tsb.Nk / 32, n_sm), ts_shape(B, L, tsb.Lk1 / 32, n_sm),
+                             ts_shape(B, L, tsb.Lk3 / 32, n_sm), ts_shape(3 * L, 3 * L, tsb.Bk / 32, n_sm)}) pf = std::max(pf, t.p_floats);
+    tsb.P = cv.take<float>(pf); tsb.P2 = cv.take<float>(pf);        // main-stream / side-stream products
     tsb.O = cv.take<float>((size_t)tsb.Mpad * tsb.ldO); tsb.bias = cv.take<float>(tsb.Nk);
   }
   // evaluation
@@ -450,45 +455,76 @@ static bool tc_eligible(const g4r_config& c) {
   if (c.adapt > G4R_ADAPT_ADAGRAD || c.grad_cap > 0.f || c.smoothing != 0.f || c.world_size > 1) return false;
   return c.step_mode == 4 || (c.step_mode >= 1 && c.step_mode <= 3 && c.layers[0] >= 160);
 }
-static int ts_pick_nt(int m_tiles, int N, int ksplit) {       // largest N tile that still gives ~a third of the SMs a tile each
-  for (int nt = 128; nt > 32; nt >>= 1) if (m_tiles * ((N + nt - 1) / nt) * ksplit >= 48) return nt;
-  return 32;
+// one mini-batch on the tensor cores (window-relative step = *base + off when base != nullptr).  Two streams (forked / joined
+// with events, so the same code is captured into the step graph): the main stream carries the chain every product waits for,
+// the side stream prepares operands that do not depend on it (weights, item-table rows, transposed operands) and runs the
+// two products nothing downstream in the step needs (dSy -> output-row update, dense gradients -> dense update).
+template <int EPI>
+static void launch_ts_epi(g4r_handle* h, cudaStream_t st, int ph, const int* base, int off, const TsGemm& g, const TsBuf& tb, int rows, int cols) {
+  LAUNCH_ON(st, ph, k_ts_epi<EPI><<<std::min(4 * h->n_sm, std::max(1, (rows * (cols / 4) + 255) / 256)), 256, 0, st>>>(h->slot, base, off, g, tb));
 }
-// one mini-batch on the tensor cores (window-relative step = *base + off when base != nullptr)
 static int enqueue_tc_step(g4r_handle* h, const int* base, int off) {
   const ModelDev& md = h->md;
   const TsBuf& tb = *static_cast<TsBuf*>(h->ts_buf);
-  cudaStream_t st = h->stream;
+  cudaStream_t st = h->stream, sd = h->side;
+  cudaEvent_t* ev = h->ts_ev;
   const int L = md.L, B = md.B, slot = h->slot;
-  const int mt = tb.Mpad / TS_RB;
   const int fillg = 2 * h->n_sm;
-  auto gemm = [&](int ph, const unsigned char* A, const unsigned char* Bm, int chunks, int m_tiles, int Ncols, int ksplit, int epi) {
-    TsGemm g; g.A = A; g.Bm = Bm; g.chunks = chunks; g.m_tiles = m_tiles; g.ksplit = ksplit; g.epi = epi;
-    g.NT = ts_pick_nt(m_tiles, Ncols, ksplit); g.n_tiles = (Ncols + g.NT - 1) / g.NT;
-    LAUNCH(ph, k_ts_gemm<<<m_tiles * g.n_tiles * ksplit, TS_THREADS, sizeof(TsSmem), st>>>(slot, base, off, g, tb));
+  auto gemm = [&](cudaStream_t q, int ph, const unsigned char* A, const unsigned char* Bm, float* P, int chunks, int rows, int cols, int epi) -> TsGemm {
+    const TsShape t = ts_shape(rows, cols, chunks, h->n_sm);
+    TsGemm g; g.A = A; g.Bm = Bm; g.P = P; g.chunks = chunks; g.m_tiles = t.m_tiles; g.n_tiles = t.n_tiles; g.NT = t.NT; g.ksplit = t.ksplit; g.ldP = t.ldP; g.epi = epi;
+    LAUNCH_ON(q, ph, k_ts_gemm<<<t.m_tiles * t.n_tiles * t.ksplit, TS_THREADS, sizeof(TsSmem), q>>>(slot, base, off, g));
+    return g;
   };
+  auto fork = [&](int e, cudaStream_t from, cudaStream_t to) { cudaEventRecord(ev[e], from); cudaStreamWaitEvent(to, ev[e], 0); };
+  fork(0, st, sd);
+  // side: weight operands, item-table operands
+  LAUNCH_ON(sd, PH_F1, k_ts_prep_w<<<dim3(fillg, 4), 256, 0, sd>>>(slot, tb));
+  cudaEventRecord(ev[1], sd);
+  LAUNCH_ON(sd, PH_SCORE, k_ts_prep_tab<<<dim3(fillg, 3), 256, 0, sd>>>(slot, base, off, tb));
+  cudaEventRecord(ev[2], sd);
+  // main: GRU forward
   LAUNCH(PH_GATHER, k_gather_in<<<std::max(1, (B + 7) / 8), 256, 0, st>>>(slot, base, off, 1));
-  LAUNCH(PH_F1, k_ts_prep_w<<<dim3(fillg, 4), 256, 0, st>>>(slot, tb));
-  LAUNCH(PH_F1, k_ts_prep_fwd<<<dim3(fillg, 2), 256, 0, st>>>(slot, base, off, tb));
-  gemm(PH_F1, tb.A1, tb.W1, tb.Lk2 / TC_KC, mt, 2 * L, 1, TS_EPI_F1);
-  LAUNCH(PH_F2, k_ts_prep_hr<<<fillg, 256, 0, st>>>(slot, base, off, tb));
-  gemm(PH_F2, tb.A2, tb.W2, tb.Lk2 / TC_KC, mt, L, 1, TS_EPI_F2);
-  LAUNCH(PH_SCORE, k_ts_prep_score<<<dim3(fillg, 5), 256, 0, st>>>(slot, base, off, tb));
-  gemm(PH_SCORE, tb.A3, tb.B3, tb.Lk1 / TC_KC, mt, md.NP, 1, TS_EPI_SCORE);
-  LAUNCH(PH_STATS, k_ts_stats<<<B, 256, 0, st>>>(slot, base, off, tb));
+  LAUNCH(PH_F1, k_ts_prep_fwd<<<dim3(fillg, 3), 256, 0, st>>>(slot, base, off, tb));
+  cudaStreamWaitEvent(st, ev[1], 0);
+  const TsGemm g1 = gemm(st, PH_F1, tb.A1, tb.W1, tb.P, tb.Lk2 / TC_KC, B, 2 * L, TS_EPI_F1);
+  launch_ts_epi<TS_EPI_F1>(h, st, PH_F1, base, off, g1, tb, B, 2 * L);
+  fork(3, st, sd);
+  LAUNCH_ON(sd, PH_DENSE, k_ts_prep_a8<<<fillg, 256, 0, sd>>>(slot, base, off, tb));
+  const TsGemm g2 = gemm(st, PH_F2, tb.A2, tb.W2, tb.P, tb.Lk2 / TC_KC, B, L, TS_EPI_F2);
+  launch_ts_epi<TS_EPI_F2>(h, st, PH_F2, base, off, g2, tb, B, L);
+  fork(4, st, sd);
+  LAUNCH_ON(sd, PH_LOSSGRAD, k_ts_prep_yt<<<fillg, 256, 0, sd>>>(slot, base, off, tb));
+  // main: scores, loss, dL/do
+  cudaStreamWaitEvent(st, ev[2], 0);
+  const TsGemm g3 = gemm(st, PH_SCORE, tb.A3, tb.B3, tb.P, tb.Lk1 / TC_KC, B, md.NP, TS_EPI_SCORE);
+  LAUNCH(PH_STATS, k_ts_stats<<<B, 256, 0, st>>>(slot, base, off, g3, tb));
   LAUNCH(PH_LOSSGRAD, k_ts_lossgrad<<<B, 256, 0, st>>>(slot, base, off, tb));
-  LAUNCH(PH_LOSSGRAD, k_ts_prep_g<<<dim3(fillg, 3), 256, 0, st>>>(slot, base, off, tb));
-  gemm(PH_LOSSGRAD, tb.A4, tb.B4, tb.Bk / TC_KC, tb.Nk / TS_RB, L, 1, TS_EPI_DSY);
-  gemm(PH_LOSSGRAD, tb.A5, tb.B5, tb.Nk / TC_KC, mt, L, tb.nsplit, TS_EPI_DH);
-  LAUNCH(PH_B1, k_ts_b1<<<std::min(4 * h->n_sm, (B * L + 255) / 256), 256, 0, st>>>(slot, base, off, tb.nsplit));
-  LAUNCH(PH_B2, k_ts_prep_b2<<<fillg, 256, 0, st>>>(slot, base, off, tb));
-  gemm(PH_B2, tb.A6, tb.W3, tb.Lk1 / TC_KC, mt, L, 1, TS_EPI_B2);
-  LAUNCH(PH_B3, k_ts_prep_bwd<<<dim3(fillg, 3), 256, 0, st>>>(slot, base, off, tb));
-  gemm(PH_B3, tb.A7, tb.W4, tb.Lk3 / TC_KC, mt, L, 1, TS_EPI_B3);
-  gemm(PH_DENSE, tb.A8, tb.B8, tb.Bk / TC_KC, (3 * L + TS_RB - 1) / TS_RB, 3 * L, 1, TS_EPI_DENSE);
-  LAUNCH(PH_DENSE, k_ts_bh<<<(3 * L + 31) / 32, 256, 0, st>>>(slot, base, off));
-  LAUNCH(PH_LOSSGRAD, k_apply_rows<<<md.NCH, SC_THREADS, 0, st>>>(slot, base, off));
+  fork(5, st, sd);
+  // side: dSy product and the update of the scored rows
+  LAUNCH_ON(sd, PH_LOSSGRAD, k_ts_prep_g<<<dim3(fillg, 2), 256, 0, sd>>>(slot, base, off, tb));
+  const TsGemm g4 = gemm(sd, PH_LOSSGRAD, tb.A4, tb.B4, tb.P2, tb.Bk / TC_KC, tb.Nk, L, TS_EPI_DSY);
+  launch_ts_epi<TS_EPI_DSY>(h, sd, PH_LOSSGRAD, base, off, g4, tb, tb.Nk, L);
+  LAUNCH_ON(sd, PH_LOSSGRAD, k_apply_rows<<<md.NCH, SC_THREADS, 0, sd>>>(slot, base, off));
+  cudaEventRecord(ev[6], sd);
+  // main: GRU backward
+  const TsGemm g5 = gemm(st, PH_LOSSGRAD, tb.A5, tb.B5, tb.P, tb.Nk / TC_KC, B, L, TS_EPI_DH);
+  LAUNCH(PH_B1, k_ts_b1<<<std::min(4 * h->n_sm, (B * (L / 4) + 255) / 256), 256, 0, st>>>(slot, base, off, g5, tb));
+  const TsGemm g6 = gemm(st, PH_B2, tb.A6, tb.W3, tb.P, tb.Lk1 / TC_KC, B, L, TS_EPI_B2);
+  launch_ts_epi<TS_EPI_B2>(h, st, PH_B2, base, off, g6, tb, B, L);
+  fork(7, st, sd);
+  // side: dense gradients + update
+  LAUNCH_ON(sd, PH_DENSE, k_ts_prep_b8<<<fillg, 256, 0, sd>>>(slot, base, off, tb));
+  const TsGemm g8 = gemm(sd, PH_DENSE, tb.A8, tb.B8, tb.P2, tb.Bk / TC_KC, 3 * L, 3 * L, TS_EPI_DENSE);
+  launch_ts_epi<TS_EPI_DENSE>(h, sd, PH_DENSE, base, off, g8, tb, 3 * L, 3 * L);
+  LAUNCH_ON(sd, PH_DENSE, k_ts_bh<<<(3 * L + 31) / 32, 256, 0, sd>>>(slot, base, off));
+  cudaEventRecord(ev[8], sd);
+  // main: dL/d(input rows), then the input-row update (after the scored-row update: both touch the shared table)
+  const TsGemm g7 = gemm(st, PH_B3, tb.A7, tb.W4, tb.P, tb.Lk3 / TC_KC, B, L, TS_EPI_B3);
+  launch_ts_epi<TS_EPI_B3>(h, st, PH_B3, base, off, g7, tb, B, L);
+  cudaStreamWaitEvent(st, ev[6], 0);
   LAUNCH(PH_SPARSE_IN, k_sparse_in<<<B, 128, 0, st>>>(slot, base, off, 1));
+  cudaStreamWaitEvent(st, ev[8], 0);
   return G4R_OK;
 }
 
@@ -577,6 +613,8 @@ extern "C" int g4r_destroy(g4r_handle* h) {
   if (h->hCost) cudaFreeHost(h->hCost);
   if (h->hFlags) cudaFreeHost(h->hFlags);
   if (h->own_ws && h->ws) cudaFree(h->ws);
+  if (h->side) cudaStreamDestroy(h->side);
+  for (cudaEvent_t e : h->ts_ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return G4R_OK;
@@ -619,6 +657,8 @@ extern "C" int g4r_create(const g4r_config* cfg, void* device_workspace, size_t 
   h->ws_bytes = need;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(G4R_ERR_CUDA, "stream create failed");
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
+  if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess) return bail(G4R_ERR_CUDA, "stream create failed");
+  for (cudaEvent_t& e : h->ts_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   if (cudaMemsetAsync(h->ws, 0, need, h->stream) != cudaSuccess) return bail(G4R_ERR_CUDA, "memset failed");
   // 256-byte align the carve base
   char* base = (char*)align_up((size_t)h->ws, 256);

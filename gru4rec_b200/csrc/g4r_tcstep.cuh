@@ -20,22 +20,11 @@
 
 constexpr int TS_RB = 128;                               // rows per operand block
 constexpr uint32_t TS_BLK = TS_RB * TC_KC * 4;           // bytes of one hi (or lo) block: 16 KB
-constexpr int TS_STAGES = 3;
-constexpr int TS_NT_MAX = 128;
-constexpr uint32_t TS_STAGE_BYTES = 2 * TS_BLK + 2 * TS_NT_MAX * TC_KC * 4;   // 64 KB
 constexpr int TS_THREADS = 192;                          // 4 epilogue warps + TMA warp + MMA warp
 
-enum { TS_EPI_F1 = 0, TS_EPI_F2, TS_EPI_SCORE, TS_EPI_DSY, TS_EPI_DH, TS_EPI_B2, TS_EPI_B3, TS_EPI_DENSE };
+enum { TS_EPI_F1 = 0, TS_EPI_F2, TS_EPI_SCORE, TS_EPI_DSY, TS_EPI_DH, TS_EPI_B2, TS_EPI_B3, TS_EPI_DENSE };   // SCORE / DH: the sum of the splits is folded into k_ts_stats / k_ts_b1
 
 
-struct TsSmem {
-  alignas(1024) unsigned char stage[TS_STAGES][TS_STAGE_BYTES];
-  alignas(8) unsigned long long stage_full[TS_STAGES];
-  unsigned long long stage_free[TS_STAGES];
-  unsigned long long acc_full;
-  uint32_t tmem_base;
-  int err;
-};
 
 __device__ __forceinline__ void ts_put4(unsigned char* base, int n_chunk, int row, int k, float4 v) {
   const int rb = row / TS_RB, r = row % TS_RB, c = k / TC_KC, kq = (k % TC_KC) >> 2;
@@ -77,7 +66,16 @@ __device__ __forceinline__ void ts_colsum(int n_cols, int n_rows, FLoad ld, FOut
 }
 
 
-// ---- P1: A1 = [in0 | H(slot)] (lanes x 2L), compact copy of the old hidden state (gru4rec.py:459-460 operands) ----
+struct TsGemm {
+  const unsigned char* A; const unsigned char* Bm;
+  float* P;              // partial tiles [ksplit][m_tiles * 128][ldP]
+  int chunks;            // K_pad / 32 (both operands)
+  int m_tiles, n_tiles, NT, ksplit, ldP;
+  int epi;
+};
+
+// ---- P1: A1 = [in0 | H(slot)] (lanes x 2L), the in0 half of A2 = [in0 | Hold * r], compact copy of the old hidden state
+// (gru4rec.py:459-461 operands); the Hold * r half of A2 comes from the gate epilogue ----
 __global__ void __launch_bounds__(256) k_ts_prep_fwd(int slot, const int* base, int off, TsBuf tb) {
   const ModelDev& md = MD; const int s = STEP_IDX;
   const LayerDev& ly = md.layer[0];
@@ -90,6 +88,12 @@ __global__ void __launch_bounds__(256) k_ts_prep_fwd(int slot, const int* base, 
       const int sl = (md.wF[(size_t)s * md.B + b] & 2) ? -1 : md.wSlot[(size_t)s * md.B + b];
       return sl >= 0 ? ld4(ly.H + (size_t)sl * ldL + (k - L)) : ts_zero4();
     });
+  } else if (blockIdx.y == 1) {
+    const int n_chunk = tb.Lk2 / TC_KC;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M * (L / 4); i += gridDim.x * blockDim.x) {
+      const int b = i / (L / 4), k = (i % (L / 4)) * 4;
+      ts_put4(tb.A2, n_chunk, b, k, ld4(md.in0 + (size_t)b * md.ld_in0 + k));
+    }
   } else {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M * (ldL / 4); i += gridDim.x * blockDim.x) {
       const int b = i / (ldL / 4), c4 = i % (ldL / 4);
@@ -126,23 +130,9 @@ __global__ void __launch_bounds__(256) k_ts_prep_w(int slot, TsBuf tb) {
     ts_fill(tb.W4, (L + TS_RB - 1) / TS_RB * TS_RB, tb.Lk3, true, [&](int n, int k) -> float4 { return (n < L && k < 3 * L) ? ld4(Wx + (size_t)n * ly.ld3 + k) : ts_zero4(); });
   }
 }
-// ---- P3: A2 = [in0 | Hold * r] ----
-__global__ void __launch_bounds__(256) k_ts_prep_hr(int slot, const int* base, int off, TsBuf tb) {
-  const ModelDev& md = MD; const int s = STEP_IDX;
-  const LayerDev& ly = md.layer[0];
-  const int M = md.wM[s], L = ly.L, ldL = ly.ldL;
-  ts_fill(tb.A2, tb.Mpad, tb.Lk2, true, [&](int b, int k) -> float4 {
-    if (b >= M) return ts_zero4();
-    if (k < L) return ld4(md.in0 + (size_t)b * md.ld_in0 + k);
-    if (k - L >= L) return ts_zero4();
-    const float4 h = ld4(ly.Hold + (size_t)b * ldL + (k - L)), r = ld4(ly.r + (size_t)b * ldL + (k - L));
-    return make_float4(h.x * r.x, h.y * r.y, h.z * r.z, h.w * r.w);
-  });
-}
-// ---- P4: operands of the score GEMM and of its two gradients ----
-//   A3 (b, k < L) = h[b][k];  B3 (j, k < L) = Wy[item_j][k];  B5 (c < L, k = j) = Wy[item_j][c];  B4 (c < L, k = b) = h[b][c]
-//   bias[j] = By[item_j] - logq * log(P0 ...) (gru4rec.py:486-495)
-__global__ void __launch_bounds__(256) k_ts_prep_score(int slot, const int* base, int off, TsBuf tb) {
+// ---- P3: item-table operands of the score product and of dL/dh (they depend on the previous step's sparse update only) ----
+//   B3 (j, k < L) = Wy[item_j][k];  B5 (c < L, k = j) = Wy[item_j][c];  bias[j] = By[item_j] - logq * log(P0 ...) (gru4rec.py:486-495)
+__global__ void __launch_bounds__(256) k_ts_prep_tab(int slot, const int* base, int off, TsBuf tb) {
   const ModelDev& md = MD; const int s = STEP_IDX;
   const LayerDev& ly = md.layer[0];
   const int M = md.wM[s], L = ly.L, ldL = ly.ldL;
@@ -150,19 +140,11 @@ __global__ void __launch_bounds__(256) k_ts_prep_score(int slot, const int* base
   const int* __restrict__ pItem = md.pItem + (size_t)s * md.NP;
   const float* __restrict__ Wy = md.Wy;
   if (blockIdx.y == 0) {
-    ts_fill(tb.A3, tb.Mpad, tb.Lk1, true, [&](int b, int k) -> float4 { return (b < M && k < L) ? ld4(ly.y + (size_t)b * ldL + k) : ts_zero4(); });
-  } else if (blockIdx.y == 1) {
     ts_fill(tb.B3, tb.Nk, tb.Lk1, true, [&](int j, int k) -> float4 { return (j < N && k < L) ? ld4(Wy + (size_t)pItem[j] * ldL + k) : ts_zero4(); });
-  } else if (blockIdx.y == 2) {
+  } else if (blockIdx.y == 1) {
     ts_fill(tb.B5, (L + TS_RB - 1) / TS_RB * TS_RB, tb.Nk, false, [&](int c, int k) -> float4 {
       float v[4];
       for (int u = 0; u < 4; u++) { const int j = k + u; v[u] = (c < L && j < N) ? Wy[(size_t)pItem[j] * ldL + c] : 0.f; }
-      return make_float4(v[0], v[1], v[2], v[3]);
-    });
-  } else if (blockIdx.y == 3) {
-    ts_fill(tb.B4, (L + TS_RB - 1) / TS_RB * TS_RB, tb.Bk, false, [&](int c, int k) -> float4 {
-      float v[4];
-      for (int u = 0; u < 4; u++) { const int b = k + u; v[u] = (c < L && b < M) ? ly.y[(size_t)b * ldL + c] : 0.f; }
       return make_float4(v[0], v[1], v[2], v[3]);
     });
   } else {
@@ -175,9 +157,42 @@ __global__ void __launch_bounds__(256) k_ts_prep_score(int slot, const int* base
     }
   }
 }
+// ---- P4: left operand of the dense-gradient product, A8 (m < 3L, k = b) = [Hold*r ; Hold ; in0]^T (known once the gates are) ----
+__global__ void __launch_bounds__(256) k_ts_prep_a8(int slot, const int* base, int off, TsBuf tb) {
+  const ModelDev& md = MD; const int s = STEP_IDX;
+  const LayerDev& ly = md.layer[0];
+  const int M = md.wM[s], L = ly.L, ldL = ly.ldL;
+  const int R3 = (3 * L + TS_RB - 1) / TS_RB * TS_RB;
+  ts_fill(tb.A8, R3, tb.Bk, false, [&](int mrow, int k) -> float4 {
+    float v[4];
+    for (int u = 0; u < 4; u++) {
+      const int b = k + u;
+      float x = 0.f;
+      if (mrow < 3 * L && b < M) {
+        if (mrow < L) x = ly.Hold[(size_t)b * ldL + mrow] * ly.r[(size_t)b * ldL + mrow];
+        else if (mrow < 2 * L) x = ly.Hold[(size_t)b * ldL + mrow - L];
+        else x = md.in0[(size_t)b * md.ld_in0 + mrow - 2 * L];
+      }
+      v[u] = x;
+    }
+    return make_float4(v[0], v[1], v[2], v[3]);
+  });
+}
+// ---- P5: B4 (c < L, k = b) = h[b][c] (right operand of dSy) ----
+__global__ void __launch_bounds__(256) k_ts_prep_yt(int slot, const int* base, int off, TsBuf tb) {
+  const ModelDev& md = MD; const int s = STEP_IDX;
+  const LayerDev& ly = md.layer[0];
+  const int M = md.wM[s], L = ly.L, ldL = ly.ldL;
+  ts_fill(tb.B4, (L + TS_RB - 1) / TS_RB * TS_RB, tb.Bk, false, [&](int c, int k) -> float4 {
+    float v[4];
+    for (int u = 0; u < 4; u++) { const int b = k + u; v[u] = (c < L && b < M) ? ly.y[(size_t)b * ldL + c] : 0.f; }
+    return make_float4(v[0], v[1], v[2], v[3]);
+  });
+}
 
-// ---- row statistics of the losses straight from the lane-major score matrix (same merge as phase_score / phase_stats) ----
-__global__ void __launch_bounds__(256) k_ts_stats(int slot, const int* base, int off, TsBuf tb) {
+// ---- scores o = sum of the K-split partials + bias, written lane-major, and the row statistics of the losses in the same pass
+// (same merge as phase_score / phase_stats) ----
+__global__ void __launch_bounds__(256) k_ts_stats(int slot, const int* base, int off, TsGemm g, TsBuf tb) {
   const ModelDev& md = MD; const int s = STEP_IDX;
   const int M = md.wM[s];
   const int N = M + (md.wSti[s] >= 0 ? md.S : 0);
@@ -185,12 +200,25 @@ __global__ void __launch_bounds__(256) k_ts_stats(int slot, const int* base, int
   if (b >= M) return;
   __shared__ float sW[8 * 8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* orow = tb.O + (size_t)b * tb.ldO;
+  float* orow = tb.O + (size_t)b * tb.ldO;
+  const float* prow = g.P + (size_t)b * g.ldP;
+  const size_t ps = (size_t)g.m_tiles * TS_RB * g.ldP;
   const int tc = md.pTcol[(size_t)s * md.B + b];
   const bool pw = loss_pairwise(md.loss);
-  const float t = pw ? act_fwd(md.fact, orow[tc]) : 0.f;
+  float t = 0.f;
+  if (pw) { float o = prow[tc]; for (int k = 1; k < g.ksplit; k++) o += prow[k * ps + tc]; t = act_fwd(md.fact, o + tb.bias[tc]); }
   float m = -INFINITY, Z = 0.f, A = 0.f, Q = 0.f, D = 0.f, T = 0.f, has = 0.f;
-  for (int j = tid; j < N; j += blockDim.x) stat_add_elem(md, orow[j], j == tc, t, m, Z, A, Q, D, T, has);
+  for (int j = tid * 4; j < N; j += blockDim.x * 4) {
+    float4 v = ld4(prow + j);
+    for (int k = 1; k < g.ksplit; k++) { const float4 w = ld4(prow + k * ps + j); v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
+    const float4 bz = ld4(tb.bias + j);
+    v.x += bz.x; v.y += bz.y; v.z += bz.z; v.w += bz.w;
+    st4(orow + j, v);
+    stat_add_elem(md, v.x, j == tc, t, m, Z, A, Q, D, T, has);
+    if (j + 1 < N) stat_add_elem(md, v.y, j + 1 == tc, t, m, Z, A, Q, D, T, has);
+    if (j + 2 < N) stat_add_elem(md, v.z, j + 2 == tc, t, m, Z, A, Q, D, T, has);
+    if (j + 3 < N) stat_add_elem(md, v.w, j + 3 == tc, t, m, Z, A, Q, D, T, has);
+  }
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {   // fixed butterfly order
     const float m2 = __shfl_xor_sync(0xffffffffu, m, o), Z2 = __shfl_xor_sync(0xffffffffu, Z, o), A2 = __shfl_xor_sync(0xffffffffu, A, o),
@@ -206,7 +234,7 @@ __global__ void __launch_bounds__(256) k_ts_stats(int slot, const int* base, int
     stats_finalize(md, b, M, N, m, Z, A, Q, D, T, t);
   }
 }
-// ---- dL/do in place (lane-major), cost of the step ----
+// ---- dL/do in place (lane-major) and as the left operand A5 (b, k = j) of the dL/dh product, cost of the step ----
 __global__ void __launch_bounds__(256) k_ts_lossgrad(int slot, const int* base, int off, TsBuf tb) {
   const ModelDev& md = MD; const int s = STEP_IDX;
   const int M = md.wM[s];
@@ -218,7 +246,19 @@ __global__ void __launch_bounds__(256) k_ts_lossgrad(int slot, const int* base, 
   __syncthreads();
   const int tc = md.pTcol[(size_t)s * md.B + b];
   float* orow = tb.O + (size_t)b * tb.ldO;
-  for (int j = threadIdx.x; j < N; j += blockDim.x) orow[j] = loss_grad_elem(md, sRS, orow[j], j == tc, M, N);
+  const int n_chunk = tb.Nk / TC_KC;
+  for (int j = threadIdx.x * 4; j < tb.Nk; j += blockDim.x * 4) {      // the K padding of A5 beyond the live columns is rewritten with zeros
+    float4 v = ts_zero4();
+    if (j < N) {
+      v = ld4(orow + j);
+      v.x = loss_grad_elem(md, sRS, v.x, j == tc, M, N);
+      v.y = j + 1 < N ? loss_grad_elem(md, sRS, v.y, j + 1 == tc, M, N) : 0.f;
+      v.z = j + 2 < N ? loss_grad_elem(md, sRS, v.z, j + 2 == tc, M, N) : 0.f;
+      v.w = j + 3 < N ? loss_grad_elem(md, sRS, v.w, j + 3 == tc, M, N) : 0.f;
+      st4(orow + j, v);
+    }
+    ts_put4(tb.A5, n_chunk, b, j, v);
+  }
   if (b == 0 && threadIdx.x == 0) {
     float c = 0.f;
     for (int bb = 0; bb < M; bb++) c += md.RS[(size_t)bb * G4R_NSTAT + 6];
@@ -227,20 +267,13 @@ __global__ void __launch_bounds__(256) k_ts_lossgrad(int slot, const int* base, 
     if (c != c) atomicExch(md.nanflag, 1);
   }
 }
-// ---- P5: operands of the two score gradients from G = dL/do: A5 (b, k = j) = G[b][j]; A4 (j, k = b) = G[b][j]; dby[j] = sum_b G[b][j] ----
+// ---- P6: A4 (j, k = b) = G[b][j] (left operand of dSy); dby[j] = sum_b G[b][j] ----
 __global__ void __launch_bounds__(256) k_ts_prep_g(int slot, const int* base, int off, TsBuf tb) {
   const ModelDev& md = MD; const int s = STEP_IDX;
   const int M = md.wM[s];
   const int N = M + (md.wSti[s] >= 0 ? md.S : 0);
   const float* __restrict__ G = tb.O;
   if (blockIdx.y == 0) {
-    ts_fill(tb.A5, tb.Mpad, tb.Nk, true, [&](int b, int k) -> float4 {
-      if (b >= M || k >= N) return ts_zero4();
-      float4 v = ld4(G + (size_t)b * tb.ldO + k);       // ldO, N offsets are multiples of 4
-      if (k + 1 >= N) v.y = 0.f; if (k + 2 >= N) v.z = 0.f; if (k + 3 >= N) v.w = 0.f;
-      return v;
-    });
-  } else if (blockIdx.y == 1) {
     ts_fill(tb.A4, tb.Nk, tb.Bk, false, [&](int j, int k) -> float4 {
       float v[4];
       for (int u = 0; u < 4; u++) { const int b = k + u; v[u] = (j < N && b < M) ? G[(size_t)b * tb.ldO + j] : 0.f; }
@@ -250,63 +283,49 @@ __global__ void __launch_bounds__(256) k_ts_prep_g(int slot, const int* base, in
     ts_colsum(N, M, [&](int b, int j) { return G[(size_t)b * tb.ldO + j]; }, [&](int j, float t) { md.DBY[j] = t; });
   }
 }
-// ---- b1: dL/dh = sum of the K-split partials (fixed order), then the elementwise GRU backward ----
-__global__ void __launch_bounds__(256) k_ts_b1(int slot, const int* base, int off, int nsplit) {
+// ---- b1: dL/dh = sum of the K-split partials (fixed order), then the elementwise GRU backward;
+// da_h / da_z go to dvec and straight into the operands A6 = da_h and A7 = dvec ----
+__global__ void __launch_bounds__(256) k_ts_b1(int slot, const int* base, int off, TsGemm g, TsBuf tb) {
   const ModelDev& md = MD; const int s = STEP_IDX;
   const LayerDev& ly = md.layer[0];
-  const int M = md.wM[s], L = ly.L, ldL = ly.ldL;
-  const size_t cs = (size_t)md.B * ldL;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < M * L; e += gridDim.x * blockDim.x) {
-    const int b = e / L, c = e % L;
+  const int M = md.wM[s], L = ly.L, ldL = ly.ldL, L4 = L / 4;
+  const size_t ps = (size_t)g.m_tiles * TS_RB * g.ldP;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < M * L4; e += gridDim.x * blockDim.x) {
+    const int b = e / L4, c = (e % L4) * 4;
     const size_t o = (size_t)b * ldL + c;
-    float dy = 0.f;
-    for (int k = 0; k < nsplit; k++) dy += md.part[(size_t)k * cs + o];
-    const float ht = ly.ht[o], ho = ly.Hold[o], z = ly.z[o], ah = ly.ah[o];
-    float dh = dy;
-    if (md.p_drop_h > 0.f) dh *= drop_scale(md.drop_seed, md.wG[s], 0u, (uint32_t)(b * L + c), 1.0f - md.p_drop_h);
-    const float dz = dh * (ht - ho);
-    const float dah = dh * z * act_der(md.hact, ah, ht);
-    ly.dvec[(size_t)b * ly.ld3 + c] = dah;
-    ly.dvec[(size_t)b * ly.ld3 + 2 * L + c] = dz * z * (1.f - z);
+    const float* p = g.P + (size_t)b * g.ldP + c;
+    float4 dy = ld4(p);
+    for (int k = 1; k < g.ksplit; k++) { const float4 w = ld4(p + k * ps); dy.x += w.x; dy.y += w.y; dy.z += w.z; dy.w += w.w; }
+    const float4 ht = ld4(ly.ht + o), ho = ld4(ly.Hold + o), z = ld4(ly.z + o), ah = ld4(ly.ah + o);
+    float dyv[4] = {dy.x, dy.y, dy.z, dy.w};
+    const float htv[4] = {ht.x, ht.y, ht.z, ht.w}, hov[4] = {ho.x, ho.y, ho.z, ho.w}, zv[4] = {z.x, z.y, z.z, z.w}, ahv[4] = {ah.x, ah.y, ah.z, ah.w};
+    float dah[4], dz[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      float dh = dyv[u];
+      if (md.p_drop_h > 0.f) dh *= drop_scale(md.drop_seed, md.wG[s], 0u, (uint32_t)(b * L + c + u), 1.0f - md.p_drop_h);
+      dah[u] = dh * zv[u] * act_der(md.hact, ahv[u], htv[u]);
+      dz[u] = dh * (htv[u] - hov[u]) * zv[u] * (1.f - zv[u]);
+    }
+    const float4 a4 = make_float4(dah[0], dah[1], dah[2], dah[3]), z4 = make_float4(dz[0], dz[1], dz[2], dz[3]);
+    st4(ly.dvec + (size_t)b * ly.ld3 + c, a4);
+    st4(ly.dvec + (size_t)b * ly.ld3 + 2 * L + c, z4);
+    ts_put4(tb.A6, tb.Lk1 / TC_KC, b, c, a4);
+    ts_put4(tb.A7, tb.Lk3 / TC_KC, b, c, a4);
+    ts_put4(tb.A7, tb.Lk3 / TC_KC, b, 2 * L + c, z4);
   }
 }
-// ---- P6: A6 = da_h (lanes x L) ----
-__global__ void __launch_bounds__(256) k_ts_prep_b2(int slot, const int* base, int off, TsBuf tb) {
+// ---- P7: B8 (n < 3L, k = b) = dvec^T (right operand of the dense-gradient product) ----
+__global__ void __launch_bounds__(256) k_ts_prep_b8(int slot, const int* base, int off, TsBuf tb) {
   const ModelDev& md = MD; const int s = STEP_IDX;
   const LayerDev& ly = md.layer[0];
   const int M = md.wM[s], L = ly.L;
-  ts_fill(tb.A6, tb.Mpad, tb.Lk1, true, [&](int b, int k) -> float4 { return (b < M && k < L) ? ld4(ly.dvec + (size_t)b * ly.ld3 + k) : ts_zero4(); });
-}
-// ---- P7: A7 = dvec (lanes x 3L); A8 (m < 3L, k = b) = [Hold*r ; Hold ; in0]^T; B8 (n < 3L, k = b) = dvec^T ----
-__global__ void __launch_bounds__(256) k_ts_prep_bwd(int slot, const int* base, int off, TsBuf tb) {
-  const ModelDev& md = MD; const int s = STEP_IDX;
-  const LayerDev& ly = md.layer[0];
-  const int M = md.wM[s], L = ly.L, ldL = ly.ldL;
   const int R3 = (3 * L + TS_RB - 1) / TS_RB * TS_RB;
-  if (blockIdx.y == 0) {
-    ts_fill(tb.A7, tb.Mpad, tb.Lk3, true, [&](int b, int k) -> float4 { return (b < M && k < 3 * L) ? ld4(ly.dvec + (size_t)b * ly.ld3 + k) : ts_zero4(); });
-  } else if (blockIdx.y == 1) {
-    ts_fill(tb.A8, R3, tb.Bk, false, [&](int mrow, int k) -> float4 {
-      float v[4];
-      for (int u = 0; u < 4; u++) {
-        const int b = k + u;
-        float x = 0.f;
-        if (mrow < 3 * L && b < M) {
-          if (mrow < L) x = ly.Hold[(size_t)b * ldL + mrow] * ly.r[(size_t)b * ldL + mrow];
-          else if (mrow < 2 * L) x = ly.Hold[(size_t)b * ldL + mrow - L];
-          else x = md.in0[(size_t)b * md.ld_in0 + mrow - 2 * L];
-        }
-        v[u] = x;
-      }
-      return make_float4(v[0], v[1], v[2], v[3]);
-    });
-  } else {
-    ts_fill(tb.B8, R3, tb.Bk, false, [&](int n, int k) -> float4 {
-      float v[4];
-      for (int u = 0; u < 4; u++) { const int b = k + u; v[u] = (n < 3 * L && b < M) ? ly.dvec[(size_t)b * ly.ld3 + n] : 0.f; }
-      return make_float4(v[0], v[1], v[2], v[3]);
-    });
-  }
+  ts_fill(tb.B8, R3, tb.Bk, false, [&](int n, int k) -> float4 {
+    float v[4];
+    for (int u = 0; u < 4; u++) { const int b = k + u; v[u] = (n < 3 * L && b < M) ? ly.dvec[(size_t)b * ly.ld3 + n] : 0.f; }
+    return make_float4(v[0], v[1], v[2], v[3]);
+  });
 }
 // ---- dBh = sum_b dvec (gru4rec.py:462 bias gradient) with its update ----
 __global__ void __launch_bounds__(256) k_ts_bh(int slot, const int* base, int off) {
@@ -318,62 +337,112 @@ __global__ void __launch_bounds__(256) k_ts_bh(int slot, const int* base, int of
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// the GEMM: D[128 x NT] (+)= A[128 x K] B[NT x K]^T, 3xTF32, fused epilogue
+// the GEMM: P[ks][128 x NT tile] = A[128 x K_ks] B[NT x K_ks]^T, 3xTF32.  A tcgen05.mma costs ~150 cycles to issue whatever its
+// N (scripts/micro/mma_rate.cu), so the tiles are as wide as the instruction allows (N = 256 wherever the product has more than
+// 128 columns) and the parallelism comes from splitting K over CTAs: every CTA writes its raw partial tile, a light elementwise
+// kernel (k_ts_epi) adds the K splits in fixed order and applies the fused epilogue with coalesced accesses.
 // ---------------------------------------------------------------------------------------------------------------------
-struct TsGemm {
-  const unsigned char* A; const unsigned char* Bm;
-  int chunks;            // K_pad / 32 (both operands)
-  int m_tiles, n_tiles, NT, ksplit;
-  int epi;
-};
-__device__ __forceinline__ void ts_epilogue(const ModelDev& md, const TsBuf& tb, int epi, int s, int M, int N, int m, int n, int ks, float v) {
+// live extent of a product at this step (dynamic mini-batch size / column count)
+__device__ __forceinline__ void ts_limits(const ModelDev& md, int epi, int M, int N, int& m_lim, int& n_lim) {
+  const int L = md.layer[0].L;
+  switch (epi) {
+    case TS_EPI_F1: m_lim = M; n_lim = 2 * L; break;
+    case TS_EPI_SCORE: m_lim = M; n_lim = N; break;
+    case TS_EPI_DSY: m_lim = N; n_lim = L; break;
+    case TS_EPI_DENSE: m_lim = 3 * L; n_lim = 3 * L; break;
+    default: m_lim = M; n_lim = L; break;
+  }
+}
+// fused epilogue of four consecutive columns (m, n .. n+3) of a product; every live extent along n is a multiple of 4 (L % 4 == 0)
+template <int EPI>
+__device__ __forceinline__ void ts_epilogue4(const ModelDev& md, const TsBuf& tb, int s, int m, int n, float4 v) {
   const LayerDev& ly = md.layer[0];
   const int L = ly.L, ldL = ly.ldL;
-  switch (epi) {
-    case TS_EPI_F1: {       // rz = sigmoid(vec[:, L:] + H Wrz) (gru4rec.py:460)
-      if (m >= M || n >= 2 * L) return;
-      const float g = sigmoidf_(v + ly.Bh[L + n]);
-      if (n < L) ly.r[(size_t)m * ldL + n] = g; else ly.z[(size_t)m * ldL + (n - L)] = g;
-    } break;
-    case TS_EPI_F2: {       // h~ = act((H * r) Wh + vec[:, :L]); h = (1 - z) H + z h~; dropout; reset (gru4rec.py:461-466)
-      if (m >= M || n >= L) return;
-      const float a = v + ly.Bh[n];
-      const float ht = act_fwd(md.hact, a);
-      const float z = ly.z[(size_t)m * ldL + n], ho = ly.Hold[(size_t)m * ldL + n];
-      float h = (1.0f - z) * ho + z * ht;
-      if (md.p_drop_h > 0.f) h *= drop_scale(md.drop_seed, md.wG[s], 0u, (uint32_t)(m * L + n), 1.0f - md.p_drop_h);
-      ly.ah[(size_t)m * ldL + n] = a; ly.ht[(size_t)m * ldL + n] = ht; ly.y[(size_t)m * ldL + n] = h;
-      ly.H[(size_t)md.wSlot[(size_t)s * md.B + m] * ldL + n] = (md.wF[(size_t)s * md.B + m] & 1) ? 0.f : h;
-    } break;
-    case TS_EPI_SCORE:      // o = h Sy^T + by (- logq correction) (gru4rec.py:493-495)
-      if (m < M && n < N) tb.O[(size_t)m * tb.ldO + n] = v + tb.bias[n];
-      break;
-    case TS_EPI_DSY:        // dSy_j = sum_b g[b][j] h[b]
-      if (m < N && n < L) md.DSY[(size_t)m * ldL + n] = v;
-      break;
-    case TS_EPI_DH:         // partial dL/dh of K split `ks` (summed in fixed order by phase_b1)
-      if (m < M && n < L) md.part[((size_t)ks * md.B + m) * ldL + n] = v;
-      break;
-    case TS_EPI_B2: {       // da_r = (da_h Wh^T) * H * r (1 - r)
-      if (m >= M || n >= L) return;
-      const float r = ly.r[(size_t)m * ldL + n];
-      ly.dvec[(size_t)m * ly.ld3 + L + n] = v * ly.Hold[(size_t)m * ldL + n] * r * (1.f - r);
-    } break;
-    case TS_EPI_B3: {       // dL/d(gathered input row) = (dvec Wx^T) * embedding-dropout mask
-      if (m >= M || n >= L) return;
-      if (md.p_drop_e > 0.f) v *= drop_scale(md.drop_seed, md.wG[s], G4R_STREAM_EMBED, (uint32_t)(m * L + n), 1.0f - md.p_drop_e);
-      md.dSx[(size_t)m * md.ld_in0 + n] = v;
-    } break;
-    case TS_EPI_DENSE: {    // rows: [H*r | H | in0] features, columns: dvec = [da_h | da_r | da_z]  (dWh, dWrz, dWx + update, gru4rec.py:390-406)
-      if (m >= 3 * L || n >= 3 * L) return;
-      if (m < L) { if (n < L) { const size_t o = (size_t)m * ldL + n; dense_update(md, ly.Wh + o, ly.Wh_acc ? ly.Wh_acc + o : nullptr, ly.Wh_vel ? ly.Wh_vel + o : nullptr, v, (size_t)L * ldL); } }
-      else if (m < 2 * L) { if (n >= L) { const size_t o = (size_t)(m - L) * ly.ld2 + (n - L); dense_update(md, ly.Wrz + o, ly.Wrz_acc ? ly.Wrz_acc + o : nullptr, ly.Wrz_vel ? ly.Wrz_vel + o : nullptr, v, (size_t)L * ly.ld2); } }
-      else { const size_t o = (size_t)(m - 2 * L) * ly.ld3 + n; dense_update(md, ly.Wx + o, ly.Wx_acc ? ly.Wx_acc + o : nullptr, ly.Wx_vel ? ly.Wx_vel + o : nullptr, v, (size_t)L * ly.ld3); }
-    } break;
+  if (EPI == TS_EPI_F1) {          // rz = sigmoid(vec[:, L:] + H Wrz) (gru4rec.py:460); the r half also makes the Hold * r part of A2
+    const float4 bh = ld4(ly.Bh + L + n);
+    const float4 g = make_float4(sigmoidf_(v.x + bh.x), sigmoidf_(v.y + bh.y), sigmoidf_(v.z + bh.z), sigmoidf_(v.w + bh.w));
+    if (n < L) {
+      st4(ly.r + (size_t)m * ldL + n, g);
+      const float4 ho = ld4(ly.Hold + (size_t)m * ldL + n);
+      ts_put4(tb.A2, tb.Lk2 / TC_KC, m, L + n, make_float4(ho.x * g.x, ho.y * g.y, ho.z * g.z, ho.w * g.w));
+    } else st4(ly.z + (size_t)m * ldL + (n - L), g);
+  } else if (EPI == TS_EPI_F2) {   // h~ = act((H * r) Wh + vec[:, :L]); h = (1 - z) H + z h~; dropout; reset (gru4rec.py:461-466); h is also A3
+    const float4 bh = ld4(ly.Bh + n), z = ld4(ly.z + (size_t)m * ldL + n), ho = ld4(ly.Hold + (size_t)m * ldL + n);
+    const float a[4] = {v.x + bh.x, v.y + bh.y, v.z + bh.z, v.w + bh.w}, zv[4] = {z.x, z.y, z.z, z.w}, hov[4] = {ho.x, ho.y, ho.z, ho.w};
+    float ht[4], hn[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      ht[u] = act_fwd(md.hact, a[u]);
+      hn[u] = (1.0f - zv[u]) * hov[u] + zv[u] * ht[u];
+      if (md.p_drop_h > 0.f) hn[u] *= drop_scale(md.drop_seed, md.wG[s], 0u, (uint32_t)(m * L + n + u), 1.0f - md.p_drop_h);
+    }
+    const float4 h4 = make_float4(hn[0], hn[1], hn[2], hn[3]);
+    st4(ly.ah + (size_t)m * ldL + n, make_float4(a[0], a[1], a[2], a[3]));
+    st4(ly.ht + (size_t)m * ldL + n, make_float4(ht[0], ht[1], ht[2], ht[3]));
+    st4(ly.y + (size_t)m * ldL + n, h4);
+    st4(ly.H + (size_t)md.wSlot[(size_t)s * md.B + m] * ldL + n, (md.wF[(size_t)s * md.B + m] & 1) ? ts_zero4() : h4);
+    ts_put4(tb.A3, tb.Lk1 / TC_KC, m, n, h4);
+  } else if (EPI == TS_EPI_DSY) {  // dSy_j = sum_b g[b][j] h[b]
+    st4(md.DSY + (size_t)m * ldL + n, v);
+  } else if (EPI == TS_EPI_B2) {   // da_r = (da_h Wh^T) * H * r (1 - r); completes dvec and its operand A7
+    const float4 r = ld4(ly.r + (size_t)m * ldL + n), ho = ld4(ly.Hold + (size_t)m * ldL + n);
+    const float4 d = make_float4(v.x * ho.x * r.x * (1.f - r.x), v.y * ho.y * r.y * (1.f - r.y), v.z * ho.z * r.z * (1.f - r.z), v.w * ho.w * r.w * (1.f - r.w));
+    st4(ly.dvec + (size_t)m * ly.ld3 + L + n, d);
+    ts_put4(tb.A7, tb.Lk3 / TC_KC, m, L + n, d);
+  } else if (EPI == TS_EPI_B3) {   // dL/d(gathered input row) = (dvec Wx^T) * embedding-dropout mask
+    if (md.p_drop_e > 0.f) {
+      const uint32_t e = (uint32_t)(m * L + n); const float keep = 1.0f - md.p_drop_e;
+      v.x *= drop_scale(md.drop_seed, md.wG[s], G4R_STREAM_EMBED, e, keep); v.y *= drop_scale(md.drop_seed, md.wG[s], G4R_STREAM_EMBED, e + 1, keep);
+      v.z *= drop_scale(md.drop_seed, md.wG[s], G4R_STREAM_EMBED, e + 2, keep); v.w *= drop_scale(md.drop_seed, md.wG[s], G4R_STREAM_EMBED, e + 3, keep);
+    }
+    st4(md.dSx + (size_t)m * md.ld_in0 + n, v);
+  } else if (EPI == TS_EPI_DENSE) { // rows: [H*r | H | in0] features, columns: dvec = [da_h | da_r | da_z]  (dWh, dWrz, dWx + update, gru4rec.py:390-406)
+    const float g4[4] = {v.x, v.y, v.z, v.w};
+    if (m < L) {
+      if (n < L) { const size_t o = (size_t)m * ldL + n;
+#pragma unroll
+        for (int u = 0; u < 4; u++) dense_update(md, ly.Wh + o + u, ly.Wh_acc ? ly.Wh_acc + o + u : nullptr, ly.Wh_vel ? ly.Wh_vel + o + u : nullptr, g4[u], (size_t)L * ldL); }
+    } else if (m < 2 * L) {
+      if (n >= L) { const size_t o = (size_t)(m - L) * ly.ld2 + (n - L);
+#pragma unroll
+        for (int u = 0; u < 4; u++) dense_update(md, ly.Wrz + o + u, ly.Wrz_acc ? ly.Wrz_acc + o + u : nullptr, ly.Wrz_vel ? ly.Wrz_vel + o + u : nullptr, g4[u], (size_t)L * ly.ld2); }
+    } else { const size_t o = (size_t)(m - 2 * L) * ly.ld3 + n;
+#pragma unroll
+      for (int u = 0; u < 4; u++) dense_update(md, ly.Wx + o + u, ly.Wx_acc ? ly.Wx_acc + o + u : nullptr, ly.Wx_vel ? ly.Wx_vel + o + u : nullptr, g4[u], (size_t)L * ly.ld3); }
+  }
+}
+// sum of the K splits (fixed order) + fused epilogue; consecutive threads on consecutive column quads
+template <int EPI>
+__global__ void __launch_bounds__(256) k_ts_epi(int slot, const int* base, int off, TsGemm g, TsBuf tb) {
+  const ModelDev& md = MD; const int s = STEP_IDX;
+  const int M = md.wM[s];
+  const int N = M + (md.wSti[s] >= 0 ? md.S : 0);
+  int m_lim, n_lim;
+  ts_limits(md, EPI, M, N, m_lim, n_lim);
+  const int n4 = n_lim >> 2;
+  const size_t ps = (size_t)g.m_tiles * TS_RB * g.ldP;
+  const int L = md.layer[0].L;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)m_lim * n4; i += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / n4), n = (int)(i % n4) * 4;
+    if (EPI == TS_EPI_DENSE && ((m < L && n >= L) || (m >= L && m < 2 * L && n < L))) continue;   // blocks nobody uses
+    const float* p = g.P + (size_t)m * g.ldP + n;
+    float4 v = ld4(p);
+    for (int k = 1; k < g.ksplit; k++) { const float4 w = ld4(p + k * ps); v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
+    ts_epilogue4<EPI>(md, tb, s, m, n, v);
   }
 }
 
-__global__ void __launch_bounds__(TS_THREADS, 1) k_ts_gemm(int slot, const int* base, int off, TsGemm g, TsBuf tb) {
+constexpr uint32_t TS_SMEM_OPER = 192 * 1024;
+struct TsSmem {
+  alignas(1024) unsigned char stage[TS_SMEM_OPER];
+  alignas(8) unsigned long long stage_full[4];
+  unsigned long long stage_free[4];
+  unsigned long long acc_full;
+  uint32_t tmem_base;
+  int err;
+};
+
+__global__ void __launch_bounds__(TS_THREADS, 1) k_ts_gemm(int slot, const int* base, int off, TsGemm g) {
   extern __shared__ __align__(1024) unsigned char ts_raw[];
   TsSmem& sm = *reinterpret_cast<TsSmem*>(ts_raw);
   const ModelDev& md = MD; const int s = STEP_IDX;
@@ -386,13 +455,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_ts_gemm(int slot, const int* 
   // tiles without any live output leave at once (dynamic batch size / column count; unused blocks of the dense-gradient product)
   {
     int m_lim, n_lim;
-    switch (g.epi) {
-      case TS_EPI_F1: m_lim = M; n_lim = 2 * L; break;
-      case TS_EPI_SCORE: m_lim = M; n_lim = N; break;
-      case TS_EPI_DSY: m_lim = N; n_lim = L; break;
-      case TS_EPI_DENSE: m_lim = 3 * L; n_lim = 3 * L; break;
-      default: m_lim = M; n_lim = L; break;
-    }
+    ts_limits(md, g.epi, M, N, m_lim, n_lim);
     if (m0 >= m_lim || n0 >= n_lim) return;
     if (g.epi == TS_EPI_DENSE) {
       const int blo = m0 / L, bhi = min(m0 + TS_RB - 1, 3 * L - 1) / L;    // feature blocks the tile's rows touch
@@ -401,17 +464,19 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_ts_gemm(int slot, const int* 
     }
   }
   const int cps = (g.chunks + g.ksplit - 1) / g.ksplit;
-  const int c_beg = ks * cps, c_end = min(g.chunks, c_beg + cps);
-  const bool empty = c_beg >= c_end;           // a K split without chunks contributes zeros
+  const int c_beg = ks * cps, c_end = min(g.chunks, c_beg + cps);     // never empty (ts_shape)
+  const uint32_t b_bytes = (uint32_t)g.NT * TC_KC * 4;        // one hi (or lo) slab of the N tile
+  const uint32_t stage_bytes = 2 * TS_BLK + 2 * b_bytes;      // 64 KB (NT = 128, 3 stages) or 96 KB (NT = 256, 2 stages)
+  const uint32_t n_stage = TS_SMEM_OPER / stage_bytes;
   if (tid == 0) {
-    for (int i = 0; i < TS_STAGES; i++) { tc_mbar_init(&sm.stage_free[i], 1); tc_mbar_init(&sm.stage_full[i], 1); }
+    for (int i = 0; i < 4; i++) { tc_mbar_init(&sm.stage_free[i], 1); tc_mbar_init(&sm.stage_full[i], 1); }
     tc_mbar_init(&sm.acc_full, 1);
     sm.err = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tc_smem_u32(&sm.tmem_base)), "r"(128u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tc_smem_u32(&sm.tmem_base)), "r"((uint32_t)g.NT) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -419,30 +484,31 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_ts_gemm(int slot, const int* 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = sm.tmem_base;
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.NT >> 3) << 17) | ((uint32_t)(TS_RB >> 4) << 24);
-  const uint32_t b_bytes = (uint32_t)g.NT * TC_KC * 4;        // one hi (or lo) slab of the N tile
   if (warp == 4) {
     if (lane == 0) {
       unsigned int it = 0;
-      const int rbB = n0 / TS_RB;
-      const uint32_t b_off = (uint32_t)((n0 % TS_RB) >> 3) * 1024u;
+      const int nb = g.NT / TS_RB;                      // 128-row operand blocks per N tile
       for (int c = c_beg; c < c_end; c++, it++) {
-        const uint32_t st = it % TS_STAGES, use = it / TS_STAGES;
+        const uint32_t st = it % n_stage, use = it / n_stage;
+        unsigned char* dst = sm.stage + st * stage_bytes;
         if (use > 0) tc_mbar_wait(&sm.stage_free[st], (use - 1) & 1u, &sm.err);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(tc_smem_u32(&sm.stage_full[st])), "r"(2 * TS_BLK + 2 * b_bytes) : "memory");
-        tc_bulk_copy(sm.stage[st], g.A + ((size_t)mt * g.chunks + c) * 2 * TS_BLK, 2 * TS_BLK, &sm.stage_full[st]);
-        const unsigned char* bsrc = g.Bm + ((size_t)rbB * g.chunks + c) * 2 * TS_BLK + b_off;
-        tc_bulk_copy(sm.stage[st] + 2 * TS_BLK, bsrc, b_bytes, &sm.stage_full[st]);
-        tc_bulk_copy(sm.stage[st] + 2 * TS_BLK + b_bytes, bsrc + TS_BLK, b_bytes, &sm.stage_full[st]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(tc_smem_u32(&sm.stage_full[st])), "r"(stage_bytes) : "memory");
+        tc_bulk_copy(dst, g.A + ((size_t)mt * g.chunks + c) * 2 * TS_BLK, 2 * TS_BLK, &sm.stage_full[st]);
+        for (int q = 0; q < nb; q++) {                  // smem: [hi of all blocks | lo of all blocks]
+          const unsigned char* bsrc = g.Bm + ((size_t)(nt * nb + q) * g.chunks + c) * 2 * TS_BLK;
+          tc_bulk_copy(dst + 2 * TS_BLK + q * TS_BLK, bsrc, TS_BLK, &sm.stage_full[st]);
+          tc_bulk_copy(dst + 2 * TS_BLK + b_bytes + q * TS_BLK, bsrc + TS_BLK, TS_BLK, &sm.stage_full[st]);
+        }
       }
     }
   } else if (warp == 5) {
     if (lane == 0) {
       unsigned int it = 0;
       for (int c = c_beg; c < c_end; c++, it++) {
-        const uint32_t st = it % TS_STAGES, use = it / TS_STAGES;
+        const uint32_t st = it % n_stage, use = it / n_stage;
         tc_mbar_wait(&sm.stage_full[st], use & 1u, &sm.err);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_hi = tc_smem_u32(sm.stage[st]), a_lo = a_hi + TS_BLK, b_hi = a_hi + 2 * TS_BLK, b_lo = b_hi + b_bytes;
+        const uint32_t a_hi = tc_smem_u32(sm.stage + st * stage_bytes), a_lo = a_hi + TS_BLK, b_hi = a_hi + 2 * TS_BLK, b_lo = b_hi + b_bytes;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const uint32_t o = (uint32_t)j * 32u;        // 8 values along K = 32 bytes inside the swizzle atom
@@ -452,17 +518,13 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_ts_gemm(int slot, const int* 
         }
         tc_commit(&sm.stage_free[st]);
       }
-      if (empty) tc_mbar_arrive(&sm.acc_full); else tc_commit(&sm.acc_full);
+      tc_commit(&sm.acc_full);
     }
   } else {
     tc_mbar_wait(&sm.acc_full, 0u, &sm.err);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // TMEM lane = tile row, so a thread holds one row: the tile is transposed through shared memory (the operand stages are free
-    // once the accumulator is complete) and the epilogue then walks it with consecutive threads on consecutive columns --
-    // coalesced loads / stores of the row-major outputs and of the parameter / optimizer-state rows of the dense update
-    float* sT = reinterpret_cast<float*>(sm.stage);
-    const int ldt = g.NT + 1;
-    const int row = warp * 32 + lane;
+    // TMEM lane = tile row: a thread stores its row's 32-column groups as whole 128-byte lines of the partial tile
+    float* prow = g.P + ((size_t)ks * g.m_tiles * TS_RB + m0 + warp * 32 + lane) * g.ldP + n0;
     for (int q = 0; q < g.NT / 32; q++) {
       uint32_t r[32];
       const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + q * 32;
@@ -474,19 +536,14 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_ts_gemm(int slot, const int* 
                      "=r"(r[30]), "=r"(r[31]) : "r"(taddr) : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int j = 0; j < 32; j++) sT[row * ldt + q * 32 + j] = empty ? 0.f : __uint_as_float(r[j]);
-    }
-    asm volatile("bar.sync 3, 128;" ::: "memory");
-    for (int i = 0; i < g.NT; i++) {
-      const int idx = i * 128 + tid;
-      const int rr = idx / g.NT, cc = idx % g.NT;
-      ts_epilogue(md, tb, g.epi, s, M, N, m0 + rr, n0 + cc, ks, sT[rr * ldt + cc]);
+      for (int j = 0; j < 8; j++)
+        *reinterpret_cast<uint4*>(prow + q * 32 + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 4) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(128u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)g.NT) : "memory");
   }
 }

@@ -37,26 +37,32 @@ struct MgDev {                       // device pointers of the multi-GPU state
 struct MgTensor { float *p, *acc, *vel; size_t goff; int count; };
 struct TsBuf {                 // device buffers of the tensor-core step (owned by the handle's workspace)
   unsigned char *A1, *A2, *A3, *A4, *A5, *A6, *A7, *A8;      // left operands  (rows x K) as hi|lo blocks
-  unsigned char *W1, *W2, *W3, *W4, *B3, *B4, *B5, *B8;      // right operands (n x K)
-  float *P, *P2;                                             // partial tiles of the split-K products (main / side stream)
+  unsigned char *W1, *W2, *W3, *W4, *B3, *B4, *B5, *B8a, *B8b;   // right operands (n x K)
+  float *Pa, *Pb;                                            // partial tiles of the two dense-gradient products (split K through global memory)
   float *O, *bias;                                           // scores / dL/do [Bpad x ldO] (lane-major), bias of the sorted columns [NP]
   int ldO;
   int Mpad, Lk2, Lk1, Lk3, Nk, Bk;                           // padded extents: lanes; K = 2L, L, 3L, columns, lanes (multiples of 32)
+  int Lp;                                                    // L rounded up to the 256-wide N tile (segments of B8a)
 };
-
-
-// tiling of one tensor-core product (g4r_tcstep.cuh): N tile, tile counts, K splits, leading dimension / size of the partial tiles
+// tiling of one tensor-core product (g4r_tcstep.cuh): N tile, tile counts, K splits, leading dimension / size of the partial tiles.
+// cluster_cap > 0: the K splits of a tile form a thread-block cluster (power of two <= cap, divides the 128 tile rows)
 struct TsShape { int NT, m_tiles, n_tiles, ksplit, ldP; size_t p_floats; };
-static inline TsShape ts_shape(int rows, int cols, int chunks, int n_sm) {
+static inline TsShape ts_shape(int rows, int cols, int chunks, int n_sm, int cluster_cap) {
   TsShape t;
   t.NT = cols > 128 ? 256 : 128;
-  t.m_tiles = (rows + 128 - 1) / 128; t.n_tiles = (cols + t.NT - 1) / t.NT;
+  t.m_tiles = (rows + 127) / 128; t.n_tiles = (cols + t.NT - 1) / t.NT;
   const int tiles = t.m_tiles * t.n_tiles;
-  int ks = (n_sm - 8 + tiles - 1) / tiles;                  // about one CTA per SM
+  int ks = (n_sm - 8) / tiles;                              // about one CTA per SM
   if (ks > chunks) ks = chunks;
   if (ks < 1) ks = 1;
-  const int cps = (chunks + ks - 1) / ks;
-  t.ksplit = (chunks + cps - 1) / cps;                      // no empty splits
+  if (cluster_cap > 0) {
+    int p2 = 1;
+    while (p2 * 2 <= ks && p2 * 2 <= cluster_cap) p2 *= 2;
+    t.ksplit = p2;
+  } else {
+    const int cps = (chunks + ks - 1) / ks;
+    t.ksplit = (chunks + cps - 1) / cps;                    // no empty splits
+  }
   t.ldP = t.n_tiles * t.NT;
   t.p_floats = (size_t)t.ksplit * t.m_tiles * 128 * t.ldP;
   return t;

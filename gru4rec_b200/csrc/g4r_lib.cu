@@ -83,7 +83,7 @@ struct g4r_handle {
   bool two_pass = false;         // grad_cap: gradients are exported, the global norm is taken, then a second pass applies them scaled
   bool phase_only = false;       // grad_cap / smoothing add phases that only the per-phase launch sequence has
   float* dGscale = nullptr;
-  bool tc_ok = false; void* ts_buf = nullptr; cudaStream_t side = nullptr; cudaEvent_t ts_ev[10] = {};      // tensor-core training step (g4r_tcstep.cuh): TsBuf*
+  bool tc_ok = false; void* ts_buf = nullptr; cudaStream_t side = nullptr, side2 = nullptr; cudaEvent_t ts_ev[12] = {};      // tensor-core training step (g4r_tcstep.cuh): TsBuf*
   std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_phase;
 };
 
@@ -297,15 +297,13 @@ static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
     tsb.Mpad = r128(B); tsb.Lk1 = r32(L); tsb.Lk2 = r32(2 * L); tsb.Lk3 = r32(3 * L); tsb.Nk = r128(NP); tsb.Bk = r32(B);
     tsb.ldO = tsb.Nk;
     auto op = [&](int rows, int K) { return cv.take<unsigned char>((size_t)((rows + 255) / 256 * 256) * K * 8); };   // hi + lo: 8 bytes per element; rows padded to a 256-wide N tile
+    tsb.Lp = (L + 255) / 256 * 256;
     tsb.A1 = op(B, tsb.Lk2); tsb.A2 = op(B, tsb.Lk2); tsb.A3 = op(B, tsb.Lk1); tsb.A4 = op(NP, tsb.Bk); tsb.A5 = op(B, tsb.Nk);
     tsb.A6 = op(B, tsb.Lk1); tsb.A7 = op(B, tsb.Lk3); tsb.A8 = op(3 * L, tsb.Bk);
     tsb.W1 = op(2 * L, tsb.Lk2); tsb.W2 = op(L, tsb.Lk2); tsb.W3 = op(L, tsb.Lk1); tsb.W4 = op(L, tsb.Lk3);
-    tsb.B3 = op(NP, tsb.Lk1); tsb.B4 = op(L, tsb.Bk); tsb.B5 = op(L, tsb.Nk); tsb.B8 = op(3 * L, tsb.Bk);
-    size_t pf = 0;          // partial-tile buffer: the largest of the eight products (they run one after the other)
-    for (const TsShape& t : {ts_shape(B, 2 * L, tsb.Lk2 / 32, n_sm), ts_shape(B, L, tsb.Lk2 / 32, n_sm), ts_shape(B, NP, tsb.Lk1 / 32, n_sm),
-                             ts_shape(tsb.Nk, L, tsb.Bk / 32, n_sm), ts_shape(B, L, tsb.Nk / 32, n_sm), ts_shape(B, L, tsb.Lk1 / 32, n_sm),
-                             ts_shape(B, L, tsb.Lk3 / 32, n_sm), ts_shape(3 * L, 3 * L, tsb.Bk / 32, n_sm)}) pf = std::max(pf, t.p_floats);
-    tsb.P = cv.take<float>(pf); tsb.P2 = cv.take<float>(pf);        // main-stream / side-stream products
+    tsb.B3 = op(NP, tsb.Lk1); tsb.B4 = op(L, tsb.Bk); tsb.B5 = op(L, tsb.Nk); tsb.B8a = op(2 * tsb.Lp, tsb.Bk); tsb.B8b = op(L, tsb.Bk);
+    tsb.Pa = cv.take<float>(ts_shape(3 * L, 2 * tsb.Lp, tsb.Bk / 32, n_sm, 0).p_floats);
+    tsb.Pb = cv.take<float>(ts_shape(3 * L, L, tsb.Bk / 32, n_sm, 0).p_floats);
     tsb.O = cv.take<float>((size_t)tsb.Mpad * tsb.ldO); tsb.bias = cv.take<float>(tsb.Nk);
   }
   // evaluation
@@ -455,76 +453,103 @@ static bool tc_eligible(const g4r_config& c) {
   if (c.adapt > G4R_ADAPT_ADAGRAD || c.grad_cap > 0.f || c.smoothing != 0.f || c.world_size > 1) return false;
   return c.step_mode == 4 || (c.step_mode >= 1 && c.step_mode <= 3 && c.layers[0] >= 160);
 }
-// one mini-batch on the tensor cores (window-relative step = *base + off when base != nullptr).  Two streams (forked / joined
-// with events, so the same code is captured into the step graph): the main stream carries the chain every product waits for,
-// the side stream prepares operands that do not depend on it (weights, item-table rows, transposed operands) and runs the
-// two products nothing downstream in the step needs (dSy -> output-row update, dense gradients -> dense update).
+// one mini-batch on the tensor cores (window-relative step = *base + off when base != nullptr).  Three streams (forked / joined
+// with events, so the same code is captured into the step graph): the main stream carries the chain every product waits for;
+// side stream 1 prepares operands that do not depend on it (weights, item-table rows, transposed operands) and runs the dSy
+// product + the update of the scored rows; side stream 2 runs the dense-gradient products + dense update.
+static int g_ts_cluster_cap = 0;       // largest cluster the K splits may form (8 = portable limit; G4R_TS_CLUSTER overrides)
+template <int EPI>
+static int launch_ts_gemm(g4r_handle* h, cudaStream_t q, int ph, const int* base, int off, TsGemm g, const TsBuf& tb) {
+  cudaLaunchConfig_t lc = {};
+  cudaLaunchAttribute at[1];
+  lc.gridDim = dim3(g.m_tiles * g.n_tiles * g.ksplit); lc.blockDim = dim3(TS_THREADS); lc.dynamicSmemBytes = sizeof(TsSmem); lc.stream = q;
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = g.P ? 1 : g.ksplit; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  lc.attrs = at; lc.numAttrs = 1;
+  int slot = h->slot;
+  void* args[] = {&slot, (void*)&base, &off, &g, (void*)&tb};
+  cudaError_t e = cudaSuccess;
+  LAUNCH_ON(q, ph, e = cudaLaunchKernelExC(&lc, (const void*)k_ts_gemm<EPI>, args));
+  if (e != cudaSuccess) { h->err = std::string("k_ts_gemm launch: ") + cudaGetErrorString(e); return G4R_ERR_CUDA; }
+  return G4R_OK;
+}
 template <int EPI>
 static void launch_ts_epi(g4r_handle* h, cudaStream_t st, int ph, const int* base, int off, const TsGemm& g, const TsBuf& tb, int rows, int cols) {
   LAUNCH_ON(st, ph, k_ts_epi<EPI><<<std::min(4 * h->n_sm, std::max(1, (rows * (cols / 4) + 255) / 256)), 256, 0, st>>>(h->slot, base, off, g, tb));
 }
+static int ts_opt_in(g4r_handle* h) {
+  if (!g_ts_cluster_cap) { const char* e = getenv("G4R_TS_CLUSTER"); g_ts_cluster_cap = e ? std::max(1, std::min(16, atoi(e))) : 8; }
+  const void* fns[] = {(const void*)k_ts_gemm<TS_EPI_F1>, (const void*)k_ts_gemm<TS_EPI_F2>, (const void*)k_ts_gemm<TS_EPI_SCORE>, (const void*)k_ts_gemm<TS_EPI_DSY>,
+                       (const void*)k_ts_gemm<TS_EPI_DH>, (const void*)k_ts_gemm<TS_EPI_B2>, (const void*)k_ts_gemm<TS_EPI_B3>,
+                       (const void*)k_ts_gemm<TS_EPI_DENSE_A>, (const void*)k_ts_gemm<TS_EPI_DENSE_B>};
+  for (const void* f : fns) {
+    if (raise_smem_limit(f, sizeof(TsSmem)) != cudaSuccess) return G4R_ERR_CUDA;
+    if (g_ts_cluster_cap > 8 && cudaFuncSetAttribute(f, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return G4R_ERR_CUDA;
+  }
+  return G4R_OK;
+}
 static int enqueue_tc_step(g4r_handle* h, const int* base, int off) {
   const ModelDev& md = h->md;
   const TsBuf& tb = *static_cast<TsBuf*>(h->ts_buf);
-  cudaStream_t st = h->stream, sd = h->side;
+  cudaStream_t st = h->stream, s1 = h->side, s2 = h->side2;
   cudaEvent_t* ev = h->ts_ev;
   const int L = md.L, B = md.B, slot = h->slot;
   const int fillg = 2 * h->n_sm;
-  auto gemm = [&](cudaStream_t q, int ph, const unsigned char* A, const unsigned char* Bm, float* P, int chunks, int rows, int cols, int epi) -> TsGemm {
-    const TsShape t = ts_shape(rows, cols, chunks, h->n_sm);
-    TsGemm g; g.A = A; g.Bm = Bm; g.P = P; g.chunks = chunks; g.m_tiles = t.m_tiles; g.n_tiles = t.n_tiles; g.NT = t.NT; g.ksplit = t.ksplit; g.ldP = t.ldP; g.epi = epi;
-    LAUNCH_ON(q, ph, k_ts_gemm<<<t.m_tiles * t.n_tiles * t.ksplit, TS_THREADS, sizeof(TsSmem), q>>>(slot, base, off, g));
+  auto mk = [&](const unsigned char* A, const unsigned char* Bm, float* P, int chunks, int rows, int cols) -> TsGemm {
+    const TsShape t = ts_shape(rows, cols, chunks, h->n_sm, P ? 0 : g_ts_cluster_cap);
+    TsGemm g; g.A = A; g.Bm = Bm; g.P = P; g.chunks = chunks; g.m_tiles = t.m_tiles; g.n_tiles = t.n_tiles; g.NT = t.NT; g.ksplit = t.ksplit; g.ldP = t.ldP; g.epi = 0;
     return g;
   };
+#define TS_GEMM(EPI, q, ph, g) do { const int rc_ = launch_ts_gemm<EPI>(h, q, ph, base, off, g, tb); if (rc_) return rc_; } while (0)
   auto fork = [&](int e, cudaStream_t from, cudaStream_t to) { cudaEventRecord(ev[e], from); cudaStreamWaitEvent(to, ev[e], 0); };
-  fork(0, st, sd);
-  // side: weight operands, item-table operands
-  LAUNCH_ON(sd, PH_F1, k_ts_prep_w<<<dim3(fillg, 4), 256, 0, sd>>>(slot, tb));
-  cudaEventRecord(ev[1], sd);
-  LAUNCH_ON(sd, PH_SCORE, k_ts_prep_tab<<<dim3(fillg, 3), 256, 0, sd>>>(slot, base, off, tb));
-  cudaEventRecord(ev[2], sd);
-  // main: GRU forward
-  LAUNCH(PH_GATHER, k_gather_in<<<std::max(1, (B + 7) / 8), 256, 0, st>>>(slot, base, off, 1));
-  LAUNCH(PH_F1, k_ts_prep_fwd<<<dim3(fillg, 3), 256, 0, st>>>(slot, base, off, tb));
+  fork(0, st, s1);
+  // side 1: weight operands, item-table operands
+  LAUNCH_ON(s1, PH_F1, k_ts_prep_w<<<dim3(fillg, 4), 256, 0, s1>>>(slot, tb));
+  cudaEventRecord(ev[1], s1);
+  LAUNCH_ON(s1, PH_SCORE, k_ts_prep_tab<<<dim3(fillg, 3), 256, 0, s1>>>(slot, base, off, tb));
+  cudaEventRecord(ev[2], s1);
+  // main: input rows, GRU forward
+  LAUNCH(PH_GATHER, k_ts_prep_fwd<<<dim3(fillg, 2), 256, 0, st>>>(slot, base, off, tb));
   cudaStreamWaitEvent(st, ev[1], 0);
-  const TsGemm g1 = gemm(st, PH_F1, tb.A1, tb.W1, tb.P, tb.Lk2 / TC_KC, B, 2 * L, TS_EPI_F1);
-  launch_ts_epi<TS_EPI_F1>(h, st, PH_F1, base, off, g1, tb, B, 2 * L);
-  fork(3, st, sd);
-  LAUNCH_ON(sd, PH_DENSE, k_ts_prep_a8<<<fillg, 256, 0, sd>>>(slot, base, off, tb));
-  const TsGemm g2 = gemm(st, PH_F2, tb.A2, tb.W2, tb.P, tb.Lk2 / TC_KC, B, L, TS_EPI_F2);
-  launch_ts_epi<TS_EPI_F2>(h, st, PH_F2, base, off, g2, tb, B, L);
-  fork(4, st, sd);
-  LAUNCH_ON(sd, PH_LOSSGRAD, k_ts_prep_yt<<<fillg, 256, 0, sd>>>(slot, base, off, tb));
+  TS_GEMM(TS_EPI_F1, st, PH_F1, mk(tb.A1, tb.W1, nullptr, tb.Lk2 / TC_KC, B, 2 * L));
+  fork(3, st, s1);
+  LAUNCH_ON(s1, PH_DENSE, k_ts_prep_a8<<<fillg, 256, 0, s1>>>(slot, base, off, tb));
+  cudaEventRecord(ev[9], s1);
+  TS_GEMM(TS_EPI_F2, st, PH_F2, mk(tb.A2, tb.W2, nullptr, tb.Lk2 / TC_KC, B, L));
+  fork(4, st, s1);
+  LAUNCH_ON(s1, PH_LOSSGRAD, k_ts_prep_yt<<<fillg, 256, 0, s1>>>(slot, base, off, tb));
   // main: scores, loss, dL/do
   cudaStreamWaitEvent(st, ev[2], 0);
-  const TsGemm g3 = gemm(st, PH_SCORE, tb.A3, tb.B3, tb.P, tb.Lk1 / TC_KC, B, md.NP, TS_EPI_SCORE);
-  LAUNCH(PH_STATS, k_ts_stats<<<B, 256, 0, st>>>(slot, base, off, g3, tb));
-  LAUNCH(PH_LOSSGRAD, k_ts_lossgrad<<<B, 256, 0, st>>>(slot, base, off, tb));
-  fork(5, st, sd);
-  // side: dSy product and the update of the scored rows
-  LAUNCH_ON(sd, PH_LOSSGRAD, k_ts_prep_g<<<dim3(fillg, 2), 256, 0, sd>>>(slot, base, off, tb));
-  const TsGemm g4 = gemm(sd, PH_LOSSGRAD, tb.A4, tb.B4, tb.P2, tb.Bk / TC_KC, tb.Nk, L, TS_EPI_DSY);
-  launch_ts_epi<TS_EPI_DSY>(h, sd, PH_LOSSGRAD, base, off, g4, tb, tb.Nk, L);
-  LAUNCH_ON(sd, PH_LOSSGRAD, k_apply_rows<<<md.NCH, SC_THREADS, 0, sd>>>(slot, base, off));
-  cudaEventRecord(ev[6], sd);
-  // main: GRU backward
-  const TsGemm g5 = gemm(st, PH_LOSSGRAD, tb.A5, tb.B5, tb.P, tb.Nk / TC_KC, B, L, TS_EPI_DH);
-  LAUNCH(PH_B1, k_ts_b1<<<std::min(4 * h->n_sm, (B * (L / 4) + 255) / 256), 256, 0, st>>>(slot, base, off, g5, tb));
-  const TsGemm g6 = gemm(st, PH_B2, tb.A6, tb.W3, tb.P, tb.Lk1 / TC_KC, B, L, TS_EPI_B2);
-  launch_ts_epi<TS_EPI_B2>(h, st, PH_B2, base, off, g6, tb, B, L);
-  fork(7, st, sd);
-  // side: dense gradients + update
-  LAUNCH_ON(sd, PH_DENSE, k_ts_prep_b8<<<fillg, 256, 0, sd>>>(slot, base, off, tb));
-  const TsGemm g8 = gemm(sd, PH_DENSE, tb.A8, tb.B8, tb.P2, tb.Bk / TC_KC, 3 * L, 3 * L, TS_EPI_DENSE);
-  launch_ts_epi<TS_EPI_DENSE>(h, sd, PH_DENSE, base, off, g8, tb, 3 * L, 3 * L);
-  LAUNCH_ON(sd, PH_DENSE, k_ts_bh<<<(3 * L + 31) / 32, 256, 0, sd>>>(slot, base, off));
-  cudaEventRecord(ev[8], sd);
-  // main: dL/d(input rows), then the input-row update (after the scored-row update: both touch the shared table)
-  const TsGemm g7 = gemm(st, PH_B3, tb.A7, tb.W4, tb.P, tb.Lk3 / TC_KC, B, L, TS_EPI_B3);
-  launch_ts_epi<TS_EPI_B3>(h, st, PH_B3, base, off, g7, tb, B, L);
+  TS_GEMM(TS_EPI_SCORE, st, PH_SCORE, mk(tb.A3, tb.B3, nullptr, tb.Lk1 / TC_KC, B, md.NP));
+  LAUNCH(PH_LOSSGRAD, k_ts_loss<<<B, 256, 0, st>>>(slot, base, off, tb));
+  fork(5, st, s1);
+  // side 1: dSy product and the update of the scored rows
+  LAUNCH_ON(s1, PH_LOSSGRAD, k_ts_prep_g<<<dim3(fillg, 2), 256, 0, s1>>>(slot, base, off, tb));
+  TS_GEMM(TS_EPI_DSY, s1, PH_LOSSGRAD, mk(tb.A4, tb.B4, nullptr, tb.Bk / TC_KC, tb.Nk, L));
+  LAUNCH_ON(s1, PH_LOSSGRAD, k_apply_rows<<<md.NCH, SC_THREADS, 0, s1>>>(slot, base, off));
+  cudaEventRecord(ev[6], s1);
+  // main: GRU backward (b1 is the epilogue of the dL/dh product)
+  TS_GEMM(TS_EPI_DH, st, PH_B1, mk(tb.A5, tb.B5, nullptr, tb.Nk / TC_KC, B, L));
+  fork(7, st, s2);
+  // side 2: dense gradients of the da_h / da_z columns + update
+  LAUNCH_ON(s2, PH_DENSE, k_ts_prep_b8<<<fillg, 256, 0, s2>>>(slot, base, off, tb, 0));
+  cudaStreamWaitEvent(s2, ev[9], 0);       // A8 comes from side 1
+  const TsGemm g8a = mk(tb.A8, tb.B8a, tb.Pa, tb.Bk / TC_KC, 3 * L, 2 * tb.Lp);
+  TS_GEMM(TS_EPI_DENSE_A, s2, PH_DENSE, g8a);
+  launch_ts_epi<TS_EPI_DENSE_A>(h, s2, PH_DENSE, base, off, g8a, tb, 3 * L, 2 * tb.Lp);
+  TS_GEMM(TS_EPI_B2, st, PH_B2, mk(tb.A6, tb.W3, nullptr, tb.Lk1 / TC_KC, B, L));
+  fork(8, st, s2);
+  // side 2: the da_r columns
+  LAUNCH_ON(s2, PH_DENSE, k_ts_prep_b8<<<fillg, 256, 0, s2>>>(slot, base, off, tb, 1));
+  const TsGemm g8b = mk(tb.A8, tb.B8b, tb.Pb, tb.Bk / TC_KC, 3 * L, L);
+  TS_GEMM(TS_EPI_DENSE_B, s2, PH_DENSE, g8b);
+  launch_ts_epi<TS_EPI_DENSE_B>(h, s2, PH_DENSE, base, off, g8b, tb, 3 * L, L);
+  // main: dL/d(input rows), the bias gradient, then the input-row update (after the scored-row update: both touch the shared table)
+  TS_GEMM(TS_EPI_B3, st, PH_B3, mk(tb.A7, tb.W4, nullptr, tb.Lk3 / TC_KC, B, L));
+  LAUNCH(PH_DENSE, k_ts_bh<<<(3 * L + 31) / 32, 256, 0, st>>>(slot, base, off));
   cudaStreamWaitEvent(st, ev[6], 0);
   LAUNCH(PH_SPARSE_IN, k_sparse_in<<<B, 128, 0, st>>>(slot, base, off, 1));
-  cudaStreamWaitEvent(st, ev[8], 0);
+  cudaEventRecord(ev[10], s2); cudaStreamWaitEvent(st, ev[10], 0);
+#undef TS_GEMM
   return G4R_OK;
 }
 
@@ -614,6 +639,7 @@ extern "C" int g4r_destroy(g4r_handle* h) {
   if (h->hFlags) cudaFreeHost(h->hFlags);
   if (h->own_ws && h->ws) cudaFree(h->ws);
   if (h->side) cudaStreamDestroy(h->side);
+  if (h->side2) cudaStreamDestroy(h->side2);
   for (cudaEvent_t e : h->ts_ev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -657,7 +683,7 @@ extern "C" int g4r_create(const g4r_config* cfg, void* device_workspace, size_t 
   h->ws_bytes = need;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(G4R_ERR_CUDA, "stream create failed");
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
-  if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess) return bail(G4R_ERR_CUDA, "stream create failed");
+  if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&h->side2, cudaStreamNonBlocking) != cudaSuccess) return bail(G4R_ERR_CUDA, "stream create failed");
   for (cudaEvent_t& e : h->ts_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   if (cudaMemsetAsync(h->ws, 0, need, h->stream) != cudaSuccess) return bail(G4R_ERR_CUDA, "memset failed");
   // 256-byte align the carve base
@@ -706,7 +732,7 @@ extern "C" int g4r_create(const g4r_config* cfg, void* device_workspace, size_t 
     cudaMallocHost(&h->hFlags, 4 * sizeof(int));
   }
   if (h->tc_ok) {
-    if (raise_smem_limit((const void*)k_ts_gemm, sizeof(TsSmem)) != cudaSuccess) return bail(G4R_ERR_CUDA, "k_ts_gemm: shared memory opt-in failed");
+    if (ts_opt_in(h) != G4R_OK) return bail(G4R_ERR_CUDA, "k_ts_gemm: shared memory / cluster opt-in failed");
     h->fast_ok = false; h->fastc_ok = false;
   }
   if (cfg->step_mode == 1 && h->pk_blocks == 0) return bail(G4R_ERR_INVALID, "persistent mode unavailable (cooperative launch / shared memory)");

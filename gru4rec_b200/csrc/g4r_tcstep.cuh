@@ -22,7 +22,6 @@ constexpr int TS_RB = 128;                               // rows per operand blo
 constexpr uint32_t TS_BLK = TS_RB * TC_KC * 4;           // bytes of one hi (or lo) block: 16 KB
 constexpr int TS_THREADS = 192;                          // 4 epilogue warps + TMA warp + MMA warp
 
-enum { TS_EPI_F1 = 0, TS_EPI_F2, TS_EPI_SCORE, TS_EPI_DSY, TS_EPI_DH, TS_EPI_B2, TS_EPI_B3, TS_EPI_DENSE };   // SCORE / DH: the sum of the splits is folded into k_ts_stats / k_ts_b1
 
 
 
@@ -74,31 +73,47 @@ struct TsGemm {
   int epi;
 };
 
-// ---- P1: A1 = [in0 | H(slot)] (lanes x 2L), the in0 half of A2 = [in0 | Hold * r], compact copy of the old hidden state
-// (gru4rec.py:459-461 operands); the Hold * r half of A2 comes from the gate epilogue ----
+// ---- P1: gather of the input rows (shared table, embedding dropout, optimizer-state snapshots: phase_gather_in), A1 = [in0 | H(slot)]
+// (lanes x 2L), the in0 half of A2 = [in0 | Hold * r], compact copy of the old hidden state (gru4rec.py:459-461 operands); the
+// Hold * r half of A2 comes from the gate epilogue ----
+__device__ __forceinline__ float4 ts_in0_quad(const ModelDev& md, int s, int b, int k, int item) {
+  float4 v = ld4(md.Wy + (size_t)item * md.ld_in0 + k);
+  if (md.p_drop_e > 0.f) {
+    const uint32_t e = (uint32_t)(b * md.in0_dim + k); const float keep = 1.0f - md.p_drop_e; const uint32_t gs = md.wG[s];
+    v.x *= drop_scale(md.drop_seed, gs, G4R_STREAM_EMBED, e, keep); v.y *= drop_scale(md.drop_seed, gs, G4R_STREAM_EMBED, e + 1, keep);
+    v.z *= drop_scale(md.drop_seed, gs, G4R_STREAM_EMBED, e + 2, keep); v.w *= drop_scale(md.drop_seed, gs, G4R_STREAM_EMBED, e + 3, keep);
+  }
+  return v;
+}
 __global__ void __launch_bounds__(256) k_ts_prep_fwd(int slot, const int* base, int off, TsBuf tb) {
   const ModelDev& md = MD; const int s = STEP_IDX;
   const LayerDev& ly = md.layer[0];
-  const int M = md.wM[s], L = ly.L, ldL = ly.ldL;
-  if (blockIdx.y == 0) {
-    ts_fill(tb.A1, tb.Mpad, tb.Lk2, true, [&](int b, int k) -> float4 {
-      if (b >= M) return ts_zero4();
-      if (k < L) return ld4(md.in0 + (size_t)b * md.ld_in0 + k);
-      if (k - L >= L) return ts_zero4();
-      const int sl = (md.wF[(size_t)s * md.B + b] & 2) ? -1 : md.wSlot[(size_t)s * md.B + b];
-      return sl >= 0 ? ld4(ly.H + (size_t)sl * ldL + (k - L)) : ts_zero4();
-    });
-  } else if (blockIdx.y == 1) {
+  const int M = md.wM[s], L = ly.L, ldL = ly.ldL, L4 = L / 4;
+  const int* __restrict__ wX = md.wX + (size_t)s * md.B;
+  if (blockIdx.y == 0) {          // A1, in0 half of A2, in0 itself
     const int n_chunk = tb.Lk2 / TC_KC;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M * (L / 4); i += gridDim.x * blockDim.x) {
-      const int b = i / (L / 4), k = (i % (L / 4)) * 4;
-      ts_put4(tb.A2, n_chunk, b, k, ld4(md.in0 + (size_t)b * md.ld_in0 + k));
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M * 2 * L4; i += gridDim.x * blockDim.x) {
+      const int b = i / (2 * L4), k = (i % (2 * L4)) * 4;
+      if (k < L) {
+        const float4 v = ts_in0_quad(md, s, b, k, wX[b]);
+        st4(md.in0 + (size_t)b * md.ld_in0 + k, v);
+        ts_put4(tb.A1, n_chunk, b, k, v);
+        ts_put4(tb.A2, n_chunk, b, k, v);
+      } else {
+        const int sl = (md.wF[(size_t)s * md.B + b] & 2) ? -1 : md.wSlot[(size_t)s * md.B + b];
+        const float4 hv = sl >= 0 ? ld4(ly.H + (size_t)sl * ldL + (k - L)) : ts_zero4();
+        st4(ly.Hold + (size_t)b * ldL + (k - L), hv);
+        ts_put4(tb.A1, n_chunk, b, k, hv);
+      }
     }
-  } else {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M * (ldL / 4); i += gridDim.x * blockDim.x) {
-      const int b = i / (ldL / 4), c4 = i % (ldL / 4);
-      const int sl = (md.wF[(size_t)s * md.B + b] & 2) ? -1 : md.wSlot[(size_t)s * md.B + b];
-      st4(ly.Hold + (size_t)b * ldL + c4 * 4, sl >= 0 ? ld4(ly.H + (size_t)sl * ldL + c4 * 4) : ts_zero4());
+  } else {                        // raw rows (no dropout) and optimizer-state snapshots for the input-row update
+    const int ld = md.ld_in0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M * (ld / 4); i += gridDim.x * blockDim.x) {
+      const int b = i / (ld / 4), c = (i % (ld / 4)) * 4;
+      const size_t src = (size_t)wX[b] * ld + c, dst = (size_t)b * ld + c;
+      st4(md.Sx + dst, ld4(md.Wy + src));
+      if (md.Wy_acc) st4(md.snapAcc + dst, ld4(md.Wy_acc + src));
+      if (md.Wy_vel) st4(md.snapVel + dst, ld4(md.Wy_vel + src));
     }
   }
 }
@@ -190,30 +205,24 @@ __global__ void __launch_bounds__(256) k_ts_prep_yt(int slot, const int* base, i
   });
 }
 
-// ---- scores o = sum of the K-split partials + bias, written lane-major, and the row statistics of the losses in the same pass
-// (same merge as phase_score / phase_stats) ----
-__global__ void __launch_bounds__(256) k_ts_stats(int slot, const int* base, int off, TsGemm g, TsBuf tb) {
+// ---- row statistics of the losses from the lane-major score matrix (same merge as phase_score / phase_stats), then dL/do of the
+// same row in place and as the left operand A5 (b, k = j) of the dL/dh product: a row needs only its own statistics ----
+__global__ void __launch_bounds__(256) k_ts_loss(int slot, const int* base, int off, TsBuf tb) {
   const ModelDev& md = MD; const int s = STEP_IDX;
   const int M = md.wM[s];
   const int N = M + (md.wSti[s] >= 0 ? md.S : 0);
   const int b = blockIdx.x;
   if (b >= M) return;
   __shared__ float sW[8 * 8];
+  __shared__ float sRS[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* orow = tb.O + (size_t)b * tb.ldO;
-  const float* prow = g.P + (size_t)b * g.ldP;
-  const size_t ps = (size_t)g.m_tiles * TS_RB * g.ldP;
   const int tc = md.pTcol[(size_t)s * md.B + b];
   const bool pw = loss_pairwise(md.loss);
-  float t = 0.f;
-  if (pw) { float o = prow[tc]; for (int k = 1; k < g.ksplit; k++) o += prow[k * ps + tc]; t = act_fwd(md.fact, o + tb.bias[tc]); }
+  const float t = pw ? act_fwd(md.fact, orow[tc]) : 0.f;
   float m = -INFINITY, Z = 0.f, A = 0.f, Q = 0.f, D = 0.f, T = 0.f, has = 0.f;
   for (int j = tid * 4; j < N; j += blockDim.x * 4) {
-    float4 v = ld4(prow + j);
-    for (int k = 1; k < g.ksplit; k++) { const float4 w = ld4(prow + k * ps + j); v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
-    const float4 bz = ld4(tb.bias + j);
-    v.x += bz.x; v.y += bz.y; v.z += bz.z; v.w += bz.w;
-    st4(orow + j, v);
+    const float4 v = ld4(orow + j);
     stat_add_elem(md, v.x, j == tc, t, m, Z, A, Q, D, T, has);
     if (j + 1 < N) stat_add_elem(md, v.y, j + 1 == tc, t, m, Z, A, Q, D, T, has);
     if (j + 2 < N) stat_add_elem(md, v.z, j + 2 == tc, t, m, Z, A, Q, D, T, has);
@@ -233,21 +242,11 @@ __global__ void __launch_bounds__(256) k_ts_stats(int slot, const int* base, int
     if (loss_softmaxneg(md.loss)) stat_merge(m, Z, A, Q, D, 0.f, 0.f, 0.f, 0.f, 0.f);   // the zeroed diagonal takes part in the max (gru4rec.py:200-202)
     stats_finalize(md, b, M, N, m, Z, A, Q, D, T, t);
   }
-}
-// ---- dL/do in place (lane-major) and as the left operand A5 (b, k = j) of the dL/dh product, cost of the step ----
-__global__ void __launch_bounds__(256) k_ts_lossgrad(int slot, const int* base, int off, TsBuf tb) {
-  const ModelDev& md = MD; const int s = STEP_IDX;
-  const int M = md.wM[s];
-  const int N = M + (md.wSti[s] >= 0 ? md.S : 0);
-  const int b = blockIdx.x;
-  if (b >= M) return;
-  __shared__ float sRS[8];
-  if (threadIdx.x < 8) sRS[threadIdx.x] = md.RS[(size_t)b * G4R_NSTAT + threadIdx.x];
   __syncthreads();
-  const int tc = md.pTcol[(size_t)s * md.B + b];
-  float* orow = tb.O + (size_t)b * tb.ldO;
+  if (tid < 8) sRS[tid] = md.RS[(size_t)b * G4R_NSTAT + tid];
+  __syncthreads();
   const int n_chunk = tb.Nk / TC_KC;
-  for (int j = threadIdx.x * 4; j < tb.Nk; j += blockDim.x * 4) {      // the K padding of A5 beyond the live columns is rewritten with zeros
+  for (int j = tid * 4; j < tb.Nk; j += blockDim.x * 4) {      // the K padding of A5 beyond the live columns is rewritten with zeros
     float4 v = ts_zero4();
     if (j < N) {
       v = ld4(orow + j);
@@ -258,13 +257,6 @@ __global__ void __launch_bounds__(256) k_ts_lossgrad(int slot, const int* base, 
       st4(orow + j, v);
     }
     ts_put4(tb.A5, n_chunk, b, j, v);
-  }
-  if (b == 0 && threadIdx.x == 0) {
-    float c = 0.f;
-    for (int bb = 0; bb < M; bb++) c += md.RS[(size_t)bb * G4R_NSTAT + 6];
-    c = __fdiv_rn(c, (float)md.B);            // cost = loss / batch_size (gru4rec.py:577)
-    md.cost[s] = c;
-    if (c != c) atomicExch(md.nanflag, 1);
   }
 }
 // ---- P6: A4 (j, k = b) = G[b][j] (left operand of dSy); dby[j] = sum_b G[b][j] ----
@@ -283,49 +275,26 @@ __global__ void __launch_bounds__(256) k_ts_prep_g(int slot, const int* base, in
     ts_colsum(N, M, [&](int b, int j) { return G[(size_t)b * tb.ldO + j]; }, [&](int j, float t) { md.DBY[j] = t; });
   }
 }
-// ---- b1: dL/dh = sum of the K-split partials (fixed order), then the elementwise GRU backward;
-// da_h / da_z go to dvec and straight into the operands A6 = da_h and A7 = dvec ----
-__global__ void __launch_bounds__(256) k_ts_b1(int slot, const int* base, int off, TsGemm g, TsBuf tb) {
-  const ModelDev& md = MD; const int s = STEP_IDX;
-  const LayerDev& ly = md.layer[0];
-  const int M = md.wM[s], L = ly.L, ldL = ly.ldL, L4 = L / 4;
-  const size_t ps = (size_t)g.m_tiles * TS_RB * g.ldP;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < M * L4; e += gridDim.x * blockDim.x) {
-    const int b = e / L4, c = (e % L4) * 4;
-    const size_t o = (size_t)b * ldL + c;
-    const float* p = g.P + (size_t)b * g.ldP + c;
-    float4 dy = ld4(p);
-    for (int k = 1; k < g.ksplit; k++) { const float4 w = ld4(p + k * ps); dy.x += w.x; dy.y += w.y; dy.z += w.z; dy.w += w.w; }
-    const float4 ht = ld4(ly.ht + o), ho = ld4(ly.Hold + o), z = ld4(ly.z + o), ah = ld4(ly.ah + o);
-    float dyv[4] = {dy.x, dy.y, dy.z, dy.w};
-    const float htv[4] = {ht.x, ht.y, ht.z, ht.w}, hov[4] = {ho.x, ho.y, ho.z, ho.w}, zv[4] = {z.x, z.y, z.z, z.w}, ahv[4] = {ah.x, ah.y, ah.z, ah.w};
-    float dah[4], dz[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      float dh = dyv[u];
-      if (md.p_drop_h > 0.f) dh *= drop_scale(md.drop_seed, md.wG[s], 0u, (uint32_t)(b * L + c + u), 1.0f - md.p_drop_h);
-      dah[u] = dh * zv[u] * act_der(md.hact, ahv[u], htv[u]);
-      dz[u] = dh * (htv[u] - hov[u]) * zv[u] * (1.f - zv[u]);
-    }
-    const float4 a4 = make_float4(dah[0], dah[1], dah[2], dah[3]), z4 = make_float4(dz[0], dz[1], dz[2], dz[3]);
-    st4(ly.dvec + (size_t)b * ly.ld3 + c, a4);
-    st4(ly.dvec + (size_t)b * ly.ld3 + 2 * L + c, z4);
-    ts_put4(tb.A6, tb.Lk1 / TC_KC, b, c, a4);
-    ts_put4(tb.A7, tb.Lk3 / TC_KC, b, c, a4);
-    ts_put4(tb.A7, tb.Lk3 / TC_KC, b, 2 * L + c, z4);
-  }
-}
-// ---- P7: B8 (n < 3L, k = b) = dvec^T (right operand of the dense-gradient product) ----
-__global__ void __launch_bounds__(256) k_ts_prep_b8(int slot, const int* base, int off, TsBuf tb) {
+// ---- P7: right operands of the dense-gradient products (k = b): B8a rows [0, Lp) = da_h^T, [Lp, 2 Lp) = da_z^T (known after b1),
+// B8b rows [0, L) = da_r^T (known after b2) ----
+__global__ void __launch_bounds__(256) k_ts_prep_b8(int slot, const int* base, int off, TsBuf tb, int part) {
   const ModelDev& md = MD; const int s = STEP_IDX;
   const LayerDev& ly = md.layer[0];
   const int M = md.wM[s], L = ly.L;
-  const int R3 = (3 * L + TS_RB - 1) / TS_RB * TS_RB;
-  ts_fill(tb.B8, R3, tb.Bk, false, [&](int n, int k) -> float4 {
-    float v[4];
-    for (int u = 0; u < 4; u++) { const int b = k + u; v[u] = (n < 3 * L && b < M) ? ly.dvec[(size_t)b * ly.ld3 + n] : 0.f; }
-    return make_float4(v[0], v[1], v[2], v[3]);
-  });
+  if (part == 0) {
+    ts_fill(tb.B8a, 2 * tb.Lp, tb.Bk, false, [&](int n, int k) -> float4 {
+      const int seg = n / tb.Lp, c = n % tb.Lp;
+      float v[4];
+      for (int u = 0; u < 4; u++) { const int b = k + u; v[u] = (c < L && b < M) ? ly.dvec[(size_t)b * ly.ld3 + (seg ? 2 * L : 0) + c] : 0.f; }
+      return make_float4(v[0], v[1], v[2], v[3]);
+    });
+  } else {
+    ts_fill(tb.B8b, (L + TS_RB - 1) / TS_RB * TS_RB, tb.Bk, false, [&](int n, int k) -> float4 {
+      float v[4];
+      for (int u = 0; u < 4; u++) { const int b = k + u; v[u] = (n < L && b < M) ? ly.dvec[(size_t)b * ly.ld3 + L + n] : 0.f; }
+      return make_float4(v[0], v[1], v[2], v[3]);
+    });
+  }
 }
 // ---- dBh = sum_b dvec (gru4rec.py:462 bias gradient) with its update ----
 __global__ void __launch_bounds__(256) k_ts_bh(int slot, const int* base, int off) {
@@ -337,21 +306,40 @@ __global__ void __launch_bounds__(256) k_ts_bh(int slot, const int* base, int of
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// the GEMM: P[ks][128 x NT tile] = A[128 x K_ks] B[NT x K_ks]^T, 3xTF32.  A tcgen05.mma costs ~150 cycles to issue whatever its
-// N (scripts/micro/mma_rate.cu), so the tiles are as wide as the instruction allows (N = 256 wherever the product has more than
-// 128 columns) and the parallelism comes from splitting K over CTAs: every CTA writes its raw partial tile, a light elementwise
-// kernel (k_ts_epi) adds the K splits in fixed order and applies the fused epilogue with coalesced accesses.
+// the GEMM: D[128 x NT tile] = A[128 x K] B[NT x K]^T, 3xTF32.  A tcgen05.mma costs ~150 cycles to issue whatever its N
+// (scripts/micro/mma_rate.cu), so the tiles are as wide as the instruction allows (N = 256 wherever the product has more than
+// 128 columns) and the parallelism comes from splitting K over the CTAs of a thread-block CLUSTER: each CTA accumulates its K
+// slice in TMEM, parks the partial tile in its own shared memory, and after a cluster barrier every CTA sums one band of rows over
+// all peers through distributed shared memory (fixed order) and applies the fused epilogue with coalesced accesses.
+// (TsGemm.P != nullptr: partial tiles go to global memory instead and k_ts_epi reduces them -- the dense-update products, whose
+// epilogue is a full optimizer step per element and wants the whole GPU.)
 // ---------------------------------------------------------------------------------------------------------------------
+enum { TS_EPI_F1 = 0, TS_EPI_F2, TS_EPI_SCORE, TS_EPI_DSY, TS_EPI_DH, TS_EPI_B2, TS_EPI_B3, TS_EPI_DENSE_A, TS_EPI_DENSE_B };
 // live extent of a product at this step (dynamic mini-batch size / column count)
-__device__ __forceinline__ void ts_limits(const ModelDev& md, int epi, int M, int N, int& m_lim, int& n_lim) {
+template <int EPI>
+__device__ __forceinline__ void ts_limits(const ModelDev& md, const TsBuf& tb, int M, int N, int& m_lim, int& n_lim) {
   const int L = md.layer[0].L;
-  switch (epi) {
-    case TS_EPI_F1: m_lim = M; n_lim = 2 * L; break;
-    case TS_EPI_SCORE: m_lim = M; n_lim = N; break;
-    case TS_EPI_DSY: m_lim = N; n_lim = L; break;
-    case TS_EPI_DENSE: m_lim = 3 * L; n_lim = 3 * L; break;
-    default: m_lim = M; n_lim = L; break;
+  if (EPI == TS_EPI_F1) { m_lim = M; n_lim = 2 * L; }
+  else if (EPI == TS_EPI_SCORE) { m_lim = M; n_lim = (N + 3) & ~3; }
+  else if (EPI == TS_EPI_DSY) { m_lim = N; n_lim = L; }
+  else if (EPI == TS_EPI_DENSE_A) { m_lim = 3 * L; n_lim = 2 * tb.Lp; }
+  else if (EPI == TS_EPI_DENSE_B) { m_lim = 3 * L; n_lim = L; }
+  else { m_lim = M; n_lim = L; }
+}
+// does the tile [m0, m0 + 128) x [n0, n0 + NT) hold any live output?
+template <int EPI>
+__device__ __forceinline__ bool ts_tile_live(const ModelDev& md, const TsBuf& tb, int M, int N, int m0, int n0) {
+  int m_lim, n_lim;
+  ts_limits<EPI>(md, tb, M, N, m_lim, n_lim);
+  if (m0 >= m_lim || n0 >= n_lim) return false;
+  const int L = md.layer[0].L;
+  if (EPI == TS_EPI_DENSE_A || EPI == TS_EPI_DENSE_B) {
+    const int blo = m0 / L, bhi = min(m0 + TS_RB - 1, 3 * L - 1) / L;      // feature blocks (H*r | H | in0) the tile's rows touch
+    if (EPI == TS_EPI_DENSE_B) return bhi >= 1;                            // da_r: dWrz and dWx only
+    if (n0 % tb.Lp >= L) return false;
+    return n0 / tb.Lp == 0 ? (blo == 0 || bhi == 2) : bhi >= 1;            // da_h: dWh, dWx;  da_z: dWrz, dWx
   }
+  return true;
 }
 // fused epilogue of four consecutive columns (m, n .. n+3) of a product; every live extent along n is a multiple of 4 (L % 4 == 0)
 template <int EPI>
@@ -382,8 +370,30 @@ __device__ __forceinline__ void ts_epilogue4(const ModelDev& md, const TsBuf& tb
     st4(ly.y + (size_t)m * ldL + n, h4);
     st4(ly.H + (size_t)md.wSlot[(size_t)s * md.B + m] * ldL + n, (md.wF[(size_t)s * md.B + m] & 1) ? ts_zero4() : h4);
     ts_put4(tb.A3, tb.Lk1 / TC_KC, m, n, h4);
+  } else if (EPI == TS_EPI_SCORE) { // o = h Sy^T + by (- logq correction) (gru4rec.py:493-495), lane-major
+    const float4 bz = ld4(tb.bias + n);
+    st4(tb.O + (size_t)m * tb.ldO + n, make_float4(v.x + bz.x, v.y + bz.y, v.z + bz.z, v.w + bz.w));
   } else if (EPI == TS_EPI_DSY) {  // dSy_j = sum_b g[b][j] h[b]
     st4(md.DSY + (size_t)m * ldL + n, v);
+  } else if (EPI == TS_EPI_DH) {   // b1: v = dL/dh; elementwise GRU backward; da_h / da_z go to dvec and into A6 = da_h, A7 = dvec
+    const size_t o = (size_t)m * ldL + n;
+    const float4 ht = ld4(ly.ht + o), ho = ld4(ly.Hold + o), z = ld4(ly.z + o), ah = ld4(ly.ah + o);
+    const float dyv[4] = {v.x, v.y, v.z, v.w}, htv[4] = {ht.x, ht.y, ht.z, ht.w}, hov[4] = {ho.x, ho.y, ho.z, ho.w}, zv[4] = {z.x, z.y, z.z, z.w},
+                ahv[4] = {ah.x, ah.y, ah.z, ah.w};
+    float dah[4], dz[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      float dh = dyv[u];
+      if (md.p_drop_h > 0.f) dh *= drop_scale(md.drop_seed, md.wG[s], 0u, (uint32_t)(m * L + n + u), 1.0f - md.p_drop_h);
+      dah[u] = dh * zv[u] * act_der(md.hact, ahv[u], htv[u]);
+      dz[u] = dh * (htv[u] - hov[u]) * zv[u] * (1.f - zv[u]);
+    }
+    const float4 a4 = make_float4(dah[0], dah[1], dah[2], dah[3]), z4 = make_float4(dz[0], dz[1], dz[2], dz[3]);
+    st4(ly.dvec + (size_t)m * ly.ld3 + n, a4);
+    st4(ly.dvec + (size_t)m * ly.ld3 + 2 * L + n, z4);
+    ts_put4(tb.A6, tb.Lk1 / TC_KC, m, n, a4);
+    ts_put4(tb.A7, tb.Lk3 / TC_KC, m, n, a4);
+    ts_put4(tb.A7, tb.Lk3 / TC_KC, m, 2 * L + n, z4);
   } else if (EPI == TS_EPI_B2) {   // da_r = (da_h Wh^T) * H * r (1 - r); completes dvec and its operand A7
     const float4 r = ld4(ly.r + (size_t)m * ldL + n), ho = ld4(ly.Hold + (size_t)m * ldL + n);
     const float4 d = make_float4(v.x * ho.x * r.x * (1.f - r.x), v.y * ho.y * r.y * (1.f - r.y), v.z * ho.z * r.z * (1.f - r.z), v.w * ho.w * r.w * (1.f - r.w));
@@ -396,35 +406,32 @@ __device__ __forceinline__ void ts_epilogue4(const ModelDev& md, const TsBuf& tb
       v.z *= drop_scale(md.drop_seed, md.wG[s], G4R_STREAM_EMBED, e + 2, keep); v.w *= drop_scale(md.drop_seed, md.wG[s], G4R_STREAM_EMBED, e + 3, keep);
     }
     st4(md.dSx + (size_t)m * md.ld_in0 + n, v);
-  } else if (EPI == TS_EPI_DENSE) { // rows: [H*r | H | in0] features, columns: dvec = [da_h | da_r | da_z]  (dWh, dWrz, dWx + update, gru4rec.py:390-406)
+  } else {   // dense gradients + update: rows m = [H*r | H | in0] features; columns = da_h | da_z (A) or da_r (B)  (dWh, dWrz, dWx, gru4rec.py:390-406)
+    int col;                       // column of dvec = [da_h | da_r | da_z]
+    if (EPI == TS_EPI_DENSE_A) { const int c = n % tb.Lp; if (c >= L) return; col = n / tb.Lp ? 2 * L + c : c; }
+    else col = L + n;
+    float* p; float* acc; float* vel; size_t ast;
+    if (m < L) { if (col >= L) return; const size_t o = (size_t)m * ldL + col; p = ly.Wh + o; acc = ly.Wh_acc ? ly.Wh_acc + o : nullptr; vel = ly.Wh_vel ? ly.Wh_vel + o : nullptr; ast = (size_t)L * ldL; }
+    else if (m < 2 * L) { if (col < L) return; const size_t o = (size_t)(m - L) * ly.ld2 + (col - L); p = ly.Wrz + o; acc = ly.Wrz_acc ? ly.Wrz_acc + o : nullptr; vel = ly.Wrz_vel ? ly.Wrz_vel + o : nullptr; ast = (size_t)L * ly.ld2; }
+    else { const size_t o = (size_t)(m - 2 * L) * ly.ld3 + col; p = ly.Wx + o; acc = ly.Wx_acc ? ly.Wx_acc + o : nullptr; vel = ly.Wx_vel ? ly.Wx_vel + o : nullptr; ast = (size_t)L * ly.ld3; }
     const float g4[4] = {v.x, v.y, v.z, v.w};
-    if (m < L) {
-      if (n < L) { const size_t o = (size_t)m * ldL + n;
 #pragma unroll
-        for (int u = 0; u < 4; u++) dense_update(md, ly.Wh + o + u, ly.Wh_acc ? ly.Wh_acc + o + u : nullptr, ly.Wh_vel ? ly.Wh_vel + o + u : nullptr, g4[u], (size_t)L * ldL); }
-    } else if (m < 2 * L) {
-      if (n >= L) { const size_t o = (size_t)(m - L) * ly.ld2 + (n - L);
-#pragma unroll
-        for (int u = 0; u < 4; u++) dense_update(md, ly.Wrz + o + u, ly.Wrz_acc ? ly.Wrz_acc + o + u : nullptr, ly.Wrz_vel ? ly.Wrz_vel + o + u : nullptr, g4[u], (size_t)L * ly.ld2); }
-    } else { const size_t o = (size_t)(m - 2 * L) * ly.ld3 + n;
-#pragma unroll
-      for (int u = 0; u < 4; u++) dense_update(md, ly.Wx + o + u, ly.Wx_acc ? ly.Wx_acc + o + u : nullptr, ly.Wx_vel ? ly.Wx_vel + o + u : nullptr, g4[u], (size_t)L * ly.ld3); }
+    for (int u = 0; u < 4; u++) dense_update(md, p + u, acc ? acc + u : nullptr, vel ? vel + u : nullptr, g4[u], ast);
   }
 }
-// sum of the K splits (fixed order) + fused epilogue; consecutive threads on consecutive column quads
+// sum of the K splits written to global memory (fixed order) + fused epilogue; consecutive threads on consecutive column quads
 template <int EPI>
 __global__ void __launch_bounds__(256) k_ts_epi(int slot, const int* base, int off, TsGemm g, TsBuf tb) {
   const ModelDev& md = MD; const int s = STEP_IDX;
   const int M = md.wM[s];
   const int N = M + (md.wSti[s] >= 0 ? md.S : 0);
   int m_lim, n_lim;
-  ts_limits(md, EPI, M, N, m_lim, n_lim);
+  ts_limits<EPI>(md, tb, M, N, m_lim, n_lim);
   const int n4 = n_lim >> 2;
   const size_t ps = (size_t)g.m_tiles * TS_RB * g.ldP;
-  const int L = md.layer[0].L;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)m_lim * n4; i += (long long)gridDim.x * blockDim.x) {
     const int m = (int)(i / n4), n = (int)(i % n4) * 4;
-    if (EPI == TS_EPI_DENSE && ((m < L && n >= L) || (m >= L && m < 2 * L && n < L))) continue;   // blocks nobody uses
+    if (!ts_tile_live<EPI>(md, tb, M, N, m / TS_RB * TS_RB, n / g.NT * g.NT)) continue;      // that tile was never computed
     const float* p = g.P + (size_t)m * g.ldP + n;
     float4 v = ld4(p);
     for (int k = 1; k < g.ksplit; k++) { const float4 w = ld4(p + k * ps); v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
@@ -441,30 +448,33 @@ struct TsSmem {
   uint32_t tmem_base;
   int err;
 };
+__device__ __forceinline__ void ts_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
-__global__ void __launch_bounds__(TS_THREADS, 1) k_ts_gemm(int slot, const int* base, int off, TsGemm g) {
+template <int EPI>
+__global__ void __launch_bounds__(TS_THREADS, 1) k_ts_gemm(int slot, const int* base, int off, TsGemm g, TsBuf tb) {
   extern __shared__ __align__(1024) unsigned char ts_raw[];
   TsSmem& sm = *reinterpret_cast<TsSmem*>(ts_raw);
   const ModelDev& md = MD; const int s = STEP_IDX;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int M = md.wM[s];
   const int N = M + (md.wSti[s] >= 0 ? md.S : 0);
-  const int L = md.layer[0].L;
+  // the cluster = the K splits of one tile (consecutive blocks): all of them take the same early exit
   const int ks = blockIdx.x % g.ksplit, nt = (blockIdx.x / g.ksplit) % g.n_tiles, mt = blockIdx.x / (g.ksplit * g.n_tiles);
   const int m0 = mt * TS_RB, n0 = nt * g.NT;
-  // tiles without any live output leave at once (dynamic batch size / column count; unused blocks of the dense-gradient product)
-  {
-    int m_lim, n_lim;
-    ts_limits(md, g.epi, M, N, m_lim, n_lim);
-    if (m0 >= m_lim || n0 >= n_lim) return;
-    if (g.epi == TS_EPI_DENSE) {
-      const int blo = m0 / L, bhi = min(m0 + TS_RB - 1, 3 * L - 1) / L;    // feature blocks the tile's rows touch
-      const bool need_lo = blo == 0 || bhi == 2, need_hi = bhi >= 1;       // columns [0, L) / [L, 3L)
-      if (!((need_lo && n0 < L) || (need_hi && n0 + g.NT > L))) return;
-    }
+  if (!ts_tile_live<EPI>(md, tb, M, N, m0, n0)) return;     // dynamic batch size / column count; unused blocks of the dense-gradient products
+  if (EPI == TS_EPI_DH && blockIdx.x == 0 && tid == 0) {    // cost of the step = loss / batch_size (gru4rec.py:577); the row losses are final
+    float c = 0.f;
+    for (int bb = 0; bb < M; bb++) c += md.RS[(size_t)bb * G4R_NSTAT + 6];
+    c = __fdiv_rn(c, (float)md.B);
+    md.cost[s] = c;
+    if (c != c) atomicExch(md.nanflag, 1);
   }
   const int cps = (g.chunks + g.ksplit - 1) / g.ksplit;
-  const int c_beg = ks * cps, c_end = min(g.chunks, c_beg + cps);     // never empty (ts_shape)
+  const int c_beg = ks * cps, c_end = min(g.chunks, c_beg + cps);
+  const bool empty = c_beg >= c_end;                          // a K split without chunks contributes zeros
   const uint32_t b_bytes = (uint32_t)g.NT * TC_KC * 4;        // one hi (or lo) slab of the N tile
   const uint32_t stage_bytes = 2 * TS_BLK + 2 * b_bytes;      // 64 KB (NT = 128, 3 stages) or 96 KB (NT = 256, 2 stages)
   const uint32_t n_stage = TS_SMEM_OPER / stage_bytes;
@@ -518,27 +528,62 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_ts_gemm(int slot, const int* 
         }
         tc_commit(&sm.stage_free[st]);
       }
-      tc_commit(&sm.acc_full);
+      if (empty) tc_mbar_arrive(&sm.acc_full); else tc_commit(&sm.acc_full);
     }
   } else {
     tc_mbar_wait(&sm.acc_full, 0u, &sm.err);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // TMEM lane = tile row: a thread stores its row's 32-column groups as whole 128-byte lines of the partial tile
-    float* prow = g.P + ((size_t)ks * g.m_tiles * TS_RB + m0 + warp * 32 + lane) * g.ldP + n0;
+    // TMEM lane = tile row: a thread holds its row's 32-column groups.  They go either to the global partial tile (whole 128-byte
+    // lines) or to this CTA's shared-memory copy (the operand stages are free once the accumulator is complete)
+    const int row = warp * 32 + lane;
+    float* sT = reinterpret_cast<float*>(sm.stage);
+    const int ldt = g.NT + 4;
+    float* prow = g.P ? g.P + ((size_t)ks * g.m_tiles * TS_RB + m0 + row) * g.ldP + n0 : sT + (size_t)row * ldt;
     for (int q = 0; q < g.NT / 32; q++) {
       uint32_t r[32];
       const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + q * 32;
-      asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                   "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                     "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
-                     "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
-                     "=r"(r[30]), "=r"(r[31]) : "r"(taddr) : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (!empty) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                     "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                       "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+                       "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+                       "=r"(r[30]), "=r"(r[31]) : "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j++) r[j] = 0u;
+      }
 #pragma unroll
       for (int j = 0; j < 8; j++)
         *reinterpret_cast<uint4*>(prow + q * 32 + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
     }
+  }
+  if (!g.P) {
+    // cluster reduce: CTA `ks` owns rows [ks * 128 / ksplit, ...) of the tile; it adds the K splits in rank order straight from the
+    // peers' shared memory and runs the epilogue, consecutive threads on consecutive column quads
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();                     // the single-thread roles rejoin their warps before the aligned cluster barrier
+    ts_cluster_sync();
+    int m_lim, n_lim;
+    ts_limits<EPI>(md, tb, M, N, m_lim, n_lim);
+    const int rpc = TS_RB / g.ksplit, q4 = g.NT / 4, ldt = g.NT + 4;
+    const uint32_t sT = tc_smem_u32(sm.stage);
+    for (int idx = tid; idx < rpc * q4; idx += TS_THREADS) {
+      const int row = ks * rpc + idx / q4, c = (idx % q4) * 4;
+      const int m = m0 + row, n = n0 + c;
+      if (m >= m_lim || n >= n_lim) continue;
+      const uint32_t local = sT + (uint32_t)(row * ldt + c) * 4u;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int p = 0; p < g.ksplit; p++) {
+        uint32_t remote; float4 w;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(p));
+        asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w) : "r"(remote) : "memory");
+        if (p == 0) v = w; else { v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
+      }
+      ts_epilogue4<EPI>(md, tb, s, m, n, v);
+    }
+    ts_cluster_sync();                   // nobody leaves while a peer still reads its tile
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();

@@ -38,7 +38,7 @@ struct MgTensor { float *p, *acc, *vel; size_t goff; int count; };
 struct TsBuf {                 // device buffers of the tensor-core step (owned by the handle's workspace)
   unsigned char *A1, *A2, *A3, *A4, *A5, *A6, *A7, *A8;      // left operands  (rows x K) as hi|lo blocks
   unsigned char *W1, *W2, *W3, *W4, *B3, *B4, *B5, *B8a, *B8b;   // right operands (n x K)
-  float *Pa, *Pb;                                            // partial tiles of the two dense-gradient products (split K through global memory)
+  float *P, *P1, *Pa, *Pb;                                   // partial tiles of the split-K products: main stream, dSy (side 1), dense gradients (side 2)
   float *O, *bias;                                           // scores / dL/do [Bpad x ldO] (lane-major), bias of the sorted columns [NP]
   int ldO;
   int Mpad, Lk2, Lk1, Lk3, Nk, Bk;                           // padded extents: lanes; K = 2L, L, 3L, columns, lanes (multiples of 32)
@@ -213,6 +213,8 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// read-only path: for arrays the running kernel never writes (lets the compiler hoist the load above unrelated stores)
+__device__ __forceinline__ float4 ldn4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 // ------------------------------------------------------------------------------------------------
 // generic CTA-tile GEMM accumulate: acc[TM][TN] += sum_k A(m,k) * B(k,n) for the thread's micro tile of a

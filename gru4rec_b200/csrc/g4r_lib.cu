@@ -83,7 +83,7 @@ struct g4r_handle {
   bool two_pass = false;         // grad_cap: gradients are exported, the global norm is taken, then a second pass applies them scaled
   bool phase_only = false;       // grad_cap / smoothing add phases that only the per-phase launch sequence has
   float* dGscale = nullptr;
-  bool tc_ok = false; void* ts_buf = nullptr; cudaStream_t side = nullptr, side2 = nullptr; cudaEvent_t ts_ev[12] = {};      // tensor-core training step (g4r_tcstep.cuh): TsBuf*
+  bool tc_ok = false; void* ts_buf = nullptr; unsigned long long* ts_dbg = nullptr; cudaStream_t side = nullptr, side2 = nullptr; cudaEvent_t ts_ev[12] = {};      // tensor-core training step (g4r_tcstep.cuh): TsBuf*
   std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_phase;
 };
 
@@ -302,6 +302,11 @@ static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
     tsb.A6 = op(B, tsb.Lk1); tsb.A7 = op(B, tsb.Lk3); tsb.A8 = op(3 * L, tsb.Bk);
     tsb.W1 = op(2 * L, tsb.Lk2); tsb.W2 = op(L, tsb.Lk2); tsb.W3 = op(L, tsb.Lk1); tsb.W4 = op(L, tsb.Lk3);
     tsb.B3 = op(NP, tsb.Lk1); tsb.B4 = op(L, tsb.Bk); tsb.B5 = op(L, tsb.Nk); tsb.B8a = op(2 * tsb.Lp, tsb.Bk); tsb.B8b = op(L, tsb.Bk);
+    size_t pf = 0;          // the main-stream products run one after the other: one buffer of the largest size (any cluster cap)
+    for (const TsShape& t : {ts_shape(B, 2 * L, tsb.Lk2 / 32, n_sm, 16), ts_shape(B, L, tsb.Lk2 / 32, n_sm, 16), ts_shape(B, NP, tsb.Lk1 / 32, n_sm, 16),
+                             ts_shape(B, L, tsb.Nk / 32, n_sm, 16), ts_shape(B, L, tsb.Lk1 / 32, n_sm, 16), ts_shape(B, L, tsb.Lk3 / 32, n_sm, 16)}) pf = std::max(pf, t.p_floats);
+    tsb.P = cv.take<float>(pf);
+    tsb.P1 = cv.take<float>(ts_shape(tsb.Nk, L, tsb.Bk / 32, n_sm, 16).p_floats);
     tsb.Pa = cv.take<float>(ts_shape(3 * L, 2 * tsb.Lp, tsb.Bk / 32, n_sm, 0).p_floats);
     tsb.Pb = cv.take<float>(ts_shape(3 * L, L, tsb.Bk / 32, n_sm, 0).p_floats);
     tsb.O = cv.take<float>((size_t)tsb.Mpad * tsb.ldO); tsb.bias = cv.take<float>(tsb.Nk);
@@ -453,37 +458,75 @@ static bool tc_eligible(const g4r_config& c) {
   if (c.adapt > G4R_ADAPT_ADAGRAD || c.grad_cap > 0.f || c.smoothing != 0.f || c.world_size > 1) return false;
   return c.step_mode == 4 || (c.step_mode >= 1 && c.step_mode <= 3 && c.layers[0] >= 160);
 }
+// G4R_TS_STAMP=1: per-product phase timeline of the last step (median / max over the CTAs, microseconds after the first CTA's entry)
+static void ts_print_stamps(g4r_handle* h) {
+  std::vector<unsigned long long> d(9 * 512 * 16);
+  cudaDeviceSynchronize();
+  cudaMemcpy(d.data(), h->ts_dbg, d.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  for (int e = 0; e < 9; e++) {
+    unsigned long long t0 = ~0ull; int n = 0;
+    for (int c = 0; c < 512; c++) { const unsigned long long v = d[((size_t)e * 512 + c) * 16]; if (v && d[((size_t)e * 512 + c) * 16 + 1]) { t0 = std::min(t0, v); n++; } }
+    if (!n) continue;
+    fprintf(stderr, "[ts stamps] product %d, %d live CTAs:", e, n);
+    for (int i = 0; i < 10; i++) {
+      std::vector<double> v;
+      for (int c = 0; c < 512; c++) { const unsigned long long* r = &d[((size_t)e * 512 + c) * 16]; if (r[0] && r[1] && r[i]) v.push_back((double)(r[i] - t0) / 1000.0); }
+      if (v.empty()) { fprintf(stderr, " -"); continue; }
+      std::sort(v.begin(), v.end());
+      fprintf(stderr, " %d:%.1f/%.1f", i, v[v.size() / 2], v.back());
+    }
+    fprintf(stderr, "\n");
+  }
+}
 // one mini-batch on the tensor cores (window-relative step = *base + off when base != nullptr).  Three streams (forked / joined
 // with events, so the same code is captured into the step graph): the main stream carries the chain every product waits for;
 // side stream 1 prepares operands that do not depend on it (weights, item-table rows, transposed operands) and runs the dSy
 // product + the update of the scored rows; side stream 2 runs the dense-gradient products + dense update.
+static int g_ts_pdl = 0;               // programmatic dependent launch along the main chain (G4R_TS_PDL=0 switches it off)
+static int g_ts_cluster_big = 16;      // cluster size for the long-K products (non-portable size; G4R_TS_CLUSTER_BIG overrides)
 static int g_ts_cluster_cap = 0;       // largest cluster the K splits may form (8 = portable limit; G4R_TS_CLUSTER overrides)
 template <int EPI>
 static int launch_ts_gemm(g4r_handle* h, cudaStream_t q, int ph, const int* base, int off, TsGemm g, const TsBuf& tb) {
   cudaLaunchConfig_t lc = {};
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   lc.gridDim = dim3(g.m_tiles * g.n_tiles * g.ksplit); lc.blockDim = dim3(TS_THREADS); lc.dynamicSmemBytes = sizeof(TsSmem); lc.stream = q;
-  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = g.P ? 1 : g.ksplit; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  lc.attrs = at; lc.numAttrs = 1;
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = g.fused ? g.ksplit : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at; lc.numAttrs = (g_ts_pdl && q == h->stream) ? 2 : 1;
   int slot = h->slot;
+  if (h->ts_dbg) g.dbg = h->ts_dbg + (size_t)EPI * 512 * 16;
   void* args[] = {&slot, (void*)&base, &off, &g, (void*)&tb};
   cudaError_t e = cudaSuccess;
   LAUNCH_ON(q, ph, e = cudaLaunchKernelExC(&lc, (const void*)k_ts_gemm<EPI>, args));
   if (e != cudaSuccess) { h->err = std::string("k_ts_gemm launch: ") + cudaGetErrorString(e); return G4R_ERR_CUDA; }
   return G4R_OK;
 }
+// main-stream elementwise kernel (slot, base, off[, tb]) as a programmatic dependent of its predecessor
+static void launch_pdl(g4r_handle* h, int ph, const void* fn, dim3 grid, dim3 block, const int* base, int off, const TsBuf* tb) {
+  cudaLaunchConfig_t lc = {};
+  cudaLaunchAttribute at[1];
+  lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = 0; lc.stream = h->stream;
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at; lc.numAttrs = g_ts_pdl ? 1 : 0;
+  int slot = h->slot;
+  void* args[] = {&slot, (void*)&base, &off, (void*)tb};
+  LAUNCH(ph, cudaLaunchKernelExC(&lc, fn, args));
+}
 template <int EPI>
 static void launch_ts_epi(g4r_handle* h, cudaStream_t st, int ph, const int* base, int off, const TsGemm& g, const TsBuf& tb, int rows, int cols) {
   LAUNCH_ON(st, ph, k_ts_epi<EPI><<<std::min(4 * h->n_sm, std::max(1, (rows * (cols / 4) + 255) / 256)), 256, 0, st>>>(h->slot, base, off, g, tb));
 }
 static int ts_opt_in(g4r_handle* h) {
+  { const char* e = getenv("G4R_TS_PDL"); g_ts_pdl = e ? atoi(e) : 1; }
+  if (getenv("G4R_TS_STAMP") && !h->ts_dbg) { cudaMalloc(&h->ts_dbg, 9 * 512 * 16 * sizeof(unsigned long long)); cudaMemset(h->ts_dbg, 0, 9 * 512 * 16 * sizeof(unsigned long long)); }
+  { const char* e = getenv("G4R_TS_CLUSTER_BIG"); if (e) g_ts_cluster_big = std::max(1, std::min(16, atoi(e))); }
   if (!g_ts_cluster_cap) { const char* e = getenv("G4R_TS_CLUSTER"); g_ts_cluster_cap = e ? std::max(1, std::min(16, atoi(e))) : 8; }
   const void* fns[] = {(const void*)k_ts_gemm<TS_EPI_F1>, (const void*)k_ts_gemm<TS_EPI_F2>, (const void*)k_ts_gemm<TS_EPI_SCORE>, (const void*)k_ts_gemm<TS_EPI_DSY>,
                        (const void*)k_ts_gemm<TS_EPI_DH>, (const void*)k_ts_gemm<TS_EPI_B2>, (const void*)k_ts_gemm<TS_EPI_B3>,
                        (const void*)k_ts_gemm<TS_EPI_DENSE_A>, (const void*)k_ts_gemm<TS_EPI_DENSE_B>};
   for (const void* f : fns) {
     if (raise_smem_limit(f, sizeof(TsSmem)) != cudaSuccess) return G4R_ERR_CUDA;
-    if (g_ts_cluster_cap > 8 && cudaFuncSetAttribute(f, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return G4R_ERR_CUDA;
+    if (cudaFuncSetAttribute(f, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return G4R_ERR_CUDA;
   }
   return G4R_OK;
 }
@@ -495,8 +538,11 @@ static int enqueue_tc_step(g4r_handle* h, const int* base, int off) {
   const int L = md.L, B = md.B, slot = h->slot;
   const int fillg = 2 * h->n_sm;
   auto mk = [&](const unsigned char* A, const unsigned char* Bm, float* P, int chunks, int rows, int cols) -> TsGemm {
-    const TsShape t = ts_shape(rows, cols, chunks, h->n_sm, P ? 0 : g_ts_cluster_cap);
-    TsGemm g; g.A = A; g.Bm = Bm; g.P = P; g.chunks = chunks; g.m_tiles = t.m_tiles; g.n_tiles = t.n_tiles; g.NT = t.NT; g.ksplit = t.ksplit; g.ldP = t.ldP; g.epi = 0;
+    const bool fused = P != tb.Pa && P != tb.Pb;
+    int cap = g_ts_cluster_cap;
+    if (chunks > 4 * cap) cap = std::max(cap, g_ts_cluster_big);       // long K (dL/dh, dL/d input): more, shorter splits
+    const TsShape t = ts_shape(rows, cols, chunks, h->n_sm, fused ? cap : 0);
+    TsGemm g; g.A = A; g.Bm = Bm; g.P = P; g.fused = fused; g.dbg = nullptr; g.chunks = chunks; g.m_tiles = t.m_tiles; g.n_tiles = t.n_tiles; g.NT = t.NT; g.ksplit = t.ksplit; g.ldP = t.ldP; g.epi = 0;
     return g;
   };
 #define TS_GEMM(EPI, q, ph, g) do { const int rc_ = launch_ts_gemm<EPI>(h, q, ph, base, off, g, tb); if (rc_) return rc_; } while (0)
@@ -510,25 +556,25 @@ static int enqueue_tc_step(g4r_handle* h, const int* base, int off) {
   // main: input rows, GRU forward
   LAUNCH(PH_GATHER, k_ts_prep_fwd<<<dim3(fillg, 2), 256, 0, st>>>(slot, base, off, tb));
   cudaStreamWaitEvent(st, ev[1], 0);
-  TS_GEMM(TS_EPI_F1, st, PH_F1, mk(tb.A1, tb.W1, nullptr, tb.Lk2 / TC_KC, B, 2 * L));
+  TS_GEMM(TS_EPI_F1, st, PH_F1, mk(tb.A1, tb.W1, tb.P, tb.Lk2 / TC_KC, B, 2 * L));
   fork(3, st, s1);
   LAUNCH_ON(s1, PH_DENSE, k_ts_prep_a8<<<fillg, 256, 0, s1>>>(slot, base, off, tb));
   cudaEventRecord(ev[9], s1);
-  TS_GEMM(TS_EPI_F2, st, PH_F2, mk(tb.A2, tb.W2, nullptr, tb.Lk2 / TC_KC, B, L));
+  TS_GEMM(TS_EPI_F2, st, PH_F2, mk(tb.A2, tb.W2, tb.P, tb.Lk2 / TC_KC, B, L));
   fork(4, st, s1);
   LAUNCH_ON(s1, PH_LOSSGRAD, k_ts_prep_yt<<<fillg, 256, 0, s1>>>(slot, base, off, tb));
   // main: scores, loss, dL/do
   cudaStreamWaitEvent(st, ev[2], 0);
-  TS_GEMM(TS_EPI_SCORE, st, PH_SCORE, mk(tb.A3, tb.B3, nullptr, tb.Lk1 / TC_KC, B, md.NP));
-  LAUNCH(PH_LOSSGRAD, k_ts_loss<<<B, 256, 0, st>>>(slot, base, off, tb));
+  TS_GEMM(TS_EPI_SCORE, st, PH_SCORE, mk(tb.A3, tb.B3, tb.P, tb.Lk1 / TC_KC, B, md.NP));
+  launch_pdl(h, PH_LOSSGRAD, (const void*)k_ts_loss, dim3(B), dim3(256), base, off, &tb);
   fork(5, st, s1);
   // side 1: dSy product and the update of the scored rows
   LAUNCH_ON(s1, PH_LOSSGRAD, k_ts_prep_g<<<dim3(fillg, 2), 256, 0, s1>>>(slot, base, off, tb));
-  TS_GEMM(TS_EPI_DSY, s1, PH_LOSSGRAD, mk(tb.A4, tb.B4, nullptr, tb.Bk / TC_KC, tb.Nk, L));
+  TS_GEMM(TS_EPI_DSY, s1, PH_LOSSGRAD, mk(tb.A4, tb.B4, tb.P1, tb.Bk / TC_KC, tb.Nk, L));
   LAUNCH_ON(s1, PH_LOSSGRAD, k_apply_rows<<<md.NCH, SC_THREADS, 0, s1>>>(slot, base, off));
   cudaEventRecord(ev[6], s1);
   // main: GRU backward (b1 is the epilogue of the dL/dh product)
-  TS_GEMM(TS_EPI_DH, st, PH_B1, mk(tb.A5, tb.B5, nullptr, tb.Nk / TC_KC, B, L));
+  TS_GEMM(TS_EPI_DH, st, PH_B1, mk(tb.A5, tb.B5, tb.P, tb.Nk / TC_KC, B, L));
   fork(7, st, s2);
   // side 2: dense gradients of the da_h / da_z columns + update
   LAUNCH_ON(s2, PH_DENSE, k_ts_prep_b8<<<fillg, 256, 0, s2>>>(slot, base, off, tb, 0));
@@ -536,7 +582,7 @@ static int enqueue_tc_step(g4r_handle* h, const int* base, int off) {
   const TsGemm g8a = mk(tb.A8, tb.B8a, tb.Pa, tb.Bk / TC_KC, 3 * L, 2 * tb.Lp);
   TS_GEMM(TS_EPI_DENSE_A, s2, PH_DENSE, g8a);
   launch_ts_epi<TS_EPI_DENSE_A>(h, s2, PH_DENSE, base, off, g8a, tb, 3 * L, 2 * tb.Lp);
-  TS_GEMM(TS_EPI_B2, st, PH_B2, mk(tb.A6, tb.W3, nullptr, tb.Lk1 / TC_KC, B, L));
+  TS_GEMM(TS_EPI_B2, st, PH_B2, mk(tb.A6, tb.W3, tb.P, tb.Lk1 / TC_KC, B, L));
   fork(8, st, s2);
   // side 2: the da_r columns
   LAUNCH_ON(s2, PH_DENSE, k_ts_prep_b8<<<fillg, 256, 0, s2>>>(slot, base, off, tb, 1));
@@ -544,8 +590,8 @@ static int enqueue_tc_step(g4r_handle* h, const int* base, int off) {
   TS_GEMM(TS_EPI_DENSE_B, s2, PH_DENSE, g8b);
   launch_ts_epi<TS_EPI_DENSE_B>(h, s2, PH_DENSE, base, off, g8b, tb, 3 * L, L);
   // main: dL/d(input rows), the bias gradient, then the input-row update (after the scored-row update: both touch the shared table)
-  TS_GEMM(TS_EPI_B3, st, PH_B3, mk(tb.A7, tb.W4, nullptr, tb.Lk3 / TC_KC, B, L));
-  LAUNCH(PH_DENSE, k_ts_bh<<<(3 * L + 31) / 32, 256, 0, st>>>(slot, base, off));
+  TS_GEMM(TS_EPI_B3, st, PH_B3, mk(tb.A7, tb.W4, tb.P, tb.Lk3 / TC_KC, B, L));
+  launch_pdl(h, PH_DENSE, (const void*)k_ts_bh, dim3((3 * L + 31) / 32), dim3(256), base, off, nullptr);
   cudaStreamWaitEvent(st, ev[6], 0);
   LAUNCH(PH_SPARSE_IN, k_sparse_in<<<B, 128, 0, st>>>(slot, base, off, 1));
   cudaEventRecord(ev[10], s2); cudaStreamWaitEvent(st, ev[10], 0);
@@ -638,6 +684,7 @@ extern "C" int g4r_destroy(g4r_handle* h) {
   if (h->hCost) cudaFreeHost(h->hCost);
   if (h->hFlags) cudaFreeHost(h->hFlags);
   if (h->own_ws && h->ws) cudaFree(h->ws);
+  if (h->ts_dbg) { ts_print_stamps(h); cudaFree(h->ts_dbg); }
   if (h->side) cudaStreamDestroy(h->side);
   if (h->side2) cudaStreamDestroy(h->side2);
   for (cudaEvent_t e : h->ts_ev) if (e) cudaEventDestroy(e);

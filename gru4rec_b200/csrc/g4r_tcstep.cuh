@@ -8,23 +8,32 @@
 //             TMEM reproduces the fp32 product to ~2^-21 relative) and stored as [hi | lo] blocks of 128 rows x 32 k-values in the
 //             K-major 128-byte-swizzle UMMA layout by small "prep" kernels that also do the gathers
 //             (Wy[item] rows of the score columns, H through the lane slots), transposes and elementwise products (H * r);
-//   GEMM      one CTA per 128 x NT output tile (NT = 32..128): a TMA thread streams the operand blocks with bulk copies into a
-//             3-stage shared-memory ring (mbarrier complete_tx), an MMA thread issues tcgen05.mma kind::tf32 (M = 128, N = NT,
-//             K = 8) and hands stages back with tcgen05.commit, four epilogue warps read the accumulator with tcgen05.ld and
-//             apply the fused epilogue (gates + sigmoid, candidate + GRU update + dropout + reset, score + bias, dSy rows,
-//             partial dL/dh per K split, da_r, dL/d(input), dense gradient + Adagrad/momentum update);
-//   the rest  row statistics, dL/do, the partial-sum reduce (b1), and the deterministic sparse updates reuse the generic
-//             phases (g4r_kernels.cuh) -- same numerics, same duplicate rules.
+//   GEMM      128 x 256 output tiles (a tcgen05.mma costs ~150 cycles to issue whatever its N, so N is as wide as the
+//             instruction allows); K is split over the CTAs of a thread-block cluster.  Per CTA: a TMA thread streams the operand
+//             blocks with bulk copies into a 2-stage shared-memory ring (mbarrier complete_tx), an MMA thread issues tcgen05.mma
+//             kind::tf32 (M = 128, N = 256, K = 8) and hands stages back with tcgen05.commit, four warps read the accumulator with
+//             tcgen05.ld; the partial tile goes through L2, and after a cluster barrier each CTA adds the K splits of its band of
+//             rows in K order and applies the fused epilogue (gates + sigmoid + the H*r operand, candidate + GRU update + dropout +
+//             reset + the score operand, score + bias, dSy rows, b1 = elementwise GRU backward + operands, da_r, dL/d(input));
+//             the two dense-gradient products leave their partial tiles to an elementwise kernel that does the optimizer step;
+//   schedule  three streams joined by events (captured into the step graph), programmatic dependent launch along the main chain;
+//   the rest  row statistics + dL/do (one kernel per step), and the deterministic sparse updates reuse the generic phases
+//             (g4r_kernels.cuh) -- same numerics, same duplicate rules.
 // Included from g4r_lib.cu after g4r_eval.cuh (uses its mbarrier / UMMA helpers).
 #pragma once
+#include <cooperative_groups.h>
 
 constexpr int TS_RB = 128;                               // rows per operand block
 constexpr uint32_t TS_BLK = TS_RB * TC_KC * 4;           // bytes of one hi (or lo) block: 16 KB
-constexpr int TS_THREADS = 192;                          // 4 epilogue warps + TMA warp + MMA warp
+constexpr int TS_THREADS = 512;                          // 4 TMEM-reading warps + TMA warp + MMA warp; all 16 warps run the reduce / epilogue
 
 
 
 
+// programmatic dependent launch: a kernel launched with the attribute may start (and set itself up) while its predecessor in the
+// stream still runs; it consumes the predecessor's results only after pdl_wait().  No-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void ts_put4(unsigned char* base, int n_chunk, int row, int k, float4 v) {
   const int rb = row / TS_RB, r = row % TS_RB, c = k / TC_KC, kq = (k % TC_KC) >> 2;
   unsigned char* hi = base + ((size_t)rb * n_chunk + c) * 2 * TS_BLK + tc_block_off(r, kq);
@@ -68,6 +77,8 @@ __device__ __forceinline__ void ts_colsum(int n_cols, int n_rows, FLoad ld, FOut
 struct TsGemm {
   const unsigned char* A; const unsigned char* Bm;
   float* P;              // partial tiles [ksplit][m_tiles * 128][ldP]
+  int fused;                 // 1: the K splits are a cluster, reduce + epilogue in the kernel; 0: k_ts_epi does it
+  unsigned long long* dbg;   // per-CTA phase timestamps (G4R_TS_STAMP=1), else nullptr
   int chunks;            // K_pad / 32 (both operands)
   int m_tiles, n_tiles, NT, ksplit, ldP;
   int epi;
@@ -90,6 +101,7 @@ __global__ void __launch_bounds__(256) k_ts_prep_fwd(int slot, const int* base, 
   const LayerDev& ly = md.layer[0];
   const int M = md.wM[s], L = ly.L, ldL = ly.ldL, L4 = L / 4;
   const int* __restrict__ wX = md.wX + (size_t)s * md.B;
+  pdl_trigger();
   if (blockIdx.y == 0) {          // A1, in0 half of A2, in0 itself
     const int n_chunk = tb.Lk2 / TC_KC;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M * 2 * L4; i += gridDim.x * blockDim.x) {
@@ -212,6 +224,7 @@ __global__ void __launch_bounds__(256) k_ts_loss(int slot, const int* base, int 
   const int M = md.wM[s];
   const int N = M + (md.wSti[s] >= 0 ? md.S : 0);
   const int b = blockIdx.x;
+  pdl_wait(); pdl_trigger();
   if (b >= M) return;
   __shared__ float sW[8 * 8];
   __shared__ float sRS[8];
@@ -301,6 +314,7 @@ __global__ void __launch_bounds__(256) k_ts_bh(int slot, const int* base, int of
   const ModelDev& md = MD; const int s = STEP_IDX;
   const LayerDev& ly = md.layer[0];
   const int M = md.wM[s];
+  pdl_wait(); pdl_trigger();
   ts_colsum(3 * ly.L, M, [&](int b, int c) { return ly.dvec[(size_t)b * ly.ld3 + c]; },
             [&](int c, float g) { dense_update(md, ly.Bh + c, ly.Bh_acc ? ly.Bh_acc + c : nullptr, ly.Bh_vel ? ly.Bh_vel + c : nullptr, g, (size_t)ly.ld3); });
 }
@@ -347,15 +361,15 @@ __device__ __forceinline__ void ts_epilogue4(const ModelDev& md, const TsBuf& tb
   const LayerDev& ly = md.layer[0];
   const int L = ly.L, ldL = ly.ldL;
   if (EPI == TS_EPI_F1) {          // rz = sigmoid(vec[:, L:] + H Wrz) (gru4rec.py:460); the r half also makes the Hold * r part of A2
-    const float4 bh = ld4(ly.Bh + L + n);
+    const float4 bh = ldn4(ly.Bh + L + n);
     const float4 g = make_float4(sigmoidf_(v.x + bh.x), sigmoidf_(v.y + bh.y), sigmoidf_(v.z + bh.z), sigmoidf_(v.w + bh.w));
     if (n < L) {
       st4(ly.r + (size_t)m * ldL + n, g);
-      const float4 ho = ld4(ly.Hold + (size_t)m * ldL + n);
+      const float4 ho = ldn4(ly.Hold + (size_t)m * ldL + n);
       ts_put4(tb.A2, tb.Lk2 / TC_KC, m, L + n, make_float4(ho.x * g.x, ho.y * g.y, ho.z * g.z, ho.w * g.w));
     } else st4(ly.z + (size_t)m * ldL + (n - L), g);
   } else if (EPI == TS_EPI_F2) {   // h~ = act((H * r) Wh + vec[:, :L]); h = (1 - z) H + z h~; dropout; reset (gru4rec.py:461-466); h is also A3
-    const float4 bh = ld4(ly.Bh + n), z = ld4(ly.z + (size_t)m * ldL + n), ho = ld4(ly.Hold + (size_t)m * ldL + n);
+    const float4 bh = ldn4(ly.Bh + n), z = ldn4(ly.z + (size_t)m * ldL + n), ho = ldn4(ly.Hold + (size_t)m * ldL + n);
     const float a[4] = {v.x + bh.x, v.y + bh.y, v.z + bh.z, v.w + bh.w}, zv[4] = {z.x, z.y, z.z, z.w}, hov[4] = {ho.x, ho.y, ho.z, ho.w};
     float ht[4], hn[4];
 #pragma unroll
@@ -371,13 +385,13 @@ __device__ __forceinline__ void ts_epilogue4(const ModelDev& md, const TsBuf& tb
     st4(ly.H + (size_t)md.wSlot[(size_t)s * md.B + m] * ldL + n, (md.wF[(size_t)s * md.B + m] & 1) ? ts_zero4() : h4);
     ts_put4(tb.A3, tb.Lk1 / TC_KC, m, n, h4);
   } else if (EPI == TS_EPI_SCORE) { // o = h Sy^T + by (- logq correction) (gru4rec.py:493-495), lane-major
-    const float4 bz = ld4(tb.bias + n);
+    const float4 bz = ldn4(tb.bias + n);
     st4(tb.O + (size_t)m * tb.ldO + n, make_float4(v.x + bz.x, v.y + bz.y, v.z + bz.z, v.w + bz.w));
   } else if (EPI == TS_EPI_DSY) {  // dSy_j = sum_b g[b][j] h[b]
     st4(md.DSY + (size_t)m * ldL + n, v);
   } else if (EPI == TS_EPI_DH) {   // b1: v = dL/dh; elementwise GRU backward; da_h / da_z go to dvec and into A6 = da_h, A7 = dvec
     const size_t o = (size_t)m * ldL + n;
-    const float4 ht = ld4(ly.ht + o), ho = ld4(ly.Hold + o), z = ld4(ly.z + o), ah = ld4(ly.ah + o);
+    const float4 ht = ldn4(ly.ht + o), ho = ldn4(ly.Hold + o), z = ldn4(ly.z + o), ah = ldn4(ly.ah + o);
     const float dyv[4] = {v.x, v.y, v.z, v.w}, htv[4] = {ht.x, ht.y, ht.z, ht.w}, hov[4] = {ho.x, ho.y, ho.z, ho.w}, zv[4] = {z.x, z.y, z.z, z.w},
                 ahv[4] = {ah.x, ah.y, ah.z, ah.w};
     float dah[4], dz[4];
@@ -395,7 +409,7 @@ __device__ __forceinline__ void ts_epilogue4(const ModelDev& md, const TsBuf& tb
     ts_put4(tb.A7, tb.Lk3 / TC_KC, m, n, a4);
     ts_put4(tb.A7, tb.Lk3 / TC_KC, m, 2 * L + n, z4);
   } else if (EPI == TS_EPI_B2) {   // da_r = (da_h Wh^T) * H * r (1 - r); completes dvec and its operand A7
-    const float4 r = ld4(ly.r + (size_t)m * ldL + n), ho = ld4(ly.Hold + (size_t)m * ldL + n);
+    const float4 r = ldn4(ly.r + (size_t)m * ldL + n), ho = ldn4(ly.Hold + (size_t)m * ldL + n);
     const float4 d = make_float4(v.x * ho.x * r.x * (1.f - r.x), v.y * ho.y * r.y * (1.f - r.y), v.z * ho.z * r.z * (1.f - r.z), v.w * ho.w * r.w * (1.f - r.w));
     st4(ly.dvec + (size_t)m * ly.ld3 + L + n, d);
     ts_put4(tb.A7, tb.Lk3 / TC_KC, m, L + n, d);
@@ -453,6 +467,7 @@ __device__ __forceinline__ void ts_cluster_sync() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+#define TS_STAMP(i) do { if (g.dbg) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g.dbg[(size_t)blockIdx.x * 16 + (i)] = t_; } } while (0)
 template <int EPI>
 __global__ void __launch_bounds__(TS_THREADS, 1) k_ts_gemm(int slot, const int* base, int off, TsGemm g, TsBuf tb) {
   extern __shared__ __align__(1024) unsigned char ts_raw[];
@@ -464,14 +479,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_ts_gemm(int slot, const int* 
   // the cluster = the K splits of one tile (consecutive blocks): all of them take the same early exit
   const int ks = blockIdx.x % g.ksplit, nt = (blockIdx.x / g.ksplit) % g.n_tiles, mt = blockIdx.x / (g.ksplit * g.n_tiles);
   const int m0 = mt * TS_RB, n0 = nt * g.NT;
-  if (!ts_tile_live<EPI>(md, tb, M, N, m0, n0)) return;     // dynamic batch size / column count; unused blocks of the dense-gradient products
-  if (EPI == TS_EPI_DH && blockIdx.x == 0 && tid == 0) {    // cost of the step = loss / batch_size (gru4rec.py:577); the row losses are final
-    float c = 0.f;
-    for (int bb = 0; bb < M; bb++) c += md.RS[(size_t)bb * G4R_NSTAT + 6];
-    c = __fdiv_rn(c, (float)md.B);
-    md.cost[s] = c;
-    if (c != c) atomicExch(md.nanflag, 1);
-  }
+  if (tid == 0) TS_STAMP(0);
+  if (!ts_tile_live<EPI>(md, tb, M, N, m0, n0)) { pdl_wait(); return; }     // dynamic batch size / column count; unused blocks of the dense-gradient products
   const int cps = (g.chunks + g.ksplit - 1) / g.ksplit;
   const int c_beg = ks * cps, c_end = min(g.chunks, c_beg + cps);
   const bool empty = c_beg >= c_end;                          // a K split without chunks contributes zeros
@@ -494,6 +503,16 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_ts_gemm(int slot, const int* 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = sm.tmem_base;
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.NT >> 3) << 17) | ((uint32_t)(TS_RB >> 4) << 24);
+  if (tid == 0) TS_STAMP(1);
+  pdl_wait();               // everything above overlapped the previous kernel of the stream; its results are visible from here on
+  pdl_trigger();
+  if (EPI == TS_EPI_DH && blockIdx.x == 0 && tid == 0) {    // cost of the step = loss / batch_size (gru4rec.py:577); the row losses are final
+    float c = 0.f;
+    for (int bb = 0; bb < M; bb++) c += md.RS[(size_t)bb * G4R_NSTAT + 6];
+    c = __fdiv_rn(c, (float)md.B);
+    md.cost[s] = c;
+    if (c != c) atomicExch(md.nanflag, 1);
+  }
   if (warp == 4) {
     if (lane == 0) {
       unsigned int it = 0;
@@ -509,6 +528,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_ts_gemm(int slot, const int* 
           tc_bulk_copy(dst + 2 * TS_BLK + q * TS_BLK, bsrc, TS_BLK, &sm.stage_full[st]);
           tc_bulk_copy(dst + 2 * TS_BLK + b_bytes + q * TS_BLK, bsrc + TS_BLK, TS_BLK, &sm.stage_full[st]);
         }
+        if (c == c_beg) TS_STAMP(2);
       }
     }
   } else if (warp == 5) {
@@ -517,6 +537,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_ts_gemm(int slot, const int* 
       for (int c = c_beg; c < c_end; c++, it++) {
         const uint32_t st = it % n_stage, use = it / n_stage;
         tc_mbar_wait(&sm.stage_full[st], use & 1u, &sm.err);
+        if (c == c_beg) TS_STAMP(3);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_hi = tc_smem_u32(sm.stage + st * stage_bytes), a_lo = a_hi + TS_BLK, b_hi = a_hi + 2 * TS_BLK, b_lo = b_hi + b_bytes;
 #pragma unroll
@@ -529,61 +550,85 @@ __global__ void __launch_bounds__(TS_THREADS, 1) k_ts_gemm(int slot, const int* 
         tc_commit(&sm.stage_free[st]);
       }
       if (empty) tc_mbar_arrive(&sm.acc_full); else tc_commit(&sm.acc_full);
+      TS_STAMP(4);
     }
-  } else {
+  } else if (warp < 4) {
     tc_mbar_wait(&sm.acc_full, 0u, &sm.err);
+    if (tid == 0) TS_STAMP(5);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // TMEM lane = tile row: a thread holds its row's 32-column groups.  They go either to the global partial tile (whole 128-byte
-    // lines) or to this CTA's shared-memory copy (the operand stages are free once the accumulator is complete)
-    const int row = warp * 32 + lane;
+  }
+  // TMEM lane = tile row: an epilogue thread holds its row in 32-column groups
+  auto load_group = [&](int q, uint32_t (&r)[32]) {
+    if (empty) {
+#pragma unroll
+      for (int j = 0; j < 32; j++) r[j] = 0u;
+      return;
+    }
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + q * 32;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+                   "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+                   "=r"(r[30]), "=r"(r[31]) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  };
+  // split K through global memory (L2).  TMEM lane = tile row, so a thread holds one row: the tile is transposed through shared
+  // memory (the operand stages are free once the accumulator is complete) and all warps store it as whole 512-byte row pieces
+  {
     float* sT = reinterpret_cast<float*>(sm.stage);
-    const int ldt = g.NT + 4;
-    float* prow = g.P ? g.P + ((size_t)ks * g.m_tiles * TS_RB + m0 + row) * g.ldP + n0 : sT + (size_t)row * ldt;
-    for (int q = 0; q < g.NT / 32; q++) {
-      uint32_t r[32];
-      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + q * 32;
-      if (!empty) {
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                     "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                       "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
-                       "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
-                       "=r"(r[30]), "=r"(r[31]) : "r"(taddr) : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      } else {
+    const int ldt = g.NT + 4, q4 = g.NT / 4;
+    if (warp < 4) {
+      float* srow = sT + (size_t)(warp * 32 + lane) * ldt;
+      for (int q = 0; q < g.NT / 32; q++) {
+        uint32_t r[32];
+        load_group(q, r);
 #pragma unroll
-        for (int j = 0; j < 32; j++) r[j] = 0u;
+        for (int j = 0; j < 8; j++)
+          *reinterpret_cast<uint4*>(srow + q * 32 + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
       }
-#pragma unroll
-      for (int j = 0; j < 8; j++)
-        *reinterpret_cast<uint4*>(prow + q * 32 + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) TS_STAMP(6);
+    float* ptile = g.P + ((size_t)ks * g.m_tiles * TS_RB + m0) * g.ldP + n0;
+    for (int idx = tid; idx < TS_RB * q4; idx += TS_THREADS) {
+      const int row = idx / q4, c = (idx % q4) * 4;
+      *reinterpret_cast<float4*>(ptile + (size_t)row * g.ldP + c) = *reinterpret_cast<const float4*>(sT + (size_t)row * ldt + c);
     }
   }
-  if (!g.P) {
-    // cluster reduce: CTA `ks` owns rows [ks * 128 / ksplit, ...) of the tile; it adds the K splits in rank order straight from the
-    // peers' shared memory and runs the epilogue, consecutive threads on consecutive column quads
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();                     // the single-thread roles rejoin their warps before the aligned cluster barrier
+  if (g.fused) {
+    // the K splits of a tile are the CTAs of one cluster (co-resident): after the cluster barrier (release / acquire) CTA `ks` adds
+    // the splits of its band of rows in K order -- the same sum whatever the schedule -- and applies the epilogue, consecutive
+    // threads on consecutive column quads.  (Measured: exchanging the tiles through distributed shared memory instead costs
+    // 6.7 us per 128 KB tile at ~20 B/clk per SM; L2 moves the same bytes in ~1.3 us.)
+    __threadfence();
     ts_cluster_sync();
+    if (tid == 0) TS_STAMP(7);
     int m_lim, n_lim;
     ts_limits<EPI>(md, tb, M, N, m_lim, n_lim);
-    const int rpc = TS_RB / g.ksplit, q4 = g.NT / 4, ldt = g.NT + 4;
-    const uint32_t sT = tc_smem_u32(sm.stage);
-    for (int idx = tid; idx < rpc * q4; idx += TS_THREADS) {
-      const int row = ks * rpc + idx / q4, c = (idx % q4) * 4;
-      const int m = m0 + row, n = n0 + c;
-      if (m >= m_lim || n >= n_lim) continue;
-      const uint32_t local = sT + (uint32_t)(row * ldt + c) * 4u;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int p = 0; p < g.ksplit; p++) {
-        uint32_t remote; float4 w;
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(p));
-        asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w) : "r"(remote) : "memory");
-        if (p == 0) v = w; else { v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
+    const int rpc = TS_RB / g.ksplit, q4 = g.NT / 4, total = rpc * q4;
+    const size_t ps = (size_t)g.m_tiles * TS_RB * g.ldP;
+    for (int i0 = tid; i0 < total; i0 += TS_THREADS * 4) {       // four quads per thread at a time: all their loads are in flight together
+      float4 acc[4]; int mm[4], nn[4]; bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int idx = i0 + u * TS_THREADS;
+        mm[u] = m0 + ks * rpc + idx / q4; nn[u] = n0 + (idx % q4) * 4;
+        ok[u] = idx < total && mm[u] < m_lim && nn[u] < n_lim;
+        acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      ts_epilogue4<EPI>(md, tb, s, m, n, v);
+      for (int k = 0; k < g.ksplit; k++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (ok[u]) {
+          const float4 w = __ldcg(reinterpret_cast<const float4*>(g.P + k * ps + (size_t)mm[u] * g.ldP + nn[u]));
+          if (k == 0) acc[u] = w; else { acc[u].x += w.x; acc[u].y += w.y; acc[u].z += w.z; acc[u].w += w.w; }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) if (ok[u]) ts_epilogue4<EPI>(md, tb, s, mm[u], nn[u], acc[u]);
     }
-    ts_cluster_sync();                   // nobody leaves while a peer still reads its tile
+    if (tid == 0) TS_STAMP(8);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();

@@ -267,12 +267,13 @@ extern "C" int g4r_eval_schedule(g4r_handle* h, const g4r_schedule* s, const int
   CK(cudaMemsetAsync(e->dSums, 0, 128 * sizeof(double), st));
   // tensor-core scoring (full-catalogue ranking of a wide batch): the item table is split once per evaluation into hi / lo
   // TF32 operand blocks; cfg.eval_tc: 1 forces the fp32 FFMA tiles, 2 forces tcgen05
-  const int tc_chunks = (h->md.L + TC_KC - 1) / TC_KC, tc_tiles = (I + TC_N - 1) / TC_N, tc_lblocks = (Be + TC_M - 1) / TC_M;
+  const int tc_chunks = (h->md.L + 1 + TC_KC - 1) / TC_KC,      // + the bias column
+             tc_tiles = (I + TC_N - 1) / TC_N, tc_lblocks = (Be + TC_M - 1) / TC_M;
   const bool tc_possible = e->n_cand == 0 && mode != 3 && h->cfg.eval_tc != 1 && (h->cfg.eval_tc == 2 || (Bs >= 64 && I >= 2048));
   if (tc_possible) {
     if (!e->dAsplit) CK(cudaMalloc(&e->dAsplit, (size_t)tc_lblocks * tc_chunks * 2 * TC_A_BYTES));     // hidden states: blocks of 128 lanes
     if (!e->dBsplit) CK(cudaMalloc(&e->dBsplit, (size_t)tc_tiles * tc_chunks * 2 * TC_B_BYTES));       // item table: blocks of 256 items
-    k_tc_split<TC_N><<<dim3(tc_tiles, tc_chunks), 256, 0, st>>>(h->md.Wy, I, h->md.ldL, h->md.L, e->dBsplit, tc_chunks);
+    k_tc_split<TC_N><<<dim3(tc_tiles, tc_chunks), 256, 0, st>>>(h->md.Wy, I, h->md.ldL, h->md.L, e->dBsplit, tc_chunks, h->md.By, 0.f);
     h->launches++;
   }
   int64_t done = 0;
@@ -308,7 +309,7 @@ extern "C" int g4r_eval_schedule(g4r_handle* h, const g4r_schedule* s, const int
       const int M_i = e->hM[i];
       const bool tc = tc_possible && (h->cfg.eval_tc == 2 || M_i >= 64);
       if (tc) {
-        k_tc_split<TC_M><<<dim3((M_i + TC_M - 1) / TC_M, tc_chunks), 256, 0, st>>>(h->md.layer[h->md.n_layers - 1].y, M_i, h->md.ldL, h->md.L, e->dAsplit, tc_chunks);
+        k_tc_split<TC_M><<<dim3((M_i + TC_M - 1) / TC_M, tc_chunks), 256, 0, st>>>(h->md.layer[h->md.n_layers - 1].y, M_i, h->md.ldL, h->md.L, e->dAsplit, tc_chunks, nullptr, 1.0f);
         k_eval_tc<<<std::min(tc_tiles, h->n_sm), TC_THREADS, sizeof(TcSmem), st>>>(e->slot, (int)i, h->dTgt, h->dRankCnt, e->dAsplit, e->dBsplit);
         h->launches++;
       } else k_eval_score<false><<<(n_comp + EV_IT - 1) / EV_IT, EV_THREADS, eval_smem_bytes(), st>>>(e->slot, (int)i, h->dTgt, h->dRankCnt, nullptr, e->n_cand > 0 ? e->dCand : nullptr, e->n_cand, tie);

@@ -90,8 +90,13 @@ __device__ __forceinline__ void tc_commit(unsigned long long* bar) {
 // states): block (rb, c) = rows [rb * RB, +RB) x k [32 c, +32) as [hi | lo], each in the K-major 128-byte-swizzle layout
 // (tc_block_off).  The scoring kernel then feeds the tensor cores with plain bulk copies (TMA) -- no register staging on the
 // critical path.
+// The contraction runs over K + 1 values: column K holds `one` on the hidden-state side and the item bias on the table side
+// (bias != nullptr), so the accumulator is the complete pre-activation score; table rows past the catalogue get a bias of -3e38,
+// which no threshold ever reaches (the epilogue needs no per-column validity test).
+constexpr float TC_PAD_BIAS = -3.0e38f;
 template <int RB>
-__global__ void __launch_bounds__(256) k_tc_split(const float* __restrict__ src, int nrows, int ld, int K, unsigned char* __restrict__ dst, int n_chunk) {
+__global__ void __launch_bounds__(256) k_tc_split(const float* __restrict__ src, int nrows, int ld, int K, unsigned char* __restrict__ dst, int n_chunk,
+                                                  const float* __restrict__ bias, float one) {
   const int rb = blockIdx.x, c = blockIdx.y;
   unsigned char* hi = dst + ((size_t)rb * n_chunk + c) * 2 * (RB * TC_KC * 4);
   unsigned char* lo = hi + RB * TC_KC * 4;
@@ -101,6 +106,11 @@ __global__ void __launch_bounds__(256) k_tc_split(const float* __restrict__ src,
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     const int row = rb * RB + r;
     if (row < nrows && k0 + cc * 4 < K) v = ld4(src + (size_t)row * ld + k0 + cc * 4);
+    if (K - (k0 + cc * 4) >= 0 && K - (k0 + cc * 4) < 4) {       // the extra column (K % 4 == 0 is not required)
+      const float x = bias ? (row < nrows ? bias[row] : TC_PAD_BIAS) : one;
+      const int u = K - (k0 + cc * 4);
+      if (u == 0) v = make_float4(x, 0.f, 0.f, 0.f); else if (u == 1) v.y = x, v.z = 0.f, v.w = 0.f; else if (u == 2) v.z = x, v.w = 0.f; else v.w = x;
+    }
     const uint32_t off = tc_block_off(r, cc);
     uint4 h, l;
     h.x = tc_tf32(v.x); h.y = tc_tf32(v.y); h.z = tc_tf32(v.z); h.w = tc_tf32(v.w);
@@ -115,6 +125,26 @@ __device__ __forceinline__ void tc_bulk_copy(void* sdst, const void* gsrc, uint3
                :: "r"(tc_smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(tc_smem_u32(bar)) : "memory");
 }
 
+// Ranking compares act(x) with the target score t = act(x_t).  act is monotone non-decreasing, so for every lane there are two
+// pre-activation thresholds with  act(x) > t  <=>  x > hi  and  act(x) == t  <=>  lo <= x <= hi : they are found once per lane by
+// bisection over the ordered fp32 bit patterns with the very act_fwd the fp32 kernels use (64 evaluations per lane), and the
+// per-item work drops to two compares.
+__device__ __forceinline__ uint32_t tc_fkey(float f) { const uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float tc_fkey_inv(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+__device__ __forceinline__ void tc_thresholds(const ActSpec a, bool elem_act, float t, float& lo, float& hi) {
+  if (!elem_act) { lo = hi = t; return; }
+  const uint32_t kmin = tc_fkey(-INFINITY), kmax = tc_fkey(INFINITY);
+  // first key whose activation exceeds t (kmax + 1 if none): hi is the key before it
+  uint32_t l = kmin, r = kmax + 1u;
+  while (l < r) { const uint32_t m = l + ((r - l) >> 1); if (act_fwd(a, tc_fkey_inv(m)) > t) r = m; else l = m + 1u; }
+  hi = l > kmin ? tc_fkey_inv(l - 1u) : -INFINITY;
+  const uint32_t first_gt = l;
+  // first key whose activation reaches t
+  l = kmin; r = first_gt;
+  while (l < r) { const uint32_t m = l + ((r - l) >> 1); if (act_fwd(a, tc_fkey_inv(m)) >= t) r = m; else l = m + 1u; }
+  lo = tc_fkey_inv(l);        // an empty tie band ends with lo = the first value above hi: x >= lo <=> x > hi
+}
+
 // cnt[b*2 + 0] += #items with score > target score of lane b; cnt[b*2 + 1] += #items with score == target (the target itself
 // counts as one tie, exactly as in the fp32 kernel where its score equals the target score bit for bit).
 // Tile = 128 evaluation lanes (UMMA M, TMEM lanes: one lane per epilogue thread, so the counting is thread-local) x 256 items
@@ -125,7 +155,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_eval_tc(int slot, int s, cons
   TcSmem& sm = *reinterpret_cast<TcSmem*>(tc_raw);
   const ModelDev& md = MD;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int M = md.wM[s], I = md.n_items, K = md.L;
+  const int M = md.wM[s], I = md.n_items, K = md.L + 1;        // + the bias column
   const int n_tiles = (I + TC_N - 1) / TC_N;         // item tiles
   const int n_lb = (M + TC_M - 1) / TC_M;            // lane blocks
   const int n_chunk = (K + TC_KC - 1) / TC_KC;
@@ -195,21 +225,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_eval_tc(int slot, int s, cons
     for (int lb = 0; lb < n_lb; lb++) {
       const int b = lb * TC_M + q4 * 32 + lane;
       const bool vrow = b < M;
-      const float tg = vrow ? tgt[b] : 0.f;
       const int yit = vrow ? md.wY[(size_t)s * md.B + b] : -1;
-      int cgt = 0, ceq = 0;
+      float lo = INFINITY, hi = INFINITY;
+      if (vrow) tc_thresholds(md.fact, elem_act, tgt[b], lo, hi);
+      int cgt = 0, cge = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, wi++) {
         const uint32_t acc = wi & 1u;
         const int i0 = t * TC_N;
-        {   // bias of the tile's items (double buffered with the accumulator)
-          const int e = tid;                     // 256 epilogue threads <-> 256 items
-          sm.sBy[acc][e] = (i0 + e < I) ? md.By[i0 + e] : 0.f;
-        }
         tc_mbar_wait(&sm.acc_full[acc], (wi >> 1) & 1u, &sm.err);
-        asm volatile("bar.sync 2, 256;" ::: "memory");       // sBy of this tile complete
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int self_col = yit - i0;                       // the target's own column (if it falls into this tile)
-        const int n_valid = min(TC_N, I - i0);
 #pragma unroll 1
         for (int q = 0; q < 4; q++) {
           const int c0 = half * 128 + q * 32;
@@ -224,18 +249,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_eval_tc(int slot, int s, cons
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int j = 0; j < 32; j++) {
-            const int n = c0 + j;
-            float sc = __uint_as_float(r[j]) + sm.sBy[acc][n];
-            if (elem_act) sc = act_fwd(md.fact, sc);
-            const bool self = n == self_col;
-            const bool live = !self && n < n_valid;
-            cgt += (live && sc > tg) ? 1 : 0;
-            ceq += (self || (live && sc == tg)) ? 1 : 0;
+            const float x = __uint_as_float(r[j]);
+            cgt += (x > hi) ? 1 : 0;
+            cge += (x >= lo) ? 1 : 0;
+          }
+          if ((unsigned)(self_col - c0) < 32u) {             // rare: take the target's own column back out, it counts as exactly one tie
+            float xs = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; j++) if (j == self_col - c0) xs = __uint_as_float(r[j]);
+            cgt -= (xs > hi) ? 1 : 0;
+            cge -= (xs >= lo) ? 1 : 0;
+            cge += 1;                                        // == (self: not above) + one tie
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         tc_mbar_arrive(&sm.acc_free[acc]);
       }
+      const int ceq = cge - cgt;                            // lo <= x <= hi
       if (vrow) { if (cgt) atomicAdd(&cnt[b * 2], cgt); if (ceq) atomicAdd(&cnt[b * 2 + 1], ceq); }
     }
   }

@@ -16,6 +16,7 @@ import argparse
 import json
 import os
 import sys
+import subprocess
 import threading
 import time
 
@@ -85,16 +86,30 @@ class ClockSampler(threading.Thread):
     def __init__(self, gpu_index=0):
         threading.Thread.__init__(self, daemon=True)
         self.rows, self.stop_flag, self.gpu_index, self.timed = [], False, gpu_index, False
+        self.err, self.source = None, 'NVML, 2 ms period, whole measurement'
 
     def run(self):
+        names = {'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20, 'sw_power_cap': 0x4}
         try:
             import pynvml as nv
             nv.nvmlInit()
             h = nv.nvmlDeviceGetHandleByIndex(self.gpu_index)
             mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-        except Exception:
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception as e:            # no usable NVML binding: poll nvidia-smi instead (slower period, same fields)
+            self.err = repr(e)
+            self.source = 'nvidia-smi, ~30 ms period, whole measurement'
+            q = ['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=clocks.sm,clocks.max.sm,clocks_throttle_reasons.active',
+                 '--format=csv,noheader,nounits']
+            while not self.stop_flag:
+                try:
+                    f = subprocess.run(q, capture_output=True, text=True, timeout=5).stdout.strip().split(',')
+                    rs = int(f[2].strip(), 16)
+                    self.rows.append((float(f[0]), float(f[1]), [k for k, v in names.items() if rs & v], self.timed))
+                except Exception as e2:
+                    self.err = repr(e2)
+                time.sleep(0.02)
             return
-        names = {'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20, 'sw_power_cap': 0x4}
         while not self.stop_flag:
             try:
                 sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
@@ -103,17 +118,27 @@ class ClockSampler(threading.Thread):
                 except Exception:
                     rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 self.rows.append((sm, mx, [k for k, v in names.items() if rs & v], self.timed))
-            except Exception:
-                pass
+            except Exception as e:
+                self.err = repr(e)
             time.sleep(0.002)
 
     def summary(self):
         if not self.rows:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0, 'error': self.err}
         sm = [r[0] for r in self.rows]
         reasons = sorted({x for r in self.rows for x in r[2]})
         return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(self.rows[0][1]), 'reasons': reasons, 'samples': len(sm),
-                'samples_timed': int(sum(1 for r in self.rows if r[3])), 'source': 'NVML, 2 ms period, whole measurement'}
+                'samples_timed': int(sum(1 for r in self.rows if r[3])), 'source': self.source}
+
+
+def peak_tensor():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['bf16_tflops_sustained']), 'measured sustained bf16 (MEASURED_PEAKS.json)'
+        except Exception:
+            pass
+    return 2250.0, 'nominal dense bf16 (B200_PROFILING.md)'
 
 
 def peak_hbm():
@@ -382,6 +407,7 @@ def main():
                       'algorithmic_bytes': lg_bytes,
                       'note': 'k_fast: statistics-ready -> rows-updated segment of a chunk CTA (globaltimer), sparse Adagrad/momentum update of the Wy/By rows'}
     clocks.stop_flag = True
+    clocks.join(2.0)
     per_phase = None
     if prof is not None:
         lg_ms, lg_n = prof['lossgrad_update']
@@ -399,6 +425,18 @@ def main():
         kernel = 'k_persistent (generic persistent kernel, one launch per window: the whole step)' if int(cfg.step_mode) >= 1 else 'per-phase kernels (CUDA graph)'
     step_s = dev_ms / 1000.0 / K                      # lock-step time (every rank moves step_bytes per lock step)
     achieved = step_bytes / step_s / 1e9
+    tensor = None
+    if world == 1 and eng.uses_tensor_cores():
+        # the step ran on the tcgen05 path (g4r_tcstep.cuh): the contractions bound it, not the row traffic.  fp32-equivalent
+        # FLOPs of the eight products: gates, candidate, scores, dSy, dL/dh, d(H*r), dL/d(input), dense gradients
+        L = mk['layers'][-1]
+        macs = 16.0 * B * L * L + 3.0 * B * N * L
+        tf_peak, tf_src = peak_tensor()
+        tensor = {'flops_per_step': 2.0 * macs, 'achieved': 2.0 * macs / step_s / 1e12, 'peak': tf_peak / 6.0, 'unit': 'TFLOP/s',
+                  'peak_source': tf_src + '; bf16 dense / 2 (TF32 rate) / 3 (3xTF32: three tensor-core products per fp32 product)'}
+        tensor['frac'] = tensor['achieved'] / tensor['peak']
+        kernel = ('k_ts_gemm (tcgen05 kind::tf32, 3xTF32, 128x256 tiles, K split over thread-block clusters; 8 products per mini-batch on 3 streams '
+                  '+ operand-preparation / loss / sparse-update kernels; one CUDA graph per 16 mini-batches)')
     traffic, traffic_src, traffic_kernel = ncu_traffic(args.workload) if world == 1 else (None, None, None)
     if world == 1:
         par = 'dp1'
@@ -421,12 +459,17 @@ def main():
         'e2e': {'value': e2e_value, 'unit': 'mb/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4},
         'gpu_launches': int(launches),
         'clocks': clocks.summary(),
-        'roofline': {'bound': 'hbm', 'kernel': kernel, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+        'roofline': {'bound': 'tensor' if tensor else 'hbm', 'kernel': kernel,
+                     'achieved': tensor['achieved'] if tensor else achieved, 'peak': tensor['peak'] if tensor else peak,
+                     'unit': 'TFLOP/s' if tensor else 'GB/s', 'frac': tensor['frac'] if tensor else achieved / peak,
+                     'tensor': tensor, 'hbm': {'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak},
                      'traffic': traffic, 'traffic_source': traffic_src, 'traffic_kernel': traffic_kernel,
                      'peak_source': peak_src, 'algorithmic_bytes_per_launch': step_bytes * K, 'algorithmic_bytes_per_step': step_bytes,
                      'us_per_step': step_s * 1e6,
-                     'note': 'latency-bound: ~15 dependent phases per mini-batch over an L2-resident working set (SURVEY fact 5); the HBM roofline is the contract\'s '
-                             'denominator, not the binding limit',
+                     'note': ('tensor-core path: a chain of 7 dependent split-K products per mini-batch (each ~4 us of tcgen05 issue + ~12 us of launch, '
+                              'operand fetch, L2 exchange and epilogue latency); the fraction is against the 3xTF32-equivalent tensor peak') if tensor else
+                             ('latency-bound: ~15 dependent phases per mini-batch over an L2-resident working set (SURVEY fact 5); the HBM roofline is the '
+                              'contract\'s denominator, not the binding limit'),
                      'k_fast_update_phase': fast_phase, 'per_phase_mode': per_phase},
         'wall_s_timed_region': wall,
     }

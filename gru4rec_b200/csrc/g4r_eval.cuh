@@ -30,7 +30,8 @@ __global__ void __launch_bounds__(128) k_eval_tgt(int slot, int s, float* tgt, i
   const float* yr = md.layer[md.n_layers - 1].y + (size_t)b * md.ldL;
   const float* wr = md.Wy + (size_t)item * md.ldL;
   float a = 0.f;
-  for (int c4 = 0; c4 < md.ldL / 4; c4++) {
+#pragma unroll 8
+  for (int c4 = 0; c4 < md.ldL / 4; c4++) {          // loads batched by the unroll, the fma chain keeps its order
     const float4 y = ld4(yr + c4 * 4), w = ld4(wr + c4 * 4);
     a = fmaf(y.x, w.x, a); a = fmaf(y.y, w.y, a); a = fmaf(y.z, w.z, a); a = fmaf(y.w, w.w, a);
   }
@@ -304,7 +305,7 @@ extern "C" int g4r_eval_schedule(g4r_handle* h, const g4r_schedule* s, const int
     CK(cudaMemcpyAsync(e->dG, e->hG, (size_t)w * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     for (int64_t i = 0; i < w; i++) {
       eval_forward(h, e, (int)i);
-      k_eval_tgt<<<(Be + 127) / 128, 128, 0, st>>>(e->slot, (int)i, h->dTgt, h->dRankCnt, tie, e->n_cand > 0 ? 1 : 0);
+      k_eval_tgt<<<(Be + 31) / 32, 32, 0, st>>>(e->slot, (int)i, h->dTgt, h->dRankCnt, tie, e->n_cand > 0 ? 1 : 0);
       const int n_comp = e->n_cand > 0 ? e->n_cand : I;
       const int M_i = e->hM[i];
       const bool tc = tc_possible && (h->cfg.eval_tc == 2 || M_i >= 64);

@@ -584,17 +584,19 @@ static int enqueue_tc_step(g4r_handle* h, const int* base, int off) {
   launch_ts_epi<TS_EPI_DENSE_A>(h, s2, PH_DENSE, base, off, g8a, tb, 3 * L, 2 * tb.Lp);
   TS_GEMM(TS_EPI_B2, st, PH_B2, mk(tb.A6, tb.W3, tb.P, tb.Lk1 / TC_KC, B, L));
   fork(8, st, s2);
+  cudaStreamWaitEvent(s1, ev[8], 0);       // side 1 (idle by now): the bias gradient + update, dvec is complete
+  LAUNCH_ON(s1, PH_DENSE, k_ts_bh<<<(3 * L + 31) / 32, 256, 0, s1>>>(slot, base, off));
   // side 2: the da_r columns
   LAUNCH_ON(s2, PH_DENSE, k_ts_prep_b8<<<fillg, 256, 0, s2>>>(slot, base, off, tb, 1));
   const TsGemm g8b = mk(tb.A8, tb.B8b, tb.Pb, tb.Bk / TC_KC, 3 * L, L);
   TS_GEMM(TS_EPI_DENSE_B, s2, PH_DENSE, g8b);
   launch_ts_epi<TS_EPI_DENSE_B>(h, s2, PH_DENSE, base, off, g8b, tb, 3 * L, L);
-  // main: dL/d(input rows), the bias gradient, then the input-row update (after the scored-row update: both touch the shared table)
+  // main: dL/d(input rows), then the input-row update (after the scored-row update: both touch the shared table)
   TS_GEMM(TS_EPI_B3, st, PH_B3, mk(tb.A7, tb.W4, tb.P, tb.Lk3 / TC_KC, B, L));
-  launch_pdl(h, PH_DENSE, (const void*)k_ts_bh, dim3((3 * L + 31) / 32), dim3(256), base, off, nullptr);
   cudaStreamWaitEvent(st, ev[6], 0);
   LAUNCH(PH_SPARSE_IN, k_sparse_in<<<B, 128, 0, st>>>(slot, base, off, 1));
   cudaEventRecord(ev[10], s2); cudaStreamWaitEvent(st, ev[10], 0);
+  cudaEventRecord(ev[11], s1); cudaStreamWaitEvent(st, ev[11], 0);
 #undef TS_GEMM
   return G4R_OK;
 }

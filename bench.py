@@ -287,15 +287,21 @@ def main():
     host = gru._init_host_weights()
     for name, w in host.items():
         eng.set(name, w)
-    items, offset, order, supports = build_workload(wl, 2 * (K + W), seed=rank)
+    need_steps = 2 * K + W + min(K, 512) + 64         # warm-up, timed region, e2e arm, the per-kernel profiling / stamp passes
+    grow = 1.0
+    while True:                                       # synthetic sessions until the schedule covers every arm
+        items, offset, order, supports = build_workload(wl, int(need_steps * grow), seed=rank)
+        sched = _lib.Schedule(items, offset, order, B, mk['n_sample'], mode=0)
+        if sched.n_steps >= need_steps or grow > 8:
+            break
+        grow *= 1.5
+    assert sched.n_steps >= need_steps, 'synthetic workload too small'
     P = supports.astype(np.float64) ** mk.get('sample_alpha', 0.75)
     P = P.cumsum() / P.sum(); P[-1] = 1
     eng.set_sampling_cdf(P.astype(np.float32))
     if mk.get('logq', 0):
         eng.set_logq_support(np.maximum(supports, 1).astype(np.float32))
     eng.generate_samples()
-    sched = _lib.Schedule(items, offset, order, B, mk['n_sample'], mode=0)
-    assert sched.n_steps >= 2 * (K + W), 'synthetic workload too small'
 
     def barrier():
         torch.cuda.synchronize()

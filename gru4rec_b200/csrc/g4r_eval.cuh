@@ -21,7 +21,7 @@ __device__ __forceinline__ float tie_noise(unsigned int seed, int s, int b, unsi
 }
 
 // target score of every lane, computed with the same sequential k order as the tile kernel (bitwise equal)
-__global__ void __launch_bounds__(128) k_eval_tgt(int slot, int s, float* tgt, int* cnt, unsigned int tie, int subset_mode) {
+__global__ void __launch_bounds__(128) k_eval_tgt(int slot, int s, float* tgt, int* cnt, unsigned int tie, int subset_mode, int lohi_stride) {
   const ModelDev& md = MD;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   const int M = md.wM[s];
@@ -36,7 +36,13 @@ __global__ void __launch_bounds__(128) k_eval_tgt(int slot, int s, float* tgt, i
     a = fmaf(y.x, w.x, a); a = fmaf(y.y, w.y, a); a = fmaf(y.z, w.z, a); a = fmaf(y.w, w.w, a);
   }
   float sc = a + md.By[item];
+  const float pre = sc;
   if (md.fact.kind <= G4R_ACT_SELU) sc = act_fwd(md.fact, sc);
+  if (lohi_stride > 0) {      // tcgen05 ranking: the two pre-activation thresholds of this lane (g4r_eval_tc.cuh)
+    float lo, hi;
+    tc_thresholds(md.fact, md.fact.kind <= G4R_ACT_SELU, sc, pre, lo, hi);
+    tgt[lohi_stride + b] = lo; tgt[2 * lohi_stride + b] = hi;
+  }
   if (tie) sc += tie_noise(tie, s, b, subset_mode ? 0x40000000U + (unsigned int)b : (unsigned int)item);
   tgt[b] = sc;
   cnt[b * 2 + 0] = 0; cnt[b * 2 + 1] = 0;
@@ -305,13 +311,13 @@ extern "C" int g4r_eval_schedule(g4r_handle* h, const g4r_schedule* s, const int
     CK(cudaMemcpyAsync(e->dG, e->hG, (size_t)w * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     for (int64_t i = 0; i < w; i++) {
       eval_forward(h, e, (int)i);
-      k_eval_tgt<<<(Be + 31) / 32, 32, 0, st>>>(e->slot, (int)i, h->dTgt, h->dRankCnt, tie, e->n_cand > 0 ? 1 : 0);
+      k_eval_tgt<<<(Be + 31) / 32, 32, 0, st>>>(e->slot, (int)i, h->dTgt, h->dRankCnt, tie, e->n_cand > 0 ? 1 : 0, tc_possible ? Be : 0);
       const int n_comp = e->n_cand > 0 ? e->n_cand : I;
       const int M_i = e->hM[i];
       const bool tc = tc_possible && (h->cfg.eval_tc == 2 || M_i >= 64);
       if (tc) {
         k_tc_split<TC_M><<<dim3((M_i + TC_M - 1) / TC_M, tc_chunks), 256, 0, st>>>(h->md.layer[h->md.n_layers - 1].y, M_i, h->md.ldL, h->md.L, e->dAsplit, tc_chunks, nullptr, 1.0f);
-        k_eval_tc<<<std::min(tc_tiles, h->n_sm), TC_THREADS, sizeof(TcSmem), st>>>(e->slot, (int)i, h->dTgt, h->dRankCnt, e->dAsplit, e->dBsplit);
+        k_eval_tc<<<std::min(tc_tiles, h->n_sm), TC_THREADS, sizeof(TcSmem), st>>>(e->slot, (int)i, h->dTgt, Be, h->dRankCnt, e->dAsplit, e->dBsplit);
         h->launches++;
       } else k_eval_score<false><<<(n_comp + EV_IT - 1) / EV_IT, EV_THREADS, eval_smem_bytes(), st>>>(e->slot, (int)i, h->dTgt, h->dRankCnt, nullptr, e->n_cand > 0 ? e->dCand : nullptr, e->n_cand, tie);
       k_eval_rank<<<1, 256, 0, st>>>(e->slot, (int)i, h->dRankCnt, e->dCut, n_cut, mode, e->dSums);

@@ -131,25 +131,37 @@ __device__ __forceinline__ void tc_bulk_copy(void* sdst, const void* gsrc, uint3
 // per-item work drops to two compares.
 __device__ __forceinline__ uint32_t tc_fkey(float f) { const uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
 __device__ __forceinline__ float tc_fkey_inv(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
-__device__ __forceinline__ void tc_thresholds(const ActSpec a, bool elem_act, float t, float& lo, float& hi) {
+// x_t = the target's own pre-activation (act(x_t) == t): both thresholds are normally within a few ulps of it, so the search
+// gallops away from key(x_t) (1, 2, 4, ... keys) and bisects the last bracket -- a handful of evaluations outside the flat
+// regions of the activation, at most ~64 inside them.
+__device__ __forceinline__ void tc_thresholds(const ActSpec a, bool elem_act, float t, float x_t, float& lo, float& hi) {
   if (!elem_act) { lo = hi = t; return; }
-  const uint32_t kmin = tc_fkey(-INFINITY), kmax = tc_fkey(INFINITY);
-  // first key whose activation exceeds t (kmax + 1 if none): hi is the key before it
-  uint32_t l = kmin, r = kmax + 1u;
+  const uint32_t kmin = tc_fkey(-INFINITY), kmax = tc_fkey(INFINITY), k0 = min(max(tc_fkey(x_t), kmin), kmax);
+  // upper: first key above k0 whose activation exceeds t (kmax + 1 if none); invariant act(l - 1) <= t
+  uint32_t l = k0 + 1u, r = kmax + 1u;
+  for (uint32_t d = 1u; l < r; d <<= 1) {
+    const uint32_t m = (kmax - l < d) ? kmax : l + d - 1u;          // probe
+    if (act_fwd(a, tc_fkey_inv(m)) > t) { r = m; break; }
+    l = m + 1u;
+    if (d >= 0x80000000u) break;
+  }
   while (l < r) { const uint32_t m = l + ((r - l) >> 1); if (act_fwd(a, tc_fkey_inv(m)) > t) r = m; else l = m + 1u; }
-  hi = l > kmin ? tc_fkey_inv(l - 1u) : -INFINITY;
-  const uint32_t first_gt = l;
-  // first key whose activation reaches t
-  l = kmin; r = first_gt;
-  while (l < r) { const uint32_t m = l + ((r - l) >> 1); if (act_fwd(a, tc_fkey_inv(m)) >= t) r = m; else l = m + 1u; }
-  lo = tc_fkey_inv(l);        // an empty tie band ends with lo = the first value above hi: x >= lo <=> x > hi
+  hi = tc_fkey_inv(l - 1u);
+  // lower: smallest key whose activation still reaches t; invariant act(r2) >= t
+  uint32_t r2 = k0, l2 = kmin;
+  for (uint32_t d = 1u; l2 < r2; d <<= 1) {
+    const uint32_t m = (r2 - kmin < d) ? kmin : r2 - d;
+    if (act_fwd(a, tc_fkey_inv(m)) >= t) { r2 = m; if (d >= 0x80000000u) break; } else { l2 = m + 1u; break; }
+  }
+  while (l2 < r2) { const uint32_t m = l2 + ((r2 - l2) >> 1); if (act_fwd(a, tc_fkey_inv(m)) >= t) r2 = m; else l2 = m + 1u; }
+  lo = tc_fkey_inv(r2);
 }
 
 // cnt[b*2 + 0] += #items with score > target score of lane b; cnt[b*2 + 1] += #items with score == target (the target itself
 // counts as one tie, exactly as in the fp32 kernel where its score equals the target score bit for bit).
 // Tile = 128 evaluation lanes (UMMA M, TMEM lanes: one lane per epilogue thread, so the counting is thread-local) x 256 items
 // (UMMA N, TMEM columns).  Asplit: hidden-state blocks of 128 lanes, Bsplit: item-table blocks of 256 items (k_tc_split).
-__global__ void __launch_bounds__(TC_THREADS, 1) k_eval_tc(int slot, int s, const float* __restrict__ tgt, int* cnt,
+__global__ void __launch_bounds__(TC_THREADS, 1) k_eval_tc(int slot, int s, const float* __restrict__ tgt, int tgt_stride, int* cnt,
                                                            const unsigned char* __restrict__ Asplit, const unsigned char* __restrict__ Bsplit) {
   extern __shared__ __align__(1024) unsigned char tc_raw[];
   TcSmem& sm = *reinterpret_cast<TcSmem*>(tc_raw);
@@ -226,8 +238,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_eval_tc(int slot, int s, cons
       const int b = lb * TC_M + q4 * 32 + lane;
       const bool vrow = b < M;
       const int yit = vrow ? md.wY[(size_t)s * md.B + b] : -1;
-      float lo = INFINITY, hi = INFINITY;
-      if (vrow) tc_thresholds(md.fact, elem_act, tgt[b], lo, hi);
+      const float lo = vrow ? tgt[tgt_stride + b] : INFINITY, hi = vrow ? tgt[2 * tgt_stride + b] : INFINITY;   // k_eval_tgt
       int cgt = 0, cge = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, wi++) {
         const uint32_t acc = wi & 1u;

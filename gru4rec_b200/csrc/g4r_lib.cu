@@ -312,7 +312,7 @@ static void layout(const g4r_config& c, Carver& cv, g4r_handle* h, int n_sm) {
     tsb.O = cv.take<float>((size_t)tsb.Mpad * tsb.ldO); tsb.bias = cv.take<float>(tsb.Nk);
   }
   // evaluation
-  int* dRank = cv.take<int>((size_t)Be * 4); float* dTgt = cv.take<float>(Be);
+  int* dRank = cv.take<int>((size_t)Be * 4); float* dTgt = cv.take<float>((size_t)Be * 3);   // target scores | lower | upper pre-activation thresholds (tcgen05 ranking)
   if (!cv.dry) {
     md.wX = dX; md.wY = dY; md.wSlot = dSlot; md.wM = dM; md.wSti = dSti; md.wXnext = dXnext; md.wF = dF; md.wXflag = dXflag; md.wG = dG;
     md.ST = dST; md.logP0t = dL0t; md.logP0s = dL0s;

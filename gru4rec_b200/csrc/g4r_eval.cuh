@@ -309,20 +309,32 @@ extern "C" int g4r_eval_schedule(g4r_handle* h, const g4r_schedule* s, const int
     CK(cudaMemcpyAsync(e->dM, e->hM, (size_t)w * sizeof(int), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(e->dSti, e->hSti, (size_t)w * sizeof(int), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(e->dG, e->hG, (size_t)w * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    // two streams: the GRU forward of mini-batch i+1 (st) overlaps the ranking of mini-batch i (rk).  The ranking reads the
+    // hidden output only in its first kernels (target scores, operand split -- or the fp32 tile kernel itself), after which the
+    // forward stream may overwrite it; everything the ranking kernels share (target scores, counters, operand blocks, metric
+    // sums) is ordered by the ranking stream itself, so the sums accumulate in mini-batch order as before.
+    cudaStream_t rk = h->side;
     for (int64_t i = 0; i < w; i++) {
       eval_forward(h, e, (int)i);
-      k_eval_tgt<<<(Be + 31) / 32, 32, 0, st>>>(e->slot, (int)i, h->dTgt, h->dRankCnt, tie, e->n_cand > 0 ? 1 : 0, tc_possible ? Be : 0);
+      CK(cudaEventRecord(h->ts_ev[0], st)); CK(cudaStreamWaitEvent(rk, h->ts_ev[0], 0));
+      k_eval_tgt<<<(Be + 31) / 32, 32, 0, rk>>>(e->slot, (int)i, h->dTgt, h->dRankCnt, tie, e->n_cand > 0 ? 1 : 0, tc_possible ? Be : 0);
       const int n_comp = e->n_cand > 0 ? e->n_cand : I;
       const int M_i = e->hM[i];
       const bool tc = tc_possible && (h->cfg.eval_tc == 2 || M_i >= 64);
       if (tc) {
-        k_tc_split<TC_M><<<dim3((M_i + TC_M - 1) / TC_M, tc_chunks), 256, 0, st>>>(h->md.layer[h->md.n_layers - 1].y, M_i, h->md.ldL, h->md.L, e->dAsplit, tc_chunks, nullptr, 1.0f);
-        k_eval_tc<<<std::min(tc_tiles, h->n_sm), TC_THREADS, sizeof(TcSmem), st>>>(e->slot, (int)i, h->dTgt, Be, h->dRankCnt, e->dAsplit, e->dBsplit);
+        k_tc_split<TC_M><<<dim3((M_i + TC_M - 1) / TC_M, tc_chunks), 256, 0, rk>>>(h->md.layer[h->md.n_layers - 1].y, M_i, h->md.ldL, h->md.L, e->dAsplit, tc_chunks, nullptr, 1.0f);
+        CK(cudaEventRecord(h->ts_ev[1], rk));
+        k_eval_tc<<<std::min(tc_tiles, h->n_sm), TC_THREADS, sizeof(TcSmem), rk>>>(e->slot, (int)i, h->dTgt, Be, h->dRankCnt, e->dAsplit, e->dBsplit);
         h->launches++;
-      } else k_eval_score<false><<<(n_comp + EV_IT - 1) / EV_IT, EV_THREADS, eval_smem_bytes(), st>>>(e->slot, (int)i, h->dTgt, h->dRankCnt, nullptr, e->n_cand > 0 ? e->dCand : nullptr, e->n_cand, tie);
-      k_eval_rank<<<1, 256, 0, st>>>(e->slot, (int)i, h->dRankCnt, e->dCut, n_cut, mode, e->dSums);
+      } else {
+        k_eval_score<false><<<(n_comp + EV_IT - 1) / EV_IT, EV_THREADS, eval_smem_bytes(), rk>>>(e->slot, (int)i, h->dTgt, h->dRankCnt, nullptr, e->n_cand > 0 ? e->dCand : nullptr, e->n_cand, tie);
+        CK(cudaEventRecord(h->ts_ev[1], rk));
+      }
+      CK(cudaStreamWaitEvent(st, h->ts_ev[1], 0));        // the hidden output of this mini-batch has been consumed
+      k_eval_rank<<<1, 256, 0, rk>>>(e->slot, (int)i, h->dRankCnt, e->dCut, n_cut, mode, e->dSums);
       h->launches += 3;
     }
+    CK(cudaEventRecord(h->ts_ev[2], rk)); CK(cudaStreamWaitEvent(st, h->ts_ev[2], 0));   // window complete before its staging is reused
     CK(cudaGetLastError());
     done += w;
   }

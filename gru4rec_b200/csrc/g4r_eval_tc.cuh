@@ -11,15 +11,17 @@
 // relative on the scores, far inside the 1e-4 bar on Recall / MRR.  The target's own column is excluded explicitly (it is
 // the one comparison that must be exact), so a rank can only move where two DIFFERENT items' scores differ by < 1e-6 relative.
 //
-// Structure (one CTA per SM, 256 threads, persistent over its item tiles):
-//   pre-pass   k_tc_split writes the operands as hi / lo TF32 blocks in the canonical K-major no-swizzle UMMA layout (8 x 16-byte
-//              core matrices): the item table once per evaluation, the hidden states once per mini-batch
+// Structure (one CTA per SM, 320 threads, persistent over its item tiles):
+//   pre-pass   k_tc_split writes the operands as hi / lo TF32 blocks in the K-major 128-byte-swizzle UMMA layout: the item table
+//              once per evaluation, the hidden states once per mini-batch; one extra K column carries the item bias (1.0 on the
+//              hidden-state side), so the accumulator is the complete pre-activation score
 //   warp 8     TMA producer (one thread): two bulk copies (cp.async.bulk -> mbarrier complete_tx) per 32-wide K chunk fill a
 //              96 KB stage [A hi | A lo | B hi | B lo]; two stages
 //   warp 9     MMA issuer (one thread): 12 tcgen05.mma per chunk, tcgen05.commit hands the stage back / publishes the accumulator
-//   warps 0-7  epilogue: wait for the accumulator (2 x 256 TMEM columns, double buffered), tcgen05.ld 32 columns at a time,
-//              bias + final activation + compare with the lane's target score -- a thread owns one evaluation lane (TMEM
-//              lane), so the two counters are thread-local; two warps per lane quarter split the tile's columns
+//   warps 0-7  epilogue: wait for the accumulator (2 x 256 TMEM columns, double buffered), tcgen05.ld 32 columns at a time, two
+//              compares per item against the lane's pre-activation thresholds (k_eval_tgt computes them once per lane) -- a
+//              thread owns one evaluation lane (TMEM lane), so the two counters are thread-local; two warps per lane quarter
+//              split the tile's columns
 // All waits are mbarrier try_wait loops with a time-out that sets an error flag (a wrong phase must not hang the box).
 #pragma once
 
@@ -40,10 +42,9 @@ struct TcSmem {
   alignas(8) unsigned long long stage_full[TC_STAGES];    // operand blocks of the stage have landed (TMA complete_tx)
   unsigned long long stage_free[TC_STAGES];    // MMAs that read the stage have completed (tcgen05.commit)
   unsigned long long acc_full[2];              // all MMAs of the tile have completed (tcgen05.commit)
-  unsigned long long acc_free[2];              // epilogue has drained the accumulator (128 arrivals)
+  unsigned long long acc_free[2];              // epilogue has drained the accumulator (256 arrivals)
   uint32_t tmem_base;
   int err;
-  float sBy[2][TC_N];                          // output bias of the tile's items (per accumulator)
 };
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

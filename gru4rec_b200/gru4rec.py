@@ -432,15 +432,38 @@ class GRU4Rec:
             except _lib.NaNError:
                 print(str(epoch) + ': NaN error!')
                 self.error_during_train = True
+                if world > 1:      # the peers find out at their next exchange (time-out -> RuntimeError); nothing collective here
+                    self._engine.close(); self._engine = None; self._host = None
                 return
-            avgc = np.sum(c * cc) / np.sum(cc)
+            sum_c, sum_e, n_mb = np.sum(c * cc), np.sum(cc), len(c)
+            if world > 1:
+                # one epoch line for the whole job: event-weighted loss, mini-batches and events of all ranks
+                from .parallel import allreduce_sum
+                sum_c, sum_e, n_mb = allreduce_sum([sum_c, sum_e, n_mb], dist)
+            avgc = sum_c / sum_e
             if np.isnan(avgc):
                 print('Epoch {}: NaN error!'.format(str(epoch)))
                 self.error_during_train = True
-                return
+                break
             t1 = time.time()
             dt = t1 - t0
-            print('Epoch{} --> loss: {:.6f} \t({:.2f}s) \t[{:.2f} mb/s | {:.0f} e/s]'.format(epoch + 1, avgc, dt, len(c) / dt, np.sum(cc) / dt))
+            print('Epoch{} --> loss: {:.6f} \t({:.2f}s) \t[{:.2f} mb/s | {:.0f} e/s]'.format(epoch + 1, avgc, dt, n_mb / dt, sum_e / dt))
+        if world > 1:
+            self._release_multi_gpu_engine()
+
+    def _release_multi_gpu_engine(self):
+        """End of a multi-GPU fit(): every rank assembles the full parameter set on the host (the item tables are row-sharded
+        over the ranks' library-owned segments), then all ranks release their training engines together -- no rank frees its
+        segment while a peer still reads it.  Scoring / saving afterwards needs no collective (evaluate_gpu, predict_next_batch
+        rebuild a single-GPU engine from the host copy; savemodel pickles it)."""
+        eng = self._engine
+        if eng is None:
+            return
+        host = self._pull_host()
+        eng._quiesce()
+        eng.close()
+        self._engine = None
+        self._host = host
 
     def _train_epoch_cpu_store(self, eng, sched, pop, generate_length):
         """store_type='cpu' (legacy, gru4rec.py:605-614): samples are drawn by NumPy on the host, one store at a time."""

@@ -101,7 +101,7 @@ def _train(model_class, args):
     started = time.time()
     gru.fit(frame, sample_store=args.sample_store_size, store_type=store_type)
     print('Total training time: {:.2f}s'.format(time.time() - started))
-    if args.save_model is not None:
+    if args.save_model is not None and getattr(args, 'rank', 0) == 0:
         print('Saving trained model to: {}'.format(args.save_model))
         gru.savemodel(args.save_model)
     return gru
@@ -123,11 +123,26 @@ def _evaluate(gru, evaluation, args):
             print('PRIMARY METRIC: {}'.format(result[primary][0]))
 
 
+def _join_distributed_job():
+    """`torchrun --nproc-per-node N run.py ...` (one process per GPU; the reference is single-device): join the job the launcher
+    described, so that fit() trains data-parallel and evaluate_gpu() scores a shard of the test sessions per rank.  Every rank
+    runs the same command on the same files; only rank 0 prints and saves.  Returns (world_size, rank)."""
+    if int(os.environ.get('WORLD_SIZE', '1') or 1) <= 1:
+        return 1, 0
+    from gru4rec_b200.parallel import init_from_env
+    world, rank = init_from_env()
+    if rank != 0:
+        sys.stdout = open(os.devnull, 'w')
+    return world, rank
+
+
 def main(argv=None):
     args = build_parser().parse_args(argv)
     here = os.path.dirname(os.path.abspath(__file__))
     if here not in sys.path:
         sys.path.insert(0, here)
+    world, rank = _join_distributed_job()
+    args.rank = rank
     model_class = importlib.import_module(args.gru4rec_model).GRU4Rec
     import evaluation
     chosen = [args.parameter_string is not None, args.parameter_file is not None, bool(args.load_model)]
@@ -140,6 +155,11 @@ def main(argv=None):
         gru = _train(model_class, args)
     if args.test is not None:
         _evaluate(gru, evaluation, args)
+    if world > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.barrier()
+            dist.destroy_process_group()
 
 
 if __name__ == '__main__':

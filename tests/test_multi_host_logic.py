@@ -100,3 +100,107 @@ def test_world_size_2_gloo():
         p.join(120)
     res = sorted(q.get(timeout=5) for _ in range(2))
     assert res == [(0, 'ok'), (1, 'ok')]
+
+
+class _OracleScoringEngine(object):
+    """Stand-in for the device engine in the CPU test below: scores the C++-built (sharded) evaluation schedule with the
+    oracle, returning what g4r_eval_schedule returns (per-cut-off hit / reciprocal-rank sums in double, event count)."""
+
+    def __init__(self, model):
+        self.m, self.items = model, None
+
+    def set_eval_items(self, items=None):
+        self.items = None if items is None else np.asarray(items, dtype=np.int64)
+
+    def eval_schedule(self, sched, cuts, mode):
+        m = self.m
+        e = sched.export()
+        B = sched.batch_size
+        H = [np.zeros((B, L), dtype=np.float32) for L in m.layers]
+        rec = np.zeros(len(cuts)); mrr = np.zeros(len(cuts)); n = 0
+        name = {0: 'standard', 1: 'conservative', 2: 'median', 3: 'tiebreaking'}[mode]
+        for k in range(sched.n_steps):
+            M = int(e['M'][k])
+            X, Y = e['X'][k, :M].astype(np.int64), e['Y'][k, :M].astype(np.int64)
+            ycols = None if self.items is None else np.concatenate([Y, self.items])
+            yhat = m.predict_step(X, H, slots=e['slots'][k, :M].astype(np.int64), zero=(e['F'][k, :M] & 2) != 0, Y=ycols)
+            rk = m.ranks(yhat, Y, name, self.items)
+            with np.errstate(divide='ignore', invalid='ignore'):
+                for j, c in enumerate(cuts):
+                    rec[j] += (rk <= c).sum(); mrr[j] += ((rk <= c) / rk).sum()
+            n += M
+        return rec, mrr, n
+
+
+def _eval_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle')); sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
+    os.environ['RANK'] = str(rank); os.environ['WORLD_SIZE'] = str(world); os.environ['LOCAL_RANK'] = str(rank)
+    import contextlib
+    import io
+    import pandas as pd
+    import gru4rec_oracle as orc
+    from gru4rec_b200 import evaluation, parallel
+    from gru4rec_b200.gru4rec import GRU4Rec
+    from gru4rec_b200.synth import make_sessions, train_test_split
+    assert parallel.init_from_env(backend='gloo') == (world, rank)          # what run.py does under torchrun
+    assert parallel.init_from_env(backend='gloo') == (world, rank)          # idempotent
+    df = make_sessions(n_items=80, n_events=1500, seed=3)
+    tr, te = train_test_split(df, 0.3)
+    d = orc.prepare_fit_data(tr)
+    mk = dict(layers=[10, 12], batch_size=4, n_sample=8, loss='cross-entropy', final_act='softmax', embedding=9)
+    m = orc.OracleGRU4Rec(**mk); m.init(d['n_items'])
+    gru = GRU4Rec(**mk)
+    gru.n_items, gru.itemidmap, gru.error_during_train = d['n_items'], d['itemidmap'], False
+    fake = _OracleScoringEngine(m)
+    gru._ensure_engine = lambda lanes: fake
+    ti, toff = orc.prepare_eval_data(te, d['itemidmap'])
+    n_sess = len(toff) - 1
+    # shards: disjoint, complete, balanced
+    shards = [None] * world
+    dist.all_gather_object(shards, parallel.shard_eval_sessions(n_sess, rank, world).tolist())
+    assert sorted(x for s in shards for x in s) == list(range(n_sess)) and max(map(len, shards)) - min(map(len, shards)) <= 1
+    cand = d['itemidmap'].index.values[::3]
+    assert n_sess >= 100 > len(shards[rank])
+    for mode in ('standard', 'conservative', 'median'):
+        for items in (None, cand):
+            for bs in (7, 100):                   # 100 lanes > the sessions of one shard: the shard runs on fewer lanes
+                with contextlib.redirect_stdout(io.StringIO()):
+                    rec, mrr = evaluation.evaluate_gpu(gru, te.copy(), items=items, cut_off=[1, 5, 20], batch_size=bs, mode=mode)
+                idx = None if items is None else d['itemidmap'][items].values
+                rec0, mrr0 = m.evaluate(ti, toff, batch_size=bs, cut_off=(1, 5, 20), mode=mode, items=idx)     # the whole test set on one "device"
+                np.testing.assert_allclose(rec, rec0, rtol=1e-12, atol=0)
+                np.testing.assert_allclose(mrr, mrr0, rtol=1e-12, atol=0)
+                both = [None] * world
+                dist.all_gather_object(both, (rec, mrr))
+                assert both[0] == both[1]                                     # every rank returns the job's result
+    # fewer sessions than lanes: the reference's IndexError on every rank, before anything is scored
+    with contextlib.redirect_stdout(io.StringIO()):
+        with pytest.raises(IndexError):
+            evaluation.evaluate_gpu(gru, te.copy(), cut_off=[20], batch_size=n_sess + 1)
+    # sharding switched off: every rank scores everything
+    os.environ['G4R_EVAL_SHARD'] = '0'
+    with contextlib.redirect_stdout(io.StringIO()):
+        rec, mrr = evaluation.evaluate_gpu(gru, te.copy(), cut_off=[20], batch_size=7)
+    rec0, mrr0 = m.evaluate(ti, toff, batch_size=7, cut_off=(20,))
+    np.testing.assert_allclose(rec, rec0, rtol=1e-12); np.testing.assert_allclose(mrr, mrr0, rtol=1e-12)
+    # the job-wide epoch line of fit(): sums over ranks
+    tot = parallel.allreduce_sum([1.5 + rank, 10.0, 3], dist)
+    np.testing.assert_allclose(tot, [1.5 * world + sum(range(world)), 10.0 * world, 3 * world])
+    q.put((rank, 'ok'))
+    dist.destroy_process_group()
+
+
+def test_sharded_evaluation_world_size_2_gloo():
+    """evaluate_gpu under a 2-process job: every rank scores every second test session, the summed result equals the
+    oracle's evaluation of the whole test set (all tie modes, with and without a candidate list)."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29810 + os.getpid() % 150
+    procs = [ctx.Process(target=_eval_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+    res = sorted(q.get(timeout=5) for _ in range(2))
+    assert res == [(0, 'ok'), (1, 'ok')]

@@ -408,7 +408,7 @@ class GRU4Rec:
         data_items = data.ItemIdx.values
         # under torchrun: synchronous data parallelism, every rank trains a shard of the sessions
         sched = None
-        n_sample_eff = self.n_sample if use_store else (self.n_sample if store_type == 'cpu' else self.n_sample)
+        n_sample_eff = self.n_sample
         for epoch in range(self.n_epochs):
             t0 = time.time()
             eng.reset_hidden()

@@ -217,6 +217,12 @@ class Schedule(object):
         self._lib.g4r_schedule_export(self.h, _ptr(X), _ptr(Y), _ptr(F), _ptr(M), _ptr(S))
         return dict(X=X, Y=Y, F=F, M=M, slots=S)
 
+    def batch_sizes(self):
+        """M of every mini-batch (the weights of the epoch loss, gru4rec.py:654) without copying the index arrays."""
+        M = np.empty(self.n_steps, np.int32)
+        self._lib.g4r_schedule_export(self.h, None, None, None, _ptr(M), None)
+        return M
+
     def __del__(self):
         try:
             if self.h:

@@ -421,7 +421,7 @@ class GRU4Rec:
                     session_idx_arr = shard_sessions(session_idx_arr, rank, world)
                 sched = _lib.Schedule(data_items, offset_sessions, session_idx_arr, self.batch_size, n_sample_eff, mode=0)
                 n_steps = sched.n_steps if world == 1 else common_steps(sched.n_steps, dist)
-                cc = sched.export()['M'][:n_steps].astype(np.float64)
+                cc = sched.batch_sizes()[:n_steps].astype(np.float64)
             try:
                 if per_step_sampling:
                     c = self._train_epoch_per_step_samples(eng, sched, pop)

@@ -31,6 +31,7 @@ def test_train_schedule_equals_oracle(B, n_sample, seed):
     e = s.export()
     assert s.n_steps == len(steps)
     assert s.n_events == sum(st['M'] for st in steps)
+    np.testing.assert_array_equal(s.batch_sizes(), e['M'])      # the M-only export fit() uses for the epoch loss weights
     for k, st in enumerate(steps):
         M = st['M']
         assert e['M'][k] == M
@@ -281,3 +282,20 @@ def test_schedules_equal_oracle_on_random_session_structures(seed):
             np.testing.assert_array_equal(e['Y'][k, :M], st['Y'])
             np.testing.assert_array_equal((e['F'][k, :M] >> 1) & 1, st['Z'].astype(np.uint8))
             np.testing.assert_array_equal(e['slots'][k, :M], st['slots'])
+
+
+def test_run_py_outside_a_launcher_is_a_single_process(monkeypatch):
+    """run.py joins a torch.distributed job only when a launcher describes one (WORLD_SIZE > 1)."""
+    import importlib
+    for k in ('WORLD_SIZE', 'RANK', 'LOCAL_RANK'):
+        monkeypatch.delenv(k, raising=False)
+    run = importlib.import_module('run')
+    assert run._join_distributed_job() == (1, 0)
+    monkeypatch.setenv('WORLD_SIZE', '1')
+    assert run._join_distributed_job() == (1, 0)
+    from gru4rec_b200 import parallel
+    assert parallel.env_world() == (1, 0, 0) and parallel.init_from_env() == (1, 0)
+    monkeypatch.setenv('WORLD_SIZE', '4'); monkeypatch.setenv('RANK', '2'); monkeypatch.setenv('LOCAL_RANK', '2')
+    assert parallel.env_world() == (4, 2, 2)
+    np.testing.assert_array_equal(parallel.shard_eval_sessions(10, 2, 4), [2, 6])
+    assert len(parallel.shard_eval_sessions(2, 3, 4)) == 0               # a rank without sessions contributes zeros

@@ -5,6 +5,14 @@ reference's own plugin seam (run.py:21,39).  Constructor arguments, set_params()
 fit() / predict_next_batch() / savemodel() / loadmodel() signatures and printed lines follow the reference;
 the per-mini-batch work runs in libg4r.so (hand-written sm_100a CUDA) through ctypes.  PyTorch is used
 only to allocate the device workspace.  There is no CPU fallback.
+
+Interface restatement, stated plainly: `__init__` (argument list, defaults, attribute assignments), `set_params` (the
+coercion table and its `SET ... TO ...` / error prints), `init_matrix`, `generate_neg_samples` and the popularity / CDF
+preamble of `fit` are the reference's statements almost line for line (gru4rec.py:97-135, 162-187, 254-260, 507-514,
+534-556).  That is deliberate and required by the drop-in boundary: keyword names, defaults, coercions, printed lines,
+exception types and the NumPy random-stream consumption order are the interface, and
+tests/golden/set_params_cases.json + the golden fixtures pin them against the reference class.  Everything below that
+surface (schedule, step, optimizers, evaluation, persistence plumbing, multi-GPU) is this repository's own design.
 """
 import pickle
 import time

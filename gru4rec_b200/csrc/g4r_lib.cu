@@ -1032,32 +1032,45 @@ extern "C" int g4r_schedule_build(const int64_t* data_items, int64_t n_events, c
   auto sess_of = [&](int64_t it) -> int64_t { return order ? order[it] : it; };
   std::vector<int64_t> iters(B), start(B), end(B);
   std::vector<int32_t> slots(B);
-  std::vector<uint8_t> zero_next(B, 0);
+  std::vector<uint8_t> zero_next(B, 0), fin(B), valid(B);
   for (int b = 0; b < B; b++) { iters[b] = b; start[b] = offs[sess_of(b)]; end[b] = offs[sess_of(b) + 1]; slots[b] = b; }
+  {
+    // capacity up front: a full lane set consumes B events per step (the tail of the epoch, where sessions run out, adds a
+    // little).  At RSC15 size the arrays are ~270 MB; growing them by doubling would touch that memory twice.
+    int64_t ev = 0;
+    if (order) { for (int64_t i = 0; i < n_sessions; i++) ev += offs[order[i] + 1] - offs[order[i]]; } else ev = (int64_t)offs[n_sessions] - offs[0];
+    const size_t guess = (size_t)(std::max<int64_t>(ev, 0) / B + 64) * 5 / 4;
+    s->X.reserve(guess * B); s->Y.reserve(guess * B); s->slots.reserve(guess * B); s->F.reserve(guess * B); s->M.reserve(guess);
+  }
   int64_t maxiter = B - 1;
   int M = B;
   while (true) {
     int64_t minlen = end[0] - start[0];
     for (int b = 1; b < M; b++) minlen = std::min(minlen, end[b] - start[b]);
-    for (int64_t i = 0; i + 1 < minlen; i++) {
-      const size_t base = s->X.size();
-      s->X.resize(base + B, -1); s->Y.resize(base + B, -1); s->slots.resize(base + B, 0); s->F.resize(base + B, 0);
-      for (int b = 0; b < M; b++) {
-        const int64_t p = start[b] + i;
-        if (p + 1 >= n_events) { delete s; g_create_error = "schedule: event index out of range"; return G4R_ERR_INDEX; }
-        s->X[base + b] = (int32_t)data_items[p];
-        s->Y[base + b] = (int32_t)data_items[p + 1];
-        s->slots[base + b] = slots[b];
-        uint8_t f = 0;
-        if (mode == 0) { if (p + 1 == end[b] - 1) f |= 1; }
-        else if (zero_next[b]) { f |= 2; }
-        s->F[base + b] = f;
+    const int64_t nst = minlen - 1;        // mini-batches all M lanes can take before the shortest running session ends
+    if (nst > 0) {
+      for (int b = 0; b < M; b++)
+        if (start[b] + nst >= n_events) { delete s; g_create_error = "schedule: event index out of range"; return G4R_ERR_INDEX; }
+      const size_t base = s->X.size(), add = (size_t)nst * B;
+      s->X.resize(base + add); s->Y.resize(base + add); s->slots.resize(base + add); s->F.resize(base + add);      // zero-filled
+      int32_t* X = s->X.data() + base; int32_t* Y = s->Y.data() + base; int32_t* SL = s->slots.data() + base; uint8_t* F = s->F.data() + base;
+      for (int64_t i = 0; i < nst; i++) {
+        int32_t* x = X + i * B; int32_t* y = Y + i * B; int32_t* sl = SL + i * B;
+        for (int b = 0; b < M; b++) {
+          const int64_t p = start[b] + i;
+          x[b] = (int32_t)data_items[p]; y[b] = (int32_t)data_items[p + 1]; sl[b] = slots[b];
+        }
+        for (int b = M; b < B; b++) { x[b] = -1; y[b] = -1; }
       }
-      if (mode == 1) std::fill(zero_next.begin(), zero_next.begin() + M, 0);
-      s->M.push_back(M);
-      s->n_events += M;
+      if (mode == 0) {       // bit 0: the step that consumes a session's last event -- the lane's state is reset after it (gru4rec.py:647-651)
+        uint8_t* f = F + (nst - 1) * B;
+        for (int b = 0; b < M; b++) if (end[b] - start[b] == minlen) f[b] = 1;
+      } else {               // bit 1: the lane starts a new session with this step -- its state is zeroed before it (evaluation.py:136-139)
+        for (int b = 0; b < M; b++) if (zero_next[b]) { F[b] = 2; zero_next[b] = 0; }
+      }
+      s->M.insert(s->M.end(), (size_t)nst, M);
+      s->n_events += nst * M;
     }
-    std::vector<uint8_t> fin(M), valid(M);
     int n_finished = 0;
     for (int b = 0; b < M; b++) { start[b] += minlen - 1; fin[b] = (end[b] - start[b] <= 1); }
     for (int b = 0; b < M; b++) if (fin[b]) { n_finished++; iters[b] = maxiter + n_finished; }
@@ -1070,11 +1083,13 @@ extern "C" int g4r_schedule_build(const int64_t* data_items, int64_t n_events, c
       start[b] = offs[ss]; end[b] = offs[ss + 1];
       if (mode == 1) zero_next[b] = 1;
     }
-    int w = 0;
-    for (int b = 0; b < M; b++) if (valid[b]) {
-      iters[w] = iters[b]; start[w] = start[b]; end[w] = end[b]; slots[w] = slots[b]; zero_next[w] = zero_next[b]; w++;
+    if (n_valid < M) {
+      int w = 0;
+      for (int b = 0; b < M; b++) if (valid[b]) {
+        iters[w] = iters[b]; start[w] = start[b]; end[w] = end[b]; slots[w] = slots[b]; zero_next[w] = zero_next[b]; w++;
+      }
+      M = w;
     }
-    M = w;
   }
   s->n_steps = (int64_t)s->M.size();
   *out = s;

@@ -299,3 +299,23 @@ def test_run_py_outside_a_launcher_is_a_single_process(monkeypatch):
     assert parallel.env_world() == (4, 2, 2)
     np.testing.assert_array_equal(parallel.shard_eval_sessions(10, 2, 4), [2, 6])
     assert len(parallel.shard_eval_sessions(2, 3, 4)) == 0               # a rank without sessions contributes zeros
+
+
+def test_c_caller_links_against_the_abi(tmp_path):
+    """include/g4r.h is plain C99 and a C program can drive the host-side entry points of libg4r.so."""
+    import shutil
+    import subprocess
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('no gcc')
+    inc, libdir = os.path.join(ROOT, 'include'), os.path.join(ROOT, 'gru4rec_b200')
+    r = subprocess.run([gcc, '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror', '-fsyntax-only', '-x', 'c', os.path.join(inc, 'g4r.h')], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    exe = str(tmp_path / 'c_abi_caller')
+    cuda_lib = '/usr/local/cuda/lib64'
+    r = subprocess.run([gcc, '-std=c99', '-Wall', '-Wextra', '-pedantic', '-I' + inc, os.path.join(ROOT, 'tests', 'c_abi_caller.c'), '-L' + libdir, '-lg4r',
+                        '-Wl,-rpath,' + libdir, '-L' + cuda_lib, '-Wl,-rpath,' + cuda_lib, '-o', exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert 'c caller ok' in r.stdout and 'step 0: M=2 X=[5,1] Y=[6,2] reset=[0,1]' in r.stdout

@@ -469,7 +469,10 @@ def main():
                      'achieved': tensor['achieved'] if tensor else achieved, 'peak': tensor['peak'] if tensor else peak,
                      'unit': 'TFLOP/s' if tensor else 'GB/s', 'frac': tensor['frac'] if tensor else achieved / peak,
                      'tensor': tensor, 'hbm': {'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak},
-                     'traffic': traffic, 'traffic_source': traffic_src, 'traffic_kernel': traffic_kernel,
+                     # DRAM bytes (ncu dram__bytes_read.sum + dram__bytes_write.sum) on the same footing as algorithmic_bytes_per_launch:
+                     # the committed capture's bytes per mini-batch x the K mini-batches of the timed region
+                     'traffic': (traffic * K) if traffic is not None else None, 'traffic_per_step': traffic,
+                     'traffic_source': traffic_src, 'traffic_kernel': traffic_kernel,
                      'peak_source': peak_src, 'algorithmic_bytes_per_launch': step_bytes * K, 'algorithmic_bytes_per_step': step_bytes,
                      'us_per_step': step_s * 1e6,
                      'note': ('tensor-core path: a chain of 7 dependent split-K products per mini-batch (each ~4 us of tcgen05 issue + ~12 us of launch, '

@@ -102,36 +102,6 @@ def test_world_size_2_gloo():
     assert res == [(0, 'ok'), (1, 'ok')]
 
 
-class _OracleScoringEngine(object):
-    """Stand-in for the device engine in the CPU test below: scores the C++-built (sharded) evaluation schedule with the
-    oracle, returning what g4r_eval_schedule returns (per-cut-off hit / reciprocal-rank sums in double, event count)."""
-
-    def __init__(self, model):
-        self.m, self.items = model, None
-
-    def set_eval_items(self, items=None):
-        self.items = None if items is None else np.asarray(items, dtype=np.int64)
-
-    def eval_schedule(self, sched, cuts, mode):
-        m = self.m
-        e = sched.export()
-        B = sched.batch_size
-        H = [np.zeros((B, L), dtype=np.float32) for L in m.layers]
-        rec = np.zeros(len(cuts)); mrr = np.zeros(len(cuts)); n = 0
-        name = {0: 'standard', 1: 'conservative', 2: 'median', 3: 'tiebreaking'}[mode]
-        for k in range(sched.n_steps):
-            M = int(e['M'][k])
-            X, Y = e['X'][k, :M].astype(np.int64), e['Y'][k, :M].astype(np.int64)
-            ycols = None if self.items is None else np.concatenate([Y, self.items])
-            yhat = m.predict_step(X, H, slots=e['slots'][k, :M].astype(np.int64), zero=(e['F'][k, :M] & 2) != 0, Y=ycols)
-            rk = m.ranks(yhat, Y, name, self.items)
-            with np.errstate(divide='ignore', invalid='ignore'):
-                for j, c in enumerate(cuts):
-                    rec[j] += (rk <= c).sum(); mrr[j] += ((rk <= c) / rk).sum()
-            n += M
-        return rec, mrr, n
-
-
 def _eval_worker(rank, world, port, q):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle')); sys.path.insert(0, os.path.join(ROOT, 'tests'))
     os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
@@ -152,7 +122,9 @@ def _eval_worker(rank, world, port, q):
     m = orc.OracleGRU4Rec(**mk); m.init(d['n_items'])
     gru = GRU4Rec(**mk)
     gru.n_items, gru.itemidmap, gru.error_during_train = d['n_items'], d['itemidmap'], False
-    fake = _OracleScoringEngine(m)
+    import oracle_engine
+    fake = oracle_engine.OracleEngine(gru._make_config(0, 512, training=False, single=True), mk)      # scores with the oracle (tests/oracle_engine.py)
+    fake.m = m
     gru._ensure_engine = lambda lanes: fake
     ti, toff = orc.prepare_eval_data(te, d['itemidmap'])
     n_sess = len(toff) - 1

@@ -1035,11 +1035,17 @@ extern "C" int g4r_schedule_build(const int64_t* data_items, int64_t n_events, c
   std::vector<uint8_t> zero_next(B, 0), fin(B), valid(B);
   for (int b = 0; b < B; b++) { iters[b] = b; start[b] = offs[sess_of(b)]; end[b] = offs[sess_of(b) + 1]; slots[b] = b; }
   {
-    // capacity up front: a full lane set consumes B events per step (the tail of the epoch, where sessions run out, adds a
-    // little).  At RSC15 size the arrays are ~270 MB; growing them by doubling would touch that memory twice.
-    int64_t ev = 0;
-    if (order) { for (int64_t i = 0; i < n_sessions; i++) ev += offs[order[i] + 1] - offs[order[i]]; } else ev = (int64_t)offs[n_sessions] - offs[0];
-    const size_t guess = (size_t)(std::max<int64_t>(ev, 0) / B + 64) * 5 / 4;
+    // capacity up front.  While sessions are left every step runs all B lanes and consumes B (input, target) pairs; once the
+    // supply is exhausted the remaining lanes finish their sessions within max_len steps.  A session of length l holds l - 1
+    // pairs, so steps <= pairs / B + max_len.  At RSC15 size the arrays are ~270 MB: growing them by doubling would touch that
+    // memory twice (page faults dominate the build time).
+    int64_t pairs = 0, max_len = 1;
+    for (int64_t i = 0; i < n_sessions; i++) {
+      const int64_t ss = sess_of(i), len = (int64_t)offs[ss + 1] - offs[ss];
+      if (len > 1) pairs += len - 1;
+      max_len = std::max(max_len, len);
+    }
+    const size_t guess = (size_t)(pairs / B + max_len + 2);
     s->X.reserve(guess * B); s->Y.reserve(guess * B); s->slots.reserve(guess * B); s->F.reserve(guess * B); s->M.reserve(guess);
   }
   int64_t maxiter = B - 1;

@@ -307,7 +307,7 @@ def main():
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
 
     clocks = ClockSampler(local_rank); clocks.start()
     h2d = B * (4 + 4 + 4 + 1) + 12

@@ -278,7 +278,16 @@ def main():
                            replicated=args.replicated)
     eng = _lib.Engine(cfg, device=local_rank)
     if world > 1:
-        eng.init_multi_gpu(dist)
+        try:
+            eng.init_multi_gpu(dist)
+        except NotImplementedError as e:
+            # e.g. BASELINE configs[4] (Rees46 x 8 GPUs): constrained-embedding models have no multi-GPU training path
+            if rank == 0:
+                print(json.dumps({'metric': 'mini-batches/sec', 'n_gpus': world, 'config': bench_config(wl, world), 'unavailable': str(e)}))
+            eng.close()
+            dist.barrier()
+            dist.destroy_process_group()
+            return
     sharded = world > 1 and eng.sharded()
     # parameters: the reference's initialisation (gru4rec.py:254-294); data: synthetic sessions of the workload's shape, disjoint per rank
     import gru4rec as g4

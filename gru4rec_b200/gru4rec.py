@@ -395,6 +395,11 @@ class GRU4Rec:
             print('Warn: learning_rate is not 1.0 while using adadelta. Setting learning_rate to 1.0')
             self.learning_rate = 1.0
         world, rank = self._world()
+        if world > 1 and self.constrained_embedding:
+            # the merged update of a shared table interleaves the input rows Wy[X] with the score columns of every rank; the
+            # library refuses it too (g4r_mg_init) -- say so before any engine is built, identically on every rank
+            raise NotImplementedError('constrained_embedding=True does not train on several GPUs yet: run fit() in one process '
+                                      '(evaluate_gpu / predict_next_batch of the trained model do run under torchrun)')
         if world > 1 and store_type == 'cpu':
             # the host-side sampler draws from one NumPy stream and refills at rank-local step counts: the lock-step ranks
             # would diverge (different numbers of collectives) -- only the device store is defined for multi-GPU training

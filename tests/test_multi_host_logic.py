@@ -156,6 +156,12 @@ def _eval_worker(rank, world, port, q):
         rec, mrr = evaluation.evaluate_gpu(gru, te.copy(), cut_off=[20], batch_size=7)
     rec0, mrr0 = m.evaluate(ti, toff, batch_size=7, cut_off=(20,))
     np.testing.assert_allclose(rec, rec0, rtol=1e-12); np.testing.assert_allclose(mrr, mrr0, rtol=1e-12)
+    # a shared-embedding model has no multi-GPU training path: refused before any engine exists, on every rank
+    shared = GRU4Rec(layers=[10], batch_size=4, n_sample=8, loss='cross-entropy', final_act='softmax', constrained_embedding=True)
+    with contextlib.redirect_stdout(io.StringIO()):
+        with pytest.raises(NotImplementedError, match='several GPUs'):
+            shared.fit(tr.copy())
+    assert shared._engine is None
     # the job-wide epoch line of fit(): sums over ranks
     tot = parallel.allreduce_sum([1.5 + rank, 10.0, 3], dist)
     np.testing.assert_allclose(tot, [1.5 * world + sum(range(world)), 10.0 * world, 3 * world])
